@@ -1,0 +1,293 @@
+#!/usr/bin/env python
+"""bench.py -- atom-steps/s of the LJ argon NVE hot path (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port)
+
+A "step" is one NVE timestep (drift + wrap + skin check + [list rebuild] + LJ force + kick + thermo)
+of the whole synthetic FCC-argon system.  N=1 runs BASELINE configs[2] (4M atoms, rc = 2.5 sigma);
+N>1 runs configs[3] (32M atoms, spatial decomposition) strong-scaled over the ranks.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "atom-steps/sec LJ argon NVE"
+UNIT = "atom-steps/s"
+DT = 0.25          # example/input.pis:8
+SIGMA = 3.405
+RC = 2.5 * SIGMA   # BASELINE configs: rc = 2.5 sigma
+SKIN = 0.3 * SIGMA
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            with open(p) as f:
+                return json.load(f), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int = 0):
+        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self) -> dict:
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in self.rows)]
+        try:
+            pw = max(float(r[2]) for r in self.rows)
+        except ValueError:
+            pw = None
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "power_w_max": pw,
+                "samples": len(self.rows), "reasons": reasons}
+
+
+def argon_oracle(atoms):
+    from oracle.pis_oracle import Oracle
+
+    orc = Oracle(atoms.sim_box.h_colmajor(), masses=atoms.masses)
+    orc.insert(1, 1, 0.238, SIGMA, RC)
+    return orc
+
+
+def time_cpu_path(ncell: int, temperature: float, steps: int, warmup: int, threads: int, seed: int = 12345):
+    """The reference's CPU path (oracle port, OpenMP all-core variant of the LJVOffsetManager loop) on an
+    FCC-argon system of ncell^3*4 atoms: returns (atom-steps/s, cores, seconds per step list)."""
+    from pis_b200.lattice import fcc_argon
+
+    atoms = fcc_argon(ncell, temperature=temperature, seed=seed)
+    orc = argon_oracle(atoms)
+    cores = threads if threads > 0 else orc.max_threads()
+    mode = "omp" if cores > 1 else "serial"
+    x, v = atoms.positions.copy(), atoms.velocities.copy()
+    f = np.zeros_like(x)
+    orc.compute_potential(x, atoms.type_ids, forces=f, mode=mode, threads=cores)
+    for _ in range(warmup):
+        orc.verlet_step_nve(x, v, f, atoms.type_ids, DT, mode=mode, threads=cores)
+    per = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        orc.verlet_step_nve(x, v, f, atoms.type_ids, DT, mode=mode, threads=cores)
+        per.append(time.perf_counter() - t0)
+    tot = sum(per)
+    return atoms.n_atoms * steps / tot, cores, per
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path.  The Rust reference cannot be
+    built here (no rustc), so this is the oracle port, with all host threads, each step a bounded sample
+    (a 256k-atom FCC-argon block: same lattice, density, cutoff and dt as the 4M workload)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ncell = args.ref_ncell
+    t0 = time.perf_counter()
+    value, cores, per = time_cpu_path(ncell, args.temperature, args.steps, args.warmup, args.cpu_threads)
+    n = 4 * ncell ** 3
+    ms = 1e3 * sum(per) / len(per)
+    sample = (f"{n}-atom FCC argon block per step (same a=5.41, rc=2.5sigma, dt=0.25, T0={args.temperature}K as the "
+              f"{4 * args.ncell ** 3}-atom workload), OpenMP all-core variant of the LJVOffsetManager loop, "
+              f"{args.steps} timed steps")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, n_gpus: int) -> dict:
+    ncell = args.ncell if n_gpus == 1 else args.ncell_multi
+    return {"workload": f"synthetic FCC argon {4 * ncell ** 3} atoms ({ncell}^3 cells, a=5.41), LJ rc=2.5sigma "
+                        f"skin=0.3sigma, NVE dt=0.25, T0={args.temperature}K",
+            "n_atoms": 4 * ncell ** 3, "rc": RC, "skin": SKIN, "dt": DT, "T0": args.temperature,
+            "l2_policy": "working set (state + neighbour list, GBs) >> 126 MB L2; no explicit flush",
+            "parallelism": "1 GPU" if n_gpus == 1 else f"spatial decomposition over {n_gpus} GPUs"}
+
+
+def run_single(args):
+    import torch
+
+    from pis_b200 import LennardJones, LJCudaManager, capi
+    from pis_b200.lattice import fcc_argon
+
+    if capi.load().pisb_device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.init()
+    t_wall0 = time.perf_counter()
+    ncell = args.ncell
+    atoms = fcc_argon(ncell, temperature=args.temperature, seed=12345, pinned=True)
+    n = atoms.n_atoms
+    mgr = LJCudaManager(skin=SKIN, device=0)
+    mgr.insert((1, 1), LennardJones(0.238, SIGMA, RC, True))
+    mgr.attach(atoms)
+    mgr.compute()
+    stream = torch.cuda.ExternalStream(mgr.stream_ptr)
+    # ---- warm-up (untimed) ----
+    if args.warmup > 0:
+        mgr.step_nve(DT, args.warmup)
+    mgr.synchronize()
+    st0 = mgr.stats()
+    mgr.set_profiling(True)
+    mgr.timings(reset=True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(0) as clk:
+        torch.cuda.synchronize()
+        ev0.record(stream)
+        th = mgr.step_nve(DT, args.steps)
+        ev1.record(stream)
+        torch.cuda.synchronize()
+    ms_total = ev0.elapsed_time(ev1)
+    tim = mgr.timings()
+    mgr.set_profiling(False)
+    st1 = mgr.stats()
+    ms_per_step = ms_total / args.steps
+    value = n * args.steps / (ms_total * 1e-3)
+    launches = st1["n_launches"] - st0["n_launches"]
+    builds = st1["n_builds"] - st0["n_builds"]
+
+    # ---- roofline of the dominant kernel (LJ force): algorithmic bytes = (48 + 4K) per atom ----
+    peaks, peak_kind = measured_peaks()
+    nn = np.zeros(n, dtype=np.int32)
+    capi.check(mgr._h, capi.load().pisb_neighbours(mgr._h, capi._ptr(nn), None, 0))
+    k_mean = float(nn.mean())
+    f_ms = tim["force"]["ms"] / max(tim["force"]["launches"], 1)
+    bytes_per_launch = (48.0 + 4.0 * k_mean) * n
+    achieved = bytes_per_launch / (f_ms * 1e-3) / 1e9
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "force_traffic.json")
+    if os.path.exists(tp):
+        try:
+            with open(tp) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"kernel": "k_force", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_kind,
+                "algorithmic_bytes_per_atom": 48.0 + 4.0 * k_mean, "mean_neighbours": k_mean,
+                "ms_per_launch": f_ms, "share_of_step": tim["force"]["ms"] / ms_total,
+                "note": "k_force is FP64-pipe bound, not HBM bound (see DESIGN.md); frac is HBM bytes/peak"}
+    kernel_ms = {k: round(v["ms"] / args.steps, 5) for k, v in tim.items() if v["launches"]}
+
+    # ---- end-to-end: the reference-facing trait call with HOST buffers, every step ----
+    e2e_steps = max(3, min(args.e2e_steps, args.steps))
+    mgr.download(atoms)
+    mgr.verlet_step_nve(atoms, DT)  # warm the staging buffers
+    mgr.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        mgr.verlet_step_nve(atoms, DT)
+    mgr.synchronize()
+    e2e_s = time.perf_counter() - t0
+    e2e = {"value": n * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 72 * n, "d2h_bytes_per_step": 72 * n + 32,
+           "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
+           "call": "LJCudaManager.verlet_step_nve(atoms, dt) == pisb_verlet_step_nve_host: pinned host x,v,F up, "
+                   "one step, x,v,F + PE down"}
+
+    # ---- CPU baseline: oracle port on a bounded sample ----
+    cpu = None
+    if not args.no_cpu_baseline:
+        cvalue, cores, per = time_cpu_path(args.ref_ncell, args.temperature, args.cpu_steps, 1, args.cpu_threads)
+        svalue, _, sper = time_cpu_path(args.ref_ncell_serial, args.temperature, 2, 1, 1)
+        cpu = {"value": cvalue, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{4 * args.ref_ncell ** 3}-atom FCC argon block, {args.cpu_steps} steps, OpenMP all-core variant "
+                         f"({sum(per):.1f} s)",
+               "serial_value": svalue, "serial_sample": f"{4 * args.ref_ncell_serial ** 3} atoms, 2 steps, 1 thread "
+                                                        f"(what the reference actually executes)"}
+
+    h = th["pe"] + th["ke"]
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": workload_config(args, 1), "clocks": clk.summary(), "e2e": e2e,
+        "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+        "kernel_ms_per_step": kernel_ms, "list_builds_in_timed_region": int(builds),
+        "energy_drift_rel": float(np.abs(h - h[0]).max() / abs(h[0])),
+        "stats": st1, "wall_s": time.perf_counter() - t_wall0,
+    }
+    print(json.dumps(line), flush=True)
+    mgr.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ncell", type=int, default=100, help="FCC cells per edge at N=1 (100 -> 4M atoms)")
+    ap.add_argument("--ncell-multi", type=int, default=200, help="FCC cells per edge at N>1 (200 -> 32M atoms)")
+    ap.add_argument("--temperature", type=float, default=43.0, help="initial temperature (K); 43 K exercises rebuilds")
+    ap.add_argument("--ref-ncell", type=int, default=40, help="CPU sample size (40 -> 256k atoms)")
+    ap.add_argument("--ref-ncell-serial", type=int, default=20)
+    ap.add_argument("--cpu-steps", type=int, default=5)
+    ap.add_argument("--cpu-threads", type=int, default=0)
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1 or args.gpus > 1:
+        from pis_b200 import multigpu_bench
+
+        return multigpu_bench.run(args)
+    return run_single(args)
+
+
+if __name__ == "__main__":
+    main()

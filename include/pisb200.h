@@ -1,0 +1,169 @@
+/*
+ * pisb200.h -- C ABI of libpisb200.so: the B200-native (sm_100a) implementation of the PIS
+ * per-timestep MD hot path (cell binning -> Verlet neighbour list -> Lennard-Jones
+ * force/energy/virial -> velocity-Verlet NVE), f64, device-resident.
+ *
+ * The reference (vivekadishankara/pis, Rust) has no FFI; its hot path sits behind the Rust trait
+ * `PotentialManager` (src/potentials/potential.rs:12-136).  Each entry point below names the
+ * reference interface it replaces (paths relative to the reference repo).  INTEGRATION.md shows
+ * the Rust `extern "C"` block + `impl PotentialManager for LJCudaManager` a maintainer would add.
+ *
+ * Conventions: plain pointers and sizes only; every function returns a PISB_* code (0 = ok);
+ * pisb_last_error(h) gives the message for the last failure on that handle (h may be NULL for
+ * pisb_create failures).  Host arrays are xyz-interleaved 3N doubles in ORIGINAL atom order,
+ * exactly nalgebra's Matrix3xX<f64> storage (src/atoms/new.rs:9-17); types are 1-based.
+ * A handle is not re-entrant; independent handles may be used from different threads.
+ * There is NO CPU fallback: without a CUDA device every call fails with PISB_ERR_NO_DEVICE.
+ */
+#ifndef PISB200_H
+#define PISB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define PISB_API __attribute__((visibility("default")))
+#else
+#define PISB_API
+#endif
+
+typedef struct pisb_handle pisb_t;
+
+enum {
+    PISB_OK = 0,
+    PISB_ERR_INVALID = 1,   /* bad argument / degenerate input (box smaller than 2 cutoffs, ...) */
+    PISB_ERR_CUDA = 2,      /* a CUDA runtime call failed; see pisb_last_error */
+    PISB_ERR_NO_DEVICE = 3, /* no usable CUDA device: the product path has no CPU fallback */
+    PISB_ERR_CAPACITY = 4,  /* neighbour-list / cell capacity exceeded and regrow failed */
+    PISB_ERR_STATE = 5,     /* call order violated (e.g. step before upload / set_box) */
+    PISB_ERR_COMM = 6       /* multi-GPU communicator failure */
+};
+
+/* Per-step observables.  Replaces what Simulation::output computes on the host every step
+ * (src/simulation.rs:79-82): step_potential, Atoms::kinetic_energy (src/atoms/properties.rs:17-24)
+ * and the trace of Atoms::virial_tensor (properties.rs:49-51,62).  virial_pair is the periodic
+ * pair virial sum_{i<j} r_ij . f_ij (north_star: "pair force/energy/virial"), which the
+ * reference does not compute. */
+typedef struct {
+    double pe;          /* total shifted LJ potential energy (return value of verlet_step_nve) */
+    double ke;          /* sum 0.5 m v^2 */
+    double virial_ref;  /* tr(X F^T) with wrapped absolute positions, as the reference's pressure uses */
+    double virial_pair; /* sum over pairs r_ij . f_ij */
+} pisb_thermo;
+
+typedef struct {
+    int64_t n_atoms;        /* owned atoms on this handle */
+    int64_t n_ghost;        /* ghost atoms (multi-GPU), 0 on a single GPU */
+    int64_t n_cells[3];     /* cell grid */
+    int64_t list_capacity;  /* neighbour slots per atom (K_max) */
+    int64_t max_neighbours; /* largest list length at the last build */
+    int64_t total_neighbours; /* sum of list lengths at the last build */
+    int64_t n_builds;       /* neighbour-list builds so far */
+    int64_t n_steps;        /* NVE steps so far */
+    int64_t n_launches;     /* kernels launched by this handle so far */
+    int64_t device_bytes;   /* device memory held */
+} pisb_stats_t;
+
+/* kernel classes for pisb_timings */
+enum {
+    PISB_K_INTEGRATE = 0, /* fused velocity-Verlet kick/drift + wrap + thermo + displacement check */
+    PISB_K_BIN = 1,       /* cell index + histogram */
+    PISB_K_SORT = 2,      /* scan + scatter + in-cell order + permute */
+    PISB_K_BUILD = 3,     /* neighbour-list build */
+    PISB_K_FORCE = 4,     /* LJ force/energy/virial */
+    PISB_K_REDUCE = 5,    /* thermo finalisation */
+    PISB_K_HALO = 6,      /* halo pack/unpack + exchange (multi-GPU) */
+    PISB_K_COPY = 7,      /* host<->device staging conversion */
+    PISB_K_COUNT = 8
+};
+
+PISB_API const char *pisb_version(void);
+PISB_API int pisb_device_count(void);
+
+/* Create a device-backed LJ manager.
+ * Replaces: LJVOffsetManager::new + insert((i,j), LennardJones::new(eps, sigma, rcut, shift))
+ *   (src/potentials/lennard_jones.rs:14-30,182-184; src/system.rs:134-164;
+ *    src/readers/input_file/commands.rs:171,263-292) and Atoms.masses (src/atoms/new.rs:12).
+ * eps/sigma/rcut/present are dense n_types x n_types, entry for 1-based pair (i,j) at
+ * [(i-1)*n_types + (j-1)], stored AS GIVEN: lookups read (min,max) like the reference's sorted
+ * HashMap key (src/potentials/potential.rs:181-192), so an entry given as (2,1) is never found.
+ * present[k] == 0 => no potential for that pair: the pair is skipped (reference prints a line and
+ * skips, lennard_jones.rs:216-222).  shift: energy shift at rcut (always 1 in the reference).
+ * skin: Verlet skin distance (NEW; the reference rebuilds cells every call and has no skin).
+ *   skin == 0 reproduces the reference's "rebuild every call" behaviour. */
+PISB_API int pisb_create(int device, int n_types, const double *mass, const double *eps,
+                         const double *sigma, const double *rcut, const unsigned char *present,
+                         int shift, double skin, pisb_t **out);
+PISB_API int pisb_destroy(pisb_t *h);
+PISB_API const char *pisb_last_error(pisb_t *h);
+
+/* Replaces: SimulationBox{h, h_inv, pbc} (src/simulation_box.rs:5-15).  h9/hinv9 column-major.
+ * h_inv is an INPUT (the reference caches nalgebra's try_inverse; the device never recomputes it). */
+PISB_API int pisb_set_box(pisb_t *h, const double *h9, const double *hinv9, const int *pbc3);
+
+/* Replaces: the Atoms the trait methods borrow (`&mut Atoms`, src/atoms/new.rs:9-17).
+ * pos/vel/force are 3N xyz-interleaved doubles in original order; vel/force may be NULL (= zeros);
+ * types 1-based.  Invalidates the neighbour list unless the atom count, box and list are still
+ * valid for the new positions (checked on the device against the positions at the last build). */
+PISB_API int pisb_upload(pisb_t *h, int64_t n, const double *pos, const double *vel,
+                         const double *force, const int32_t *types);
+
+/* Replaces: PotentialManager::compute_potential(&self, &mut Atoms) -> f64
+ *   (src/potentials/potential.rs:13; live impl LJVOffsetManager, lennard_jones.rs:186-244).
+ * accumulate != 0: forces are ADDED to the device force buffer (the reference semantics: caller
+ * zeroes, potential.rs:24); accumulate == 0: forces are overwritten.  Positions are NOT wrapped
+ * (the reference's step-0 call runs on the input positions, src/simulation.rs:28). */
+PISB_API int pisb_compute(pisb_t *h, int accumulate, double *pe);
+
+/* Replaces: PotentialManager::verlet_step_nve(&self, &mut Atoms, dt) -> f64, nsteps times
+ *   (src/potentials/potential.rs:15-33), fused with the per-step observables of
+ *   Simulation::output (src/simulation.rs:79-82).  State stays on the device; out (may be NULL)
+ *   receives nsteps records; out[s].pe is the value verlet_step_nve returns at step s. */
+PISB_API int pisb_step_nve(pisb_t *h, double dt, int64_t nsteps, pisb_thermo *out);
+
+/* Copy state back in ORIGINAL atom order (any pointer may be NULL).  Replaces reading
+ * atoms.positions / velocities / forces on the host (e.g. DumpTraj::write_atoms_info,
+ * src/writers/dump_traj.rs:52-66). */
+PISB_API int pisb_download(pisb_t *h, double *pos, double *vel, double *force);
+
+/* Observables of the CURRENT device state (KE, virial_ref from current x, v, F; pe/virial_pair of
+ * the last force evaluation).  Replaces Atoms::kinetic_energy / virial_tensor().trace(). */
+PISB_API int pisb_thermo_now(pisb_t *h, pisb_thermo *out);
+
+/* Strict drop-in for ONE trait call with HOST buffers: upload pos/vel/force (pinned staging),
+ * one verlet_step_nve, download pos/vel/force, return PE.  This is what an unmodified
+ * Simulation::run (src/simulation.rs:31-37,52) drives through the Rust shim. */
+PISB_API int pisb_verlet_step_nve_host(pisb_t *h, int64_t n, double *pos, double *vel,
+                                       double *force, const int32_t *types, double dt, double *pe);
+
+/* Test hook: the current Verlet list in ORIGINAL atom ids.  nnbr[n]; nbr[n * cap_per_atom]
+ * row-major, rows unsorted.  Semantic source: LJVPBuildListManager::build_neighbour_list
+ * (src/potentials/lennard_jones.rs:345-415) with rcut := rcut + skin. */
+PISB_API int pisb_neighbours(pisb_t *h, int32_t *nnbr, int32_t *nbr, int64_t cap_per_atom);
+/* Force a list rebuild at the next force evaluation (test hook). */
+PISB_API int pisb_invalidate_list(pisb_t *h);
+
+PISB_API int pisb_stats(pisb_t *h, pisb_stats_t *out);
+
+/* Per-kernel-class device timing (CUDA events on the handle's stream).  enable: 0/1.
+ * pisb_timings drains recorded events: ms[PISB_K_COUNT], launches[PISB_K_COUNT] accumulated since
+ * the last pisb_timings_reset. */
+PISB_API int pisb_set_profiling(pisb_t *h, int enable);
+PISB_API int pisb_timings(pisb_t *h, double *ms, int64_t *launches);
+PISB_API int pisb_timings_reset(pisb_t *h);
+
+/* The CUDA stream (cudaStream_t) all work of this handle is launched on, and a full sync. */
+PISB_API void *pisb_stream(pisb_t *h);
+PISB_API int pisb_synchronize(pisb_t *h);
+
+/* Tuning knobs (0 = keep default): list_capacity = neighbour slots per atom (auto-grown on
+ * overflow), force_variant = kernel variant selector for A/B measurements. */
+PISB_API int pisb_set_option(pisb_t *h, const char *name, double value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PISB200_H */

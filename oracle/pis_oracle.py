@@ -1,0 +1,229 @@
+"""ctypes loader for oracle/libpis_oracle.so -- the CPU ORACLE (TEST INFRASTRUCTURE ONLY).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this module.  Nothing under pis_b200/ imports it.  PARITY UNPINNED by the reference (no rustc here,
+reference tests pin no physics): see the header of pis_oracle.c.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(_HERE, "pis_oracle.c")
+LIB = os.path.join(_HERE, "libpis_oracle.so")
+
+
+class Box(C.Structure):
+    _fields_ = [("h", C.c_double * 9), ("hinv", C.c_double * 9), ("pbc", C.c_int * 3)]
+
+
+class Table(C.Structure):
+    _fields_ = [("n_types", C.c_int), ("eps", C.c_void_p), ("sigma", C.c_void_p), ("rcut", C.c_void_p),
+                ("present", C.c_void_p), ("shift", C.c_int)]
+
+
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(SRC):
+        subprocess.run(["gcc", "-O2", "-std=c11", "-ffp-contract=off", "-fno-fast-math", "-fopenmp", "-fPIC",
+                        "-shared", "-fvisibility=hidden", "-o", LIB, SRC, "-lm"], check=True, cwd=_HERE)
+    return LIB
+
+
+def load():
+    global _lib
+    if _lib is None:
+        build()
+        lib = C.CDLL(LIB)
+        vp, d, i64 = C.c_void_p, C.c_double, C.c_int64
+        bp, tp = C.POINTER(Box), C.POINTER(Table)
+        sig = {
+            "orc_box_new": (C.c_int, [vp, vp, bp]),
+            "orc_box_from_lammps": (C.c_int, [d] * 9 + [bp]),
+            "orc_box_volume": (d, [bp]),
+            "orc_min_image": (None, [bp, vp]),
+            "orc_wrap_pos": (None, [bp, vp]),
+            "orc_max_rcut": (d, [tp]),
+            "orc_divide_into_cells": (None, [bp, d, vp]),
+            "orc_rcut_cells": (None, [bp, vp, i64, C.c_uint64, C.c_uint64, C.c_uint64, vp, vp, vp]),
+            "orc_forward_offsets": (vp, []),
+            "orc_lj_pair": (None, [d, d, d, C.c_int, vp, vp, vp]),
+            "orc_set_quiet": (None, [C.c_int]),
+            "orc_compute_potential": (d, [bp, tp, i64, vp, vp, vp]),
+            "orc_compute_potential_omp": (d, [bp, tp, i64, vp, vp, vp, C.c_int]),
+            "orc_compute_potential_n2": (d, [bp, tp, i64, vp, vp, vp]),
+            "orc_build_neighbour_list": (i64, [bp, tp, i64, vp, vp, d, vp, vp, i64]),
+            "orc_compute_potential_list": (d, [bp, tp, i64, vp, vp, vp, vp, vp]),
+            "orc_kinetic_energy": (d, [i64, vp, vp, vp]),
+            "orc_temperature": (d, [i64, d]),
+            "orc_virial_trace": (d, [i64, vp, vp]),
+            "orc_pressure": (d, [bp, i64, vp, vp, d]),
+            "orc_verlet_step_nve": (d, [bp, tp, i64, vp, vp, vp, vp, vp, d, C.c_int, C.c_int]),
+            "orc_run_nve": (None, [bp, tp, i64, vp, vp, vp, vp, vp, d, i64, C.c_int, C.c_int, vp]),
+            "orc_rcut_threshold": (d, [d]),
+            "orc_max_threads": (C.c_int, []),
+        }
+        for name, (res, args) in sig.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Oracle:
+    """Convenience wrapper: one box + one pair table + masses."""
+
+    def __init__(self, h_colmajor, pbc=(1, 1, 1), n_types=1, masses=(39.948,), shift=True):
+        self.lib = load()
+        self.box = Box()
+        h = np.ascontiguousarray(h_colmajor, dtype=np.float64).reshape(9)
+        pb = np.array([int(p) for p in pbc], dtype=np.int32)
+        if self.lib.orc_box_new(_p(h), _p(pb), C.byref(self.box)) != 0:
+            raise ValueError("Box matrix should be invertible")
+        self.n_types = n_types
+        self.eps = np.zeros((n_types, n_types))
+        self.sigma = np.zeros((n_types, n_types))
+        self.rcut = np.zeros((n_types, n_types))
+        self.present = np.zeros((n_types, n_types), dtype=np.uint8)
+        self.masses = np.ascontiguousarray(masses, dtype=np.float64)
+        self.table = Table(n_types, _p(self.eps).value, _p(self.sigma).value, _p(self.rcut).value,
+                           _p(self.present).value, int(shift))
+        self.lib.orc_set_quiet(1)
+
+    @classmethod
+    def cubic(cls, L, **kw):
+        return cls([L, 0, 0, 0, L, 0, 0, 0, L], **kw)
+
+    def insert(self, i, j, eps, sigma, rcut):
+        self.eps[i - 1, j - 1], self.sigma[i - 1, j - 1], self.rcut[i - 1, j - 1] = eps, sigma, rcut
+        self.present[i - 1, j - 1] = 1
+
+    @property
+    def h(self):
+        return np.array(self.box.h[:]).reshape(3, 3).T
+
+    @property
+    def hinv(self):
+        return np.array(self.box.hinv[:]).reshape(3, 3).T
+
+    def max_rcut(self):
+        return self.lib.orc_max_rcut(C.byref(self.table))
+
+    def divide_into_cells(self, rcut):
+        n = np.zeros(3, dtype=np.uint64)
+        self.lib.orc_divide_into_cells(C.byref(self.box), float(rcut), _p(n))
+        return tuple(int(x) for x in n)
+
+    def rcut_cells(self, pos, nx, ny, nz):
+        pos = np.ascontiguousarray(pos, dtype=np.float64)
+        n = pos.shape[0]
+        cell_of = np.zeros(n, dtype=np.int64)
+        start = np.zeros(nx * ny * nz + 1, dtype=np.int64)
+        atoms = np.zeros(n, dtype=np.int64)
+        self.lib.orc_rcut_cells(C.byref(self.box), _p(pos), n, nx, ny, nz, _p(cell_of), _p(start), _p(atoms))
+        return cell_of, start, atoms
+
+    def min_image(self, d):
+        d = np.array(d, dtype=np.float64)
+        self.lib.orc_min_image(C.byref(self.box), _p(d))
+        return d
+
+    def wrap(self, r):
+        r = np.array(r, dtype=np.float64)
+        self.lib.orc_wrap_pos(C.byref(self.box), _p(r))
+        return r
+
+    def lj_pair(self, eps, sigma, rcut, rij, shift=True):
+        rij = np.ascontiguousarray(rij, dtype=np.float64)
+        u = C.c_double()
+        f = np.zeros(3)
+        self.lib.orc_lj_pair(eps, sigma, rcut, int(shift), _p(rij), C.byref(u), _p(f))
+        return u.value, f
+
+    def compute_potential(self, pos, types, forces=None, mode="serial", threads=0):
+        pos = np.ascontiguousarray(pos, dtype=np.float64)
+        types = np.ascontiguousarray(types, dtype=np.int32)
+        n = pos.shape[0]
+        f = np.zeros((n, 3)) if forces is None else forces
+        b, t = C.byref(self.box), C.byref(self.table)
+        if mode == "serial":
+            pe = self.lib.orc_compute_potential(b, t, n, _p(pos), _p(types), _p(f))
+        elif mode == "omp":
+            pe = self.lib.orc_compute_potential_omp(b, t, n, _p(pos), _p(types), _p(f), threads)
+        elif mode == "n2":
+            pe = self.lib.orc_compute_potential_n2(b, t, n, _p(pos), _p(types), _p(f))
+        else:
+            raise ValueError(mode)
+        return pe, f
+
+    def build_neighbour_list(self, pos, types, extra=0.0):
+        pos = np.ascontiguousarray(pos, dtype=np.float64)
+        types = np.ascontiguousarray(types, dtype=np.int32)
+        n = pos.shape[0]
+        start = np.zeros(n + 1, dtype=np.int64)
+        cap = max(64 * n, 1024)
+        while True:
+            nbr = np.zeros(cap, dtype=np.int32)
+            tot = self.lib.orc_build_neighbour_list(C.byref(self.box), C.byref(self.table), n, _p(pos), _p(types),
+                                                    float(extra), _p(start), _p(nbr), cap)
+            if tot >= 0:
+                return start, nbr[:tot]
+            cap *= 4
+
+    def compute_potential_list(self, pos, types, start, nbr):
+        pos = np.ascontiguousarray(pos, dtype=np.float64)
+        types = np.ascontiguousarray(types, dtype=np.int32)
+        f = np.zeros_like(pos)
+        pe = self.lib.orc_compute_potential_list(C.byref(self.box), C.byref(self.table), pos.shape[0], _p(pos),
+                                                 _p(types), _p(start), _p(nbr), _p(f))
+        return pe, f
+
+    def kinetic_energy(self, vel, types):
+        vel = np.ascontiguousarray(vel, dtype=np.float64)
+        types = np.ascontiguousarray(types, dtype=np.int32)
+        return self.lib.orc_kinetic_energy(vel.shape[0], _p(vel), _p(types), _p(self.masses))
+
+    def temperature(self, n, ke):
+        return self.lib.orc_temperature(n, ke)
+
+    def virial_trace(self, pos, forces):
+        pos = np.ascontiguousarray(pos, dtype=np.float64)
+        forces = np.ascontiguousarray(forces, dtype=np.float64)
+        return self.lib.orc_virial_trace(pos.shape[0], _p(pos), _p(forces))
+
+    def pressure(self, pos, forces, ke):
+        return self.lib.orc_pressure(C.byref(self.box), pos.shape[0], _p(pos), _p(forces), ke)
+
+    def verlet_step_nve(self, pos, vel, forces, types, dt, mode="serial", threads=0):
+        """In place on pos/vel/forces ((N,3) float64 C-contiguous). Returns PE(t+dt)."""
+        for a in (pos, vel, forces):
+            assert a.dtype == np.float64 and a.flags.c_contiguous
+        types = np.ascontiguousarray(types, dtype=np.int32)
+        return self.lib.orc_verlet_step_nve(C.byref(self.box), C.byref(self.table), pos.shape[0], _p(pos), _p(vel),
+                                            _p(forces), _p(types), _p(self.masses), float(dt),
+                                            0 if mode == "serial" else 1, threads)
+
+    def run_nve(self, pos, vel, forces, types, dt, steps, mode="serial", threads=0):
+        """Simulation::run NVE arm. Returns thermo[(steps+1), 5] = PE, KE, H, T, P (row 0: step-0 PE)."""
+        types = np.ascontiguousarray(types, dtype=np.int32)
+        thermo = np.zeros((steps + 1, 5))
+        self.lib.orc_run_nve(C.byref(self.box), C.byref(self.table), pos.shape[0], _p(pos), _p(vel), _p(forces),
+                             _p(types), _p(self.masses), float(dt), steps, 0 if mode == "serial" else 1, threads,
+                             _p(thermo))
+        return thermo
+
+    def rcut_threshold(self, rc):
+        return self.lib.orc_rcut_threshold(float(rc))
+
+    def max_threads(self):
+        return self.lib.orc_max_threads()

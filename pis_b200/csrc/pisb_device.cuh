@@ -1,0 +1,163 @@
+// pisb_device.cuh -- device-side building blocks shared by the sm_100a kernels.
+//
+// Arithmetic in the "exact" paths restates the reference operation-for-operation with
+// round-to-nearest intrinsics (__dmul_rn/__dadd_rn are never contracted into FMA), so that
+// per-pair terms are bit-identical to the Rust code they replace:
+//   minimum image  : src/simulation_box.rs:17-27   (s = h_inv*d; s -= round(s); d = h*s)
+//   wrap           : src/simulation_box.rs:29-42   (s = h_inv*r; s -= floor(s); r = h*s)
+//   |rij| > rcut   : src/potentials/lennard_jones.rs:224,404, as r2 > T with
+//                    T = max{t : sqrt(t) <= rcut} (sqrt-free, exactly equivalent)
+//   LJ pair        : src/potentials/lennard_jones.rs:33-55
+// nalgebra's Matrix3*Vector3 is a column-axpy gemv: y_i = ((a_i0*x0) + a_i1*x1) + a_i2*x2.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pisb {
+
+struct BoxDev {
+    double h[9];     // column-major
+    double hinv[9];  // column-major, supplied by the host (never recomputed here)
+    int pbc[3];
+    int ortho;       // all off-diagonal elements of h and hinv are zero
+};
+
+// Per type-pair constants, precomputed on the host with the reference's own expression order.
+struct PairDev {
+    double c4;      // 4.0 * epsilon
+    double c24;     // 24.0 * epsilon
+    double sig2;    // sigma * sigma            (sigma.powi(2))
+    double t_rc;    // max{t : sqrt(t) <= rcut}
+    double t_list;  // max{t : sqrt(t) <= rcut + skin}
+    double ucut;    // 4 eps ((s/rc)^12 - (s/rc)^6) if shift else 0
+    int present;
+    int pad;
+};
+
+// Read-only 32-byte gather of one atom record (two LDG.E.128.CONSTANT).
+__device__ __forceinline__ double4 ldg_d4(const double4 *p) {
+    const double2 *q = reinterpret_cast<const double2 *>(p);
+    const double2 a = __ldg(q), b = __ldg(q + 1);
+    return make_double4(a.x, a.y, b.x, b.y);
+}
+
+__device__ __forceinline__ int type_of(double w) { return (int)__double_as_longlong(w); }
+__device__ __forceinline__ double type_as_double(int t) { return __longlong_as_double((long long)t); }
+
+// y = M * x in nalgebra's evaluation order (general 3x3), or the diagonal shortcut when the box
+// is orthorhombic (adding the exact zeros of the off-diagonal products cannot change a value).
+template <bool ORTHO>
+__device__ __forceinline__ void matvec(const double *__restrict__ m, double x0, double x1, double x2,
+                                       double &y0, double &y1, double &y2) {
+    if (ORTHO) {
+        y0 = __dmul_rn(m[0], x0);
+        y1 = __dmul_rn(m[4], x1);
+        y2 = __dmul_rn(m[8], x2);
+    } else {
+        y0 = __dmul_rn(m[0], x0);
+        y1 = __dmul_rn(m[1], x0);
+        y2 = __dmul_rn(m[2], x0);
+        y0 = __dadd_rn(__dmul_rn(m[3], x1), y0);
+        y1 = __dadd_rn(__dmul_rn(m[4], x1), y1);
+        y2 = __dadd_rn(__dmul_rn(m[5], x1), y2);
+        y0 = __dadd_rn(__dmul_rn(m[6], x2), y0);
+        y1 = __dadd_rn(__dmul_rn(m[7], x2), y1);
+        y2 = __dadd_rn(__dmul_rn(m[8], x2), y2);
+    }
+}
+
+// apply_boundary_conditions_dis.  round() is half-away-from-zero like Rust's f64::round.
+template <bool ORTHO>
+__device__ __forceinline__ void min_image(const BoxDev &b, double &dx, double &dy, double &dz) {
+    double sx, sy, sz;
+    matvec<ORTHO>(b.hinv, dx, dy, dz, sx, sy, sz);
+    if (b.pbc[0]) sx = __dsub_rn(sx, round(sx));
+    if (b.pbc[1]) sy = __dsub_rn(sy, round(sy));
+    if (b.pbc[2]) sz = __dsub_rn(sz, round(sz));
+    matvec<ORTHO>(b.h, sx, sy, sz, dx, dy, dz);
+}
+
+// apply_boundary_conditions_pos
+template <bool ORTHO>
+__device__ __forceinline__ void wrap_pos(const BoxDev &b, double &x, double &y, double &z) {
+    double sx, sy, sz;
+    matvec<ORTHO>(b.hinv, x, y, z, sx, sy, sz);
+    if (b.pbc[0]) sx = __dsub_rn(sx, floor(sx));
+    if (b.pbc[1]) sy = __dsub_rn(sy, floor(sy));
+    if (b.pbc[2]) sz = __dsub_rn(sz, floor(sz));
+    matvec<ORTHO>(b.h, sx, sy, sz, x, y, z);
+}
+
+// Vector3::norm_squared: (x*x + y*y) + z*z
+__device__ __forceinline__ double norm2(double x, double y, double z) {
+    return __dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z));
+}
+
+// LennardJones::compute_potential on an in-range pair: returns u (shifted) and the scalar fs with
+// force-on-j = fs * rij.
+__device__ __forceinline__ void lj_pair(const PairDev &p, double r2, double &u, double &fs) {
+    double inv = __ddiv_rn(1.0, r2);
+    double s2 = __dmul_rn(p.sig2, inv);
+    double s6 = __dmul_rn(__dmul_rn(s2, s2), s2);
+    double s12 = __dmul_rn(s6, s6);
+    u = __dsub_rn(__dmul_rn(p.c4, __dsub_rn(s12, s6)), p.ucut);
+    fs = __dmul_rn(__dmul_rn(p.c24, __dsub_rn(__dmul_rn(2.0, s12), s6)), inv);
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Deterministic block reduction of NQ doubles per thread into partials[q * nblocks + blockIdx.x];
+// the last block to finish (ticket) sums the partials in fixed order and calls fin(q, sum).
+// All threads of the block must call this.  smem: NQ * 32 doubles.
+template <int NQ, int NT, typename Fin>
+__device__ __forceinline__ void block_reduce_finalize(double (&v)[NQ], double *__restrict__ partials,
+                                                      unsigned int *__restrict__ ticket, Fin fin) {
+    __shared__ double s_red[NQ][NT / 32];
+    __shared__ bool s_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        double w = warp_sum(v[q]);
+        if (lane == 0) s_red[q][warp] = w;
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            double w = lane < NT / 32 ? s_red[q][lane] : 0.0;
+            w = warp_sum(w);
+            if (lane == 0) partials[(size_t)q * gridDim.x + blockIdx.x] = w;
+        }
+    }
+    if (threadIdx.x == 0) {
+        __threadfence();
+        unsigned int t = atomicAdd(ticket, 1u);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // fixed-order sum over blocks: thread t takes blocks t, t+NT, ... then the block tree
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        double acc = 0.0;
+        for (unsigned int b = threadIdx.x; b < gridDim.x; b += NT)
+            acc += __ldcg(&partials[(size_t)q * gridDim.x + b]);
+        double w = warp_sum(acc);
+        __syncthreads();
+        if (lane == 0) s_red[q][warp] = w;
+        __syncthreads();
+        if (warp == 0) {
+            double z = lane < NT / 32 ? s_red[q][lane] : 0.0;
+            z = warp_sum(z);
+            if (lane == 0) fin(q, z);
+        }
+    }
+    if (threadIdx.x == 0) *ticket = 0u;
+}
+
+}  // namespace pisb

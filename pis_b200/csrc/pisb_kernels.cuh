@@ -1,0 +1,608 @@
+// pisb_kernels.cuh -- the sm_100a kernels of the hot path (single translation unit with pisb_sim.cu).
+//
+// Device data layout (all arrays in CELL-SORTED slot order; `id[slot]` = original atom index):
+//   xt  : double4 {x, y, z, type-bits}   one 32-byte sector per atom: a neighbour gather costs
+//                                        exactly one sector and carries the type for the pair table
+//   v*, f*, g* : SoA doubles             streamed, never gathered (f = force at current x,
+//                                        g = force at previous x, swapped by the host every step)
+//   xb* : SoA doubles                    positions at the last list build (skin trigger)
+//   nbr : int32 [K_cap][n_pad]           TRANSPOSED full Verlet list: row k holds the k-th neighbour
+//                                        of every atom, so a warp reads 128 contiguous bytes
+//   cell_start : int32 [n_cells+1]       CSR of the cell-sorted order (x fastest, like cell_index)
+#pragma once
+#include "pisb_device.cuh"
+
+namespace pisb {
+
+constexpr int TPB = 256;        // streaming kernels
+constexpr int TPB_FORCE = 128;  // force / build kernels
+
+// flags[] (device ints)
+enum { FLAG_REBUILD = 0, FLAG_MAXNBR = 1, FLAG_NBUILDS = 2, FLAG_BADTYPE = 3, FLAG_COUNT = 8 };
+
+struct Grid {
+    int n[3];      // cells per dimension
+    int lo[3];     // stencil offsets lo..hi per dim (dedupes n<3)
+    int hi[3];
+    int ncell;
+};
+
+// ------------------------------------------------------------------------------------------------
+// Host AoS <-> device layout.  Replaces nothing in the reference: it is the boundary copy.
+// `order_by_id` : slot_of_id (keep the current cell-sorted order) or nullptr (identity order).
+// ------------------------------------------------------------------------------------------------
+struct LoadArgs {
+    int n;
+    const double *pos, *vel, *frc;  // AoS staging (device), vel/frc may be null
+    const int *types;               // 1-based types in ORIGINAL order (device copy kept by the handle)
+    const int *slot_of_id;          // may be null => identity
+    double4 *xt;
+    double *vx, *vy, *vz, *fx, *fy, *fz;
+    int *id;
+    int n_types;
+    int *flags;
+};
+
+__global__ void __launch_bounds__(TPB) k_load_aos(LoadArgs a) {
+    int o = blockIdx.x * blockDim.x + threadIdx.x;  // original index
+    if (o >= a.n) return;
+    int s = a.slot_of_id ? a.slot_of_id[o] : o;
+    double4 x;
+    x.x = a.pos[3 * (size_t)o];
+    x.y = a.pos[3 * (size_t)o + 1];
+    x.z = a.pos[3 * (size_t)o + 2];
+    int t = a.types[o];
+    if (t < 1 || t > a.n_types) {
+        a.flags[FLAG_BADTYPE] = o + 1;
+        t = 1;
+    }
+    x.w = type_as_double(t);
+    a.xt[s] = x;
+    a.vx[s] = a.vel ? a.vel[3 * (size_t)o] : 0.0;
+    a.vy[s] = a.vel ? a.vel[3 * (size_t)o + 1] : 0.0;
+    a.vz[s] = a.vel ? a.vel[3 * (size_t)o + 2] : 0.0;
+    a.fx[s] = a.frc ? a.frc[3 * (size_t)o] : 0.0;
+    a.fy[s] = a.frc ? a.frc[3 * (size_t)o + 1] : 0.0;
+    a.fz[s] = a.frc ? a.frc[3 * (size_t)o + 2] : 0.0;
+    a.id[s] = o;
+}
+
+struct StoreArgs {
+    int n;
+    const double4 *xt;
+    const double *vx, *vy, *vz, *fx, *fy, *fz;
+    const int *id;
+    double *pos, *vel, *frc;  // AoS staging (device), any may be null
+};
+
+__global__ void __launch_bounds__(TPB) k_store_aos(StoreArgs a) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= a.n) return;
+    size_t o = (size_t)a.id[s];
+    if (a.pos) {
+        double4 x = a.xt[s];
+        a.pos[3 * o] = x.x;
+        a.pos[3 * o + 1] = x.y;
+        a.pos[3 * o + 2] = x.z;
+    }
+    if (a.vel) {
+        a.vel[3 * o] = a.vx[s];
+        a.vel[3 * o + 1] = a.vy[s];
+        a.vel[3 * o + 2] = a.vz[s];
+    }
+    if (a.frc) {
+        a.frc[3 * o] = a.fx[s];
+        a.frc[3 * o + 1] = a.fy[s];
+        a.frc[3 * o + 2] = a.fz[s];
+    }
+}
+
+// Skin trigger on freshly uploaded positions: any |minimg(x - x_build)|^2 > (skin/2)^2 => rebuild.
+template <bool ORTHO>
+__global__ void __launch_bounds__(TPB) k_check_displacement(int n, const double4 *__restrict__ xt,
+                                                            const double *__restrict__ xbx,
+                                                            const double *__restrict__ xby,
+                                                            const double *__restrict__ xbz, BoxDev box,
+                                                            double half_skin2, int *flags) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double4 x = xt[i];
+    double dx = x.x - xbx[i], dy = x.y - xby[i], dz = x.z - xbz[i];
+    min_image<ORTHO>(box, dx, dy, dz);
+    double r2 = norm2(dx, dy, dz);
+    if (!(r2 <= half_skin2)) flags[FLAG_REBUILD] = 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused velocity-Verlet kernel.
+//   KICK : second half of step k     v += ((a_t + a_tdt) * 0.5) * dt           potential.rs:28-30
+//          + per-step observables    KE (properties.rs:17-24), tr(X F^T) (properties.rs:49-51)
+//   DRIFT: first half of step k+1    x += (v*dt) + ((a*0.5) * dt^2)            potential.rs:16-18
+//          + wrap (potential.rs:20-22 -> simulation_box.rs:29-42) + skin trigger
+//   a = F / m[type-1] is a true division (properties.rs:32-39).
+// f = force at the current positions, g = force at the previous positions.
+// ------------------------------------------------------------------------------------------------
+struct VVArgs {
+    int n;
+    double4 *xt;
+    double *vx, *vy, *vz;
+    const double *fx, *fy, *fz;  // F(t+dt) for KICK, F(t) for DRIFT
+    const double *gx, *gy, *gz;  // F(t) for KICK
+    const double *xbx, *xby, *xbz;
+    const double *mass;  // per type
+    BoxDev box;
+    double dt, dt2, half_skin2;
+    int always_rebuild;
+    int *flags;
+    double *partials;
+    unsigned int *ticket;
+    pisb_thermo *thermo;  // record of the step the KICK completes
+};
+
+template <bool KICK, bool DRIFT, bool ORTHO>
+__global__ void __launch_bounds__(TPB) k_vv(VVArgs a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double red[4] = {0.0, 0.0, 0.0, 0.0};  // ke, x*fx, y*fy, z*fz
+    if (i < a.n) {
+        double4 x = a.xt[i];
+        const double m = a.mass[type_of(x.w) - 1];
+        double vx = a.vx[i], vy = a.vy[i], vz = a.vz[i];
+        const double fx = a.fx[i], fy = a.fy[i], fz = a.fz[i];
+        const double ax = __ddiv_rn(fx, m), ay = __ddiv_rn(fy, m), az = __ddiv_rn(fz, m);
+        if (KICK) {
+            const double ox = __ddiv_rn(a.gx[i], m), oy = __ddiv_rn(a.gy[i], m), oz = __ddiv_rn(a.gz[i], m);
+            vx = __dadd_rn(vx, __dmul_rn(__dmul_rn(__dadd_rn(ox, ax), 0.5), a.dt));
+            vy = __dadd_rn(vy, __dmul_rn(__dmul_rn(__dadd_rn(oy, ay), 0.5), a.dt));
+            vz = __dadd_rn(vz, __dmul_rn(__dmul_rn(__dadd_rn(oz, az), 0.5), a.dt));
+            a.vx[i] = vx;
+            a.vy[i] = vy;
+            a.vz[i] = vz;
+            red[0] = __dmul_rn(__dmul_rn(0.5, m), norm2(vx, vy, vz));
+            red[1] = __dmul_rn(x.x, fx);
+            red[2] = __dmul_rn(x.y, fy);
+            red[3] = __dmul_rn(x.z, fz);
+        }
+        if (DRIFT) {
+            x.x = __dadd_rn(x.x, __dadd_rn(__dmul_rn(vx, a.dt), __dmul_rn(__dmul_rn(ax, 0.5), a.dt2)));
+            x.y = __dadd_rn(x.y, __dadd_rn(__dmul_rn(vy, a.dt), __dmul_rn(__dmul_rn(ay, 0.5), a.dt2)));
+            x.z = __dadd_rn(x.z, __dadd_rn(__dmul_rn(vz, a.dt), __dmul_rn(__dmul_rn(az, 0.5), a.dt2)));
+            wrap_pos<ORTHO>(a.box, x.x, x.y, x.z);
+            a.xt[i] = x;
+            if (a.always_rebuild) {
+                if (i == 0) a.flags[FLAG_REBUILD] = 1;
+            } else {
+                double dx = x.x - a.xbx[i], dy = x.y - a.xby[i], dz = x.z - a.xbz[i];
+                min_image<ORTHO>(a.box, dx, dy, dz);
+                if (!(norm2(dx, dy, dz) <= a.half_skin2)) a.flags[FLAG_REBUILD] = 1;
+            }
+        }
+    }
+    if (KICK) {
+        pisb_thermo *th = a.thermo;
+        double t3[3];
+        block_reduce_finalize<4, TPB>(red, a.partials, a.ticket, [&](int q, double s) {
+            if (q == 0) th->ke = s;
+            else t3[q - 1] = s;
+            if (q == 3) th->virial_ref = (t3[0] + t3[1]) + t3[2];
+        });
+    }
+}
+
+// KE / virial_ref of the current state without touching it (pisb_thermo_now).
+__global__ void __launch_bounds__(TPB) k_observe(int n, const double4 *__restrict__ xt,
+                                                 const double *__restrict__ vx, const double *__restrict__ vy,
+                                                 const double *__restrict__ vz, const double *__restrict__ fx,
+                                                 const double *__restrict__ fy, const double *__restrict__ fz,
+                                                 const double *__restrict__ mass, double *partials,
+                                                 unsigned int *ticket, pisb_thermo *th) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double red[4] = {0.0, 0.0, 0.0, 0.0};
+    if (i < n) {
+        double4 x = xt[i];
+        const double m = mass[type_of(x.w) - 1];
+        red[0] = __dmul_rn(__dmul_rn(0.5, m), norm2(vx[i], vy[i], vz[i]));
+        red[1] = __dmul_rn(x.x, fx[i]);
+        red[2] = __dmul_rn(x.y, fy[i]);
+        red[3] = __dmul_rn(x.z, fz[i]);
+    }
+    double t3[3];
+    block_reduce_finalize<4, TPB>(red, partials, ticket, [&](int q, double s) {
+        if (q == 0) th->ke = s;
+        else t3[q - 1] = s;
+        if (q == 3) th->virial_ref = (t3[0] + t3[1]) + t3[2];
+    });
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cell binning (replaces Atoms::rcut_cells, src/atoms/neighbour_list.rs:9-42).  The cell index is
+// (cz*ny + cy)*nx + cx like cell_index (:61-63).  Unlike the reference, the fractional coordinate
+// is wrapped before binning so that unwrapped step-0 inputs land in their periodic cell (the
+// reference saturates negatives to cell 0 and then misses pairs: SURVEY appendix A.2).
+// All rebuild-chain kernels exit immediately unless flags[FLAG_REBUILD] is set: the chain is
+// launched every step and the skin trigger decides on the device, with no host round trip.
+// ------------------------------------------------------------------------------------------------
+template <bool ORTHO>
+__global__ void __launch_bounds__(TPB) k_bin(int n, const double4 *__restrict__ xt, BoxDev box, Grid g,
+                                             int *__restrict__ cell_of, int *__restrict__ cell_count,
+                                             const int *flags) {
+    if (flags[FLAG_REBUILD] == 0) return;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double4 x = xt[i];
+    double s[3];
+    matvec<ORTHO>(box.hinv, x.x, x.y, x.z, s[0], s[1], s[2]);
+    int c[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        double sd = s[d];
+        if (box.pbc[d]) sd = sd - floor(sd);
+        // saturating conversion like Rust `as usize` (NaN/negative -> 0)
+        unsigned long long cd = __double2ull_rz(floor(sd * (double)g.n[d]));
+        if (cd >= (unsigned long long)g.n[d]) cd = box.pbc[d] ? cd % (unsigned long long)g.n[d] : (unsigned long long)(g.n[d] - 1);
+        c[d] = (int)cd;
+    }
+    int cell = (c[2] * g.n[1] + c[1]) * g.n[0] + c[0];
+    cell_of[i] = cell;
+    atomicAdd(&cell_count[cell], 1);
+}
+
+// Exclusive scan of cell_count -> cell_start, three phases over tiles of SCAN_TILE entries.
+constexpr int SCAN_TPB = 256;
+constexpr int SCAN_IPT = 8;
+constexpr int SCAN_TILE = SCAN_TPB * SCAN_IPT;
+
+__device__ __forceinline__ int block_exclusive_scan_int(int v, int &total) {
+    __shared__ int s_w[SCAN_TPB / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int w = lane < SCAN_TPB / 32 ? s_w[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += t;
+        }
+        if (lane < SCAN_TPB / 32) s_w[lane] = w;
+    }
+    __syncthreads();
+    int base = warp > 0 ? s_w[warp - 1] : 0;
+    total = s_w[SCAN_TPB / 32 - 1];
+    __syncthreads();
+    return base + inc - v;
+}
+
+__global__ void __launch_bounds__(SCAN_TPB) k_scan_tiles(int ncell, const int *__restrict__ cell_count,
+                                                         int *__restrict__ tile_sum, const int *flags) {
+    if (flags[FLAG_REBUILD] == 0) return;
+    int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_IPT;
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_IPT; ++k)
+        if (base + k < ncell) s += cell_count[base + k];
+    int total;
+    block_exclusive_scan_int(s, total);
+    if (threadIdx.x == 0) tile_sum[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(SCAN_TPB) k_scan_sums(int ntiles, int *__restrict__ tile_sum, const int *flags) {
+    if (flags[FLAG_REBUILD] == 0) return;
+    int carry = 0;
+    for (int base = 0; base < ntiles; base += SCAN_TPB) {
+        int idx = base + threadIdx.x;
+        int v = idx < ntiles ? tile_sum[idx] : 0;
+        int total;
+        int ex = block_exclusive_scan_int(v, total);
+        if (idx < ntiles) tile_sum[idx] = carry + ex;
+        carry += total;
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_TPB) k_scan_apply(int ncell, int n_atoms, int *__restrict__ cell_count,
+                                                         const int *__restrict__ tile_sum,
+                                                         int *__restrict__ cell_start, const int *flags) {
+    if (flags[FLAG_REBUILD] == 0) return;
+    int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_IPT;
+    int v[SCAN_IPT];
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_IPT; ++k) {
+        v[k] = base + k < ncell ? cell_count[base + k] : 0;
+        s += v[k];
+    }
+    int total;
+    int ex = block_exclusive_scan_int(s, total) + tile_sum[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_IPT; ++k) {
+        if (base + k < ncell) {
+            cell_start[base + k] = ex;
+            cell_count[base + k] = 0;  // reused as the fill cursor by k_fill
+        }
+        ex += v[k];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) cell_start[ncell] = n_atoms;
+}
+
+// Scatter slot indices into their cell segment (arrival order, fixed up by k_sort_cells).
+__global__ void __launch_bounds__(TPB) k_fill(int n, const int *__restrict__ cell_of,
+                                              const int *__restrict__ cell_start, int *__restrict__ cell_fill,
+                                              int *__restrict__ order, const int *flags) {
+    if (flags[FLAG_REBUILD] == 0) return;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int c = cell_of[i];
+    int p = cell_start[c] + atomicAdd(&cell_fill[c], 1);
+    order[p] = i;
+}
+
+// Within each cell order atoms by ORIGINAL id: deterministic regardless of atomic arrival order,
+// and the same within-cell order as the reference's push loop (ascending atom index,
+// src/atoms/neighbour_list.rs:17,38).  One thread per cell; cells hold ~16 atoms.
+__global__ void __launch_bounds__(TPB) k_sort_cells(int ncell, const int *__restrict__ cell_start,
+                                                    int *__restrict__ order, const int *__restrict__ id,
+                                                    const int *flags) {
+    if (flags[FLAG_REBUILD] == 0) return;
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncell) return;
+    const int b = cell_start[c], e = cell_start[c + 1];
+    for (int a = b + 1; a < e; ++a) {
+        int oa = order[a];
+        int ka = id[oa];
+        int p = a - 1;
+        while (p >= b) {
+            int op = order[p];
+            if (id[op] <= ka) break;
+            order[p + 1] = op;
+            --p;
+        }
+        order[p + 1] = oa;
+    }
+}
+
+// Permute every per-atom array into the new cell-sorted order (gather into scratch), and record
+// the build positions.  k_copy_back then moves scratch into the primary arrays, so the host-side
+// pointers never depend on whether the device decided to rebuild.
+struct PermArgs {
+    int n;
+    const int *order;
+    const double4 *xt;
+    const double *vx, *vy, *vz, *fx, *fy, *fz;
+    const int *id;
+    double4 *s_xt;
+    double *s_vx, *s_vy, *s_vz, *s_fx, *s_fy, *s_fz;
+    int *s_id;
+    const int *flags;
+};
+
+__global__ void __launch_bounds__(TPB) k_permute(PermArgs a) {
+    if (a.flags[FLAG_REBUILD] == 0) return;
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= a.n) return;
+    int o = a.order[p];
+    a.s_xt[p] = a.xt[o];
+    a.s_vx[p] = a.vx[o];
+    a.s_vy[p] = a.vy[o];
+    a.s_vz[p] = a.vz[o];
+    a.s_fx[p] = a.fx[o];
+    a.s_fy[p] = a.fy[o];
+    a.s_fz[p] = a.fz[o];
+    a.s_id[p] = a.id[o];
+}
+
+struct CopyBackArgs {
+    int n;
+    const double4 *s_xt;
+    const double *s_vx, *s_vy, *s_vz, *s_fx, *s_fy, *s_fz;
+    const int *s_id;
+    double4 *xt;
+    double *vx, *vy, *vz, *fx, *fy, *fz;
+    int *id;
+    int *slot_of_id;
+    double *xbx, *xby, *xbz;
+    const int *flags;
+};
+
+__global__ void __launch_bounds__(TPB) k_copy_back(CopyBackArgs a) {
+    if (a.flags[FLAG_REBUILD] == 0) return;
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= a.n) return;
+    double4 x = a.s_xt[p];
+    a.xt[p] = x;
+    a.xbx[p] = x.x;
+    a.xby[p] = x.y;
+    a.xbz[p] = x.z;
+    a.vx[p] = a.s_vx[p];
+    a.vy[p] = a.s_vy[p];
+    a.vz[p] = a.s_vz[p];
+    a.fx[p] = a.s_fx[p];
+    a.fy[p] = a.s_fy[p];
+    a.fz[p] = a.s_fz[p];
+    int o = a.s_id[p];
+    a.id[p] = o;
+    a.slot_of_id[o] = p;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Verlet-list build: FULL list, one thread per atom over the 27-cell stencil.
+// Semantics: LJVPBuildListManager::build_neighbour_list (src/potentials/lennard_jones.rs:345-415)
+// with rcut := rcut + skin: skip i == j, minimum image, `|rij| > rcut -> skip` (inclusive cutoff).
+// Atoms of one cell are consecutive slots, so the lanes of a warp that share a cell walk the same
+// candidate sequence (broadcast loads) and the transposed list rows are written coalesced.
+// ------------------------------------------------------------------------------------------------
+struct BuildArgs {
+    int n, npad, kcap;
+    const double4 *xt;
+    const int *cell_start;
+    BoxDev box;
+    Grid g;
+    PairDev pair0;           // single-type fast path
+    const PairDev *table;    // n_types x n_types (MULTI)
+    int n_types;
+    int *nbr;
+    int *nnbr;
+    int *flags;
+};
+
+template <bool ORTHO, bool MULTI>
+__global__ void __launch_bounds__(TPB_FORCE) k_build_list(BuildArgs a) {
+    if (a.flags[FLAG_REBUILD] == 0) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int cnt = 0;
+    if (i < a.n) {
+        const double4 xi = a.xt[i];
+        const int ti = MULTI ? type_of(xi.w) : 1;
+        // cell of slot i from its (already binned) position: recompute like k_bin
+        double s[3];
+        matvec<ORTHO>(a.box.hinv, xi.x, xi.y, xi.z, s[0], s[1], s[2]);
+        int c[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            double sd = s[d];
+            if (a.box.pbc[d]) sd = sd - floor(sd);
+            unsigned long long cd = __double2ull_rz(floor(sd * (double)a.g.n[d]));
+            if (cd >= (unsigned long long)a.g.n[d])
+                cd = a.box.pbc[d] ? cd % (unsigned long long)a.g.n[d] : (unsigned long long)(a.g.n[d] - 1);
+            c[d] = (int)cd;
+        }
+        int *row = a.nbr + i;
+        for (int dz = a.g.lo[2]; dz <= a.g.hi[2]; ++dz) {
+            int cz = c[2] + dz;
+            if (cz < 0 || cz >= a.g.n[2]) {
+                if (!a.box.pbc[2]) continue;
+                cz += cz < 0 ? a.g.n[2] : -a.g.n[2];
+            }
+            for (int dy = a.g.lo[1]; dy <= a.g.hi[1]; ++dy) {
+                int cy = c[1] + dy;
+                if (cy < 0 || cy >= a.g.n[1]) {
+                    if (!a.box.pbc[1]) continue;
+                    cy += cy < 0 ? a.g.n[1] : -a.g.n[1];
+                }
+                for (int dx = a.g.lo[0]; dx <= a.g.hi[0]; ++dx) {
+                    int cx = c[0] + dx;
+                    if (cx < 0 || cx >= a.g.n[0]) {
+                        if (!a.box.pbc[0]) continue;
+                        cx += cx < 0 ? a.g.n[0] : -a.g.n[0];
+                    }
+                    const int cell = (cz * a.g.n[1] + cy) * a.g.n[0] + cx;
+                    const int jb = __ldg(&a.cell_start[cell]), je = __ldg(&a.cell_start[cell + 1]);
+                    for (int j = jb; j < je; ++j) {
+                        if (j == i) continue;
+                        const double4 xj = ldg_d4(&a.xt[j]);
+                        double ddx = __dsub_rn(xj.x, xi.x), ddy = __dsub_rn(xj.y, xi.y), ddz = __dsub_rn(xj.z, xi.z);
+                        min_image<ORTHO>(a.box, ddx, ddy, ddz);
+                        const double r2 = norm2(ddx, ddy, ddz);
+                        double t_list;
+                        if (MULTI) {
+                            const int tj = type_of(xj.w);
+                            const int lo = min(ti, tj), hi = max(ti, tj);
+                            const PairDev *p = &a.table[(lo - 1) * a.n_types + (hi - 1)];
+                            if (!p->present) continue;
+                            t_list = p->t_list;
+                        } else {
+                            t_list = a.pair0.t_list;
+                        }
+                        if (r2 > t_list) continue;
+                        if (cnt < a.kcap) row[(size_t)cnt * a.npad] = j;
+                        ++cnt;
+                    }
+                }
+            }
+        }
+        a.nnbr[i] = cnt < a.kcap ? cnt : a.kcap;
+    }
+    // record the largest list (overflow is detected by the host as max > kcap)
+    int m = cnt;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_down_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(&a.flags[FLAG_MAXNBR], m);
+}
+
+__global__ void k_finish_rebuild(int *flags) {
+    if (flags[FLAG_REBUILD] == 0) return;
+    flags[FLAG_REBUILD] = 0;
+    flags[FLAG_NBUILDS] += 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LJ force / energy / virial over the Verlet list: one thread per atom, full list, no atomics.
+// Replaces LJVOffsetManager::compute_potential (src/potentials/lennard_jones.rs:186-244) through
+// the list consumer's form (:419-455): F_i += -f_ij per listed j inside rcut, PE = sum(u)/2.
+// Per-pair terms are bit-identical to the reference's; only the summation order differs.
+// ------------------------------------------------------------------------------------------------
+struct ForceArgs {
+    int n, npad;
+    const double4 *xt;
+    const int *nbr;
+    const int *nnbr;
+    BoxDev box;
+    PairDev pair0;
+    const PairDev *table;
+    int n_types;
+    const double *ax, *ay, *az;  // accumulate source (may alias the outputs) or null
+    double *fx, *fy, *fz;        // output
+    double *partials;
+    unsigned int *ticket;
+    pisb_thermo *thermo;
+};
+
+template <bool ORTHO, bool MULTI>
+__global__ void __launch_bounds__(TPB_FORCE) k_force(ForceArgs a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double red[2] = {0.0, 0.0};  // sum u, sum fs*r2
+    if (i < a.n) {
+        const double4 xi = a.xt[i];
+        const int ti = MULTI ? type_of(xi.w) : 1;
+        const int nn = a.nnbr[i];
+        const int *row = a.nbr + i;
+        double fx = 0.0, fy = 0.0, fz = 0.0, pe = 0.0, vir = 0.0;
+        int jn = nn > 0 ? __ldg(row) : 0;
+        for (int k = 0; k < nn; ++k) {
+            const int j = jn;
+            if (k + 1 < nn) jn = __ldg(row + (size_t)(k + 1) * a.npad);
+            const double4 xj = ldg_d4(&a.xt[j]);
+            double dx = __dsub_rn(xj.x, xi.x), dy = __dsub_rn(xj.y, xi.y), dz = __dsub_rn(xj.z, xi.z);
+            min_image<ORTHO>(a.box, dx, dy, dz);
+            const double r2 = norm2(dx, dy, dz);
+            PairDev p;
+            if (MULTI) {
+                const int tj = type_of(xj.w);
+                const int lo = min(ti, tj), hi = max(ti, tj);
+                p = a.table[(lo - 1) * a.n_types + (hi - 1)];
+                if (!p.present) continue;
+            } else {
+                p = a.pair0;
+            }
+            if (r2 > p.t_rc) continue;
+            double u, fs;
+            lj_pair(p, r2, u, fs);
+            fx = __dsub_rn(fx, __dmul_rn(fs, dx));
+            fy = __dsub_rn(fy, __dmul_rn(fs, dy));
+            fz = __dsub_rn(fz, __dmul_rn(fs, dz));
+            pe = __dadd_rn(pe, u);
+            vir = fma(fs, r2, vir);
+        }
+        if (a.ax) {
+            fx += a.ax[i];
+            fy += a.ay[i];
+            fz += a.az[i];
+        }
+        a.fx[i] = fx;
+        a.fy[i] = fy;
+        a.fz[i] = fz;
+        red[0] = pe;
+        red[1] = vir;
+    }
+    pisb_thermo *th = a.thermo;
+    block_reduce_finalize<2, TPB_FORCE>(red, a.partials, a.ticket, [&](int q, double s) {
+        if (q == 0) th->pe = s / 2.0;
+        else th->virial_pair = s / 2.0;
+    });
+}
+
+}  // namespace pisb

@@ -1,0 +1,914 @@
+// pisb_sim.cu -- handle, device memory, launch sequences and the C ABI of libpisb200.so.
+// Kernels live in pisb_kernels.cuh.  No CPU fallback: every entry point needs a CUDA device.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "pisb200.h"
+#include "pisb_kernels.cuh"
+
+using namespace pisb;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+std::string fmt(const char *f, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, f);
+    vsnprintf(buf, sizeof buf, f, ap);
+    va_end(ap);
+    return buf;
+}
+
+// max{t : sqrt(t) <= rc}: with IEEE sqrt monotone, `sqrt(r2) > rc` <=> `r2 > t` exactly.
+double sqrt_threshold(double rc) {
+    if (!(rc > 0.0) || !std::isfinite(rc)) return rc > 0.0 ? rc : 0.0;
+    double t = rc * rc;
+    while (std::sqrt(t) > rc) t = std::nextafter(t, 0.0);
+    while (std::sqrt(std::nextafter(t, INFINITY)) <= rc) t = std::nextafter(t, INFINITY);
+    return t;
+}
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;  // elements
+};
+
+}  // namespace
+
+struct pisb_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+
+    // potential
+    int n_types = 0;
+    std::vector<double> mass, eps, sigma, rcut;
+    std::vector<unsigned char> present;
+    int shift = 1;
+    double skin = 0.0;
+    double max_rcut = 0.0;
+    std::vector<PairDev> pairs;
+
+    // box / grid
+    BoxDev box{};
+    bool have_box = false;
+    Grid grid{};
+    bool grid_ok = false;
+
+    // atoms
+    int n = 0, npad = 0, kcap = 0;
+    bool have_atoms = false;
+    bool list_valid = false;   // a list exists for the current atom set / box
+    bool forces_current = false;
+    int kcap_user = 0;
+
+    // device arrays
+    DevBuf<double4> xt, s_xt;
+    DevBuf<double> v[3], f[3], g[3], xb[3], s_v[3], s_f[3];
+    DevBuf<int> id, s_id, slot_of_id, cell_of, order, nnbr, nbr;
+    DevBuf<int> cell_count, cell_start, tile_sum;
+    DevBuf<double> mass_d, partials, st_pos, st_vel, st_frc;
+    DevBuf<int> st_types;
+    DevBuf<PairDev> table_d;
+    DevBuf<pisb_thermo> thermo_d;
+    int *flags = nullptr;
+    unsigned int *ticket = nullptr;
+    int *h_flags = nullptr;          // pinned
+    pisb_thermo *h_thermo = nullptr; // pinned
+    size_t h_thermo_cap = 0;
+    double *h_stage = nullptr;       // pinned staging for pageable host buffers
+    size_t h_stage_cap = 0;
+    int64_t device_bytes = 0;
+
+    // stats
+    int64_t n_steps = 0, n_launches = 0;
+    int64_t max_nbr = 0, total_nbr = 0;
+    int64_t n_builds_host = 0;
+
+    // profiling
+    bool profiling = false;
+    struct Ev {
+        cudaEvent_t a, b;
+        int cls;
+    };
+    std::vector<Ev> ev_pool;
+    size_t ev_used = 0;
+    double t_ms[PISB_K_COUNT] = {0};
+    int64_t t_n[PISB_K_COUNT] = {0};
+};
+
+namespace {
+
+int fail(pisb_t *h, int code, const std::string &msg) {
+    if (h) h->err = msg;
+    else g_create_error = msg;
+    return code;
+}
+
+#define CUDA_TRY(h, expr)                                                                          \
+    do {                                                                                           \
+        cudaError_t e_ = (expr);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(h, PISB_ERR_CUDA, fmt("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__, \
+                                              cudaGetErrorString(e_)));                            \
+    } while (0)
+
+#define TRY(expr)                      \
+    do {                               \
+        int rc_ = (expr);              \
+        if (rc_ != PISB_OK) return rc_; \
+    } while (0)
+
+template <typename T>
+int dev_reserve(pisb_t *h, DevBuf<T> &b, size_t n) {
+    if (n <= b.cap) return PISB_OK;
+    if (b.p) {
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        CUDA_TRY(h, cudaFree(b.p));
+        h->device_bytes -= (int64_t)(b.cap * sizeof(T));
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    CUDA_TRY(h, cudaMalloc((void **)&b.p, n * sizeof(T)));
+    b.cap = n;
+    h->device_bytes += (int64_t)(n * sizeof(T));
+    return PISB_OK;
+}
+
+template <typename T>
+void dev_free(pisb_t *h, DevBuf<T> &b) {
+    if (b.p) cudaFree(b.p);
+    h->device_bytes -= (int64_t)(b.cap * sizeof(T));
+    b.p = nullptr;
+    b.cap = 0;
+}
+
+// ---- profiling -------------------------------------------------------------------------------
+struct LaunchScope {
+    pisb_t *h;
+    int idx = -1;
+    LaunchScope(pisb_t *h_, int cls) : h(h_) {
+        h->n_launches++;
+        if (!h->profiling) return;
+        if (h->ev_used == h->ev_pool.size()) {
+            pisb_handle::Ev e;
+            cudaEventCreate(&e.a);
+            cudaEventCreate(&e.b);
+            e.cls = cls;
+            h->ev_pool.push_back(e);
+        }
+        idx = (int)h->ev_used++;
+        h->ev_pool[idx].cls = cls;
+        cudaEventRecord(h->ev_pool[idx].a, h->stream);
+    }
+    ~LaunchScope() {
+        if (idx >= 0) cudaEventRecord(h->ev_pool[idx].b, h->stream);
+    }
+};
+
+void drain_events(pisb_t *h) {
+    if (h->ev_used == 0) return;
+    cudaStreamSynchronize(h->stream);
+    for (size_t i = 0; i < h->ev_used; ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->ev_pool[i].a, h->ev_pool[i].b) == cudaSuccess) {
+            h->t_ms[h->ev_pool[i].cls] += ms;
+            h->t_n[h->ev_pool[i].cls] += 1;
+        }
+    }
+    h->ev_used = 0;
+}
+
+inline int nblk(int n, int tpb) { return (n + tpb - 1) / tpb; }
+
+int check_launch(pisb_t *h, const char *what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(h, PISB_ERR_CUDA, fmt("launch %s: %s", what, cudaGetErrorString(e)));
+    return PISB_OK;
+}
+
+// ---- setup -----------------------------------------------------------------------------------
+int build_pair_table(pisb_t *h) {
+    const int nt = h->n_types;
+    h->pairs.assign((size_t)nt * nt, PairDev{});
+    h->max_rcut = 0.0;
+    for (int k = 0; k < nt * nt; ++k) {
+        PairDev &p = h->pairs[k];
+        p.present = h->present[k] ? 1 : 0;
+        if (!p.present) continue;
+        const double e = h->eps[k], s = h->sigma[k], rc = h->rcut[k];
+        if (h->max_rcut < rc) h->max_rcut = rc;  // PairPotentialManager::max_rcut (potential.rs:170-179)
+        p.c4 = 4.0 * e;
+        p.c24 = 24.0 * e;
+        p.sig2 = s * s;
+        p.t_rc = sqrt_threshold(rc);
+        p.t_list = sqrt_threshold(rc + h->skin);
+        if (h->shift) {
+            // lennard_jones.rs:44-52, same expression order
+            const double q = s / rc;
+            const double ci2 = q * q;
+            const double ca = (ci2 * ci2) * ci2;
+            const double cr = ca * ca;
+            p.ucut = 4.0 * e * (cr - ca);
+        } else {
+            p.ucut = 0.0;
+        }
+    }
+    TRY(dev_reserve(h, h->table_d, (size_t)nt * nt));
+    CUDA_TRY(h, cudaMemcpyAsync(h->table_d.p, h->pairs.data(), sizeof(PairDev) * nt * nt,
+                                cudaMemcpyHostToDevice, h->stream));
+    TRY(dev_reserve(h, h->mass_d, (size_t)nt));
+    CUDA_TRY(h, cudaMemcpyAsync(h->mass_d.p, h->mass.data(), sizeof(double) * nt, cudaMemcpyHostToDevice,
+                                h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return PISB_OK;
+}
+
+// Cell grid: n_d = max(1, floor(|h col d| / (max_rcut + skin))) -- Atoms::divide_into_cells
+// (src/atoms/neighbour_list.rs:45-57) with rcut := max_rcut + skin; capped so that the cell count
+// stays O(N) for dilute systems (a coarser grid is still correct: cell edge >= list cutoff).
+int setup_grid(pisb_t *h) {
+    h->grid_ok = false;
+    if (!h->have_box || !h->have_atoms) return PISB_OK;
+    const double rc_list = h->max_rcut + h->skin;
+    if (!(rc_list > 0.0)) return fail(h, PISB_ERR_INVALID, "no pair potential present (max_rcut = 0)");
+    Grid g{};
+    for (int d = 0; d < 3; ++d) {
+        const double *c = &h->box.h[d * 3];
+        const double len = std::sqrt((c[0] * c[0] + c[1] * c[1]) + c[2] * c[2]);
+        double nd = std::floor(len / rc_list);
+        if (!(nd >= 1.0)) nd = 1.0;
+        if (nd > 1024.0) nd = 1024.0;
+        g.n[d] = (int)nd;
+        if (h->box.pbc[d] && g.n[d] < 2)
+            return fail(h, PISB_ERR_INVALID,
+                        fmt("box edge %d (%.6g) is shorter than 2 x (rcut + skin) = %.6g: the single-image "
+                            "minimum-image convention of the reference (simulation_box.rs:17-27) is invalid",
+                            d, len, 2.0 * rc_list));
+    }
+    const int64_t cell_cap = std::max<int64_t>(4 * (int64_t)h->n + 1024, 27);
+    while ((int64_t)g.n[0] * g.n[1] * g.n[2] > cell_cap) {
+        int dmax = 0;
+        for (int d = 1; d < 3; ++d)
+            if (g.n[d] > g.n[dmax]) dmax = d;
+        g.n[dmax] = std::max(3, g.n[dmax] * 3 / 4);
+        if (g.n[0] <= 3 && g.n[1] <= 3 && g.n[2] <= 3) break;
+    }
+    for (int d = 0; d < 3; ++d) {
+        // unique stencil offsets (the reference double-counts when n < 3: SURVEY appendix A.1)
+        if (g.n[d] == 1) g.lo[d] = 0, g.hi[d] = 0;
+        else if (g.n[d] == 2) g.lo[d] = 0, g.hi[d] = 1;
+        else g.lo[d] = -1, g.hi[d] = 1;
+    }
+    g.ncell = g.n[0] * g.n[1] * g.n[2];
+    h->grid = g;
+    TRY(dev_reserve(h, h->cell_count, (size_t)g.ncell + 1));
+    TRY(dev_reserve(h, h->cell_start, (size_t)g.ncell + 1));
+    TRY(dev_reserve(h, h->tile_sum, (size_t)nblk(g.ncell, SCAN_TILE) + 1));
+    h->grid_ok = true;
+    h->list_valid = false;
+    return PISB_OK;
+}
+
+int estimate_kcap(pisb_t *h) {
+    if (h->kcap_user > 0) return h->kcap_user;
+    const double *m = h->box.h;
+    const double vol = std::fabs(m[0] * (m[4] * m[8] - m[5] * m[7]) - m[3] * (m[1] * m[8] - m[2] * m[7]) +
+                                 m[6] * (m[1] * m[5] - m[2] * m[4]));
+    const double rl = h->max_rcut + h->skin;
+    double k = vol > 0 ? (double)h->n / vol * 4.18879020478639 * rl * rl * rl : 64.0;
+    k = 1.3 * k + 24.0;
+    if (k > (double)h->n) k = (double)std::max(h->n, 1);
+    if (k > 4096.0) k = 4096.0;
+    return (int)std::ceil(k);
+}
+
+int reserve_atoms(pisb_t *h, int n) {
+    const size_t cap = (size_t)n;
+    TRY(dev_reserve(h, h->xt, cap));
+    TRY(dev_reserve(h, h->s_xt, cap));
+    for (int d = 0; d < 3; ++d) {
+        TRY(dev_reserve(h, h->v[d], cap));
+        TRY(dev_reserve(h, h->f[d], cap));
+        TRY(dev_reserve(h, h->g[d], cap));
+        TRY(dev_reserve(h, h->xb[d], cap));
+        TRY(dev_reserve(h, h->s_v[d], cap));
+        TRY(dev_reserve(h, h->s_f[d], cap));
+    }
+    TRY(dev_reserve(h, h->id, cap));
+    TRY(dev_reserve(h, h->s_id, cap));
+    TRY(dev_reserve(h, h->slot_of_id, cap));
+    TRY(dev_reserve(h, h->cell_of, cap));
+    TRY(dev_reserve(h, h->order, cap));
+    TRY(dev_reserve(h, h->nnbr, cap));
+    TRY(dev_reserve(h, h->partials, (size_t)4 * (nblk(n, TPB_FORCE) + 1)));
+    return PISB_OK;
+}
+
+int reserve_list(pisb_t *h) {
+    h->npad = (h->n + 31) / 32 * 32;
+    TRY(dev_reserve(h, h->nbr, (size_t)h->kcap * (size_t)h->npad));
+    return PISB_OK;
+}
+
+int reserve_thermo(pisb_t *h, size_t n) {
+    TRY(dev_reserve(h, h->thermo_d, n));
+    if (h->h_thermo_cap < n) {
+        if (h->h_thermo) cudaFreeHost(h->h_thermo);
+        h->h_thermo = nullptr;
+        CUDA_TRY(h, cudaHostAlloc((void **)&h->h_thermo, sizeof(pisb_thermo) * n, cudaHostAllocDefault));
+        h->h_thermo_cap = n;
+    }
+    return PISB_OK;
+}
+
+// ---- launch sequences ------------------------------------------------------------------------
+template <typename F>
+int dispatch_ortho(pisb_t *h, F &&f) {
+    return h->box.ortho ? f(std::true_type{}) : f(std::false_type{});
+}
+
+// The rebuild chain: every kernel returns at once unless flags[FLAG_REBUILD] is set.
+int launch_rebuild_chain(pisb_t *h) {
+    const int n = h->n;
+    const Grid g = h->grid;
+    cudaStream_t st = h->stream;
+    {
+        LaunchScope ls(h, PISB_K_BIN);
+        CUDA_TRY(h, cudaMemsetAsync(h->cell_count.p, 0, sizeof(int) * ((size_t)g.ncell + 1), st));
+        if (h->box.ortho)
+            k_bin<true><<<nblk(n, TPB), TPB, 0, st>>>(n, h->xt.p, h->box, g, h->cell_of.p, h->cell_count.p, h->flags);
+        else
+            k_bin<false><<<nblk(n, TPB), TPB, 0, st>>>(n, h->xt.p, h->box, g, h->cell_of.p, h->cell_count.p, h->flags);
+    }
+    {
+        LaunchScope ls(h, PISB_K_SORT);
+        const int ntiles = nblk(g.ncell, SCAN_TILE);
+        k_scan_tiles<<<ntiles, SCAN_TPB, 0, st>>>(g.ncell, h->cell_count.p, h->tile_sum.p, h->flags);
+        k_scan_sums<<<1, SCAN_TPB, 0, st>>>(ntiles, h->tile_sum.p, h->flags);
+        k_scan_apply<<<ntiles, SCAN_TPB, 0, st>>>(g.ncell, n, h->cell_count.p, h->tile_sum.p, h->cell_start.p, h->flags);
+        k_fill<<<nblk(n, TPB), TPB, 0, st>>>(n, h->cell_of.p, h->cell_start.p, h->cell_count.p, h->order.p, h->flags);
+        k_sort_cells<<<nblk(g.ncell, TPB), TPB, 0, st>>>(g.ncell, h->cell_start.p, h->order.p, h->id.p, h->flags);
+        PermArgs pa{n, h->order.p, h->xt.p, h->v[0].p, h->v[1].p, h->v[2].p, h->f[0].p, h->f[1].p, h->f[2].p,
+                    h->id.p, h->s_xt.p, h->s_v[0].p, h->s_v[1].p, h->s_v[2].p, h->s_f[0].p, h->s_f[1].p,
+                    h->s_f[2].p, h->s_id.p, h->flags};
+        k_permute<<<nblk(n, TPB), TPB, 0, st>>>(pa);
+        CopyBackArgs ca{n, h->s_xt.p, h->s_v[0].p, h->s_v[1].p, h->s_v[2].p, h->s_f[0].p, h->s_f[1].p, h->s_f[2].p,
+                        h->s_id.p, h->xt.p, h->v[0].p, h->v[1].p, h->v[2].p, h->f[0].p, h->f[1].p, h->f[2].p,
+                        h->id.p, h->slot_of_id.p, h->xb[0].p, h->xb[1].p, h->xb[2].p, h->flags};
+        k_copy_back<<<nblk(n, TPB), TPB, 0, st>>>(ca);
+        h->n_launches += 6;
+    }
+    {
+        LaunchScope ls(h, PISB_K_BUILD);
+        BuildArgs ba{n, h->npad, h->kcap, h->xt.p, h->cell_start.p, h->box, g, h->pairs[0], h->table_d.p,
+                     h->n_types, h->nbr.p, h->nnbr.p, h->flags};
+        const bool multi = h->n_types > 1;
+        const int nb = nblk(n, TPB_FORCE);
+        if (h->box.ortho) {
+            if (multi) k_build_list<true, true><<<nb, TPB_FORCE, 0, st>>>(ba);
+            else k_build_list<true, false><<<nb, TPB_FORCE, 0, st>>>(ba);
+        } else {
+            if (multi) k_build_list<false, true><<<nb, TPB_FORCE, 0, st>>>(ba);
+            else k_build_list<false, false><<<nb, TPB_FORCE, 0, st>>>(ba);
+        }
+        k_finish_rebuild<<<1, 1, 0, st>>>(h->flags);
+        h->n_launches += 1;
+    }
+    return check_launch(h, "rebuild chain");
+}
+
+// f_out = (acc ? acc + LJ : LJ); thermo record gets pe and virial_pair.
+int launch_force(pisb_t *h, double *const out[3], const double *const acc[3], pisb_thermo *rec) {
+    LaunchScope ls(h, PISB_K_FORCE);
+    ForceArgs fa{h->n, h->npad, h->xt.p, h->nbr.p, h->nnbr.p, h->box, h->pairs[0], h->table_d.p, h->n_types,
+                 acc ? acc[0] : nullptr, acc ? acc[1] : nullptr, acc ? acc[2] : nullptr,
+                 out[0], out[1], out[2], h->partials.p, h->ticket, rec};
+    const bool multi = h->n_types > 1;
+    const int nb = nblk(h->n, TPB_FORCE);
+    cudaStream_t st = h->stream;
+    if (h->box.ortho) {
+        if (multi) k_force<true, true><<<nb, TPB_FORCE, 0, st>>>(fa);
+        else k_force<true, false><<<nb, TPB_FORCE, 0, st>>>(fa);
+    } else {
+        if (multi) k_force<false, true><<<nb, TPB_FORCE, 0, st>>>(fa);
+        else k_force<false, false><<<nb, TPB_FORCE, 0, st>>>(fa);
+    }
+    return check_launch(h, "k_force");
+}
+
+int launch_vv(pisb_t *h, bool kick, bool drift, double dt, pisb_thermo *rec) {
+    LaunchScope ls(h, PISB_K_INTEGRATE);
+    const double hs = 0.5 * h->skin;
+    VVArgs a{h->n, h->xt.p, h->v[0].p, h->v[1].p, h->v[2].p, h->f[0].p, h->f[1].p, h->f[2].p,
+             h->g[0].p, h->g[1].p, h->g[2].p, h->xb[0].p, h->xb[1].p, h->xb[2].p, h->mass_d.p, h->box,
+             dt, dt * dt, hs * hs, h->skin > 0.0 ? 0 : 1, h->flags, h->partials.p, h->ticket, rec};
+    const int nb = nblk(h->n, TPB);
+    cudaStream_t st = h->stream;
+    const bool o = h->box.ortho != 0;
+#define VV(K, D)                                                   \
+    do {                                                           \
+        if (o) k_vv<K, D, true><<<nb, TPB, 0, st>>>(a);            \
+        else k_vv<K, D, false><<<nb, TPB, 0, st>>>(a);             \
+    } while (0)
+    if (kick && drift) VV(true, true);
+    else if (kick) VV(true, false);
+    else VV(false, true);
+#undef VV
+    return check_launch(h, "k_vv");
+}
+
+int read_flags(pisb_t *h) {
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_flags, h->flags, sizeof(int) * FLAG_COUNT, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return PISB_OK;
+}
+
+int set_flag(pisb_t *h, int which, int value) {
+    CUDA_TRY(h, cudaMemcpyAsync(h->flags + which, &value, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    return PISB_OK;
+}
+
+// Make sure a valid list exists for the CURRENT positions (host-synchronous; grows capacity).
+int ensure_list(pisb_t *h) {
+    if (!h->grid_ok) TRY(setup_grid(h));
+    if (!h->grid_ok) return fail(h, PISB_ERR_STATE, "set_box and upload must precede this call");
+    if (h->kcap == 0) {
+        h->kcap = estimate_kcap(h);
+        TRY(reserve_list(h));
+    }
+    for (int attempt = 0; attempt < 6; ++attempt) {
+        if (!h->list_valid) TRY(set_flag(h, FLAG_REBUILD, 1));
+        TRY(set_flag(h, FLAG_MAXNBR, 0));
+        TRY(launch_rebuild_chain(h));
+        TRY(read_flags(h));
+        const int mx = h->h_flags[FLAG_MAXNBR];
+        if (h->h_flags[FLAG_NBUILDS] != h->n_builds_host) {
+            h->n_builds_host = h->h_flags[FLAG_NBUILDS];
+            h->max_nbr = mx;
+        }
+        if (mx <= h->kcap) {
+            h->list_valid = true;
+            return PISB_OK;
+        }
+        if (h->kcap_user > 0 && mx > h->kcap_user)
+            return fail(h, PISB_ERR_CAPACITY, fmt("neighbour list needs %d slots per atom, list_capacity is %d", mx, h->kcap_user));
+        h->kcap = (int)(mx * 1.25) + 8;
+        h->list_valid = false;
+        TRY(reserve_list(h));
+    }
+    return fail(h, PISB_ERR_CAPACITY, "neighbour-list capacity did not converge");
+}
+
+// Stage a host AoS array on the device (pageable or pinned source).
+int stage_in(pisb_t *h, DevBuf<double> &dst, const double *src, size_t count) {
+    TRY(dev_reserve(h, dst, count));
+    CUDA_TRY(h, cudaMemcpyAsync(dst.p, src, sizeof(double) * count, cudaMemcpyHostToDevice, h->stream));
+    return PISB_OK;
+}
+
+int do_upload(pisb_t *h, int64_t n64, const double *pos, const double *vel, const double *frc,
+              const int32_t *types) {
+    if (n64 <= 0 || n64 > 2000000000LL) return fail(h, PISB_ERR_INVALID, "atom count out of range");
+    if (!pos) return fail(h, PISB_ERR_INVALID, "pos is NULL");
+    const int n = (int)n64;
+    const bool same_set = h->have_atoms && h->n == n && h->list_valid && types == nullptr;
+    if (!h->have_atoms && !types) return fail(h, PISB_ERR_INVALID, "types is NULL on first upload");
+    if (h->have_atoms && h->n != n && !types) return fail(h, PISB_ERR_INVALID, "types is NULL but the atom count changed");
+    if (!same_set) {
+        if (h->n != n) {
+            h->kcap = 0;
+            h->grid_ok = false;
+        }
+        h->n = n;
+        h->have_atoms = true;
+        h->list_valid = false;
+        TRY(reserve_atoms(h, n));
+    }
+    const size_t n3 = (size_t)3 * n;
+    TRY(stage_in(h, h->st_pos, pos, n3));
+    if (vel) TRY(stage_in(h, h->st_vel, vel, n3));
+    if (frc) TRY(stage_in(h, h->st_frc, frc, n3));
+    if (types) {
+        TRY(dev_reserve(h, h->st_types, (size_t)n));
+        CUDA_TRY(h, cudaMemcpyAsync(h->st_types.p, types, sizeof(int) * n, cudaMemcpyHostToDevice, h->stream));
+    }
+    {
+        LaunchScope ls(h, PISB_K_COPY);
+        LoadArgs la{n, h->st_pos.p, vel ? h->st_vel.p : nullptr, frc ? h->st_frc.p : nullptr,
+                    h->st_types.p, same_set ? h->slot_of_id.p : nullptr, h->xt.p,
+                    h->v[0].p, h->v[1].p, h->v[2].p, h->f[0].p, h->f[1].p, h->f[2].p, h->id.p, h->n_types, h->flags};
+        k_load_aos<<<nblk(n, TPB), TPB, 0, h->stream>>>(la);
+        TRY(check_launch(h, "k_load_aos"));
+        if (same_set && h->have_box) {
+            // keep the list if no atom moved more than skin/2 from its build position
+            const double hs = 0.5 * h->skin;
+            if (h->skin > 0.0) {
+                if (h->box.ortho)
+                    k_check_displacement<true><<<nblk(n, TPB), TPB, 0, h->stream>>>(n, h->xt.p, h->xb[0].p, h->xb[1].p, h->xb[2].p, h->box, hs * hs, h->flags);
+                else
+                    k_check_displacement<false><<<nblk(n, TPB), TPB, 0, h->stream>>>(n, h->xt.p, h->xb[0].p, h->xb[1].p, h->xb[2].p, h->box, hs * hs, h->flags);
+                h->n_launches++;
+            } else {
+                TRY(set_flag(h, FLAG_REBUILD, 1));
+            }
+        }
+    }
+    h->forces_current = false;
+    return PISB_OK;
+}
+
+int do_download(pisb_t *h, double *pos, double *vel, double *frc) {
+    if (!h->have_atoms) return fail(h, PISB_ERR_STATE, "download before upload");
+    const int n = h->n;
+    const size_t n3 = (size_t)3 * n;
+    if (pos) TRY(dev_reserve(h, h->st_pos, n3));
+    if (vel) TRY(dev_reserve(h, h->st_vel, n3));
+    if (frc) TRY(dev_reserve(h, h->st_frc, n3));
+    {
+        LaunchScope ls(h, PISB_K_COPY);
+        StoreArgs sa{n, h->xt.p, h->v[0].p, h->v[1].p, h->v[2].p, h->f[0].p, h->f[1].p, h->f[2].p, h->id.p,
+                     pos ? h->st_pos.p : nullptr, vel ? h->st_vel.p : nullptr, frc ? h->st_frc.p : nullptr};
+        k_store_aos<<<nblk(n, TPB), TPB, 0, h->stream>>>(sa);
+        TRY(check_launch(h, "k_store_aos"));
+    }
+    if (pos) CUDA_TRY(h, cudaMemcpyAsync(pos, h->st_pos.p, sizeof(double) * n3, cudaMemcpyDeviceToHost, h->stream));
+    if (vel) CUDA_TRY(h, cudaMemcpyAsync(vel, h->st_vel.p, sizeof(double) * n3, cudaMemcpyDeviceToHost, h->stream));
+    if (frc) CUDA_TRY(h, cudaMemcpyAsync(frc, h->st_frc.p, sizeof(double) * n3, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return PISB_OK;
+}
+
+int check_bad_type(pisb_t *h) {
+    if (h->h_flags[FLAG_BADTYPE] != 0) {
+        int o = h->h_flags[FLAG_BADTYPE];
+        set_flag(h, FLAG_BADTYPE, 0);
+        return fail(h, PISB_ERR_INVALID, fmt("atom %d has a type outside 1..%d", o, h->n_types));
+    }
+    return PISB_OK;
+}
+
+int do_compute(pisb_t *h, int accumulate, double *pe) {
+    if (!h->have_atoms || !h->have_box) return fail(h, PISB_ERR_STATE, "set_box and upload must precede compute");
+    TRY(ensure_list(h));
+    TRY(check_bad_type(h));
+    TRY(reserve_thermo(h, 2));
+    double *out[3] = {h->f[0].p, h->f[1].p, h->f[2].p};
+    const double *acc[3] = {h->f[0].p, h->f[1].p, h->f[2].p};
+    TRY(launch_force(h, out, accumulate ? acc : nullptr, h->thermo_d.p));
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_thermo, h->thermo_d.p, sizeof(pisb_thermo), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (pe) *pe = h->h_thermo[0].pe;
+    h->forces_current = true;
+    return PISB_OK;
+}
+
+int do_step_nve(pisb_t *h, double dt, int64_t nsteps, pisb_thermo *out) {
+    if (!h->have_atoms || !h->have_box) return fail(h, PISB_ERR_STATE, "set_box and upload must precede step_nve");
+    if (nsteps < 0) return fail(h, PISB_ERR_INVALID, "nsteps < 0");
+    if (nsteps == 0) return PISB_OK;
+    TRY(ensure_list(h));  // list for x(t); from here on the skin trigger decides on the device
+    TRY(check_bad_type(h));
+    const int64_t chunk_max = 4096;
+    int64_t done = 0;
+    while (done < nsteps) {
+        const int64_t m = std::min(chunk_max, nsteps - done);
+        TRY(reserve_thermo(h, (size_t)m + 1));
+        for (int64_t s = 0; s < m; ++s) {
+            pisb_thermo *rec = h->thermo_d.p + s;
+            // kick of the previous step of this chunk fused with this step's drift
+            if (s == 0) TRY(launch_vv(h, false, true, dt, nullptr));
+            else TRY(launch_vv(h, true, true, dt, rec - 1));
+            TRY(launch_rebuild_chain(h));
+            double *outp[3] = {h->g[0].p, h->g[1].p, h->g[2].p};
+            TRY(launch_force(h, outp, nullptr, rec));
+            for (int d = 0; d < 3; ++d) std::swap(h->f[d], h->g[d]);
+        }
+        TRY(launch_vv(h, true, false, dt, h->thermo_d.p + (m - 1)));
+        CUDA_TRY(h, cudaMemcpyAsync(h->h_thermo, h->thermo_d.p, sizeof(pisb_thermo) * m, cudaMemcpyDeviceToHost, h->stream));
+        TRY(read_flags(h));
+        if (h->h_flags[FLAG_NBUILDS] != h->n_builds_host) {
+            h->n_builds_host = h->h_flags[FLAG_NBUILDS];
+            h->max_nbr = h->h_flags[FLAG_MAXNBR];
+        }
+        if (h->h_flags[FLAG_MAXNBR] > h->kcap) {
+            const int mx = h->h_flags[FLAG_MAXNBR];
+            h->list_valid = false;
+            if (h->kcap_user == 0) {
+                h->kcap = (int)(mx * 1.25) + 8;
+                TRY(reserve_list(h));
+            }
+            return fail(h, PISB_ERR_CAPACITY,
+                        fmt("a neighbour list overflowed during the batch (needed %d slots per atom); capacity was "
+                            "grown -- re-upload the state and repeat the call", mx));
+        }
+        if (out) std::memcpy(out + done, h->h_thermo, sizeof(pisb_thermo) * m);
+        done += m;
+        h->n_steps += m;
+    }
+    h->forces_current = true;
+    return PISB_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+const char *pisb_version(void) { return "pisb200 0.1 (sm_100a)"; }
+
+int pisb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+const char *pisb_last_error(pisb_t *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int pisb_create(int device, int n_types, const double *mass, const double *eps, const double *sigma,
+                const double *rcut, const unsigned char *present, int shift, double skin, pisb_t **out) {
+    if (!out) return fail(nullptr, PISB_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (n_types < 1 || n_types > 64 || !mass || !eps || !sigma || !rcut || !present)
+        return fail(nullptr, PISB_ERR_INVALID, "bad potential table arguments");
+    if (!(skin >= 0.0)) return fail(nullptr, PISB_ERR_INVALID, "skin must be >= 0");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(nullptr, PISB_ERR_NO_DEVICE,
+                    fmt("no CUDA device available (%s): libpisb200 has no CPU fallback",
+                        e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    }
+    if (device < 0 || device >= ndev) return fail(nullptr, PISB_ERR_INVALID, fmt("device %d out of range (0..%d)", device, ndev - 1));
+    pisb_t *h = new pisb_handle();
+    h->device = device;
+    h->n_types = n_types;
+    h->mass.assign(mass, mass + n_types);
+    h->eps.assign(eps, eps + n_types * n_types);
+    h->sigma.assign(sigma, sigma + n_types * n_types);
+    h->rcut.assign(rcut, rcut + n_types * n_types);
+    h->present.assign(present, present + n_types * n_types);
+    h->shift = shift ? 1 : 0;
+    h->skin = skin;
+    auto bail = [&](int rc) {
+        g_create_error = h->err;
+        pisb_destroy(h);
+        return rc;
+    };
+    if (cudaSetDevice(device) != cudaSuccess) return bail(fail(h, PISB_ERR_CUDA, "cudaSetDevice failed"));
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess)
+        return bail(fail(h, PISB_ERR_CUDA, "cudaStreamCreate failed"));
+    if (cudaMalloc((void **)&h->flags, sizeof(int) * FLAG_COUNT) != cudaSuccess ||
+        cudaMalloc((void **)&h->ticket, sizeof(unsigned int)) != cudaSuccess ||
+        cudaHostAlloc((void **)&h->h_flags, sizeof(int) * FLAG_COUNT, cudaHostAllocDefault) != cudaSuccess)
+        return bail(fail(h, PISB_ERR_CUDA, "allocating control words failed"));
+    cudaMemsetAsync(h->flags, 0, sizeof(int) * FLAG_COUNT, h->stream);
+    cudaMemsetAsync(h->ticket, 0, sizeof(unsigned int), h->stream);
+    int rc = build_pair_table(h);
+    if (rc != PISB_OK) return bail(rc);
+    *out = h;
+    return PISB_OK;
+}
+
+int pisb_destroy(pisb_t *h) {
+    if (!h) return PISB_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    dev_free(h, h->xt);
+    dev_free(h, h->s_xt);
+    for (int d = 0; d < 3; ++d) {
+        dev_free(h, h->v[d]);
+        dev_free(h, h->f[d]);
+        dev_free(h, h->g[d]);
+        dev_free(h, h->xb[d]);
+        dev_free(h, h->s_v[d]);
+        dev_free(h, h->s_f[d]);
+    }
+    dev_free(h, h->id);
+    dev_free(h, h->s_id);
+    dev_free(h, h->slot_of_id);
+    dev_free(h, h->cell_of);
+    dev_free(h, h->order);
+    dev_free(h, h->nnbr);
+    dev_free(h, h->nbr);
+    dev_free(h, h->cell_count);
+    dev_free(h, h->cell_start);
+    dev_free(h, h->tile_sum);
+    dev_free(h, h->mass_d);
+    dev_free(h, h->partials);
+    dev_free(h, h->st_pos);
+    dev_free(h, h->st_vel);
+    dev_free(h, h->st_frc);
+    dev_free(h, h->st_types);
+    dev_free(h, h->table_d);
+    dev_free(h, h->thermo_d);
+    if (h->flags) cudaFree(h->flags);
+    if (h->ticket) cudaFree(h->ticket);
+    if (h->h_flags) cudaFreeHost(h->h_flags);
+    if (h->h_thermo) cudaFreeHost(h->h_thermo);
+    if (h->h_stage) cudaFreeHost(h->h_stage);
+    for (auto &e : h->ev_pool) {
+        cudaEventDestroy(e.a);
+        cudaEventDestroy(e.b);
+    }
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return PISB_OK;
+}
+
+int pisb_set_box(pisb_t *h, const double *h9, const double *hinv9, const int *pbc3) {
+    if (!h) return PISB_ERR_INVALID;
+    if (!h9 || !hinv9 || !pbc3) return fail(h, PISB_ERR_INVALID, "NULL box argument");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    BoxDev b{};
+    bool ortho = true;
+    for (int k = 0; k < 9; ++k) {
+        b.h[k] = h9[k];
+        b.hinv[k] = hinv9[k];
+        if (!std::isfinite(h9[k]) || !std::isfinite(hinv9[k])) return fail(h, PISB_ERR_INVALID, "box matrix is not finite");
+        if (k % 4 != 0 && (h9[k] != 0.0 || hinv9[k] != 0.0)) ortho = false;
+    }
+    for (int d = 0; d < 3; ++d) b.pbc[d] = pbc3[d] ? 1 : 0;
+    b.ortho = ortho ? 1 : 0;
+    const bool changed = !h->have_box || std::memcmp(&b, &h->box, sizeof b) != 0;
+    h->box = b;
+    h->have_box = true;
+    if (changed) {
+        h->grid_ok = false;
+        h->list_valid = false;
+        if (h->have_atoms) TRY(setup_grid(h));
+    }
+    return PISB_OK;
+}
+
+int pisb_upload(pisb_t *h, int64_t n, const double *pos, const double *vel, const double *force,
+                const int32_t *types) {
+    if (!h) return PISB_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    TRY(do_upload(h, n, pos, vel, force, types));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));  // host buffers may be reused by the caller
+    return PISB_OK;
+}
+
+int pisb_compute(pisb_t *h, int accumulate, double *pe) {
+    if (!h) return PISB_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    return do_compute(h, accumulate, pe);
+}
+
+int pisb_step_nve(pisb_t *h, double dt, int64_t nsteps, pisb_thermo *out) {
+    if (!h) return PISB_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    return do_step_nve(h, dt, nsteps, out);
+}
+
+int pisb_download(pisb_t *h, double *pos, double *vel, double *force) {
+    if (!h) return PISB_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    return do_download(h, pos, vel, force);
+}
+
+int pisb_thermo_now(pisb_t *h, pisb_thermo *out) {
+    if (!h || !out) return PISB_ERR_INVALID;
+    if (!h->have_atoms) return fail(h, PISB_ERR_STATE, "thermo before upload");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    TRY(reserve_thermo(h, 2));
+    {
+        LaunchScope ls(h, PISB_K_REDUCE);
+        k_observe<<<nblk(h->n, TPB), TPB, 0, h->stream>>>(h->n, h->xt.p, h->v[0].p, h->v[1].p, h->v[2].p, h->f[0].p,
+                                                          h->f[1].p, h->f[2].p, h->mass_d.p, h->partials.p,
+                                                          h->ticket, h->thermo_d.p);
+        TRY(check_launch(h, "k_observe"));
+    }
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_thermo, h->thermo_d.p, sizeof(pisb_thermo), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    *out = h->h_thermo[0];
+    return PISB_OK;
+}
+
+int pisb_verlet_step_nve_host(pisb_t *h, int64_t n, double *pos, double *vel, double *force,
+                              const int32_t *types, double dt, double *pe) {
+    if (!h) return PISB_ERR_INVALID;
+    if (!pos || !vel || !force) return fail(h, PISB_ERR_INVALID, "pos/vel/force must be non-NULL");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    // types are only re-sent when the atom set is new (they cannot change inside the trait call)
+    const bool fresh = !h->have_atoms || h->n != (int)n;
+    if (fresh && !types) return fail(h, PISB_ERR_INVALID, "types is NULL on first call");
+    TRY(do_upload(h, n, pos, vel, force, fresh ? types : nullptr));
+    pisb_thermo th;
+    TRY(do_step_nve(h, dt, 1, &th));
+    TRY(do_download(h, pos, vel, force));
+    if (pe) *pe = th.pe;
+    return PISB_OK;
+}
+
+int pisb_neighbours(pisb_t *h, int32_t *nnbr, int32_t *nbr, int64_t cap_per_atom) {
+    if (!h || !nnbr) return PISB_ERR_INVALID;
+    if (!h->have_atoms || !h->have_box) return fail(h, PISB_ERR_STATE, "neighbours before upload/set_box");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    TRY(ensure_list(h));
+    const int n = h->n;
+    std::vector<int> hn(n), hid(n), hl((size_t)h->kcap * h->npad);
+    CUDA_TRY(h, cudaMemcpyAsync(hn.data(), h->nnbr.p, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(hid.data(), h->id.p, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(hl.data(), h->nbr.p, sizeof(int) * hl.size(), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    int64_t total = 0;
+    for (int s = 0; s < n; ++s) {
+        const int o = hid[s];
+        nnbr[o] = hn[s];
+        total += hn[s];
+        if (nbr) {
+            if (hn[s] > cap_per_atom) return fail(h, PISB_ERR_CAPACITY, fmt("cap_per_atom %lld < list length %d", (long long)cap_per_atom, hn[s]));
+            for (int k = 0; k < hn[s]; ++k) nbr[(size_t)o * cap_per_atom + k] = hid[hl[(size_t)k * h->npad + s]];
+        }
+    }
+    h->total_nbr = total;
+    return PISB_OK;
+}
+
+int pisb_invalidate_list(pisb_t *h) {
+    if (!h) return PISB_ERR_INVALID;
+    h->list_valid = false;
+    return PISB_OK;
+}
+
+int pisb_stats(pisb_t *h, pisb_stats_t *out) {
+    if (!h || !out) return PISB_ERR_INVALID;
+    std::memset(out, 0, sizeof *out);
+    out->n_atoms = h->n;
+    out->n_ghost = 0;
+    for (int d = 0; d < 3; ++d) out->n_cells[d] = h->grid.n[d];
+    out->list_capacity = h->kcap;
+    out->max_neighbours = h->max_nbr;
+    out->total_neighbours = h->total_nbr;
+    out->n_builds = h->n_builds_host;
+    out->n_steps = h->n_steps;
+    out->n_launches = h->n_launches;
+    out->device_bytes = h->device_bytes;
+    return PISB_OK;
+}
+
+int pisb_set_profiling(pisb_t *h, int enable) {
+    if (!h) return PISB_ERR_INVALID;
+    drain_events(h);
+    h->profiling = enable != 0;
+    return PISB_OK;
+}
+
+int pisb_timings(pisb_t *h, double *ms, int64_t *launches) {
+    if (!h) return PISB_ERR_INVALID;
+    cudaSetDevice(h->device);
+    drain_events(h);
+    for (int k = 0; k < PISB_K_COUNT; ++k) {
+        if (ms) ms[k] = h->t_ms[k];
+        if (launches) launches[k] = h->t_n[k];
+    }
+    return PISB_OK;
+}
+
+int pisb_timings_reset(pisb_t *h) {
+    if (!h) return PISB_ERR_INVALID;
+    drain_events(h);
+    for (int k = 0; k < PISB_K_COUNT; ++k) h->t_ms[k] = 0.0, h->t_n[k] = 0;
+    return PISB_OK;
+}
+
+void *pisb_stream(pisb_t *h) { return h ? (void *)h->stream : nullptr; }
+
+int pisb_synchronize(pisb_t *h) {
+    if (!h) return PISB_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return PISB_OK;
+}
+
+int pisb_set_option(pisb_t *h, const char *name, double value) {
+    if (!h || !name) return PISB_ERR_INVALID;
+    if (!std::strcmp(name, "list_capacity")) {
+        h->kcap_user = value > 0 ? (int)value : 0;
+        h->kcap = 0;
+        h->list_valid = false;
+        return PISB_OK;
+    }
+    return fail(h, PISB_ERR_INVALID, fmt("unknown option '%s'", name));
+}
+
+}  // extern "C"

@@ -1,0 +1,250 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on identical
+seeded inputs.  Bars (BASELINE.json north_star): neighbour lists bit-exact as sorted pair sets;
+forces within 1e-10 relative; energy / temperature traces within 1e-9 relative."""
+import numpy as np
+import pytest
+
+from pis_b200 import Atoms, LennardJones, SimulationBox
+from pis_b200.lattice import fcc_argon
+from tests.helpers import RC25, SKIN, argon_pair, csr_rows_sorted, force_rel_err, make_manager, make_oracle
+
+pytestmark = pytest.mark.gpu
+
+FORCE_TOL = 1e-10
+ENERGY_TOL = 1e-9
+
+
+def _jittered(ncell, jitter=0.15, temperature=30.0, seed=7):
+    return fcc_argon(ncell, temperature=temperature, seed=seed, jitter=jitter)
+
+
+@pytest.mark.parametrize("ncell,skin", [(10, 0.0), (10, SKIN), (16, SKIN)])
+def test_compute_potential_parity(ncell, skin):
+    atoms = _jittered(ncell)
+    table = {(1, 1): argon_pair()}
+    orc = make_oracle(atoms, table)
+    pe_ref, f_ref = orc.compute_potential(atoms.positions, atoms.type_ids)
+    mgr = make_manager(skin=skin)
+    pe = mgr.compute_potential(atoms)  # adds into atoms.forces (zeros)
+    assert abs(pe - pe_ref) <= ENERGY_TOL * abs(pe_ref)
+    assert force_rel_err(atoms.forces, f_ref).max() <= FORCE_TOL
+    # Newton's third law on the full-list kernel
+    assert np.abs(atoms.forces.sum(axis=0)).max() < 1e-9
+
+
+def test_compute_potential_accumulates():
+    atoms = _jittered(6)
+    atoms.forces[...] = 1.25
+    mgr = make_manager(skin=SKIN, rc=8.5)
+    orc = make_oracle(atoms, {(1, 1): argon_pair(8.5)})
+    _, f_ref = orc.compute_potential(atoms.positions, atoms.type_ids)
+    mgr.compute_potential(atoms)
+    assert force_rel_err(atoms.forces - 1.25, f_ref).max() <= 1e-9  # 1.25 + f rounding
+
+
+def test_argon4000_lattice_known_answer():
+    """example/argon4000.txt geometry: 54 neighbours/atom, step-0 PE = -6956.99645673589."""
+    atoms = fcc_argon(10, temperature=0.0)
+    mgr = make_manager(skin=0.0, rc=8.5)
+    pe = mgr.compute_potential(atoms)
+    assert abs(pe - (-6956.99645673589)) < 1e-8
+    assert np.abs(atoms.forces).max() < 1e-12
+    rows = mgr.neighbours(atoms.n_atoms)
+    assert all(len(r) == 54 for r in rows)
+
+
+@pytest.mark.parametrize("ncell,skin", [(8, 0.0), (8, SKIN), (12, SKIN)])
+def test_neighbour_list_exact(ncell, skin):
+    atoms = _jittered(ncell, jitter=0.3)
+    table = {(1, 1): argon_pair()}
+    orc = make_oracle(atoms, table)
+    start, nbr = orc.build_neighbour_list(atoms.positions, atoms.type_ids, extra=skin)
+    ref_rows = csr_rows_sorted(start, nbr)
+    mgr = make_manager(skin=skin)
+    mgr.attach(atoms)
+    rows = mgr.neighbours(atoms.n_atoms)
+    assert sum(len(r) for r in rows) == len(nbr)
+    for i, (a, b) in enumerate(zip(rows, ref_rows)):
+        assert np.array_equal(a, b), f"atom {i}"
+
+
+def test_neighbour_list_shell_on_cutoff():
+    """Cutoff is inclusive and evaluated as sqrt(r2) > rc: put an FCC shell exactly on the list cutoff."""
+    atoms = fcc_argon(8, temperature=0.0)
+    a = 5.41
+    rc = a * np.sqrt(1.5)  # 3rd shell distance a*sqrt(3/2); lattice r2 values straddle it by rounding
+    table = {(1, 1): LennardJones(0.238, 3.405, rc, True)}
+    orc = make_oracle(atoms, table)
+    start, nbr = orc.build_neighbour_list(atoms.positions, atoms.type_ids, extra=0.0)
+    mgr = make_manager(skin=0.0, table=table)
+    mgr.attach(atoms)
+    rows = mgr.neighbours(atoms.n_atoms)
+    for a_, b_ in zip(rows, csr_rows_sorted(start, nbr)):
+        assert np.array_equal(a_, b_)
+    pe_ref, f_ref = orc.compute_potential(atoms.positions, atoms.type_ids)
+    pe = mgr.compute()
+    assert abs(pe - pe_ref) <= ENERGY_TOL * abs(pe_ref)
+
+
+def test_drift_is_bit_exact_and_kick_close():
+    """One verlet_step_nve from identical (x, v, F): positions are bit-identical (same arithmetic,
+    same inputs), velocities differ only through the force summation order."""
+    atoms = _jittered(8)
+    table = {(1, 1): argon_pair()}
+    orc = make_oracle(atoms, table)
+    _, f0 = orc.compute_potential(atoms.positions, atoms.type_ids)
+    x, v, f = atoms.positions.copy(), atoms.velocities.copy(), f0.copy()
+    pe_ref = orc.verlet_step_nve(x, v, f, atoms.type_ids, 0.25)
+    atoms.forces[...] = f0
+    mgr = make_manager(skin=SKIN)
+    pe = mgr.verlet_step_nve(atoms, 0.25)
+    assert np.array_equal(atoms.positions, x)
+    assert abs(pe - pe_ref) <= ENERGY_TOL * abs(pe_ref)
+    assert force_rel_err(atoms.forces, f).max() <= FORCE_TOL
+    assert np.abs(atoms.velocities - v).max() <= 1e-13 * max(1.0, np.abs(v).max())
+
+
+def test_nve_trace_parity_1000_steps():
+    """argon4000-sized system, 1000 NVE steps: PE / KE / T traces within 1e-9 relative of the oracle."""
+    atoms = fcc_argon(10, temperature=5.0, seed=12345)
+    table = {(1, 1): argon_pair(8.5)}
+    orc = make_oracle(atoms, table)
+    x, v = atoms.positions.copy(), atoms.velocities.copy()
+    f = np.zeros_like(x)
+    steps = 1000
+    ref = orc.run_nve(x, v, f, atoms.type_ids, 0.25, steps)
+    mgr = make_manager(skin=SKIN, rc=8.5)
+    mgr.attach(atoms)
+    pe0 = mgr.compute()
+    assert abs(pe0 - ref[0, 0]) <= ENERGY_TOL * abs(ref[0, 0])
+    th = mgr.step_nve(0.25, steps)
+    pe_ref, ke_ref, t_ref = ref[1:, 0], ref[1:, 1], ref[1:, 3]
+    assert np.max(np.abs(th["pe"] - pe_ref) / np.abs(pe_ref)) <= ENERGY_TOL
+    assert np.max(np.abs(th["ke"] - ke_ref) / np.abs(ke_ref)) <= ENERGY_TOL
+    t_gpu = np.array([atoms.temerature(k) for k in th["ke"]])
+    assert np.max(np.abs(t_gpu - t_ref) / np.abs(t_ref)) <= ENERGY_TOL
+    # pressure uses tr(X F^T) with wrapped positions (properties.rs:61-65)
+    p_gpu = np.array([atoms.pressure(k, w) for k, w in zip(th["ke"], th["virial_ref"])])
+    assert np.max(np.abs(p_gpu - ref[1:, 4]) / np.maximum(np.abs(ref[1:, 4]), 1e-6)) <= 1e-6
+    # NVE: the Hamiltonian is conserved
+    h = th["pe"] + th["ke"]
+    assert np.abs(h - h[0]).max() <= 2e-4 * abs(h[0])
+
+
+def test_hot_run_rebuilds_and_matches_no_skin():
+    """A hot system triggers list rebuilds; list-with-skin forces == no-list forces at the end."""
+    atoms = fcc_argon(8, temperature=60.0, seed=3, jitter=0.05)
+    mgr = make_manager(skin=SKIN)
+    mgr.attach(atoms)
+    mgr.compute()
+    th = mgr.step_nve(0.25, 300)
+    st = mgr.stats()
+    assert st["n_builds"] >= 3
+    h = th["pe"] + th["ke"]
+    assert np.abs(h - h[0]).max() <= 5e-4 * abs(h[0])
+    mgr.download(atoms)
+    f_skin = atoms.forces.copy()
+    orc = make_oracle(atoms, {(1, 1): argon_pair()})
+    pe_ref, f_ref = orc.compute_potential(atoms.positions, atoms.type_ids)
+    assert force_rel_err(f_skin, f_ref).max() <= FORCE_TOL
+    assert abs(th["pe"][-1] - pe_ref) <= ENERGY_TOL * abs(pe_ref)
+
+
+def test_host_step_equals_resident_step():
+    a1 = _jittered(6, temperature=40.0)
+    a2 = Atoms(a1.type_ids, a1.masses, a1.positions.copy(), a1.sim_box, velocities=a1.velocities.copy())
+    m1, m2 = make_manager(skin=SKIN), make_manager(skin=SKIN)
+    m1.compute_potential(a1)
+    m2.attach(a2)
+    m2.compute()
+    pes = [m1.verlet_step_nve(a1, 0.25) for _ in range(20)]
+    th = m2.step_nve(0.25, 20)
+    m2.download(a2)
+    assert np.allclose(pes, th["pe"], rtol=1e-12, atol=0)
+    assert np.abs(a1.positions - a2.positions).max() < 1e-9
+    assert np.abs(a1.velocities - a2.velocities).max() < 1e-10
+
+
+def test_two_types_and_missing_pair():
+    """Dense per-type-pair table; keys are stored as given and looked up sorted (potential.rs:181-192):
+    (2,1) is never found, so 1-2 pairs are skipped -- like the reference."""
+    atoms = _jittered(6, jitter=0.2)
+    atoms.type_ids[::3] = 2
+    atoms.masses = [39.948, 20.18]
+    for table in (
+        {(1, 1): LennardJones(0.238, 3.405, 8.5), (1, 2): LennardJones(0.15, 3.0, 7.5), (2, 2): LennardJones(0.07, 2.8, 7.0)},
+        {(1, 1): LennardJones(0.238, 3.405, 8.5), (2, 1): LennardJones(0.15, 3.0, 7.5), (2, 2): LennardJones(0.07, 2.8, 7.0)},
+    ):
+        atoms.forces[...] = 0.0
+        orc = make_oracle(atoms, table)
+        pe_ref, f_ref = orc.compute_potential(atoms.positions, atoms.type_ids)
+        mgr = make_manager(skin=0.5, table=table)
+        pe = mgr.compute_potential(atoms)
+        assert abs(pe - pe_ref) <= ENERGY_TOL * abs(pe_ref)
+        assert force_rel_err(atoms.forces, f_ref).max() <= FORCE_TOL
+        start, nbr = orc.build_neighbour_list(atoms.positions, atoms.type_ids, extra=0.5)
+        for a_, b_ in zip(mgr.neighbours(atoms.n_atoms), csr_rows_sorted(start, nbr)):
+            assert np.array_equal(a_, b_)
+
+
+def test_triclinic_box_general_path():
+    """Non-orthorhombic h exercises the full 3x3 mat-vec restatement (NPT makes the box triclinic)."""
+    base = _jittered(6, jitter=0.2)
+    L = base.sim_box.h[0, 0]
+    box = SimulationBox.from_lammps_data(0, L, 0, L, 0, L, xy=3.1, xz=-2.2, yz=1.7)
+    atoms = Atoms(base.type_ids, base.masses, base.positions, box, velocities=base.velocities)
+    table = {(1, 1): argon_pair(8.5)}
+    orc = make_oracle(atoms, table)
+    pe_ref, f_ref = orc.compute_potential(atoms.positions, atoms.type_ids)
+    mgr = make_manager(skin=0.0, rc=8.5)
+    pe = mgr.compute_potential(atoms)
+    assert abs(pe - pe_ref) <= ENERGY_TOL * abs(pe_ref)
+    assert force_rel_err(atoms.forces, f_ref).max() <= FORCE_TOL
+    x, v, f = atoms.positions.copy(), atoms.velocities.copy(), atoms.forces.copy()
+    orc.verlet_step_nve(x, v, f, atoms.type_ids, 0.25)
+    mgr.verlet_step_nve(atoms, 0.25)
+    assert np.abs(atoms.positions - x).max() < 1e-12
+
+
+def test_edge_positions_on_boundary_and_beyond():
+    """Atoms exactly on 0 / L and coordinates >= L (unwrapped step-0 input): same pairs as the oracle."""
+    atoms = fcc_argon(7, temperature=0.0)
+    L = atoms.sim_box.h[0, 0]
+    atoms.positions[5] = [L, 0.3, L]
+    atoms.positions[11] = [L + 1.0, L + 2.5, 0.7]
+    atoms.positions[17] = [0.0, L, 0.0]
+    table = {(1, 1): argon_pair(8.5)}
+    orc = make_oracle(atoms, table)
+    pe_ref, f_ref = orc.compute_potential(atoms.positions, atoms.type_ids)
+    mgr = make_manager(skin=0.0, rc=8.5)
+    pe = mgr.compute_potential(atoms)
+    assert abs(pe - pe_ref) <= ENERGY_TOL * abs(pe_ref)
+    assert force_rel_err(atoms.forces, f_ref).max() <= FORCE_TOL
+
+
+def test_two_atoms_analytic():
+    """u(2^(1/6) sigma) = -eps - u_cut and f = 0 there."""
+    eps, sig, rc = 0.238, 3.405, 8.5
+    L = 40.0
+    r = 2.0 ** (1.0 / 6.0) * sig
+    box = SimulationBox.from_lammps_data(0, L, 0, L, 0, L)
+    atoms = Atoms([1, 1], [39.948], [[1.0, 1.0, 1.0], [1.0 + r, 1.0, 1.0]], box)
+    mgr = make_manager(skin=0.0, rc=rc)
+    pe = mgr.compute_potential(atoms)
+    ucut = 4 * eps * ((sig / rc) ** 12 - (sig / rc) ** 6)
+    assert abs(pe - (-eps - ucut)) < 1e-12
+    assert np.abs(atoms.forces).max() < 1e-10
+
+
+def test_errors():
+    from pis_b200.capi import PisbError
+
+    box = SimulationBox.from_lammps_data(0, 10, 0, 10, 0, 10)  # shorter than 2 cutoffs
+    atoms = Atoms([1, 1], [39.948], [[1.0, 1.0, 1.0], [4.0, 1.0, 1.0]], box)
+    mgr = make_manager(skin=0.0, rc=8.5)
+    with pytest.raises(PisbError):
+        mgr.compute_potential(atoms)
+    atoms2 = fcc_argon(6, temperature=0.0)
+    atoms2.type_ids[3] = 5
+    with pytest.raises(PisbError):
+        make_manager(skin=0.0, rc=8.5).compute_potential(atoms2)
