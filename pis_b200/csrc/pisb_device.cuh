@@ -34,11 +34,12 @@ struct PairDev {
     int pad;
 };
 
-// Read-only 32-byte gather of one atom record (two LDG.E.128.CONSTANT).
+// Read-only 32-byte gather of one atom record as ONE 256-bit request (sm_100 LDG.E.ENL2.256.CONSTANT):
+// the neighbour gathers are L1TEX-request bound, and two 128-bit loads cost two tag passes per sector.
 __device__ __forceinline__ double4 ldg_d4(const double4 *p) {
-    const double2 *q = reinterpret_cast<const double2 *>(p);
-    const double2 a = __ldg(q), b = __ldg(q + 1);
-    return make_double4(a.x, a.y, b.x, b.y);
+    double4 v;
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+    return v;
 }
 
 __device__ __forceinline__ int type_of(double w) { return (int)__double_as_longlong(w); }

@@ -20,12 +20,35 @@ constexpr int TPB_FORCE = 128;  // force / build kernels
 // flags[] (device ints)
 enum { FLAG_REBUILD = 0, FLAG_MAXNBR = 1, FLAG_NBUILDS = 2, FLAG_BADTYPE = 3, FLAG_COUNT = 8 };
 
+// Neighbour list layout: K-tiles of 4.  Entry (k, i) lives at ((k/4)*npad + i)*4 + k%4, so the four
+// neighbours k..k+3 of atom i are one aligned int4 and a warp reads 512 contiguous bytes per tile.
+__host__ __device__ __forceinline__ size_t nbr_at(int k, int i, int npad) {
+    return ((size_t)(k >> 2) * (size_t)npad + (size_t)i) * 4 + (size_t)(k & 3);
+}
+
 struct Grid {
     int n[3];      // cells per dimension
     int lo[3];     // stencil offsets lo..hi per dim (dedupes n<3)
     int hi[3];
     int ncell;
 };
+
+// FP32 shadow of a position for the v2 pre-filter: the WRAPPED coordinate (the filter only needs an
+// approximation consistent with the minimum image) + the type bits in w.
+__device__ __forceinline__ float4 make_xf(const BoxDev &b, const double4 &x) {
+    double c[3] = {x.x, x.y, x.z};
+    if (b.ortho) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            if (b.pbc[d]) {
+                double s = c[d] * b.hinv[4 * d];
+                s -= floor(s);
+                c[d] = b.h[4 * d] * s;
+            }
+        }
+    }
+    return make_float4((float)c[0], (float)c[1], (float)c[2], __int_as_float(type_of(x.w)));
+}
 
 // ------------------------------------------------------------------------------------------------
 // Host AoS <-> device layout.  Replaces nothing in the reference: it is the boundary copy.
@@ -41,6 +64,8 @@ struct LoadArgs {
     int *id;
     int n_types;
     int *flags;
+    float4 *xf;   // written when the current order/list is kept (null otherwise: the rebuild writes it)
+    BoxDev box;
 };
 
 __global__ void __launch_bounds__(TPB) k_load_aos(LoadArgs a) {
@@ -58,6 +83,7 @@ __global__ void __launch_bounds__(TPB) k_load_aos(LoadArgs a) {
     }
     x.w = type_as_double(t);
     a.xt[s] = x;
+    if (a.xf) a.xf[s] = make_xf(a.box, x);
     a.vx[s] = a.vel ? a.vel[3 * (size_t)o] : 0.0;
     a.vy[s] = a.vel ? a.vel[3 * (size_t)o + 1] : 0.0;
     a.vz[s] = a.vel ? a.vel[3 * (size_t)o + 2] : 0.0;
@@ -125,6 +151,7 @@ __global__ void __launch_bounds__(TPB) k_check_displacement(int n, const double4
 struct VVArgs {
     int n;
     double4 *xt;
+    float4 *xf;
     double *vx, *vy, *vz;
     const double *fx, *fy, *fz;  // F(t+dt) for KICK, F(t) for DRIFT
     const double *gx, *gy, *gz;  // F(t) for KICK
@@ -168,6 +195,7 @@ __global__ void __launch_bounds__(TPB) k_vv(VVArgs a) {
             x.z = __dadd_rn(x.z, __dadd_rn(__dmul_rn(vz, a.dt), __dmul_rn(__dmul_rn(az, 0.5), a.dt2)));
             wrap_pos<ORTHO>(a.box, x.x, x.y, x.z);
             a.xt[i] = x;
+            a.xf[i] = make_float4((float)x.x, (float)x.y, (float)x.z, __int_as_float(type_of(x.w)));
             if (a.always_rebuild) {
                 if (i == 0) a.flags[FLAG_REBUILD] = 1;
             } else {
@@ -406,6 +434,8 @@ struct CopyBackArgs {
     int *slot_of_id;
     double *xbx, *xby, *xbz;
     const int *flags;
+    float4 *xf;
+    BoxDev box;
 };
 
 __global__ void __launch_bounds__(TPB) k_copy_back(CopyBackArgs a) {
@@ -414,6 +444,7 @@ __global__ void __launch_bounds__(TPB) k_copy_back(CopyBackArgs a) {
     if (p >= a.n) return;
     double4 x = a.s_xt[p];
     a.xt[p] = x;
+    a.xf[p] = make_xf(a.box, x);
     a.xbx[p] = x.x;
     a.xby[p] = x.y;
     a.xbz[p] = x.z;
@@ -470,7 +501,6 @@ __global__ void __launch_bounds__(TPB_FORCE) k_build_list(BuildArgs a) {
                 cd = a.box.pbc[d] ? cd % (unsigned long long)a.g.n[d] : (unsigned long long)(a.g.n[d] - 1);
             c[d] = (int)cd;
         }
-        int *row = a.nbr + i;
         for (int dz = a.g.lo[2]; dz <= a.g.hi[2]; ++dz) {
             int cz = c[2] + dz;
             if (cz < 0 || cz >= a.g.n[2]) {
@@ -508,7 +538,7 @@ __global__ void __launch_bounds__(TPB_FORCE) k_build_list(BuildArgs a) {
                             t_list = a.pair0.t_list;
                         }
                         if (r2 > t_list) continue;
-                        if (cnt < a.kcap) row[(size_t)cnt * a.npad] = j;
+                        if (cnt < a.kcap) a.nbr[nbr_at(cnt, i, a.npad)] = j;
                         ++cnt;
                     }
                 }
@@ -559,12 +589,11 @@ __global__ void __launch_bounds__(TPB_FORCE) k_force(ForceArgs a) {
         const double4 xi = a.xt[i];
         const int ti = MULTI ? type_of(xi.w) : 1;
         const int nn = a.nnbr[i];
-        const int *row = a.nbr + i;
         double fx = 0.0, fy = 0.0, fz = 0.0, pe = 0.0, vir = 0.0;
-        int jn = nn > 0 ? __ldg(row) : 0;
+        int jn = nn > 0 ? __ldg(a.nbr + nbr_at(0, i, a.npad)) : 0;
         for (int k = 0; k < nn; ++k) {
             const int j = jn;
-            if (k + 1 < nn) jn = __ldg(row + (size_t)(k + 1) * a.npad);
+            if (k + 1 < nn) jn = __ldg(a.nbr + nbr_at(k + 1, i, a.npad));
             const double4 xj = ldg_d4(&a.xt[j]);
             double dx = __dsub_rn(xj.x, xi.x), dy = __dsub_rn(xj.y, xi.y), dz = __dsub_rn(xj.z, xi.z);
             min_image<ORTHO>(a.box, dx, dy, dz);
@@ -603,6 +632,429 @@ __global__ void __launch_bounds__(TPB_FORCE) k_force(ForceArgs a) {
         if (q == 0) th->pe = s / 2.0;
         else th->virial_pair = s / 2.0;
     });
+}
+
+// ================================================================================================
+// v2 kernels (orthorhombic boxes): FP32 pre-filter + per-thread compaction + exact FP64 physics.
+//
+// B200 has 128 FP32 lanes but only 64 FP64 lanes per SM, FRND/F2F run at quarter rate, and the
+// exact cutoff test costs ~33 FP64 issue slots per listed pair.  So the in/out decision is made on
+// the otherwise idle FP32 pipe from a float4 copy of the (wrapped) positions:
+//     r2f > hi  -> certainly outside        r2f < lo -> certainly inside
+//     otherwise (a relative guard band of a few 1e-4 around the threshold, sized on the host from
+//     the FP32 error bound (35 L/rc + 8) 2^-24) -> the exact FP64 reference predicate decides.
+// The decision is therefore bit-identical to the reference's `rij.norm() > rcut` for every pair.
+// Pairs found inside are compacted into a per-thread shared-memory queue and evaluated in a second,
+// divergence-free FP64 loop with the reference's operation order (per-pair terms stay bit-identical;
+// rint-by-magic-constant replaces round(): ties (|s| = 0.5) only occur at |d| = L/2 >= rc + skin,
+// i.e. never for an in-range pair).  Warps whose atoms all sit farther than rc+2 skin from every
+// periodic face skip the image search (round(s) == 0 exactly).
+// ================================================================================================
+struct BoxF {
+    float L[3], invL[3];
+    float margin;  // rc_list + skin: atoms farther than this from every face need no image search
+    int pbc[3];
+};
+
+struct PairF {
+    float lo_rc, hi_rc, lo_list, hi_list;
+};
+
+constexpr int QCAP = 64;  // compaction queue entries per thread
+
+__device__ __forceinline__ float rint_magic_f(float s) { return __fsub_rn(__fadd_rn(s, 12582912.0f), 12582912.0f); }
+__device__ __forceinline__ double rint_magic_d(double s) {
+    return __dsub_rn(__dadd_rn(s, 6755399441055744.0), 6755399441055744.0);
+}
+
+template <bool IMAGE>
+__device__ __forceinline__ float r2_f32(const BoxF &b, const float4 &xi, const float4 &xj) {
+    float dx = xj.x - xi.x, dy = xj.y - xi.y, dz = xj.z - xi.z;
+    if (IMAGE) {
+        if (b.pbc[0]) dx = fmaf(-rint_magic_f(dx * b.invL[0]), b.L[0], dx);
+        if (b.pbc[1]) dy = fmaf(-rint_magic_f(dy * b.invL[1]), b.L[1], dy);
+        if (b.pbc[2]) dz = fmaf(-rint_magic_f(dz * b.invL[2]), b.L[2], dz);
+    }
+    return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+}
+
+// exact reference r2 (orthorhombic), true round(): used in the guard band
+__device__ __forceinline__ double r2_exact_ortho(const BoxDev &b, const double4 &xi, const double4 &xj) {
+    double dx = __dsub_rn(xj.x, xi.x), dy = __dsub_rn(xj.y, xi.y), dz = __dsub_rn(xj.z, xi.z);
+    min_image<true>(b, dx, dy, dz);
+    return norm2(dx, dy, dz);
+}
+
+// reference displacement for a pair known to be in range (no ties possible): magic rint
+template <bool IMAGE>
+__device__ __forceinline__ void disp_inrange_ortho(const BoxDev &b, const double4 &xi, const double4 &xj,
+                                                   double &dx, double &dy, double &dz) {
+    dx = __dsub_rn(xj.x, xi.x);
+    dy = __dsub_rn(xj.y, xi.y);
+    dz = __dsub_rn(xj.z, xi.z);
+    double sx = __dmul_rn(b.hinv[0], dx), sy = __dmul_rn(b.hinv[4], dy), sz = __dmul_rn(b.hinv[8], dz);
+    if (IMAGE) {
+        if (b.pbc[0]) sx = __dsub_rn(sx, rint_magic_d(sx));
+        if (b.pbc[1]) sy = __dsub_rn(sy, rint_magic_d(sy));
+        if (b.pbc[2]) sz = __dsub_rn(sz, rint_magic_d(sz));
+    }
+    dx = __dmul_rn(b.h[0], sx);
+    dy = __dmul_rn(b.h[4], sy);
+    dz = __dmul_rn(b.h[8], sz);
+}
+
+__device__ __forceinline__ bool is_interior(const BoxF &b, const float4 &x) {
+    bool in = true;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const float c = d == 0 ? x.x : (d == 1 ? x.y : x.z);
+        if (b.pbc[d]) in = in && (c >= b.margin) && (c <= b.L[d] - b.margin);
+    }
+    return in;
+}
+
+struct Force2Args {
+    int n, npad;
+    const double4 *xt;
+    const float4 *xf;
+    const int *nbr;
+    const int *nnbr;
+    BoxDev box;
+    BoxF boxf;
+    PairDev pair0;
+    PairF pairf0;
+    const PairDev *table;
+    const PairF *tablef;
+    int n_types;
+    const double *ax, *ay, *az;
+    double *fx, *fy, *fz;
+    double *partials;
+    unsigned int *ticket;
+    pisb_thermo *thermo;
+};
+
+// One in-range pair, reference operation order (bit-identical per-pair terms).
+template <bool MULTI, bool IMAGE>
+__device__ __forceinline__ void pair_terms(const BoxDev &box, const PairDev &pair0, const PairDev *table, int n_types,
+                                           int ti, const double4 &xi, const double4 &xj, double &dx, double &dy,
+                                           double &dz, double &r2, double &u, double &fs) {
+    disp_inrange_ortho<IMAGE>(box, xi, xj, dx, dy, dz);
+    r2 = norm2(dx, dy, dz);
+    if (MULTI) {
+        const int tj = type_of(xj.w);
+        const PairDev p = table[(min(ti, tj) - 1) * n_types + (max(ti, tj) - 1)];
+        lj_pair(p, r2, u, fs);
+    } else {
+        lj_pair(pair0, r2, u, fs);
+    }
+}
+
+#define PISB_ACCUM(dx, dy, dz, r2, u, fs)        \
+    do {                                         \
+        fx = __dsub_rn(fx, __dmul_rn(fs, dx));   \
+        fy = __dsub_rn(fy, __dmul_rn(fs, dy));   \
+        fz = __dsub_rn(fz, __dmul_rn(fs, dz));   \
+        pe = __dadd_rn(pe, u);                   \
+        vir = fma(fs, r2, vir);                  \
+    } while (0)
+
+constexpr int FU = 4;  // phase-1 unroll: independent index loads + gathers in flight per thread
+
+template <bool MULTI, bool IMAGE>
+__device__ __forceinline__ void force2_body(const Force2Args &a, int i, int (*q)[TPB_FORCE], double &fx, double &fy,
+                                            double &fz, double &pe, double &vir) {
+    const double4 xi = a.xt[i];
+    const float4 xif = a.xf[i];
+    const int ti = MULTI ? __float_as_int(xif.w) : 1;
+    const int nn = a.nnbr[i];
+    const int tid = threadIdx.x;
+    int k = 0;
+    while (true) {
+        // ---- phase 1: FP32 filter, FU neighbours at a time; compact the in-range ones ----
+        int cnt = 0;
+        while (k < nn && cnt <= QCAP - FU) {
+            int j[FU];
+            float4 xjf[FU];
+#pragma unroll
+            {
+                const int4 t = __ldg(reinterpret_cast<const int4 *>(a.nbr) + ((size_t)(k >> 2) * a.npad + i));
+                j[0] = t.x;
+                j[1] = (k + 1 < nn) ? t.y : i;
+                j[2] = (k + 2 < nn) ? t.z : i;
+                j[3] = (k + 3 < nn) ? t.w : i;
+            }
+#pragma unroll
+            for (int u = 0; u < FU; ++u) xjf[u] = __ldg(&a.xf[j[u]]);
+#pragma unroll
+            for (int u = 0; u < FU; ++u) {
+                const float r2f = r2_f32<IMAGE>(a.boxf, xif, xjf[u]);
+                PairF pf;
+                int pidx = 0;
+                if (MULTI) {
+                    const int tj = __float_as_int(xjf[u].w);
+                    pidx = (min(ti, tj) - 1) * a.n_types + (max(ti, tj) - 1);
+                    pf = a.tablef[pidx];
+                } else {
+                    pf = a.pairf0;
+                }
+                bool in = r2f < pf.lo_rc;  // lo_rc < 0 encodes "pair absent"
+                if (!in && r2f <= pf.hi_rc) {
+                    const double4 xj = ldg_d4(&a.xt[j[u]]);
+                    const double t_rc = MULTI ? a.table[pidx].t_rc : a.pair0.t_rc;
+                    in = !(r2_exact_ortho(a.box, xi, xj) > t_rc);
+                }
+                if (in && (k + u < nn)) {
+                    q[cnt][tid] = j[u];
+                    ++cnt;
+                }
+            }
+            k += FU;
+        }
+        // ---- phase 2: exact FP64 pair terms, two independent chains per iteration ----
+        int c = 0;
+        for (; c + 1 < cnt; c += 2) {
+            const int j0 = q[c][tid], j1 = q[c + 1][tid];
+            const double4 x0 = ldg_d4(&a.xt[j0]);
+            const double4 x1 = ldg_d4(&a.xt[j1]);
+            double dx0, dy0, dz0, r20, u0, fs0, dx1, dy1, dz1, r21, u1, fs1;
+            pair_terms<MULTI, IMAGE>(a.box, a.pair0, a.table, a.n_types, ti, xi, x0, dx0, dy0, dz0, r20, u0, fs0);
+            pair_terms<MULTI, IMAGE>(a.box, a.pair0, a.table, a.n_types, ti, xi, x1, dx1, dy1, dz1, r21, u1, fs1);
+            PISB_ACCUM(dx0, dy0, dz0, r20, u0, fs0);
+            PISB_ACCUM(dx1, dy1, dz1, r21, u1, fs1);
+        }
+        if (c < cnt) {
+            const double4 x0 = ldg_d4(&a.xt[q[c][tid]]);
+            double dx0, dy0, dz0, r20, u0, fs0;
+            pair_terms<MULTI, IMAGE>(a.box, a.pair0, a.table, a.n_types, ti, xi, x0, dx0, dy0, dz0, r20, u0, fs0);
+            PISB_ACCUM(dx0, dy0, dz0, r20, u0, fs0);
+        }
+        if (k >= nn) break;
+    }
+}
+
+// v3: all-FP64 (no pre-filter, no queue, L1 stays a cache) with the latency fixed: the list is read
+// as one int4 per 4 neighbours and prefetched one tile ahead (the index stream comes from DRAM), four
+// gathers are in flight per thread, rint is the magic-constant form and interior warps skip the image
+// search.  Same results as v1/v2, bit for bit.
+template <bool MULTI, bool IMAGE>
+__device__ __forceinline__ void force3_body(const Force2Args &a, int i, double &fx, double &fy, double &fz, double &pe,
+                                            double &vir) {
+    const double4 xi = a.xt[i];
+    const int ti = MULTI ? type_of(xi.w) : 1;
+    const int nn = a.nnbr[i];
+    const int4 *tiles = reinterpret_cast<const int4 *>(a.nbr) + i;
+    int4 cur = nn > 0 ? __ldg(tiles) : make_int4(i, i, i, i);
+    for (int k = 0; k < nn; k += 4) {
+        int4 nxt = cur;
+        if (k + 4 < nn) nxt = __ldg(tiles + (size_t)((k >> 2) + 1) * a.npad);
+        int j[4] = {cur.x, cur.y, cur.z, cur.w};
+        bool in[4];
+        double4 xj[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            in[u] = k + u < nn;
+            if (!in[u]) j[u] = i;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) xj[u] = ldg_d4(&a.xt[j[u]]);
+        double dx[4], dy[4], dz[4], r2[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            disp_inrange_ortho<IMAGE>(a.box, xi, xj[u], dx[u], dy[u], dz[u]);
+            r2[u] = norm2(dx[u], dy[u], dz[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            PairDev p = a.pair0;
+            if (MULTI) {
+                const int tj = type_of(xj[u].w);
+                p = a.table[(min(ti, tj) - 1) * a.n_types + (max(ti, tj) - 1)];
+                in[u] = in[u] && p.present;
+            }
+            if (in[u] && !(r2[u] > p.t_rc)) {
+                double uu, fs;
+                lj_pair(p, r2[u], uu, fs);
+                PISB_ACCUM(dx[u], dy[u], dz[u], r2[u], uu, fs);
+            }
+        }
+        cur = nxt;
+    }
+}
+
+template <bool MULTI>
+__global__ void __launch_bounds__(TPB_FORCE) k_force_v3(Force2Args a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double red[2] = {0.0, 0.0};
+    const bool active = i < a.n;
+    bool interior = true;
+    if (active) interior = is_interior(a.boxf, a.xf[i]);
+    const bool warp_interior = __all_sync(0xffffffffu, interior);
+    if (active) {
+        double fx = 0.0, fy = 0.0, fz = 0.0, pe = 0.0, vir = 0.0;
+        if (warp_interior) force3_body<MULTI, false>(a, i, fx, fy, fz, pe, vir);
+        else force3_body<MULTI, true>(a, i, fx, fy, fz, pe, vir);
+        if (a.ax) {
+            fx += a.ax[i];
+            fy += a.ay[i];
+            fz += a.az[i];
+        }
+        a.fx[i] = fx;
+        a.fy[i] = fy;
+        a.fz[i] = fz;
+        red[0] = pe;
+        red[1] = vir;
+    }
+    pisb_thermo *th = a.thermo;
+    block_reduce_finalize<2, TPB_FORCE>(red, a.partials, a.ticket, [&](int qq, double s) {
+        if (qq == 0) th->pe = s / 2.0;
+        else th->virial_pair = s / 2.0;
+    });
+}
+
+template <bool MULTI>
+__global__ void __launch_bounds__(TPB_FORCE) k_force_v2(Force2Args a) {
+    __shared__ int s_q[QCAP][TPB_FORCE];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double red[2] = {0.0, 0.0};
+    const bool active = i < a.n;
+    bool interior = true;
+    if (active) interior = is_interior(a.boxf, a.xf[i]);
+    const bool warp_interior = __all_sync(0xffffffffu, interior);
+    if (active) {
+        double fx = 0.0, fy = 0.0, fz = 0.0, pe = 0.0, vir = 0.0;
+        if (warp_interior) force2_body<MULTI, false>(a, i, s_q, fx, fy, fz, pe, vir);
+        else force2_body<MULTI, true>(a, i, s_q, fx, fy, fz, pe, vir);
+        if (a.ax) {
+            fx += a.ax[i];
+            fy += a.ay[i];
+            fz += a.az[i];
+        }
+        a.fx[i] = fx;
+        a.fy[i] = fy;
+        a.fz[i] = fz;
+        red[0] = pe;
+        red[1] = vir;
+    }
+    pisb_thermo *th = a.thermo;
+    block_reduce_finalize<2, TPB_FORCE>(red, a.partials, a.ticket, [&](int qq, double s) {
+        if (qq == 0) th->pe = s / 2.0;
+        else th->virial_pair = s / 2.0;
+    });
+}
+
+struct Build2Args {
+    int n, npad, kcap;
+    const double4 *xt;
+    const float4 *xf;
+    const int *cell_start;
+    BoxDev box;
+    BoxF boxf;
+    Grid g;
+    PairDev pair0;
+    PairF pairf0;
+    const PairDev *table;
+    const PairF *tablef;
+    int n_types;
+    int *nbr;
+    int *nnbr;
+    int *flags;
+};
+
+template <bool MULTI, bool IMAGE>
+__device__ __forceinline__ int build2_body(const Build2Args &a, int i) {
+    int cnt = 0;
+    const double4 xi = a.xt[i];
+    const float4 xif = a.xf[i];
+    const int ti = MULTI ? __float_as_int(xif.w) : 1;
+    double s[3];
+    matvec<true>(a.box.hinv, xi.x, xi.y, xi.z, s[0], s[1], s[2]);
+    int c[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        double sd = s[d];
+        if (a.box.pbc[d]) sd = sd - floor(sd);
+        unsigned long long cd = __double2ull_rz(floor(sd * (double)a.g.n[d]));
+        if (cd >= (unsigned long long)a.g.n[d])
+            cd = a.box.pbc[d] ? cd % (unsigned long long)a.g.n[d] : (unsigned long long)(a.g.n[d] - 1);
+        c[d] = (int)cd;
+    }
+    int *const tile0 = a.nbr + (size_t)i * 4;
+    const size_t tile_stride = (size_t)a.npad * 4;
+    auto test = [&](int jj, const float4 &xjf) {
+        const float r2f = r2_f32<IMAGE>(a.boxf, xif, xjf);
+        PairF pf;
+        int pidx = 0;
+        if (MULTI) {
+            const int tj = __float_as_int(xjf.w);
+            pidx = (min(ti, tj) - 1) * a.n_types + (max(ti, tj) - 1);
+            pf = a.tablef[pidx];
+        } else {
+            pf = a.pairf0;
+        }
+        bool in = r2f < pf.lo_list;
+        if (!in && r2f <= pf.hi_list) {  // guard band: the exact FP64 reference predicate decides
+            const double4 xj = ldg_d4(&a.xt[jj]);
+            const double t_list = MULTI ? a.table[pidx].t_list : a.pair0.t_list;
+            in = !(r2_exact_ortho(a.box, xi, xj) > t_list);
+        }
+        if (in && jj != i) {
+            if (cnt < a.kcap) tile0[(size_t)(cnt >> 2) * tile_stride + (cnt & 3)] = jj;
+            ++cnt;
+        }
+    };
+    // candidates of a contiguous slot range [jb, je): 4 independent loads in flight, scalar tail
+    auto scan = [&](int jb, int je) {
+        int j = jb;
+        for (; j + 4 <= je; j += 4) {
+            float4 xjf[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) xjf[u] = __ldg(&a.xf[j + u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) test(j + u, xjf[u]);
+        }
+        for (; j < je; ++j) test(j, __ldg(&a.xf[j]));
+    };
+    const int nx = a.g.n[0];
+    for (int dz = a.g.lo[2]; dz <= a.g.hi[2]; ++dz) {
+        int cz = c[2] + dz;
+        if (cz < 0) cz += a.g.n[2];
+        else if (cz >= a.g.n[2]) cz -= a.g.n[2];
+        for (int dy = a.g.lo[1]; dy <= a.g.hi[1]; ++dy) {
+            int cy = c[1] + dy;
+            if (cy < 0) cy += a.g.n[1];
+            else if (cy >= a.g.n[1]) cy -= a.g.n[1];
+            const int rb = (cz * a.g.n[1] + cy) * nx;
+            // the x-neighbour cells of one row are consecutive slots: same visiting order as
+            // dx = lo..hi with periodic wrap (wrapped-low part, main part, wrapped-high part)
+            int xlo = c[0] + a.g.lo[0];
+            const int xhi = c[0] + a.g.hi[0];
+            if (xlo < 0) {
+                scan(__ldg(&a.cell_start[rb + xlo + nx]), __ldg(&a.cell_start[rb + nx]));
+                xlo = 0;
+            }
+            const int xhi_main = min(xhi, nx - 1);
+            scan(__ldg(&a.cell_start[rb + xlo]), __ldg(&a.cell_start[rb + xhi_main + 1]));
+            if (xhi >= nx) scan(__ldg(&a.cell_start[rb]), __ldg(&a.cell_start[rb + xhi - nx + 1]));
+        }
+    }
+    a.nnbr[i] = cnt < a.kcap ? cnt : a.kcap;
+    return cnt;
+}
+
+template <bool MULTI>
+__global__ void __launch_bounds__(TPB_FORCE) k_build_list_v2(Build2Args a) {
+    if (a.flags[FLAG_REBUILD] == 0) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = i < a.n;
+    bool interior = true;
+    if (active) interior = is_interior(a.boxf, a.xf[i]);
+    const bool warp_interior = __all_sync(0xffffffffu, interior);
+    int cnt = 0;
+    if (active) cnt = warp_interior ? build2_body<MULTI, false>(a, i) : build2_body<MULTI, true>(a, i);
+    int m = cnt;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_down_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(&a.flags[FLAG_MAXNBR], m);
 }
 
 }  // namespace pisb

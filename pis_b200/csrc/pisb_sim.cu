@@ -59,6 +59,11 @@ struct pisb_handle {
     double skin = 0.0;
     double max_rcut = 0.0;
     std::vector<PairDev> pairs;
+    std::vector<PairF> pairsf;
+    BoxF boxf{};
+    int force_variant = 0;  // 0 = auto (v3 when orthorhombic + fully periodic, else v1), 1 = v1, 2 = v2, 3 = v3
+    int build_variant = 0;
+    int cell_div = 0;  // cells per list cutoff per dimension: 0 = auto, 1 = reference-sized cells, 2 = half-size cells
 
     // box / grid
     BoxDev box{};
@@ -75,6 +80,8 @@ struct pisb_handle {
 
     // device arrays
     DevBuf<double4> xt, s_xt;
+    DevBuf<float4> xf;
+    DevBuf<PairF> tablef_d;
     DevBuf<double> v[3], f[3], g[3], xb[3], s_v[3], s_f[3];
     DevBuf<int> id, s_id, slot_of_id, cell_of, order, nnbr, nbr;
     DevBuf<int> cell_count, cell_start, tile_sum;
@@ -235,6 +242,54 @@ int build_pair_table(pisb_t *h) {
     return PISB_OK;
 }
 
+// FP32 pre-filter constants (v2 kernels): guard band from the FP32 error bound
+//   |r2f - r2| / r2 <= (17.4 L/r + 4) 2^-24   (positions rounded to f32 in [0, L], image shift by fl32(L))
+// doubled for safety.  lo/hi are rounded outwards so the band can only grow.
+float f32_below(double v) {
+    float f = (float)v;
+    if ((double)f > v) f = std::nextafterf(f, -INFINITY);
+    return f;
+}
+float f32_above(double v) {
+    float f = (float)v;
+    if ((double)f < v) f = std::nextafterf(f, INFINITY);
+    return f;
+}
+
+bool v2_possible(const pisb_t *h) {
+    return h->have_box && h->box.ortho && h->box.pbc[0] && h->box.pbc[1] && h->box.pbc[2];
+}
+
+int setup_filter(pisb_t *h) {
+    if (!h->have_box) return PISB_OK;
+    const int nt = h->n_types;
+    double lmax = 0.0;
+    for (int d = 0; d < 3; ++d) {
+        h->boxf.L[d] = (float)h->box.h[4 * d];
+        h->boxf.invL[d] = (float)h->box.hinv[4 * d];
+        h->boxf.pbc[d] = h->box.pbc[d];
+        lmax = std::max(lmax, std::fabs(h->box.h[4 * d]));
+    }
+    h->boxf.margin = f32_above((h->max_rcut + 2.0 * h->skin) * 1.0001);
+    h->pairsf.assign((size_t)nt * nt, PairF{-1.f, -1.f, -1.f, -1.f});
+    for (int k = 0; k < nt * nt; ++k) {
+        if (!h->pairs[k].present) continue;
+        const double rc = h->rcut[k], rl = rc + h->skin;
+        const double band_rc = (35.0 * lmax / rc + 8.0) * std::ldexp(1.0, -24);
+        const double band_l = (35.0 * lmax / rl + 8.0) * std::ldexp(1.0, -24);
+        PairF &f = h->pairsf[k];
+        f.lo_rc = f32_below(h->pairs[k].t_rc * (1.0 - band_rc));
+        f.hi_rc = f32_above(h->pairs[k].t_rc * (1.0 + band_rc));
+        f.lo_list = f32_below(h->pairs[k].t_list * (1.0 - band_l));
+        f.hi_list = f32_above(h->pairs[k].t_list * (1.0 + band_l));
+    }
+    TRY(dev_reserve(h, h->tablef_d, (size_t)nt * nt));
+    CUDA_TRY(h, cudaMemcpyAsync(h->tablef_d.p, h->pairsf.data(), sizeof(PairF) * nt * nt, cudaMemcpyHostToDevice,
+                                h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return PISB_OK;
+}
+
 // Cell grid: n_d = max(1, floor(|h col d| / (max_rcut + skin))) -- Atoms::divide_into_cells
 // (src/atoms/neighbour_list.rs:45-57) with rcut := max_rcut + skin; capped so that the cell count
 // stays O(N) for dilute systems (a coarser grid is still correct: cell edge >= list cutoff).
@@ -244,21 +299,37 @@ int setup_grid(pisb_t *h) {
     const double rc_list = h->max_rcut + h->skin;
     if (!(rc_list > 0.0)) return fail(h, PISB_ERR_INVALID, "no pair potential present (max_rcut = 0)");
     Grid g{};
+    // Half-size cells (edge >= rc_list/2, 5^3 stencil) cut the candidate volume from 27 to 15.6 rc_list^3.
+    // Only with the range-scanning v2 build and when every dimension has >= 5 such cells.
+    int div = h->cell_div == 0 ? 1 : h->cell_div;  // auto = 1 (half-size cells measured no faster)
+    if (div < 1) div = 1;
+    if (div > 2) div = 2;
+    if (!(h->build_variant == 2 || (h->build_variant == 0 && v2_possible(h)))) div = 1;
+    const int64_t cell_cap = std::max<int64_t>(4 * (int64_t)h->n + 1024, 27);
+    double prod = 1.0;
+    for (int d = 0; d < 3 && div > 1; ++d) {
+        const double *c = &h->box.h[d * 3];
+        const double len = std::sqrt((c[0] * c[0] + c[1] * c[1]) + c[2] * c[2]);
+        const double nd = std::floor(len / (rc_list / div));
+        if (nd < 2 * div + 1 || nd > 2048.0) div = 1;
+        prod *= nd;
+    }
+    if (div > 1 && prod > (double)cell_cap) div = 1;  // dilute system: keep the cell count O(N)
     for (int d = 0; d < 3; ++d) {
         const double *c = &h->box.h[d * 3];
         const double len = std::sqrt((c[0] * c[0] + c[1] * c[1]) + c[2] * c[2]);
         double nd = std::floor(len / rc_list);
         if (!(nd >= 1.0)) nd = 1.0;
-        if (nd > 1024.0) nd = 1024.0;
+        if (div > 1) nd = std::floor(len / (rc_list / div));
+        if (nd > 2048.0) nd = 2048.0;
         g.n[d] = (int)nd;
-        if (h->box.pbc[d] && g.n[d] < 2)
+        if (h->box.pbc[d] && g.n[d] < 2 * div)
             return fail(h, PISB_ERR_INVALID,
                         fmt("box edge %d (%.6g) is shorter than 2 x (rcut + skin) = %.6g: the single-image "
                             "minimum-image convention of the reference (simulation_box.rs:17-27) is invalid",
                             d, len, 2.0 * rc_list));
     }
-    const int64_t cell_cap = std::max<int64_t>(4 * (int64_t)h->n + 1024, 27);
-    while ((int64_t)g.n[0] * g.n[1] * g.n[2] > cell_cap) {
+    while (div == 1 && (int64_t)g.n[0] * g.n[1] * g.n[2] > cell_cap) {
         int dmax = 0;
         for (int d = 1; d < 3; ++d)
             if (g.n[d] > g.n[dmax]) dmax = d;
@@ -267,7 +338,8 @@ int setup_grid(pisb_t *h) {
     }
     for (int d = 0; d < 3; ++d) {
         // unique stencil offsets (the reference double-counts when n < 3: SURVEY appendix A.1)
-        if (g.n[d] == 1) g.lo[d] = 0, g.hi[d] = 0;
+        if (div > 1) g.lo[d] = -div, g.hi[d] = div;
+        else if (g.n[d] == 1) g.lo[d] = 0, g.hi[d] = 0;
         else if (g.n[d] == 2) g.lo[d] = 0, g.hi[d] = 1;
         else g.lo[d] = -1, g.hi[d] = 1;
     }
@@ -276,6 +348,7 @@ int setup_grid(pisb_t *h) {
     TRY(dev_reserve(h, h->cell_count, (size_t)g.ncell + 1));
     TRY(dev_reserve(h, h->cell_start, (size_t)g.ncell + 1));
     TRY(dev_reserve(h, h->tile_sum, (size_t)nblk(g.ncell, SCAN_TILE) + 1));
+    TRY(setup_filter(h));
     h->grid_ok = true;
     h->list_valid = false;
     return PISB_OK;
@@ -297,6 +370,7 @@ int estimate_kcap(pisb_t *h) {
 int reserve_atoms(pisb_t *h, int n) {
     const size_t cap = (size_t)n;
     TRY(dev_reserve(h, h->xt, cap));
+    TRY(dev_reserve(h, h->xf, cap));
     TRY(dev_reserve(h, h->s_xt, cap));
     for (int d = 0; d < 3; ++d) {
         TRY(dev_reserve(h, h->v[d], cap));
@@ -318,6 +392,7 @@ int reserve_atoms(pisb_t *h, int n) {
 
 int reserve_list(pisb_t *h) {
     h->npad = (h->n + 31) / 32 * 32;
+    h->kcap = (h->kcap + 3) / 4 * 4;  // whole K-tiles of 4
     TRY(dev_reserve(h, h->nbr, (size_t)h->kcap * (size_t)h->npad));
     return PISB_OK;
 }
@@ -366,7 +441,7 @@ int launch_rebuild_chain(pisb_t *h) {
         k_permute<<<nblk(n, TPB), TPB, 0, st>>>(pa);
         CopyBackArgs ca{n, h->s_xt.p, h->s_v[0].p, h->s_v[1].p, h->s_v[2].p, h->s_f[0].p, h->s_f[1].p, h->s_f[2].p,
                         h->s_id.p, h->xt.p, h->v[0].p, h->v[1].p, h->v[2].p, h->f[0].p, h->f[1].p, h->f[2].p,
-                        h->id.p, h->slot_of_id.p, h->xb[0].p, h->xb[1].p, h->xb[2].p, h->flags};
+                        h->id.p, h->slot_of_id.p, h->xb[0].p, h->xb[1].p, h->xb[2].p, h->flags, h->xf.p, h->box};
         k_copy_back<<<nblk(n, TPB), TPB, 0, st>>>(ca);
         h->n_launches += 6;
     }
@@ -376,7 +451,14 @@ int launch_rebuild_chain(pisb_t *h) {
                      h->n_types, h->nbr.p, h->nnbr.p, h->flags};
         const bool multi = h->n_types > 1;
         const int nb = nblk(n, TPB_FORCE);
-        if (h->box.ortho) {
+        const bool v2 = h->build_variant == 2 || (h->build_variant == 0 && v2_possible(h));
+        if (v2) {
+            if (!v2_possible(h)) return fail(h, PISB_ERR_INVALID, "build_variant 2 needs an orthorhombic, fully periodic box");
+            Build2Args b2{n, h->npad, h->kcap, h->xt.p, h->xf.p, h->cell_start.p, h->box, h->boxf, g, h->pairs[0],
+                          h->pairsf[0], h->table_d.p, h->tablef_d.p, h->n_types, h->nbr.p, h->nnbr.p, h->flags};
+            if (multi) k_build_list_v2<true><<<nb, TPB_FORCE, 0, st>>>(b2);
+            else k_build_list_v2<false><<<nb, TPB_FORCE, 0, st>>>(b2);
+        } else if (h->box.ortho) {
             if (multi) k_build_list<true, true><<<nb, TPB_FORCE, 0, st>>>(ba);
             else k_build_list<true, false><<<nb, TPB_FORCE, 0, st>>>(ba);
         } else {
@@ -398,7 +480,20 @@ int launch_force(pisb_t *h, double *const out[3], const double *const acc[3], pi
     const bool multi = h->n_types > 1;
     const int nb = nblk(h->n, TPB_FORCE);
     cudaStream_t st = h->stream;
-    if (h->box.ortho) {
+    const bool v2 = h->force_variant >= 2 || (h->force_variant == 0 && v2_possible(h));
+    if (v2) {
+        if (!v2_possible(h)) return fail(h, PISB_ERR_INVALID, "force_variant 2/3 needs an orthorhombic, fully periodic box");
+        Force2Args f2{h->n, h->npad, h->xt.p, h->xf.p, h->nbr.p, h->nnbr.p, h->box, h->boxf, h->pairs[0], h->pairsf[0],
+                      h->table_d.p, h->tablef_d.p, h->n_types, fa.ax, fa.ay, fa.az, out[0], out[1], out[2],
+                      h->partials.p, h->ticket, rec};
+        if (h->force_variant != 2) {  // auto = v3 (measured fastest: profiles/)
+            if (multi) k_force_v3<true><<<nb, TPB_FORCE, 0, st>>>(f2);
+            else k_force_v3<false><<<nb, TPB_FORCE, 0, st>>>(f2);
+        } else {
+            if (multi) k_force_v2<true><<<nb, TPB_FORCE, 0, st>>>(f2);
+            else k_force_v2<false><<<nb, TPB_FORCE, 0, st>>>(f2);
+        }
+    } else if (h->box.ortho) {
         if (multi) k_force<true, true><<<nb, TPB_FORCE, 0, st>>>(fa);
         else k_force<true, false><<<nb, TPB_FORCE, 0, st>>>(fa);
     } else {
@@ -411,7 +506,7 @@ int launch_force(pisb_t *h, double *const out[3], const double *const acc[3], pi
 int launch_vv(pisb_t *h, bool kick, bool drift, double dt, pisb_thermo *rec) {
     LaunchScope ls(h, PISB_K_INTEGRATE);
     const double hs = 0.5 * h->skin;
-    VVArgs a{h->n, h->xt.p, h->v[0].p, h->v[1].p, h->v[2].p, h->f[0].p, h->f[1].p, h->f[2].p,
+    VVArgs a{h->n, h->xt.p, h->xf.p, h->v[0].p, h->v[1].p, h->v[2].p, h->f[0].p, h->f[1].p, h->f[2].p,
              h->g[0].p, h->g[1].p, h->g[2].p, h->xb[0].p, h->xb[1].p, h->xb[2].p, h->mass_d.p, h->box,
              dt, dt * dt, hs * hs, h->skin > 0.0 ? 0 : 1, h->flags, h->partials.p, h->ticket, rec};
     const int nb = nblk(h->n, TPB);
@@ -508,7 +603,8 @@ int do_upload(pisb_t *h, int64_t n64, const double *pos, const double *vel, cons
         LaunchScope ls(h, PISB_K_COPY);
         LoadArgs la{n, h->st_pos.p, vel ? h->st_vel.p : nullptr, frc ? h->st_frc.p : nullptr,
                     h->st_types.p, same_set ? h->slot_of_id.p : nullptr, h->xt.p,
-                    h->v[0].p, h->v[1].p, h->v[2].p, h->f[0].p, h->f[1].p, h->f[2].p, h->id.p, h->n_types, h->flags};
+                    h->v[0].p, h->v[1].p, h->v[2].p, h->f[0].p, h->f[1].p, h->f[2].p, h->id.p, h->n_types, h->flags,
+                    (same_set && h->have_box) ? h->xf.p : nullptr, h->box};
         k_load_aos<<<nblk(n, TPB), TPB, 0, h->stream>>>(la);
         TRY(check_launch(h, "k_load_aos"));
         if (same_set && h->have_box) {
@@ -692,6 +788,8 @@ int pisb_destroy(pisb_t *h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     dev_free(h, h->xt);
+    dev_free(h, h->xf);
+    dev_free(h, h->tablef_d);
     dev_free(h, h->s_xt);
     for (int d = 0; d < 3; ++d) {
         dev_free(h, h->v[d]);
@@ -837,7 +935,7 @@ int pisb_neighbours(pisb_t *h, int32_t *nnbr, int32_t *nbr, int64_t cap_per_atom
         total += hn[s];
         if (nbr) {
             if (hn[s] > cap_per_atom) return fail(h, PISB_ERR_CAPACITY, fmt("cap_per_atom %lld < list length %d", (long long)cap_per_atom, hn[s]));
-            for (int k = 0; k < hn[s]; ++k) nbr[(size_t)o * cap_per_atom + k] = hid[hl[(size_t)k * h->npad + s]];
+            for (int k = 0; k < hn[s]; ++k) nbr[(size_t)o * cap_per_atom + k] = hid[hl[nbr_at(k, s, h->npad)]];
         }
     }
     h->total_nbr = total;
@@ -906,6 +1004,17 @@ int pisb_set_option(pisb_t *h, const char *name, double value) {
         h->kcap_user = value > 0 ? (int)value : 0;
         h->kcap = 0;
         h->list_valid = false;
+        return PISB_OK;
+    }
+    if (!std::strcmp(name, "force_variant")) {
+        h->force_variant = (int)value;
+        return PISB_OK;
+    }
+    if (!std::strcmp(name, "build_variant") || !std::strcmp(name, "cell_div")) {
+        if (name[0] == 'b') h->build_variant = (int)value;
+        else h->cell_div = (int)value;
+        h->list_valid = false;
+        h->grid_ok = false;
         return PISB_OK;
     }
     return fail(h, PISB_ERR_INVALID, fmt("unknown option '%s'", name));

@@ -38,6 +38,7 @@ class LJCudaManager:
         self._sig = None      # signature of (table, masses) the handle was created with
         self._box_sig = None
         self._atoms_id = None
+        self._options: dict[str, float] = {}
 
     # ---- PairPotentialManager surface (src/potentials/potential.rs:148-193) -------------------
     @classmethod
@@ -88,6 +89,8 @@ class LJCudaManager:
                               capi._ptr(present), int(shift), self.skin, C.byref(h))
         capi.check(None, rc_)
         self._h, self._sig, self._box_sig, self._atoms_id = h, sig, None, None
+        for k, v in self._options.items():
+            capi.check(self._h, lib.pisb_set_option(self._h, k.encode(), float(v)))
 
     def _ensure_box(self, atoms: Atoms):
         b = atoms.sim_box
@@ -198,7 +201,10 @@ class LJCudaManager:
         return {k: {"ms": float(ms[i]), "launches": int(cnt[i])} for i, k in enumerate(capi.K_NAMES)}
 
     def set_option(self, name: str, value: float):
-        capi.check(self._h, capi.load().pisb_set_option(self._h, name.encode(), float(value)))
+        """Tuning knob (list_capacity, force_variant, build_variant); kept across handle re-creation."""
+        self._options[name] = float(value)
+        if self._h:
+            capi.check(self._h, capi.load().pisb_set_option(self._h, name.encode(), float(value)))
 
     def synchronize(self):
         capi.check(self._h, capi.load().pisb_synchronize(self._h))

@@ -16,8 +16,23 @@ def argon_pair(rc=RC25):
     return LennardJones(ARGON["epsilon"], ARGON["sigma"], rc, True)
 
 
-def make_manager(skin=0.0, rc=RC25, table=None):
+# kernel-variant combinations (force_variant, build_variant, cell_div); see DESIGN.md
+VARIANTS = {
+    0: None,              # library defaults
+    1: (1, 1, 1),         # v1: plain all-FP64 kernels, reference-sized cells
+    2: (2, 2, 1),         # v2: FP32 pre-filter + queue force kernel, pre-filter build
+    3: (3, 2, 1),         # v3: 4-wide prefetching all-FP64 force kernel, pre-filter build
+    4: (3, 2, 2),         # v3 + half-size cells (5^3 stencil)
+}
+
+
+def make_manager(skin=0.0, rc=RC25, table=None, variant=0):
     m = LJCudaManager(skin=skin)
+    if VARIANTS[variant]:
+        fv, bv, cd = VARIANTS[variant]
+        m.set_option("force_variant", fv)
+        m.set_option("build_variant", bv)
+        m.set_option("cell_div", cd)
     if table is None:
         m.insert((1, 1), argon_pair(rc))
     else:

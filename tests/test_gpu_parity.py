@@ -18,13 +18,14 @@ def _jittered(ncell, jitter=0.15, temperature=30.0, seed=7):
     return fcc_argon(ncell, temperature=temperature, seed=seed, jitter=jitter)
 
 
+@pytest.mark.parametrize("variant", [1, 2, 3, 4])
 @pytest.mark.parametrize("ncell,skin", [(10, 0.0), (10, SKIN), (16, SKIN)])
-def test_compute_potential_parity(ncell, skin):
+def test_compute_potential_parity(ncell, skin, variant):
     atoms = _jittered(ncell)
     table = {(1, 1): argon_pair()}
     orc = make_oracle(atoms, table)
     pe_ref, f_ref = orc.compute_potential(atoms.positions, atoms.type_ids)
-    mgr = make_manager(skin=skin)
+    mgr = make_manager(skin=skin, variant=variant)
     pe = mgr.compute_potential(atoms)  # adds into atoms.forces (zeros)
     assert abs(pe - pe_ref) <= ENERGY_TOL * abs(pe_ref)
     assert force_rel_err(atoms.forces, f_ref).max() <= FORCE_TOL
@@ -53,14 +54,15 @@ def test_argon4000_lattice_known_answer():
     assert all(len(r) == 54 for r in rows)
 
 
+@pytest.mark.parametrize("variant", [1, 2, 3, 4])
 @pytest.mark.parametrize("ncell,skin", [(8, 0.0), (8, SKIN), (12, SKIN)])
-def test_neighbour_list_exact(ncell, skin):
+def test_neighbour_list_exact(ncell, skin, variant):
     atoms = _jittered(ncell, jitter=0.3)
     table = {(1, 1): argon_pair()}
     orc = make_oracle(atoms, table)
     start, nbr = orc.build_neighbour_list(atoms.positions, atoms.type_ids, extra=skin)
     ref_rows = csr_rows_sorted(start, nbr)
-    mgr = make_manager(skin=skin)
+    mgr = make_manager(skin=skin, variant=variant)
     mgr.attach(atoms)
     rows = mgr.neighbours(atoms.n_atoms)
     assert sum(len(r) for r in rows) == len(nbr)
@@ -214,9 +216,9 @@ def test_edge_positions_on_boundary_and_beyond():
     """Atoms exactly on 0 / L and coordinates >= L (unwrapped step-0 input): same pairs as the oracle."""
     atoms = fcc_argon(7, temperature=0.0)
     L = atoms.sim_box.h[0, 0]
-    atoms.positions[5] = [L, 0.3, L]
+    atoms.positions[5] = [L, 0.9, L]
     atoms.positions[11] = [L + 1.0, L + 2.5, 0.7]
-    atoms.positions[17] = [0.0, L, 0.0]
+    atoms.positions[17] = [0.0, L, 1.3]
     table = {(1, 1): argon_pair(8.5)}
     orc = make_oracle(atoms, table)
     pe_ref, f_ref = orc.compute_potential(atoms.positions, atoms.type_ids)
@@ -252,3 +254,54 @@ def test_errors():
     atoms2.type_ids[3] = 5
     with pytest.raises(PisbError):
         make_manager(skin=0.0, rc=8.5).compute_potential(atoms2)
+
+
+def test_v2_prefilter_is_bitwise_equal_to_v1():
+    """The FP32 pre-filter only decides in/out (exact fallback in the guard band) and phase 2 keeps
+    the reference operation order: v2 forces / energies are BIT-identical to the all-FP64 v1 kernels."""
+    atoms = _jittered(12, jitter=0.25, temperature=50.0)
+    out = []
+    for variant in (1, 2, 3):
+        a = Atoms(atoms.type_ids, atoms.masses, atoms.positions.copy(), atoms.sim_box, velocities=atoms.velocities.copy())
+        m = make_manager(skin=SKIN, variant=variant)
+        m.attach(a)
+        pe0 = m.compute()
+        th = m.step_nve(0.25, 25)
+        m.download(a)
+        out.append((pe0, th, a.positions.copy(), a.velocities.copy(), a.forces.copy()))
+    for other in (1, 2):
+        assert out[0][0] == out[other][0]
+        for name in ("pe", "ke", "virial_ref", "virial_pair"):
+            assert np.array_equal(out[0][1][name], out[other][1][name]), name
+        for k in (2, 3, 4):
+            assert np.array_equal(out[0][k], out[other][k])
+
+
+def test_guard_band_pairs_sit_on_the_cutoff():
+    """Stress the guard band: many pairs placed within +-1e-7 (relative) of rc and of rc+skin, i.e. far
+    inside the FP32-ambiguous band; sets must still be exact and forces must still match."""
+    rng = np.random.default_rng(5)
+    base = fcc_argon(8, temperature=0.0)
+    L = base.sim_box.h[0, 0]
+    n = 600
+    pos = np.zeros((2 * n, 3))
+    centers = rng.uniform(0, L, size=(n, 3))
+    dirs = rng.standard_normal((n, 3))
+    dirs /= np.linalg.norm(dirs, axis=1)[:, None]
+    target = np.where(np.arange(n) % 2 == 0, RC25, RC25 + SKIN) * (1.0 + rng.uniform(-1e-7, 1e-7, size=n))
+    pos[0::2] = centers
+    pos[1::2] = centers + dirs * target[:, None]
+    pos -= np.floor(pos / L) * L
+    atoms = Atoms(np.ones(2 * n, dtype=np.int32), [39.948], pos, base.sim_box)
+    table = {(1, 1): argon_pair()}
+    orc = make_oracle(atoms, table)
+    start, nbr = orc.build_neighbour_list(atoms.positions, atoms.type_ids, extra=SKIN)
+    pe_ref, f_ref = orc.compute_potential(atoms.positions, atoms.type_ids)
+    mgr = make_manager(skin=SKIN, variant=4)
+    mgr.attach(atoms)
+    for a_, b_ in zip(mgr.neighbours(atoms.n_atoms), csr_rows_sorted(start, nbr)):
+        assert np.array_equal(a_, b_)
+    pe = mgr.compute()
+    mgr.download(atoms)
+    assert abs(pe - pe_ref) <= 1e-12 * max(abs(pe_ref), 1.0)
+    assert np.abs(atoms.forces - f_ref).max() <= 1e-13 * max(np.abs(f_ref).max(), 1.0)
