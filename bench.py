@@ -5,8 +5,9 @@
   python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port)
 
 A "step" is one NVE timestep (drift + wrap + skin check + [list rebuild] + LJ force + kick + thermo)
-of the whole synthetic FCC-argon system.  N=1 runs BASELINE configs[2] (4M atoms, rc = 2.5 sigma);
-N>1 runs configs[3] (32M atoms, spatial decomposition) strong-scaled over the ranks.
+of the whole synthetic FCC-argon system.  N=1 runs BASELINE configs[2] (4M atoms, rc = 2.5 sigma); N>1 runs the spatially decomposed path
+with one 4M-atom brick per GPU (weak scaling: N=8 is configs[3], 32M atoms on 2x2x2 bricks);
+--strong runs the 32M-atom system on any N.
 Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
@@ -137,7 +138,7 @@ def run_reference(args):
               f"{args.steps} timed steps")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak",
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if args.strong else "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args, args.gpus),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
@@ -148,10 +149,10 @@ def run_reference(args):
 
 
 def workload_config(args, n_gpus: int) -> dict:
-    ncell = args.ncell if n_gpus == 1 else args.ncell_multi
-    return {"workload": f"synthetic FCC argon {4 * ncell ** 3} atoms ({ncell}^3 cells, a=5.41), LJ rc=2.5sigma "
+    n_atoms = 4 * args.ncell ** 3 * n_gpus if not (args.strong and n_gpus > 1) else 4 * args.ncell_multi ** 3
+    return {"workload": f"synthetic FCC argon {n_atoms} atoms (a=5.41), LJ rc=2.5sigma "
                         f"skin=0.3sigma, NVE dt=0.25, T0={args.temperature}K",
-            "n_atoms": 4 * ncell ** 3, "rc": RC, "skin": SKIN, "dt": DT, "T0": args.temperature,
+            "n_atoms": n_atoms, "rc": RC, "skin": SKIN, "dt": DT, "T0": args.temperature,
             "l2_policy": "working set (state + neighbour list, GBs) >> 126 MB L2; no explicit flush",
             "parallelism": "1 GPU" if n_gpus == 1 else f"spatial decomposition over {n_gpus} GPUs"}
 
@@ -276,6 +277,7 @@ def main():
     ap.add_argument("--cpu-threads", type=int, default=0)
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--strong", action="store_true", help="N>1: run the 32M-atom system instead of 4M atoms per GPU")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

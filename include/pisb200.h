@@ -159,6 +159,23 @@ PISB_API int pisb_timings_reset(pisb_t *h);
 PISB_API void *pisb_stream(pisb_t *h);
 PISB_API int pisb_synchronize(pisb_t *h);
 
+/* ---- multi-GPU: spatial decomposition, ONE PROCESS PER GPU (new; the reference is single-process) ----
+ * The periodic box is cut into grid3[0] x grid3[1] x grid3[2] bricks (each 1 or 2), one per rank;
+ * ranks exchange ghost-atom positions every step with ncclSend/ncclRecv over NVLink and migrate atoms
+ * on list-rebuild steps.  Bootstrap: rank 0 calls pisb_comm_unique_id and broadcasts the 128 bytes
+ * (torch.distributed / MPI / a file -- plumbing), then every rank calls pisb_comm_init.
+ * After pisb_comm_init: pisb_set_box (the GLOBAL box), pisb_upload_owned (this rank's atoms with
+ * their global ids; atoms outside the rank's brick are migrated at the first rebuild), then
+ * pisb_compute / pisb_step_nve as on one GPU -- thermo records come back globally reduced. */
+PISB_API int pisb_comm_unique_id(void *out128, int nbytes);
+PISB_API int pisb_comm_init(pisb_t *h, int rank, int nranks, const void *unique_id128, const int *grid3);
+PISB_API int pisb_upload_owned(pisb_t *h, int64_t n_own, const double *pos, const double *vel,
+                               const double *force, const int32_t *types, const int32_t *global_ids);
+/* Owned atoms of this rank in device slot order (the order pisb_neighbours rows use in multi-GPU
+ * mode, where list entries are global ids).  Arrays hold up to cap atoms; *n_out = count. */
+PISB_API int pisb_download_owned(pisb_t *h, int64_t cap, double *pos, double *vel, double *force,
+                                 int32_t *global_ids, int64_t *n_out);
+
 /* Tuning knobs (0 = keep default): list_capacity = neighbour slots per atom (auto-grown on
  * overflow), force_variant = kernel variant selector for A/B measurements. */
 PISB_API int pisb_set_option(pisb_t *h, const char *name, double value);

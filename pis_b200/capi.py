@@ -68,6 +68,10 @@ SIGNATURES = {
     "pisb_stream": (_vp, [_vp]),
     "pisb_synchronize": (C.c_int, [_vp]),
     "pisb_set_option": (C.c_int, [_vp, C.c_char_p, C.c_double]),
+    "pisb_comm_unique_id": (C.c_int, [_vp, C.c_int]),
+    "pisb_comm_init": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp]),
+    "pisb_upload_owned": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp, _vp]),
+    "pisb_download_owned": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp, C.POINTER(C.c_int64)]),
 }
 
 _lib = None

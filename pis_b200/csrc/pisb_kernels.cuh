@@ -31,7 +31,51 @@ struct Grid {
     int lo[3];     // stencil offsets lo..hi per dim (dedupes n<3)
     int hi[3];
     int ncell;
+    // multi-GPU: dims that are decomposed over ranks are binned brick-locally and non-periodically
+    // (ghost atoms supply the periodic / neighbouring images); positions stay GLOBAL wrapped coordinates.
+    int local[3];
+    double center[3];    // brick centre (global coordinate)
+    double half[3];      // half extent of the extended brick: brick/2 + ghost width
+    double inv_edge[3];  // cells per unit length
 };
+
+// ghost flag lives above the type in the w lane of the position record (and bit 30 of xf.w)
+__device__ __forceinline__ bool is_ghost(double w) { return (__double_as_longlong(w) >> 32) & 1; }
+__device__ __forceinline__ double type_ghost_as_double(int t, bool ghost) {
+    return __longlong_as_double((long long)t | ((long long)(ghost ? 1 : 0) << 32));
+}
+// "dead" slots (atoms that migrated away, stale ghosts) carry bit 33 (and the ghost bit, so every kernel
+// skips them); k_bin files them in a sentinel bucket behind the last cell and the sort drops them.
+__device__ __forceinline__ bool is_dead(double w) { return (__double_as_longlong(w) >> 33) & 1; }
+__device__ __forceinline__ double mark_dead(double w) { return __longlong_as_double(__double_as_longlong(w) | (3LL << 32)); }
+constexpr int XF_GHOST_BIT = 1 << 30;
+__device__ __forceinline__ bool xf_is_ghost(const float4 &x) { return (__float_as_int(x.w) & XF_GHOST_BIT) != 0; }
+__device__ __forceinline__ int xf_type(const float4 &x) { return __float_as_int(x.w) & (XF_GHOST_BIT - 1); }
+
+// Cell coordinates of a position (shared by k_bin and the build kernels so they always agree).
+template <bool ORTHO>
+__device__ __forceinline__ void cell_coords(const BoxDev &box, const Grid &g, double x, double y, double z, int *c) {
+    double s[3];
+    matvec<ORTHO>(box.hinv, x, y, z, s[0], s[1], s[2]);
+    const double r[3] = {x, y, z};
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        if (g.local[d]) {
+            double dc = r[d] - g.center[d];
+            dc -= box.h[4 * d] * rint(dc * box.hinv[4 * d]);
+            int cd = (int)floor((dc + g.half[d]) * g.inv_edge[d]);
+            c[d] = min(max(cd, 0), g.n[d] - 1);
+        } else {
+            double sd = s[d];
+            if (box.pbc[d]) sd = sd - floor(sd);
+            // saturating conversion like Rust `as usize` (NaN/negative -> 0)
+            unsigned long long cd = __double2ull_rz(floor(sd * (double)g.n[d]));
+            if (cd >= (unsigned long long)g.n[d])
+                cd = box.pbc[d] ? cd % (unsigned long long)g.n[d] : (unsigned long long)(g.n[d] - 1);
+            c[d] = (int)cd;
+        }
+    }
+}
 
 // FP32 shadow of a position for the v2 pre-filter: the WRAPPED coordinate (the filter only needs an
 // approximation consistent with the minimum image) + the type bits in w.
@@ -47,7 +91,8 @@ __device__ __forceinline__ float4 make_xf(const BoxDev &b, const double4 &x) {
             }
         }
     }
-    return make_float4((float)c[0], (float)c[1], (float)c[2], __int_as_float(type_of(x.w)));
+    return make_float4((float)c[0], (float)c[1], (float)c[2],
+                       __int_as_float(type_of(x.w) | (is_ghost(x.w) ? XF_GHOST_BIT : 0)));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -66,6 +111,7 @@ struct LoadArgs {
     int *flags;
     float4 *xf;   // written when the current order/list is kept (null otherwise: the rebuild writes it)
     BoxDev box;
+    const int *gids;  // multi-GPU: global ids of the uploaded (owned) atoms; null => id = upload index
 };
 
 __global__ void __launch_bounds__(TPB) k_load_aos(LoadArgs a) {
@@ -90,7 +136,7 @@ __global__ void __launch_bounds__(TPB) k_load_aos(LoadArgs a) {
     a.fx[s] = a.frc ? a.frc[3 * (size_t)o] : 0.0;
     a.fy[s] = a.frc ? a.frc[3 * (size_t)o + 1] : 0.0;
     a.fz[s] = a.frc ? a.frc[3 * (size_t)o + 2] : 0.0;
-    a.id[s] = o;
+    a.id[s] = a.gids ? a.gids[o] : o;
 }
 
 struct StoreArgs {
@@ -170,7 +216,7 @@ template <bool KICK, bool DRIFT, bool ORTHO>
 __global__ void __launch_bounds__(TPB) k_vv(VVArgs a) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double red[4] = {0.0, 0.0, 0.0, 0.0};  // ke, x*fx, y*fy, z*fz
-    if (i < a.n) {
+    if (i < a.n && !is_ghost(a.xt[i].w)) {
         double4 x = a.xt[i];
         const double m = a.mass[type_of(x.w) - 1];
         double vx = a.vx[i], vy = a.vy[i], vz = a.vz[i];
@@ -225,7 +271,7 @@ __global__ void __launch_bounds__(TPB) k_observe(int n, const double4 *__restric
                                                  unsigned int *ticket, pisb_thermo *th) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double red[4] = {0.0, 0.0, 0.0, 0.0};
-    if (i < n) {
+    if (i < n && !is_ghost(xt[i].w)) {
         double4 x = xt[i];
         const double m = mass[type_of(x.w) - 1];
         red[0] = __dmul_rn(__dmul_rn(0.5, m), norm2(vx[i], vy[i], vz[i]));
@@ -257,19 +303,10 @@ __global__ void __launch_bounds__(TPB) k_bin(int n, const double4 *__restrict__ 
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double4 x = xt[i];
-    double s[3];
-    matvec<ORTHO>(box.hinv, x.x, x.y, x.z, s[0], s[1], s[2]);
     int c[3];
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-        double sd = s[d];
-        if (box.pbc[d]) sd = sd - floor(sd);
-        // saturating conversion like Rust `as usize` (NaN/negative -> 0)
-        unsigned long long cd = __double2ull_rz(floor(sd * (double)g.n[d]));
-        if (cd >= (unsigned long long)g.n[d]) cd = box.pbc[d] ? cd % (unsigned long long)g.n[d] : (unsigned long long)(g.n[d] - 1);
-        c[d] = (int)cd;
-    }
+    cell_coords<ORTHO>(box, g, x.x, x.y, x.z, c);
     int cell = (c[2] * g.n[1] + c[1]) * g.n[0] + c[0];
+    if (is_dead(x.w)) cell = g.ncell;  // sentinel bucket (multi-GPU rebuilds)
     cell_of[i] = cell;
     atomicAdd(&cell_count[cell], 1);
 }
@@ -456,7 +493,7 @@ __global__ void __launch_bounds__(TPB) k_copy_back(CopyBackArgs a) {
     a.fz[p] = a.s_fz[p];
     int o = a.s_id[p];
     a.id[p] = o;
-    a.slot_of_id[o] = p;
+    if (a.slot_of_id) a.slot_of_id[o] = p;  // null in multi-GPU mode (ids are global there)
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -485,38 +522,28 @@ __global__ void __launch_bounds__(TPB_FORCE) k_build_list(BuildArgs a) {
     if (a.flags[FLAG_REBUILD] == 0) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     int cnt = 0;
-    if (i < a.n) {
+    if (i < a.n && is_ghost(a.xt[i].w)) a.nnbr[i] = 0;
+    if (i < a.n && !is_ghost(a.xt[i].w)) {
         const double4 xi = a.xt[i];
         const int ti = MULTI ? type_of(xi.w) : 1;
-        // cell of slot i from its (already binned) position: recompute like k_bin
-        double s[3];
-        matvec<ORTHO>(a.box.hinv, xi.x, xi.y, xi.z, s[0], s[1], s[2]);
         int c[3];
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-            double sd = s[d];
-            if (a.box.pbc[d]) sd = sd - floor(sd);
-            unsigned long long cd = __double2ull_rz(floor(sd * (double)a.g.n[d]));
-            if (cd >= (unsigned long long)a.g.n[d])
-                cd = a.box.pbc[d] ? cd % (unsigned long long)a.g.n[d] : (unsigned long long)(a.g.n[d] - 1);
-            c[d] = (int)cd;
-        }
+        cell_coords<ORTHO>(a.box, a.g, xi.x, xi.y, xi.z, c);
         for (int dz = a.g.lo[2]; dz <= a.g.hi[2]; ++dz) {
             int cz = c[2] + dz;
             if (cz < 0 || cz >= a.g.n[2]) {
-                if (!a.box.pbc[2]) continue;
+                if (!a.box.pbc[2] || a.g.local[2]) continue;
                 cz += cz < 0 ? a.g.n[2] : -a.g.n[2];
             }
             for (int dy = a.g.lo[1]; dy <= a.g.hi[1]; ++dy) {
                 int cy = c[1] + dy;
                 if (cy < 0 || cy >= a.g.n[1]) {
-                    if (!a.box.pbc[1]) continue;
+                    if (!a.box.pbc[1] || a.g.local[1]) continue;
                     cy += cy < 0 ? a.g.n[1] : -a.g.n[1];
                 }
                 for (int dx = a.g.lo[0]; dx <= a.g.hi[0]; ++dx) {
                     int cx = c[0] + dx;
                     if (cx < 0 || cx >= a.g.n[0]) {
-                        if (!a.box.pbc[0]) continue;
+                        if (!a.box.pbc[0] || a.g.local[0]) continue;
                         cx += cx < 0 ? a.g.n[0] : -a.g.n[0];
                     }
                     const int cell = (cz * a.g.n[1] + cy) * a.g.n[0] + cx;
@@ -585,7 +612,7 @@ template <bool ORTHO, bool MULTI>
 __global__ void __launch_bounds__(TPB_FORCE) k_force(ForceArgs a) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double red[2] = {0.0, 0.0};  // sum u, sum fs*r2
-    if (i < a.n) {
+    if (i < a.n && !is_ghost(a.xt[i].w)) {
         const double4 xi = a.xt[i];
         const int ti = MULTI ? type_of(xi.w) : 1;
         const int nn = a.nnbr[i];
@@ -765,7 +792,7 @@ __device__ __forceinline__ void force2_body(const Force2Args &a, int i, int (*q)
                                             double &fz, double &pe, double &vir) {
     const double4 xi = a.xt[i];
     const float4 xif = a.xf[i];
-    const int ti = MULTI ? __float_as_int(xif.w) : 1;
+    const int ti = MULTI ? xf_type(xif) : 1;
     const int nn = a.nnbr[i];
     const int tid = threadIdx.x;
     int k = 0;
@@ -791,7 +818,7 @@ __device__ __forceinline__ void force2_body(const Force2Args &a, int i, int (*q)
                 PairF pf;
                 int pidx = 0;
                 if (MULTI) {
-                    const int tj = __float_as_int(xjf[u].w);
+                    const int tj = xf_type(xjf[u]);
                     pidx = (min(ti, tj) - 1) * a.n_types + (max(ti, tj) - 1);
                     pf = a.tablef[pidx];
                 } else {
@@ -885,7 +912,7 @@ template <bool MULTI>
 __global__ void __launch_bounds__(TPB_FORCE) k_force_v3(Force2Args a) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double red[2] = {0.0, 0.0};
-    const bool active = i < a.n;
+    const bool active = i < a.n && !xf_is_ghost(a.xf[i]);
     bool interior = true;
     if (active) interior = is_interior(a.boxf, a.xf[i]);
     const bool warp_interior = __all_sync(0xffffffffu, interior);
@@ -916,7 +943,7 @@ __global__ void __launch_bounds__(TPB_FORCE) k_force_v2(Force2Args a) {
     __shared__ int s_q[QCAP][TPB_FORCE];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double red[2] = {0.0, 0.0};
-    const bool active = i < a.n;
+    const bool active = i < a.n && !xf_is_ghost(a.xf[i]);
     bool interior = true;
     if (active) interior = is_interior(a.boxf, a.xf[i]);
     const bool warp_interior = __all_sync(0xffffffffu, interior);
@@ -965,19 +992,9 @@ __device__ __forceinline__ int build2_body(const Build2Args &a, int i) {
     int cnt = 0;
     const double4 xi = a.xt[i];
     const float4 xif = a.xf[i];
-    const int ti = MULTI ? __float_as_int(xif.w) : 1;
-    double s[3];
-    matvec<true>(a.box.hinv, xi.x, xi.y, xi.z, s[0], s[1], s[2]);
+    const int ti = MULTI ? xf_type(xif) : 1;
     int c[3];
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-        double sd = s[d];
-        if (a.box.pbc[d]) sd = sd - floor(sd);
-        unsigned long long cd = __double2ull_rz(floor(sd * (double)a.g.n[d]));
-        if (cd >= (unsigned long long)a.g.n[d])
-            cd = a.box.pbc[d] ? cd % (unsigned long long)a.g.n[d] : (unsigned long long)(a.g.n[d] - 1);
-        c[d] = (int)cd;
-    }
+    cell_coords<true>(a.box, a.g, xi.x, xi.y, xi.z, c);
     int *const tile0 = a.nbr + (size_t)i * 4;
     const size_t tile_stride = (size_t)a.npad * 4;
     auto test = [&](int jj, const float4 &xjf) {
@@ -985,7 +1002,7 @@ __device__ __forceinline__ int build2_body(const Build2Args &a, int i) {
         PairF pf;
         int pidx = 0;
         if (MULTI) {
-            const int tj = __float_as_int(xjf.w);
+            const int tj = xf_type(xjf);
             pidx = (min(ti, tj) - 1) * a.n_types + (max(ti, tj) - 1);
             pf = a.tablef[pidx];
         } else {
@@ -1017,24 +1034,28 @@ __device__ __forceinline__ int build2_body(const Build2Args &a, int i) {
     const int nx = a.g.n[0];
     for (int dz = a.g.lo[2]; dz <= a.g.hi[2]; ++dz) {
         int cz = c[2] + dz;
-        if (cz < 0) cz += a.g.n[2];
-        else if (cz >= a.g.n[2]) cz -= a.g.n[2];
+        if (cz < 0 || cz >= a.g.n[2]) {
+            if (a.g.local[2]) continue;
+            cz += cz < 0 ? a.g.n[2] : -a.g.n[2];
+        }
         for (int dy = a.g.lo[1]; dy <= a.g.hi[1]; ++dy) {
             int cy = c[1] + dy;
-            if (cy < 0) cy += a.g.n[1];
-            else if (cy >= a.g.n[1]) cy -= a.g.n[1];
+            if (cy < 0 || cy >= a.g.n[1]) {
+                if (a.g.local[1]) continue;
+                cy += cy < 0 ? a.g.n[1] : -a.g.n[1];
+            }
             const int rb = (cz * a.g.n[1] + cy) * nx;
             // the x-neighbour cells of one row are consecutive slots: same visiting order as
             // dx = lo..hi with periodic wrap (wrapped-low part, main part, wrapped-high part)
             int xlo = c[0] + a.g.lo[0];
             const int xhi = c[0] + a.g.hi[0];
             if (xlo < 0) {
-                scan(__ldg(&a.cell_start[rb + xlo + nx]), __ldg(&a.cell_start[rb + nx]));
+                if (!a.g.local[0]) scan(__ldg(&a.cell_start[rb + xlo + nx]), __ldg(&a.cell_start[rb + nx]));
                 xlo = 0;
             }
             const int xhi_main = min(xhi, nx - 1);
             scan(__ldg(&a.cell_start[rb + xlo]), __ldg(&a.cell_start[rb + xhi_main + 1]));
-            if (xhi >= nx) scan(__ldg(&a.cell_start[rb]), __ldg(&a.cell_start[rb + xhi - nx + 1]));
+            if (xhi >= nx && !a.g.local[0]) scan(__ldg(&a.cell_start[rb]), __ldg(&a.cell_start[rb + xhi - nx + 1]));
         }
     }
     a.nnbr[i] = cnt < a.kcap ? cnt : a.kcap;
@@ -1045,7 +1066,8 @@ template <bool MULTI>
 __global__ void __launch_bounds__(TPB_FORCE) k_build_list_v2(Build2Args a) {
     if (a.flags[FLAG_REBUILD] == 0) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = i < a.n;
+    if (i < a.n && xf_is_ghost(a.xf[i])) a.nnbr[i] = 0;
+    const bool active = i < a.n && !xf_is_ghost(a.xf[i]);
     bool interior = true;
     if (active) interior = is_interior(a.boxf, a.xf[i]);
     const bool warp_interior = __all_sync(0xffffffffu, interior);

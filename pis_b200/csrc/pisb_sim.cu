@@ -8,11 +8,16 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <string>
 #include <vector>
 
 #include "pisb200.h"
 #include "pisb_kernels.cuh"
+#include "pisb_multi.cuh"
+
+#include <dlfcn.h>
+#include <nccl.h>
 
 using namespace pisb;
 
@@ -97,6 +102,18 @@ struct pisb_handle {
     double *h_stage = nullptr;       // pinned staging for pageable host buffers
     size_t h_stage_cap = 0;
     int64_t device_bytes = 0;
+
+    // multi-GPU (spatial decomposition; see pisb_multi.cuh)
+    bool multi = false;
+    Decomp dc{};
+    ncclComm_t comm = nullptr;
+    int n_own = 0, n_ghost = 0, ncap_atoms = 0;
+    DevBuf<int> m_dest, m_pig, m_cnt, m_allcnt, m_off, send_idx, ghost_slot, newslot;
+    DevBuf<double> mig_send, mig_recv;
+    DevBuf<double4> halo_send, halo_recv;
+    std::vector<int> gs_cnt, gr_cnt, gs_off, gr_off;  // per-peer ghost send/recv counts and offsets
+    int send_total = 0;
+    int *h_counts = nullptr;  // pinned, nranks^2 ints
 
     // stats
     int64_t n_steps = 0, n_launches = 0;
@@ -305,6 +322,7 @@ int setup_grid(pisb_t *h) {
     if (div < 1) div = 1;
     if (div > 2) div = 2;
     if (!(h->build_variant == 2 || (h->build_variant == 0 && v2_possible(h)))) div = 1;
+    if (h->multi) div = 1;
     const int64_t cell_cap = std::max<int64_t>(4 * (int64_t)h->n + 1024, 27);
     double prod = 1.0;
     for (int d = 0; d < 3 && div > 1; ++d) {
@@ -343,11 +361,36 @@ int setup_grid(pisb_t *h) {
         else if (g.n[d] == 2) g.lo[d] = 0, g.hi[d] = 1;
         else g.lo[d] = -1, g.hi[d] = 1;
     }
+    if (h->multi) {
+        // decomposed dimensions: brick-local, non-periodic binning over brick + ghost shell
+        if (!v2_possible(h)) return fail(h, PISB_ERR_INVALID, "multi-GPU mode needs an orthorhombic, fully periodic box");
+        Decomp &dc = h->dc;
+        dc.gw = rc_list * (1.0 + 1e-6);
+        for (int d = 0; d < 3; ++d) {
+            const double len = h->box.h[4 * d];
+            const double w = len / dc.P[d];
+            dc.lo[d] = dc.b[d] * w;
+            dc.hi[d] = dc.b[d] == dc.P[d] - 1 ? len : (dc.b[d] + 1) * w;
+            if (dc.P[d] == 1) continue;
+            if (w < 2.0 * dc.gw)
+                return fail(h, PISB_ERR_INVALID, fmt("brick width %.6g in dimension %d is below 2 x (rcut + skin) = %.6g", w, d, 2.0 * dc.gw));
+            const double half = 0.5 * w + dc.gw + h->skin;
+            int nd = (int)std::floor(2.0 * half / rc_list);
+            if (nd < 3) nd = 3;
+            g.n[d] = nd;
+            g.local[d] = 1;
+            g.center[d] = dc.lo[d] + 0.5 * w;
+            g.half[d] = half;
+            g.inv_edge[d] = nd / (2.0 * half);
+            g.lo[d] = -1;
+            g.hi[d] = 1;
+        }
+    }
     g.ncell = g.n[0] * g.n[1] * g.n[2];
     h->grid = g;
-    TRY(dev_reserve(h, h->cell_count, (size_t)g.ncell + 1));
-    TRY(dev_reserve(h, h->cell_start, (size_t)g.ncell + 1));
-    TRY(dev_reserve(h, h->tile_sum, (size_t)nblk(g.ncell, SCAN_TILE) + 1));
+    TRY(dev_reserve(h, h->cell_count, (size_t)g.ncell + 2));
+    TRY(dev_reserve(h, h->cell_start, (size_t)g.ncell + 2));
+    TRY(dev_reserve(h, h->tile_sum, (size_t)nblk(g.ncell + 1, SCAN_TILE) + 1));
     TRY(setup_filter(h));
     h->grid_ok = true;
     h->list_valid = false;
@@ -360,9 +403,10 @@ int estimate_kcap(pisb_t *h) {
     const double vol = std::fabs(m[0] * (m[4] * m[8] - m[5] * m[7]) - m[3] * (m[1] * m[8] - m[2] * m[7]) +
                                  m[6] * (m[1] * m[5] - m[2] * m[4]));
     const double rl = h->max_rcut + h->skin;
-    double k = vol > 0 ? (double)h->n / vol * 4.18879020478639 * rl * rl * rl : 64.0;
+    const double n_glob = h->multi ? (double)h->n_own * h->dc.nranks : (double)h->n;
+    double k = vol > 0 ? n_glob / vol * 4.18879020478639 * rl * rl * rl : 64.0;
     k = 1.3 * k + 24.0;
-    if (k > (double)h->n) k = (double)std::max(h->n, 1);
+    if (k > n_glob) k = std::max(n_glob, 1.0);
     if (k > 4096.0) k = 4096.0;
     return (int)std::ceil(k);
 }
@@ -391,7 +435,7 @@ int reserve_atoms(pisb_t *h, int n) {
 }
 
 int reserve_list(pisb_t *h) {
-    h->npad = (h->n + 31) / 32 * 32;
+    h->npad = (std::max(h->n, h->ncap_atoms) + 31) / 32 * 32;
     h->kcap = (h->kcap + 3) / 4 * 4;  // whole K-tiles of 4
     TRY(dev_reserve(h, h->nbr, (size_t)h->kcap * (size_t)h->npad));
     return PISB_OK;
@@ -418,10 +462,11 @@ int dispatch_ortho(pisb_t *h, F &&f) {
 int launch_rebuild_chain(pisb_t *h) {
     const int n = h->n;
     const Grid g = h->grid;
+    const int nb = g.ncell + (h->multi ? 1 : 0);  // + sentinel bucket for dead slots
     cudaStream_t st = h->stream;
     {
         LaunchScope ls(h, PISB_K_BIN);
-        CUDA_TRY(h, cudaMemsetAsync(h->cell_count.p, 0, sizeof(int) * ((size_t)g.ncell + 1), st));
+        CUDA_TRY(h, cudaMemsetAsync(h->cell_count.p, 0, sizeof(int) * ((size_t)nb + 1), st));
         if (h->box.ortho)
             k_bin<true><<<nblk(n, TPB), TPB, 0, st>>>(n, h->xt.p, h->box, g, h->cell_of.p, h->cell_count.p, h->flags);
         else
@@ -429,10 +474,10 @@ int launch_rebuild_chain(pisb_t *h) {
     }
     {
         LaunchScope ls(h, PISB_K_SORT);
-        const int ntiles = nblk(g.ncell, SCAN_TILE);
-        k_scan_tiles<<<ntiles, SCAN_TPB, 0, st>>>(g.ncell, h->cell_count.p, h->tile_sum.p, h->flags);
+        const int ntiles = nblk(nb, SCAN_TILE);
+        k_scan_tiles<<<ntiles, SCAN_TPB, 0, st>>>(nb, h->cell_count.p, h->tile_sum.p, h->flags);
         k_scan_sums<<<1, SCAN_TPB, 0, st>>>(ntiles, h->tile_sum.p, h->flags);
-        k_scan_apply<<<ntiles, SCAN_TPB, 0, st>>>(g.ncell, n, h->cell_count.p, h->tile_sum.p, h->cell_start.p, h->flags);
+        k_scan_apply<<<ntiles, SCAN_TPB, 0, st>>>(nb, n, h->cell_count.p, h->tile_sum.p, h->cell_start.p, h->flags);
         k_fill<<<nblk(n, TPB), TPB, 0, st>>>(n, h->cell_of.p, h->cell_start.p, h->cell_count.p, h->order.p, h->flags);
         k_sort_cells<<<nblk(g.ncell, TPB), TPB, 0, st>>>(g.ncell, h->cell_start.p, h->order.p, h->id.p, h->flags);
         PermArgs pa{n, h->order.p, h->xt.p, h->v[0].p, h->v[1].p, h->v[2].p, h->f[0].p, h->f[1].p, h->f[2].p,
@@ -441,7 +486,8 @@ int launch_rebuild_chain(pisb_t *h) {
         k_permute<<<nblk(n, TPB), TPB, 0, st>>>(pa);
         CopyBackArgs ca{n, h->s_xt.p, h->s_v[0].p, h->s_v[1].p, h->s_v[2].p, h->s_f[0].p, h->s_f[1].p, h->s_f[2].p,
                         h->s_id.p, h->xt.p, h->v[0].p, h->v[1].p, h->v[2].p, h->f[0].p, h->f[1].p, h->f[2].p,
-                        h->id.p, h->slot_of_id.p, h->xb[0].p, h->xb[1].p, h->xb[2].p, h->flags, h->xf.p, h->box};
+                        h->id.p, h->multi ? nullptr : h->slot_of_id.p, h->xb[0].p, h->xb[1].p, h->xb[2].p, h->flags, h->xf.p,
+                        h->box};
         k_copy_back<<<nblk(n, TPB), TPB, 0, st>>>(ca);
         h->n_launches += 6;
     }
@@ -604,7 +650,7 @@ int do_upload(pisb_t *h, int64_t n64, const double *pos, const double *vel, cons
         LoadArgs la{n, h->st_pos.p, vel ? h->st_vel.p : nullptr, frc ? h->st_frc.p : nullptr,
                     h->st_types.p, same_set ? h->slot_of_id.p : nullptr, h->xt.p,
                     h->v[0].p, h->v[1].p, h->v[2].p, h->f[0].p, h->f[1].p, h->f[2].p, h->id.p, h->n_types, h->flags,
-                    (same_set && h->have_box) ? h->xf.p : nullptr, h->box};
+                    (same_set && h->have_box) ? h->xf.p : nullptr, h->box, nullptr};
         k_load_aos<<<nblk(n, TPB), TPB, 0, h->stream>>>(la);
         TRY(check_launch(h, "k_load_aos"));
         if (same_set && h->have_box) {
@@ -655,8 +701,12 @@ int check_bad_type(pisb_t *h) {
     return PISB_OK;
 }
 
+int do_compute_multi(pisb_t *h, int accumulate, double *pe);
+int do_step_nve_multi(pisb_t *h, double dt, int64_t nsteps, pisb_thermo *out);
+
 int do_compute(pisb_t *h, int accumulate, double *pe) {
     if (!h->have_atoms || !h->have_box) return fail(h, PISB_ERR_STATE, "set_box and upload must precede compute");
+    if (h->multi) return do_compute_multi(h, accumulate, pe);
     TRY(ensure_list(h));
     TRY(check_bad_type(h));
     TRY(reserve_thermo(h, 2));
@@ -674,6 +724,7 @@ int do_step_nve(pisb_t *h, double dt, int64_t nsteps, pisb_thermo *out) {
     if (!h->have_atoms || !h->have_box) return fail(h, PISB_ERR_STATE, "set_box and upload must precede step_nve");
     if (nsteps < 0) return fail(h, PISB_ERR_INVALID, "nsteps < 0");
     if (nsteps == 0) return PISB_OK;
+    if (h->multi) return do_step_nve_multi(h, dt, nsteps, out);
     TRY(ensure_list(h));  // list for x(t); from here on the skin trigger decides on the device
     TRY(check_bad_type(h));
     const int64_t chunk_max = 4096;
@@ -713,6 +764,339 @@ int do_step_nve(pisb_t *h, double dt, int64_t nsteps, pisb_thermo *out) {
         done += m;
         h->n_steps += m;
     }
+    h->forces_current = true;
+    return PISB_OK;
+}
+
+
+// ================================================================================================
+// multi-GPU host orchestration (see pisb_multi.cuh for the scheme)
+// ================================================================================================
+struct NcclApi {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+NcclApi g_nccl;
+
+// NCCL is loaded lazily (dlopen) so that single-GPU users do not need it; under torch the already
+// loaded libnccl.so.2 is picked up.
+int load_nccl(pisb_t *h) {
+    if (g_nccl.lib) return PISB_OK;
+    void *lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) return fail(h, PISB_ERR_COMM, fmt("cannot load libnccl.so.2: %s", dlerror()));
+#define SYM(field, name)                                                             \
+    *(void **)(&g_nccl.field) = dlsym(lib, name);                                    \
+    if (!g_nccl.field) return fail(h, PISB_ERR_COMM, "libnccl is missing symbol " name)
+    SYM(GetUniqueId, "ncclGetUniqueId");
+    SYM(CommInitRank, "ncclCommInitRank");
+    SYM(CommDestroy, "ncclCommDestroy");
+    SYM(Send, "ncclSend");
+    SYM(Recv, "ncclRecv");
+    SYM(GroupStart, "ncclGroupStart");
+    SYM(GroupEnd, "ncclGroupEnd");
+    SYM(AllReduce, "ncclAllReduce");
+    SYM(AllGather, "ncclAllGather");
+    SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+    g_nccl.lib = lib;
+    return PISB_OK;
+}
+
+#define NCCL_TRY(h, expr)                                                                              \
+    do {                                                                                               \
+        ncclResult_t r_ = (expr);                                                                      \
+        if (r_ != ncclSuccess)                                                                         \
+            return fail(h, PISB_ERR_COMM, fmt("%s failed at line %d: %s", #expr, __LINE__, g_nccl.GetErrorString(r_))); \
+    } while (0)
+
+// all-gather `cnt` (nranks ints per rank) and bring the nranks^2 table to the host (synchronous)
+int gather_counts(pisb_t *h) {
+    const int R = h->dc.nranks;
+    NCCL_TRY(h, g_nccl.AllGather(h->m_cnt.p, h->m_allcnt.p, R, ncclInt, h->comm, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_counts, h->m_allcnt.p, sizeof(int) * R * R, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return PISB_OK;
+}
+
+// grouped pairwise exchange of `rec` doubles per item with every other rank
+int exchange(pisb_t *h, const double *sbuf, const std::vector<int> &scnt, const std::vector<int> &soff, double *rbuf,
+             const std::vector<int> &rcnt, const std::vector<int> &roff, int rec) {
+    const int R = h->dc.nranks, me = h->dc.rank;
+    LaunchScope ls(h, PISB_K_HALO);
+    NCCL_TRY(h, g_nccl.GroupStart());
+    for (int r = 0; r < R; ++r) {
+        if (r == me) continue;
+        if (scnt[r] > 0)
+            NCCL_TRY(h, g_nccl.Send(sbuf + (size_t)soff[r] * rec, (size_t)scnt[r] * rec, ncclDouble, r, h->comm, h->stream));
+        if (rcnt[r] > 0)
+            NCCL_TRY(h, g_nccl.Recv(rbuf + (size_t)roff[r] * rec, (size_t)rcnt[r] * rec, ncclDouble, r, h->comm, h->stream));
+    }
+    NCCL_TRY(h, g_nccl.GroupEnd());
+    return PISB_OK;
+}
+
+double wall_now() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
+// Atom migration + ghost selection + cell sort + list build.  Host-synchronous (counts cross PCIe).
+int multi_rebuild(pisb_t *h) {
+    const bool trace = std::getenv("PISB_TRACE") != nullptr;
+    double tw[8];
+    tw[0] = wall_now();
+    if (!h->grid_ok) TRY(setup_grid(h));
+    if (!h->grid_ok) return fail(h, PISB_ERR_STATE, "set_box and upload must precede this call");
+    const int R = h->dc.nranks, me = h->dc.rank;
+    cudaStream_t st = h->stream;
+    TRY(dev_reserve(h, h->m_cnt, (size_t)R));
+    TRY(dev_reserve(h, h->m_allcnt, (size_t)R * R));
+    TRY(dev_reserve(h, h->m_off, (size_t)R));
+    TRY(dev_reserve(h, h->m_dest, (size_t)h->ncap_atoms));
+    TRY(dev_reserve(h, h->m_pig, (size_t)h->ncap_atoms));
+    TRY(dev_reserve(h, h->newslot, (size_t)h->ncap_atoms));
+    TRY(dev_reserve(h, h->ghost_slot, (size_t)h->ncap_atoms));
+    std::vector<int> scnt(R), rcnt(R), soff(R), roff(R);
+
+    // ---- 1. migration: owned atoms whose wrapped position left the brick go to their new owner ----
+    const int n_slots0 = h->n;  // live + (after this step) dead slots
+    {
+        LaunchScope ls(h, PISB_K_HALO);
+        CUDA_TRY(h, cudaMemsetAsync(h->m_cnt.p, 0, sizeof(int) * R, st));
+        k_mig_count<<<nblk(std::max(n_slots0, 1), TPB), TPB, 0, st>>>(n_slots0, h->xt.p, h->box, h->dc, h->m_dest.p, h->m_pig.p, h->m_cnt.p);
+        TRY(check_launch(h, "k_mig_count"));
+    }
+    tw[1] = wall_now();
+    TRY(gather_counts(h));
+    tw[2] = wall_now();
+    int stot = 0, rtot = 0;
+    for (int r = 0; r < R; ++r) {
+        scnt[r] = r == me ? 0 : h->h_counts[me * R + r];
+        rcnt[r] = r == me ? 0 : h->h_counts[r * R + me];
+        soff[r] = stot;
+        roff[r] = rtot;
+        stot += scnt[r];
+        rtot += rcnt[r];
+    }
+    const int n_own = h->n_own - stot + rtot;
+    if (n_slots0 + rtot > h->ncap_atoms)
+        return fail(h, PISB_ERR_CAPACITY, fmt("rank %d: %d slots + %d arrivals exceed the local capacity %d", me, n_slots0, rtot, h->ncap_atoms));
+    TRY(dev_reserve(h, h->mig_send, (size_t)std::max(stot, 1) * MIG_REC));
+    TRY(dev_reserve(h, h->mig_recv, (size_t)std::max(rtot, 1) * MIG_REC));
+    CUDA_TRY(h, cudaMemcpyAsync(h->m_off.p, soff.data(), sizeof(int) * R, cudaMemcpyHostToDevice, st));
+    {
+        LaunchScope ls(h, PISB_K_HALO);
+        MigArgs ma{n_slots0, h->xt.p, h->v[0].p, h->v[1].p, h->v[2].p, h->f[0].p, h->f[1].p, h->f[2].p, h->id.p,
+                   h->m_dest.p, h->m_pig.p, h->m_off.p, h->mig_send.p};
+        k_mig_pack<<<nblk(std::max(n_slots0, 1), TPB), TPB, 0, st>>>(ma);
+        TRY(check_launch(h, "k_mig_pack"));
+    }
+    if (stot + rtot > 0 || R > 1) TRY(exchange(h, h->mig_send.p, scnt, soff, h->mig_recv.p, rcnt, roff, MIG_REC));
+    if (rtot > 0) {
+        LaunchScope ls(h, PISB_K_HALO);
+        MigUnpackArgs u2{rtot, n_slots0, h->mig_recv.p, h->xt.p, h->v[0].p, h->v[1].p, h->v[2].p,
+                         h->f[0].p, h->f[1].p, h->f[2].p, h->id.p};
+        k_mig_unpack<<<nblk(rtot, TPB), TPB, 0, st>>>(u2);
+        TRY(check_launch(h, "k_mig_unpack"));
+    }
+    h->n_own = n_own;
+    const int n_slots1 = n_slots0 + rtot;  // owned atoms (old + arrived) live somewhere in [0, n_slots1)
+
+    tw[3] = wall_now();
+    // ---- 2. ghosts: owned atoms within gw of a brick face go to the rank(s) across ----
+    {
+        LaunchScope ls(h, PISB_K_HALO);
+        CUDA_TRY(h, cudaMemsetAsync(h->m_cnt.p, 0, sizeof(int) * R, st));
+        k_ghost_select<false><<<nblk(std::max(n_slots1, 1), TPB), TPB, 0, st>>>(n_slots1, h->xt.p, h->dc, h->m_cnt.p, nullptr, nullptr);
+        TRY(check_launch(h, "k_ghost_select"));
+    }
+    TRY(gather_counts(h));
+    h->gs_cnt.assign(R, 0);
+    h->gr_cnt.assign(R, 0);
+    h->gs_off.assign(R, 0);
+    h->gr_off.assign(R, 0);
+    int gs = 0, gr = 0;
+    for (int r = 0; r < R; ++r) {
+        h->gs_cnt[r] = r == me ? 0 : h->h_counts[me * R + r];
+        h->gr_cnt[r] = r == me ? 0 : h->h_counts[r * R + me];
+        h->gs_off[r] = gs;
+        h->gr_off[r] = gr;
+        gs += h->gs_cnt[r];
+        gr += h->gr_cnt[r];
+    }
+    h->send_total = gs;
+    h->n_ghost = gr;
+    if (n_slots1 + gr > h->ncap_atoms)
+        return fail(h, PISB_ERR_CAPACITY, fmt("rank %d needs %d local slots (owned + ghost + stale), capacity %d", me, n_slots1 + gr, h->ncap_atoms));
+    TRY(dev_reserve(h, h->send_idx, (size_t)std::max(gs, 1)));
+    TRY(dev_reserve(h, h->halo_send, (size_t)std::max(gs, 1)));
+    TRY(dev_reserve(h, h->halo_recv, (size_t)std::max(gr, 1)));
+    TRY(dev_reserve(h, h->mig_send, (size_t)std::max(gs, 1) * GHOST_REC));
+    TRY(dev_reserve(h, h->mig_recv, (size_t)std::max(gr, 1) * GHOST_REC));
+    CUDA_TRY(h, cudaMemcpyAsync(h->m_off.p, h->gs_off.data(), sizeof(int) * R, cudaMemcpyHostToDevice, st));
+    {
+        LaunchScope ls(h, PISB_K_HALO);
+        CUDA_TRY(h, cudaMemsetAsync(h->m_cnt.p, 0, sizeof(int) * R, st));
+        k_ghost_select<true><<<nblk(std::max(n_slots1, 1), TPB), TPB, 0, st>>>(n_slots1, h->xt.p, h->dc, h->m_cnt.p, h->m_off.p, h->send_idx.p);
+        if (gs > 0) k_ghost_pack_full<<<nblk(gs, TPB), TPB, 0, st>>>(gs, h->send_idx.p, h->xt.p, h->id.p, h->mig_send.p);
+        TRY(check_launch(h, "k_ghost_pack_full"));
+        h->n_launches += 1;
+    }
+    TRY(exchange(h, h->mig_send.p, h->gs_cnt, h->gs_off, h->mig_recv.p, h->gr_cnt, h->gr_off, GHOST_REC));
+    if (gr > 0) {
+        LaunchScope ls(h, PISB_K_HALO);
+        k_ghost_append<<<nblk(gr, TPB), TPB, 0, st>>>(gr, n_slots1, h->mig_recv.p, h->xt.p, h->v[0].p, h->v[1].p, h->v[2].p,
+                                                     h->f[0].p, h->f[1].p, h->f[2].p, h->id.p);
+        TRY(check_launch(h, "k_ghost_append"));
+    }
+    h->n = n_slots1 + gr;  // slots entering the sort; the dead ones are dropped by it
+    tw[4] = wall_now();
+
+    // ---- 3. cell sort + list build over owned + ghost atoms; remap the halo index lists ----
+    if (h->kcap == 0) {
+        h->kcap = estimate_kcap(h);
+        TRY(reserve_list(h));
+    }
+    for (int attempt = 0; attempt < 6; ++attempt) {
+        TRY(set_flag(h, FLAG_REBUILD, 1));
+        TRY(set_flag(h, FLAG_MAXNBR, 0));
+        TRY(launch_rebuild_chain(h));
+        {
+            LaunchScope ls(h, PISB_K_HALO);
+            k_inverse_perm<<<nblk(h->n, TPB), TPB, 0, st>>>(h->n, h->order.p, h->newslot.p);
+            if (gs > 0) k_remap<<<nblk(gs, TPB), TPB, 0, st>>>(gs, h->send_idx.p, h->newslot.p);
+            if (gr > 0) {
+                if (attempt == 0) k_ghost_slots<<<nblk(gr, TPB), TPB, 0, st>>>(gr, n_slots1, h->newslot.p, h->ghost_slot.p);
+                else k_remap<<<nblk(gr, TPB), TPB, 0, st>>>(gr, h->ghost_slot.p, h->newslot.p);
+            }
+            TRY(check_launch(h, "halo remap"));
+            h->n_launches += 2;
+        }
+        h->n = n_own + gr;  // live slots (cell-sorted) after the sort compacted the dead ones away
+        tw[5] = wall_now();
+        TRY(read_flags(h));
+        tw[6] = wall_now();
+        const int mx = h->h_flags[FLAG_MAXNBR];
+        h->n_builds_host = h->h_flags[FLAG_NBUILDS];
+        h->max_nbr = mx;
+        if (mx <= h->kcap) {
+            h->list_valid = true;
+            if (trace)
+                fprintf(stderr, "[pisb rank %d] rebuild wall (ms): count-launch %.3f gather1 %.3f mig %.3f ghosts %.3f chain-launch %.3f chain-sync %.3f | leave %d arrive %d ghosts %d\n",
+                        me, 1e3 * (tw[1] - tw[0]), 1e3 * (tw[2] - tw[1]), 1e3 * (tw[3] - tw[2]), 1e3 * (tw[4] - tw[3]),
+                        1e3 * (tw[5] - tw[4]), 1e3 * (tw[6] - tw[5]), stot, rtot, gr);
+            return PISB_OK;
+        }
+        if (h->kcap_user > 0) return fail(h, PISB_ERR_CAPACITY, fmt("neighbour list needs %d slots per atom, list_capacity is %d", mx, h->kcap_user));
+        h->kcap = (int)(mx * 1.25) + 8;
+        TRY(reserve_list(h));
+    }
+    return fail(h, PISB_ERR_CAPACITY, "neighbour-list capacity did not converge");
+}
+
+// Per-step ghost position exchange (no rebuild).
+int halo_exchange(pisb_t *h) {
+    cudaStream_t st = h->stream;
+    if (h->send_total > 0) {
+        LaunchScope ls(h, PISB_K_HALO);
+        k_halo_pack<<<nblk(h->send_total, TPB), TPB, 0, st>>>(h->send_total, h->send_idx.p, h->xt.p, h->halo_send.p);
+        TRY(check_launch(h, "k_halo_pack"));
+    }
+    TRY(exchange(h, reinterpret_cast<const double *>(h->halo_send.p), h->gs_cnt, h->gs_off,
+                 reinterpret_cast<double *>(h->halo_recv.p), h->gr_cnt, h->gr_off, 4));
+    if (h->n_ghost > 0) {
+        LaunchScope ls(h, PISB_K_HALO);
+        k_halo_unpack<<<nblk(h->n_ghost, TPB), TPB, 0, st>>>(h->n_ghost, h->ghost_slot.p, h->halo_recv.p, h->xt.p, h->xf.p, h->box);
+        TRY(check_launch(h, "k_halo_unpack"));
+    }
+    return PISB_OK;
+}
+
+int allreduce_thermo(pisb_t *h, size_t nrec) {
+    LaunchScope ls(h, PISB_K_REDUCE);
+    NCCL_TRY(h, g_nccl.AllReduce(h->thermo_d.p, h->thermo_d.p, nrec * 4, ncclDouble, ncclSum, h->comm, h->stream));
+    return PISB_OK;
+}
+
+int do_compute_multi(pisb_t *h, int accumulate, double *pe) {
+    if (!h->list_valid) TRY(multi_rebuild(h));
+    TRY(check_bad_type(h));
+    TRY(reserve_thermo(h, 2));
+    double *out[3] = {h->f[0].p, h->f[1].p, h->f[2].p};
+    const double *acc[3] = {h->f[0].p, h->f[1].p, h->f[2].p};
+    TRY(launch_force(h, out, accumulate ? acc : nullptr, h->thermo_d.p));
+    TRY(allreduce_thermo(h, 1));
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_thermo, h->thermo_d.p, sizeof(pisb_thermo), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (pe) *pe = h->h_thermo[0].pe;
+    h->forces_current = true;
+    return PISB_OK;
+}
+
+int do_step_nve_multi(pisb_t *h, double dt, int64_t nsteps, pisb_thermo *out) {
+    if (!h->list_valid) TRY(multi_rebuild(h));
+    TRY(check_bad_type(h));
+    const bool trace = std::getenv("PISB_TRACE") != nullptr;
+    double t_vv = 0, t_flag = 0, t_reb = 0, t_halo = 0, t_force = 0, t_tail = 0;
+    int n_reb = 0;
+    const int64_t chunk_max = 4096;
+    int64_t done = 0;
+    while (done < nsteps) {
+        const int64_t m = std::min(chunk_max, nsteps - done);
+        TRY(reserve_thermo(h, (size_t)m + 1));
+        CUDA_TRY(h, cudaMemsetAsync(h->thermo_d.p, 0, sizeof(pisb_thermo) * (m + 1), h->stream));
+        for (int64_t s = 0; s < m; ++s) {
+            pisb_thermo *rec = h->thermo_d.p + s;
+            double t0 = wall_now();
+            if (s == 0) TRY(launch_vv(h, false, true, dt, nullptr));
+            else TRY(launch_vv(h, true, true, dt, rec - 1));
+            double t1 = wall_now();
+            // every rank must take the same branch: max-reduce the skin trigger, then read it
+            NCCL_TRY(h, g_nccl.AllReduce(h->flags + FLAG_REBUILD, h->flags + FLAG_REBUILD, 1, ncclInt, ncclMax, h->comm, h->stream));
+            CUDA_TRY(h, cudaMemcpyAsync(h->h_flags, h->flags, sizeof(int) * FLAG_COUNT, cudaMemcpyDeviceToHost, h->stream));
+            // the ghost exchange is queued BEFORE the host reads the flag, so the read-back latency hides
+            // behind it; on a rebuild step it is merely redundant (the rebuild re-selects the ghosts)
+            TRY(halo_exchange(h));
+            CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+            double t2 = wall_now();
+            const bool reb = h->h_flags[FLAG_REBUILD] != 0;
+            if (reb) TRY(multi_rebuild(h));
+            double t3 = wall_now();
+            double *outp[3] = {h->g[0].p, h->g[1].p, h->g[2].p};
+            TRY(launch_force(h, outp, nullptr, rec));
+            for (int d = 0; d < 3; ++d) std::swap(h->f[d], h->g[d]);
+            double t4 = wall_now();
+            t_vv += t1 - t0;
+            t_flag += t2 - t1;
+            (reb ? t_reb : t_halo) += t3 - t2;
+            n_reb += reb;
+            t_force += t4 - t3;
+        }
+        double t5 = wall_now();
+        TRY(launch_vv(h, true, false, dt, h->thermo_d.p + (m - 1)));
+        TRY(allreduce_thermo(h, (size_t)m));
+        CUDA_TRY(h, cudaMemcpyAsync(h->h_thermo, h->thermo_d.p, sizeof(pisb_thermo) * m, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        t_tail += wall_now() - t5;
+        if (out) std::memcpy(out + done, h->h_thermo, sizeof(pisb_thermo) * m);
+        done += m;
+        h->n_steps += m;
+    }
+    if (trace)
+        fprintf(stderr, "[pisb rank %d] %lld steps host wall (ms): vv %.2f flag+sync %.2f rebuild %.2f (%d) halo %.2f force-launch %.2f tail %.2f\n",
+                h->dc.rank, (long long)nsteps, 1e3 * t_vv, 1e3 * t_flag, 1e3 * t_reb, n_reb, 1e3 * t_halo, 1e3 * t_force, 1e3 * t_tail);
     h->forces_current = true;
     return PISB_OK;
 }
@@ -817,6 +1201,20 @@ int pisb_destroy(pisb_t *h) {
     dev_free(h, h->st_types);
     dev_free(h, h->table_d);
     dev_free(h, h->thermo_d);
+    dev_free(h, h->m_dest);
+    dev_free(h, h->m_pig);
+    dev_free(h, h->m_cnt);
+    dev_free(h, h->m_allcnt);
+    dev_free(h, h->m_off);
+    dev_free(h, h->send_idx);
+    dev_free(h, h->ghost_slot);
+    dev_free(h, h->newslot);
+    dev_free(h, h->mig_send);
+    dev_free(h, h->mig_recv);
+    dev_free(h, h->halo_send);
+    dev_free(h, h->halo_recv);
+    if (h->h_counts) cudaFreeHost(h->h_counts);
+    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     if (h->flags) cudaFree(h->flags);
     if (h->ticket) cudaFree(h->ticket);
     if (h->h_flags) cudaFreeHost(h->h_flags);
@@ -895,6 +1293,7 @@ int pisb_thermo_now(pisb_t *h, pisb_thermo *out) {
                                                           h->ticket, h->thermo_d.p);
         TRY(check_launch(h, "k_observe"));
     }
+    if (h->multi) TRY(allreduce_thermo(h, 1));
     CUDA_TRY(h, cudaMemcpyAsync(h->h_thermo, h->thermo_d.p, sizeof(pisb_thermo), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     *out = h->h_thermo[0];
@@ -921,7 +1320,11 @@ int pisb_neighbours(pisb_t *h, int32_t *nnbr, int32_t *nbr, int64_t cap_per_atom
     if (!h || !nnbr) return PISB_ERR_INVALID;
     if (!h->have_atoms || !h->have_box) return fail(h, PISB_ERR_STATE, "neighbours before upload/set_box");
     CUDA_TRY(h, cudaSetDevice(h->device));
-    TRY(ensure_list(h));
+    if (h->multi) {
+        if (!h->list_valid) TRY(multi_rebuild(h));
+    } else {
+        TRY(ensure_list(h));
+    }
     const int n = h->n;
     std::vector<int> hn(n), hid(n), hl((size_t)h->kcap * h->npad);
     CUDA_TRY(h, cudaMemcpyAsync(hn.data(), h->nnbr.p, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
@@ -929,6 +1332,26 @@ int pisb_neighbours(pisb_t *h, int32_t *nnbr, int32_t *nbr, int64_t cap_per_atom
     CUDA_TRY(h, cudaMemcpyAsync(hl.data(), h->nbr.p, sizeof(int) * hl.size(), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     int64_t total = 0;
+    if (h->multi) {
+        // rows in owned-slot order (the order pisb_download_owned uses); entries are GLOBAL ids
+        std::vector<double4> hx(n);
+        CUDA_TRY(h, cudaMemcpy(hx.data(), h->xt.p, sizeof(double4) * n, cudaMemcpyDeviceToHost));
+        int o = 0;
+        for (int s = 0; s < n; ++s) {
+            long long wb;
+            std::memcpy(&wb, &hx[s].w, 8);
+            if ((wb >> 32) & 1) continue;
+            nnbr[o] = hn[s];
+            total += hn[s];
+            if (nbr) {
+                if (hn[s] > cap_per_atom) return fail(h, PISB_ERR_CAPACITY, "cap_per_atom too small");
+                for (int k = 0; k < hn[s]; ++k) nbr[(size_t)o * cap_per_atom + k] = hid[hl[nbr_at(k, s, h->npad)]];
+            }
+            ++o;
+        }
+        h->total_nbr = total;
+        return PISB_OK;
+    }
     for (int s = 0; s < n; ++s) {
         const int o = hid[s];
         nnbr[o] = hn[s];
@@ -951,8 +1374,8 @@ int pisb_invalidate_list(pisb_t *h) {
 int pisb_stats(pisb_t *h, pisb_stats_t *out) {
     if (!h || !out) return PISB_ERR_INVALID;
     std::memset(out, 0, sizeof *out);
-    out->n_atoms = h->n;
-    out->n_ghost = 0;
+    out->n_atoms = h->multi ? h->n_own : h->n;
+    out->n_ghost = h->multi ? h->n_ghost : 0;
     for (int d = 0; d < 3; ++d) out->n_cells[d] = h->grid.n[d];
     out->list_capacity = h->kcap;
     out->max_neighbours = h->max_nbr;
@@ -986,6 +1409,134 @@ int pisb_timings_reset(pisb_t *h) {
     if (!h) return PISB_ERR_INVALID;
     drain_events(h);
     for (int k = 0; k < PISB_K_COUNT; ++k) h->t_ms[k] = 0.0, h->t_n[k] = 0;
+    return PISB_OK;
+}
+
+
+// ---- multi-GPU entry points -------------------------------------------------------------------
+int pisb_comm_unique_id(void *out, int nbytes) {
+    if (!out || nbytes < (int)sizeof(ncclUniqueId)) return fail(nullptr, PISB_ERR_INVALID, "unique-id buffer must hold 128 bytes");
+    TRY(load_nccl(nullptr));
+    ncclUniqueId id;
+    ncclResult_t r = g_nccl.GetUniqueId(&id);
+    if (r != ncclSuccess) return fail(nullptr, PISB_ERR_COMM, fmt("ncclGetUniqueId: %s", g_nccl.GetErrorString(r)));
+    std::memcpy(out, &id, sizeof id);
+    return PISB_OK;
+}
+
+int pisb_comm_init(pisb_t *h, int rank, int nranks, const void *unique_id, const int *grid3) {
+    if (!h || !unique_id || !grid3) return PISB_ERR_INVALID;
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(h, PISB_ERR_INVALID, "bad rank / nranks");
+    for (int d = 0; d < 3; ++d)
+        if (grid3[d] != 1 && grid3[d] != 2) return fail(h, PISB_ERR_INVALID, "bricks per dimension must be 1 or 2 (one NVSwitch node)");
+    if (grid3[0] * grid3[1] * grid3[2] != nranks) return fail(h, PISB_ERR_INVALID, "grid does not match nranks");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    TRY(load_nccl(h));
+    ncclUniqueId id;
+    std::memcpy(&id, unique_id, sizeof id);
+    NCCL_TRY(h, g_nccl.CommInitRank(&h->comm, nranks, id, rank));
+    h->multi = true;
+    h->dc = Decomp{};
+    for (int d = 0; d < 3; ++d) h->dc.P[d] = grid3[d];
+    h->dc.rank = rank;
+    h->dc.nranks = nranks;
+    h->dc.b[0] = rank % grid3[0];
+    h->dc.b[1] = (rank / grid3[0]) % grid3[1];
+    h->dc.b[2] = rank / (grid3[0] * grid3[1]);
+    CUDA_TRY(h, cudaHostAlloc((void **)&h->h_counts, sizeof(int) * nranks * nranks, cudaHostAllocDefault));
+    h->grid_ok = false;
+    h->list_valid = false;
+    return PISB_OK;
+}
+
+int pisb_upload_owned(pisb_t *h, int64_t n_own, const double *pos, const double *vel, const double *force,
+                      const int32_t *types, const int32_t *gids) {
+    if (!h) return PISB_ERR_INVALID;
+    if (!h->multi) return fail(h, PISB_ERR_STATE, "pisb_comm_init must precede pisb_upload_owned");
+    if (!h->have_box) return fail(h, PISB_ERR_STATE, "pisb_set_box must precede pisb_upload_owned");
+    if (n_own < 0 || n_own > 2000000000LL || (n_own > 0 && (!pos || !types || !gids)))
+        return fail(h, PISB_ERR_INVALID, "bad pisb_upload_owned arguments");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const int n = (int)n_own;
+    // capacity: owned + ghost shell, with head-room for density fluctuations and migration
+    double ratio = 1.0;
+    const double gw = (h->max_rcut + h->skin) * 1.05 + h->skin;
+    for (int d = 0; d < 3; ++d)
+        if (h->dc.P[d] > 1) {
+            const double w = h->box.h[4 * d] / h->dc.P[d];
+            ratio *= (w + 2.0 * gw) / w;
+        }
+    const int cap = (int)std::min(2.0e9, (2.0 * ratio - 1.0) * 1.25 * std::max(n, 1024) + 4096.0);  // owned + stale + fresh ghosts
+    if (cap > h->ncap_atoms) {
+        h->ncap_atoms = cap;
+        h->kcap = 0;
+    }
+    h->n = n;
+    h->n_own = n;
+    h->n_ghost = 0;
+    h->have_atoms = true;
+    h->list_valid = false;
+    h->grid_ok = false;
+    TRY(reserve_atoms(h, h->ncap_atoms));
+    const size_t n3 = (size_t)3 * std::max(n, 1);
+    TRY(dev_reserve(h, h->st_pos, n3));
+    TRY(dev_reserve(h, h->st_vel, n3));
+    TRY(dev_reserve(h, h->st_frc, n3));
+    TRY(dev_reserve(h, h->st_types, (size_t)std::max(n, 1)));
+    TRY(dev_reserve(h, h->m_dest, (size_t)std::max(n, 1)));  // staging for gids
+    if (n > 0) {
+        CUDA_TRY(h, cudaMemcpyAsync(h->st_pos.p, pos, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, h->stream));
+        if (vel) CUDA_TRY(h, cudaMemcpyAsync(h->st_vel.p, vel, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, h->stream));
+        if (force) CUDA_TRY(h, cudaMemcpyAsync(h->st_frc.p, force, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(h, cudaMemcpyAsync(h->st_types.p, types, sizeof(int) * n, cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(h, cudaMemcpyAsync(h->m_dest.p, gids, sizeof(int) * n, cudaMemcpyHostToDevice, h->stream));
+        LaunchScope ls(h, PISB_K_COPY);
+        LoadArgs la{n, h->st_pos.p, vel ? h->st_vel.p : nullptr, force ? h->st_frc.p : nullptr, h->st_types.p, nullptr,
+                    h->xt.p, h->v[0].p, h->v[1].p, h->v[2].p, h->f[0].p, h->f[1].p, h->f[2].p, h->id.p, h->n_types,
+                    h->flags, nullptr, h->box, h->m_dest.p};
+        k_load_aos<<<nblk(n, TPB), TPB, 0, h->stream>>>(la);
+        TRY(check_launch(h, "k_load_aos"));
+    }
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->forces_current = false;
+    return PISB_OK;
+}
+
+int pisb_download_owned(pisb_t *h, int64_t cap, double *pos, double *vel, double *force, int32_t *gids,
+                        int64_t *n_out) {
+    if (!h || !n_out) return PISB_ERR_INVALID;
+    if (!h->multi || !h->have_atoms) return fail(h, PISB_ERR_STATE, "pisb_download_owned needs multi-GPU mode and uploaded atoms");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    const int n = h->n;
+    std::vector<double4> hx(n);
+    std::vector<int> hid(n);
+    std::vector<double> hv[3], hf[3];
+    CUDA_TRY(h, cudaMemcpy(hx.data(), h->xt.p, sizeof(double4) * n, cudaMemcpyDeviceToHost));
+    CUDA_TRY(h, cudaMemcpy(hid.data(), h->id.p, sizeof(int) * n, cudaMemcpyDeviceToHost));
+    for (int d = 0; d < 3; ++d) {
+        if (vel) {
+            hv[d].resize(n);
+            CUDA_TRY(h, cudaMemcpy(hv[d].data(), h->v[d].p, sizeof(double) * n, cudaMemcpyDeviceToHost));
+        }
+        if (force) {
+            hf[d].resize(n);
+            CUDA_TRY(h, cudaMemcpy(hf[d].data(), h->f[d].p, sizeof(double) * n, cudaMemcpyDeviceToHost));
+        }
+    }
+    int64_t o = 0;
+    for (int s = 0; s < n; ++s) {
+        long long wb;
+        std::memcpy(&wb, &hx[s].w, 8);
+        if ((wb >> 32) & 1) continue;
+        if (o >= cap) return fail(h, PISB_ERR_CAPACITY, "pisb_download_owned: cap too small");
+        if (pos) pos[3 * o] = hx[s].x, pos[3 * o + 1] = hx[s].y, pos[3 * o + 2] = hx[s].z;
+        if (vel) vel[3 * o] = hv[0][s], vel[3 * o + 1] = hv[1][s], vel[3 * o + 2] = hv[2][s];
+        if (force) force[3 * o] = hf[0][s], force[3 * o + 1] = hf[1][s], force[3 * o + 2] = hf[2][s];
+        if (gids) gids[o] = hid[s];
+        ++o;
+    }
+    *n_out = o;
     return PISB_OK;
 }
 

@@ -3,7 +3,8 @@
 post-processing (drift removal + rescale, src/atoms/velocities.rs:35-59).
 
 The reference's Gaussian stream (rand 0.10 SmallRng + rand_distr Normal) is third-party and
-unpinned, so velocities come from a generator defined here (numpy Philox, counter-based); the same
+unpinned, so velocities come from a generator defined here (splitmix64 + Box-Muller keyed by the
+global atom id, see decomposition.gaussian_by_id); the same
 arrays are then fed to both the GPU path and the oracle.
 """
 from __future__ import annotations
@@ -30,9 +31,10 @@ def fcc_positions(a: float, nx: int, ny: int, nz: int) -> np.ndarray:
 def create_velocities(n: int, masses_per_atom: np.ndarray, temperature: float, seed: int) -> np.ndarray:
     """Gaussian velocities with sigma_i = sqrt(kB T / m_i) (velocities.rs:24), then remove_drift
     (:35-50) and rescale_to_temperature (:52-59)."""
-    rng = np.random.Generator(np.random.Philox(seed))
+    from .decomposition import gaussian_by_id  # counter-based: identical values on any GPU count
+
     sig = np.sqrt(KB_KJPERMOLEKELVIN * temperature / masses_per_atom)
-    v = rng.standard_normal((n, 3)) * sig[:, None]
+    v = gaussian_by_id(np.arange(n), seed) * sig[:, None]
     total_mass = masses_per_atom.sum()
     vcm = (v * masses_per_atom[:, None]).sum(axis=0) / total_mass
     v -= vcm[None, :]
