@@ -1,8 +1,8 @@
-"""Build recipe for the native pieces (run by __graft_entry__.build()).
+"""Build recipe for the PRODUCT's native pieces (run by __graft_entry__.build(); the test oracle has
+its own recipe in oracle/pis_oracle.py).
 
   pis_b200/libpisb200.so   hand-written sm_100a kernels + C ABI (include/pisb200.h)      [product]
   pis_b200/pis_b200_cli    C++ host CLI mirroring the reference's `pis -i input.pis`       [product]
-  oracle/libpis_oracle.so  plain-C CPU restatement of the reference hot path              [test infrastructure]
 
 Everything is compiled in-tree with explicit nvcc / gcc command lines so the artefacts travel with
 the repo snapshot to the GPU box (no JIT cache).
@@ -18,8 +18,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "pis_b200", "csrc")
 LIB = os.path.join(ROOT, "pis_b200", "libpisb200.so")
 CLI = os.path.join(ROOT, "pis_b200", "pis_b200_cli")
-ORACLE_SRC = os.path.join(ROOT, "oracle", "pis_oracle.c")
-ORACLE_LIB = os.path.join(ROOT, "oracle", "libpis_oracle.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -89,20 +87,11 @@ def build_cli(force: bool = False) -> str | None:
     return CLI
 
 
-def build_oracle(force: bool = False) -> str:
-    if not force and _newer(ORACLE_LIB, [ORACLE_SRC]):
-        return ORACLE_LIB
-    _run(["gcc", "-O2", "-std=c11", "-ffp-contract=off", "-fno-fast-math", "-fopenmp", "-fPIC", "-shared",
-          "-fvisibility=hidden", "-o", ORACLE_LIB, ORACLE_SRC, "-lm"])
-    return ORACLE_LIB
-
-
 def build_all(force: bool = False) -> None:
     build_library(force)
     build_cli(force)
-    build_oracle(force)
 
 
 if __name__ == "__main__":
     build_all(force="--force" in sys.argv)
-    print("built:", LIB, ORACLE_LIB)
+    print("built:", LIB)

@@ -1,0 +1,52 @@
+"""Generate the committed golden fixtures.
+
+  python tests/golden/make_golden.py
+
+* oracle_small.json   : a 108-atom jittered FCC-argon system -- positions, velocities, step-0 PE and forces,
+                        the full neighbour list with skin, and a 25-step NVE thermo trace, all produced by the
+                        CPU oracle (oracle/pis_oracle.c).  NOT reference output: the Rust reference cannot be
+                        built in this image (parity unpinned).
+* argon4000_head.json : the header and first 16 atoms of the reference's example/argon4000.txt, read from
+                        /root/reference when present -- pins the FCC generator's atom order and the reader.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from oracle.pis_oracle import Oracle  # noqa: E402
+from pis_b200.lattice import fcc_argon  # noqa: E402
+
+
+def main():
+    atoms = fcc_argon(3, temperature=30.0, seed=21, jitter=0.12)
+    L = float(atoms.sim_box.h[0, 0])
+    rc, skin, dt, steps = 7.0, 0.9, 0.25, 25   # L = 16.23 >= 2 * (rc + skin)
+    o = Oracle.cubic(L)
+    o.insert(1, 1, 0.238, 3.405, rc)
+    pe, f = o.compute_potential(atoms.positions, atoms.type_ids)
+    start, nbr = o.build_neighbour_list(atoms.positions, atoms.type_ids, extra=skin)
+    x, v = atoms.positions.copy(), atoms.velocities.copy()
+    th = o.run_nve(x, v, np.zeros_like(x), atoms.type_ids, dt, steps)
+    g = {"L": L, "rc": rc, "skin": skin, "dt": dt, "steps": steps, "eps": 0.238, "sigma": 3.405, "mass": 39.948,
+         "positions": atoms.positions.tolist(), "velocities": atoms.velocities.tolist(),
+         "types": atoms.type_ids.tolist(), "pe": pe, "forces": f.tolist(),
+         "neighbours_skin": [sorted(nbr[start[i]:start[i + 1]].tolist()) for i in range(atoms.n_atoms)],
+         "thermo": th.tolist(), "positions_end": x.tolist()}
+    with open(os.path.join(HERE, "oracle_small.json"), "w") as fh:
+        json.dump(g, fh)
+    ref = "/root/reference/example/argon4000.txt"
+    if os.path.exists(ref):
+        with open(ref) as fh:
+            lines = [ln.rstrip("\n") for ln in fh.readlines()[:32]]
+        with open(os.path.join(HERE, "argon4000_head.json"), "w") as fh:
+            json.dump({"source": "example/argon4000.txt (first 32 lines)", "lines": lines}, fh, indent=0)
+    print("golden fixtures written")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,221 @@
+"""CPU tests of the oracle (oracle/pis_oracle.c).  The reference's own tests pin no physics and the
+Rust reference cannot be built here, so the oracle is pinned against analytic known answers, an
+independent numpy restatement, its own O(N^2) driver and the committed golden vectors."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle.pis_oracle import Oracle
+from pis_b200.lattice import fcc_argon
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+EPS, SIG = 0.238, 3.405
+
+
+def numpy_lj(pos, L, eps, sig, rc):
+    """Independent restatement: O(N^2), minimum image as d - L*round(d/L) (NOT the reference's h*(hinv*d) form)."""
+    n = len(pos)
+    d = pos[None, :, :] - pos[:, None, :]
+    d -= L * np.round(d / L)
+    r2 = (d * d).sum(-1)
+    np.fill_diagonal(r2, np.inf)
+    mask = np.sqrt(r2) <= rc
+    inv = np.where(mask, 1.0 / r2, 0.0)
+    s6 = (sig * sig * inv) ** 3
+    ucut = 4 * eps * ((sig / rc) ** 12 - (sig / rc) ** 6)
+    u = np.where(mask, 4 * eps * (s6 * s6 - s6) - ucut, 0.0)
+    fs = np.where(mask, 24 * eps * (2 * s6 * s6 - s6) * inv, 0.0)
+    f = -(fs[:, :, None] * d).sum(axis=1)
+    return 0.5 * u.sum(), f, mask
+
+
+def make(L, rc=8.5):
+    o = Oracle.cubic(L)
+    o.insert(1, 1, EPS, SIG, rc)
+    return o
+
+
+def test_two_atom_minimum():
+    rc = 8.5
+    o = make(40.0, rc)
+    r = 2.0 ** (1.0 / 6.0) * SIG
+    u, f = o.lj_pair(EPS, SIG, rc, [r, 0.0, 0.0])
+    ucut = 4 * EPS * ((SIG / rc) ** 12 - (SIG / rc) ** 6)
+    assert abs(u - (-EPS - ucut)) < 1e-14
+    assert np.abs(f).max() < 1e-13
+    u2, _ = o.lj_pair(EPS, SIG, rc, [r, 0.0, 0.0], shift=False)
+    assert abs(u2 + EPS) < 1e-14
+
+
+def test_argon4000_lattice_sum():
+    """example/argon4000.txt geometry (10^3 FCC cells, a = 5.41, rc = 8.5): SURVEY 8c known answer."""
+    atoms = fcc_argon(10, temperature=0.0)
+    o = make(54.1)
+    assert o.divide_into_cells(o.max_rcut()) == (6, 6, 6)
+    pe, f = o.compute_potential(atoms.positions, atoms.type_ids)
+    assert abs(pe - (-6956.99645673589)) < 1e-8
+    assert np.abs(f).max() < 1e-12
+    start, nbr = o.build_neighbour_list(atoms.positions, atoms.type_ids)
+    assert len(nbr) == 216000 and np.all(np.diff(start) == 54)
+    start, nbr = o.build_neighbour_list(atoms.positions, atoms.type_ids, extra=0.3 * SIG)
+    assert np.all(np.diff(start) == 86)
+
+
+def test_cell_driver_equals_n2_and_numpy():
+    atoms = fcc_argon(6, temperature=0.0, jitter=0.25, seed=4)
+    L = atoms.sim_box.h[0, 0]
+    o = make(L)
+    pe, f = o.compute_potential(atoms.positions, atoms.type_ids)
+    pe2, f2 = o.compute_potential(atoms.positions, atoms.type_ids, mode="n2")
+    pe3, f3 = o.compute_potential(atoms.positions, atoms.type_ids, mode="omp", threads=3)
+    assert abs(pe - pe2) < 1e-11 * abs(pe) and np.abs(f - f2).max() < 1e-12
+    assert abs(pe - pe3) < 1e-11 * abs(pe) and np.abs(f - f3).max() < 1e-12
+    pe_np, f_np, _ = numpy_lj(atoms.positions, L, EPS, SIG, 8.5)
+    assert abs(pe - pe_np) < 1e-10 * abs(pe)
+    assert np.abs(f - f_np).max() < 1e-10 * np.abs(f_np).max()
+    assert np.abs(f.sum(axis=0)).max() < 1e-11  # Newton's third law
+
+
+def test_full_list_matches_bruteforce_and_list_consumer():
+    atoms = fcc_argon(6, temperature=0.0, jitter=0.3, seed=9)
+    L = atoms.sim_box.h[0, 0]
+    o = make(L)
+    for extra in (0.0, 1.0215):
+        start, nbr = o.build_neighbour_list(atoms.positions, atoms.type_ids, extra=extra)
+        _, _, mask = numpy_lj(atoms.positions, L, EPS, SIG, 8.5 + extra)
+        for i in range(0, atoms.n_atoms, 37):
+            assert np.array_equal(np.sort(nbr[start[i]:start[i + 1]]), np.nonzero(mask[i])[0])
+        pe_l, f_l = o.compute_potential_list(atoms.positions, atoms.type_ids, start, nbr)
+        pe, f = o.compute_potential(atoms.positions, atoms.type_ids)
+        assert abs(pe - pe_l) < 1e-11 * abs(pe) and np.abs(f - f_l).max() < 1e-12
+
+
+def test_forward_offsets_are_a_half_shell():
+    import ctypes as C
+
+    o = make(30.0)
+    ptr = C.cast(o.lib.orc_forward_offsets(), C.POINTER(C.c_int * 42))
+    offs = {tuple(ptr.contents[3 * k:3 * k + 3]) for k in range(14)}
+    neg = {(-a, -b, -c) for a, b, c in offs}
+    assert len(offs) == 14 and offs & neg == {(0, 0, 0)} and len(offs | neg) == 27
+
+
+def test_box_wrap_and_minimum_image_semantics():
+    o = make(54.1)
+    assert o.hinv[0, 0] == 1.0 / 54.1  # adjugate/determinant form happens to equal 1/L for this box
+    p2 = make(64.0)  # power-of-two box: s = 0.5 exactly
+    assert np.array_equal(p2.min_image([32.0, 0.0, 0.0]), [-32.0, 0.0, 0.0])       # round half away from zero
+    assert np.array_equal(p2.min_image([-32.0, 0.0, 0.0]), [32.0, 0.0, 0.0])
+    assert np.array_equal(p2.min_image([96.0, -31.0, 33.0]), [-32.0, -31.0, -31.0])
+    w = p2.wrap([-1e-17, 64.0, 70.0])
+    assert w[0] == 64.0 and w[1] == 0.0 and w[2] == 6.0                            # s - floor(s) may round to 1.0 -> x == L
+    assert o.wrap([0.0, 54.1, 60.0])[1] == 54.1 * (54.1 * (1.0 / 54.1) - 0.0)      # L itself is (almost) a fixed point
+    tri = Oracle([10.0, 0, 0, 2.0, 9.0, 0, 1.0, -1.5, 8.0])
+    assert np.allclose(tri.h @ tri.hinv, np.eye(3), atol=1e-15)
+    assert abs(tri.lib.orc_box_volume(tri.box) - 720.0) < 1e-12
+    with pytest.raises(ValueError):
+        Oracle([1.0, 0, 0, 2.0, 0, 0, 0, 0, 1.0])
+
+
+def test_cell_binning_saturates_like_rust_casts():
+    o = make(30.0, rc=9.0)
+    n = o.divide_into_cells(9.0)
+    assert n == (3, 3, 3)
+    pos = np.array([[-0.5, 1.0, 1.0], [30.0, 1.0, 1.0], [31.0, 29.9, 1.0], [float("nan"), 1.0, 1.0]])
+    cell_of, start, atoms = o.rcut_cells(pos, *n)
+    assert cell_of[0] == 0          # negative -> saturates to cell 0 (not the periodic cell)
+    assert cell_of[1] == 0          # s == 1.0 -> cell n -> % n == 0
+    assert cell_of[2] == 0 + 2 * 3  # x wraps via %, y in the last cell
+    assert cell_of[3] == 0          # NaN -> 0
+    assert start[-1] == 4 and sorted(atoms.tolist()) == [0, 1, 2, 3]
+    assert o.divide_into_cells(100.0) == (1, 1, 1)
+
+
+def test_observables_and_step_against_numpy():
+    atoms = fcc_argon(5, temperature=20.0, jitter=0.1, seed=2)
+    L = atoms.sim_box.h[0, 0]
+    o = make(L)
+    x, v = atoms.positions.copy(), atoms.velocities.copy()
+    _, f = o.compute_potential(x, atoms.type_ids)
+    ke = o.kinetic_energy(v, atoms.type_ids)
+    assert abs(ke - 0.5 * 39.948 * (v * v).sum()) < 1e-12 * ke
+    assert abs(o.temperature(len(x), ke) - 2 * ke / (3 * len(x) * 0.0083144621)) < 1e-12
+    assert abs(o.temperature(len(x), ke) - 20.0) < 1e-9  # create_velocities rescales to T exactly
+    vir = o.virial_trace(x, f)
+    assert abs(vir - (x * f).sum()) < 1e-10 * max(abs(vir), 1.0)
+    assert abs(o.pressure(x, f, ke) - (2 * ke + vir) / (3 * L ** 3)) < 1e-15
+    # one velocity-Verlet step, restated with numpy
+    dt = 0.25
+    a0 = f / 39.948
+    x_np = x + (v * dt + (a0 * 0.5) * dt * dt)
+    x_np -= np.floor(x_np / L) * L
+    pe_np, f_np, _ = numpy_lj(x_np, L, EPS, SIG, 8.5)
+    v_np = v + ((a0 + f_np / 39.948) * 0.5) * dt
+    pe = o.verlet_step_nve(x, v, f, atoms.type_ids, dt)
+    assert np.abs(x - x_np).max() < 1e-12 and np.abs(v - v_np).max() < 1e-13
+    assert abs(pe - pe_np) < 1e-10 * abs(pe)
+
+
+def test_nve_conserves_energy_and_serial_equals_omp():
+    atoms = fcc_argon(5, temperature=5.0, seed=12345)
+    L = atoms.sim_box.h[0, 0]
+    o = make(L)
+    x, v = atoms.positions.copy(), atoms.velocities.copy()
+    th = o.run_nve(x, v, np.zeros_like(x), atoms.type_ids, 0.25, 200)
+    h = th[1:, 2]
+    assert np.abs(h - h[0]).max() < 2e-4 * abs(h[0])  # force is not shifted at rc: small drift is inherent
+    x2, v2 = atoms.positions.copy(), atoms.velocities.copy()
+    th2 = o.run_nve(x2, v2, np.zeros_like(x2), atoms.type_ids, 0.25, 200, mode="omp", threads=2)
+    assert np.max(np.abs(th2[1:, 0] - th[1:, 0]) / np.abs(th[1:, 0])) < 1e-11
+
+
+def test_missing_pair_and_key_order_quirk():
+    """Table keys are stored as given and looked up sorted: an entry given as (2,1) is never found."""
+    atoms = fcc_argon(4, temperature=0.0, jitter=0.1, seed=1)
+    atoms.type_ids[::2] = 2
+    L = atoms.sim_box.h[0, 0]
+    good = Oracle.cubic(L, n_types=2, masses=(39.948, 20.0))
+    bad = Oracle.cubic(L, n_types=2, masses=(39.948, 20.0))
+    for o, key in ((good, (1, 2)), (bad, (2, 1))):
+        o.insert(1, 1, EPS, SIG, 8.0)
+        o.insert(2, 2, 0.1, 3.0, 7.0)
+        o.insert(key[0], key[1], 0.15, 3.2, 7.5)
+    pe_g, _ = good.compute_potential(atoms.positions, atoms.type_ids)
+    pe_b, _ = bad.compute_potential(atoms.positions, atoms.type_ids)
+    only_same = Oracle.cubic(L, n_types=2, masses=(39.948, 20.0))
+    only_same.insert(1, 1, EPS, SIG, 8.0)
+    only_same.insert(2, 2, 0.1, 3.0, 7.0)
+    pe_s, _ = only_same.compute_potential(atoms.positions, atoms.type_ids)
+    assert pe_g != pe_b
+    # (2,1) is unreachable for pair lookup but still counts in max_rcut (cell grid) -> same energy as without it
+    assert abs(pe_b - pe_s) < 1e-12 * abs(pe_s)
+    assert bad.max_rcut() == 8.0 and good.max_rcut() == 8.0
+
+
+def test_sqrt_free_threshold_is_exact():
+    o = make(30.0)
+    for rc in (8.5, 8.5125, 9.534, 2.5 * 3.405, 1.0, 7.0 / 3.0):
+        t = o.rcut_threshold(rc)
+        assert np.sqrt(t) <= rc < np.sqrt(np.nextafter(t, np.inf))
+
+
+def test_golden_vectors():
+    """tests/golden/oracle_small.json was produced by tests/golden/make_golden.py from this oracle; it pins
+    the oracle against silent drift and is what the GPU tests also compare with."""
+    with open(os.path.join(GOLDEN, "oracle_small.json")) as f:
+        g = json.load(f)
+    pos = np.array(g["positions"])
+    vel = np.array(g["velocities"])
+    types = np.array(g["types"], dtype=np.int32)
+    o = make(g["L"], g["rc"])
+    pe, f = o.compute_potential(pos, types)
+    assert pe == g["pe"]
+    assert np.array_equal(f, np.array(g["forces"]))
+    start, nbr = o.build_neighbour_list(pos, types, extra=g["skin"])
+    assert [sorted(nbr[start[i]:start[i + 1]].tolist()) for i in range(len(pos))] == g["neighbours_skin"]
+    x, v, ff = pos.copy(), vel.copy(), np.zeros_like(pos)
+    th = o.run_nve(x, v, ff, types, g["dt"], g["steps"])
+    assert np.array_equal(th, np.array(g["thermo"]))
+    assert np.array_equal(x, np.array(g["positions_end"]))
