@@ -1,5 +1,5 @@
 """Build recipe for the PRODUCT's native pieces (run by __graft_entry__.build(); the test oracle has
-its own recipe in oracle/pis_oracle.py).
+its own recipe under oracle/).
 
   pis_b200/libpisb200.so   hand-written sm_100a kernels + C ABI (include/pisb200.h)      [product]
   pis_b200/pis_b200_cli    C++ host CLI mirroring the reference's `pis -i input.pis`       [product]
