@@ -62,13 +62,11 @@ def _sources(dirpath: str, exts: tuple[str, ...]) -> list[str]:
 
 
 def build_library(force: bool = False, verbose_ptxas: bool = False) -> str:
-    deps = _sources(CSRC, (".cu", ".cuh", ".h", ".cpp", ".hpp")) + [os.path.join(ROOT, "include", "pisb200.h")]
+    deps = _sources(CSRC, (".cu", ".cuh")) + [os.path.join(ROOT, "include", "pisb200.h")]
     if not force and _newer(LIB, deps):
         return LIB
     cus = [s for s in _sources(CSRC, (".cu",))]
-    cpps = [s for s in _sources(os.path.join(CSRC, "host"), (".cpp",)) if not s.endswith("main.cpp")] \
-        if os.path.isdir(os.path.join(CSRC, "host")) else []
-    cmd = [_nvcc(), *NVCC_FLAGS, "-shared", "-o", LIB, *cus, *cpps]
+    cmd = [_nvcc(), *NVCC_FLAGS, "-shared", "-o", LIB, *cus]
     if verbose_ptxas:
         cmd += ["-Xptxas", "-v"]
     _run(cmd)
@@ -83,7 +81,8 @@ def build_cli(force: bool = False) -> str | None:
     if not force and _newer(CLI, deps):
         return CLI
     _run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-I", os.path.join(ROOT, "include"), "-I", CSRC,
-          "-o", CLI, main, "-L", os.path.dirname(LIB), "-lpisb200", "-Wl,-rpath,$ORIGIN"])
+          "-I", os.path.join(CSRC, "host"), "-o", CLI, main, os.path.join(CSRC, "host", "pis_host.cpp"),
+          "-L", os.path.dirname(LIB), "-lpisb200", "-Wl,-rpath,$ORIGIN"])
     return CLI
 
 

@@ -1,0 +1,196 @@
+"""The C++ host CLI (pis_b200/pis_b200_cli): input-script / LAMMPS-data readers (CPU, via --check), and the
+full NVE run with thermo lines + dump.lammpstrj against the oracle (GPU).  The parser cases follow the
+reference's own test module (src/tests/command_tests.rs), driven through the script instead of rstest."""
+import json
+import os
+import subprocess
+from decimal import Decimal
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "pis_b200", "pis_b200_cli")
+
+DATA3 = """3 atoms
+1 atom types
+
+0.0 5.0 xlo xhi
+0.0 5.0 ylo yhi
+0.0 5.0 zlo zhi
+
+Masses
+1 39.948
+
+Atoms
+1 1 0.0 0.0 0.0   # trailing comments are tolerated (positional parsing)
+2 1 1.0 1.0 1.0
+3 1 2.5 2.5 2.5
+"""
+
+
+def rust_display(x: float) -> str:
+    if x != x:
+        return "NaN"
+    s = format(Decimal(repr(float(x))), "f")
+    if "." in s:
+        s = s.rstrip("0").rstrip(".")
+    return s if s not in ("", "-") else "0"
+
+
+def check(tmp_path, script: str, data: str | None = None, expect_fail=False):
+    if data is not None:
+        (tmp_path / "data.txt").write_text(data)
+    (tmp_path / "in.pis").write_text(script)
+    r = subprocess.run([CLI, "-i", "in.pis", "--check"], cwd=tmp_path, capture_output=True, text=True)
+    if expect_fail:
+        assert r.returncode == 1 and r.stderr.startswith("Error: "), (r.returncode, r.stderr)
+        return r.stderr.strip()
+    assert r.returncode == 0, r.stderr
+    return json.loads(r.stdout)
+
+
+def test_defaults_and_basic_commands(tmp_path):
+    ctx = check(tmp_path, "timestep 0.005\nrun 250\n")
+    assert ctx["timestep"] == 0.005 and ctx["steps"] == 250 and ctx["ensemble"] == "NVE"
+    assert ctx["dump"] == {"name": "default_dump", "group": "all", "style": "atoms", "dump_step": 1, "file_name": "dump.lammpstrj"}
+    ctx = check(tmp_path, "# comment\n\nrun\n   timestep 0.25 # inline comment\n")  # <2 tokens -> ignored
+    assert ctx["timestep"] == 0.25 and ctx["steps"] == 100
+    ctx = check(tmp_path, "dump dp1 all atom 10 dump.lammpstrj\n")
+    assert ctx["dump"]["dump_step"] == 10 and ctx["dump"]["style"] == "atom" and ctx["dump"]["name"] == "dp1"
+
+
+@pytest.mark.parametrize("script,needle", [
+    ("frobnicate 1 2\n", "Invalid command frobnicate found line: 1"),
+    ("timestep abc\n", "Error parsing floating number from string abc"),
+    ("run -5\n", "Negative value -5 not allowed on line: 1"),
+    ("run 1.5\n", "Error parsing integer number from string 1.5: invalid digit found in string"),
+    ("run 99999999999\n", "number too large to fit in target type"),
+    ("velocity all set 1 2 3\n", "Invalid argument: set at line: 1"),
+    ("velocity all create 5.0 1 dist triangular\n", "Invalid argument: triangular"),
+    ("velocity all create 5.0 1 loop geom\n", "Invalid argument: loop"),
+    ("velocity all\n", "Missing argument on line 1"),
+    ("pair_coeff 1 1 0.2 3.4\n", "Potential manager not initialized"),
+    ("dump d all atom x out.traj\n", "Error parsing integer number from string x"),
+    ("dump d all atom 5\n", "Missing argument on line 1"),
+    ("fix f all nvt temp 1.0 2.0\n", "Missing argument on line 1"),
+    ("fix f all nvt pressure 1 2 3\n", "Invalid argument: pressure"),
+    ("read_data nope.txt\n", "Failed to open input file 'nope.txt'"),
+])
+def test_parser_errors(tmp_path, script, needle):
+    assert needle in check(tmp_path, script, expect_fail=True)
+
+
+def test_velocity_command(tmp_path):
+    ctx = check(tmp_path, "velocity all create 300.0 12345 dist gaussian\n")
+    assert ctx["velocity"] == {"group": "all", "start_velocity": True, "temperature": 300, "seed": 12345, "dist": "gaussian"}
+    ctx = check(tmp_path, "velocity all create 10.0\n")   # missing seed -> 0
+    assert ctx["velocity"]["seed"] == 0
+    ctx = check(tmp_path, "velocity all create 10.0 dist uniform\n")  # non-integer seed token -> seed 0, token re-read as keyword
+    assert ctx["velocity"]["seed"] == 0 and ctx["velocity"]["dist"] == "uniform"
+
+
+def test_fix_selects_ensemble(tmp_path):
+    assert check(tmp_path, "fix a all nvt temp 5.0 5.0 50\n")["ensemble"] == "NVT"
+    assert check(tmp_path, "fix a all npt temp 5.0 50.0 100 iso 0.01 0.01 1000\n")["ensemble"] == "NPT"
+    assert check(tmp_path, "fix a all nve temp 5.0 50.0 100\n")["ensemble"] == "NVE"   # unknown style: silently ignored
+    assert check(tmp_path, "fix a all nvt iso 1 1 1\n")["ensemble"] == "NVE"           # iso without npt: ignored
+
+
+def test_read_data(tmp_path):
+    ctx = check(tmp_path, "read_data data.txt\n", DATA3)
+    a = ctx["atoms"]
+    assert a["n_atoms"] == 3 and a["box"] == [5, 5, 5] and a["masses"] == [39.948]
+    assert a["first_positions"] == [0, 0, 0, 1, 1, 1, 2.5, 2.5, 2.5]
+    assert ctx["potential"] is None
+    # with neither a Velocities section nor a velocity command, 300 K / seed 0 velocities are created silently
+    assert ctx["velocity"]["start_velocity"] is True and any(v != 0 for v in a["first_velocities"])
+    for bad_id in ("0", "4"):
+        msg = check(tmp_path, "read_data data.txt\n", DATA3.replace("3 1 2.5", f"{bad_id} 1 2.5"), expect_fail=True)
+        assert f"Atom count mismatch: expected 3, found {bad_id}" in msg
+
+
+def test_velocities_section_and_paircoeffs(tmp_path):
+    data = DATA3 + "\nVelocities\n1 0.1 0.2 0.3\n2 0.0 0.0 0.0\n3 -0.1 -0.2 -0.3\n\nPairCoeffs\n1 0.238 3.405 8.5\n"
+    ctx = check(tmp_path, "read_data data.txt\n", data)
+    assert ctx["velocity"]["start_velocity"] is False
+    assert ctx["atoms"]["first_velocities"] == [0.1, 0.2, 0.3, 0, 0, 0, -0.1, -0.2, -0.3]
+    assert ctx["potential"]["pairs"] == [{"i": 1, "j": 1, "epsilon": 0.238, "sigma": 3.405, "rcut": 8.5}]
+    # a velocity command AFTER read_data replaces the context and re-randomises (commands.rs:80,141)
+    ctx = check(tmp_path, "read_data data.txt\nvelocity all create 5.0 7\n", data)
+    assert ctx["velocity"]["start_velocity"] is True
+    # default rc = 2.5 sigma; and the reference's "i j eps sigma rc" mis-parse (token 1 read as epsilon)
+    ctx = check(tmp_path, "read_data data.txt\n", DATA3 + "\nPairCoeffs\n1 0.5 2.0\n")
+    assert ctx["potential"]["pairs"][0]["rcut"] == 5
+    ctx = check(tmp_path, "read_data data.txt\n", DATA3.replace("1 atom types", "2 atom types") + "\nPairCoeffs\n1 2 0.6 1.1 2.8\n")
+    assert ctx["potential"]["pairs"] == [{"i": 1, "j": 1, "epsilon": 2, "sigma": 0.6, "rcut": 1.1}]
+
+
+def test_pair_style_replaces_data_file_potential(tmp_path):
+    data = DATA3 + "\nPairCoeffs\n1 0.238 3.405 8.5\n"
+    ctx = check(tmp_path, "read_data data.txt\npair_style lj/cut 7.0\npair_coeff 1 1 0.1 3.0\npair_coeff 2 1 0.2 3.1 6.5\n", data)
+    assert ctx["potential"]["pairs"] == [{"i": 1, "j": 1, "epsilon": 0.1, "sigma": 3, "rcut": 7},
+                                         {"i": 2, "j": 1, "epsilon": 0.2, "sigma": 3.1, "rcut": 6.5}]   # key kept as given
+    assert "Unknown pair style: 'eam'" in check(tmp_path, "pair_style eam 1.0\n", expect_fail=True)
+
+
+def test_cli_errors(tmp_path):
+    r = subprocess.run([CLI, "-i", "missing.pis"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 1 and "Failed to open input file 'missing.pis'" in r.stderr
+    (tmp_path / "in.pis").write_text("read_data data.txt\nrun 3\n")
+    (tmp_path / "data.txt").write_text(DATA3)
+    r = subprocess.run([CLI, "-i", "in.pis"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 1 and "Potential manager not initialized" in r.stderr
+
+
+@pytest.mark.gpu
+def test_cli_nve_run_matches_oracle(tmp_path):
+    """example/input.pis shape (NVE): thermo lines and dump.lammpstrj against the oracle's Simulation::run."""
+    from oracle.pis_oracle import Oracle
+    from pis_b200.lattice import fcc_argon
+
+    atoms = fcc_argon(6, temperature=5.0, seed=12345)
+    n, L = atoms.n_atoms, atoms.sim_box.h[0, 0]
+    lines = [f"{n} atoms", "1 atom types", "", f"0.0 {rust_display(L)} xlo xhi", f"0.0 {rust_display(L)} ylo yhi",
+             f"0.0 {rust_display(L)} zlo zhi", "", "Masses", "1 39.948", "", "PairCoeffs", "1 0.238 3.405 8.5", "", "Atoms"]
+    lines += [f"{i + 1} 1 {repr(float(p[0]))} {repr(float(p[1]))} {repr(float(p[2]))}" for i, p in enumerate(atoms.positions)]
+    lines += ["", "Velocities"]
+    lines += [f"{i + 1} {repr(float(v[0]))} {repr(float(v[1]))} {repr(float(v[2]))}" for i, v in enumerate(atoms.velocities)]
+    (tmp_path / "argon.txt").write_text("\n".join(lines) + "\n")
+    steps = 40
+    (tmp_path / "input.pis").write_text(f"timestep 0.25\nread_data argon.txt\ndump dp1 all atom 10 dump.lammpstrj\nrun {steps}\n")
+    r = subprocess.run([CLI, "-i", "input.pis", "--skin", "1.0215"], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    out = r.stdout.strip().splitlines()
+
+    o = Oracle.cubic(L)
+    o.insert(1, 1, 0.238, 3.405, 8.5)
+    x, v = atoms.positions.copy(), atoms.velocities.copy()
+    snaps = {0: x.copy()}
+    f = np.zeros_like(x)
+    pe0, _ = o.compute_potential(x, atoms.type_ids, forces=f)
+    assert out[0].split()[0] == "0" and abs(float(out[0].split()[1]) - pe0) <= 1e-9 * abs(pe0)
+    assert len(out) == steps + 1
+    for s in range(1, steps + 1):
+        pe = o.verlet_step_nve(x, v, f, atoms.type_ids, 0.25)
+        ke = o.kinetic_energy(v, atoms.type_ids)
+        ref = [pe, ke, pe + ke, o.temperature(n, ke), o.pressure(x, f, ke)]
+        got = out[s].split()
+        assert got[0] == str(s) and len(got) == 6
+        for g, e in zip(got[1:], ref):
+            assert len(g.split(".")[1]) == 3                      # {:.3}
+            assert abs(float(g) - e) <= 1.1e-3 + 1e-9 * abs(e)
+        if s % 10 == 0:
+            snaps[s] = x.copy()
+    dump = (tmp_path / "dump.lammpstrj").read_text().splitlines()
+    frame = 9 + n
+    assert len(dump) == frame * (steps // 10 + 1)
+    for k, s in enumerate(sorted(snaps)):
+        blk = dump[k * frame:(k + 1) * frame]
+        assert blk[:9] == ["ITEM: TIMESTEP", str(s), "ITEM: NUMBER OF ATOMS", str(n), "ITEM: BOX BOUNDS pp pp pp",
+                           f"0 {rust_display(L)}", f"0 {rust_display(L)}", f"0 {rust_display(L)}", "ITEM: ATOMS id type x y z"]
+        rows = np.array([[float(t) for t in ln.split()] for ln in blk[9:]])
+        assert np.array_equal(rows[:, 0], np.arange(1, n + 1)) and (rows[:, 1] == 1).all()
+        assert np.abs(rows[:, 2:] - snaps[s]).max() < 1e-9
+        if s == 0:  # frame 0 is the input, printed with Rust `{}` float formatting
+            assert blk[9 + 1] == "2 1 " + " ".join(rust_display(c) for c in atoms.positions[1])

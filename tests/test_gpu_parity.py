@@ -305,3 +305,52 @@ def test_guard_band_pairs_sit_on_the_cutoff():
     mgr.download(atoms)
     assert abs(pe - pe_ref) <= 1e-12 * max(abs(pe_ref), 1.0)
     assert np.abs(atoms.forces - f_ref).max() <= 1e-13 * max(np.abs(f_ref).max(), 1.0)
+
+
+def test_gpu_matches_committed_golden_vectors():
+    """tests/golden/oracle_small.json (made by tests/golden/make_golden.py) without running the oracle."""
+    import json
+    import os
+
+    with open(os.path.join(os.path.dirname(__file__), "golden", "oracle_small.json")) as f:
+        g = json.load(f)
+    box = SimulationBox.from_lammps_data(0, g["L"], 0, g["L"], 0, g["L"])
+    atoms = Atoms(g["types"], [g["mass"]], g["positions"], box, velocities=g["velocities"])
+    table = {(1, 1): LennardJones(g["eps"], g["sigma"], g["rc"], True)}
+    mgr = make_manager(skin=g["skin"], table=table)
+    mgr.attach(atoms)
+    rows = mgr.neighbours(atoms.n_atoms)
+    assert [r.tolist() for r in rows] == g["neighbours_skin"]
+    pe = mgr.compute()
+    mgr.download(atoms)
+    f_ref = np.array(g["forces"])
+    assert abs(pe - g["pe"]) <= 1e-12 * abs(g["pe"])
+    assert force_rel_err(atoms.forces, f_ref).max() <= FORCE_TOL
+    th = mgr.step_nve(g["dt"], g["steps"])
+    ref = np.array(g["thermo"])
+    assert np.max(np.abs(th["pe"] - ref[1:, 0]) / np.abs(ref[1:, 0])) <= ENERGY_TOL
+    assert np.max(np.abs(th["ke"] - ref[1:, 1]) / np.abs(ref[1:, 1])) <= ENERGY_TOL
+    mgr.download(atoms)
+    assert np.abs(atoms.positions - np.array(g["positions_end"])).max() < 1e-10
+
+
+def test_multi_gpu_equals_single_gpu():
+    """2-rank spatially decomposed run == 1-GPU run (neighbour sets exact per global id, forces 1e-10,
+    traces 1e-9).  Needs 2 visible GPUs; the torchrun launch mirrors the driver's."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    from pis_b200 import capi
+
+    if capi.load().pisb_device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29577", os.path.join(root, "tools", "multi_check.py"), "12", "40", "60"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert r.returncode == 0 and lines, r.stdout[-2000:] + r.stderr[-2000:]
+    out = json.loads(lines[-1])
+    assert out["ok"], out
