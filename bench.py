@@ -207,19 +207,22 @@ def run_single(args):
     bytes_per_launch = (48.0 + 4.0 * k_mean) * n
     achieved = bytes_per_launch / (f_ms * 1e-3) / 1e9
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    traffic = None
+    traffic, fp64_pct = None, None
     tp = os.path.join(ROOT, "profiles", "force_traffic.json")
     if os.path.exists(tp):
         try:
             with open(tp) as f:
-                traffic = json.load(f).get("dram_bytes_per_launch")
+                tj = json.load(f)
+            traffic, fp64_pct = tj.get("dram_bytes_per_launch"), tj.get("fp64_pipe_active_pct")
         except Exception:
             traffic = None
-    roofline = {"kernel": "k_force", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"kernel": "k_force_v3", "bound": "hbm", "algorithmic_bytes_per_launch": bytes_per_launch,
+                "fp64_pipe_active_pct_ncu": fp64_pct, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_kind,
                 "algorithmic_bytes_per_atom": 48.0 + 4.0 * k_mean, "mean_neighbours": k_mean,
                 "ms_per_launch": f_ms, "share_of_step": tim["force"]["ms"] / ms_total,
-                "note": "k_force is FP64-pipe bound, not HBM bound (see DESIGN.md); frac is HBM bytes/peak"}
+                "note": "the force kernel is bound by the FP64 pipe and L1TEX gather throughput, not by HBM (ncu: profiles/); "
+                        "frac is algorithmic HBM bytes / measured copy peak; traffic = ncu dram bytes per launch"}
     kernel_ms = {k: round(v["ms"] / args.steps, 5) for k, v in tim.items() if v["launches"]}
 
     # ---- end-to-end: the reference-facing trait call with HOST buffers, every step ----

@@ -25,7 +25,7 @@ from pis_b200.lattice import fcc_argon  # noqa: E402
 def main():
     atoms = fcc_argon(3, temperature=30.0, seed=21, jitter=0.12)
     L = float(atoms.sim_box.h[0, 0])
-    rc, skin, dt, steps = 7.0, 0.9, 0.25, 25   # L = 16.23 >= 2 * (rc + skin)
+    rc, skin, dt, steps = 4.6, 0.8, 0.25, 25   # L = 16.23 >= 3 * (rc + skin): 3 cells per edge (n < 3 double-counts in the reference)
     o = Oracle.cubic(L)
     o.insert(1, 1, 0.238, 3.405, rc)
     pe, f = o.compute_potential(atoms.positions, atoms.type_ids)
