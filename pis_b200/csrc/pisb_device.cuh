@@ -42,6 +42,14 @@ __device__ __forceinline__ double4 ldg_d4(const double4 *p) {
     return v;
 }
 
+// Streaming (read-once) loads of the neighbour-index tiles: keep them out of L1 so the gathered
+// position sectors stay resident.
+__device__ __forceinline__ int4 ldg_stream_i4(const int4 *p) {
+    int4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
 __device__ __forceinline__ int type_of(double w) { return (int)__double_as_longlong(w); }
 __device__ __forceinline__ double type_as_double(int t) { return __longlong_as_double((long long)t); }
 

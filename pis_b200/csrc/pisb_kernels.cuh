@@ -870,10 +870,10 @@ __device__ __forceinline__ void force3_body(const Force2Args &a, int i, double &
     const int ti = MULTI ? type_of(xi.w) : 1;
     const int nn = a.nnbr[i];
     const int4 *tiles = reinterpret_cast<const int4 *>(a.nbr) + i;
-    int4 cur = nn > 0 ? __ldg(tiles) : make_int4(i, i, i, i);
+    int4 cur = nn > 0 ? ldg_stream_i4(tiles) : make_int4(i, i, i, i);
     for (int k = 0; k < nn; k += 4) {
         int4 nxt = cur;
-        if (k + 4 < nn) nxt = __ldg(tiles + (size_t)((k >> 2) + 1) * a.npad);
+        if (k + 4 < nn) nxt = ldg_stream_i4(tiles + (size_t)((k >> 2) + 1) * a.npad);
         int j[4] = {cur.x, cur.y, cur.z, cur.w};
         bool in[4];
         double4 xj[4];
