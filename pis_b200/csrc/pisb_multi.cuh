@@ -203,10 +203,20 @@ __global__ void __launch_bounds__(TPB) k_halo_pack(int count, const int *__restr
     if (k < count) buf[k] = xt[send_idx[k]];
 }
 
+// flag_in[r] = skin-trigger flag received from rank r (exchanged in the same NCCL group as the ghosts):
+// the global decision max_r(flag) is formed here, so no separate all-reduce is needed (with P_d <= 2
+// every rank is a peer of every other).
 __global__ void __launch_bounds__(TPB) k_halo_unpack(int count, const int *__restrict__ ghost_slot,
                                                      const double4 *__restrict__ buf, double4 *__restrict__ xt,
-                                                     float4 *__restrict__ xf, BoxDev box) {
+                                                     float4 *__restrict__ xf, BoxDev box, const int *__restrict__ flag_in,
+                                                     int nranks, int me, int *__restrict__ flags) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k == 0 && flag_in) {
+        int f = flags[FLAG_REBUILD];
+        for (int r = 0; r < nranks; ++r)
+            if (r != me) f = max(f, flag_in[r]);
+        flags[FLAG_REBUILD] = f;
+    }
     if (k >= count) return;
     const int s = ghost_slot[k];
     double4 x = buf[k];

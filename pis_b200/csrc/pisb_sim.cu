@@ -108,7 +108,7 @@ struct pisb_handle {
     Decomp dc{};
     ncclComm_t comm = nullptr;
     int n_own = 0, n_ghost = 0, ncap_atoms = 0;
-    DevBuf<int> m_dest, m_pig, m_cnt, m_allcnt, m_off, send_idx, ghost_slot, newslot;
+    DevBuf<int> m_dest, m_pig, m_cnt, m_allcnt, m_off, send_idx, ghost_slot, newslot, flag_in;
     DevBuf<double> mig_send, mig_recv;
     DevBuf<double4> halo_send, halo_recv;
     std::vector<int> gs_cnt, gr_cnt, gs_off, gr_off;  // per-peer ghost send/recv counts and offsets
@@ -168,6 +168,14 @@ int dev_reserve(pisb_t *h, DevBuf<T> &b, size_t n) {
     b.cap = n;
     h->device_bytes += (int64_t)(n * sizeof(T));
     return PISB_OK;
+}
+
+// For buffers whose size follows a fluctuating count (migration / halo): grow with 50 % head-room so
+// that the cudaFree + cudaMalloc pair (a device-wide synchronisation) happens O(log) times, not per rebuild.
+template <typename T>
+int dev_reserve_grow(pisb_t *h, DevBuf<T> &b, size_t n, size_t min_elems = 4096) {
+    if (n <= b.cap) return PISB_OK;
+    return dev_reserve(h, b, std::max(min_elems, n + n / 2));
 }
 
 template <typename T>
@@ -893,8 +901,8 @@ int multi_rebuild(pisb_t *h) {
     const int n_own = h->n_own - stot + rtot;
     if (n_slots0 + rtot > h->ncap_atoms)
         return fail(h, PISB_ERR_CAPACITY, fmt("rank %d: %d slots + %d arrivals exceed the local capacity %d", me, n_slots0, rtot, h->ncap_atoms));
-    TRY(dev_reserve(h, h->mig_send, (size_t)std::max(stot, 1) * MIG_REC));
-    TRY(dev_reserve(h, h->mig_recv, (size_t)std::max(rtot, 1) * MIG_REC));
+    TRY(dev_reserve_grow(h, h->mig_send, (size_t)std::max(stot, 1) * MIG_REC));
+    TRY(dev_reserve_grow(h, h->mig_recv, (size_t)std::max(rtot, 1) * MIG_REC));
     CUDA_TRY(h, cudaMemcpyAsync(h->m_off.p, soff.data(), sizeof(int) * R, cudaMemcpyHostToDevice, st));
     {
         LaunchScope ls(h, PISB_K_HALO);
@@ -940,11 +948,11 @@ int multi_rebuild(pisb_t *h) {
     h->n_ghost = gr;
     if (n_slots1 + gr > h->ncap_atoms)
         return fail(h, PISB_ERR_CAPACITY, fmt("rank %d needs %d local slots (owned + ghost + stale), capacity %d", me, n_slots1 + gr, h->ncap_atoms));
-    TRY(dev_reserve(h, h->send_idx, (size_t)std::max(gs, 1)));
-    TRY(dev_reserve(h, h->halo_send, (size_t)std::max(gs, 1)));
-    TRY(dev_reserve(h, h->halo_recv, (size_t)std::max(gr, 1)));
-    TRY(dev_reserve(h, h->mig_send, (size_t)std::max(gs, 1) * GHOST_REC));
-    TRY(dev_reserve(h, h->mig_recv, (size_t)std::max(gr, 1) * GHOST_REC));
+    TRY(dev_reserve_grow(h, h->send_idx, (size_t)std::max(gs, 1)));
+    TRY(dev_reserve_grow(h, h->halo_send, (size_t)std::max(gs, 1)));
+    TRY(dev_reserve_grow(h, h->halo_recv, (size_t)std::max(gr, 1)));
+    TRY(dev_reserve_grow(h, h->mig_send, (size_t)std::max(gs, 1) * GHOST_REC));
+    TRY(dev_reserve_grow(h, h->mig_recv, (size_t)std::max(gr, 1) * GHOST_REC));
     CUDA_TRY(h, cudaMemcpyAsync(h->m_off.p, h->gs_off.data(), sizeof(int) * R, cudaMemcpyHostToDevice, st));
     {
         LaunchScope ls(h, PISB_K_HALO);
@@ -1006,19 +1014,40 @@ int multi_rebuild(pisb_t *h) {
     return fail(h, PISB_ERR_CAPACITY, "neighbour-list capacity did not converge");
 }
 
-// Per-step ghost position exchange (no rebuild).
-int halo_exchange(pisb_t *h) {
+// Per-step ghost position exchange (no rebuild).  with_flag: the skin-trigger flag of every rank travels in the
+// same NCCL group and k_halo_unpack forms the global max (replaces a separate all-reduce).
+int halo_exchange(pisb_t *h, bool with_flag) {
     cudaStream_t st = h->stream;
+    const int R = h->dc.nranks, me = h->dc.rank;
     if (h->send_total > 0) {
         LaunchScope ls(h, PISB_K_HALO);
         k_halo_pack<<<nblk(h->send_total, TPB), TPB, 0, st>>>(h->send_total, h->send_idx.p, h->xt.p, h->halo_send.p);
         TRY(check_launch(h, "k_halo_pack"));
     }
-    TRY(exchange(h, reinterpret_cast<const double *>(h->halo_send.p), h->gs_cnt, h->gs_off,
-                 reinterpret_cast<double *>(h->halo_recv.p), h->gr_cnt, h->gr_off, 4));
-    if (h->n_ghost > 0) {
+    if (with_flag) TRY(dev_reserve(h, h->flag_in, (size_t)R));
+    {
         LaunchScope ls(h, PISB_K_HALO);
-        k_halo_unpack<<<nblk(h->n_ghost, TPB), TPB, 0, st>>>(h->n_ghost, h->ghost_slot.p, h->halo_recv.p, h->xt.p, h->xf.p, h->box);
+        const double *sbuf = reinterpret_cast<const double *>(h->halo_send.p);
+        double *rbuf = reinterpret_cast<double *>(h->halo_recv.p);
+        NCCL_TRY(h, g_nccl.GroupStart());
+        for (int r = 0; r < R; ++r) {
+            if (r == me) continue;
+            if (h->gs_cnt[r] > 0)
+                NCCL_TRY(h, g_nccl.Send(sbuf + (size_t)h->gs_off[r] * 4, (size_t)h->gs_cnt[r] * 4, ncclDouble, r, h->comm, st));
+            if (h->gr_cnt[r] > 0)
+                NCCL_TRY(h, g_nccl.Recv(rbuf + (size_t)h->gr_off[r] * 4, (size_t)h->gr_cnt[r] * 4, ncclDouble, r, h->comm, st));
+            if (with_flag) {
+                NCCL_TRY(h, g_nccl.Send(h->flags + FLAG_REBUILD, 1, ncclInt, r, h->comm, st));
+                NCCL_TRY(h, g_nccl.Recv(h->flag_in.p + r, 1, ncclInt, r, h->comm, st));
+            }
+        }
+        NCCL_TRY(h, g_nccl.GroupEnd());
+    }
+    if (h->n_ghost > 0 || with_flag) {
+        LaunchScope ls(h, PISB_K_HALO);
+        k_halo_unpack<<<nblk(std::max(h->n_ghost, 1), TPB), TPB, 0, st>>>(h->n_ghost, h->ghost_slot.p, h->halo_recv.p, h->xt.p,
+                                                                         h->xf.p, h->box, with_flag ? h->flag_in.p : nullptr, R, me,
+                                                                         h->flags);
         TRY(check_launch(h, "k_halo_unpack"));
     }
     return PISB_OK;
@@ -1064,11 +1093,11 @@ int do_step_nve_multi(pisb_t *h, double dt, int64_t nsteps, pisb_thermo *out) {
             else TRY(launch_vv(h, true, true, dt, rec - 1));
             double t1 = wall_now();
             // every rank must take the same branch: max-reduce the skin trigger, then read it
-            NCCL_TRY(h, g_nccl.AllReduce(h->flags + FLAG_REBUILD, h->flags + FLAG_REBUILD, 1, ncclInt, ncclMax, h->comm, h->stream));
+            // every rank must take the same branch: the skin-trigger flags ride along with the ghost exchange and
+            // are max-reduced by k_halo_unpack; the host then reads the decision.  On a rebuild step the ghost
+            // exchange is merely redundant (the rebuild re-selects the ghosts).
+            TRY(halo_exchange(h, true));
             CUDA_TRY(h, cudaMemcpyAsync(h->h_flags, h->flags, sizeof(int) * FLAG_COUNT, cudaMemcpyDeviceToHost, h->stream));
-            // the ghost exchange is queued BEFORE the host reads the flag, so the read-back latency hides
-            // behind it; on a rebuild step it is merely redundant (the rebuild re-selects the ghosts)
-            TRY(halo_exchange(h));
             CUDA_TRY(h, cudaStreamSynchronize(h->stream));
             double t2 = wall_now();
             const bool reb = h->h_flags[FLAG_REBUILD] != 0;
@@ -1209,6 +1238,7 @@ int pisb_destroy(pisb_t *h) {
     dev_free(h, h->send_idx);
     dev_free(h, h->ghost_slot);
     dev_free(h, h->newslot);
+    dev_free(h, h->flag_in);
     dev_free(h, h->mig_send);
     dev_free(h, h->mig_recv);
     dev_free(h, h->halo_send);
