@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpisb200.so")
+LIB_PATH = os.environ.get("PISB_LIB") or os.path.join(_HERE, "libpisb200.so")  # PISB_LIB: A/B builds (tools/)
 
 PISB_OK, PISB_ERR_INVALID, PISB_ERR_CUDA, PISB_ERR_NO_DEVICE, PISB_ERR_CAPACITY, PISB_ERR_STATE, PISB_ERR_COMM = range(7)
 K_NAMES = ["integrate", "bin", "sort", "build", "force", "reduce", "halo", "copy"]

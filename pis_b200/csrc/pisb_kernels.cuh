@@ -802,7 +802,6 @@ __device__ __forceinline__ void force2_body(const Force2Args &a, int i, int (*q)
         while (k < nn && cnt <= QCAP - FU) {
             int j[FU];
             float4 xjf[FU];
-#pragma unroll
             {
                 const int4 t = __ldg(reinterpret_cast<const int4 *>(a.nbr) + ((size_t)(k >> 2) * a.npad + i));
                 j[0] = t.x;
