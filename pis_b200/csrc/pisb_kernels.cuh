@@ -907,8 +907,9 @@ __device__ __forceinline__ void force3_body(const Force2Args &a, int i, double &
     }
 }
 
+// 8 resident blocks/SM (64 registers, 32 warps): measured best, profiles/r01_force_launch_config.txt
 template <bool MULTI>
-__global__ void __launch_bounds__(TPB_FORCE) k_force_v3(Force2Args a) {
+__global__ void __launch_bounds__(TPB_FORCE, 8) k_force_v3(Force2Args a) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double red[2] = {0.0, 0.0};
     const bool active = i < a.n && !xf_is_ghost(a.xf[i]);
