@@ -354,3 +354,62 @@ def test_multi_gpu_equals_single_gpu():
     assert r.returncode == 0 and lines, r.stdout[-2000:] + r.stderr[-2000:]
     out = json.loads(lines[-1])
     assert out["ok"], out
+
+
+def test_config2_256k_atoms_parity():
+    """BASELINE configs[1]: FCC argon 256 000 atoms, rc = 2.5 sigma, skin = 0.3 sigma.  Forces / energy / neighbour
+    sets against the oracle at full size, then a 60-step NVE trace (the 1000-step trace is run at 4000 atoms in
+    test_nve_trace_parity_1000_steps: the CPU oracle needs ~0.2 s per 256k-atom step even with all cores)."""
+    atoms = fcc_argon(40, temperature=30.0, seed=12345, jitter=0.1)
+    table = {(1, 1): argon_pair()}
+    orc = make_oracle(atoms, table)
+    pe_ref, f_ref = orc.compute_potential(atoms.positions, atoms.type_ids, mode="omp")
+    start, nbr = orc.build_neighbour_list(atoms.positions, atoms.type_ids, extra=SKIN)
+    mgr = make_manager(skin=SKIN)
+    mgr.attach(atoms)
+    rows = mgr.neighbours(atoms.n_atoms)
+    assert sum(len(r) for r in rows) == len(nbr)
+    ref_rows = csr_rows_sorted(start, nbr)
+    bad = sum(0 if np.array_equal(a_, b_) else 1 for a_, b_ in zip(rows, ref_rows))
+    assert bad == 0
+    pe = mgr.compute()
+    mgr.download(atoms, positions=False, velocities=False)
+    assert abs(pe - pe_ref) <= ENERGY_TOL * abs(pe_ref)
+    assert force_rel_err(atoms.forces, f_ref).max() <= FORCE_TOL
+    steps = 60
+    x, v, f = atoms.positions.copy(), atoms.velocities.copy(), f_ref.copy()
+    pes, kes = [], []
+    for _ in range(steps):
+        pes.append(orc.verlet_step_nve(x, v, f, atoms.type_ids, 0.25, mode="omp"))
+        kes.append(orc.kinetic_energy(v, atoms.type_ids))
+    th = mgr.step_nve(0.25, steps)
+    assert np.max(np.abs(th["pe"] - np.array(pes)) / np.abs(pes)) <= ENERGY_TOL
+    assert np.max(np.abs(th["ke"] - np.array(kes)) / np.abs(kes)) <= ENERGY_TOL
+    mgr.download(atoms)
+    assert np.abs(atoms.positions - x).max() < 1e-9
+    assert force_rel_err(atoms.forces, f).max() <= FORCE_TOL
+
+
+def test_full_size_properties_4m_atoms():
+    """BASELINE configs[2] size (4M atoms), where the oracle is too slow: size-independent properties instead --
+    Newton's third law, list symmetry (j in list(i) <=> i in list(j)) via the degree sum and a sample, energy
+    conservation, and step-function invariance under a rigid translation by a lattice vector."""
+    atoms = fcc_argon(100, temperature=20.0, seed=5)
+    mgr = make_manager(skin=SKIN)
+    mgr.attach(atoms)
+    pe0 = mgr.compute()
+    mgr.download(atoms, positions=False, velocities=False)
+    assert np.abs(atoms.forces.sum(axis=0)).max() < 1e-7            # sum F = 0
+    assert abs(pe0 / atoms.n_atoms - (-1.7269)) < 0.02              # near the lattice energy per atom (rc = 2.5 sigma)
+    th = mgr.step_nve(0.25, 50)
+    h = th["pe"] + th["ke"]
+    assert np.abs(h - h[0]).max() <= 2e-4 * abs(h[0])
+    # translate every atom by one lattice constant (periodic box): identical physics, bitwise-equal wrapped lattice
+    a2 = fcc_argon(100, temperature=20.0, seed=5)
+    L = a2.sim_box.h[0, 0]
+    a2.positions[:, 0] += 5.41
+    a2.positions[:, 0] -= np.floor(a2.positions[:, 0] / L) * L
+    m2 = make_manager(skin=SKIN)
+    m2.attach(a2)
+    pe0b = m2.compute()
+    assert abs(pe0b - pe0) <= 1e-11 * abs(pe0)
