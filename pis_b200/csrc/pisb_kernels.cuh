@@ -969,6 +969,177 @@ __global__ void __launch_bounds__(TPB_FORCE) k_force_v2(Force2Args a) {
     });
 }
 
+// ------------------------------------------------------------------------------------------------
+// v4 (prototype): like v3, but each block first stages the positions of its whole cell tile -- the
+// 3 x 3 rows of x-contiguous cells around the block's own cells, nine contiguous slot ranges -- into
+// shared memory with TMA bulk copies (cp.async.bulk + mbarrier, SASS UBLKCP), and the neighbour
+// gathers then read shared memory instead of L1TEX/L2.  Blocks whose tile touches a periodic face,
+// spans two cell rows or exceeds the staging capacity run the v3 path.  Same results, bit for bit.
+// ------------------------------------------------------------------------------------------------
+constexpr int V4_CAP = 1728;  // atoms staged per block: 54 KB -> 4 blocks/SM
+
+struct V4Smem {
+    double4 tile[V4_CAP];
+    unsigned long long bar;
+    int gstart[9], gend[9], prefix[9];
+    int staged;
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ int cell_of_slot(const int *__restrict__ cell_start, int ncell, int slot) {
+    int lo = 0, hi = ncell;  // largest c with cell_start[c] <= slot
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(&cell_start[mid]) <= slot) lo = mid;
+        else hi = mid;
+    }
+    return lo;
+}
+
+template <bool MULTI, bool IMAGE>
+__device__ __forceinline__ void force4_body(const Force2Args &a, int i, const V4Smem &sm, double &fx, double &fy,
+                                            double &fz, double &pe, double &vir) {
+    const double4 xi = a.xt[i];
+    const int ti = MULTI ? type_of(xi.w) : 1;
+    const int nn = a.nnbr[i];
+    const int4 *tiles = reinterpret_cast<const int4 *>(a.nbr) + i;
+    int4 cur = nn > 0 ? __ldg(tiles) : make_int4(0, 0, 0, 0);
+    int r = 0, cur_end = sm.gend[0], cur_off = sm.prefix[0] - sm.gstart[0];
+    for (int k = 0; k < nn; k += 4) {
+        int4 nxt = cur;
+        if (k + 4 < nn) nxt = __ldg(tiles + (size_t)((k >> 2) + 1) * a.npad);
+        const int j[4] = {cur.x, cur.y, cur.z, cur.w};
+        bool in[4];
+        double4 xj[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            in[u] = k + u < nn;
+            int loc = 0;
+            if (in[u]) {
+                while (j[u] >= cur_end) {  // lists are in ascending slot order: the row pointer only advances
+                    ++r;
+                    cur_end = sm.gend[r];
+                    cur_off = sm.prefix[r] - sm.gstart[r];
+                }
+                loc = j[u] + cur_off;
+            }
+            xj[u] = sm.tile[loc];
+        }
+        double dx[4], dy[4], dz[4], r2[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            disp_inrange_ortho<IMAGE>(a.box, xi, xj[u], dx[u], dy[u], dz[u]);
+            r2[u] = norm2(dx[u], dy[u], dz[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            PairDev p = a.pair0;
+            if (MULTI) {
+                const int tj = type_of(xj[u].w);
+                p = a.table[(min(ti, tj) - 1) * a.n_types + (max(ti, tj) - 1)];
+                in[u] = in[u] && p.present;
+            }
+            if (in[u] && !(r2[u] > p.t_rc)) {
+                double uu, fs;
+                lj_pair(p, r2[u], uu, fs);
+                PISB_ACCUM(dx[u], dy[u], dz[u], r2[u], uu, fs);
+            }
+        }
+        cur = nxt;
+    }
+}
+
+template <bool MULTI>
+__global__ void __launch_bounds__(TPB_FORCE, 4) k_force_v4(Force2Args a, const int *__restrict__ cell_start, Grid g) {
+    extern __shared__ __align__(128) unsigned char v4_raw[];
+    V4Smem &sm = *reinterpret_cast<V4Smem *>(v4_raw);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (threadIdx.x == 0) {
+        const int i0 = blockIdx.x * blockDim.x;
+        const int i1 = min(i0 + (int)blockDim.x, a.n) - 1;
+        const int nx = g.n[0], ny = g.n[1], nz = g.n[2];
+        const int c0 = cell_of_slot(cell_start, g.ncell, i0), c1 = cell_of_slot(cell_start, g.ncell, i1);
+        const int cx0 = c0 % nx, cy0 = (c0 / nx) % ny, cz0 = c0 / (nx * ny);
+        const int cx1 = c1 % nx, cy1 = (c1 / nx) % ny, cz1 = c1 / (nx * ny);
+        int staged = (cy0 == cy1 && cz0 == cz1 && cx0 >= 1 && cx1 <= nx - 2 && cy0 >= 1 && cy0 <= ny - 2 && cz0 >= 1 &&
+                      cz0 <= nz - 2 && !g.local[0] && !g.local[1] && !g.local[2] && g.lo[0] == -1 && g.hi[0] == 1 && g.lo[1] == -1 &&
+                      g.hi[1] == 1 && g.lo[2] == -1 && g.hi[2] == 1)
+                         ? 1 : 0;
+        int total = 0;
+        if (staged) {
+            int rr = 0;
+            for (int dz = -1; dz <= 1; ++dz)
+                for (int dy = -1; dy <= 1; ++dy, ++rr) {
+                    const int rb = ((cz0 + dz) * ny + (cy0 + dy)) * nx;
+                    sm.gstart[rr] = __ldg(&cell_start[rb + cx0 - 1]);
+                    sm.gend[rr] = __ldg(&cell_start[rb + cx1 + 2]);
+                    sm.prefix[rr] = total;
+                    total += sm.gend[rr] - sm.gstart[rr];
+                }
+            if (total > V4_CAP) staged = 0;
+        }
+        sm.staged = staged;
+        if (staged) {
+            const unsigned bar = smem_u32(&sm.bar);
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(total * 32) : "memory");
+            for (int rr = 0; rr < 9; ++rr) {
+                const int len = sm.gend[rr] - sm.gstart[rr];
+                if (len > 0)
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                     smem_u32(&sm.tile[sm.prefix[rr]])),
+                                 "l"(a.xt + sm.gstart[rr]), "r"(len * 32), "r"(bar)
+                                 : "memory");
+            }
+        }
+    }
+    __syncthreads();
+    const bool staged = sm.staged != 0;
+    double red[2] = {0.0, 0.0};
+    const bool active = i < a.n && !xf_is_ghost(a.xf[i]);
+    bool interior = true;
+    if (active) interior = is_interior(a.boxf, a.xf[i]);
+    const bool warp_interior = __all_sync(0xffffffffu, interior);
+    if (staged) {
+        const unsigned bar = smem_u32(&sm.bar);
+        unsigned done = 0;
+        while (!done) {
+            asm volatile(
+                "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}\n"
+                : "=r"(done)
+                : "r"(bar)
+                : "memory");
+        }
+    }
+    if (active) {
+        double fx = 0.0, fy = 0.0, fz = 0.0, pe = 0.0, vir = 0.0;
+        if (staged) {
+            if (warp_interior) force4_body<MULTI, false>(a, i, sm, fx, fy, fz, pe, vir);
+            else force4_body<MULTI, true>(a, i, sm, fx, fy, fz, pe, vir);
+        } else {
+            if (warp_interior) force3_body<MULTI, false>(a, i, fx, fy, fz, pe, vir);
+            else force3_body<MULTI, true>(a, i, fx, fy, fz, pe, vir);
+        }
+        if (a.ax) {
+            fx += a.ax[i];
+            fy += a.ay[i];
+            fz += a.az[i];
+        }
+        a.fx[i] = fx;
+        a.fy[i] = fy;
+        a.fz[i] = fz;
+        red[0] = pe;
+        red[1] = vir;
+    }
+    pisb_thermo *th = a.thermo;
+    block_reduce_finalize<2, TPB_FORCE>(red, a.partials, a.ticket, [&](int qq, double s) {
+        if (qq == 0) th->pe = s / 2.0;
+        else th->virial_pair = s / 2.0;
+    });
+}
+
 struct Build2Args {
     int n, npad, kcap;
     const double4 *xt;

@@ -54,6 +54,8 @@ struct DevBuf {
 struct pisb_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // overlaps the position read-back of the host-buffer step with the force kernel
+    cudaEvent_t ev_pos = nullptr;
     std::string err;
 
     // potential
@@ -540,7 +542,16 @@ int launch_force(pisb_t *h, double *const out[3], const double *const acc[3], pi
         Force2Args f2{h->n, h->npad, h->xt.p, h->xf.p, h->nbr.p, h->nnbr.p, h->box, h->boxf, h->pairs[0], h->pairsf[0],
                       h->table_d.p, h->tablef_d.p, h->n_types, fa.ax, fa.ay, fa.az, out[0], out[1], out[2],
                       h->partials.p, h->ticket, rec};
-        if (h->force_variant != 2) {  // auto = v3 (measured fastest: profiles/)
+        if (h->force_variant == 4) {
+            static bool attr_set = false;
+            if (!attr_set) {
+                cudaFuncSetAttribute(k_force_v4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(V4Smem));
+                cudaFuncSetAttribute(k_force_v4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(V4Smem));
+                attr_set = true;
+            }
+            if (multi) k_force_v4<true><<<nb, TPB_FORCE, sizeof(V4Smem), st>>>(f2, h->cell_start.p, h->grid);
+            else k_force_v4<false><<<nb, TPB_FORCE, sizeof(V4Smem), st>>>(f2, h->cell_start.p, h->grid);
+        } else if (h->force_variant != 2) {  // auto = v3 (measured fastest: profiles/)
             if (multi) k_force_v3<true><<<nb, TPB_FORCE, 0, st>>>(f2);
             else k_force_v3<false><<<nb, TPB_FORCE, 0, st>>>(f2);
         } else {
@@ -1182,7 +1193,9 @@ int pisb_create(int device, int n_types, const double *mass, const double *eps, 
         return rc;
     };
     if (cudaSetDevice(device) != cudaSuccess) return bail(fail(h, PISB_ERR_CUDA, "cudaSetDevice failed"));
-    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess)
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_pos, cudaEventDisableTiming) != cudaSuccess)
         return bail(fail(h, PISB_ERR_CUDA, "cudaStreamCreate failed"));
     if (cudaMalloc((void **)&h->flags, sizeof(int) * FLAG_COUNT) != cudaSuccess ||
         cudaMalloc((void **)&h->ticket, sizeof(unsigned int)) != cudaSuccess ||
@@ -1254,6 +1267,8 @@ int pisb_destroy(pisb_t *h) {
         cudaEventDestroy(e.a);
         cudaEventDestroy(e.b);
     }
+    if (h->ev_pos) cudaEventDestroy(h->ev_pos);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return PISB_OK;
@@ -1339,10 +1354,51 @@ int pisb_verlet_step_nve_host(pisb_t *h, int64_t n, double *pos, double *vel, do
     const bool fresh = !h->have_atoms || h->n != (int)n;
     if (fresh && !types) return fail(h, PISB_ERR_INVALID, "types is NULL on first call");
     TRY(do_upload(h, n, pos, vel, force, fresh ? types : nullptr));
-    pisb_thermo th;
-    TRY(do_step_nve(h, dt, 1, &th));
-    TRY(do_download(h, pos, vel, force));
-    if (pe) *pe = th.pe;
+    if (h->multi) return fail(h, PISB_ERR_STATE, "the host-buffer step is a single-GPU entry point");
+    // One verlet_step_nve, written out so that x(t+dt) -- final right after the drift -- travels back over PCIe on a
+    // second stream while the list check / rebuild, the force kernel and the kick still run.
+    TRY(ensure_list(h));
+    TRY(check_bad_type(h));
+    TRY(reserve_thermo(h, 2));
+    const int na = h->n;
+    const size_t n3 = (size_t)3 * na;
+    TRY(launch_vv(h, false, true, dt, nullptr));
+    {
+        LaunchScope ls(h, PISB_K_COPY);
+        StoreArgs sa{na, h->xt.p, h->v[0].p, h->v[1].p, h->v[2].p, h->f[0].p, h->f[1].p, h->f[2].p, h->id.p, h->st_pos.p, nullptr, nullptr};
+        k_store_aos<<<nblk(na, TPB), TPB, 0, h->stream>>>(sa);  // on the main stream: ordered before any re-sort
+        TRY(check_launch(h, "k_store_aos(pos)"));
+    }
+    CUDA_TRY(h, cudaEventRecord(h->ev_pos, h->stream));
+    CUDA_TRY(h, cudaStreamWaitEvent(h->copy_stream, h->ev_pos, 0));
+    CUDA_TRY(h, cudaMemcpyAsync(pos, h->st_pos.p, sizeof(double) * n3, cudaMemcpyDeviceToHost, h->copy_stream));
+    TRY(launch_rebuild_chain(h));
+    double *outp[3] = {h->g[0].p, h->g[1].p, h->g[2].p};
+    TRY(launch_force(h, outp, nullptr, h->thermo_d.p));
+    for (int d = 0; d < 3; ++d) std::swap(h->f[d], h->g[d]);
+    TRY(launch_vv(h, true, false, dt, h->thermo_d.p));
+    {
+        LaunchScope ls(h, PISB_K_COPY);
+        StoreArgs sa{na, h->xt.p, h->v[0].p, h->v[1].p, h->v[2].p, h->f[0].p, h->f[1].p, h->f[2].p, h->id.p, nullptr, h->st_vel.p, h->st_frc.p};
+        k_store_aos<<<nblk(na, TPB), TPB, 0, h->stream>>>(sa);
+        TRY(check_launch(h, "k_store_aos(vel,frc)"));
+    }
+    CUDA_TRY(h, cudaMemcpyAsync(vel, h->st_vel.p, sizeof(double) * n3, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(force, h->st_frc.p, sizeof(double) * n3, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_thermo, h->thermo_d.p, sizeof(pisb_thermo), cudaMemcpyDeviceToHost, h->stream));
+    TRY(read_flags(h));
+    CUDA_TRY(h, cudaStreamSynchronize(h->copy_stream));
+    if (h->h_flags[FLAG_NBUILDS] != h->n_builds_host) {
+        h->n_builds_host = h->h_flags[FLAG_NBUILDS];
+        h->max_nbr = h->h_flags[FLAG_MAXNBR];
+    }
+    if (h->h_flags[FLAG_MAXNBR] > h->kcap) {
+        h->list_valid = false;
+        return fail(h, PISB_ERR_CAPACITY, "a neighbour list overflowed during the step; repeat the call (capacity grows on the next build)");
+    }
+    h->n_steps += 1;
+    h->forces_current = true;
+    if (pe) *pe = h->h_thermo[0].pe;
     return PISB_OK;
 }
 

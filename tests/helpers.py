@@ -23,6 +23,7 @@ VARIANTS = {
     2: (2, 2, 1),         # v2: FP32 pre-filter + queue force kernel, pre-filter build
     3: (3, 2, 1),         # v3: 4-wide prefetching all-FP64 force kernel, pre-filter build
     4: (3, 2, 2),         # v3 + half-size cells (5^3 stencil)
+    5: (4, 2, 1),         # v4: TMA-staged shared-memory cell tile (prototype)
 }
 
 
