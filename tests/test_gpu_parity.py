@@ -413,3 +413,65 @@ def test_full_size_properties_4m_atoms():
     m2.attach(a2)
     pe0b = m2.compute()
     assert abs(pe0b - pe0) <= 1e-11 * abs(pe0)
+
+
+def test_non_cubic_box_and_vacuum_slab():
+    """Orthorhombic box with three different edges, half of it empty (a slab: empty cells, uneven density)."""
+    base = fcc_argon(8, temperature=25.0, seed=8, jitter=0.1)
+    a = 5.41
+    keep = base.positions[:, 2] < 4 * a                      # keep the lower half in z -> vacuum above
+    pos = base.positions[keep] * np.array([1.0, 1.0, 1.0])
+    box = SimulationBox.from_lammps_data(0, 8 * a, 0, 8 * a + 3.7, 0, 8 * a + 9.1)
+    atoms = Atoms(np.ones(keep.sum(), dtype=np.int32), [39.948], pos, box, velocities=base.velocities[keep])
+    table = {(1, 1): argon_pair()}
+    orc = make_oracle(atoms, table)
+    pe_ref, f_ref = orc.compute_potential(atoms.positions, atoms.type_ids)
+    start, nbr = orc.build_neighbour_list(atoms.positions, atoms.type_ids, extra=SKIN)
+    mgr = make_manager(skin=SKIN)
+    mgr.attach(atoms)
+    for a_, b_ in zip(mgr.neighbours(atoms.n_atoms), csr_rows_sorted(start, nbr)):
+        assert np.array_equal(a_, b_)
+    pe = mgr.compute()
+    mgr.download(atoms, positions=False, velocities=False)
+    assert abs(pe - pe_ref) <= ENERGY_TOL * abs(pe_ref)
+    assert force_rel_err(atoms.forces, f_ref).max() <= FORCE_TOL
+    x, v, f = atoms.positions.copy(), atoms.velocities.copy(), f_ref.copy()
+    pes = [orc.verlet_step_nve(x, v, f, atoms.type_ids, 0.25) for _ in range(40)]
+    th = mgr.step_nve(0.25, 40)
+    assert np.max(np.abs(th["pe"] - np.array(pes)) / np.abs(pes)) <= ENERGY_TOL
+
+
+def test_list_capacity_grows_and_user_cap_is_enforced():
+    """A dense cluster exceeds the density-based capacity estimate: the list is regrown transparently;
+    an explicit list_capacity that is too small is reported as PISB_ERR_CAPACITY."""
+    from pis_b200.capi import PISB_ERR_CAPACITY, PisbError
+
+    rng = np.random.default_rng(11)
+    L = 60.0
+    n = 400
+    # all atoms inside a 14 A ball in a large box: mean density is tiny, local density is high
+    pts = rng.standard_normal((4000, 3))
+    pts = pts[np.linalg.norm(pts, axis=1) < 2.0][:n] * 3.5 + L / 2
+    # thin out pairs closer than 2.9 A so the energy stays finite
+    keep = []
+    for p in pts:
+        if all(np.linalg.norm(p - q) > 2.9 for q in keep):
+            keep.append(p)
+    pos = np.array(keep)
+    box = SimulationBox.from_lammps_data(0, L, 0, L, 0, L)
+    atoms = Atoms(np.ones(len(pos), dtype=np.int32), [39.948], pos, box)
+    table = {(1, 1): argon_pair()}
+    orc = make_oracle(atoms, table)
+    pe_ref, f_ref = orc.compute_potential(atoms.positions, atoms.type_ids)
+    mgr = make_manager(skin=SKIN)
+    pe = mgr.compute_potential(atoms)
+    st = mgr.stats()
+    assert st["max_neighbours"] > 30 and st["list_capacity"] >= st["max_neighbours"]
+    assert abs(pe - pe_ref) <= ENERGY_TOL * abs(pe_ref)
+    assert force_rel_err(atoms.forces, f_ref).max() <= FORCE_TOL
+    small = make_manager(skin=SKIN)
+    small.set_option("list_capacity", 8)
+    atoms.forces[...] = 0.0
+    with pytest.raises(PisbError) as e:
+        small.compute_potential(atoms)
+    assert e.value.code == PISB_ERR_CAPACITY
