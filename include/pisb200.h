@@ -124,6 +124,27 @@ PISB_API int pisb_compute(pisb_t *h, int accumulate, double *pe);
  *   receives nsteps records; out[s].pe is the value verlet_step_nve returns at step s. */
 PISB_API int pisb_step_nve(pisb_t *h, double dt, int64_t nsteps, pisb_thermo *out);
 
+/* Nose-Hoover chain state == NHThermostatChain (src/ensemble/nvt.rs:4-17; chain_size is 3, nvt.rs:108). */
+typedef struct {
+    int32_t chain_size;
+    int32_t pad;
+    double start_temperature, end_temperature, target_temperature;
+    double xi[3], eta[3], g[3], q[3];
+} pisb_nhc;
+
+/* Replaces: NHThermostatChain::new_from_args (nvt.rs:21-56,99-112): target = start, q_i = kB T tau^2 / 10^i. */
+PISB_API int pisb_nhc_init(pisb_nhc *out, double start_temperature, double end_temperature, double tau);
+
+/* Replaces: PotentialManager::verlet_step_nvt_nhc (src/potentials/potential.rs:35-58) followed by
+ *   NHThermostatChain::calculate_target_temperature(i, total_steps) (src/simulation.rs:53-57), nsteps times,
+ *   device-resident (the chain lives on the GPU during the batch).  first_step: index i of the first step
+ *   of this batch in the run; total_steps: the run length the temperature ramp refers to.
+ *   out[s] as in pisb_step_nve (ke is the kinetic energy after the second thermostat scaling);
+ *   nhc_energy[s] (may be NULL) = nhc.kinetic_energy() + nhc.potential_energy(n), the thermostat's share of the
+ *   Hamiltonian (simulation.rs:101-104).  Single-GPU only. */
+PISB_API int pisb_step_nvt_nhc(pisb_t *h, double dt, int64_t nsteps, pisb_nhc *chain, int64_t first_step,
+                               int64_t total_steps, pisb_thermo *out, double *nhc_energy);
+
 /* Copy state back in ORIGINAL atom order (any pointer may be NULL).  Replaces reading
  * atoms.positions / velocities / forces on the host (e.g. DumpTraj::write_atoms_info,
  * src/writers/dump_traj.rs:52-66). */

@@ -609,6 +609,102 @@ ORC_API void orc_run_nve(const orc_box *b, const orc_table *t, int64_t n, double
     }
 }
 
+/* ---- NVT: Nose-Hoover chain (src/ensemble/nvt.rs) and verlet_step_nvt_nhc (src/potentials/potential.rs:35-58) ---- */
+typedef struct {
+    int32_t chain_size; /* always 3: nvt.rs:108 */
+    int32_t pad;
+    double start_temperature, end_temperature, target_temperature;
+    double xi[3], eta[3], g[3], q[3];
+} orc_nhc;
+
+static const double ORC_KB = 0.0083144621;
+
+/* NHThermostatChain::new via new_from_args: target = start, chain_size = 3.  ref: nvt.rs:21-56,99-112 */
+ORC_API void orc_nhc_new(orc_nhc *c, double start_temperature, double end_temperature, double tau) {
+    memset(c, 0, sizeof *c);
+    c->chain_size = 3;
+    c->start_temperature = start_temperature;
+    c->end_temperature = end_temperature;
+    c->target_temperature = start_temperature;
+    double q_value = ORC_KB * c->target_temperature * (tau * tau);
+    double p10 = 1.0;
+    for (int i = 0; i < 3; ++i) {
+        c->q[i] = q_value / p10; /* (10.0).powi(i): 1, 10, 100 exactly */
+        p10 *= 10.0;
+    }
+}
+
+/* ref: nvt.rs:59-69 */
+ORC_API void orc_nhc_compute_forces(orc_nhc *c, double kinetic_energy, int64_t n_atoms) {
+    c->g[0] = 2.0 * kinetic_energy - ((double)(n_atoms * 3)) * ORC_KB * c->target_temperature;
+    for (int j = 1; j < c->chain_size; ++j)
+        c->g[j] = c->q[j - 1] * (c->xi[j - 1] * c->xi[j - 1]) - ORC_KB * c->target_temperature;
+}
+
+/* ref: nvt.rs:72-80 -- xi is ASSIGNED (not incremented) and eta never advances: reproduced as written */
+ORC_API void orc_nhc_propagate_half_step(orc_nhc *c, double timestep) {
+    int j = c->chain_size - 1;
+    c->xi[j] = 0.5 * timestep * c->g[j] / c->q[j];
+    for (int l = j - 1; l >= 0; --l)
+        c->xi[l] = (0.5 * timestep * c->g[l] / c->q[l]) * exp(-0.25 * timestep * c->xi[l + 1]);
+}
+
+/* ref: nvt.rs:82-97 */
+ORC_API double orc_nhc_kinetic_energy(const orc_nhc *c) {
+    double ke = 0.0;
+    for (int i = 0; i < c->chain_size; ++i) ke += 0.5 * c->q[i] * (c->xi[i] * c->xi[i]);
+    return ke;
+}
+ORC_API double orc_nhc_potential_energy(const orc_nhc *c, int64_t n_atoms) {
+    double pe = (double)(n_atoms * 3) * ORC_KB * c->target_temperature * c->eta[0];
+    for (int i = 1; i < c->chain_size; ++i) pe += ORC_KB * c->target_temperature * c->eta[i];
+    return pe;
+}
+
+/* ref: nvt.rs:114-123 */
+ORC_API void orc_nhc_calculate_target_temperature(orc_nhc *c, int64_t current_timestep, int64_t total_timesteps) {
+    c->target_temperature = c->start_temperature +
+                            ((c->end_temperature - c->start_temperature) / (double)total_timesteps) * (double)current_timestep;
+}
+
+/* PotentialManager::verlet_step_nvt_nhc.  ref: src/potentials/potential.rs:35-58 */
+ORC_API double orc_verlet_step_nvt_nhc(const orc_box *b, const orc_table *t, int64_t n, double *pos, double *vel,
+                                       double *forces, const int32_t *types, const double *masses, double dt,
+                                       orc_nhc *nhc, int mode, int n_threads) {
+    double kinetic_energy = orc_kinetic_energy(n, vel, types, masses);
+    orc_nhc_compute_forces(nhc, kinetic_energy, n);
+    orc_nhc_propagate_half_step(nhc, dt);
+    double scale = exp(-0.5 * dt * nhc->xi[0]);
+    for (int64_t k = 0; k < 3 * n; ++k) vel[k] = vel[k] * scale;
+    double potential_energy = orc_verlet_step_nve(b, t, n, pos, vel, forces, types, masses, dt, mode, n_threads);
+    for (int64_t k = 0; k < 3 * n; ++k) vel[k] = vel[k] * scale;
+    kinetic_energy = orc_kinetic_energy(n, vel, types, masses);
+    orc_nhc_compute_forces(nhc, kinetic_energy, n);
+    orc_nhc_propagate_half_step(nhc, dt);
+    return potential_energy;
+}
+
+/* Simulation::run, NVT arm (src/simulation.rs:8-115): rows as orc_run_nve with H = PE + KE + nhc KE + nhc PE. */
+ORC_API void orc_run_nvt(const orc_box *b, const orc_table *t, int64_t n, double *pos, double *vel, double *forces,
+                         const int32_t *types, const double *masses, double dt, int64_t steps, orc_nhc *nhc, int mode,
+                         int n_threads, double *thermo) {
+    double pe0 = mode == 0 ? orc_compute_potential(b, t, n, pos, types, forces)
+                           : orc_compute_potential_omp(b, t, n, pos, types, forces, n_threads);
+    thermo[0] = pe0;
+    thermo[1] = thermo[2] = thermo[3] = thermo[4] = 0.0;
+    for (int64_t s = 0; s < steps; ++s) {
+        double pe = orc_verlet_step_nvt_nhc(b, t, n, pos, vel, forces, types, masses, dt, nhc, mode, n_threads);
+        orc_nhc_calculate_target_temperature(nhc, s, steps); /* simulation.rs:55 */
+        double ke = orc_kinetic_energy(n, vel, types, masses);
+        double *row = &thermo[(s + 1) * 5];
+        row[0] = pe;
+        row[1] = ke;
+        row[2] = pe + ke + orc_nhc_kinetic_energy(nhc) + orc_nhc_potential_energy(nhc, n);
+        row[3] = orc_temperature(n, ke);
+        row[4] = orc_pressure(b, n, pos, forces, ke);
+    }
+}
+
 /* Largest double T with sqrt(T) <= rc (correctly-rounded sqrt is monotone), so that
  * `sqrt(r2) > rc`  <=>  `r2 > T` exactly.  Test helper for the sqrt-free device predicate. */
 ORC_API double orc_rcut_threshold(double rc) {

@@ -21,6 +21,12 @@ class Box(C.Structure):
     _fields_ = [("h", C.c_double * 9), ("hinv", C.c_double * 9), ("pbc", C.c_int * 3)]
 
 
+class Nhc(C.Structure):
+    _fields_ = [("chain_size", C.c_int32), ("pad", C.c_int32), ("start_temperature", C.c_double),
+                ("end_temperature", C.c_double), ("target_temperature", C.c_double), ("xi", C.c_double * 3),
+                ("eta", C.c_double * 3), ("g", C.c_double * 3), ("q", C.c_double * 3)]
+
+
 class Table(C.Structure):
     _fields_ = [("n_types", C.c_int), ("eps", C.c_void_p), ("sigma", C.c_void_p), ("rcut", C.c_void_p),
                 ("present", C.c_void_p), ("shift", C.c_int)]
@@ -66,6 +72,10 @@ def load():
             "orc_pressure": (d, [bp, i64, vp, vp, d]),
             "orc_verlet_step_nve": (d, [bp, tp, i64, vp, vp, vp, vp, vp, d, C.c_int, C.c_int]),
             "orc_run_nve": (None, [bp, tp, i64, vp, vp, vp, vp, vp, d, i64, C.c_int, C.c_int, vp]),
+            "orc_nhc_new": (None, [C.POINTER(Nhc), d, d, d]),
+            "orc_nhc_kinetic_energy": (d, [C.POINTER(Nhc)]),
+            "orc_verlet_step_nvt_nhc": (d, [bp, tp, i64, vp, vp, vp, vp, vp, d, C.POINTER(Nhc), C.c_int, C.c_int]),
+            "orc_run_nvt": (None, [bp, tp, i64, vp, vp, vp, vp, vp, d, i64, C.POINTER(Nhc), C.c_int, C.c_int, vp]),
             "orc_rcut_threshold": (d, [d]),
             "orc_max_threads": (C.c_int, []),
         }
@@ -220,6 +230,20 @@ class Oracle:
         self.lib.orc_run_nve(C.byref(self.box), C.byref(self.table), pos.shape[0], _p(pos), _p(vel), _p(forces),
                              _p(types), _p(self.masses), float(dt), steps, 0 if mode == "serial" else 1, threads,
                              _p(thermo))
+        return thermo
+
+    def nhc_new(self, start_temperature, end_temperature, tau):
+        c = Nhc()
+        self.lib.orc_nhc_new(C.byref(c), float(start_temperature), float(end_temperature), float(tau))
+        return c
+
+    def run_nvt(self, pos, vel, forces, types, dt, steps, nhc, mode="serial", threads=0):
+        """Simulation::run NVT arm. thermo[(steps+1), 5] = PE, KE, H (incl. thermostat energy), T, P."""
+        types = np.ascontiguousarray(types, dtype=np.int32)
+        thermo = np.zeros((steps + 1, 5))
+        self.lib.orc_run_nvt(C.byref(self.box), C.byref(self.table), pos.shape[0], _p(pos), _p(vel), _p(forces),
+                             _p(types), _p(self.masses), float(dt), steps, C.byref(nhc), 0 if mode == "serial" else 1,
+                             threads, _p(thermo))
         return thermo
 
     def rcut_threshold(self, rc):

@@ -35,6 +35,13 @@ class Stats(C.Structure):
         return d
 
 
+class Nhc(C.Structure):
+    """pisb_nhc == NHThermostatChain (src/ensemble/nvt.rs:4-17), 3 links."""
+    _fields_ = [("chain_size", C.c_int32), ("pad", C.c_int32), ("start_temperature", C.c_double),
+                ("end_temperature", C.c_double), ("target_temperature", C.c_double), ("xi", C.c_double * 3),
+                ("eta", C.c_double * 3), ("g", C.c_double * 3), ("q", C.c_double * 3)]
+
+
 class PisbError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"pisb error {code}: {msg}")
@@ -68,6 +75,8 @@ SIGNATURES = {
     "pisb_stream": (_vp, [_vp]),
     "pisb_synchronize": (C.c_int, [_vp]),
     "pisb_set_option": (C.c_int, [_vp, C.c_char_p, C.c_double]),
+    "pisb_nhc_init": (C.c_int, [C.POINTER(Nhc), C.c_double, C.c_double, C.c_double]),
+    "pisb_step_nvt_nhc": (C.c_int, [_vp, C.c_double, C.c_int64, C.POINTER(Nhc), C.c_int64, C.c_int64, _vp, _vp]),
     "pisb_comm_unique_id": (C.c_int, [_vp, C.c_int]),
     "pisb_comm_init": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp]),
     "pisb_upload_owned": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp, _vp]),

@@ -253,6 +253,11 @@ double LJCudaManager::compute(bool accumulate) {
 
 void LJCudaManager::step_nve(double dt, int64_t nsteps, pisb_thermo *out) { check(pisb_step_nve(h_, dt, nsteps, out)); }
 
+void LJCudaManager::step_nvt_nhc(double dt, int64_t nsteps, pisb_nhc &chain, int64_t first_step, int64_t total_steps,
+                                 pisb_thermo *out, double *nhc_energy) {
+    check(pisb_step_nvt_nhc(h_, dt, nsteps, &chain, first_step, total_steps, out, nhc_energy));
+}
+
 void LJCudaManager::download(Atoms &atoms, bool pos, bool vel, bool frc) {
     check(pisb_download(h_, pos ? atoms.positions.data() : nullptr, vel ? atoms.velocities.data() : nullptr,
                         frc ? atoms.forces.data() : nullptr));
@@ -538,10 +543,13 @@ void DumpTraj::write_step(const Atoms &atoms, size_t step) {
 
 // ---- Simulation::run, NVE arm (src/simulation.rs:8-88) ---------------------------------------------------
 void Simulation::run(LJCudaManager &mgr, SimulationContext &ctx, FILE *out) {
-    if (ctx.nh_chain_args || ctx.mtk_barostat_args)
+    if (ctx.mtk_barostat_args)
         throw PisError("UnsupportedEnsemble",
-                       "fix nvt / npt selects the NVT / NPT ensemble (simulation.rs:125-132); the B200 path implements the NVE "
-                       "hot path only -- remove the fix line");
+                       "fix npt selects the NPT ensemble (simulation.rs:125-132); the B200 path implements the NVE hot path and the "
+                       "NVT Nose-Hoover wrapper only -- remove the `iso` keyword or the fix line");
+    const bool nvt = ctx.nh_chain_args.has_value();  // Ensemble::from_ctx (simulation.rs:125-132)
+    pisb_nhc chain{};
+    if (nvt) pisb_nhc_init(&chain, ctx.nh_chain_args->start_temperature, ctx.nh_chain_args->end_temperature, ctx.nh_chain_args->tau);
     if (!ctx.atoms) throw PisError("NoAtomsDefined", "No atoms defined in input file");
     Atoms &atoms = *ctx.atoms;
     const double dt = ctx.timestep;
@@ -551,6 +559,7 @@ void Simulation::run(LJCudaManager &mgr, SimulationContext &ctx, FILE *out) {
     const double first_potential = mgr.compute_potential(atoms);  // uploads; forces stay resident too
     std::fprintf(out, "0 %s\n", rust_display_f64(first_potential).c_str());
     std::vector<pisb_thermo> th;
+    std::vector<double> nhc_e;
     size_t i = 0;
     while (i < steps) {
         // run up to the next dump step on the device; only thermo scalars come back per step
@@ -558,7 +567,9 @@ void Simulation::run(LJCudaManager &mgr, SimulationContext &ctx, FILE *out) {
         if (dump_step > 0) chunk = std::min(chunk, dump_step - (i % dump_step));
         chunk = std::min<size_t>(chunk, 1000);
         th.resize(chunk);
-        mgr.step_nve(dt, (int64_t)chunk, th.data());
+        nhc_e.assign(chunk, 0.0);
+        if (nvt) mgr.step_nvt_nhc(dt, (int64_t)chunk, chain, (int64_t)i, (int64_t)steps, th.data(), nhc_e.data());
+        else mgr.step_nve(dt, (int64_t)chunk, th.data());
         for (size_t k = 0; k < chunk; ++k) {
             const size_t step = i + k + 1;
             if (dump_step > 0 && step % dump_step == 0) {
@@ -566,7 +577,8 @@ void Simulation::run(LJCudaManager &mgr, SimulationContext &ctx, FILE *out) {
                 dumper.write_step(atoms, step);
             }
             const double ke = th[k].ke, pe = th[k].pe;
-            std::fprintf(out, "%zu %.3f %.3f %.3f %.3f %.3f\n", step, pe, ke, pe + ke, atoms.temerature(ke),
+            // compute_hamiltonian (simulation.rs:90-115): NVT adds the thermostat's kinetic + potential energy
+            std::fprintf(out, "%zu %.3f %.3f %.3f %.3f %.3f\n", step, pe, ke, pe + ke + nhc_e[k], atoms.temerature(ke),
                          atoms.pressure(ke, th[k].virial_ref));
         }
         i += chunk;

@@ -8,7 +8,7 @@
 //   Command / run_*    src/readers/input_file/commands.rs
 //   SimulationContext  src/readers/simulation_context.rs
 //   System             src/system.rs
-//   Simulation         src/simulation.rs   (NVE arm; NVT/NPT are out of scope and rejected)
+//   Simulation         src/simulation.rs   (NVE and NVT arms; NPT is out of scope and rejected)
 //   DumpTraj           src/writers/dump_traj.rs
 #pragma once
 #include <cstdint>
@@ -83,6 +83,8 @@ class LJCudaManager {
     void attach(const Atoms &atoms);
     double compute(bool accumulate);
     void step_nve(double dt, int64_t nsteps, pisb_thermo *out);
+    void step_nvt_nhc(double dt, int64_t nsteps, pisb_nhc &chain, int64_t first_step, int64_t total_steps, pisb_thermo *out,
+                      double *nhc_energy);  // verlet_step_nvt_nhc x nsteps (potential.rs:35-58)
     void download(Atoms &atoms, bool pos, bool vel, bool frc);
     pisb_stats_t stats();
     std::map<std::pair<int, int>, LennardJones> table;
@@ -149,7 +151,7 @@ class DumpTraj {                   // dump_traj.rs:12-75
 enum class Ensemble { NVE, NVT, NPT };  // simulation.rs:118-133
 
 struct Simulation {
-    static void run(LJCudaManager &mgr, SimulationContext &ctx, FILE *thermo_out);  // simulation.rs:8-39 (NVE)
+    static void run(LJCudaManager &mgr, SimulationContext &ctx, FILE *thermo_out);  // simulation.rs:8-39 (NVE, NVT)
 };
 
 class System {                     // system.rs:35-183

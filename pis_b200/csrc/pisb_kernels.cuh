@@ -210,6 +210,7 @@ struct VVArgs {
     double *partials;
     unsigned int *ticket;
     pisb_thermo *thermo;  // record of the step the KICK completes
+    const double *vscale;  // NVT: thermostat scale exp(-dt/2 xi_1) read from device memory (null for NVE)
 };
 
 template <bool KICK, bool DRIFT, bool ORTHO>
@@ -227,6 +228,12 @@ __global__ void __launch_bounds__(TPB) k_vv(VVArgs a) {
             vx = __dadd_rn(vx, __dmul_rn(__dmul_rn(__dadd_rn(ox, ax), 0.5), a.dt));
             vy = __dadd_rn(vy, __dmul_rn(__dmul_rn(__dadd_rn(oy, ay), 0.5), a.dt));
             vz = __dadd_rn(vz, __dmul_rn(__dmul_rn(__dadd_rn(oz, az), 0.5), a.dt));
+            if (a.vscale) {  // verlet_step_nvt_nhc: velocities = &velocities * scale AFTER the NVE step (potential.rs:50)
+                const double sc = *a.vscale;
+                vx = __dmul_rn(vx, sc);
+                vy = __dmul_rn(vy, sc);
+                vz = __dmul_rn(vz, sc);
+            }
             a.vx[i] = vx;
             a.vy[i] = vy;
             a.vz[i] = vz;
@@ -236,6 +243,15 @@ __global__ void __launch_bounds__(TPB) k_vv(VVArgs a) {
             red[3] = __dmul_rn(x.z, fz);
         }
         if (DRIFT) {
+            if (!KICK && a.vscale) {  // ... and BEFORE it (potential.rs:45-46); stored, the kick starts from the scaled v
+                const double sc = *a.vscale;
+                vx = __dmul_rn(vx, sc);
+                vy = __dmul_rn(vy, sc);
+                vz = __dmul_rn(vz, sc);
+                a.vx[i] = vx;
+                a.vy[i] = vy;
+                a.vz[i] = vz;
+            }
             x.x = __dadd_rn(x.x, __dadd_rn(__dmul_rn(vx, a.dt), __dmul_rn(__dmul_rn(ax, 0.5), a.dt2)));
             x.y = __dadd_rn(x.y, __dadd_rn(__dmul_rn(vy, a.dt), __dmul_rn(__dmul_rn(ay, 0.5), a.dt2)));
             x.z = __dadd_rn(x.z, __dadd_rn(__dmul_rn(vz, a.dt), __dmul_rn(__dmul_rn(az, 0.5), a.dt2)));
@@ -259,6 +275,48 @@ __global__ void __launch_bounds__(TPB) k_vv(VVArgs a) {
             else t3[q - 1] = s;
             if (q == 3) th->virial_ref = (t3[0] + t3[1]) + t3[2];
         });
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Nose-Hoover chain (src/ensemble/nvt.rs), kept on the device so an NVT batch needs no host round
+// trip: one thread advances the chain from the kinetic energy the kick kernel just reduced.
+// Quirks kept as written in the reference: xi is ASSIGNED in propagate_half_step (:72-80), eta never
+// advances, the chain has 3 links (:108), the target temperature ramps linearly per step (:114-123).
+// ------------------------------------------------------------------------------------------------
+struct NhcDev {
+    pisb_nhc c;
+    double scale;  // exp(-0.5 dt xi[0]) of the current step
+};
+
+__global__ void k_nhc_half(NhcDev *nhc, const double *ke_ptr, long long n_atoms, double dt, int second_half,
+                           long long step_index, long long total_steps, double *energy_out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    pisb_nhc &c = nhc->c;
+    const double KB = 0.0083144621;  // src/constants.rs:3
+    const double ke = *ke_ptr;
+    // compute_forces (:59-69)
+    c.g[0] = __dsub_rn(__dmul_rn(2.0, ke), __dmul_rn(__dmul_rn((double)(n_atoms * 3), KB), c.target_temperature));
+    for (int j = 1; j < 3; ++j)
+        c.g[j] = __dsub_rn(__dmul_rn(c.q[j - 1], __dmul_rn(c.xi[j - 1], c.xi[j - 1])), __dmul_rn(KB, c.target_temperature));
+    // propagate_half_step (:72-80)
+    c.xi[2] = __ddiv_rn(__dmul_rn(__dmul_rn(0.5, dt), c.g[2]), c.q[2]);
+    for (int l = 1; l >= 0; --l)
+        c.xi[l] = __dmul_rn(__ddiv_rn(__dmul_rn(__dmul_rn(0.5, dt), c.g[l]), c.q[l]), exp(__dmul_rn(__dmul_rn(-0.25, dt), c.xi[l + 1])));
+    if (!second_half) {
+        nhc->scale = exp(__dmul_rn(__dmul_rn(-0.5, dt), c.xi[0]));  // potential.rs:45
+    } else {
+        // Simulation::step: calculate_target_temperature(i, steps) (simulation.rs:55; nvt.rs:114-123)
+        c.target_temperature = __dadd_rn(c.start_temperature,
+                                         __dmul_rn(__ddiv_rn(__dsub_rn(c.end_temperature, c.start_temperature), (double)total_steps),
+                                                   (double)step_index));
+        if (energy_out) {  // nhc.kinetic_energy() + nhc.potential_energy(n) for the Hamiltonian (simulation.rs:101-104)
+            double tke = 0.0;
+            for (int i = 0; i < 3; ++i) tke = __dadd_rn(tke, __dmul_rn(__dmul_rn(0.5, c.q[i]), __dmul_rn(c.xi[i], c.xi[i])));
+            double tpe = __dmul_rn(__dmul_rn(__dmul_rn((double)(n_atoms * 3), KB), c.target_temperature), c.eta[0]);
+            for (int i = 1; i < 3; ++i) tpe = __dadd_rn(tpe, __dmul_rn(__dmul_rn(KB, c.target_temperature), c.eta[i]));
+            *energy_out = __dadd_rn(tke, tpe);
+        }
     }
 }
 

@@ -95,6 +95,8 @@ struct pisb_handle {
     DevBuf<double> mass_d, partials, st_pos, st_vel, st_frc;
     DevBuf<int> st_types;
     DevBuf<PairDev> table_d;
+    DevBuf<NhcDev> nhc_d;
+    DevBuf<double> nhc_energy_d;
     DevBuf<pisb_thermo> thermo_d;
     int *flags = nullptr;
     unsigned int *ticket = nullptr;
@@ -568,12 +570,12 @@ int launch_force(pisb_t *h, double *const out[3], const double *const acc[3], pi
     return check_launch(h, "k_force");
 }
 
-int launch_vv(pisb_t *h, bool kick, bool drift, double dt, pisb_thermo *rec) {
+int launch_vv(pisb_t *h, bool kick, bool drift, double dt, pisb_thermo *rec, const double *vscale = nullptr) {
     LaunchScope ls(h, PISB_K_INTEGRATE);
     const double hs = 0.5 * h->skin;
     VVArgs a{h->n, h->xt.p, h->xf.p, h->v[0].p, h->v[1].p, h->v[2].p, h->f[0].p, h->f[1].p, h->f[2].p,
              h->g[0].p, h->g[1].p, h->g[2].p, h->xb[0].p, h->xb[1].p, h->xb[2].p, h->mass_d.p, h->box,
-             dt, dt * dt, hs * hs, h->skin > 0.0 ? 0 : 1, h->flags, h->partials.p, h->ticket, rec};
+             dt, dt * dt, hs * hs, h->skin > 0.0 ? 0 : 1, h->flags, h->partials.p, h->ticket, rec, vscale};
     const int nb = nblk(h->n, TPB);
     cudaStream_t st = h->stream;
     const bool o = h->box.ortho != 0;
@@ -787,6 +789,75 @@ int do_step_nve(pisb_t *h, double dt, int64_t nsteps, pisb_thermo *out) {
     return PISB_OK;
 }
 
+
+
+// NVT batch: verlet_step_nvt_nhc x nsteps with the chain on the device (see k_nhc_half).
+int do_step_nvt(pisb_t *h, double dt, int64_t nsteps, pisb_nhc *chain, int64_t first_step, int64_t total_steps,
+                pisb_thermo *out, double *nhc_energy) {
+    if (!h->have_atoms || !h->have_box) return fail(h, PISB_ERR_STATE, "set_box and upload must precede step_nvt_nhc");
+    if (h->multi) return fail(h, PISB_ERR_STATE, "pisb_step_nvt_nhc is a single-GPU entry point");
+    if (!chain || chain->chain_size != 3) return fail(h, PISB_ERR_INVALID, "chain must be a 3-link pisb_nhc (pisb_nhc_init)");
+    if (nsteps < 0 || total_steps <= 0) return fail(h, PISB_ERR_INVALID, "bad step counts");
+    if (nsteps == 0) return PISB_OK;
+    TRY(ensure_list(h));
+    TRY(check_bad_type(h));
+    TRY(dev_reserve(h, h->nhc_d, 1));
+    NhcDev init{};
+    init.c = *chain;
+    init.scale = 1.0;
+    CUDA_TRY(h, cudaMemcpyAsync(h->nhc_d.p, &init, sizeof init, cudaMemcpyHostToDevice, h->stream));
+    const int64_t chunk_max = 4096;
+    int64_t done = 0;
+    std::vector<double> he;
+    while (done < nsteps) {
+        const int64_t m = std::min(chunk_max, nsteps - done);
+        TRY(reserve_thermo(h, (size_t)m + 2));
+        TRY(dev_reserve(h, h->nhc_energy_d, (size_t)m));
+        pisb_thermo *ke0 = h->thermo_d.p + m;  // scratch record: KE of the state entering the batch
+        {
+            LaunchScope ls(h, PISB_K_REDUCE);
+            k_observe<<<nblk(h->n, TPB), TPB, 0, h->stream>>>(h->n, h->xt.p, h->v[0].p, h->v[1].p, h->v[2].p, h->f[0].p, h->f[1].p,
+                                                              h->f[2].p, h->mass_d.p, h->partials.p, h->ticket, ke0);
+            TRY(check_launch(h, "k_observe"));
+        }
+        for (int64_t s = 0; s < m; ++s) {
+            pisb_thermo *rec = h->thermo_d.p + s;
+            const double *ke_in = s == 0 ? &ke0->ke : &(rec - 1)->ke;
+            k_nhc_half<<<1, 32, 0, h->stream>>>(h->nhc_d.p, ke_in, (long long)h->n, dt, 0, 0, 1, nullptr);
+            TRY(launch_vv(h, false, true, dt, nullptr, &h->nhc_d.p->scale));
+            TRY(launch_rebuild_chain(h));
+            double *outp[3] = {h->g[0].p, h->g[1].p, h->g[2].p};
+            TRY(launch_force(h, outp, nullptr, rec));
+            for (int d = 0; d < 3; ++d) std::swap(h->f[d], h->g[d]);
+            TRY(launch_vv(h, true, false, dt, rec, &h->nhc_d.p->scale));
+            k_nhc_half<<<1, 32, 0, h->stream>>>(h->nhc_d.p, &rec->ke, (long long)h->n, dt, 1, (long long)(first_step + done + s),
+                                                (long long)total_steps, h->nhc_energy_d.p + s);
+            h->n_launches += 2;
+        }
+        TRY(check_launch(h, "nvt step"));
+        CUDA_TRY(h, cudaMemcpyAsync(h->h_thermo, h->thermo_d.p, sizeof(pisb_thermo) * m, cudaMemcpyDeviceToHost, h->stream));
+        he.resize((size_t)m);
+        CUDA_TRY(h, cudaMemcpyAsync(he.data(), h->nhc_energy_d.p, sizeof(double) * m, cudaMemcpyDeviceToHost, h->stream));
+        TRY(read_flags(h));
+        if (h->h_flags[FLAG_NBUILDS] != h->n_builds_host) {
+            h->n_builds_host = h->h_flags[FLAG_NBUILDS];
+            h->max_nbr = h->h_flags[FLAG_MAXNBR];
+        }
+        if (h->h_flags[FLAG_MAXNBR] > h->kcap) {
+            h->list_valid = false;
+            return fail(h, PISB_ERR_CAPACITY, "a neighbour list overflowed during the batch; re-upload the state and repeat the call");
+        }
+        if (out) std::memcpy(out + done, h->h_thermo, sizeof(pisb_thermo) * m);
+        if (nhc_energy) std::memcpy(nhc_energy + done, he.data(), sizeof(double) * m);
+        done += m;
+        h->n_steps += m;
+    }
+    NhcDev fin{};
+    CUDA_TRY(h, cudaMemcpy(&fin, h->nhc_d.p, sizeof fin, cudaMemcpyDeviceToHost));
+    *chain = fin.c;
+    h->forces_current = true;
+    return PISB_OK;
+}
 
 // ================================================================================================
 // multi-GPU host orchestration (see pisb_multi.cuh for the scheme)
@@ -1242,6 +1313,8 @@ int pisb_destroy(pisb_t *h) {
     dev_free(h, h->st_frc);
     dev_free(h, h->st_types);
     dev_free(h, h->table_d);
+    dev_free(h, h->nhc_d);
+    dev_free(h, h->nhc_energy_d);
     dev_free(h, h->thermo_d);
     dev_free(h, h->m_dest);
     dev_free(h, h->m_pig);
@@ -1318,6 +1391,29 @@ int pisb_step_nve(pisb_t *h, double dt, int64_t nsteps, pisb_thermo *out) {
     if (!h) return PISB_ERR_INVALID;
     CUDA_TRY(h, cudaSetDevice(h->device));
     return do_step_nve(h, dt, nsteps, out);
+}
+
+int pisb_nhc_init(pisb_nhc *out, double start_temperature, double end_temperature, double tau) {
+    if (!out) return PISB_ERR_INVALID;
+    std::memset(out, 0, sizeof *out);
+    out->chain_size = 3;
+    out->start_temperature = start_temperature;
+    out->end_temperature = end_temperature;
+    out->target_temperature = start_temperature;
+    const double q_value = 0.0083144621 * out->target_temperature * (tau * tau);
+    double p10 = 1.0;
+    for (int i = 0; i < 3; ++i) {
+        out->q[i] = q_value / p10;
+        p10 *= 10.0;
+    }
+    return PISB_OK;
+}
+
+int pisb_step_nvt_nhc(pisb_t *h, double dt, int64_t nsteps, pisb_nhc *chain, int64_t first_step, int64_t total_steps,
+                      pisb_thermo *out, double *nhc_energy) {
+    if (!h) return PISB_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    return do_step_nvt(h, dt, nsteps, chain, first_step, total_steps, out, nhc_energy);
 }
 
 int pisb_download(pisb_t *h, double *pos, double *vel, double *force) {

@@ -160,6 +160,22 @@ class LJCudaManager:
         capi.check(self._h, capi.load().pisb_step_nve(self._h, float(dt), int(nsteps), capi._ptr(out)))
         return out
 
+    @staticmethod
+    def nhc_new(start_temperature: float, end_temperature: float, tau: float) -> "capi.Nhc":
+        """NHThermostatChain::new_from_args (src/ensemble/nvt.rs:99-112): 3 links, target = start."""
+        c = capi.Nhc()
+        capi.check(None, capi.load().pisb_nhc_init(C.byref(c), float(start_temperature), float(end_temperature), float(tau)))
+        return c
+
+    def step_nvt_nhc(self, dt: float, nsteps: int, chain: "capi.Nhc", first_step: int, total_steps: int):
+        """nsteps x (verlet_step_nvt_nhc + calculate_target_temperature) on the device (potential.rs:35-58,
+        simulation.rs:53-57).  Returns (thermo records, thermostat energy per step); `chain` is updated in place."""
+        out = np.zeros(int(nsteps), dtype=capi.THERMO_DTYPE)
+        en = np.zeros(int(nsteps))
+        capi.check(self._h, capi.load().pisb_step_nvt_nhc(self._h, float(dt), int(nsteps), C.byref(chain), int(first_step),
+                                                          int(total_steps), capi._ptr(out), capi._ptr(en)))
+        return out, en
+
     def download(self, atoms: Atoms, positions=True, velocities=True, forces=True):
         rc = capi.load().pisb_download(self._h, capi._ptr(atoms.positions) if positions else None,
                                        capi._ptr(atoms.velocities) if velocities else None,

@@ -144,6 +144,42 @@ def test_cli_errors(tmp_path):
 
 
 @pytest.mark.gpu
+def test_cli_nvt_run_matches_oracle(tmp_path):
+    """`fix ... nvt temp 5.0 50.0 50` through the CLI: thermo lines (H includes the thermostat energy) vs the oracle."""
+    from oracle.pis_oracle import Oracle
+    from pis_b200.lattice import fcc_argon
+
+    atoms = fcc_argon(6, temperature=5.0, seed=3)
+    n, L = atoms.n_atoms, atoms.sim_box.h[0, 0]
+    lines = [f"{n} atoms", "1 atom types", "", f"0.0 {rust_display(L)} xlo xhi", f"0.0 {rust_display(L)} ylo yhi",
+             f"0.0 {rust_display(L)} zlo zhi", "", "Masses", "1 39.948", "", "PairCoeffs", "1 0.238 3.405 8.5", "", "Atoms"]
+    lines += [f"{i + 1} 1 {repr(float(p[0]))} {repr(float(p[1]))} {repr(float(p[2]))}" for i, p in enumerate(atoms.positions)]
+    lines += ["", "Velocities"]
+    lines += [f"{i + 1} {repr(float(v[0]))} {repr(float(v[1]))} {repr(float(v[2]))}" for i, v in enumerate(atoms.velocities)]
+    (tmp_path / "argon.txt").write_text("\n".join(lines) + "\n")
+    steps = 60
+    (tmp_path / "input.pis").write_text(f"timestep 0.25\nread_data argon.txt\nfix mynvt all nvt temp 5.0 50.0 50\n"
+                                        f"dump dp1 all atom 20 dump.lammpstrj\nrun {steps}\n")
+    r = subprocess.run([CLI, "-i", "input.pis", "--skin", "1.0215"], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    out = r.stdout.strip().splitlines()
+    o = Oracle.cubic(L)
+    o.insert(1, 1, 0.238, 3.405, 8.5)
+    chain = o.nhc_new(5.0, 50.0, 50.0)
+    x, v = atoms.positions.copy(), atoms.velocities.copy()
+    ref = o.run_nvt(x, v, np.zeros_like(x), atoms.type_ids, 0.25, steps, chain)
+    assert len(out) == steps + 1
+    for s in range(1, steps + 1):
+        got = [float(t) for t in out[s].split()[1:]]
+        for g, e in zip(got, ref[s]):
+            assert abs(g - e) <= 1.1e-3 + 1e-9 * abs(e)
+    # NPT is still rejected
+    (tmp_path / "npt.pis").write_text("read_data argon.txt\nfix a all npt temp 5.0 50.0 100 iso 0.01 0.01 1000\nrun 5\n")
+    r = subprocess.run([CLI, "-i", "npt.pis"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 1 and "NPT" in r.stderr
+
+
+@pytest.mark.gpu
 def test_cli_nve_run_matches_oracle(tmp_path):
     """example/input.pis shape (NVE): thermo lines and dump.lammpstrj against the oracle's Simulation::run."""
     from oracle.pis_oracle import Oracle

@@ -475,3 +475,34 @@ def test_list_capacity_grows_and_user_cap_is_enforced():
     with pytest.raises(PisbError) as e:
         small.compute_potential(atoms)
     assert e.value.code == PISB_ERR_CAPACITY
+
+
+def test_nvt_nose_hoover_trace_parity():
+    """verlet_step_nvt_nhc (potential.rs:35-58) + NHThermostatChain (nvt.rs) with the temperature ramp of
+    `fix mynvt all nvt temp 5.0 50.0 50`; PE / KE / Hamiltonian (incl. thermostat energy) traces and the chain state."""
+    atoms = fcc_argon(8, temperature=5.0, seed=12345)
+    table = {(1, 1): argon_pair(8.5)}
+    orc = make_oracle(atoms, table)
+    steps = 400
+    chain_ref = orc.nhc_new(5.0, 50.0, 50.0)
+    x, v = atoms.positions.copy(), atoms.velocities.copy()
+    ref = orc.run_nvt(x, v, np.zeros_like(x), atoms.type_ids, 0.25, steps, chain_ref)
+    mgr = make_manager(skin=SKIN, rc=8.5)
+    mgr.attach(atoms)
+    mgr.compute()
+    chain = mgr.nhc_new(5.0, 50.0, 50.0)
+    assert list(chain.q) == list(chain_ref.q) and chain.target_temperature == 5.0
+    # two batches: the chain state and the ramp index carry over
+    th1, e1 = mgr.step_nvt_nhc(0.25, 150, chain, 0, steps)
+    th2, e2 = mgr.step_nvt_nhc(0.25, steps - 150, chain, 150, steps)
+    pe = np.concatenate([th1["pe"], th2["pe"]])
+    ke = np.concatenate([th1["ke"], th2["ke"]])
+    ham = pe + ke + np.concatenate([e1, e2])
+    assert np.max(np.abs(pe - ref[1:, 0]) / np.abs(ref[1:, 0])) <= ENERGY_TOL
+    assert np.max(np.abs(ke - ref[1:, 1]) / np.abs(ref[1:, 1])) <= ENERGY_TOL
+    assert np.max(np.abs(ham - ref[1:, 2]) / np.abs(ref[1:, 2])) <= ENERGY_TOL
+    assert atoms.temerature(ke[-1]) > 40.0                     # the ramp heated the crystal towards 50 K
+    for a_, b_ in zip(list(chain.xi) + [chain.target_temperature], list(chain_ref.xi) + [chain_ref.target_temperature]):
+        assert abs(a_ - b_) <= 1e-9 * max(abs(b_), 1e-12)
+    mgr.download(atoms)
+    assert np.abs(atoms.positions - x).max() < 1e-8
