@@ -244,11 +244,11 @@ def run_single(args):
     cpu = None
     if not args.no_cpu_baseline:
         cvalue, cores, per = time_cpu_path(args.ref_ncell, args.temperature, args.cpu_steps, 1, args.cpu_threads)
-        svalue, _, sper = time_cpu_path(args.ref_ncell_serial, args.temperature, 2, 1, 1)
+        svalue, _, sper = time_cpu_path(args.ref_ncell_serial, args.temperature, 10, 1, 1)
         cpu = {"value": cvalue, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{4 * args.ref_ncell ** 3}-atom FCC argon block, {args.cpu_steps} steps, OpenMP all-core variant "
                          f"({sum(per):.1f} s)",
-               "serial_value": svalue, "serial_sample": f"{4 * args.ref_ncell_serial ** 3} atoms, 2 steps, 1 thread "
+               "serial_value": svalue, "serial_sample": f"{4 * args.ref_ncell_serial ** 3} atoms, 10 steps, 1 thread ({sum(sper):.1f} s) "
                                                         f"(what the reference actually executes)"}
 
     h = th["pe"] + th["ke"]
@@ -276,7 +276,7 @@ def main():
     ap.add_argument("--temperature", type=float, default=43.0, help="initial temperature (K); 43 K exercises rebuilds")
     ap.add_argument("--ref-ncell", type=int, default=40, help="CPU sample size (40 -> 256k atoms)")
     ap.add_argument("--ref-ncell-serial", type=int, default=20)
-    ap.add_argument("--cpu-steps", type=int, default=5)
+    ap.add_argument("--cpu-steps", type=int, default=40, help="CPU-baseline sample: steps of the ref-ncell block (~10 s on 16 cores)")
     ap.add_argument("--cpu-threads", type=int, default=0)
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
