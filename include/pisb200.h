@@ -192,10 +192,13 @@ PISB_API int pisb_comm_unique_id(void *out128, int nbytes);
 PISB_API int pisb_comm_init(pisb_t *h, int rank, int nranks, const void *unique_id128, const int *grid3);
 PISB_API int pisb_upload_owned(pisb_t *h, int64_t n_own, const double *pos, const double *vel,
                                const double *force, const int32_t *types, const int32_t *global_ids);
-/* Owned atoms of this rank in device slot order (the order pisb_neighbours rows use in multi-GPU
- * mode, where list entries are global ids).  Arrays hold up to cap atoms; *n_out = count. */
+/* Owned atoms of this rank (any of pos/vel/force may be NULL), compacted on the device; the order is
+ * arbitrary -- global_ids identifies each row.  Arrays hold up to cap atoms; *n_out = count. */
 PISB_API int pisb_download_owned(pisb_t *h, int64_t cap, double *pos, double *vel, double *force,
                                  int32_t *global_ids, int64_t *n_out);
+/* Test hook: global ids of the owned atoms in device slot order == the row order of pisb_neighbours in
+ * multi-GPU mode (where list entries are global ids). */
+PISB_API int pisb_owned_ids(pisb_t *h, int64_t cap, int32_t *global_ids, int64_t *n_out);
 
 /* Tuning knobs (0 = keep default): list_capacity = neighbour slots per atom (auto-grown on
  * overflow), force_variant = kernel variant selector for A/B measurements. */

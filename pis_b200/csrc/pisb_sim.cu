@@ -1686,37 +1686,54 @@ int pisb_upload_owned(pisb_t *h, int64_t n_own, const double *pos, const double 
 
 int pisb_download_owned(pisb_t *h, int64_t cap, double *pos, double *vel, double *force, int32_t *gids,
                         int64_t *n_out) {
-    if (!h || !n_out) return PISB_ERR_INVALID;
+    if (!h || !n_out || !gids) return PISB_ERR_INVALID;
     if (!h->multi || !h->have_atoms) return fail(h, PISB_ERR_STATE, "pisb_download_owned needs multi-GPU mode and uploaded atoms");
     CUDA_TRY(h, cudaSetDevice(h->device));
+    const int n = h->n, no = h->n_own;
+    if (no > cap) return fail(h, PISB_ERR_CAPACITY, "pisb_download_owned: cap too small");
+    const size_t n3 = (size_t)3 * std::max(no, 1);
+    if (pos) TRY(dev_reserve_grow(h, h->st_pos, n3));
+    if (vel) TRY(dev_reserve_grow(h, h->st_vel, n3));
+    if (force) TRY(dev_reserve_grow(h, h->st_frc, n3));
+    TRY(dev_reserve_grow(h, h->st_types, (size_t)std::max(no, 1)));  // staging for the ids
+    TRY(dev_reserve(h, h->m_cnt, (size_t)std::max(h->dc.nranks, 1)));
+    CUDA_TRY(h, cudaMemsetAsync(h->m_cnt.p, 0, sizeof(int), h->stream));
+    {
+        LaunchScope ls(h, PISB_K_COPY);
+        k_store_owned<<<nblk(std::max(n, 1), TPB), TPB, 0, h->stream>>>(n, h->xt.p, h->v[0].p, h->v[1].p, h->v[2].p, h->f[0].p,
+                                                                       h->f[1].p, h->f[2].p, h->id.p, h->m_cnt.p,
+                                                                       pos ? h->st_pos.p : nullptr, vel ? h->st_vel.p : nullptr,
+                                                                       force ? h->st_frc.p : nullptr, h->st_types.p);
+        TRY(check_launch(h, "k_store_owned"));
+    }
+    if (pos) CUDA_TRY(h, cudaMemcpyAsync(pos, h->st_pos.p, sizeof(double) * 3 * no, cudaMemcpyDeviceToHost, h->stream));
+    if (vel) CUDA_TRY(h, cudaMemcpyAsync(vel, h->st_vel.p, sizeof(double) * 3 * no, cudaMemcpyDeviceToHost, h->stream));
+    if (force) CUDA_TRY(h, cudaMemcpyAsync(force, h->st_frc.p, sizeof(double) * 3 * no, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(gids, h->st_types.p, sizeof(int) * no, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    *n_out = no;
+    return PISB_OK;
+}
+
+// Test hook (multi-GPU): global ids of the owned atoms in device slot order = the row order of pisb_neighbours.
+int pisb_owned_ids(pisb_t *h, int64_t cap, int32_t *gids, int64_t *n_out) {
+    if (!h || !n_out || !gids) return PISB_ERR_INVALID;
+    if (!h->multi || !h->have_atoms) return fail(h, PISB_ERR_STATE, "pisb_owned_ids needs multi-GPU mode and uploaded atoms");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (!h->list_valid) TRY(multi_rebuild(h));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     const int n = h->n;
     std::vector<double4> hx(n);
     std::vector<int> hid(n);
-    std::vector<double> hv[3], hf[3];
     CUDA_TRY(h, cudaMemcpy(hx.data(), h->xt.p, sizeof(double4) * n, cudaMemcpyDeviceToHost));
     CUDA_TRY(h, cudaMemcpy(hid.data(), h->id.p, sizeof(int) * n, cudaMemcpyDeviceToHost));
-    for (int d = 0; d < 3; ++d) {
-        if (vel) {
-            hv[d].resize(n);
-            CUDA_TRY(h, cudaMemcpy(hv[d].data(), h->v[d].p, sizeof(double) * n, cudaMemcpyDeviceToHost));
-        }
-        if (force) {
-            hf[d].resize(n);
-            CUDA_TRY(h, cudaMemcpy(hf[d].data(), h->f[d].p, sizeof(double) * n, cudaMemcpyDeviceToHost));
-        }
-    }
     int64_t o = 0;
     for (int s = 0; s < n; ++s) {
         long long wb;
         std::memcpy(&wb, &hx[s].w, 8);
         if ((wb >> 32) & 1) continue;
-        if (o >= cap) return fail(h, PISB_ERR_CAPACITY, "pisb_download_owned: cap too small");
-        if (pos) pos[3 * o] = hx[s].x, pos[3 * o + 1] = hx[s].y, pos[3 * o + 2] = hx[s].z;
-        if (vel) vel[3 * o] = hv[0][s], vel[3 * o + 1] = hv[1][s], vel[3 * o + 2] = hv[2][s];
-        if (force) force[3 * o] = hf[0][s], force[3 * o + 1] = hf[1][s], force[3 * o + 2] = hf[2][s];
-        if (gids) gids[o] = hid[s];
-        ++o;
+        if (o >= cap) return fail(h, PISB_ERR_CAPACITY, "pisb_owned_ids: cap too small");
+        gids[o++] = hid[s];
     }
     *n_out = o;
     return PISB_OK;

@@ -74,22 +74,30 @@ class DistributedLJ(LJCudaManager):
         capi.check(self._h, rc)
         self._atoms_id = None
 
-    def download_owned(self):
-        """(gids, pos, vel, force) of the atoms this rank owns now, in device slot order."""
-        st = self.stats()
-        cap = int(st["n_atoms"]) + 16
-        pos, vel, frc = np.zeros((cap, 3)), np.zeros((cap, 3)), np.zeros((cap, 3))
-        gid = np.zeros(cap, dtype=np.int32)
+    def download_owned(self, positions=True, velocities=True, forces=True):
+        """(gids, pos, vel, force) of the atoms this rank owns now (row order arbitrary; gids identify the rows).
+        The destination arrays are pinned and reused between calls."""
+        cap = int(self.stats()["n_atoms"]) + 16
+        if getattr(self, "_dl_cap", 0) < cap:
+            self._dl_cap = int(cap * 1.1) + 1024
+            self._dl = [capi.pinned_empty((self._dl_cap, 3)) for _ in range(3)] + [capi.pinned_empty((self._dl_cap,), np.int32)]
+        pos, vel, frc, gid = self._dl
         n = C.c_int64()
-        capi.check(self._h, capi.load().pisb_download_owned(self._h, cap, capi._ptr(pos), capi._ptr(vel), capi._ptr(frc),
-                                                            capi._ptr(gid), C.byref(n)))
+        capi.check(self._h, capi.load().pisb_download_owned(self._h, self._dl_cap, capi._ptr(pos) if positions else None,
+                                                            capi._ptr(vel) if velocities else None,
+                                                            capi._ptr(frc) if forces else None, capi._ptr(gid), C.byref(n)))
         k = n.value
         return gid[:k], pos[:k], vel[:k], frc[:k]
 
     def neighbours_owned(self):
-        """Rows (sorted global ids) for the owned atoms in download_owned() order."""
+        """(gids, rows): sorted global-id neighbour rows of the owned atoms and the global id of each row (test hook)."""
         n = int(self.stats()["n_atoms"])
-        return self.neighbours(n)
+        rows = self.neighbours(n)
+        gid = np.zeros(n + 16, dtype=np.int32)
+        k = C.c_int64()
+        capi.check(self._h, capi.load().pisb_owned_ids(self._h, n + 16, capi._ptr(gid), C.byref(k)))
+        assert k.value == n
+        return gid[:n].copy(), rows
 
 
 def gather_by_gid(gid, arrays, n_global):

@@ -100,7 +100,9 @@ def run(args):
     if rank == 0:
         peaks, peak_kind = B.measured_peaks()
         n_own = st1["n_atoms"]
-        nn_mean = 85.66 if args.temperature > 20 else 86.0
+        nn = np.zeros(int(n_own), dtype=np.int32)
+        capi.check(mgr._h, capi.load().pisb_neighbours(mgr._h, capi._ptr(nn), None, 0))
+        nn_mean = float(nn.mean())
         f_ms = tim["force"]["ms"] / max(tim["force"]["launches"], 1)
         achieved = (48.0 + 4.0 * nn_mean) * n_own / (f_ms * 1e-3) / 1e9
         peak = float(peaks.get("hbm_gbs", 6650.0))
@@ -121,7 +123,7 @@ def run(args):
                             "pisb_download_owned (x, v, F, ids) every 10 steps (the example's dump cadence); state is uploaded once"},
             "gpu_launches": int(st1["n_launches"] - st0["n_launches"]),
             "roofline": {"kernel": "k_force_v3", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_kind,
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_kind, "mean_neighbours": nn_mean,
                          "ms_per_launch": f_ms, "share_of_step": tim["force"]["ms"] / ms_total,
                          "note": "rank 0's force kernel; FP64/L1 bound, see DESIGN.md"},
             "cpu_baseline": None,

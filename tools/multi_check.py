@@ -43,15 +43,15 @@ def main():
     mgr.insert((1, 1), LennardJones(ARGON["epsilon"], ARGON["sigma"], rc, True))
     mgr.attach_owned(atoms, gid)
     pe0 = mgr.compute()
-    g0, _, _, f0 = mgr.download_owned()
-    rows0 = mgr.neighbours_owned()
+    g0, _, _, f0 = (a_.copy() for a_ in mgr.download_owned())
+    gr0, rows0 = mgr.neighbours_owned()
     th = mgr.step_nve(0.25, steps)
-    g1, x1, v1, f1 = mgr.download_owned()
+    g1, x1, v1, f1 = (a_.copy() for a_ in mgr.download_owned())
     st = mgr.stats()
     (F0,) = gather_by_gid(g0, [f0], n_global)
     X1, V1, F1 = gather_by_gid(g1, [x1, v1, f1], n_global)
     pieces = [None] * world
-    dist.all_gather_object(pieces, (g0, rows0, st))
+    dist.all_gather_object(pieces, (gr0, rows0, st))
 
     if rank == 0:
         # the same system on ONE GPU
