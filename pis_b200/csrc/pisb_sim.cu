@@ -1508,10 +1508,10 @@ int pisb_neighbours(pisb_t *h, int32_t *nnbr, int32_t *nbr, int64_t cap_per_atom
         TRY(ensure_list(h));
     }
     const int n = h->n;
-    std::vector<int> hn(n), hid(n), hl((size_t)h->kcap * h->npad);
+    std::vector<int> hn(n), hid(n), hl(nbr ? (size_t)h->kcap * h->npad : 0);  // the list itself only when rows are wanted
     CUDA_TRY(h, cudaMemcpyAsync(hn.data(), h->nnbr.p, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(hid.data(), h->id.p, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(h, cudaMemcpyAsync(hl.data(), h->nbr.p, sizeof(int) * hl.size(), cudaMemcpyDeviceToHost, h->stream));
+    if (nbr) CUDA_TRY(h, cudaMemcpyAsync(hl.data(), h->nbr.p, sizeof(int) * hl.size(), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     int64_t total = 0;
     if (h->multi) {

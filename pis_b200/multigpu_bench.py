@@ -100,9 +100,9 @@ def run(args):
     if rank == 0:
         peaks, peak_kind = B.measured_peaks()
         n_own = st1["n_atoms"]
-        nn = np.zeros(int(n_own), dtype=np.int32)
+        nn = np.zeros(int(mgr.stats()["n_atoms"]) + 64, dtype=np.int32)  # owned count NOW (atoms migrate)
         capi.check(mgr._h, capi.load().pisb_neighbours(mgr._h, capi._ptr(nn), None, 0))
-        nn_mean = float(nn.mean())
+        nn_mean = float(nn[: int(mgr.stats()['n_atoms'])].mean())
         f_ms = tim["force"]["ms"] / max(tim["force"]["launches"], 1)
         achieved = (48.0 + 4.0 * nn_mean) * n_own / (f_ms * 1e-3) / 1e9
         peak = float(peaks.get("hbm_gbs", 6650.0))
