@@ -227,6 +227,8 @@ void drain_events(pisb_t *h) {
 }
 
 inline int nblk(int n, int tpb) { return (n + tpb - 1) / tpb; }
+// capped grid for the grid-stride kernels of the (conditionally executed) rebuild chain
+inline int nblk_capped(int n, int tpb, int per_sm) { return std::max(1, std::min(nblk(n, tpb), 148 * per_sm)); }
 
 int check_launch(pisb_t *h, const char *what) {
     cudaError_t e = cudaGetLastError();
@@ -480,9 +482,9 @@ int launch_rebuild_chain(pisb_t *h) {
         LaunchScope ls(h, PISB_K_BIN);
         CUDA_TRY(h, cudaMemsetAsync(h->cell_count.p, 0, sizeof(int) * ((size_t)nb + 1), st));
         if (h->box.ortho)
-            k_bin<true><<<nblk(n, TPB), TPB, 0, st>>>(n, h->xt.p, h->box, g, h->cell_of.p, h->cell_count.p, h->flags);
+            k_bin<true><<<nblk_capped(n, TPB, 8), TPB, 0, st>>>(n, h->xt.p, h->box, g, h->cell_of.p, h->cell_count.p, h->flags);
         else
-            k_bin<false><<<nblk(n, TPB), TPB, 0, st>>>(n, h->xt.p, h->box, g, h->cell_of.p, h->cell_count.p, h->flags);
+            k_bin<false><<<nblk_capped(n, TPB, 8), TPB, 0, st>>>(n, h->xt.p, h->box, g, h->cell_of.p, h->cell_count.p, h->flags);
     }
     {
         LaunchScope ls(h, PISB_K_SORT);
@@ -490,17 +492,17 @@ int launch_rebuild_chain(pisb_t *h) {
         k_scan_tiles<<<ntiles, SCAN_TPB, 0, st>>>(nb, h->cell_count.p, h->tile_sum.p, h->flags);
         k_scan_sums<<<1, SCAN_TPB, 0, st>>>(ntiles, h->tile_sum.p, h->flags);
         k_scan_apply<<<ntiles, SCAN_TPB, 0, st>>>(nb, n, h->cell_count.p, h->tile_sum.p, h->cell_start.p, h->flags);
-        k_fill<<<nblk(n, TPB), TPB, 0, st>>>(n, h->cell_of.p, h->cell_start.p, h->cell_count.p, h->order.p, h->flags);
+        k_fill<<<nblk_capped(n, TPB, 8), TPB, 0, st>>>(n, h->cell_of.p, h->cell_start.p, h->cell_count.p, h->order.p, h->flags);
         k_sort_cells<<<nblk(g.ncell, TPB), TPB, 0, st>>>(g.ncell, h->cell_start.p, h->order.p, h->id.p, h->flags);
         PermArgs pa{n, h->order.p, h->xt.p, h->v[0].p, h->v[1].p, h->v[2].p, h->f[0].p, h->f[1].p, h->f[2].p,
                     h->id.p, h->s_xt.p, h->s_v[0].p, h->s_v[1].p, h->s_v[2].p, h->s_f[0].p, h->s_f[1].p,
                     h->s_f[2].p, h->s_id.p, h->flags};
-        k_permute<<<nblk(n, TPB), TPB, 0, st>>>(pa);
+        k_permute<<<nblk_capped(n, TPB, 8), TPB, 0, st>>>(pa);
         CopyBackArgs ca{n, h->s_xt.p, h->s_v[0].p, h->s_v[1].p, h->s_v[2].p, h->s_f[0].p, h->s_f[1].p, h->s_f[2].p,
                         h->s_id.p, h->xt.p, h->v[0].p, h->v[1].p, h->v[2].p, h->f[0].p, h->f[1].p, h->f[2].p,
                         h->id.p, h->multi ? nullptr : h->slot_of_id.p, h->xb[0].p, h->xb[1].p, h->xb[2].p, h->flags, h->xf.p,
                         h->box};
-        k_copy_back<<<nblk(n, TPB), TPB, 0, st>>>(ca);
+        k_copy_back<<<nblk_capped(n, TPB, 8), TPB, 0, st>>>(ca);
         h->n_launches += 6;
     }
     {
