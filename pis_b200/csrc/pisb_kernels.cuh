@@ -214,17 +214,29 @@ struct VVArgs {
 };
 
 template <bool KICK, bool DRIFT, bool ORTHO>
-__global__ void __launch_bounds__(TPB) k_vv(VVArgs a) {
+__global__ void __launch_bounds__(TPB, 4) k_vv(VVArgs a) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double red[4] = {0.0, 0.0, 0.0, 0.0};  // ke, x*fx, y*fy, z*fz
     if (i < a.n && !is_ghost(a.xt[i].w)) {
+        // every independent load first (the kernel is latency-bound otherwise: the mass lookup depends on x.w)
         double4 x = a.xt[i];
-        const double m = a.mass[type_of(x.w) - 1];
         double vx = a.vx[i], vy = a.vy[i], vz = a.vz[i];
         const double fx = a.fx[i], fy = a.fy[i], fz = a.fz[i];
+        double gx = 0.0, gy = 0.0, gz = 0.0, bx = 0.0, by = 0.0, bz = 0.0;
+        if (KICK) {
+            gx = a.gx[i];
+            gy = a.gy[i];
+            gz = a.gz[i];
+        }
+        if (DRIFT && !a.always_rebuild) {
+            bx = a.xbx[i];
+            by = a.xby[i];
+            bz = a.xbz[i];
+        }
+        const double m = a.mass[type_of(x.w) - 1];
         const double ax = __ddiv_rn(fx, m), ay = __ddiv_rn(fy, m), az = __ddiv_rn(fz, m);
         if (KICK) {
-            const double ox = __ddiv_rn(a.gx[i], m), oy = __ddiv_rn(a.gy[i], m), oz = __ddiv_rn(a.gz[i], m);
+            const double ox = __ddiv_rn(gx, m), oy = __ddiv_rn(gy, m), oz = __ddiv_rn(gz, m);
             vx = __dadd_rn(vx, __dmul_rn(__dmul_rn(__dadd_rn(ox, ax), 0.5), a.dt));
             vy = __dadd_rn(vy, __dmul_rn(__dmul_rn(__dadd_rn(oy, ay), 0.5), a.dt));
             vz = __dadd_rn(vz, __dmul_rn(__dmul_rn(__dadd_rn(oz, az), 0.5), a.dt));
@@ -261,7 +273,7 @@ __global__ void __launch_bounds__(TPB) k_vv(VVArgs a) {
             if (a.always_rebuild) {
                 if (i == 0) a.flags[FLAG_REBUILD] = 1;
             } else {
-                double dx = x.x - a.xbx[i], dy = x.y - a.xby[i], dz = x.z - a.xbz[i];
+                double dx = x.x - bx, dy = x.y - by, dz = x.z - bz;
                 min_image<ORTHO>(a.box, dx, dy, dz);
                 if (!(norm2(dx, dy, dz) <= a.half_skin2)) a.flags[FLAG_REBUILD] = 1;
             }
