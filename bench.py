@@ -224,6 +224,11 @@ def run_single(args):
                 "note": "the force kernel is bound by the FP64 pipe and L1TEX gather throughput, not by HBM (ncu: profiles/); "
                         "frac is algorithmic HBM bytes / measured copy peak; traffic = ncu dram bytes per launch"}
     kernel_ms = {k: round(v["ms"] / args.steps, 5) for k, v in tim.items() if v["launches"]}
+    # the streaming kernel next to it: fused kick+drift moves 200 B/atom
+    vv_ms = tim["integrate"]["ms"] / max(tim["integrate"]["launches"], 1)
+    roofline_integrate = {"kernel": "k_vv<kick,drift>", "bound": "hbm", "achieved": 200.0 * n / (vv_ms * 1e-3) / 1e9, "peak": peak,
+                          "unit": "GB/s", "frac": 200.0 * n / (vv_ms * 1e-3) / 1e9 / peak, "ms_per_launch": vv_ms,
+                          "algorithmic_bytes_per_atom": 200.0}
 
     # ---- end-to-end: the reference-facing trait call with HOST buffers, every step ----
     e2e_steps = max(3, min(args.e2e_steps, args.steps))
@@ -277,7 +282,7 @@ def run_single(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": workload_config(args, 1), "clocks": clk.summary(), "e2e": e2e,
         "e2e_resident": e2e_resident,
-        "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+        "gpu_launches": int(launches), "roofline": roofline, "roofline_integrate": roofline_integrate, "cpu_baseline": cpu,
         "kernel_ms_per_step": kernel_ms, "list_builds_in_timed_region": int(builds),
         "energy_drift_rel": float(np.abs(h - h[0]).max() / abs(h[0])),
         "stats": st1, "wall_s": time.perf_counter() - t_wall0,
