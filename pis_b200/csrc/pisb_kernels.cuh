@@ -18,7 +18,7 @@ constexpr int TPB = 256;        // streaming kernels
 constexpr int TPB_FORCE = 128;  // force / build kernels
 
 // flags[] (device ints)
-enum { FLAG_REBUILD = 0, FLAG_MAXNBR = 1, FLAG_NBUILDS = 2, FLAG_BADTYPE = 3, FLAG_COUNT = 8 };
+enum { FLAG_REBUILD = 0, FLAG_MAXNBR = 1, FLAG_NBUILDS = 2, FLAG_BADTYPE = 3, FLAG_COMM_TIMEOUT = 4, FLAG_COUNT = 8 };
 
 // Neighbour list layout: K-tiles of 4.  Entry (k, i) lives at ((k/4)*npad + i)*4 + k%4, so the four
 // neighbours k..k+3 of atom i are one aligned int4 and a warp reads 512 contiguous bytes per tile.

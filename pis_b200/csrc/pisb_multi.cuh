@@ -225,6 +225,93 @@ __global__ void __launch_bounds__(TPB) k_halo_unpack(int count, const int *__res
     xf[s] = make_xf(box, x);
 }
 
+// ---- per-step halo over peer memory (NVLink stores; no NCCL in the step loop) ---------------------------
+// Every rank maps every peer's receive buffer and signal words (CUDA IPC).  One exchange, sequence number seq:
+//   k_halo_push   : gathers this rank's ghost-source positions and STORES them straight into the peers' receive
+//                   buffers (slot [seq&1]: double-buffered, a rank can be at most one exchange ahead of a peer
+//                   because its next force step needs that peer's data);
+//   k_halo_signal : after the stores, publishes (seq << 1 | skin-trigger flag) into each peer's signal word;
+//   k_halo_pull   : spins until every peer's signal for seq has arrived, scatters the received records into the
+//                   cell-sorted ghost slots, and max-reduces the flags (the global rebuild decision).
+constexpr int P2P_MAX_RANKS = 8;
+
+struct P2PArgs {
+    int nranks, me, send_total, n_ghost;
+    int half;                        // records per parity half of every receive buffer (same on all ranks)
+    int src_off[P2P_MAX_RANKS];      // first send entry for peer r
+    int cnt[P2P_MAX_RANKS];          // entries for peer r
+    int dst_off[P2P_MAX_RANKS];      // where this rank's block starts inside peer r's receive layout
+    double4 *peer_recv[P2P_MAX_RANKS];
+    unsigned long long *peer_sig[P2P_MAX_RANKS];
+    const double4 *my_recv;
+    const unsigned long long *my_sig;  // [2][P2P_MAX_RANKS]
+};
+
+__global__ void __launch_bounds__(TPB) k_halo_push(P2PArgs a, unsigned long long seq, const int *__restrict__ send_idx,
+                                                   const double4 *__restrict__ xt) {
+    const int par = (int)(seq & 1ull);
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < a.send_total; k += gridDim.x * blockDim.x) {
+        int r = 0;
+#pragma unroll
+        for (int q = 0; q < P2P_MAX_RANKS; ++q)
+            if (q < a.nranks && a.cnt[q] > 0 && k >= a.src_off[q]) r = q;  // send entries are grouped by destination rank
+        a.peer_recv[r][(size_t)par * a.half + a.dst_off[r] + (k - a.src_off[r])] = xt[send_idx[k]];
+    }
+}
+
+__global__ void k_halo_signal(P2PArgs a, unsigned long long seq, const int *__restrict__ flags) {
+    const int r = threadIdx.x;
+    if (r >= a.nranks || r == a.me) return;
+    __threadfence_system();
+    const unsigned long long v = (seq << 1) | (unsigned long long)(flags[FLAG_REBUILD] ? 1 : 0);
+    atomicExch_system(&a.peer_sig[r][(seq & 1ull) * P2P_MAX_RANKS + a.me], v);
+}
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(TPB) k_halo_pull(P2PArgs a, unsigned long long seq, const int *__restrict__ ghost_slot,
+                                                   double4 *__restrict__ xt, float4 *__restrict__ xf, BoxDev box,
+                                                   int *__restrict__ flags, long long timeout_cycles) {
+    __shared__ int s_flag, s_timeout;
+    const int par = (int)(seq & 1ull);
+    if (threadIdx.x == 0) {
+        int f = 0, to = 0;
+        const long long t0 = clock64();
+        for (int r = 0; r < a.nranks; ++r) {
+            if (r == a.me) continue;
+            unsigned long long v;
+            while (((v = ld_acquire_sys(&a.my_sig[par * P2P_MAX_RANKS + r])) >> 1) < seq) {
+                if (clock64() - t0 > timeout_cycles) {
+                    to = 1;
+                    break;
+                }
+                __nanosleep(100);
+            }
+            f |= (int)(v & 1ull);
+        }
+        s_flag = f;
+        s_timeout = to;
+    }
+    __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (s_flag) flags[FLAG_REBUILD] = 1;
+        if (s_timeout) flags[FLAG_COMM_TIMEOUT] = 1;
+    }
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < a.n_ghost; k += gridDim.x * blockDim.x) {
+        const int s = ghost_slot[k];
+        const double2 *rp = reinterpret_cast<const double2 *>(&a.my_recv[(size_t)par * a.half + k]);
+        const double2 lo = __ldcg(rp), hi = __ldcg(rp + 1);  // L2 only: the data was written by a peer over NVLink
+        double4 x = make_double4(lo.x, lo.y, hi.x, hi.y);
+        x.w = type_ghost_as_double(type_of(x.w), true);
+        xt[s] = x;
+        xf[s] = make_xf(box, x);
+    }
+}
+
 // ---- owned-atom download ----------------------------------------------------------------------
 __global__ void __launch_bounds__(TPB) k_store_owned(int n, const double4 *__restrict__ xt, const double *vx,
                                                      const double *vy, const double *vz, const double *fx,

@@ -118,6 +118,16 @@ struct pisb_handle {
     std::vector<int> gs_cnt, gr_cnt, gs_off, gr_off;  // per-peer ghost send/recv counts and offsets
     int send_total = 0;
     int *h_counts = nullptr;  // pinned, nranks^2 ints
+    // per-step halo over peer memory (CUDA IPC + NVLink stores); NCCL send/recv is the fallback
+    int halo_mode = 0;  // 0 = auto (peer memory when it can be mapped), 1 = NCCL, 2 = peer memory or fail
+    bool p2p_tried = false, p2p_ok = false;
+    double4 *p2p_recv = nullptr;
+    unsigned long long *p2p_sig = nullptr;
+    int p2p_half = 0;
+    double4 *peer_recv[P2P_MAX_RANKS] = {nullptr};
+    unsigned long long *peer_sig[P2P_MAX_RANKS] = {nullptr};
+    int p2p_dst_off[P2P_MAX_RANKS] = {0};
+    unsigned long long halo_seq = 0;
 
     // stats
     int64_t n_steps = 0, n_launches = 0;
@@ -944,6 +954,8 @@ double wall_now() {
     return ts.tv_sec + 1e-9 * ts.tv_nsec;
 }
 
+int p2p_setup(pisb_t *h);
+
 // Atom migration + ghost selection + cell sort + list build.  Host-synchronous (counts cross PCIe).
 int multi_rebuild(pisb_t *h) {
     const bool trace = std::getenv("PISB_TRACE") != nullptr;
@@ -1030,6 +1042,16 @@ int multi_rebuild(pisb_t *h) {
     }
     h->send_total = gs;
     h->n_ghost = gr;
+    if (!h->p2p_tried) TRY(p2p_setup(h));
+    if (h->p2p_ok) {
+        if (gr > h->p2p_half) return fail(h, PISB_ERR_CAPACITY, "ghost count exceeds the peer-memory receive buffer");
+        for (int r = 0; r < R; ++r) {  // where my block starts inside peer r's receive layout (its gr_off[me])
+            int off = 0;
+            for (int q = 0; q < me; ++q)
+                if (q != r) off += h->h_counts[q * R + r];
+            h->p2p_dst_off[r] = off;
+        }
+    }
     if (n_slots1 + gr > h->ncap_atoms)
         return fail(h, PISB_ERR_CAPACITY, fmt("rank %d needs %d local slots (owned + ghost + stale), capacity %d", me, n_slots1 + gr, h->ncap_atoms));
     TRY(dev_reserve_grow(h, h->send_idx, (size_t)std::max(gs, 1)));
@@ -1098,9 +1120,119 @@ int multi_rebuild(pisb_t *h) {
     return fail(h, PISB_ERR_CAPACITY, "neighbour-list capacity did not converge");
 }
 
+
+// ---- peer-memory halo: map every peer's receive buffer and signal words through CUDA IPC ----------------
+struct P2PBlob {
+    cudaIpcMemHandle_t recv, sig;
+};
+
+void p2p_teardown(pisb_t *h) {
+    for (int r = 0; r < P2P_MAX_RANKS; ++r) {
+        if (h->peer_recv[r]) cudaIpcCloseMemHandle(h->peer_recv[r]);
+        if (h->peer_sig[r]) cudaIpcCloseMemHandle(h->peer_sig[r]);
+        h->peer_recv[r] = nullptr;
+        h->peer_sig[r] = nullptr;
+    }
+    if (h->p2p_recv) cudaFree(h->p2p_recv);
+    if (h->p2p_sig) cudaFree(h->p2p_sig);
+    h->p2p_recv = nullptr;
+    h->p2p_sig = nullptr;
+    h->p2p_ok = false;
+}
+
+int p2p_setup(pisb_t *h) {
+    h->p2p_tried = true;
+    h->p2p_ok = false;
+    const int R = h->dc.nranks, me = h->dc.rank;
+    if (R < 2 || R > P2P_MAX_RANKS || h->halo_mode == 1) return PISB_OK;
+    cudaStream_t st = h->stream;
+    // a common half size: the largest local capacity of any rank
+    int *d_tmp = h->m_cnt.p;
+    CUDA_TRY(h, cudaMemcpyAsync(d_tmp, &h->ncap_atoms, sizeof(int), cudaMemcpyHostToDevice, st));
+    NCCL_TRY(h, g_nccl.AllReduce(d_tmp, d_tmp, 1, ncclInt, ncclMax, h->comm, st));
+    int half = 0;
+    CUDA_TRY(h, cudaMemcpyAsync(&half, d_tmp, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+    int ok = 1;
+    if (cudaMalloc((void **)&h->p2p_recv, sizeof(double4) * 2 * (size_t)half) != cudaSuccess ||
+        cudaMalloc((void **)&h->p2p_sig, sizeof(unsigned long long) * 2 * P2P_MAX_RANKS) != cudaSuccess)
+        ok = 0;
+    P2PBlob mine{};
+    if (ok) {
+        cudaMemset(h->p2p_sig, 0, sizeof(unsigned long long) * 2 * P2P_MAX_RANKS);
+        if (cudaIpcGetMemHandle(&mine.recv, h->p2p_recv) != cudaSuccess || cudaIpcGetMemHandle(&mine.sig, h->p2p_sig) != cudaSuccess) ok = 0;
+    }
+    cudaGetLastError();
+    // all-gather the handles (bytes) over the NCCL communicator
+    DevBuf<char> d_blob;
+    TRY(dev_reserve(h, d_blob, sizeof(P2PBlob) * (size_t)(R + 1)));
+    CUDA_TRY(h, cudaMemcpyAsync(d_blob.p + sizeof(P2PBlob) * R, &mine, sizeof mine, cudaMemcpyHostToDevice, st));
+    NCCL_TRY(h, g_nccl.AllGather(d_blob.p + sizeof(P2PBlob) * R, d_blob.p, sizeof(P2PBlob), ncclChar, h->comm, st));
+    std::vector<P2PBlob> all(R);
+    CUDA_TRY(h, cudaMemcpyAsync(all.data(), d_blob.p, sizeof(P2PBlob) * R, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+    dev_free(h, d_blob);
+    for (int r = 0; r < R && ok; ++r) {
+        if (r == me) continue;
+        void *pr = nullptr, *ps = nullptr;
+        if (cudaIpcOpenMemHandle(&pr, all[r].recv, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+            cudaIpcOpenMemHandle(&ps, all[r].sig, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            ok = 0;
+            cudaGetLastError();
+            break;
+        }
+        h->peer_recv[r] = (double4 *)pr;
+        h->peer_sig[r] = (unsigned long long *)ps;
+    }
+    // every rank must take the same path
+    CUDA_TRY(h, cudaMemcpyAsync(d_tmp, &ok, sizeof(int), cudaMemcpyHostToDevice, st));
+    NCCL_TRY(h, g_nccl.AllReduce(d_tmp, d_tmp, 1, ncclInt, ncclMin, h->comm, st));
+    int all_ok = 0;
+    CUDA_TRY(h, cudaMemcpyAsync(&all_ok, d_tmp, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+    if (!all_ok) {
+        p2p_teardown(h);
+        if (h->halo_mode == 2) return fail(h, PISB_ERR_COMM, "halo_mode 2: peer memory could not be mapped through CUDA IPC");
+        return PISB_OK;
+    }
+    h->p2p_half = half;
+    h->p2p_ok = true;
+    h->halo_seq = 0;
+    return PISB_OK;
+}
+
+int halo_exchange_p2p(pisb_t *h) {
+    const int R = h->dc.nranks, me = h->dc.rank;
+    cudaStream_t st = h->stream;
+    const unsigned long long seq = ++h->halo_seq;
+    P2PArgs a{};
+    a.nranks = R;
+    a.me = me;
+    a.send_total = h->send_total;
+    a.n_ghost = h->n_ghost;
+    a.half = h->p2p_half;
+    for (int r = 0; r < R; ++r) {
+        a.src_off[r] = h->gs_off[r];
+        a.cnt[r] = h->gs_cnt[r];
+        a.dst_off[r] = h->p2p_dst_off[r];
+        a.peer_recv[r] = h->peer_recv[r];
+        a.peer_sig[r] = h->peer_sig[r];
+    }
+    a.my_recv = h->p2p_recv;
+    a.my_sig = h->p2p_sig;
+    LaunchScope ls(h, PISB_K_HALO);
+    if (h->send_total > 0) k_halo_push<<<nblk_capped(h->send_total, TPB, 4), TPB, 0, st>>>(a, seq, h->send_idx.p, h->xt.p);
+    k_halo_signal<<<1, 32, 0, st>>>(a, seq, h->flags);
+    k_halo_pull<<<nblk_capped(std::max(h->n_ghost, 1), TPB, 4), TPB, 0, st>>>(a, seq, h->ghost_slot.p, h->xt.p, h->xf.p, h->box, h->flags,
+                                                                             20000000000LL);
+    h->n_launches += 2;
+    return check_launch(h, "p2p halo");
+}
+
 // Per-step ghost position exchange (no rebuild).  with_flag: the skin-trigger flag of every rank travels in the
 // same NCCL group and k_halo_unpack forms the global max (replaces a separate all-reduce).
 int halo_exchange(pisb_t *h, bool with_flag) {
+    if (h->p2p_ok) return halo_exchange_p2p(h);  // NVLink stores + signals; the flag always rides along
     cudaStream_t st = h->stream;
     const int R = h->dc.nranks, me = h->dc.rank;
     if (h->send_total > 0) {
@@ -1184,6 +1316,7 @@ int do_step_nve_multi(pisb_t *h, double dt, int64_t nsteps, pisb_thermo *out) {
             CUDA_TRY(h, cudaMemcpyAsync(h->h_flags, h->flags, sizeof(int) * FLAG_COUNT, cudaMemcpyDeviceToHost, h->stream));
             CUDA_TRY(h, cudaStreamSynchronize(h->stream));
             double t2 = wall_now();
+            if (h->h_flags[FLAG_COMM_TIMEOUT]) return fail(h, PISB_ERR_COMM, "timed out waiting for a peer's ghost data (peer-memory halo)");
             const bool reb = h->h_flags[FLAG_REBUILD] != 0;
             if (reb) TRY(multi_rebuild(h));
             double t3 = wall_now();
@@ -1331,6 +1464,7 @@ int pisb_destroy(pisb_t *h) {
     dev_free(h, h->mig_recv);
     dev_free(h, h->halo_send);
     dev_free(h, h->halo_recv);
+    p2p_teardown(h);
     if (h->h_counts) cudaFreeHost(h->h_counts);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     if (h->flags) cudaFree(h->flags);
@@ -1654,6 +1788,10 @@ int pisb_upload_owned(pisb_t *h, int64_t n_own, const double *pos, const double 
     if (cap > h->ncap_atoms) {
         h->ncap_atoms = cap;
         h->kcap = 0;
+        if (h->p2p_tried) {  // receive buffers are sized by the capacity: map them again at the next rebuild
+            p2p_teardown(h);
+            h->p2p_tried = false;
+        }
     }
     h->n = n;
     h->n_own = n;
@@ -1756,6 +1894,10 @@ int pisb_set_option(pisb_t *h, const char *name, double value) {
         h->kcap_user = value > 0 ? (int)value : 0;
         h->kcap = 0;
         h->list_valid = false;
+        return PISB_OK;
+    }
+    if (!std::strcmp(name, "halo_mode")) {
+        h->halo_mode = (int)value;
         return PISB_OK;
     }
     if (!std::strcmp(name, "force_variant")) {
