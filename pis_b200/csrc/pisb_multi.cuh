@@ -7,9 +7,10 @@
 // GLOBAL wrapped coordinates and the pair arithmetic uses the global box, so every pair term is
 // bit-identical to the single-GPU (and reference) value; with a FULL neighbour list each rank
 // computes complete forces for its owned atoms and no reverse (force) exchange exists.
-//   every step      : ghost positions, packed by k_halo_pack, exchanged with grouped ncclSend/ncclRecv
-//                     straight over NVLink, scattered into the cell-sorted slots by k_halo_unpack;
-//                     1-int max-allreduce of the skin trigger
+//   every step      : ghost positions, gathered and STORED straight into the peers' receive buffers over NVLink
+//                     (k_halo_push on CUDA-IPC mapped peer memory, sequence-number signals, k_halo_pull scatters
+//                     into the cell-sorted slots and max-reduces the skin-trigger flags); grouped
+//                     ncclSend/ncclRecv (k_halo_pack / k_halo_unpack) is the fallback when IPC mapping fails
 //   rebuild steps   : atom migration, ghost selection, then the ordinary bin/sort/build chain
 //   end of a batch  : one sum-allreduce of all per-step thermo records
 #pragma once

@@ -116,7 +116,8 @@ def run(args):
                                    f"skin=0.3sigma, NVE dt=0.25, T0={args.temperature}K",
                        "n_atoms": n_global, "rc": B.RC, "skin": B.SKIN, "dt": B.DT, "T0": args.temperature,
                        "l2_policy": "working set per GPU (state + neighbour list, GBs) >> 126 MB L2; no explicit flush",
-                       "parallelism": f"spatial decomposition {grid[0]}x{grid[1]}x{grid[2]} bricks, NCCL send/recv halo exchange, "
+                       "parallelism": f"spatial decomposition {grid[0]}x{grid[1]}x{grid[2]} bricks, per-step halo = fused pack + NVLink stores into "
+                                      f"CUDA-IPC peer memory (NCCL for migration / rebuild traffic), "
                                       f"{n_global // world} atoms per GPU"},
             "clocks": clk.summary(),
             "e2e": {"value": n_global * e2e_steps / e2e_s, "unit": B.UNIT, "h2d_bytes_per_step": h2d_total // max(args.steps + e2e_steps + args.warmup, 1),
