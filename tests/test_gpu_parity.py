@@ -334,9 +334,11 @@ def test_gpu_matches_committed_golden_vectors():
     assert np.abs(atoms.positions - np.array(g["positions_end"])).max() < 1e-10
 
 
-def test_multi_gpu_equals_single_gpu():
+@pytest.mark.parametrize("halo_mode", [2, 1])
+def test_multi_gpu_equals_single_gpu(halo_mode):
     """2-rank spatially decomposed run == 1-GPU run (neighbour sets exact per global id, forces 1e-10,
-    traces 1e-9).  Needs 2 visible GPUs; the torchrun launch mirrors the driver's."""
+    traces 1e-9), with the peer-memory halo (2) and with the NCCL fallback (1).  Needs 2 visible GPUs; the
+    torchrun launch mirrors the driver's."""
     import json
     import os
     import subprocess
@@ -349,11 +351,11 @@ def test_multi_gpu_equals_single_gpu():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", "29577", os.path.join(root, "tools", "multi_check.py"), "12", "40", "60"]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root, env=dict(os.environ, PISB_HALO_MODE=str(halo_mode)))
     lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
     assert r.returncode == 0 and lines, r.stdout[-2000:] + r.stderr[-2000:]
     out = json.loads(lines[-1])
-    assert out["ok"], out
+    assert out["ok"] and out["halo_mode"] == halo_mode, out
 
 
 def test_config2_256k_atoms_parity():

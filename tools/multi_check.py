@@ -41,6 +41,8 @@ def main():
     atoms = Atoms(np.ones(len(gid), dtype=np.int32), [ARGON["mass"]], pos, box, velocities=vel)
     mgr = DistributedLJ(skin=skin, local_device=local, rank=rank, world=world, grid=grid)
     mgr.insert((1, 1), LennardJones(ARGON["epsilon"], ARGON["sigma"], rc, True))
+    halo_mode = int(os.environ.get("PISB_HALO_MODE", "0"))  # 0 auto (peer memory), 1 NCCL send/recv, 2 peer memory or fail
+    mgr.set_option("halo_mode", halo_mode)
     mgr.attach_owned(atoms, gid)
     pe0 = mgr.compute()
     g0, _, _, f0 = (a_.copy() for a_ in mgr.download_owned())
@@ -75,7 +77,7 @@ def main():
         mag = np.linalg.norm(ref.forces, axis=1)
         den = np.maximum(mag, 1e-3 * np.sqrt((mag ** 2).mean()))
         out = {
-            "world": world, "grid": grid, "n_global": n_global, "steps": steps,
+            "world": world, "grid": grid, "n_global": n_global, "steps": steps, "halo_mode": halo_mode,
             "neighbour_rows_mismatching": mism,
             "force0_max_abs": float(np.abs(F0 - f0_ref).max()),
             "force_rel": float((np.linalg.norm(F1 - ref.forces, axis=1) / den).max()),
