@@ -6,9 +6,18 @@
 //   v*, f*, g* : SoA doubles             streamed, never gathered (f = force at current x,
 //                                        g = force at previous x, swapped by the host every step)
 //   xb* : SoA doubles                    positions at the last list build (skin trigger)
-//   nbr : int32 [K_cap][n_pad]           TRANSPOSED full Verlet list: row k holds the k-th neighbour
-//                                        of every atom, so a warp reads 128 contiguous bytes
-//   cell_start : int32 [n_cells+1]       CSR of the cell-sorted order (x fastest, like cell_index)
+//   xf  : float4                          FP32 shadow of the wrapped position (+ type / ghost bits) for the pre-filter
+//   nbr : int32 [K_cap/4][n_pad][4]      FULL Verlet list, transposed in K-tiles of 4 (see nbr_at): the neighbours
+//                                        k..k+3 of atom i are one aligned int4, a warp reads 512 contiguous bytes
+//   cell_start : int32 [n_cells+2]       CSR of the cell-sorted order (x fastest, like cell_index)
+//
+// Kernel variants (pisb_set_option "force_variant" / "build_variant"; all give bit-identical results):
+//   k_force (v1)      plain all-FP64 loop, round(); also the only path for triclinic / non-periodic boxes
+//   k_force_v2        FP32 pre-filter + shared-memory compaction queue + exact FP64 pair terms
+//   k_force_v3        DEFAULT: all-FP64, int4 index tiles prefetched, 4 x 256-bit gathers in flight, magic rint,
+//                     interior-warp shortcut, 64-register launch bound
+//   k_force_v4        v3 with the block's cell tile staged in shared memory by TMA bulk copies (prototype)
+//   k_build_list (v1) all-FP64 27-cell scan;  k_build_list_v2  DEFAULT: FP32 pre-filter over contiguous x-rows
 #pragma once
 #include "pisb_device.cuh"
 

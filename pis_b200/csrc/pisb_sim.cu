@@ -103,8 +103,6 @@ struct pisb_handle {
     int *h_flags = nullptr;          // pinned
     pisb_thermo *h_thermo = nullptr; // pinned
     size_t h_thermo_cap = 0;
-    double *h_stage = nullptr;       // pinned staging for pageable host buffers
-    size_t h_stage_cap = 0;
     int64_t device_bytes = 0;
 
     // multi-GPU (spatial decomposition; see pisb_multi.cuh)
@@ -1471,7 +1469,6 @@ int pisb_destroy(pisb_t *h) {
     if (h->ticket) cudaFree(h->ticket);
     if (h->h_flags) cudaFreeHost(h->h_flags);
     if (h->h_thermo) cudaFreeHost(h->h_thermo);
-    if (h->h_stage) cudaFreeHost(h->h_stage);
     for (auto &e : h->ev_pool) {
         cudaEventDestroy(e.a);
         cudaEventDestroy(e.b);
