@@ -319,11 +319,17 @@ __global__ void __launch_bounds__(TPB) k_store_owned(int n, const double4 *__res
                                                      const double *fy, const double *fz, const int *__restrict__ id,
                                                      int *__restrict__ counter, double *pos, double *vel, double *frc,
                                                      int *gid) {
-    int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n) return;
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool own = s < n && !is_ghost(xt[s].w);
+    // warp-aggregated slot allocation (ballot/popc): one atomic per warp instead of one per atom
+    const unsigned m = __ballot_sync(0xffffffffu, own);
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0 && m) base = atomicAdd(counter, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (!own) return;
+    const size_t o = (size_t)(base + __popc(m & ((1u << lane) - 1u)));
     const double4 x = xt[s];
-    if (is_ghost(x.w)) return;
-    const size_t o = (size_t)atomicAdd(counter, 1);
     if (pos) {
         pos[3 * o] = x.x;
         pos[3 * o + 1] = x.y;
