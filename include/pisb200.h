@@ -145,6 +145,35 @@ PISB_API int pisb_nhc_init(pisb_nhc *out, double start_temperature, double end_t
 PISB_API int pisb_step_nvt_nhc(pisb_t *h, double dt, int64_t nsteps, pisb_nhc *chain, int64_t first_step,
                                int64_t total_steps, pisb_thermo *out, double *nhc_energy);
 
+/* MTK barostat state == MTKBarostat (src/ensemble/npt.rs:11-22); 3x3 matrices column-major like nalgebra. */
+typedef struct {
+    double target_pressure[9];
+    double momentum[9];
+    double w;
+} pisb_mtk;
+
+/* Replaces: MTKBarostat::new via new_from_args (npt.rs:24-43,67-88): momentum = 0, w = 3 N kB T tau^2 with
+ *   T = the thermostat's start temperature.  `fix ... npt ... iso p p tau` gives target_pressure = p * identity
+ *   (src/readers/input_file/commands.rs:429-447). */
+PISB_API int pisb_mtk_init(pisb_mtk *out, const double *target_pressure9, double tau, int64_t n_atoms,
+                           double target_temperature);
+
+/* Replaces: PotentialManager::verlet_step_npt_mtk (src/potentials/potential.rs:112-135) followed by
+ *   calculate_target_temperature(i, total_steps) (src/simulation.rs:58-62), nsteps times: barostat half kick from
+ *   Atoms::pressure_tensor (properties.rs:45-59), v = exp(-dt/2 eta_dot) v, Atoms::scale_box with exp(dt eta_dot)
+ *   (transformations.rs:6-15), verlet_step_nvt_nhc, v scaling and barostat half kick again.  The box held by the
+ *   handle CHANGES (and in general becomes triclinic: the pressure tensor has off-diagonal terms); read it back
+ *   with pisb_get_box.  out[s].ke / virial_ref are taken AFTER the final velocity scaling, as Simulation::output sees them.
+ *   ext_energy[s] (may be NULL) = nhc KE + nhc PE + mtk.kinetic_energy() + mtk.potential_energy(h), the extended
+ *   system's share of the Hamiltonian (simulation.rs:105-113); h9_trace (may be NULL) receives the box after every
+ *   step (9 doubles per step).  One device->host read of 19 reduced sums per step.  Single-GPU only. */
+PISB_API int pisb_step_npt_mtk(pisb_t *h, double dt, int64_t nsteps, pisb_mtk *baro, pisb_nhc *chain,
+                               int64_t first_step, int64_t total_steps, pisb_thermo *out, double *ext_energy,
+                               double *h9_trace);
+
+/* The box currently held by the handle (either pointer may be NULL): atoms.sim_box.{h, h_inv} after NPT steps. */
+PISB_API int pisb_get_box(pisb_t *h, double *h9, double *hinv9);
+
 /* Copy state back in ORIGINAL atom order (any pointer may be NULL).  Replaces reading
  * atoms.positions / velocities / forces on the host (e.g. DumpTraj::write_atoms_info,
  * src/writers/dump_traj.rs:52-66). */

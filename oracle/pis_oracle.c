@@ -705,6 +705,312 @@ ORC_API void orc_run_nvt(const orc_box *b, const orc_table *t, int64_t n, double
     }
 }
 
+/* ---- NPT: MTK barostat (src/ensemble/npt.rs), scale_box (src/atoms/transformations.rs:6-15),
+ * pressure_tensor (src/atoms/properties.rs:45-59), verlet_step_npt_mtk (src/potentials/potential.rs:112-135).
+ *
+ * Third-party arithmetic restated here (source not under /root/reference): nalgebra 0.34.1 `Matrix3::exp`
+ * (linalg/exp.rs), which follows Al-Mohy & Higham, "A New Scaling and Squaring Algorithm for the Matrix
+ * Exponential" (SIAM J. Matrix Anal. Appl. 31, 2009) in the arrangement of scipy.linalg.expm: Pade order 3/5/7/9
+ * chosen from d4 = |A^4|_1^(1/4), d6 = |A^6|_1^(1/6), d8, d10 against the theta_m thresholds and ell(A, m) == 0,
+ * else order 13 with 2^s scaling and squaring; (V - U) X = (V + U) solved by LU with partial pivoting.
+ * The barostat arguments here are O(1e-6 .. 1e-2), i.e. always the order-3 branch.  PARITY UNPINNED like the rest. */
+typedef struct {
+    double target_pressure[9]; /* column-major like nalgebra */
+    double momentum[9];
+    double w;
+} orc_mtk;
+
+/* C = A * B for column-major 3x3: per output column a gemv in column-axpy order (nalgebra static gemm) */
+static void matmul3(const double *a, const double *b, double *c) {
+    double t[9];
+    for (int j = 0; j < 3; ++j) matvec3(a, &b[3 * j], &t[3 * j]);
+    memcpy(c, t, sizeof t);
+}
+static double onenorm3(const double *a) {
+    double best = 0.0;
+    for (int j = 0; j < 3; ++j) {
+        double s = (fabs(a[3 * j]) + fabs(a[3 * j + 1])) + fabs(a[3 * j + 2]);
+        if (s > best) best = s;
+    }
+    return best;
+}
+/* ell(A, m) of Al-Mohy & Higham (2009), eq. (3.11)-(3.12), with the exact 1-norm of |A|^(2m+1) */
+static int expm_ell(const double *a, int m) {
+    /* C(2p, p) * (2p + 1)! for p = 2m + 1 */
+    static const double abs_c_recip[14] = {0, 0, 0, 4487938430976000.0, 0, 1.8236839872145106e+28, 0, 1.275506339396217e+42, 0,
+                                           7.209685231212166e+56, 0, 0, 0, 2.4719128253168207e+88};
+    double aa[9], pw[9];
+    for (int k = 0; k < 9; ++k) aa[k] = fabs(a[k]);
+    memcpy(pw, aa, sizeof pw);
+    for (int k = 1; k < 2 * m + 1; ++k) matmul3(pw, aa, pw);
+    double a1 = onenorm3(a);
+    if (a1 == 0.0) return 0;
+    double alpha = onenorm3(pw) / (a1 * abs_c_recip[m]);
+    if (alpha == 0.0) return 0;
+    double v = ceil(log2(alpha / ldexp(1.0, -53)) / (2.0 * m));
+    return v > 0.0 ? (int)v : 0;
+}
+/* X = Q^-1 P, LU with partial (row) pivoting, column by column */
+static void solve_lu3(const double *q_in, const double *p, double *x) {
+    double lu[9];
+    int perm[3] = {0, 1, 2};
+    memcpy(lu, q_in, sizeof lu);
+#define LU(r, c) lu[(c) * 3 + (r)]
+    for (int k = 0; k < 3; ++k) {
+        int piv = k;
+        for (int r = k + 1; r < 3; ++r)
+            if (fabs(LU(r, k)) > fabs(LU(piv, k))) piv = r;
+        if (piv != k) {
+            for (int c = 0; c < 3; ++c) {
+                double t = LU(k, c);
+                LU(k, c) = LU(piv, c);
+                LU(piv, c) = t;
+            }
+            int t = perm[k];
+            perm[k] = perm[piv];
+            perm[piv] = t;
+        }
+        for (int r = k + 1; r < 3; ++r) {
+            LU(r, k) = LU(r, k) / LU(k, k);
+            for (int c = k + 1; c < 3; ++c) LU(r, c) -= LU(r, k) * LU(k, c);
+        }
+    }
+    for (int j = 0; j < 3; ++j) {
+        double y[3];
+        for (int r = 0; r < 3; ++r) y[r] = p[3 * j + perm[r]];
+        for (int r = 1; r < 3; ++r)
+            for (int c = 0; c < r; ++c) y[r] -= LU(r, c) * y[c];
+        for (int r = 2; r >= 0; --r) {
+            for (int c = r + 1; c < 3; ++c) y[r] -= LU(r, c) * y[c];
+            y[r] = y[r] / LU(r, r);
+        }
+        for (int r = 0; r < 3; ++r) x[3 * j + r] = y[r];
+    }
+#undef LU
+}
+/* U = A * (sum_k b[2k+1] A^(2k)), V = sum_k b[2k] A^(2k) for the Pade order m in {3,5,7,9} */
+static void expm_pade_uv(const double *a, int m, const double *b, double *u, double *v) {
+    double a2[9], pw[9], eye[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, su[9], sv[9];
+    matmul3(a, a, a2);
+    for (int k = 0; k < 9; ++k) {
+        su[k] = eye[k] * b[1];
+        sv[k] = eye[k] * b[0];
+    }
+    memcpy(pw, eye, sizeof pw);
+    for (int k = 1; 2 * k <= m; ++k) {
+        matmul3(pw, a2, pw);
+        for (int e = 0; e < 9; ++e) {
+            su[e] = pw[e] * b[2 * k + 1] + su[e];
+            sv[e] = pw[e] * b[2 * k] + sv[e];
+        }
+    }
+    matmul3(a, su, u);
+    memcpy(v, sv, sizeof sv);
+}
+ORC_API void orc_mat3_exp(const double *a, double *out) {
+    static const double b3[] = {120., 60., 12., 1.};
+    static const double b5[] = {30240., 15120., 3360., 420., 30., 1.};
+    static const double b7[] = {17297280., 8648640., 1995840., 277200., 25200., 1512., 56., 1.};
+    static const double b9[] = {17643225600., 8821612800., 2075673600., 302702400., 30270240., 2162160., 110880., 3960., 90., 1.};
+    static const double b13[] = {64764752532480000., 32382376266240000., 7771770303897600., 1187353796428800.,
+                                 129060195264000.,   10559470521600.,    670442572800.,     33522128640.,
+                                 1323241920.,        40840800.,          960960.,           16380., 182., 1.};
+    double a2[9], a4[9], a6[9], a8[9], a10[9], u[9], v[9], p[9], q[9];
+    matmul3(a, a, a2);
+    matmul3(a2, a2, a4);
+    matmul3(a4, a2, a6);
+    const double d4 = pow(onenorm3(a4), 0.25), d6 = pow(onenorm3(a6), 1.0 / 6.0);
+    int order = 0;
+    const double eta1 = fmax(d4, d6);
+    if (eta1 < 1.495585217958292e-2 && expm_ell(a, 3) == 0) order = 3;
+    else if (eta1 < 2.539398330063230e-1 && expm_ell(a, 5) == 0) order = 5;
+    else {
+        matmul3(a4, a4, a8);
+        const double d8 = pow(onenorm3(a8), 0.125);
+        const double eta3 = fmax(d6, d8);
+        if (eta3 < 9.504178996162932e-1 && expm_ell(a, 7) == 0) order = 7;
+        else if (eta3 < 2.097847961257068 && expm_ell(a, 9) == 0) order = 9;
+        else {
+            matmul3(a4, a6, a10);
+            const double d10 = pow(onenorm3(a10), 0.1);
+            const double eta4 = fmax(d8, d10), eta5 = fmin(eta3, eta4);
+            const double theta13 = 4.25;
+            int s = 0;
+            if (eta5 > 0.0) {
+                double v2 = ceil(log2(eta5 / theta13));
+                if (v2 > 0.0) s = (int)v2;
+            }
+            double as[9];
+            for (int k = 0; k < 9; ++k) as[k] = ldexp(a[k], -s);
+            s += expm_ell(as, 13);
+            for (int k = 0; k < 9; ++k) as[k] = ldexp(a[k], -s);
+            double b2[9], b4[9], b6[9], eye[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, t1[9], t2[9];
+            matmul3(as, as, b2);
+            matmul3(b2, b2, b4);
+            matmul3(b4, b2, b6);
+            for (int k = 0; k < 9; ++k) t1[k] = b13[13] * b6[k] + b13[11] * b4[k] + b13[9] * b2[k];
+            matmul3(b6, t1, t2);
+            for (int k = 0; k < 9; ++k) t2[k] = t2[k] + b13[7] * b6[k] + b13[5] * b4[k] + b13[3] * b2[k] + b13[1] * eye[k];
+            matmul3(as, t2, u);
+            for (int k = 0; k < 9; ++k) t1[k] = b13[12] * b6[k] + b13[10] * b4[k] + b13[8] * b2[k];
+            matmul3(b6, t1, t2);
+            for (int k = 0; k < 9; ++k) v[k] = t2[k] + b13[6] * b6[k] + b13[4] * b4[k] + b13[2] * b2[k] + b13[0] * eye[k];
+            for (int k = 0; k < 9; ++k) {
+                p[k] = u[k] + v[k];
+                q[k] = v[k] - u[k];
+            }
+            solve_lu3(q, p, out);
+            for (int k = 0; k < s; ++k) matmul3(out, out, out);
+            return;
+        }
+    }
+    expm_pade_uv(a, order, order == 3 ? b3 : order == 5 ? b5 : order == 7 ? b7 : b9, u, v);
+    for (int k = 0; k < 9; ++k) {
+        p[k] = u[k] + v[k];
+        q[k] = v[k] - u[k];
+    }
+    solve_lu3(q, p, out);
+}
+
+/* math::symmetrize.  ref: src/math.rs:41-43 */
+static void symmetrize3(const double *a, double *out) {
+    double t[9];
+    for (int c = 0; c < 3; ++c)
+        for (int r = 0; r < 3; ++r) t[c * 3 + r] = (a[c * 3 + r] + a[r * 3 + c]) * 0.5;
+    memcpy(out, t, sizeof t);
+}
+
+/* A(3xN) * B(3xN)^T, nalgebra's generic gemm: per output column c a gemv over atoms, out[r,c] = sum_k A[r,k] B[c,k]
+ * accumulated sequentially in k.  ref: kinetic_tensor / virial_tensor, src/atoms/properties.rs:45-51 */
+static void outer_sum3(int64_t n, const double *a, const double *b, double *out) {
+    for (int c = 0; c < 3; ++c)
+        for (int r = 0; r < 3; ++r) {
+            double acc = 0.0;
+            for (int64_t k = 0; k < n; ++k) {
+                double p = a[3 * k + r] * b[3 * k + c];
+                acc = (k == 0) ? p : p + acc;
+            }
+            out[c * 3 + r] = acc;
+        }
+}
+
+/* Atoms::pressure_tensor (the kinetic tensor carries no mass, as in the reference).  ref: properties.rs:53-59 */
+ORC_API void orc_pressure_tensor(const orc_box *b, int64_t n, const double *pos, const double *vel, const double *forces,
+                                 double *out) {
+    double kt[9], vt[9];
+    outer_sum3(n, vel, vel, kt);
+    outer_sum3(n, pos, forces, vt);
+    double volume = orc_box_volume(b);
+    for (int k = 0; k < 9; ++k) out[k] = (kt[k] + vt[k]) / volume;
+}
+
+/* MTKBarostat::new via new_from_args (target temperature = the thermostat's start temperature).  ref: npt.rs:24-43,67-88 */
+ORC_API void orc_mtk_new(orc_mtk *m, const double *target_pressure9, double tau, int64_t n_atoms, double target_temp) {
+    memcpy(m->target_pressure, target_pressure9, sizeof m->target_pressure);
+    memset(m->momentum, 0, sizeof m->momentum);
+    m->w = ((double)(3 * n_atoms)) * ORC_KB * target_temp * (tau * tau);
+}
+
+/* ref: npt.rs:45-50 */
+ORC_API void orc_mtk_delta_momentum(const orc_mtk *m, const orc_box *b, int64_t n, const double *pos, const double *vel,
+                                    const double *forces, double dt, double *out) {
+    double p[9];
+    orc_pressure_tensor(b, n, pos, vel, forces, p);
+    double f = orc_box_volume(b) * 0.5 * dt;
+    for (int k = 0; k < 9; ++k) p[k] = (p[k] - m->target_pressure[k]) * f;
+    symmetrize3(p, out);
+}
+
+/* ref: npt.rs:52-58 */
+ORC_API void orc_mtk_scale(const orc_mtk *m, double dt, int velocity_scaling, double *out) {
+    double e[9];
+    for (int k = 0; k < 9; ++k) e[k] = m->momentum[k] / m->w;
+    symmetrize3(e, e);
+    double factor = velocity_scaling ? -0.5 : 1.0;
+    for (int k = 0; k < 9; ++k) e[k] = e[k] * factor * dt;
+    orc_mat3_exp(e, out);
+}
+
+/* ref: npt.rs:60-66.  tr(M M^T) and tr(P^T h), each product element in gemv order */
+ORC_API double orc_mtk_kinetic_energy(const orc_mtk *m) {
+    double mt[9], pr[9];
+    for (int c = 0; c < 3; ++c)
+        for (int r = 0; r < 3; ++r) mt[c * 3 + r] = m->momentum[r * 3 + c];
+    matmul3(m->momentum, mt, pr);
+    return ((pr[0] + pr[4]) + pr[8]) / (2.0 * m->w);
+}
+ORC_API double orc_mtk_potential_energy(const orc_mtk *m, const double *h9) {
+    double pt[9], pr[9];
+    for (int c = 0; c < 3; ++c)
+        for (int r = 0; r < 3; ++r) pt[c * 3 + r] = m->target_pressure[r * 3 + c];
+    matmul3(pt, h9, pr);
+    return (pr[0] + pr[4]) + pr[8];
+}
+
+/* Atoms::scale_box.  ref: src/atoms/transformations.rs:6-15.  Returns 1 if the new box is singular. */
+ORC_API int orc_scale_box(orc_box *b, const double *scale9, int64_t n, double *pos) {
+    double hn[9];
+    matmul3(scale9, b->h, hn);
+    orc_box nb;
+    if (orc_box_new(hn, b->pbc, &nb)) return 1;
+    for (int64_t i = 0; i < n; ++i) {
+        double s[3];
+        matvec3(b->hinv, &pos[3 * i], s);
+        matvec3(nb.h, s, &pos[3 * i]);
+    }
+    *b = nb;
+    return 0;
+}
+
+/* PotentialManager::verlet_step_npt_mtk.  ref: src/potentials/potential.rs:112-135 */
+ORC_API double orc_verlet_step_npt_mtk(orc_box *b, const orc_table *t, int64_t n, double *pos, double *vel, double *forces,
+                                       const int32_t *types, const double *masses, double dt, orc_mtk *mtk, orc_nhc *nhc,
+                                       int mode, int n_threads) {
+    double dm[9], scale[9], scale_h[9], tv[3];
+    orc_mtk_delta_momentum(mtk, b, n, pos, vel, forces, dt, dm);
+    for (int k = 0; k < 9; ++k) mtk->momentum[k] += dm[k];
+    orc_mtk_scale(mtk, dt, 1, scale);
+    for (int64_t i = 0; i < n; ++i) {
+        matvec3(scale, &vel[3 * i], tv);
+        memcpy(&vel[3 * i], tv, sizeof tv);
+    }
+    orc_mtk_scale(mtk, dt, 0, scale_h);
+    orc_scale_box(b, scale_h, n, pos);
+    double potential_energy = orc_verlet_step_nvt_nhc(b, t, n, pos, vel, forces, types, masses, dt, nhc, mode, n_threads);
+    for (int64_t i = 0; i < n; ++i) {
+        matvec3(scale, &vel[3 * i], tv);
+        memcpy(&vel[3 * i], tv, sizeof tv);
+    }
+    orc_mtk_delta_momentum(mtk, b, n, pos, vel, forces, dt, dm);
+    for (int k = 0; k < 9; ++k) mtk->momentum[k] += dm[k];
+    return potential_energy;
+}
+
+/* Simulation::run, NPT arm (src/simulation.rs:8-115): rows as orc_run_nve with
+ * H = PE + KE + nhc KE + nhc PE + mtk KE + mtk PE; h_trace (may be NULL) receives the box after every step (9 per row). */
+ORC_API void orc_run_npt(orc_box *b, const orc_table *t, int64_t n, double *pos, double *vel, double *forces,
+                         const int32_t *types, const double *masses, double dt, int64_t steps, orc_mtk *mtk, orc_nhc *nhc,
+                         int mode, int n_threads, double *thermo, double *h_trace) {
+    double pe0 = mode == 0 ? orc_compute_potential(b, t, n, pos, types, forces)
+                           : orc_compute_potential_omp(b, t, n, pos, types, forces, n_threads);
+    thermo[0] = pe0;
+    thermo[1] = thermo[2] = thermo[3] = thermo[4] = 0.0;
+    if (h_trace) memcpy(h_trace, b->h, sizeof(double) * 9);
+    for (int64_t s = 0; s < steps; ++s) {
+        double pe = orc_verlet_step_npt_mtk(b, t, n, pos, vel, forces, types, masses, dt, mtk, nhc, mode, n_threads);
+        orc_nhc_calculate_target_temperature(nhc, s, steps); /* simulation.rs:60 */
+        double ke = orc_kinetic_energy(n, vel, types, masses);
+        double *row = &thermo[(s + 1) * 5];
+        row[0] = pe;
+        row[1] = ke;
+        row[2] = pe + ke + orc_nhc_kinetic_energy(nhc) + orc_nhc_potential_energy(nhc, n) + orc_mtk_kinetic_energy(mtk) +
+                 orc_mtk_potential_energy(mtk, b->h);
+        row[3] = orc_temperature(n, ke);
+        row[4] = orc_pressure(b, n, pos, forces, ke);
+        if (h_trace) memcpy(&h_trace[(s + 1) * 9], b->h, sizeof(double) * 9);
+    }
+}
+
 /* Largest double T with sqrt(T) <= rc (correctly-rounded sqrt is monotone), so that
  * `sqrt(r2) > rc`  <=>  `r2 > T` exactly.  Test helper for the sqrt-free device predicate. */
 ORC_API double orc_rcut_threshold(double rc) {

@@ -27,6 +27,10 @@ class Nhc(C.Structure):
                 ("eta", C.c_double * 3), ("g", C.c_double * 3), ("q", C.c_double * 3)]
 
 
+class Mtk(C.Structure):
+    _fields_ = [("target_pressure", C.c_double * 9), ("momentum", C.c_double * 9), ("w", C.c_double)]
+
+
 class Table(C.Structure):
     _fields_ = [("n_types", C.c_int), ("eps", C.c_void_p), ("sigma", C.c_void_p), ("rcut", C.c_void_p),
                 ("present", C.c_void_p), ("shift", C.c_int)]
@@ -76,6 +80,17 @@ def load():
             "orc_nhc_kinetic_energy": (d, [C.POINTER(Nhc)]),
             "orc_verlet_step_nvt_nhc": (d, [bp, tp, i64, vp, vp, vp, vp, vp, d, C.POINTER(Nhc), C.c_int, C.c_int]),
             "orc_run_nvt": (None, [bp, tp, i64, vp, vp, vp, vp, vp, d, i64, C.POINTER(Nhc), C.c_int, C.c_int, vp]),
+            "orc_mat3_exp": (None, [vp, vp]),
+            "orc_pressure_tensor": (None, [bp, i64, vp, vp, vp, vp]),
+            "orc_mtk_new": (None, [C.POINTER(Mtk), vp, d, i64, d]),
+            "orc_mtk_scale": (None, [C.POINTER(Mtk), d, C.c_int, vp]),
+            "orc_mtk_kinetic_energy": (d, [C.POINTER(Mtk)]),
+            "orc_mtk_potential_energy": (d, [C.POINTER(Mtk), vp]),
+            "orc_scale_box": (C.c_int, [bp, vp, i64, vp]),
+            "orc_verlet_step_npt_mtk": (d, [bp, tp, i64, vp, vp, vp, vp, vp, d, C.POINTER(Mtk), C.POINTER(Nhc), C.c_int,
+                                            C.c_int]),
+            "orc_run_npt": (None, [bp, tp, i64, vp, vp, vp, vp, vp, d, i64, C.POINTER(Mtk), C.POINTER(Nhc), C.c_int,
+                                   C.c_int, vp, vp]),
             "orc_rcut_threshold": (d, [d]),
             "orc_max_threads": (C.c_int, []),
         }
@@ -245,6 +260,46 @@ class Oracle:
                              _p(types), _p(self.masses), float(dt), steps, C.byref(nhc), 0 if mode == "serial" else 1,
                              threads, _p(thermo))
         return thermo
+
+    def mat3_exp(self, a_colmajor):
+        """nalgebra Matrix3::exp restated (column-major 9-vector in, 9-vector out)."""
+        a = np.ascontiguousarray(a_colmajor, dtype=np.float64).reshape(9)
+        out = np.zeros(9)
+        self.lib.orc_mat3_exp(_p(a), _p(out))
+        return out
+
+    def pressure_tensor(self, pos, vel, forces):
+        out = np.zeros(9)
+        self.lib.orc_pressure_tensor(C.byref(self.box), pos.shape[0], _p(pos), _p(vel), _p(forces), _p(out))
+        return out
+
+    def box_volume(self):
+        return self.lib.orc_box_volume(C.byref(self.box))
+
+    def scale_box(self, scale, pos):
+        """Atoms::scale_box (transformations.rs:6-15): box and positions in place; scale is a 3x3 (row, col) array."""
+        sc = np.ascontiguousarray(np.asarray(scale, dtype=np.float64).T.reshape(9))
+        if self.lib.orc_scale_box(C.byref(self.box), _p(sc), pos.shape[0], _p(pos)) != 0:
+            raise ValueError("Box matrix should be invertible")
+
+    def mtk_new(self, target_pressure, tau, n_atoms, target_temperature):
+        """MTKBarostat::new_from_args (npt.rs:67-88): `iso p` gives target = p * identity."""
+        m = Mtk()
+        tp = np.ascontiguousarray(np.eye(3) * float(target_pressure) if np.isscalar(target_pressure) else target_pressure,
+                                  dtype=np.float64).reshape(9)
+        self.lib.orc_mtk_new(C.byref(m), _p(tp), float(tau), int(n_atoms), float(target_temperature))
+        return m
+
+    def run_npt(self, pos, vel, forces, types, dt, steps, mtk, nhc, mode="serial", threads=0):
+        """Simulation::run NPT arm; the box of this Oracle is updated in place.
+        Returns (thermo[(steps+1), 5], h_trace[(steps+1), 9])."""
+        types = np.ascontiguousarray(types, dtype=np.int32)
+        thermo = np.zeros((steps + 1, 5))
+        htr = np.zeros((steps + 1, 9))
+        self.lib.orc_run_npt(C.byref(self.box), C.byref(self.table), pos.shape[0], _p(pos), _p(vel), _p(forces),
+                             _p(types), _p(self.masses), float(dt), steps, C.byref(mtk), C.byref(nhc),
+                             0 if mode == "serial" else 1, threads, _p(thermo), _p(htr))
+        return thermo, htr
 
     def rcut_threshold(self, rc):
         return self.lib.orc_rcut_threshold(float(rc))

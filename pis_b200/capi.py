@@ -42,6 +42,11 @@ class Nhc(C.Structure):
                 ("eta", C.c_double * 3), ("g", C.c_double * 3), ("q", C.c_double * 3)]
 
 
+class Mtk(C.Structure):
+    """pisb_mtk == MTKBarostat (src/ensemble/npt.rs:11-22); matrices column-major."""
+    _fields_ = [("target_pressure", C.c_double * 9), ("momentum", C.c_double * 9), ("w", C.c_double)]
+
+
 class PisbError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"pisb error {code}: {msg}")
@@ -77,6 +82,10 @@ SIGNATURES = {
     "pisb_set_option": (C.c_int, [_vp, C.c_char_p, C.c_double]),
     "pisb_nhc_init": (C.c_int, [C.POINTER(Nhc), C.c_double, C.c_double, C.c_double]),
     "pisb_step_nvt_nhc": (C.c_int, [_vp, C.c_double, C.c_int64, C.POINTER(Nhc), C.c_int64, C.c_int64, _vp, _vp]),
+    "pisb_mtk_init": (C.c_int, [C.POINTER(Mtk), _vp, C.c_double, C.c_int64, C.c_double]),
+    "pisb_step_npt_mtk": (C.c_int, [_vp, C.c_double, C.c_int64, C.POINTER(Mtk), C.POINTER(Nhc), C.c_int64, C.c_int64, _vp,
+                                    _vp, _vp]),
+    "pisb_get_box": (C.c_int, [_vp, _vp, _vp]),
     "pisb_comm_unique_id": (C.c_int, [_vp, C.c_int]),
     "pisb_comm_init": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp]),
     "pisb_upload_owned": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp, _vp]),

@@ -258,6 +258,11 @@ void LJCudaManager::step_nvt_nhc(double dt, int64_t nsteps, pisb_nhc &chain, int
     check(pisb_step_nvt_nhc(h_, dt, nsteps, &chain, first_step, total_steps, out, nhc_energy));
 }
 
+void LJCudaManager::step_npt_mtk(double dt, int64_t nsteps, pisb_mtk &baro, pisb_nhc &chain, int64_t first_step, int64_t total_steps,
+                                 pisb_thermo *out, double *ext_energy, double *h9_trace) {
+    check(pisb_step_npt_mtk(h_, dt, nsteps, &baro, &chain, first_step, total_steps, out, ext_energy, h9_trace));
+}
+
 void LJCudaManager::download(Atoms &atoms, bool pos, bool vel, bool frc) {
     check(pisb_download(h_, pos ? atoms.positions.data() : nullptr, vel ? atoms.velocities.data() : nullptr,
                         frc ? atoms.forces.data() : nullptr));
@@ -541,17 +546,22 @@ void DumpTraj::write_step(const Atoms &atoms, size_t step) {
         throw PisError("DumpWriteError", "Failed to write trajectory file '" + path_ + "': " + std::strerror(errno));
 }
 
-// ---- Simulation::run, NVE arm (src/simulation.rs:8-88) ---------------------------------------------------
+// ---- Simulation::run (src/simulation.rs:8-115): NVE, NVT and NPT arms ---------------------------------------
 void Simulation::run(LJCudaManager &mgr, SimulationContext &ctx, FILE *out) {
-    if (ctx.mtk_barostat_args)
-        throw PisError("UnsupportedEnsemble",
-                       "fix npt selects the NPT ensemble (simulation.rs:125-132); the B200 path implements the NVE hot path and the "
-                       "NVT Nose-Hoover wrapper only -- remove the `iso` keyword or the fix line");
-    const bool nvt = ctx.nh_chain_args.has_value();  // Ensemble::from_ctx (simulation.rs:125-132)
+    // Ensemble::from_ctx (simulation.rs:125-132): (thermostat, barostat) => NPT, (thermostat, -) => NVT, else NVE
+    const bool nvt = ctx.nh_chain_args.has_value();
+    const bool npt = nvt && ctx.mtk_barostat_args.has_value();
     pisb_nhc chain{};
     if (nvt) pisb_nhc_init(&chain, ctx.nh_chain_args->start_temperature, ctx.nh_chain_args->end_temperature, ctx.nh_chain_args->tau);
     if (!ctx.atoms) throw PisError("NoAtomsDefined", "No atoms defined in input file");
     Atoms &atoms = *ctx.atoms;
+    pisb_mtk baro{};
+    if (npt) {
+        // MTKBarostat::new_from_args (npt.rs:67-88): target = start_pressure * identity (commands.rs:439), T = thermostat start
+        const double p = ctx.mtk_barostat_args->start_pressure;
+        const double target[9] = {p, 0, 0, 0, p, 0, 0, 0, p};
+        pisb_mtk_init(&baro, target, ctx.mtk_barostat_args->tau, (int64_t)atoms.n_atoms, ctx.nh_chain_args->start_temperature);
+    }
     const double dt = ctx.timestep;
     const size_t steps = ctx.steps, dump_step = ctx.dump_args.dump_step;
     DumpTraj dumper(ctx.dump_args);
@@ -559,7 +569,7 @@ void Simulation::run(LJCudaManager &mgr, SimulationContext &ctx, FILE *out) {
     const double first_potential = mgr.compute_potential(atoms);  // uploads; forces stay resident too
     std::fprintf(out, "0 %s\n", rust_display_f64(first_potential).c_str());
     std::vector<pisb_thermo> th;
-    std::vector<double> nhc_e;
+    std::vector<double> ext_e, h_trace;
     size_t i = 0;
     while (i < steps) {
         // run up to the next dump step on the device; only thermo scalars come back per step
@@ -567,18 +577,29 @@ void Simulation::run(LJCudaManager &mgr, SimulationContext &ctx, FILE *out) {
         if (dump_step > 0) chunk = std::min(chunk, dump_step - (i % dump_step));
         chunk = std::min<size_t>(chunk, 1000);
         th.resize(chunk);
-        nhc_e.assign(chunk, 0.0);
-        if (nvt) mgr.step_nvt_nhc(dt, (int64_t)chunk, chain, (int64_t)i, (int64_t)steps, th.data(), nhc_e.data());
-        else mgr.step_nve(dt, (int64_t)chunk, th.data());
+        ext_e.assign(chunk, 0.0);
+        if (npt) {
+            h_trace.assign(9 * chunk, 0.0);
+            mgr.step_npt_mtk(dt, (int64_t)chunk, baro, chain, (int64_t)i, (int64_t)steps, th.data(), ext_e.data(), h_trace.data());
+        } else if (nvt) {
+            mgr.step_nvt_nhc(dt, (int64_t)chunk, chain, (int64_t)i, (int64_t)steps, th.data(), ext_e.data());
+        } else {
+            mgr.step_nve(dt, (int64_t)chunk, th.data());
+        }
         for (size_t k = 0; k < chunk; ++k) {
             const size_t step = i + k + 1;
+            if (npt) {  // scale_box changed atoms.sim_box (transformations.rs:8-13): pressure and dump bounds use the step's box
+                bool pbc[3] = {atoms.sim_box.pbc[0], atoms.sim_box.pbc[1], atoms.sim_box.pbc[2]};
+                atoms.sim_box = SimulationBox::make(&h_trace[9 * k], pbc);
+            }
             if (dump_step > 0 && step % dump_step == 0) {
                 mgr.download(atoms, true, false, false);
                 dumper.write_step(atoms, step);
             }
             const double ke = th[k].ke, pe = th[k].pe;
-            // compute_hamiltonian (simulation.rs:90-115): NVT adds the thermostat's kinetic + potential energy
-            std::fprintf(out, "%zu %.3f %.3f %.3f %.3f %.3f\n", step, pe, ke, pe + ke + nhc_e[k], atoms.temerature(ke),
+            // compute_hamiltonian (simulation.rs:90-115): NVT adds the thermostat's kinetic + potential energy, NPT also
+            // the barostat's
+            std::fprintf(out, "%zu %.3f %.3f %.3f %.3f %.3f\n", step, pe, ke, pe + ke + ext_e[k], atoms.temerature(ke),
                          atoms.pressure(ke, th[k].virial_ref));
         }
         i += chunk;

@@ -8,7 +8,7 @@
 //   Command / run_*    src/readers/input_file/commands.rs
 //   SimulationContext  src/readers/simulation_context.rs
 //   System             src/system.rs
-//   Simulation         src/simulation.rs   (NVE and NVT arms; NPT is out of scope and rejected)
+//   Simulation         src/simulation.rs   (NVE, NVT and NPT arms)
 //   DumpTraj           src/writers/dump_traj.rs
 #pragma once
 #include <cstdint>
@@ -85,6 +85,8 @@ class LJCudaManager {
     void step_nve(double dt, int64_t nsteps, pisb_thermo *out);
     void step_nvt_nhc(double dt, int64_t nsteps, pisb_nhc &chain, int64_t first_step, int64_t total_steps, pisb_thermo *out,
                       double *nhc_energy);  // verlet_step_nvt_nhc x nsteps (potential.rs:35-58)
+    void step_npt_mtk(double dt, int64_t nsteps, pisb_mtk &baro, pisb_nhc &chain, int64_t first_step, int64_t total_steps,
+                      pisb_thermo *out, double *ext_energy, double *h9_trace);  // verlet_step_npt_mtk x nsteps (potential.rs:112-135)
     void download(Atoms &atoms, bool pos, bool vel, bool frc);
     pisb_stats_t stats();
     std::map<std::pair<int, int>, LennardJones> table;
@@ -151,7 +153,7 @@ class DumpTraj {                   // dump_traj.rs:12-75
 enum class Ensemble { NVE, NVT, NPT };  // simulation.rs:118-133
 
 struct Simulation {
-    static void run(LJCudaManager &mgr, SimulationContext &ctx, FILE *thermo_out);  // simulation.rs:8-39 (NVE, NVT)
+    static void run(LJCudaManager &mgr, SimulationContext &ctx, FILE *thermo_out);  // simulation.rs:8-115 (NVE, NVT, NPT)
 };
 
 class System {                     // system.rs:35-183

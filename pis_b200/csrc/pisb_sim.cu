@@ -15,6 +15,7 @@
 #include "pisb200.h"
 #include "pisb_kernels.cuh"
 #include "pisb_multi.cuh"
+#include "pisb_npt.cuh"
 
 #include <dlfcn.h>
 #include <nccl.h>
@@ -97,6 +98,9 @@ struct pisb_handle {
     DevBuf<PairDev> table_d;
     DevBuf<NhcDev> nhc_d;
     DevBuf<double> nhc_energy_d;
+    DevBuf<double> npt_tensors_d;
+    double *h_npt = nullptr;         // pinned: 19 reduced tensor sums + thermostat energy
+    double skin_half2_override = -1.0;  // NPT: skin trigger threshold reduced by the accumulated box strain
     DevBuf<pisb_thermo> thermo_d;
     int *flags = nullptr;
     unsigned int *ticket = nullptr;
@@ -323,6 +327,7 @@ int setup_filter(pisb_t *h) {
         f.hi_list = f32_above(h->pairs[k].t_list * (1.0 + band_l));
     }
     TRY(dev_reserve(h, h->tablef_d, (size_t)nt * nt));
+    if (!v2_possible(h)) return PISB_OK;  // the FP32 pre-filter kernels are not selectable for this box
     CUDA_TRY(h, cudaMemcpyAsync(h->tablef_d.p, h->pairsf.data(), sizeof(PairF) * nt * nt, cudaMemcpyHostToDevice,
                                 h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -347,17 +352,29 @@ int setup_grid(pisb_t *h) {
     if (h->multi) div = 1;
     const int64_t cell_cap = std::max<int64_t>(4 * (int64_t)h->n + 1024, 27);
     double prod = 1.0;
-    for (int d = 0; d < 3 && div > 1; ++d) {
+    // Extent that bounds the cell count of dimension d: the reference's column norm (divide_into_cells), and for a
+    // tilted box also the perpendicular width 1 / |row d of h_inv| -- cells are slabs of the FRACTIONAL coordinate, so
+    // it is the perpendicular width that must cover the list cutoff (the reference's column norm alone can make the
+    // slabs thinner than rcut; a coarser grid is always still correct).
+    auto extent = [&](int d) {
         const double *c = &h->box.h[d * 3];
-        const double len = std::sqrt((c[0] * c[0] + c[1] * c[1]) + c[2] * c[2]);
+        double len = std::sqrt((c[0] * c[0] + c[1] * c[1]) + c[2] * c[2]);
+        if (!h->box.ortho) {
+            const double *hi = h->box.hinv;
+            const double rn = std::sqrt((hi[d] * hi[d] + hi[3 + d] * hi[3 + d]) + hi[6 + d] * hi[6 + d]);
+            if (rn > 0.0) len = std::min(len, 1.0 / rn);
+        }
+        return len;
+    };
+    for (int d = 0; d < 3 && div > 1; ++d) {
+        const double len = extent(d);
         const double nd = std::floor(len / (rc_list / div));
         if (nd < 2 * div + 1 || nd > 2048.0) div = 1;
         prod *= nd;
     }
     if (div > 1 && prod > (double)cell_cap) div = 1;  // dilute system: keep the cell count O(N)
     for (int d = 0; d < 3; ++d) {
-        const double *c = &h->box.h[d * 3];
-        const double len = std::sqrt((c[0] * c[0] + c[1] * c[1]) + c[2] * c[2]);
+        const double len = extent(d);
         double nd = std::floor(len / rc_list);
         if (!(nd >= 1.0)) nd = 1.0;
         if (div > 1) nd = std::floor(len / (rc_list / div));
@@ -585,7 +602,8 @@ int launch_vv(pisb_t *h, bool kick, bool drift, double dt, pisb_thermo *rec, con
     const double hs = 0.5 * h->skin;
     VVArgs a{h->n, h->xt.p, h->xf.p, h->v[0].p, h->v[1].p, h->v[2].p, h->f[0].p, h->f[1].p, h->f[2].p,
              h->g[0].p, h->g[1].p, h->g[2].p, h->xb[0].p, h->xb[1].p, h->xb[2].p, h->mass_d.p, h->box,
-             dt, dt * dt, hs * hs, h->skin > 0.0 ? 0 : 1, h->flags, h->partials.p, h->ticket, rec, vscale};
+             dt, dt * dt, h->skin_half2_override >= 0.0 ? h->skin_half2_override : hs * hs,
+             (h->skin > 0.0 && h->skin_half2_override != 0.0) ? 0 : 1, h->flags, h->partials.p, h->ticket, rec, vscale};
     const int nb = nblk(h->n, TPB);
     cudaStream_t st = h->stream;
     const bool o = h->box.ortho != 0;
@@ -862,6 +880,197 @@ int do_step_nvt(pisb_t *h, double dt, int64_t nsteps, pisb_nhc *chain, int64_t f
         done += m;
         h->n_steps += m;
     }
+    NhcDev fin{};
+    CUDA_TRY(h, cudaMemcpy(&fin, h->nhc_d.p, sizeof fin, cudaMemcpyDeviceToHost));
+    *chain = fin.c;
+    h->forces_current = true;
+    return PISB_OK;
+}
+
+// NPT batch: verlet_step_npt_mtk x nsteps (potential.rs:112-135).  The barostat (nine momenta) is advanced on the host from
+// the tensors the device reduces; one small device->host read per step (see pisb_npt.cuh).
+void box_from_matrices(BoxDev &b, const double *h9, const double *hinv9) {
+    bool ortho = true;
+    for (int k = 0; k < 9; ++k) {
+        b.h[k] = h9[k];
+        b.hinv[k] = hinv9[k];
+        if (k % 4 != 0 && (h9[k] != 0.0 || hinv9[k] != 0.0)) ortho = false;
+    }
+    b.ortho = ortho ? 1 : 0;
+}
+
+// MTKBarostat::delta_momentum (npt.rs:45-50) from the reduced tensors t[0..8] = V V^T, t[9..17] = X F^T
+void mtk_delta_momentum(const pisb_mtk &m, const double *t, double volume, double dt, double *out) {
+    double p[9];
+    const double f = volume * 0.5 * dt;
+    for (int k = 0; k < 9; ++k) p[k] = ((t[k] + t[9 + k]) / volume - m.target_pressure[k]) * f;
+    m3::symmetrize(p, out);
+}
+
+// MTKBarostat::scale (npt.rs:52-58)
+void mtk_scale(const pisb_mtk &m, double dt, bool velocity_scaling, double *out) {
+    double e[9];
+    for (int k = 0; k < 9; ++k) e[k] = m.momentum[k] / m.w;
+    m3::symmetrize(e, e);
+    const double factor = velocity_scaling ? -0.5 : 1.0;
+    for (int k = 0; k < 9; ++k) e[k] = e[k] * factor * dt;
+    m3::expm(e, out);
+}
+
+int launch_npt_post(pisb_t *h, const double *scale9, pisb_thermo *rec) {
+    LaunchScope ls(h, PISB_K_REDUCE);
+    NptPostArgs a{};
+    a.n = h->n;
+    a.xt = h->xt.p;
+    a.vx = h->v[0].p, a.vy = h->v[1].p, a.vz = h->v[2].p;
+    a.fx = h->f[0].p, a.fy = h->f[1].p, a.fz = h->f[2].p;
+    a.mass = h->mass_d.p;
+    a.apply_scale = scale9 ? 1 : 0;
+    if (scale9) std::memcpy(a.scale.m, scale9, sizeof a.scale.m);
+    a.partials = h->partials.p;
+    a.ticket = h->ticket;
+    a.tensors = h->npt_tensors_d.p;
+    a.thermo = rec;
+    k_npt_post<<<nblk(h->n, TPB), TPB, 0, h->stream>>>(a);
+    return check_launch(h, "k_npt_post");
+}
+
+int do_step_npt(pisb_t *h, double dt, int64_t nsteps, pisb_mtk *baro, pisb_nhc *chain, int64_t first_step,
+                int64_t total_steps, pisb_thermo *out, double *ext_energy, double *h9_trace) {
+    if (!h->have_atoms || !h->have_box) return fail(h, PISB_ERR_STATE, "set_box and upload must precede step_npt_mtk");
+    if (h->multi) return fail(h, PISB_ERR_STATE, "pisb_step_npt_mtk is a single-GPU entry point");
+    if (!baro || !(baro->w > 0.0)) return fail(h, PISB_ERR_INVALID, "barostat must come from pisb_mtk_init (w > 0)");
+    if (!chain || chain->chain_size != 3) return fail(h, PISB_ERR_INVALID, "chain must be a 3-link pisb_nhc (pisb_nhc_init)");
+    if (nsteps < 0 || total_steps <= 0) return fail(h, PISB_ERR_INVALID, "bad step counts");
+    if (nsteps == 0) return PISB_OK;
+    TRY(ensure_list(h));
+    TRY(check_bad_type(h));
+    TRY(dev_reserve(h, h->nhc_d, 1));
+    TRY(dev_reserve(h, h->nhc_energy_d, 1));
+    TRY(dev_reserve(h, h->npt_tensors_d, 19));
+    TRY(dev_reserve(h, h->partials, (size_t)19 * (nblk(h->n, TPB) + 1)));
+    TRY(reserve_thermo(h, 4));
+    if (!h->h_npt) CUDA_TRY(h, cudaHostAlloc((void **)&h->h_npt, sizeof(double) * 32, cudaHostAllocDefault));
+    NhcDev init{};
+    init.c = *chain;
+    init.scale = 1.0;
+    CUDA_TRY(h, cudaMemcpyAsync(h->nhc_d.p, &init, sizeof init, cudaMemcpyHostToDevice, h->stream));
+    pisb_thermo *rec = h->thermo_d.p, *ke0 = h->thermo_d.p + 1;
+    const double rc_list = h->max_rcut + h->skin;
+    double h_build[9], tensors[19];
+    // A list that predates this call was built in this very box: pisb_set_box invalidates the list on any change, and
+    // an NPT batch that ends with a strained list invalidates it too (below), so F = I here.
+    std::memcpy(h_build, h->box.h, sizeof h_build);
+    TRY(launch_npt_post(h, nullptr, nullptr));  // tensors of the state entering the batch
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_npt, h->npt_tensors_d.p, sizeof(double) * 19, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    std::memcpy(tensors, h->h_npt, sizeof tensors);
+    int rc = PISB_OK;
+    for (int64_t s = 0; s < nsteps && rc == PISB_OK; ++s) {
+        rc = [&]() -> int {
+            double dm[9], scale[9], scale_h[9], h_new[9], hinv_new[9];
+            double volume = std::fabs(m3::det(h->box.h));
+            mtk_delta_momentum(*baro, tensors, volume, dt, dm);
+            for (int k = 0; k < 9; ++k) baro->momentum[k] += dm[k];
+            mtk_scale(*baro, dt, true, scale);
+            mtk_scale(*baro, dt, false, scale_h);
+            m3::mul(scale_h, h->box.h, h_new);  // scale_box: h = scale * h; h_inv = try_inverse (transformations.rs:8-13)
+            if (!m3::inverse(h_new, hinv_new)) return fail(h, PISB_ERR_INVALID, "Box matrix should be invertible");
+            for (int k = 0; k < 9; ++k)
+                if (!std::isfinite(h_new[k]) || !std::isfinite(hinv_new[k])) return fail(h, PISB_ERR_INVALID, "the barostat drove the box to a non-finite matrix");
+            {
+                LaunchScope ls(h, PISB_K_INTEGRATE);
+                NptPreArgs a{};
+                a.n = h->n;
+                a.xt = h->xt.p, a.xf = h->xf.p;
+                a.vx = h->v[0].p, a.vy = h->v[1].p, a.vz = h->v[2].p;
+                a.xbx = h->xb[0].p, a.xby = h->xb[1].p, a.xbz = h->xb[2].p;
+                a.mass = h->mass_d.p;
+                std::memcpy(a.scale.m, scale, sizeof scale);
+                std::memcpy(a.hinv_old.m, h->box.hinv, sizeof scale);
+                std::memcpy(a.h_new.m, h_new, sizeof scale);
+                a.partials = h->partials.p, a.ticket = h->ticket, a.ke_out = ke0;
+                k_npt_pre<<<nblk(h->n, TPB), TPB, 0, h->stream>>>(a);
+                TRY(check_launch(h, "k_npt_pre"));
+            }
+            // new box: grid (cells are slabs of the fractional coordinate, so the grid only changes when a cell count does)
+            {
+                const Grid old = h->grid;
+                const bool lv = h->list_valid;
+                box_from_matrices(h->box, h_new, hinv_new);
+                TRY(setup_grid(h));
+                const bool same = old.n[0] == h->grid.n[0] && old.n[1] == h->grid.n[1] && old.n[2] == h->grid.n[2];
+                h->list_valid = lv && same;
+                if (!h->list_valid) {
+                    TRY(ensure_list(h));
+                    std::memcpy(h_build, h->box.h, sizeof h_build);
+                }
+            }
+            // skin budget left after the affine strain since the last build: a pair outside the list had
+            // |r_build| > rc + skin and now |r| >= sigma_min(F) |r_build| - 2 u_max, F = h h_build^-1
+            {
+                double hbi[9], F[9];
+                if (!m3::inverse(h_build, hbi)) return fail(h, PISB_ERR_INVALID, "singular build box");
+                m3::mul(h->box.h, hbi, F);
+                double e2 = 0.0;
+                for (int k = 0; k < 9; ++k) {
+                    const double d = F[k] - (k % 4 == 0 ? 1.0 : 0.0);
+                    e2 += d * d;
+                }
+                const double room = (1.0 - std::sqrt(e2)) * rc_list - h->max_rcut;
+                h->skin_half2_override = room > 0.0 ? 0.25 * room * room * (1.0 - 1e-12) : 0.0;
+            }
+            k_nhc_half<<<1, 32, 0, h->stream>>>(h->nhc_d.p, &ke0->ke, (long long)h->n, dt, 0, 0, 1, nullptr);
+            TRY(launch_vv(h, false, true, dt, nullptr, &h->nhc_d.p->scale));
+            TRY(launch_rebuild_chain(h));
+            double *outp[3] = {h->g[0].p, h->g[1].p, h->g[2].p};
+            TRY(launch_force(h, outp, nullptr, rec));
+            for (int d = 0; d < 3; ++d) std::swap(h->f[d], h->g[d]);
+            TRY(launch_vv(h, true, false, dt, rec, &h->nhc_d.p->scale));
+            k_nhc_half<<<1, 32, 0, h->stream>>>(h->nhc_d.p, &rec->ke, (long long)h->n, dt, 1, (long long)(first_step + s),
+                                                (long long)total_steps, h->nhc_energy_d.p);
+            h->n_launches += 2;
+            TRY(launch_npt_post(h, scale, rec));  // v = S v (potential.rs:129) + the tensors of the new state
+            CUDA_TRY(h, cudaMemcpyAsync(h->h_npt, h->npt_tensors_d.p, sizeof(double) * 19, cudaMemcpyDeviceToHost, h->stream));
+            CUDA_TRY(h, cudaMemcpyAsync(h->h_npt + 19, h->nhc_energy_d.p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            CUDA_TRY(h, cudaMemcpyAsync(h->h_thermo, rec, sizeof(pisb_thermo), cudaMemcpyDeviceToHost, h->stream));
+            TRY(read_flags(h));
+            if (h->h_flags[FLAG_NBUILDS] != h->n_builds_host) {
+                h->n_builds_host = h->h_flags[FLAG_NBUILDS];
+                h->max_nbr = h->h_flags[FLAG_MAXNBR];
+                std::memcpy(h_build, h->box.h, sizeof h_build);
+            }
+            if (h->h_flags[FLAG_MAXNBR] > h->kcap) {
+                h->list_valid = false;
+                return fail(h, PISB_ERR_CAPACITY, "a neighbour list overflowed during the batch; re-upload the state and repeat the call");
+            }
+            std::memcpy(tensors, h->h_npt, sizeof tensors);
+            volume = std::fabs(m3::det(h->box.h));
+            mtk_delta_momentum(*baro, tensors, volume, dt, dm);
+            for (int k = 0; k < 9; ++k) baro->momentum[k] += dm[k];
+            if (out) out[s] = h->h_thermo[0];
+            if (ext_energy) {
+                // nhc KE + PE (device) + mtk.kinetic_energy() + mtk.potential_energy(h) (npt.rs:60-66)
+                double mt[9], pt[9], pr[9];
+                for (int c = 0; c < 3; ++c)
+                    for (int r = 0; r < 3; ++r) {
+                        mt[c * 3 + r] = baro->momentum[r * 3 + c];
+                        pt[c * 3 + r] = baro->target_pressure[r * 3 + c];
+                    }
+                m3::mul(baro->momentum, mt, pr);
+                const double mke = ((pr[0] + pr[4]) + pr[8]) / (2.0 * baro->w);
+                m3::mul(pt, h->box.h, pr);
+                const double mpe = (pr[0] + pr[4]) + pr[8];
+                ext_energy[s] = ((h->h_npt[19] + mke) + mpe);
+            }
+            if (h9_trace) std::memcpy(h9_trace + 9 * s, h->box.h, sizeof(double) * 9);
+            h->n_steps += 1;
+            return PISB_OK;
+        }();
+    }
+    h->skin_half2_override = -1.0;
+    if (std::memcmp(h_build, h->box.h, sizeof h_build) != 0) h->list_valid = false;  // the next batch starts from a fresh list
+    if (rc != PISB_OK) return rc;
     NhcDev fin{};
     CUDA_TRY(h, cudaMemcpy(&fin, h->nhc_d.p, sizeof fin, cudaMemcpyDeviceToHost));
     *chain = fin.c;
@@ -1448,6 +1657,8 @@ int pisb_destroy(pisb_t *h) {
     dev_free(h, h->table_d);
     dev_free(h, h->nhc_d);
     dev_free(h, h->nhc_energy_d);
+    dev_free(h, h->npt_tensors_d);
+    if (h->h_npt) cudaFreeHost(h->h_npt);
     dev_free(h, h->thermo_d);
     dev_free(h, h->m_dest);
     dev_free(h, h->m_pig);
@@ -1547,6 +1758,29 @@ int pisb_step_nvt_nhc(pisb_t *h, double dt, int64_t nsteps, pisb_nhc *chain, int
     if (!h) return PISB_ERR_INVALID;
     CUDA_TRY(h, cudaSetDevice(h->device));
     return do_step_nvt(h, dt, nsteps, chain, first_step, total_steps, out, nhc_energy);
+}
+
+int pisb_mtk_init(pisb_mtk *out, const double *target_pressure9, double tau, int64_t n_atoms, double target_temperature) {
+    if (!out || !target_pressure9) return PISB_ERR_INVALID;
+    std::memcpy(out->target_pressure, target_pressure9, sizeof out->target_pressure);
+    std::memset(out->momentum, 0, sizeof out->momentum);
+    out->w = ((double)(3 * n_atoms)) * 0.0083144621 * target_temperature * (tau * tau);  // npt.rs:33
+    return PISB_OK;
+}
+
+int pisb_step_npt_mtk(pisb_t *h, double dt, int64_t nsteps, pisb_mtk *baro, pisb_nhc *chain, int64_t first_step,
+                      int64_t total_steps, pisb_thermo *out, double *ext_energy, double *h9_trace) {
+    if (!h) return PISB_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    return do_step_npt(h, dt, nsteps, baro, chain, first_step, total_steps, out, ext_energy, h9_trace);
+}
+
+int pisb_get_box(pisb_t *h, double *h9, double *hinv9) {
+    if (!h) return PISB_ERR_INVALID;
+    if (!h->have_box) return fail(h, PISB_ERR_STATE, "get_box before set_box");
+    if (h9) std::memcpy(h9, h->box.h, sizeof(double) * 9);
+    if (hinv9) std::memcpy(hinv9, h->box.hinv, sizeof(double) * 9);
+    return PISB_OK;
 }
 
 int pisb_download(pisb_t *h, double *pos, double *vel, double *force) {

@@ -176,6 +176,45 @@ class LJCudaManager:
                                                           int(total_steps), capi._ptr(out), capi._ptr(en)))
         return out, en
 
+    @staticmethod
+    def mtk_new(target_pressure, tau: float, n_atoms: int, target_temperature: float) -> "capi.Mtk":
+        """MTKBarostat::new_from_args (src/ensemble/npt.rs:24-43,67-88).  A scalar is the `iso p` form
+        (target = p * identity, commands.rs:439); a 3x3 array is taken as is."""
+        tp = np.eye(3) * float(target_pressure) if np.isscalar(target_pressure) else np.asarray(target_pressure, dtype=np.float64)
+        tp = np.ascontiguousarray(tp.T.reshape(9))  # column-major
+        m = capi.Mtk()
+        capi.check(None, capi.load().pisb_mtk_init(C.byref(m), capi._ptr(tp), float(tau), int(n_atoms), float(target_temperature)))
+        return m
+
+    def step_npt_mtk(self, dt: float, nsteps: int, baro: "capi.Mtk", chain: "capi.Nhc", first_step: int, total_steps: int,
+                     atoms: Atoms | None = None):
+        """nsteps x (verlet_step_npt_mtk + calculate_target_temperature) (potential.rs:112-135, simulation.rs:58-62).
+        Returns (thermo records, extended-system energy per step, box h per step as (nsteps, 3, 3)); `baro` and `chain`
+        are updated in place, and so is `atoms.sim_box` when atoms is given (scale_box changes the box)."""
+        out = np.zeros(int(nsteps), dtype=capi.THERMO_DTYPE)
+        en = np.zeros(int(nsteps))
+        h9 = np.zeros((int(nsteps), 9))
+        capi.check(self._h, capi.load().pisb_step_npt_mtk(self._h, float(dt), int(nsteps), C.byref(baro), C.byref(chain),
+                                                          int(first_step), int(total_steps), capi._ptr(out), capi._ptr(en),
+                                                          capi._ptr(h9)))
+        if atoms is not None:
+            self.sync_box(atoms)
+        return out, en, h9.reshape(-1, 3, 3).transpose(0, 2, 1)
+
+    def get_box(self):
+        """(h, h_inv) held by the device handle, as 3x3 arrays (row, column)."""
+        hc, hic = np.zeros(9), np.zeros(9)
+        capi.check(self._h, capi.load().pisb_get_box(self._h, capi._ptr(hc), capi._ptr(hic)))
+        return hc.reshape(3, 3).T.copy(), hic.reshape(3, 3).T.copy()
+
+    def sync_box(self, atoms: Atoms):
+        """atoms.sim_box <- the handle's box (after NPT steps)."""
+        h, hi = self.get_box()
+        atoms.sim_box.h[...] = h
+        atoms.sim_box.h_inv[...] = hi
+        b = atoms.sim_box
+        self._box_sig = (b.h.tobytes(), b.h_inv.tobytes(), tuple(b.pbc))
+
     def download(self, atoms: Atoms, positions=True, velocities=True, forces=True):
         rc = capi.load().pisb_download(self._h, capi._ptr(atoms.positions) if positions else None,
                                        capi._ptr(atoms.velocities) if velocities else None,

@@ -173,10 +173,51 @@ def test_cli_nvt_run_matches_oracle(tmp_path):
         got = [float(t) for t in out[s].split()[1:]]
         for g, e in zip(got, ref[s]):
             assert abs(g - e) <= 1.1e-3 + 1e-9 * abs(e)
-    # NPT is still rejected
-    (tmp_path / "npt.pis").write_text("read_data argon.txt\nfix a all npt temp 5.0 50.0 100 iso 0.01 0.01 1000\nrun 5\n")
-    r = subprocess.run([CLI, "-i", "npt.pis"], cwd=tmp_path, capture_output=True, text=True)
-    assert r.returncode == 1 and "NPT" in r.stderr
+
+
+@pytest.mark.gpu
+def test_cli_npt_run_matches_oracle(tmp_path):
+    """The reference's shipped example/input.pis line `fix mynpt all npt temp 5.0 50.0 100 iso 0.01 0.01 1000` through the
+    CLI: thermo lines (H includes thermostat + barostat energy, P uses the step's volume) and the dump's changing box bounds."""
+    from oracle.pis_oracle import Oracle
+    from pis_b200.lattice import fcc_argon
+
+    atoms = fcc_argon(6, temperature=5.0, seed=3)
+    n, L = atoms.n_atoms, atoms.sim_box.h[0, 0]
+    lines = [f"{n} atoms", "1 atom types", "", f"0.0 {rust_display(L)} xlo xhi", f"0.0 {rust_display(L)} ylo yhi",
+             f"0.0 {rust_display(L)} zlo zhi", "", "Masses", "1 39.948", "", "PairCoeffs", "1 0.238 3.405 8.5", "", "Atoms"]
+    lines += [f"{i + 1} 1 {repr(float(p[0]))} {repr(float(p[1]))} {repr(float(p[2]))}" for i, p in enumerate(atoms.positions)]
+    lines += ["", "Velocities"]
+    lines += [f"{i + 1} {repr(float(v[0]))} {repr(float(v[1]))} {repr(float(v[2]))}" for i, v in enumerate(atoms.velocities)]
+    (tmp_path / "argon.txt").write_text("\n".join(lines) + "\n")
+    steps = 60
+    (tmp_path / "input.pis").write_text(f"timestep 0.25\nread_data argon.txt\nfix mynpt all npt temp 5.0 50.0 100 iso 0.01 0.01 1000\n"
+                                        f"dump dp1 all atom 20 dump.lammpstrj\nrun {steps}\n")
+    r = subprocess.run([CLI, "-i", "input.pis", "--skin", "1.0215"], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    out = r.stdout.strip().splitlines()
+    o = Oracle.cubic(L)
+    o.insert(1, 1, 0.238, 3.405, 8.5)
+    chain = o.nhc_new(5.0, 50.0, 100.0)
+    baro = o.mtk_new(0.01, 1000.0, n, 5.0)
+    x, v = atoms.positions.copy(), atoms.velocities.copy()
+    ref, htr = o.run_npt(x, v, np.zeros_like(x), atoms.type_ids, 0.25, steps, baro, chain)
+    assert len(out) == steps + 1
+    for s in range(1, steps + 1):
+        got = [float(t) for t in out[s].split()[1:]]
+        for g, e in zip(got, ref[s]):
+            assert abs(g - e) <= 1.1e-3 + 1e-9 * abs(e)
+    dump = (tmp_path / "dump.lammpstrj").read_text().splitlines()
+    frame = 9 + n
+    assert len(dump) == frame * (steps // 20 + 1)
+    for k in range(steps // 20 + 1):
+        blk = dump[k * frame:(k + 1) * frame]
+        hs = htr[20 * k].reshape(3, 3).T
+        for d in range(3):  # bounds are `0 h_dd` from the diagonal of the step's box (dump_traj.rs:44-50)
+            assert abs(float(blk[5 + d].split()[1]) - hs[d, d]) <= 1e-9 * hs[d, d]
+    rows = np.array([[float(t) for t in ln.split()] for ln in dump[-n:]])
+    assert np.abs(rows[:, 2:] - x).max() < 1e-8
+    assert abs(htr[-1][0] - L) > 1e-6  # the barostat did move the box
 
 
 @pytest.mark.gpu

@@ -508,3 +508,62 @@ def test_nvt_nose_hoover_trace_parity():
         assert abs(a_ - b_) <= 1e-9 * max(abs(b_), 1e-12)
     mgr.download(atoms)
     assert np.abs(atoms.positions - x).max() < 1e-8
+
+
+def _npt_case(ncell, tau_p, steps, split, t_ramp=(5.0, 50.0, 100.0), pressure=0.01, skin=SKIN):
+    atoms = fcc_argon(ncell, temperature=5.0, seed=12345)
+    table = {(1, 1): argon_pair(8.5)}
+    orc = make_oracle(atoms, table)
+    chain_ref = orc.nhc_new(*t_ramp)
+    baro_ref = orc.mtk_new(pressure, tau_p, atoms.n_atoms, t_ramp[0])
+    x, v = atoms.positions.copy(), atoms.velocities.copy()
+    ref, htr = orc.run_npt(x, v, np.zeros_like(x), atoms.type_ids, 0.25, steps, baro_ref, chain_ref)
+    mgr = make_manager(skin=skin, rc=8.5)
+    mgr.attach(atoms)
+    mgr.compute()
+    cells0 = mgr.stats()["n_cells"]
+    chain = mgr.nhc_new(*t_ramp)
+    baro = mgr.mtk_new(pressure, tau_p, atoms.n_atoms, t_ramp[0])
+    assert baro.w == baro_ref.w
+    th1, e1, h1 = mgr.step_npt_mtk(0.25, split, baro, chain, 0, steps, atoms)
+    cells_mid = mgr.stats()["n_cells"]
+    th2, e2, h2 = mgr.step_npt_mtk(0.25, steps - split, baro, chain, split, steps, atoms)
+    pe = np.concatenate([th1["pe"], th2["pe"]])
+    ke = np.concatenate([th1["ke"], th2["ke"]])
+    vir = np.concatenate([th1["virial_ref"], th2["virial_ref"]])
+    ham = pe + ke + np.concatenate([e1, e2])
+    hh = np.concatenate([h1, h2])
+    assert np.max(np.abs(pe - ref[1:, 0]) / np.abs(ref[1:, 0])) <= ENERGY_TOL
+    assert np.max(np.abs(ke - ref[1:, 1]) / np.abs(ref[1:, 1])) <= ENERGY_TOL
+    assert np.max(np.abs(ham - ref[1:, 2]) / np.abs(ref[1:, 2])) <= ENERGY_TOL
+    h_ref = htr[1:].reshape(-1, 3, 3).transpose(0, 2, 1)
+    assert np.abs(hh - h_ref).max() <= 1e-9 * np.abs(h_ref).max()
+    vol = np.abs(np.linalg.det(hh))
+    pres = (2.0 * ke + vir) / (3.0 * vol)
+    assert np.max(np.abs(pres - ref[1:, 4])) <= 1e-9 * np.abs(ref[1:, 4]).max()
+    for a_, b_ in zip(list(baro.momentum) + list(chain.xi), list(baro_ref.momentum) + list(chain_ref.xi)):
+        assert abs(a_ - b_) <= 1e-8 * max(abs(b_), np.abs(np.array(baro_ref.momentum)).max() * 1e-3, 1e-12)
+    mgr.download(atoms)
+    assert np.abs(atoms.positions - x).max() < 1e-7
+    assert np.array_equal(atoms.sim_box.h, hh[-1])              # sync_box: atoms.sim_box follows scale_box
+    return mgr, (cells0, cells_mid), hh
+
+
+def test_npt_mtk_trace_parity_example_fix_line():
+    """verlet_step_npt_mtk (potential.rs:112-135) with the reference's shipped
+    `fix mynpt all npt temp 5.0 50.0 100 iso 0.01 0.01 1000`; PE / KE / H / P traces, box trace, barostat + chain state."""
+    mgr, cells0, hh = _npt_case(8, 1000.0, 300, 120)
+    off = np.abs(hh[-1] - np.diag(np.diag(hh[-1]))).max()
+    assert off > 0.0                                   # the pressure tensor's off-diagonals made the box triclinic
+    assert mgr.stats()["n_builds"] >= 2
+
+
+def test_npt_fast_barostat_regrids_cells():
+    """A stiff barostat (tau 25) strains the 9^3 FCC box by several percent within 70 steps: the cell grid drops from
+    5 to 4 cells in two dimensions mid-run and returns to 5 (re-grid + forced rebuild each time) and the skin budget
+    shrinks with the affine strain since the last build."""
+    mgr, (cells0, cells_mid), hh = _npt_case(9, 25.0, 70, 30)
+    assert list(cells0) == [5, 5, 5]
+    assert list(cells_mid) == [4, 4, 5]                 # after 30 steps x and y have shrunk below 5 list cutoffs
+    assert list(mgr.stats()["n_cells"]) == [5, 5, 5]    # ... and by step 70 the box has bounced back
+    assert np.abs(np.diag(hh) / np.diag(hh[0]) - 1.0).max() > 0.05

@@ -219,3 +219,62 @@ def test_golden_vectors():
     th = o.run_nve(x, v, ff, types, g["dt"], g["steps"])
     assert np.array_equal(th, np.array(g["thermo"]))
     assert np.array_equal(x, np.array(g["positions_end"]))
+
+
+def test_mat3_exp_restatement_against_scipy():
+    """nalgebra Matrix3::exp restated (Al-Mohy & Higham 2009) vs scipy.linalg.expm over every Pade branch."""
+    import scipy.linalg as sl
+    o = Oracle.cubic(30.0)
+    rng = np.random.default_rng(5)
+    for scale, tol in ((0.0, 0.0), (1e-9, 3e-16), (1e-5, 4e-16), (1e-2, 4e-16), (0.1, 1e-15), (0.6, 1e-13), (1.5, 1e-12), (6.0, 1e-10)):
+        a = rng.normal(size=(3, 3)) * scale
+        e = o.mat3_exp(a.T.reshape(9)).reshape(3, 3).T
+        r = sl.expm(a)
+        assert np.abs(e - r).max() <= max(tol, 1e-300) * max(np.abs(r).max(), 1.0)
+    # symmetric generator (what MTKBarostat::scale feeds it): exp(A) exp(-A) = I
+    a = rng.normal(size=(3, 3)) * 1e-3
+    a = (a + a.T) * 0.5
+    p = o.mat3_exp(a.T.reshape(9)).reshape(3, 3).T @ o.mat3_exp((-a).T.reshape(9)).reshape(3, 3).T
+    assert np.abs(p - np.eye(3)).max() < 1e-15
+
+
+def test_npt_restatement_properties():
+    """verlet_step_npt_mtk restated (potential.rs:112-135): pressure tensor vs numpy, scale_box keeps fractional
+    coordinates, zero barostat coupling (w -> inf) reduces to the NVT trace, and the box follows the sign of P - P_target."""
+    atoms = fcc_argon(5, temperature=20.0, seed=11, jitter=0.1)
+    o = Oracle.cubic(atoms.sim_box.h[0, 0])
+    o.insert(1, 1, 0.238, 3.405, 8.5)
+    x, v = atoms.positions.copy(), atoms.velocities.copy()
+    pe, f = o.compute_potential(x, atoms.type_ids)
+    pt = o.pressure_tensor(x, v, f).reshape(3, 3).T
+    vol = o.box_volume()
+    ref = (v.T @ v + x.T @ f) / vol
+    assert np.abs(pt - ref).max() <= 1e-12 * np.abs(ref).max()
+    # huge barostat mass: the box does not move and the trace equals NVT's
+    steps = 20
+    chain_a, chain_b = o.nhc_new(20.0, 30.0, 50.0), o.nhc_new(20.0, 30.0, 50.0)
+    baro = o.mtk_new(0.0, 1e30, atoms.n_atoms, 20.0)
+    xa, va = x.copy(), v.copy()
+    tha, htr = o.run_npt(xa, va, np.zeros_like(x), atoms.type_ids, 0.25, steps, baro, chain_a)
+    o2 = Oracle.cubic(atoms.sim_box.h[0, 0])
+    o2.insert(1, 1, 0.238, 3.405, 8.5)
+    xb, vb = x.copy(), v.copy()
+    thb = o2.run_nvt(xb, vb, np.zeros_like(x), atoms.type_ids, 0.25, steps, chain_b)
+    assert np.abs(htr - htr[0]).max() <= 1e-12
+    assert np.abs(tha[:, :2] - thb[:, :2]).max() <= 1e-9 * np.abs(thb[:, :2]).max()
+    # finite mass, target far above the instantaneous pressure: the box must shrink; fractional coordinates of a
+    # pure scale_box are preserved
+    o3 = Oracle.cubic(atoms.sim_box.h[0, 0])
+    o3.insert(1, 1, 0.238, 3.405, 8.5)
+    baro3 = o3.mtk_new(1.0, 50.0, atoms.n_atoms, 20.0)
+    xc, vc = x.copy(), v.copy()
+    thc, htc = o3.run_npt(xc, vc, np.zeros_like(x), atoms.type_ids, 0.25, 10, baro3, o3.nhc_new(20.0, 20.0, 50.0))
+    assert htc[-1][0] < htc[0][0] and htc[-1][4] < htc[0][4] and htc[-1][8] < htc[0][8]
+    s_before = x @ np.linalg.inv(htc[0].reshape(3, 3).T).T
+    o4 = Oracle.cubic(atoms.sim_box.h[0, 0])
+    xs = x.copy()
+    scale = np.array([[1.01, 0.002, 0.0], [0.002, 0.99, 0.001], [0.0, 0.001, 1.003]])
+    o4.scale_box(scale, xs)
+    h_new = np.array(o4.box.h).reshape(3, 3).T
+    assert np.abs(h_new - scale @ htc[0].reshape(3, 3).T).max() < 1e-12
+    assert np.abs(xs @ np.linalg.inv(h_new).T - s_before).max() < 1e-12
