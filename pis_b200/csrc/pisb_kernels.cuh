@@ -554,6 +554,7 @@ struct CopyBackArgs {
     const int *flags;
     float4 *xf;
     BoxDev box;
+    float *xp;  // pair-packed FP32 positions for k_build_list_v3 (null: not written)
 };
 
 __global__ void __launch_bounds__(TPB) k_copy_back(CopyBackArgs a) {
@@ -561,7 +562,15 @@ __global__ void __launch_bounds__(TPB) k_copy_back(CopyBackArgs a) {
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < a.n; p += gridDim.x * blockDim.x) {
         double4 x = a.s_xt[p];
         a.xt[p] = x;
-        a.xf[p] = make_xf(a.box, x);
+        const float4 xf = make_xf(a.box, x);
+        a.xf[p] = xf;
+        if (a.xp) {  // slots 2q, 2q+1 share one 32-byte record {x0,x1, y0,y1, z0,z1, w0,w1}
+            float *rec = a.xp + (size_t)(p >> 1) * 8 + (p & 1);
+            rec[0] = xf.x;
+            rec[2] = xf.y;
+            rec[4] = xf.z;
+            rec[6] = xf.w;
+        }
         a.xbx[p] = x.x;
         a.xby[p] = x.y;
         a.xbz[p] = x.z;
@@ -1327,6 +1336,203 @@ __global__ void __launch_bounds__(TPB_FORCE) k_build_list_v2(Build2Args a) {
     const bool warp_interior = __all_sync(0xffffffffu, interior);
     int cnt = 0;
     if (active) cnt = warp_interior ? build2_body<MULTI, false>(a, i) : build2_body<MULTI, true>(a, i);
+    int m = cnt;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_down_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(&a.flags[FLAG_MAXNBR], m);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// k_build_list_v3: the v2 build with the inner loop rebuilt around Blackwell's packed FP32 pipe.
+// ncu on v2 (profiles/r01_prof_build_v2b.*): 25 warp-instructions per candidate, issue-bound, the append block
+// (address arithmetic + predicated store) issued for almost every candidate because SOME lane accepts.  v3, for
+// interior warps of a single-type system:
+//   * candidates come as PAIRS: slots 2q, 2q+1 share one 32-byte record {x0,x1,y0,y1,z0,z1,w0,w1} (xp, written by
+//     k_copy_back at rebuild time), fetched with one 256-bit load; the three differences and the squared distance of
+//     BOTH candidates are 6 packed instructions (FADD2 x3, FMUL2, FFMA2 x2) instead of 12 scalar ones;
+//   * acceptance is recorded as bits of a per-thread 32-candidate mask (FSETP + predicated LOP3), a second mask marks
+//     r2 < lo: their difference is the FP32 guard band, resolved by the exact FP64 reference predicate (rare);
+//   * the list is appended once per 32 candidates by walking the set bits, so the store path is issued ~max popc
+//     times per chunk instead of once per candidate; range edges are a mask, the self pair is a split range.
+// The FP32 operations are the same IEEE operations in the same order as r2_f32<false>, so the decision is
+// bit-for-bit the one v2 makes (and therefore the reference's `rij.norm() > rcut`).
+// Boundary warps (image needed), multi-type tables and brick-local grids take the v2 body.
+// ------------------------------------------------------------------------------------------------
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t f2_pack(float lo, float hi) {
+    f32x2_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(f32x2_t v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2_t f2_sub(f32x2_t a, f32x2_t b) {
+    f32x2_t r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2_t f2_add(f32x2_t a, f32x2_t b) {
+    f32x2_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2_t f2_neg(f32x2_t a) { return a ^ 0x8000000080000000ull; }
+__device__ __forceinline__ f32x2_t f2_mul(f32x2_t a, f32x2_t b) {
+    f32x2_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2_t f2_fma(f32x2_t a, f32x2_t b, f32x2_t c) {
+    f32x2_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+struct PairRec {
+    f32x2_t x, y, z, w;
+};
+__device__ __forceinline__ PairRec ldg_pair(const float *xp, int q) {
+    PairRec r;
+    asm volatile("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(r.x), "=l"(r.y), "=l"(r.z), "=l"(r.w) : "l"(xp + (size_t)q * 8));
+    return r;
+}
+
+constexpr int B3_PAIRS = 4;  // pair records in flight per thread (8 candidates)
+
+// The exact reference predicate for a guard-band candidate (rare).  Out of line, by-value arguments only (taking the
+// address of a kernel parameter would force a local copy of the whole argument struct).  v2_possible() => fully periodic.
+__device__ __noinline__ bool build3_exact_out(double h0, double h1, double h2, double i0, double i1, double i2,
+                                              const double4 *__restrict__ xt, double xix, double xiy, double xiz, int jj,
+                                              double t_list) {
+    const double4 xj = ldg_d4(&xt[jj]);
+    double sx = __dmul_rn(i0, __dsub_rn(xj.x, xix)), sy = __dmul_rn(i1, __dsub_rn(xj.y, xiy)), sz = __dmul_rn(i2, __dsub_rn(xj.z, xiz));
+    sx = __dsub_rn(sx, round(sx));
+    sy = __dsub_rn(sy, round(sy));
+    sz = __dsub_rn(sz, round(sz));
+    return norm2(__dmul_rn(h0, sx), __dmul_rn(h1, sy), __dmul_rn(h2, sz)) > t_list;
+}
+
+template <bool IMAGE>
+__device__ __forceinline__ int build3_body(const Build2Args &a, const float *__restrict__ xp, int i) {
+    int cnt = 0;
+    const double4 xi = a.xt[i];
+    const float4 xif = a.xf[i];
+    int c[3];
+    cell_coords<true>(a.box, a.g, xi.x, xi.y, xi.z, c);
+    int *wp = a.nbr + (size_t)i * 4;  // slot of list entry number cnt
+    const ptrdiff_t tile_step = (ptrdiff_t)a.npad * 4 - 3;
+    const float lo = a.pairf0.lo_list, hi = a.pairf0.hi_list;
+    const float Lx = a.boxf.L[0], Ly = a.boxf.L[1], Lz = a.boxf.L[2];
+    const float iLx = a.boxf.invL[0], iLy = a.boxf.invL[1], iLz = a.boxf.invL[2];
+    const f32x2_t xi2 = f2_pack(xif.x, xif.x), yi2 = f2_pack(xif.y, xif.y), zi2 = f2_pack(xif.z, xif.z);
+    const f32x2_t magic = f2_pack(12582912.0f, 12582912.0f);
+    // d - L * rint(d / L) for both candidates, the same FP32 operations as r2_f32<true> (rint by magic constant)
+    auto image = [&](f32x2_t d, float L, float iL) {
+        const f32x2_t t = f2_mul(d, f2_pack(iL, iL));
+        const f32x2_t r = f2_sub(f2_add(t, magic), magic);
+        return f2_fma(f2_neg(r), f2_pack(L, L), d);
+    };
+    // candidates of the slot range [jb, je)
+    auto scan = [&](int jb, int je) {
+        const int q_end = (je + 1) >> 1;
+        for (int q0 = jb >> 1; q0 < q_end; q0 += 16) {
+            unsigned m_hi = 0u, m_lo = 0u;  // bit b <-> candidate slot 2*q0 + b
+#pragma unroll 1
+            for (int s = 0; s < 16 && q0 + s < q_end; s += B3_PAIRS) {
+                PairRec r[B3_PAIRS];
+#pragma unroll
+                for (int u = 0; u < B3_PAIRS; ++u) r[u] = ldg_pair(xp, q0 + s + u);  // array padded: reads past q_end stay in bounds
+                unsigned b_hi = 0u, b_lo = 0u;
+#pragma unroll
+                for (int u = 0; u < B3_PAIRS; ++u) {
+                    f32x2_t dx = f2_sub(r[u].x, xi2), dy = f2_sub(r[u].y, yi2), dz = f2_sub(r[u].z, zi2);
+                    if (IMAGE) {
+                        dx = image(dx, Lx, iLx);
+                        dy = image(dy, Ly, iLy);
+                        dz = image(dz, Lz, iLz);
+                    }
+                    const f32x2_t r2 = f2_fma(dz, dz, f2_fma(dy, dy, f2_mul(dx, dx)));
+                    float ra, rb;
+                    f2_unpack(r2, ra, rb);
+                    if (ra <= hi) b_hi |= 1u << (2 * u);
+                    if (rb <= hi) b_hi |= 2u << (2 * u);
+                    if (ra < lo) b_lo |= 1u << (2 * u);
+                    if (rb < lo) b_lo |= 2u << (2 * u);
+                }
+                m_hi |= b_hi << (2 * s);
+                m_lo |= b_lo << (2 * s);
+            }
+            // range edges (and whatever lies in the padding / beyond q_end)
+            const int first = jb - 2 * q0, last = je - 2 * q0;  // valid bits: [first, last)
+            unsigned valid = last >= 32 ? 0xffffffffu : ((1u << last) - 1u);
+            if (first > 0) valid &= ~((1u << first) - 1u);
+            m_hi &= valid;
+            // FP32 guard band: the exact FP64 reference predicate decides
+            unsigned band = m_hi & ~m_lo;
+            while (band) {
+                const int b = __ffs(band) - 1;
+                band &= band - 1u;
+                if (build3_exact_out(a.box.h[0], a.box.h[4], a.box.h[8], a.box.hinv[0], a.box.hinv[4], a.box.hinv[8], a.xt, xi.x,
+                                     xi.y, xi.z, 2 * q0 + b, a.pair0.t_list))
+                    m_hi &= ~(1u << b);
+            }
+            const int j0 = 2 * q0;
+            while (m_hi) {
+                const int b = __ffs(m_hi) - 1;
+                m_hi &= m_hi - 1u;
+                if (cnt < a.kcap) *wp = j0 + b;
+                ++cnt;
+                wp += (cnt & 3) ? (ptrdiff_t)1 : tile_step;
+            }
+        }
+    };
+    const int nx = a.g.n[0];
+    for (int dz = a.g.lo[2]; dz <= a.g.hi[2]; ++dz) {
+        int cz = c[2] + dz;
+        if (cz < 0 || cz >= a.g.n[2]) {
+            // interior atom: a wrapped cell lies beyond the cutoff (margin > rc + skin); brick-local dims never wrap
+            if (!IMAGE || a.g.local[2]) continue;
+            cz += cz < 0 ? a.g.n[2] : -a.g.n[2];
+        }
+        for (int dy = a.g.lo[1]; dy <= a.g.hi[1]; ++dy) {
+            int cy = c[1] + dy;
+            if (cy < 0 || cy >= a.g.n[1]) {
+                if (!IMAGE || a.g.local[1]) continue;
+                cy += cy < 0 ? a.g.n[1] : -a.g.n[1];
+            }
+            const int rb = (cz * a.g.n[1] + cy) * nx;
+            const int xlo = c[0] + a.g.lo[0], xhi = c[0] + a.g.hi[0];
+            if (IMAGE && xlo < 0 && !a.g.local[0]) scan(__ldg(&a.cell_start[rb + xlo + nx]), __ldg(&a.cell_start[rb + nx]));
+            const int jb = __ldg(&a.cell_start[rb + max(xlo, 0)]);
+            const int je = __ldg(&a.cell_start[rb + min(xhi, nx - 1) + 1]);
+            if (i >= jb && i < je) {  // the range that holds i itself: skip i == j by splitting it
+                scan(jb, i);
+                scan(i + 1, je);
+            } else {
+                scan(jb, je);
+            }
+            if (IMAGE && xhi >= nx && !a.g.local[0]) scan(__ldg(&a.cell_start[rb]), __ldg(&a.cell_start[rb + xhi - nx + 1]));
+        }
+    }
+    a.nnbr[i] = cnt < a.kcap ? cnt : a.kcap;
+    return cnt;
+}
+
+template <bool MULTI>
+__global__ void __launch_bounds__(TPB_FORCE) k_build_list_v3(Build2Args a, const float *__restrict__ xp, int fast_ok) {
+    if (a.flags[FLAG_REBUILD] == 0) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < a.n && xf_is_ghost(a.xf[i])) a.nnbr[i] = 0;
+    const bool active = i < a.n && !xf_is_ghost(a.xf[i]);
+    bool interior = true;
+    if (active) interior = is_interior(a.boxf, a.xf[i]);
+    const bool warp_interior = __all_sync(0xffffffffu, interior);
+    int cnt = 0;
+    if (active) {
+        if (!MULTI && fast_ok) cnt = warp_interior ? build3_body<false>(a, xp, i) : build3_body<true>(a, xp, i);
+        else cnt = warp_interior ? build2_body<MULTI, false>(a, i) : build2_body<MULTI, true>(a, i);
+    }
     int m = cnt;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_down_sync(0xffffffffu, m, o));

@@ -89,6 +89,7 @@ struct pisb_handle {
     // device arrays
     DevBuf<double4> xt, s_xt;
     DevBuf<float4> xf;
+    DevBuf<float> xp;  // pair-packed FP32 positions (k_build_list_v3), rewritten at every rebuild
     DevBuf<PairF> tablef_d;
     DevBuf<double> v[3], f[3], g[3], xb[3], s_v[3], s_f[3];
     DevBuf<int> id, s_id, slot_of_id, cell_of, order, nnbr, nbr;
@@ -130,6 +131,19 @@ struct pisb_handle {
     unsigned long long *peer_sig[P2P_MAX_RANKS] = {nullptr};
     int p2p_dst_off[P2P_MAX_RANKS] = {0};
     unsigned long long halo_seq = 0;
+
+    // CUDA graphs of NVE step batches (single GPU): the rebuild chain sits in a device-side conditional node
+    struct StepGraph {
+        int m = 0;
+        const void *f0 = nullptr;  // which of the two force buffers held F(t) when the batch was captured
+        cudaGraphExec_t exec = nullptr;
+    };
+    std::vector<StepGraph> graphs;
+    std::vector<unsigned char> graph_sig;  // everything the captured launches baked in (pointers, box, grid, dt, ...)
+    cudaStream_t graph_stream = nullptr;   // capture stream of the conditional bodies
+    int use_graphs = 1;                    // option "cuda_graphs"
+    bool capturing = false;
+    int64_t n_graph_launches = 0;
 
     // stats
     int64_t n_steps = 0, n_launches = 0;
@@ -345,10 +359,12 @@ int setup_grid(pisb_t *h) {
     Grid g{};
     // Half-size cells (edge >= rc_list/2, 5^3 stencil) cut the candidate volume from 27 to 15.6 rc_list^3.
     // Only with the range-scanning v2 build and when every dimension has >= 5 such cells.
-    int div = h->cell_div == 0 ? 1 : h->cell_div;  // auto = 1 (half-size cells measured no faster)
+    // auto: half-size cells with the v3 build (1.81 vs 2.05 ms per build at 4M atoms; with the scalar v2 build the shorter
+    // rows cost what the smaller candidate volume saved: profiles/r01_variants_build_v3.jsonl)
+    int div = h->cell_div == 0 ? ((h->build_variant == 0 || h->build_variant == 3) && h->n_types == 1 ? 2 : 1) : h->cell_div;
     if (div < 1) div = 1;
     if (div > 2) div = 2;
-    if (!(h->build_variant == 2 || (h->build_variant == 0 && v2_possible(h)))) div = 1;
+    if (!(h->build_variant >= 2 || (h->build_variant == 0 && v2_possible(h)))) div = 1;
     if (h->multi) div = 1;
     const int64_t cell_cap = std::max<int64_t>(4 * (int64_t)h->n + 1024, 27);
     double prod = 1.0;
@@ -454,6 +470,7 @@ int reserve_atoms(pisb_t *h, int n) {
     const size_t cap = (size_t)n;
     TRY(dev_reserve(h, h->xt, cap));
     TRY(dev_reserve(h, h->xf, cap));
+    TRY(dev_reserve(h, h->xp, ((cap + 1) / 2 + 32) * 8));
     TRY(dev_reserve(h, h->s_xt, cap));
     for (int d = 0; d < 3; ++d) {
         TRY(dev_reserve(h, h->v[d], cap));
@@ -526,7 +543,7 @@ int launch_rebuild_chain(pisb_t *h) {
         CopyBackArgs ca{n, h->s_xt.p, h->s_v[0].p, h->s_v[1].p, h->s_v[2].p, h->s_f[0].p, h->s_f[1].p, h->s_f[2].p,
                         h->s_id.p, h->xt.p, h->v[0].p, h->v[1].p, h->v[2].p, h->f[0].p, h->f[1].p, h->f[2].p,
                         h->id.p, h->multi ? nullptr : h->slot_of_id.p, h->xb[0].p, h->xb[1].p, h->xb[2].p, h->flags, h->xf.p,
-                        h->box};
+                        h->box, h->xp.p};
         k_copy_back<<<nblk_capped(n, TPB, 8), TPB, 0, st>>>(ca);
         h->n_launches += 6;
     }
@@ -536,13 +553,18 @@ int launch_rebuild_chain(pisb_t *h) {
                      h->n_types, h->nbr.p, h->nnbr.p, h->flags};
         const bool multi = h->n_types > 1;
         const int nb = nblk(n, TPB_FORCE);
-        const bool v2 = h->build_variant == 2 || (h->build_variant == 0 && v2_possible(h));
+        const bool v2 = h->build_variant >= 2 || (h->build_variant == 0 && v2_possible(h));
         if (v2) {
-            if (!v2_possible(h)) return fail(h, PISB_ERR_INVALID, "build_variant 2 needs an orthorhombic, fully periodic box");
+            if (!v2_possible(h)) return fail(h, PISB_ERR_INVALID, "build_variant 2/3 needs an orthorhombic, fully periodic box");
             Build2Args b2{n, h->npad, h->kcap, h->xt.p, h->xf.p, h->cell_start.p, h->box, h->boxf, g, h->pairs[0],
                           h->pairsf[0], h->table_d.p, h->tablef_d.p, h->n_types, h->nbr.p, h->nnbr.p, h->flags};
-            if (multi) k_build_list_v2<true><<<nb, TPB_FORCE, 0, st>>>(b2);
-            else k_build_list_v2<false><<<nb, TPB_FORCE, 0, st>>>(b2);
+            if (h->build_variant == 2) {  // v2: scalar FP32 pre-filter (kept for A/B)
+                if (multi) k_build_list_v2<true><<<nb, TPB_FORCE, 0, st>>>(b2);
+                else k_build_list_v2<false><<<nb, TPB_FORCE, 0, st>>>(b2);
+            } else {  // default: v3, packed FP32 pair records + bit-mask append for interior warps
+                if (multi) k_build_list_v3<true><<<nb, TPB_FORCE, 0, st>>>(b2, h->xp.p, 1);
+                else k_build_list_v3<false><<<nb, TPB_FORCE, 0, st>>>(b2, h->xp.p, 1);
+            }
         } else if (h->box.ortho) {
             if (multi) k_build_list<true, true><<<nb, TPB_FORCE, 0, st>>>(ba);
             else k_build_list<true, false><<<nb, TPB_FORCE, 0, st>>>(ba);
@@ -769,6 +791,143 @@ int do_compute(pisb_t *h, int accumulate, double *pe) {
     return PISB_OK;
 }
 
+// ---- NVE step batches ----------------------------------------------------------------------------------------
+// Enqueue cnt steps writing records rec[0..cnt): drift, [rebuild], force, (kick+drift, [rebuild], force) x (cnt-1), kick.
+// The kick of step k is fused with the drift of step k+1.  While a graph is being captured the rebuild chain goes
+// into an IF node whose condition a one-thread kernel copies from flags[REBUILD]; otherwise the chain is launched and
+// every kernel of it returns at once unless the flag is set.
+int capture_conditional_rebuild(pisb_t *h);
+
+int enqueue_nve_steps(pisb_t *h, double dt, int64_t cnt, pisb_thermo *rec0) {
+    for (int64_t s = 0; s < cnt; ++s) {
+        pisb_thermo *rec = rec0 + s;
+        if (s == 0) TRY(launch_vv(h, false, true, dt, nullptr));
+        else TRY(launch_vv(h, true, true, dt, rec - 1));
+        if (h->capturing) TRY(capture_conditional_rebuild(h));
+        else TRY(launch_rebuild_chain(h));
+        double *outp[3] = {h->g[0].p, h->g[1].p, h->g[2].p};
+        TRY(launch_force(h, outp, nullptr, rec));
+        for (int d = 0; d < 3; ++d) std::swap(h->f[d], h->g[d]);
+    }
+    return launch_vv(h, true, false, dt, rec0 + (cnt - 1));
+}
+
+__global__ void k_set_condition(cudaGraphConditionalHandle handle, const int *flags) {
+    cudaGraphSetConditional(handle, flags[FLAG_REBUILD] != 0 ? 1u : 0u);
+}
+
+int capture_conditional_rebuild(pisb_t *h) {
+    cudaStreamCaptureStatus status;
+    cudaGraph_t graph = nullptr;
+    const cudaGraphNode_t *deps = nullptr;
+    size_t ndeps = 0;
+    CUDA_TRY(h, cudaStreamGetCaptureInfo(h->stream, &status, nullptr, &graph, &deps, &ndeps));
+    if (status != cudaStreamCaptureStatusActive) return fail(h, PISB_ERR_STATE, "conditional rebuild outside a capture");
+    cudaGraphConditionalHandle cond;
+    CUDA_TRY(h, cudaGraphConditionalHandleCreate(&cond, graph, 0, cudaGraphCondAssignDefault));
+    k_set_condition<<<1, 1, 0, h->stream>>>(cond, h->flags);
+    TRY(check_launch(h, "k_set_condition"));
+    CUDA_TRY(h, cudaStreamGetCaptureInfo(h->stream, &status, nullptr, &graph, &deps, &ndeps));
+    cudaGraphNodeParams np{};
+    np.type = cudaGraphNodeTypeConditional;
+    np.conditional.handle = cond;
+    np.conditional.type = cudaGraphCondTypeIf;
+    np.conditional.size = 1;
+    cudaGraphNode_t node;
+    CUDA_TRY(h, cudaGraphAddNode(&node, graph, deps, ndeps, &np));
+    cudaGraph_t body = np.conditional.phGraph_out[0];
+    CUDA_TRY(h, cudaStreamBeginCaptureToGraph(h->graph_stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+    cudaStream_t main_stream = h->stream;
+    h->stream = h->graph_stream;  // the chain's launches land in the body graph
+    const int rc = launch_rebuild_chain(h);
+    h->stream = main_stream;
+    cudaGraph_t ended = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(h->graph_stream, &ended);
+    if (rc != PISB_OK) return rc;
+    if (e != cudaSuccess) return fail(h, PISB_ERR_CUDA, fmt("capturing the rebuild chain: %s", cudaGetErrorString(e)));
+    CUDA_TRY(h, cudaStreamUpdateCaptureDependencies(h->stream, &node, 1, cudaStreamSetCaptureDependencies));
+    return PISB_OK;
+}
+
+void drop_graphs(pisb_t *h) {
+    for (auto &g : h->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    h->graphs.clear();
+}
+
+// Everything a captured launch sequence bakes in.  Compared byte-wise before every replay.
+void graph_signature(pisb_t *h, double dt, std::vector<unsigned char> &sig) {
+    sig.clear();
+    auto put = [&](const void *p, size_t n) {
+        const unsigned char *b = (const unsigned char *)p;
+        sig.insert(sig.end(), b, b + n);
+    };
+    // f and g trade places every step: the pair is part of the signature, the current assignment is the graph's key
+    const void *fa = std::min<const void *>(h->f[0].p, h->g[0].p), *fb = std::max<const void *>(h->f[0].p, h->g[0].p);
+    const void *ptrs[] = {h->xt.p, h->s_xt.p, h->xf.p, h->xp.p, h->tablef_d.p, h->v[0].p, h->v[1].p, h->v[2].p, fa, fb,
+                          std::min<const void *>(h->f[1].p, h->g[1].p), std::max<const void *>(h->f[1].p, h->g[1].p),
+                          std::min<const void *>(h->f[2].p, h->g[2].p), std::max<const void *>(h->f[2].p, h->g[2].p), h->xb[0].p, h->xb[1].p, h->xb[2].p, h->s_v[0].p,
+                          h->s_v[1].p, h->s_v[2].p, h->s_f[0].p, h->s_f[1].p, h->s_f[2].p, h->id.p, h->s_id.p,
+                          h->slot_of_id.p, h->cell_of.p, h->order.p, h->nnbr.p, h->nbr.p, h->cell_count.p, h->cell_start.p,
+                          h->tile_sum.p, h->mass_d.p, h->partials.p, h->table_d.p, h->thermo_d.p, h->flags, h->ticket};
+    put(ptrs, sizeof ptrs);
+    const int ints[] = {h->n, h->npad, h->kcap, h->n_types, h->force_variant, h->build_variant, h->cell_div};
+    put(ints, sizeof ints);
+    const double dbl[] = {dt, h->skin, h->skin_half2_override, h->max_rcut};
+    put(dbl, sizeof dbl);
+    for (int k = 0; k < 9; ++k) put(&h->box.h[k], sizeof(double)), put(&h->box.hinv[k], sizeof(double));
+    put(h->box.pbc, sizeof h->box.pbc);
+    put(&h->box.ortho, sizeof(int));
+    put(h->grid.n, sizeof h->grid.n), put(h->grid.lo, sizeof h->grid.lo), put(h->grid.hi, sizeof h->grid.hi);
+    put(&h->boxf.margin, sizeof(float));
+    for (const PairDev &pd : h->pairs) {
+        const double v[] = {pd.c4, pd.c24, pd.sig2, pd.t_rc, pd.t_list, pd.ucut, (double)pd.present};
+        put(v, sizeof v);
+    }
+}
+
+// Executable graph of m NVE steps on records thermo_d[0..m) (m even: the f/g swap returns to the captured assignment).
+int get_nve_graph(pisb_t *h, double dt, int m, cudaGraphExec_t *out) {
+    std::vector<unsigned char> sig;
+    graph_signature(h, dt, sig);
+    if (sig != h->graph_sig) {
+        drop_graphs(h);
+        h->graph_sig = sig;
+    }
+    for (auto &g : h->graphs)
+        if (g.m == m && g.f0 == h->f[0].p) {
+            *out = g.exec;
+            return PISB_OK;
+        }
+    if (!h->graph_stream) CUDA_TRY(h, cudaStreamCreateWithFlags(&h->graph_stream, cudaStreamNonBlocking));
+    const int64_t launches_before = h->n_launches;
+    CUDA_TRY(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    h->capturing = true;
+    const int rc = enqueue_nve_steps(h, dt, m, h->thermo_d.p);
+    h->capturing = false;
+    h->n_launches = launches_before;  // captured, not launched
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+    if (rc != PISB_OK || e != cudaSuccess) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        if (rc != PISB_OK) return rc;
+        return fail(h, PISB_ERR_CUDA, fmt("cudaStreamEndCapture: %s", cudaGetErrorString(e)));
+    }
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t ei = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ei != cudaSuccess) return fail(h, PISB_ERR_CUDA, fmt("cudaGraphInstantiate: %s", cudaGetErrorString(ei)));
+    if (h->graphs.size() >= 8) drop_graphs(h);
+    pisb_handle::StepGraph sg;
+    sg.m = m;
+    sg.f0 = h->f[0].p;
+    sg.exec = exec;
+    h->graphs.push_back(sg);
+    *out = exec;
+    return PISB_OK;
+}
+
 int do_step_nve(pisb_t *h, double dt, int64_t nsteps, pisb_thermo *out) {
     if (!h->have_atoms || !h->have_box) return fail(h, PISB_ERR_STATE, "set_box and upload must precede step_nve");
     if (nsteps < 0) return fail(h, PISB_ERR_INVALID, "nsteps < 0");
@@ -777,27 +936,39 @@ int do_step_nve(pisb_t *h, double dt, int64_t nsteps, pisb_thermo *out) {
     TRY(ensure_list(h));  // list for x(t); from here on the skin trigger decides on the device
     TRY(check_bad_type(h));
     const int64_t chunk_max = 4096;
+    constexpr int GRAPH_M = 32;  // steps per graph replay
+    // Graph replay needs launch sequences without per-kernel timing events.
+    const bool graphs = h->use_graphs && !h->profiling;
     int64_t done = 0;
     while (done < nsteps) {
         const int64_t m = std::min(chunk_max, nsteps - done);
-        TRY(reserve_thermo(h, (size_t)m + 1));
-        for (int64_t s = 0; s < m; ++s) {
-            pisb_thermo *rec = h->thermo_d.p + s;
-            // kick of the previous step of this chunk fused with this step's drift
-            if (s == 0) TRY(launch_vv(h, false, true, dt, nullptr));
-            else TRY(launch_vv(h, true, true, dt, rec - 1));
-            TRY(launch_rebuild_chain(h));
-            double *outp[3] = {h->g[0].p, h->g[1].p, h->g[2].p};
-            TRY(launch_force(h, outp, nullptr, rec));
-            for (int d = 0; d < 3; ++d) std::swap(h->f[d], h->g[d]);
+        TRY(reserve_thermo(h, (size_t)std::max<int64_t>(m, GRAPH_M) + 1));
+        const int builds_before = (int)h->n_builds_host;
+        int64_t off = 0, graph_steps = 0;
+        while (off < m) {
+            int64_t piece = m - off;
+            if (graphs && piece >= 2) {
+                piece = std::min<int64_t>(piece, GRAPH_M) & ~(int64_t)1;
+                cudaGraphExec_t exec = nullptr;
+                TRY(get_nve_graph(h, dt, (int)piece, &exec));
+                CUDA_TRY(h, cudaGraphLaunch(exec, h->stream));
+                h->n_graph_launches++;
+                graph_steps += piece;
+                // fixed nodes: piece+1 integrator launches, piece condition setters, piece force launches
+                h->n_launches += 3 * piece + 1;
+            } else {
+                TRY(enqueue_nve_steps(h, dt, piece, h->thermo_d.p));
+            }
+            CUDA_TRY(h, cudaMemcpyAsync(h->h_thermo + off, h->thermo_d.p, sizeof(pisb_thermo) * piece, cudaMemcpyDeviceToHost, h->stream));
+            off += piece;
         }
-        TRY(launch_vv(h, true, false, dt, h->thermo_d.p + (m - 1)));
-        CUDA_TRY(h, cudaMemcpyAsync(h->h_thermo, h->thermo_d.p, sizeof(pisb_thermo) * m, cudaMemcpyDeviceToHost, h->stream));
         TRY(read_flags(h));
         if (h->h_flags[FLAG_NBUILDS] != h->n_builds_host) {
             h->n_builds_host = h->h_flags[FLAG_NBUILDS];
             h->max_nbr = h->h_flags[FLAG_MAXNBR];
         }
+        // kernels of the conditional bodies that did run: 10 per build (an upper bound when classic pieces were mixed in)
+        if (graph_steps > 0) h->n_launches += 10 * (int64_t)((int)h->n_builds_host - builds_before);
         if (h->h_flags[FLAG_MAXNBR] > h->kcap) {
             const int mx = h->h_flags[FLAG_MAXNBR];
             h->list_valid = false;
@@ -1628,6 +1799,7 @@ int pisb_destroy(pisb_t *h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     dev_free(h, h->xt);
     dev_free(h, h->xf);
+    dev_free(h, h->xp);
     dev_free(h, h->tablef_d);
     dev_free(h, h->s_xt);
     for (int d = 0; d < 3; ++d) {
@@ -1684,6 +1856,8 @@ int pisb_destroy(pisb_t *h) {
         cudaEventDestroy(e.a);
         cudaEventDestroy(e.b);
     }
+    drop_graphs(h);
+    if (h->graph_stream) cudaStreamDestroy(h->graph_stream);
     if (h->ev_pos) cudaEventDestroy(h->ev_pos);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -2125,6 +2299,10 @@ int pisb_set_option(pisb_t *h, const char *name, double value) {
         h->kcap_user = value > 0 ? (int)value : 0;
         h->kcap = 0;
         h->list_valid = false;
+        return PISB_OK;
+    }
+    if (!std::strcmp(name, "cuda_graphs")) {
+        h->use_graphs = value != 0.0 ? 1 : 0;
         return PISB_OK;
     }
     if (!std::strcmp(name, "halo_mode")) {

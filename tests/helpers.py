@@ -24,6 +24,8 @@ VARIANTS = {
     3: (3, 2, 1),         # v3: 4-wide prefetching all-FP64 force kernel, pre-filter build
     4: (3, 2, 2),         # v3 + half-size cells (5^3 stencil)
     5: (4, 2, 1),         # v4: TMA-staged shared-memory cell tile (prototype)
+    6: (3, 3, 1),         # v3 force + v3 build (packed-FP32 pair records, bit-mask append) == the defaults, explicit
+    7: (3, 3, 2),         # v3 build with half-size cells (5^3 stencil)
 }
 
 

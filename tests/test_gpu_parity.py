@@ -18,7 +18,7 @@ def _jittered(ncell, jitter=0.15, temperature=30.0, seed=7):
     return fcc_argon(ncell, temperature=temperature, seed=seed, jitter=jitter)
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7])
 @pytest.mark.parametrize("ncell,skin", [(10, 0.0), (10, SKIN), (16, SKIN)])
 def test_compute_potential_parity(ncell, skin, variant):
     atoms = _jittered(ncell)
@@ -54,7 +54,7 @@ def test_argon4000_lattice_known_answer():
     assert all(len(r) == 54 for r in rows)
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 6, 7])
 @pytest.mark.parametrize("ncell,skin", [(8, 0.0), (8, SKIN), (12, SKIN)])
 def test_neighbour_list_exact(ncell, skin, variant):
     atoms = _jittered(ncell, jitter=0.3)
@@ -261,7 +261,7 @@ def test_v2_prefilter_is_bitwise_equal_to_v1():
     the reference operation order: v2 forces / energies are BIT-identical to the all-FP64 v1 kernels."""
     atoms = _jittered(12, jitter=0.25, temperature=50.0)
     out = []
-    for variant in (1, 2, 3, 5):
+    for variant in (1, 2, 3, 5, 6):
         a = Atoms(atoms.type_ids, atoms.masses, atoms.positions.copy(), atoms.sim_box, velocities=atoms.velocities.copy())
         m = make_manager(skin=SKIN, variant=variant)
         m.attach(a)
@@ -269,7 +269,7 @@ def test_v2_prefilter_is_bitwise_equal_to_v1():
         th = m.step_nve(0.25, 25)
         m.download(a)
         out.append((pe0, th, a.positions.copy(), a.velocities.copy(), a.forces.copy()))
-    for other in (1, 2, 3):
+    for other in (1, 2, 3, 4):
         assert out[0][0] == out[other][0]
         for name in ("pe", "ke", "virial_ref", "virial_pair"):
             assert np.array_equal(out[0][1][name], out[other][1][name]), name
@@ -297,10 +297,11 @@ def test_guard_band_pairs_sit_on_the_cutoff():
     orc = make_oracle(atoms, table)
     start, nbr = orc.build_neighbour_list(atoms.positions, atoms.type_ids, extra=SKIN)
     pe_ref, f_ref = orc.compute_potential(atoms.positions, atoms.type_ids)
-    mgr = make_manager(skin=SKIN, variant=4)
-    mgr.attach(atoms)
-    for a_, b_ in zip(mgr.neighbours(atoms.n_atoms), csr_rows_sorted(start, nbr)):
-        assert np.array_equal(a_, b_)
+    for variant in (6, 7, 4):
+        mgr = make_manager(skin=SKIN, variant=variant)
+        mgr.attach(atoms)
+        for a_, b_ in zip(mgr.neighbours(atoms.n_atoms), csr_rows_sorted(start, nbr)):
+            assert np.array_equal(a_, b_)
     pe = mgr.compute()
     mgr.download(atoms)
     assert abs(pe - pe_ref) <= 1e-12 * max(abs(pe_ref), 1.0)
@@ -563,7 +564,46 @@ def test_npt_fast_barostat_regrids_cells():
     5 to 4 cells in two dimensions mid-run and returns to 5 (re-grid + forced rebuild each time) and the skin budget
     shrinks with the affine strain since the last build."""
     mgr, (cells0, cells_mid), hh = _npt_case(9, 25.0, 70, 30)
-    assert list(cells0) == [5, 5, 5]
-    assert list(cells_mid) == [4, 4, 5]                 # after 30 steps x and y have shrunk below 5 list cutoffs
+    assert list(cells0) == [10, 10, 10]                 # orthorhombic start: half-size cells (5 list cutoffs per edge)
+    assert list(cells_mid) == [4, 4, 5]                 # triclinic now (full-size cells); x and y shrank below 5 list cutoffs
     assert list(mgr.stats()["n_cells"]) == [5, 5, 5]    # ... and by step 70 the box has bounced back
     assert np.abs(np.diagonal(hh, axis1=1, axis2=2) / np.diag(hh[0]) - 1.0).max() > 0.05
+
+
+def test_cuda_graph_batches_equal_classic_launches():
+    """pisb_step_nve replays CUDA graphs of up to 32 steps with the rebuild chain inside a device-side conditional node;
+    the classic per-kernel launch sequence (option cuda_graphs = 0) must give bit-identical traces and states, across
+    rebuilds, odd step counts (the f/g force buffers trade places) and repeated calls."""
+    atoms_a = fcc_argon(12, temperature=60.0, seed=5)      # hot: several rebuilds in 150 steps
+    atoms_b = fcc_argon(12, temperature=60.0, seed=5)
+    res = []
+    for atoms, use in ((atoms_a, 1), (atoms_b, 0)):
+        mgr = make_manager(skin=SKIN)
+        mgr.set_option("cuda_graphs", use)
+        mgr.attach(atoms)
+        mgr.compute()
+        th = [mgr.step_nve(0.25, k) for k in (64, 7, 1, 33, 46)]   # even, odd, single, odd > 32, even > 32
+        st = mgr.stats()
+        mgr.download(atoms)
+        res.append((np.concatenate(th), st))
+    (tg, sg), (tc, sc) = res
+    for key in ("pe", "ke", "virial_ref", "virial_pair"):
+        assert np.array_equal(tg[key], tc[key]), key
+    assert np.array_equal(atoms_a.positions, atoms_b.positions) and np.array_equal(atoms_a.velocities, atoms_b.velocities)
+    assert np.array_equal(atoms_a.forces, atoms_b.forces)
+    assert sg["n_builds"] == sc["n_builds"] and sg["n_builds"] >= 4
+    assert sg["n_launches"] < sc["n_launches"]          # skipped rebuild chains are not launched at all
+
+
+def test_cuda_graph_small_system_matches_oracle():
+    """The reference's own example scale (4000 atoms, example/argon4000.txt geometry) through graph replays vs the oracle."""
+    atoms = fcc_argon(10, temperature=30.0, seed=2)
+    orc = make_oracle(atoms, {(1, 1): argon_pair(8.5)})
+    x, v = atoms.positions.copy(), atoms.velocities.copy()
+    ref = orc.run_nve(x, v, np.zeros_like(x), atoms.type_ids, 0.25, 200)
+    mgr = make_manager(skin=SKIN, rc=8.5)
+    mgr.attach(atoms)
+    mgr.compute()
+    th = mgr.step_nve(0.25, 200)
+    assert np.max(np.abs(th["pe"] - ref[1:, 0]) / np.abs(ref[1:, 0])) <= ENERGY_TOL
+    assert np.max(np.abs(th["ke"] - ref[1:, 1]) / np.abs(ref[1:, 1])) <= ENERGY_TOL

@@ -14,6 +14,9 @@ __global__ void k(double *out, double seed, float fseed) {
 #pragma unroll
     for (int i = 0; i < ILP; ++i) { a[i] = seed + i * 0.37 + threadIdx.x * 1e-3; f[i] = fseed + i * 0.37f + threadIdx.x * 1e-3f; }
     const double c = seed * 0.999, d = seed * 1e-3;
+    const float g0 = fseed * 0.999f, g1 = fseed * 1e-3f;
+    float2 qa = make_float2(g0, g0), qb = make_float2(g1, g1);
+    const unsigned long long q0 = *reinterpret_cast<unsigned long long *>(&qa), q1 = *reinterpret_cast<unsigned long long *>(&qb);
     for (int it = 0; it < ITERS; ++it) {
 #pragma unroll
         for (int i = 0; i < ILP; ++i) {
@@ -28,6 +31,14 @@ __global__ void k(double *out, double seed, float fseed) {
             else if (OP == 8) a[i] = floor(a[i]) + d;
             else if (OP == 9) { a[i] = (a[i] + 6755399441055744.0) - 6755399441055744.0 + d; }  // magic rint: 3 DADD
             else if (OP == 10) f[i] = rintf(f[i]) + 0.001f;
+            else if (OP == 11) f[i] = fmaf(f[i], g0, g1);      // FFMA, three register operands
+            else if (OP == 12) {                               // FFMA2 (fma.rn.f32x2): two FP32 FMAs per instruction
+                unsigned long long &p2 = reinterpret_cast<unsigned long long *>(a)[i];
+                asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(p2) : "l"(q0), "l"(q1));
+            } else if (OP == 13) {                             // FADD2
+                unsigned long long &p2 = reinterpret_cast<unsigned long long *>(a)[i];
+                asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(p2) : "l"(q1));
+            }
         }
     }
     double s = 0; float fs = 0;
@@ -68,5 +79,8 @@ int main() {
     run<8>("floor(FRND.FLOOR)+DADD", 1);
     run<9>("magic-rint (3 DADD)", 1);
     run<10>("rintf(FRND)+FADD", 1);
+    run<11>("FFMA reg,reg,reg", 1);
+    run<12>("FFMA2 (f32x2), FMAs", 2);
+    run<13>("FADD2 (f32x2), adds", 2);
     return 0;
 }

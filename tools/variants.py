@@ -9,7 +9,7 @@ ncell = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 T0 = float(sys.argv[2]) if len(sys.argv) > 2 else 43.0
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 40
 atoms = fcc_argon(ncell, temperature=T0, seed=12345)
-for fv, bv, cd in ((1, 1, 1), (2, 2, 1), (3, 2, 1), (3, 2, 2)):
+for fv, bv, cd in ((3, 2, 1), (3, 3, 1), (3, 3, 2), (3, 2, 2)):
     m = LJCudaManager(skin=0.3 * 3.405)
     m.insert((1, 1), LennardJones(0.238, 3.405, 2.5 * 3.405))
     m.set_option("force_variant", fv)
