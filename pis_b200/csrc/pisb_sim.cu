@@ -887,18 +887,7 @@ void graph_signature(pisb_t *h, double dt, std::vector<unsigned char> &sig) {
 }
 
 // Executable graph of m NVE steps on records thermo_d[0..m) (m even: the f/g swap returns to the captured assignment).
-int get_nve_graph(pisb_t *h, double dt, int m, cudaGraphExec_t *out) {
-    std::vector<unsigned char> sig;
-    graph_signature(h, dt, sig);
-    if (sig != h->graph_sig) {
-        drop_graphs(h);
-        h->graph_sig = sig;
-    }
-    for (auto &g : h->graphs)
-        if (g.m == m && g.f0 == h->f[0].p) {
-            *out = g.exec;
-            return PISB_OK;
-        }
+int capture_nve_graph(pisb_t *h, double dt, int m) {
     if (!h->graph_stream) CUDA_TRY(h, cudaStreamCreateWithFlags(&h->graph_stream, cudaStreamNonBlocking));
     const int64_t launches_before = h->n_launches;
     CUDA_TRY(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
@@ -918,14 +907,35 @@ int get_nve_graph(pisb_t *h, double dt, int m, cudaGraphExec_t *out) {
     const cudaError_t ei = cudaGraphInstantiate(&exec, graph, 0);
     cudaGraphDestroy(graph);
     if (ei != cudaSuccess) return fail(h, PISB_ERR_CUDA, fmt("cudaGraphInstantiate: %s", cudaGetErrorString(ei)));
-    if (h->graphs.size() >= 8) drop_graphs(h);
     pisb_handle::StepGraph sg;
     sg.m = m;
     sg.f0 = h->f[0].p;
     sg.exec = exec;
     h->graphs.push_back(sg);
-    *out = exec;
     return PISB_OK;
+}
+
+constexpr int GRAPH_M = 8;  // steps per replay; batches are cut into pieces of 8, 4, 2 (and a classic single step)
+
+// All piece sizes are captured together the first time a (state signature, f/g assignment) pair is seen, so the one-off
+// capture + instantiation cost (~1 ms per captured step) is paid in the first batch, not whenever a new remainder shows up.
+int get_nve_graph(pisb_t *h, double dt, int m, cudaGraphExec_t *out) {
+    std::vector<unsigned char> sig;
+    graph_signature(h, dt, sig);
+    if (sig != h->graph_sig) {
+        drop_graphs(h);
+        h->graph_sig = sig;
+    }
+    for (int pass = 0; pass < 2; ++pass) {
+        for (auto &g : h->graphs)
+            if (g.m == m && g.f0 == h->f[0].p) {
+                *out = g.exec;
+                return PISB_OK;
+            }
+        if (pass == 0)
+            for (int mm = GRAPH_M; mm >= 2; mm /= 2) TRY(capture_nve_graph(h, dt, mm));
+    }
+    return fail(h, PISB_ERR_STATE, "no graph for this batch size");
 }
 
 int do_step_nve(pisb_t *h, double dt, int64_t nsteps, pisb_thermo *out) {
@@ -936,19 +946,18 @@ int do_step_nve(pisb_t *h, double dt, int64_t nsteps, pisb_thermo *out) {
     TRY(ensure_list(h));  // list for x(t); from here on the skin trigger decides on the device
     TRY(check_bad_type(h));
     const int64_t chunk_max = 4096;
-    constexpr int GRAPH_M = 32;  // steps per graph replay
     // Graph replay needs launch sequences without per-kernel timing events.
     const bool graphs = h->use_graphs && !h->profiling;
     int64_t done = 0;
     while (done < nsteps) {
         const int64_t m = std::min(chunk_max, nsteps - done);
-        TRY(reserve_thermo(h, (size_t)std::max<int64_t>(m, GRAPH_M) + 1));
+        TRY(reserve_thermo(h, (size_t)chunk_max + 1));  // fixed size: the record pointer is baked into the graphs
         const int builds_before = (int)h->n_builds_host;
         int64_t off = 0, graph_steps = 0;
         while (off < m) {
             int64_t piece = m - off;
             if (graphs && piece >= 2) {
-                piece = std::min<int64_t>(piece, GRAPH_M) & ~(int64_t)1;
+                piece = piece >= GRAPH_M ? GRAPH_M : (piece >= 4 ? 4 : 2);
                 cudaGraphExec_t exec = nullptr;
                 TRY(get_nve_graph(h, dt, (int)piece, &exec));
                 CUDA_TRY(h, cudaGraphLaunch(exec, h->stream));

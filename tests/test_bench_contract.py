@@ -42,7 +42,7 @@ def test_cuda_arm_json_line():
               "--e2e-steps", "3"])
     assert BASE_KEYS | {"clocks", "gpu_launches", "roofline"} <= set(d)
     assert d["n_gpus"] == 1 and d["steps"] == 12 and d["warmup"] == 3 and d["higher_is_better"] is True
-    assert d["gpu_launches"] > 100 and d["value"] > 1e7
+    assert d["gpu_launches"] > 30 and d["value"] > 1e7
     rf = d["roofline"]
     assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-12
     assert d["e2e"]["h2d_bytes_per_step"] == 72 * d["config"]["n_atoms"] and d["e2e"]["value"] < d["value"]

@@ -571,7 +571,7 @@ def test_npt_fast_barostat_regrids_cells():
 
 
 def test_cuda_graph_batches_equal_classic_launches():
-    """pisb_step_nve replays CUDA graphs of up to 32 steps with the rebuild chain inside a device-side conditional node;
+    """pisb_step_nve replays CUDA graphs of 8 / 4 / 2 steps with the rebuild chain inside a device-side conditional node;
     the classic per-kernel launch sequence (option cuda_graphs = 0) must give bit-identical traces and states, across
     rebuilds, odd step counts (the f/g force buffers trade places) and repeated calls."""
     atoms_a = fcc_argon(12, temperature=60.0, seed=5)      # hot: several rebuilds in 150 steps
@@ -582,7 +582,7 @@ def test_cuda_graph_batches_equal_classic_launches():
         mgr.set_option("cuda_graphs", use)
         mgr.attach(atoms)
         mgr.compute()
-        th = [mgr.step_nve(0.25, k) for k in (64, 7, 1, 33, 46)]   # even, odd, single, odd > 32, even > 32
+        th = [mgr.step_nve(0.25, k) for k in (64, 7, 1, 33, 46)]   # multiples of 8, odd remainders (f/g parity flips), a single step
         st = mgr.stats()
         mgr.download(atoms)
         res.append((np.concatenate(th), st))
