@@ -365,7 +365,6 @@ int setup_grid(pisb_t *h) {
     if (div < 1) div = 1;
     if (div > 2) div = 2;
     if (!(h->build_variant >= 2 || (h->build_variant == 0 && v2_possible(h)))) div = 1;
-    if (h->multi) div = 1;
     const int64_t cell_cap = std::max<int64_t>(4 * (int64_t)h->n + 1024, 27);
     double prod = 1.0;
     // Extent that bounds the cell count of dimension d: the reference's column norm (divide_into_cells), and for a
@@ -430,15 +429,15 @@ int setup_grid(pisb_t *h) {
             if (w < 2.0 * dc.gw)
                 return fail(h, PISB_ERR_INVALID, fmt("brick width %.6g in dimension %d is below 2 x (rcut + skin) = %.6g", w, d, 2.0 * dc.gw));
             const double half = 0.5 * w + dc.gw + h->skin;
-            int nd = (int)std::floor(2.0 * half / rc_list);
-            if (nd < 3) nd = 3;
+            int nd = (int)std::floor(2.0 * half / (rc_list / div));  // cell edge >= rc_list / div, stencil +-div
+            if (nd < 2 * div + 1) nd = 2 * div + 1;
             g.n[d] = nd;
             g.local[d] = 1;
             g.center[d] = dc.lo[d] + 0.5 * w;
             g.half[d] = half;
             g.inv_edge[d] = nd / (2.0 * half);
-            g.lo[d] = -1;
-            g.hi[d] = 1;
+            g.lo[d] = -div;
+            g.hi[d] = div;
         }
     }
     g.ncell = g.n[0] * g.n[1] * g.n[2];
