@@ -17,6 +17,7 @@
 //   k_force_v3        DEFAULT: all-FP64, int4 index tiles prefetched, 4 x 256-bit gathers in flight, magic rint,
 //                     interior-warp shortcut, 64-register launch bound
 //   k_force_v4        v3 with the block's cell tile staged in shared memory by TMA bulk copies (prototype)
+//   k_force_split<S>  S lanes per atom (auto below ~75k atoms): same pair terms, different summation order
 //   k_build_list (v1) all-FP64 27-cell scan;  k_build_list_v2  DEFAULT: FP32 pre-filter over contiguous x-rows
 #pragma once
 #include "pisb_device.cuh"
@@ -1010,6 +1011,93 @@ __global__ void __launch_bounds__(TPB_FORCE, 8) k_force_v3(Force2Args a) {
         double fx = 0.0, fy = 0.0, fz = 0.0, pe = 0.0, vir = 0.0;
         if (warp_interior) force3_body<MULTI, false>(a, i, fx, fy, fz, pe, vir);
         else force3_body<MULTI, true>(a, i, fx, fy, fz, pe, vir);
+        if (a.ax) {
+            fx += a.ax[i];
+            fy += a.ay[i];
+            fz += a.az[i];
+        }
+        a.fx[i] = fx;
+        a.fy[i] = fy;
+        a.fz[i] = fz;
+        red[0] = pe;
+        red[1] = vir;
+    }
+    pisb_thermo *th = a.thermo;
+    block_reduce_finalize<2, TPB_FORCE>(red, a.partials, a.ticket, [&](int qq, double s) {
+        if (qq == 0) th->pe = s / 2.0;
+        else th->virial_pair = s / 2.0;
+    });
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_force_split<S>: S lanes per atom, for systems too small to fill 148 SMs with one thread per atom (the reference's
+// own example has 4000 atoms: 32 blocks, one warp per scheduler, nothing to hide the gather + FP64 latency with;
+// 28 us per launch with k_force_v3).  Lane l of an atom's group takes the K-tiles l, l+S, ... of its list row (same
+// pair arithmetic, bit-identical pair terms); the S partial sums are combined by xor-shuffles in a fixed order.
+// Only the summation order differs from k_force_v3.
+// ------------------------------------------------------------------------------------------------
+template <bool MULTI, bool IMAGE, int S>
+__device__ __forceinline__ void force_split_body(const Force2Args &a, int i, int l, double &fx, double &fy, double &fz,
+                                                 double &pe, double &vir) {
+    const double4 xi = a.xt[i];
+    const int ti = MULTI ? type_of(xi.w) : 1;
+    const int nn = a.nnbr[i];
+    const int4 *tiles = reinterpret_cast<const int4 *>(a.nbr) + i;
+    for (int k = 4 * l; k < nn; k += 4 * S) {
+        const int4 cur = __ldg(tiles + (size_t)(k >> 2) * a.npad);
+        int j[4] = {cur.x, cur.y, cur.z, cur.w};
+        bool in[4];
+        double4 xj[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            in[u] = k + u < nn;
+            if (!in[u]) j[u] = i;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) xj[u] = ldg_d4(&a.xt[j[u]]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            double dx, dy, dz;
+            disp_inrange_ortho<IMAGE>(a.box, xi, xj[u], dx, dy, dz);
+            const double r2 = norm2(dx, dy, dz);
+            PairDev p = a.pair0;
+            if (MULTI) {
+                const int tj = type_of(xj[u].w);
+                p = a.table[(min(ti, tj) - 1) * a.n_types + (max(ti, tj) - 1)];
+                in[u] = in[u] && p.present;
+            }
+            if (in[u] && !(r2 > p.t_rc)) {
+                double uu, fs;
+                lj_pair(p, r2, uu, fs);
+                PISB_ACCUM(dx, dy, dz, r2, uu, fs);
+            }
+        }
+    }
+}
+
+template <bool MULTI, int S>
+__global__ void __launch_bounds__(TPB_FORCE) k_force_split(Force2Args a) {
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = gt / S, l = gt % S;
+    double red[2] = {0.0, 0.0};
+    const bool active = i < a.n && !xf_is_ghost(a.xf[i]);
+    bool interior = true;
+    if (active) interior = is_interior(a.boxf, a.xf[i]);
+    const bool warp_interior = __all_sync(0xffffffffu, interior);
+    double fx = 0.0, fy = 0.0, fz = 0.0, pe = 0.0, vir = 0.0;
+    if (active) {
+        if (warp_interior) force_split_body<MULTI, false, S>(a, i, l, fx, fy, fz, pe, vir);
+        else force_split_body<MULTI, true, S>(a, i, l, fx, fy, fz, pe, vir);
+    }
+#pragma unroll
+    for (int o = S / 2; o > 0; o >>= 1) {
+        fx = __dadd_rn(fx, __shfl_xor_sync(0xffffffffu, fx, o));
+        fy = __dadd_rn(fy, __shfl_xor_sync(0xffffffffu, fy, o));
+        fz = __dadd_rn(fz, __shfl_xor_sync(0xffffffffu, fz, o));
+        pe = __dadd_rn(pe, __shfl_xor_sync(0xffffffffu, pe, o));
+        vir = __dadd_rn(vir, __shfl_xor_sync(0xffffffffu, vir, o));
+    }
+    if (active && l == 0) {
         if (a.ax) {
             fx += a.ax[i];
             fy += a.ay[i];

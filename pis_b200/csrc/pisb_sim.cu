@@ -485,7 +485,8 @@ int reserve_atoms(pisb_t *h, int n) {
     TRY(dev_reserve(h, h->cell_of, cap));
     TRY(dev_reserve(h, h->order, cap));
     TRY(dev_reserve(h, h->nnbr, cap));
-    TRY(dev_reserve(h, h->partials, (size_t)4 * (nblk(n, TPB_FORCE) + 1)));
+    // per-block partial sums: up to 4 quantities x blocks; small systems run the force kernel with 8 lanes per atom
+    TRY(dev_reserve(h, h->partials, (size_t)4 * (nblk(n, TPB_FORCE) + 1) + (size_t)4 * (nblk(std::min(n, 75000) * 8, TPB_FORCE) + 1)));
     return PISB_OK;
 }
 
@@ -592,7 +593,18 @@ int launch_force(pisb_t *h, double *const out[3], const double *const acc[3], pi
         Force2Args f2{h->n, h->npad, h->xt.p, h->xf.p, h->nbr.p, h->nnbr.p, h->box, h->boxf, h->pairs[0], h->pairsf[0],
                       h->table_d.p, h->tablef_d.p, h->n_types, fa.ax, fa.ay, fa.az, out[0], out[1], out[2],
                       h->partials.p, h->ticket, rec};
-        if (h->force_variant == 4) {
+        // systems that cannot fill the GPU with one thread per atom: S lanes per atom (force_variant 6 forces S = 8)
+        const int split = h->force_variant == 6 ? 8 : (h->force_variant == 0 ? (h->n <= 32768 ? 8 : (h->n <= 75000 ? 4 : 0)) : 0);
+        if (split) {
+            const int nbs = nblk(h->n * split, TPB_FORCE);
+            if (split == 8) {
+                if (multi) k_force_split<true, 8><<<nbs, TPB_FORCE, 0, st>>>(f2);
+                else k_force_split<false, 8><<<nbs, TPB_FORCE, 0, st>>>(f2);
+            } else {
+                if (multi) k_force_split<true, 4><<<nbs, TPB_FORCE, 0, st>>>(f2);
+                else k_force_split<false, 4><<<nbs, TPB_FORCE, 0, st>>>(f2);
+            }
+        } else if (h->force_variant == 4) {
             static bool attr_set = false;
             if (!attr_set) {
                 cudaFuncSetAttribute(k_force_v4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(V4Smem));

@@ -26,6 +26,7 @@ VARIANTS = {
     5: (4, 2, 1),         # v4: TMA-staged shared-memory cell tile (prototype)
     6: (3, 3, 1),         # v3 force + v3 build (packed-FP32 pair records, bit-mask append) == the defaults, explicit
     7: (3, 3, 2),         # v3 build with half-size cells (5^3 stencil)
+    8: (6, 3, 2),         # k_force_split<8>: 8 lanes per atom (the automatic choice below 32k atoms)
 }
 
 

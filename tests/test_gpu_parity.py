@@ -18,7 +18,7 @@ def _jittered(ncell, jitter=0.15, temperature=30.0, seed=7):
     return fcc_argon(ncell, temperature=temperature, seed=seed, jitter=jitter)
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7, 8])
 @pytest.mark.parametrize("ncell,skin", [(10, 0.0), (10, SKIN), (16, SKIN)])
 def test_compute_potential_parity(ncell, skin, variant):
     atoms = _jittered(ncell)
