@@ -308,7 +308,9 @@ __global__ void __launch_bounds__(TPB, 4) k_vv(VVArgs a) {
 // ------------------------------------------------------------------------------------------------
 struct NhcDev {
     pisb_nhc c;
-    double scale;  // exp(-0.5 dt xi[0]) of the current step
+    double scale;          // exp(-0.5 dt xi[0]) of the current step
+    double ke_last;        // kinetic energy the next first half step starts from (graph replays carry it on the device)
+    long long step_index;  // index of the step in progress (graph replays: the ramp index advances on the device)
 };
 
 __global__ void k_nhc_half(NhcDev *nhc, const double *ke_ptr, long long n_atoms, double dt, int second_half,
@@ -316,7 +318,8 @@ __global__ void k_nhc_half(NhcDev *nhc, const double *ke_ptr, long long n_atoms,
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     pisb_nhc &c = nhc->c;
     const double KB = 0.0083144621;  // src/constants.rs:3
-    const double ke = *ke_ptr;
+    const double ke = ke_ptr ? *ke_ptr : nhc->ke_last;  // null: carried on the device
+    if (step_index < 0) step_index = nhc->step_index;   // negative: device-resident step counter
     // compute_forces (:59-69)
     c.g[0] = __dsub_rn(__dmul_rn(2.0, ke), __dmul_rn(__dmul_rn((double)(n_atoms * 3), KB), c.target_temperature));
     for (int j = 1; j < 3; ++j)
@@ -328,6 +331,8 @@ __global__ void k_nhc_half(NhcDev *nhc, const double *ke_ptr, long long n_atoms,
     if (!second_half) {
         nhc->scale = exp(__dmul_rn(__dmul_rn(-0.5, dt), c.xi[0]));  // potential.rs:45
     } else {
+        nhc->ke_last = ke;
+        nhc->step_index = step_index + 1;
         // Simulation::step: calculate_target_temperature(i, steps) (simulation.rs:55; nvt.rs:114-123)
         c.target_temperature = __dadd_rn(c.start_temperature,
                                          __dmul_rn(__ddiv_rn(__dsub_rn(c.end_temperature, c.start_temperature), (double)total_steps),

@@ -135,6 +135,7 @@ struct pisb_handle {
     // CUDA graphs of NVE step batches (single GPU): the rebuild chain sits in a device-side conditional node
     struct StepGraph {
         int m = 0;
+        int64_t nvt_total = 0;     // 0: NVE steps; > 0: NVT steps with this ramp length
         const void *f0 = nullptr;  // which of the two force buffers held F(t) when the batch was captured
         cudaGraphExec_t exec = nullptr;
     };
@@ -880,7 +881,8 @@ void graph_signature(pisb_t *h, double dt, std::vector<unsigned char> &sig) {
                           std::min<const void *>(h->f[2].p, h->g[2].p), std::max<const void *>(h->f[2].p, h->g[2].p), h->xb[0].p, h->xb[1].p, h->xb[2].p, h->s_v[0].p,
                           h->s_v[1].p, h->s_v[2].p, h->s_f[0].p, h->s_f[1].p, h->s_f[2].p, h->id.p, h->s_id.p,
                           h->slot_of_id.p, h->cell_of.p, h->order.p, h->nnbr.p, h->nbr.p, h->cell_count.p, h->cell_start.p,
-                          h->tile_sum.p, h->mass_d.p, h->partials.p, h->table_d.p, h->thermo_d.p, h->flags, h->ticket};
+                          h->tile_sum.p, h->mass_d.p, h->partials.p, h->table_d.p, h->thermo_d.p, h->flags, h->ticket, h->nhc_d.p,
+                          h->nhc_energy_d.p};
     put(ptrs, sizeof ptrs);
     const int ints[] = {h->n, h->npad, h->kcap, h->n_types, h->force_variant, h->build_variant, h->cell_div};
     put(ints, sizeof ints);
@@ -898,12 +900,15 @@ void graph_signature(pisb_t *h, double dt, std::vector<unsigned char> &sig) {
 }
 
 // Executable graph of m NVE steps on records thermo_d[0..m) (m even: the f/g swap returns to the captured assignment).
-int capture_nve_graph(pisb_t *h, double dt, int m) {
+int enqueue_nvt_steps(pisb_t *h, double dt, int64_t cnt, int64_t total_steps, pisb_thermo *rec0, double *energy0);
+
+int capture_step_graph(pisb_t *h, double dt, int m, int64_t nvt_total) {
     if (!h->graph_stream) CUDA_TRY(h, cudaStreamCreateWithFlags(&h->graph_stream, cudaStreamNonBlocking));
     const int64_t launches_before = h->n_launches;
     CUDA_TRY(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
     h->capturing = true;
-    const int rc = enqueue_nve_steps(h, dt, m, h->thermo_d.p);
+    const int rc = nvt_total > 0 ? enqueue_nvt_steps(h, dt, m, nvt_total, h->thermo_d.p, h->nhc_energy_d.p)
+                                 : enqueue_nve_steps(h, dt, m, h->thermo_d.p);
     h->capturing = false;
     h->n_launches = launches_before;  // captured, not launched
     cudaGraph_t graph = nullptr;
@@ -920,6 +925,7 @@ int capture_nve_graph(pisb_t *h, double dt, int m) {
     if (ei != cudaSuccess) return fail(h, PISB_ERR_CUDA, fmt("cudaGraphInstantiate: %s", cudaGetErrorString(ei)));
     pisb_handle::StepGraph sg;
     sg.m = m;
+    sg.nvt_total = nvt_total;
     sg.f0 = h->f[0].p;
     sg.exec = exec;
     h->graphs.push_back(sg);
@@ -930,7 +936,7 @@ constexpr int GRAPH_M = 8;  // steps per replay; batches are cut into pieces of 
 
 // All piece sizes are captured together the first time a (state signature, f/g assignment) pair is seen, so the one-off
 // capture + instantiation cost (~1 ms per captured step) is paid in the first batch, not whenever a new remainder shows up.
-int get_nve_graph(pisb_t *h, double dt, int m, cudaGraphExec_t *out) {
+int get_step_graph(pisb_t *h, double dt, int m, int64_t nvt_total, cudaGraphExec_t *out) {
     std::vector<unsigned char> sig;
     graph_signature(h, dt, sig);
     if (sig != h->graph_sig) {
@@ -939,12 +945,14 @@ int get_nve_graph(pisb_t *h, double dt, int m, cudaGraphExec_t *out) {
     }
     for (int pass = 0; pass < 2; ++pass) {
         for (auto &g : h->graphs)
-            if (g.m == m && g.f0 == h->f[0].p) {
+            if (g.m == m && g.nvt_total == nvt_total && g.f0 == h->f[0].p) {
                 *out = g.exec;
                 return PISB_OK;
             }
-        if (pass == 0)
-            for (int mm = GRAPH_M; mm >= 2; mm /= 2) TRY(capture_nve_graph(h, dt, mm));
+        if (pass == 0) {
+            if (h->graphs.size() > 24) drop_graphs(h);
+            for (int mm = GRAPH_M; mm >= 2; mm /= 2) TRY(capture_step_graph(h, dt, mm, nvt_total));
+        }
     }
     return fail(h, PISB_ERR_STATE, "no graph for this batch size");
 }
@@ -970,7 +978,7 @@ int do_step_nve(pisb_t *h, double dt, int64_t nsteps, pisb_thermo *out) {
             if (graphs && piece >= 2) {
                 piece = piece >= GRAPH_M ? GRAPH_M : (piece >= 4 ? 4 : 2);
                 cudaGraphExec_t exec = nullptr;
-                TRY(get_nve_graph(h, dt, (int)piece, &exec));
+                TRY(get_step_graph(h, dt, (int)piece, 0, &exec));
                 CUDA_TRY(h, cudaGraphLaunch(exec, h->stream));
                 h->n_graph_launches++;
                 graph_steps += piece;
@@ -1010,7 +1018,26 @@ int do_step_nve(pisb_t *h, double dt, int64_t nsteps, pisb_thermo *out) {
 
 
 
-// NVT batch: verlet_step_nvt_nhc x nsteps with the chain on the device (see k_nhc_half).
+// NVT batch: verlet_step_nvt_nhc x nsteps with the chain on the device (see k_nhc_half).  The kinetic energy a first half
+// step starts from and the ramp's step index are carried in NhcDev, so a step sequence is the same launch list for every
+// step and can be replayed as a graph (same 8 / 4 / 2 pieces and conditional rebuild node as the NVE batches).
+int enqueue_nvt_steps(pisb_t *h, double dt, int64_t cnt, int64_t total_steps, pisb_thermo *rec0, double *energy0) {
+    for (int64_t s = 0; s < cnt; ++s) {
+        pisb_thermo *rec = rec0 + s;
+        k_nhc_half<<<1, 32, 0, h->stream>>>(h->nhc_d.p, nullptr, (long long)h->n, dt, 0, -1, 1, nullptr);
+        TRY(launch_vv(h, false, true, dt, nullptr, &h->nhc_d.p->scale));
+        if (h->capturing) TRY(capture_conditional_rebuild(h));
+        else TRY(launch_rebuild_chain(h));
+        double *outp[3] = {h->g[0].p, h->g[1].p, h->g[2].p};
+        TRY(launch_force(h, outp, nullptr, rec));
+        for (int d = 0; d < 3; ++d) std::swap(h->f[d], h->g[d]);
+        TRY(launch_vv(h, true, false, dt, rec, &h->nhc_d.p->scale));
+        k_nhc_half<<<1, 32, 0, h->stream>>>(h->nhc_d.p, &rec->ke, (long long)h->n, dt, 1, -1, (long long)total_steps, energy0 + s);
+        h->n_launches += 2;
+    }
+    return check_launch(h, "nvt step");
+}
+
 int do_step_nvt(pisb_t *h, double dt, int64_t nsteps, pisb_nhc *chain, int64_t first_step, int64_t total_steps,
                 pisb_thermo *out, double *nhc_energy) {
     if (!h->have_atoms || !h->have_box) return fail(h, PISB_ERR_STATE, "set_box and upload must precede step_nvt_nhc");
@@ -1020,48 +1047,57 @@ int do_step_nvt(pisb_t *h, double dt, int64_t nsteps, pisb_nhc *chain, int64_t f
     if (nsteps == 0) return PISB_OK;
     TRY(ensure_list(h));
     TRY(check_bad_type(h));
+    const int64_t chunk_max = 4096;
     TRY(dev_reserve(h, h->nhc_d, 1));
+    TRY(dev_reserve(h, h->nhc_energy_d, (size_t)chunk_max));
+    TRY(reserve_thermo(h, (size_t)chunk_max + 1));
+    {
+        // KE of the state entering the batch (potential.rs:41), reduced on the device, seeds the carried value
+        pisb_thermo *ke0 = h->thermo_d.p + chunk_max;
+        LaunchScope ls(h, PISB_K_REDUCE);
+        k_observe<<<nblk(h->n, TPB), TPB, 0, h->stream>>>(h->n, h->xt.p, h->v[0].p, h->v[1].p, h->v[2].p, h->f[0].p, h->f[1].p,
+                                                          h->f[2].p, h->mass_d.p, h->partials.p, h->ticket, ke0);
+        TRY(check_launch(h, "k_observe"));
+        CUDA_TRY(h, cudaMemcpyAsync(h->h_thermo, ke0, sizeof(pisb_thermo), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    }
     NhcDev init{};
     init.c = *chain;
     init.scale = 1.0;
+    init.ke_last = h->h_thermo[0].ke;
+    init.step_index = first_step;
     CUDA_TRY(h, cudaMemcpyAsync(h->nhc_d.p, &init, sizeof init, cudaMemcpyHostToDevice, h->stream));
-    const int64_t chunk_max = 4096;
+    const bool graphs = h->use_graphs && !h->profiling;
     int64_t done = 0;
     std::vector<double> he;
     while (done < nsteps) {
         const int64_t m = std::min(chunk_max, nsteps - done);
-        TRY(reserve_thermo(h, (size_t)m + 2));
-        TRY(dev_reserve(h, h->nhc_energy_d, (size_t)m));
-        pisb_thermo *ke0 = h->thermo_d.p + m;  // scratch record: KE of the state entering the batch
-        {
-            LaunchScope ls(h, PISB_K_REDUCE);
-            k_observe<<<nblk(h->n, TPB), TPB, 0, h->stream>>>(h->n, h->xt.p, h->v[0].p, h->v[1].p, h->v[2].p, h->f[0].p, h->f[1].p,
-                                                              h->f[2].p, h->mass_d.p, h->partials.p, h->ticket, ke0);
-            TRY(check_launch(h, "k_observe"));
-        }
-        for (int64_t s = 0; s < m; ++s) {
-            pisb_thermo *rec = h->thermo_d.p + s;
-            const double *ke_in = s == 0 ? &ke0->ke : &(rec - 1)->ke;
-            k_nhc_half<<<1, 32, 0, h->stream>>>(h->nhc_d.p, ke_in, (long long)h->n, dt, 0, 0, 1, nullptr);
-            TRY(launch_vv(h, false, true, dt, nullptr, &h->nhc_d.p->scale));
-            TRY(launch_rebuild_chain(h));
-            double *outp[3] = {h->g[0].p, h->g[1].p, h->g[2].p};
-            TRY(launch_force(h, outp, nullptr, rec));
-            for (int d = 0; d < 3; ++d) std::swap(h->f[d], h->g[d]);
-            TRY(launch_vv(h, true, false, dt, rec, &h->nhc_d.p->scale));
-            k_nhc_half<<<1, 32, 0, h->stream>>>(h->nhc_d.p, &rec->ke, (long long)h->n, dt, 1, (long long)(first_step + done + s),
-                                                (long long)total_steps, h->nhc_energy_d.p + s);
-            h->n_launches += 2;
-        }
-        TRY(check_launch(h, "nvt step"));
-        CUDA_TRY(h, cudaMemcpyAsync(h->h_thermo, h->thermo_d.p, sizeof(pisb_thermo) * m, cudaMemcpyDeviceToHost, h->stream));
         he.resize((size_t)m);
-        CUDA_TRY(h, cudaMemcpyAsync(he.data(), h->nhc_energy_d.p, sizeof(double) * m, cudaMemcpyDeviceToHost, h->stream));
+        const int builds_before = (int)h->n_builds_host;
+        int64_t off = 0, graph_steps = 0;
+        while (off < m) {
+            int64_t piece = m - off;
+            if (graphs && piece >= 2) {
+                piece = piece >= GRAPH_M ? GRAPH_M : (piece >= 4 ? 4 : 2);
+                cudaGraphExec_t exec = nullptr;
+                TRY(get_step_graph(h, dt, (int)piece, total_steps, &exec));
+                CUDA_TRY(h, cudaGraphLaunch(exec, h->stream));
+                h->n_graph_launches++;
+                graph_steps += piece;
+                h->n_launches += 6 * piece;  // 2 chain + 2 integrator + condition + force per step
+            } else {
+                TRY(enqueue_nvt_steps(h, dt, piece, total_steps, h->thermo_d.p, h->nhc_energy_d.p));
+            }
+            CUDA_TRY(h, cudaMemcpyAsync(h->h_thermo + off, h->thermo_d.p, sizeof(pisb_thermo) * piece, cudaMemcpyDeviceToHost, h->stream));
+            CUDA_TRY(h, cudaMemcpyAsync(he.data() + off, h->nhc_energy_d.p, sizeof(double) * piece, cudaMemcpyDeviceToHost, h->stream));
+            off += piece;
+        }
         TRY(read_flags(h));
         if (h->h_flags[FLAG_NBUILDS] != h->n_builds_host) {
             h->n_builds_host = h->h_flags[FLAG_NBUILDS];
             h->max_nbr = h->h_flags[FLAG_MAXNBR];
         }
+        if (graph_steps > 0) h->n_launches += 10 * (int64_t)((int)h->n_builds_host - builds_before);
         if (h->h_flags[FLAG_MAXNBR] > h->kcap) {
             h->list_valid = false;
             return fail(h, PISB_ERR_CAPACITY, "a neighbour list overflowed during the batch; re-upload the state and repeat the call");
