@@ -993,7 +993,9 @@ __device__ __forceinline__ void force3_body(const Force2Args &a, int i, double &
                 p = a.table[(min(ti, tj) - 1) * a.n_types + (max(ti, tj) - 1)];
                 in[u] = in[u] && p.present;
             }
-            if (in[u] && !(r2[u] > p.t_rc)) {
+            // `rij.norm() > rcut -> skip` as r2 > T; r2 and T are non-negative doubles, whose order is the order of their
+            // bit patterns: an integer compare keeps this test off the saturated FP64 pipe
+            if (in[u] && __double_as_longlong(r2[u]) <= __double_as_longlong(p.t_rc)) {
                 double uu, fs;
                 lj_pair(p, r2[u], uu, fs);
                 PISB_ACCUM(dx[u], dy[u], dz[u], r2[u], uu, fs);

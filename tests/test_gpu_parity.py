@@ -335,6 +335,38 @@ def test_gpu_matches_committed_golden_vectors():
     assert np.abs(atoms.positions - np.array(g["positions_end"])).max() < 1e-10
 
 
+def test_gpu_matches_committed_ensemble_golden_vectors():
+    """tests/golden/oracle_small_ensembles.json: 25 NVT and 25 NPT steps of the golden system, without running the oracle."""
+    import json
+    import os
+
+    gd = os.path.join(os.path.dirname(__file__), "golden")
+    with open(os.path.join(gd, "oracle_small.json")) as f:
+        g = json.load(f)
+    with open(os.path.join(gd, "oracle_small_ensembles.json")) as f:
+        e = json.load(f)
+    table = {(1, 1): LennardJones(g["eps"], g["sigma"], g["rc"], True)}
+    for ens in ("nvt", "npt"):
+        box = SimulationBox.from_lammps_data(0, g["L"], 0, g["L"], 0, g["L"])
+        atoms = Atoms(g["types"], [g["mass"]], g["positions"], box, velocities=g["velocities"])
+        mgr = make_manager(skin=g["skin"], table=table)
+        mgr.attach(atoms)
+        mgr.compute()
+        chain = mgr.nhc_new(*e["temp"])
+        ref = np.array(e[ens + "_thermo"])
+        if ens == "nvt":
+            th, en = mgr.step_nvt_nhc(g["dt"], e["steps"], chain, 0, e["steps"])
+        else:
+            baro = mgr.mtk_new(e["iso"][0], e["iso"][1], atoms.n_atoms, e["temp"][0])
+            th, en, hh = mgr.step_npt_mtk(g["dt"], e["steps"], baro, chain, 0, e["steps"], atoms)
+            h_ref = np.array(e["npt_h"])[1:].reshape(-1, 3, 3).transpose(0, 2, 1)
+            assert np.abs(hh - h_ref).max() <= 1e-9 * np.abs(h_ref).max()
+            assert np.abs(np.array(baro.momentum) - np.array(e["npt_momentum"])).max() <= 1e-8 * np.abs(np.array(e["npt_momentum"])).max()
+        assert np.max(np.abs(th["pe"] - ref[1:, 0]) / np.abs(ref[1:, 0])) <= ENERGY_TOL
+        assert np.max(np.abs(th["ke"] - ref[1:, 1]) / np.abs(ref[1:, 1])) <= ENERGY_TOL
+        assert np.max(np.abs(th["pe"] + th["ke"] + en - ref[1:, 2]) / np.abs(ref[1:, 2])) <= ENERGY_TOL
+
+
 @pytest.mark.parametrize("halo_mode", [2, 1])
 def test_multi_gpu_equals_single_gpu(halo_mode):
     """2-rank spatially decomposed run == 1-GPU run (neighbour sets exact per global id, forces 1e-10,

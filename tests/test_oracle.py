@@ -221,6 +221,27 @@ def test_golden_vectors():
     assert np.array_equal(x, np.array(g["positions_end"]))
 
 
+def test_golden_ensemble_vectors():
+    """tests/golden/oracle_small_ensembles.json pins the NVT / NPT restatements (nvt.rs, npt.rs, potential.rs:35-135)."""
+    with open(os.path.join(GOLDEN, "oracle_small.json")) as f:
+        g = json.load(f)
+    with open(os.path.join(GOLDEN, "oracle_small_ensembles.json")) as f:
+        e = json.load(f)
+    pos, vel, types = np.array(g["positions"]), np.array(g["velocities"]), np.array(g["types"], dtype=np.int32)
+    o = make(g["L"], g["rc"])
+    chain = o.nhc_new(*e["temp"])
+    th = o.run_nvt(pos.copy(), vel.copy(), np.zeros_like(pos), types, g["dt"], e["steps"], chain)
+    assert np.array_equal(th, np.array(e["nvt_thermo"])) and list(chain.xi) == e["nvt_xi"]
+    o = make(g["L"], g["rc"])
+    chain = o.nhc_new(*e["temp"])
+    baro = o.mtk_new(e["iso"][0], e["iso"][1], len(pos), e["temp"][0])
+    x = pos.copy()
+    th, htr = o.run_npt(x, vel.copy(), np.zeros_like(pos), types, g["dt"], e["steps"], baro, chain)
+    assert np.array_equal(th, np.array(e["npt_thermo"])) and np.array_equal(htr, np.array(e["npt_h"]))
+    assert list(baro.momentum) == e["npt_momentum"] and np.array_equal(x, np.array(e["npt_positions_end"]))
+    assert abs(htr[-1][0] - htr[0][0]) > 1e-3      # the barostat moved the box in 25 steps
+
+
 def test_mat3_exp_restatement_against_scipy():
     """nalgebra Matrix3::exp restated (Al-Mohy & Higham 2009) vs scipy.linalg.expm over every Pade branch."""
     import scipy.linalg as sl
