@@ -934,8 +934,9 @@ int capture_step_graph(pisb_t *h, double dt, int m, int64_t nvt_total) {
 
 constexpr int GRAPH_M = 8;  // steps per replay; batches are cut into pieces of 8, 4, 2 (and a classic single step)
 
-// All piece sizes are captured together the first time a (state signature, f/g assignment) pair is seen, so the one-off
-// capture + instantiation cost (~1 ms per captured step) is paid in the first batch, not whenever a new remainder shows up.
+// All piece sizes, for both assignments of the force buffers, are captured together the first time a state signature is
+// seen, so the one-off capture + instantiation cost (~1 ms per captured step, ~30 ms in all) is paid in the first batch,
+// not whenever a new remainder or an odd step count shows up.
 int get_step_graph(pisb_t *h, double dt, int m, int64_t nvt_total, cudaGraphExec_t *out) {
     std::vector<unsigned char> sig;
     graph_signature(h, dt, sig);
@@ -951,7 +952,11 @@ int get_step_graph(pisb_t *h, double dt, int m, int64_t nvt_total, cudaGraphExec
             }
         if (pass == 0) {
             if (h->graphs.size() > 24) drop_graphs(h);
-            for (int mm = GRAPH_M; mm >= 2; mm /= 2) TRY(capture_step_graph(h, dt, mm, nvt_total));
+            // both assignments of the two force buffers (an odd classic step flips it), so that no later batch pays
+            for (int parity = 0; parity < 2; ++parity) {
+                for (int mm = GRAPH_M; mm >= 2; mm /= 2) TRY(capture_step_graph(h, dt, mm, nvt_total));
+                for (int d = 0; d < 3; ++d) std::swap(h->f[d], h->g[d]);
+            }
         }
     }
     return fail(h, PISB_ERR_STATE, "no graph for this batch size");
