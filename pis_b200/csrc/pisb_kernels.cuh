@@ -854,6 +854,7 @@ struct Force2Args {
     double *partials;
     unsigned int *ticket;
     pisb_thermo *thermo;
+    const int *skip_flag;  // multi-GPU: the launch is speculative and returns at once if *skip_flag != 0 (a rebuild comes first)
 };
 
 // One in-range pair, reference operation order (bit-identical per-pair terms).
@@ -1008,6 +1009,7 @@ __device__ __forceinline__ void force3_body(const Force2Args &a, int i, double &
 // 8 resident blocks/SM (64 registers, 32 warps): measured best, profiles/r01_force_launch_config.txt
 template <bool MULTI>
 __global__ void __launch_bounds__(TPB_FORCE, 8) k_force_v3(Force2Args a) {
+    if (a.skip_flag && *a.skip_flag != 0) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double red[2] = {0.0, 0.0};
     const bool active = i < a.n && !xf_is_ghost(a.xf[i]);
@@ -1084,6 +1086,7 @@ __device__ __forceinline__ void force_split_body(const Force2Args &a, int i, int
 
 template <bool MULTI, int S>
 __global__ void __launch_bounds__(TPB_FORCE) k_force_split(Force2Args a) {
+    if (a.skip_flag && *a.skip_flag != 0) return;
     const int gt = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = gt / S, l = gt % S;
     double red[2] = {0.0, 0.0};

@@ -580,7 +580,7 @@ int launch_rebuild_chain(pisb_t *h) {
 }
 
 // f_out = (acc ? acc + LJ : LJ); thermo record gets pe and virial_pair.
-int launch_force(pisb_t *h, double *const out[3], const double *const acc[3], pisb_thermo *rec) {
+int launch_force(pisb_t *h, double *const out[3], const double *const acc[3], pisb_thermo *rec, const int *skip_flag = nullptr) {
     LaunchScope ls(h, PISB_K_FORCE);
     ForceArgs fa{h->n, h->npad, h->xt.p, h->nbr.p, h->nnbr.p, h->box, h->pairs[0], h->table_d.p, h->n_types,
                  acc ? acc[0] : nullptr, acc ? acc[1] : nullptr, acc ? acc[2] : nullptr,
@@ -593,7 +593,10 @@ int launch_force(pisb_t *h, double *const out[3], const double *const acc[3], pi
         if (!v2_possible(h)) return fail(h, PISB_ERR_INVALID, "force_variant 2/3 needs an orthorhombic, fully periodic box");
         Force2Args f2{h->n, h->npad, h->xt.p, h->xf.p, h->nbr.p, h->nnbr.p, h->box, h->boxf, h->pairs[0], h->pairsf[0],
                       h->table_d.p, h->tablef_d.p, h->n_types, fa.ax, fa.ay, fa.az, out[0], out[1], out[2],
-                      h->partials.p, h->ticket, rec};
+                      h->partials.p, h->ticket, rec, skip_flag};
+        // only the default kernels honour skip_flag
+        if (skip_flag && h->force_variant != 0 && h->force_variant != 3 && h->force_variant != 6)
+            return fail(h, PISB_ERR_STATE, "speculative force launch needs force_variant 0, 3 or 6");
         // systems that cannot fill the GPU with one thread per atom: S lanes per atom (force_variant 6 forces S = 8)
         const int split = h->force_variant == 6 ? 8 : (h->force_variant == 0 ? (h->n <= 32768 ? 8 : (h->n <= 75000 ? 4 : 0)) : 0);
         if (split) {
@@ -1747,20 +1750,34 @@ int do_step_nve_multi(pisb_t *h, double dt, int64_t nsteps, pisb_thermo *out) {
             if (s == 0) TRY(launch_vv(h, false, true, dt, nullptr));
             else TRY(launch_vv(h, true, true, dt, rec - 1));
             double t1 = wall_now();
-            // every rank must take the same branch: max-reduce the skin trigger, then read it
             // every rank must take the same branch: the skin-trigger flags ride along with the ghost exchange and
             // are max-reduced by k_halo_unpack; the host then reads the decision.  On a rebuild step the ghost
             // exchange is merely redundant (the rebuild re-selects the ghosts).
             TRY(halo_exchange(h, true));
-            CUDA_TRY(h, cudaMemcpyAsync(h->h_flags, h->flags, sizeof(int) * FLAG_COUNT, cudaMemcpyDeviceToHost, h->stream));
-            CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+            // The force kernel is launched BEFORE the host knows the decision: it returns at once if the (now global) rebuild
+            // flag is set, and the flag travels to the host on a second stream meanwhile -- on the ~80 % of steps without a
+            // rebuild the GPU never waits for the host round trip.
+            const bool speculate = v2_possible(h) && (h->force_variant == 0 || h->force_variant == 3 || h->force_variant == 6);
+            double *outp[3] = {h->g[0].p, h->g[1].p, h->g[2].p};
+            if (speculate) {
+                CUDA_TRY(h, cudaEventRecord(h->ev_pos, h->stream));
+                CUDA_TRY(h, cudaStreamWaitEvent(h->copy_stream, h->ev_pos, 0));
+                CUDA_TRY(h, cudaMemcpyAsync(h->h_flags, h->flags, sizeof(int) * FLAG_COUNT, cudaMemcpyDeviceToHost, h->copy_stream));
+                TRY(launch_force(h, outp, nullptr, rec, h->flags + FLAG_REBUILD));
+                const size_t spec_ev = h->ev_used;  // profiling: event pair of the speculative launch is ev_pool[spec_ev - 1]
+                CUDA_TRY(h, cudaStreamSynchronize(h->copy_stream));
+                // a launch that turned out to be a no-op is not a force evaluation: book it under the (tiny) reduce class
+                if (h->profiling && spec_ev > 0 && h->h_flags[FLAG_REBUILD] != 0) h->ev_pool[spec_ev - 1].cls = PISB_K_REDUCE;
+            } else {
+                CUDA_TRY(h, cudaMemcpyAsync(h->h_flags, h->flags, sizeof(int) * FLAG_COUNT, cudaMemcpyDeviceToHost, h->stream));
+                CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+            }
             double t2 = wall_now();
             if (h->h_flags[FLAG_COMM_TIMEOUT]) return fail(h, PISB_ERR_COMM, "timed out waiting for a peer's ghost data (peer-memory halo)");
             const bool reb = h->h_flags[FLAG_REBUILD] != 0;
             if (reb) TRY(multi_rebuild(h));
             double t3 = wall_now();
-            double *outp[3] = {h->g[0].p, h->g[1].p, h->g[2].p};
-            TRY(launch_force(h, outp, nullptr, rec));
+            if (reb || !speculate) TRY(launch_force(h, outp, nullptr, rec));
             for (int d = 0; d < 3; ++d) std::swap(h->f[d], h->g[d]);
             double t4 = wall_now();
             t_vv += t1 - t0;
