@@ -77,20 +77,24 @@ def run(args):
     st1 = mgr.stats()
     value = n_global * args.steps / (ms_total * 1e-3)
 
-    # ---- end to end: per-step call with a host read of the thermo record, owned state back every 10 steps ----
+    # ---- end to end: the Simulation::run loop of the host -- one batch per dump interval, thermo records back with the
+    #      batch, the owned POSITIONS (+ global ids: what DumpTraj::write_step needs) back on dump steps ----
     e2e_steps = max(10, min(args.e2e_steps, args.steps))
-    mgr.download_owned()  # untimed: allocates the pinned destination buffers that every later call reuses
-    mgr.step_nve(B.DT, 1)
+    mgr.download_owned(velocities=False, forces=False)  # untimed: allocates the pinned destination buffers that every later call reuses
+    mgr.step_nve(B.DT, 10)
     dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     d2h = 0
-    for s in range(e2e_steps):
-        mgr.step_nve(B.DT, 1)
-        d2h += 32
-        if (s + 1) % 10 == 0:
-            g_, x_, v_, f_ = mgr.download_owned()
-            d2h += x_.nbytes + v_.nbytes + f_.nbytes + g_.nbytes
+    s = 0
+    while s < e2e_steps:
+        chunk = min(10, e2e_steps - s)                       # dump cadence of example/input.pis
+        mgr.step_nve(B.DT, chunk)
+        d2h += 32 * chunk
+        s += chunk
+        if s % 10 == 0:
+            g_, x_, v_, f_ = mgr.download_owned(velocities=False, forces=False)
+            d2h += x_.nbytes + g_.nbytes
     mgr.synchronize()
     dist.barrier()
     e2e_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64)
@@ -122,8 +126,9 @@ def run(args):
             "clocks": clk.summary(),
             "e2e": {"value": n_global * e2e_steps / e2e_s, "unit": B.UNIT, "h2d_bytes_per_step": h2d_total // max(args.steps + e2e_steps + args.warmup, 1),
                     "d2h_bytes_per_step": d2h // e2e_steps, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
-                    "call": "per rank: pisb_step_nve(dt, 1) with the thermo record read on the host every step and "
-                            "pisb_download_owned (x, v, F, ids) every 10 steps (the example's dump cadence); state is uploaded once"},
+                    "call": "per rank: pisb_step_nve(dt, steps to the next dump) returning one thermo record per step and "
+                            "pisb_download_owned (positions + global ids) every 10 steps (the example's dump cadence); "
+                            "state is uploaded once"},
             "gpu_launches": int(st1["n_launches"] - st0["n_launches"]),
             "roofline": {"kernel": "k_force_v3", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_kind, "mean_neighbours": nn_mean,
