@@ -956,10 +956,14 @@ int get_step_graph(pisb_t *h, double dt, int m, int64_t nvt_total, cudaGraphExec
         if (pass == 0) {
             if (h->graphs.size() > 24) drop_graphs(h);
             // both assignments of the two force buffers (an odd classic step flips it), so that no later batch pays
-            for (int parity = 0; parity < 2; ++parity) {
-                for (int mm = GRAPH_M; mm >= 2; mm /= 2) TRY(capture_step_graph(h, dt, mm, nvt_total));
+            int rc = PISB_OK;
+            for (int parity = 0; parity < 2 && rc == PISB_OK; ++parity) {
+                for (int mm = GRAPH_M; mm >= 2 && rc == PISB_OK; mm /= 2) rc = capture_step_graph(h, dt, mm, nvt_total);
                 for (int d = 0; d < 3; ++d) std::swap(h->f[d], h->g[d]);
+                if (rc != PISB_OK && parity == 0)  // leave the buffers as they were
+                    for (int d = 0; d < 3; ++d) std::swap(h->f[d], h->g[d]);
             }
+            if (rc != PISB_OK) return rc;
         }
     }
     return fail(h, PISB_ERR_STATE, "no graph for this batch size");
@@ -983,10 +987,19 @@ int do_step_nve(pisb_t *h, double dt, int64_t nsteps, pisb_thermo *out) {
         int64_t off = 0, graph_steps = 0;
         while (off < m) {
             int64_t piece = m - off;
-            if (graphs && piece >= 2) {
-                piece = piece >= GRAPH_M ? GRAPH_M : (piece >= 4 ? 4 : 2);
-                cudaGraphExec_t exec = nullptr;
-                TRY(get_step_graph(h, dt, (int)piece, 0, &exec));
+            cudaGraphExec_t exec = nullptr;
+            if (graphs && h->use_graphs && piece >= 2) {
+                const int gm = piece >= GRAPH_M ? GRAPH_M : (piece >= 4 ? 4 : 2);
+                if (get_step_graph(h, dt, gm, 0, &exec) == PISB_OK) {
+                    piece = gm;
+                } else {  // e.g. a driver without conditional graph nodes: same kernels, classic launches from now on
+                    h->use_graphs = 0;
+                    exec = nullptr;
+                    drop_graphs(h);
+                    cudaGetLastError();
+                }
+            }
+            if (exec) {
                 CUDA_TRY(h, cudaGraphLaunch(exec, h->stream));
                 h->n_graph_launches++;
                 graph_steps += piece;
@@ -1085,10 +1098,19 @@ int do_step_nvt(pisb_t *h, double dt, int64_t nsteps, pisb_nhc *chain, int64_t f
         int64_t off = 0, graph_steps = 0;
         while (off < m) {
             int64_t piece = m - off;
-            if (graphs && piece >= 2) {
-                piece = piece >= GRAPH_M ? GRAPH_M : (piece >= 4 ? 4 : 2);
-                cudaGraphExec_t exec = nullptr;
-                TRY(get_step_graph(h, dt, (int)piece, total_steps, &exec));
+            cudaGraphExec_t exec = nullptr;
+            if (graphs && h->use_graphs && piece >= 2) {
+                const int gm = piece >= GRAPH_M ? GRAPH_M : (piece >= 4 ? 4 : 2);
+                if (get_step_graph(h, dt, gm, total_steps, &exec) == PISB_OK) {
+                    piece = gm;
+                } else {
+                    h->use_graphs = 0;
+                    exec = nullptr;
+                    drop_graphs(h);
+                    cudaGetLastError();
+                }
+            }
+            if (exec) {
                 CUDA_TRY(h, cudaGraphLaunch(exec, h->stream));
                 h->n_graph_launches++;
                 graph_steps += piece;
