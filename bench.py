@@ -172,6 +172,13 @@ def run_single(args):
     n = atoms.n_atoms
     mgr = LJCudaManager(skin=SKIN, device=0)
     mgr.insert((1, 1), LennardJones(0.238, SIGMA, RC, True))
+    options = {}
+    for kv in args.option:          # library options for A/B runs, e.g. --option fuse_vv=0
+        name, _, val = kv.partition("=")
+        options[name] = float(val)
+        mgr.set_option(name, float(val))
+    fv = options.get("force_variant", 0.0)   # mirrors fused_step_possible() of pisb_sim.cu
+    fused = options.get("fuse_vv", 1.0) != 0.0 and (fv == 3.0 or (fv == 0.0 and n > 75000))
     mgr.attach(atoms)
     mgr.compute()
     stream = torch.cuda.ExternalStream(mgr.stream_ptr)
@@ -209,13 +216,19 @@ def run_single(args):
     mgr.set_profiling(False)
     st2 = mgr.stats()
 
-    # ---- roofline of the dominant kernel (LJ force): algorithmic bytes = (48 + 4K) per atom ----
+    # ---- roofline of the dominant kernel.  Algorithmic bytes per atom: LJ force 48 + 4K; the fused step
+    #      kernel k_force_vv adds the integrator's streams: kick 72 (v read + write, F(t) read) and, on every launch but
+    #      the last of a batch, drift 72 (x_build read, x + FP32 shadow write) -> 192 + 4K ----
     peaks, peak_kind = measured_peaks()
     nn = np.zeros(n, dtype=np.int32)
     capi.check(mgr._h, capi.load().pisb_neighbours(mgr._h, capi._ptr(nn), None, 0))
     k_mean = float(nn.mean())
     f_ms = tim["force"]["ms"] / max(tim["force"]["launches"], 1)
-    bytes_per_launch = (48.0 + 4.0 * k_mean) * n
+    force_launches = max(tim["force"]["launches"], 1)
+    drift_frac = max(force_launches - 1, 0) / force_launches      # the profiled pass is one batch: its last launch does not drift
+    per_atom = 48.0 + 4.0 * k_mean + ((72.0 + 72.0 * drift_frac) if fused else 0.0)
+    bytes_per_launch = per_atom * n
+    kernel_name = "k_force_vv" if fused else "k_force_v3"
     achieved = bytes_per_launch / (f_ms * 1e-3) / 1e9
     peak = float(peaks.get("hbm_gbs", 6650.0))
     traffic, fp64_pct = None, None
@@ -224,24 +237,29 @@ def run_single(args):
         try:
             with open(tp) as f:
                 tj = json.load(f)
-            traffic, fp64_pct = tj.get("dram_bytes_per_launch"), tj.get("fp64_pipe_active_pct")
+            if str(tj.get("kernel", "")).startswith(kernel_name):    # a capture of another kernel says nothing about this one
+                traffic, fp64_pct = tj.get("dram_bytes_per_launch"), tj.get("fp64_pipe_active_pct")
         except Exception:
             traffic = None
-    roofline = {"kernel": "k_force_v3", "bound": "hbm", "timing": "per-launch CUDA events over the K steps that follow the timed "
+    roofline = {"kernel": kernel_name, "bound": "hbm", "timing": "per-launch CUDA events over the K steps that follow the timed "
                 "region (same state, same kernels; ms_per_step_profiled beside ms_per_step)",
                 "algorithmic_bytes_per_launch": bytes_per_launch,
                 "fp64_pipe_active_pct_ncu": fp64_pct, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_kind,
-                "algorithmic_bytes_per_atom": 48.0 + 4.0 * k_mean, "mean_neighbours": k_mean,
+                "algorithmic_bytes_per_atom": per_atom, "mean_neighbours": k_mean,
                 "ms_per_launch": f_ms, "share_of_step": tim["force"]["ms"] / ms_profiled,
-                "note": "the force kernel is bound by the FP64 pipe and L1TEX gather throughput, not by HBM (ncu: profiles/); "
+                "note": ("one launch per step: LJ force pass with the velocity-Verlet kick + drift in its epilogue; " if fused else "") +
+                        "the force pass is bound by the FP64 pipe and L1TEX gather throughput, not by HBM (ncu: profiles/); "
                         "frac is algorithmic HBM bytes / measured copy peak; traffic = ncu dram bytes per launch"}
     kernel_ms = {k: round(v["ms"] / args.steps, 5) for k, v in tim.items() if v["launches"]}
-    # the streaming kernel next to it: fused kick+drift moves 200 B/atom
+    # the streaming kernel next to it: k_vv<kick,drift> moves 200 B/atom per step; with the fused
+    # step kernel only the drift that opens a batch is left (x 32 + v 24 + F 24 + x_build 24 read, x 32 + shadow 16 written)
     vv_ms = tim["integrate"]["ms"] / max(tim["integrate"]["launches"], 1)
-    roofline_integrate = {"kernel": "k_vv<kick,drift>", "bound": "hbm", "achieved": 200.0 * n / (vv_ms * 1e-3) / 1e9, "peak": peak,
-                          "unit": "GB/s", "frac": 200.0 * n / (vv_ms * 1e-3) / 1e9 / peak, "ms_per_launch": vv_ms,
-                          "algorithmic_bytes_per_atom": 200.0}
+    vv_bytes = 152.0 if fused else 200.0
+    roofline_integrate = {"kernel": "k_vv<drift> (opens a batch)" if fused else "k_vv<kick,drift>", "bound": "hbm",
+                          "achieved": vv_bytes * n / (vv_ms * 1e-3) / 1e9, "peak": peak,
+                          "unit": "GB/s", "frac": vv_bytes * n / (vv_ms * 1e-3) / 1e9 / peak, "ms_per_launch": vv_ms,
+                          "launches": tim["integrate"]["launches"], "algorithmic_bytes_per_atom": vv_bytes}
 
     # ---- end-to-end: the reference-facing trait call with HOST buffers, every step ----
     e2e_steps = max(3, min(args.e2e_steps, args.steps))
@@ -302,6 +320,7 @@ def run_single(args):
         "kernel_ms_per_step": kernel_ms, "ms_per_step_profiled": ms_profiled / args.steps,
         "list_builds_in_timed_region": int(builds), "list_builds_in_profiled_pass": int(st2["n_builds"] - st1["n_builds"]),
         "launch_path": "CUDA graphs (8/4/2 steps per replay, conditional rebuild node); gpu_launches counts executed kernel nodes",
+        "options": options,
         "energy_drift_rel": float(np.abs(h - h[0]).max() / abs(h[0])),
         "stats": st1, "wall_s": time.perf_counter() - t_wall0,
     }
@@ -324,6 +343,7 @@ def main():
     ap.add_argument("--cpu-threads", type=int, default=0)
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--option", action="append", default=[], help="library option name=value (pisb_set_option), repeatable")
     ap.add_argument("--strong", action="store_true", help="N>1: run the 32M-atom system instead of 4M atoms per GPU")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":

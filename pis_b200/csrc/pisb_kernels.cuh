@@ -179,6 +179,96 @@ __global__ void __launch_bounds__(TPB) k_store_aos(StoreArgs a) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Chunked boundary kernels of the host-buffer step (pisb_verlet_step_nve_host): the trait call moves 288 MB each
+// way per step at 4M atoms, so the step is cut into chunks of the ORIGINAL atom order and pipelined over PCIe --
+// chunk c is drifted as soon as its x, v, F have arrived and its x(t+dt) travels back while chunk c+1 is still
+// on its way up (full duplex); after the force pass the velocities and forces leave chunk by chunk the same way.
+//   k_host_load_drift : k_load_aos (kept slot order) + k_vv<drift> for the ids [o0, o1); x(t+dt) also goes back
+//                       into the staging array, in place.  Arithmetic = k_vv's, operation for operation.
+//   k_store_range     : k_store_aos for the ids [o0, o1) (gather through slot_of_id, contiguous staging writes)
+// ------------------------------------------------------------------------------------------------
+struct HostDriftArgs {
+    int o0, o1;
+    double *pos;                 // AoS staging (device): x(t) in, x(t+dt) out
+    const double *vel, *frc;     // AoS staging (device)
+    const int *slot_of_id;
+    double4 *xt;
+    float4 *xf;
+    double *vx, *vy, *vz, *fx, *fy, *fz;
+    const double *xbx, *xby, *xbz;
+    const double *mass;
+    BoxDev box;
+    double dt, dt2, half_skin2;
+    int always_rebuild;
+    int *flags;
+};
+
+template <bool ORTHO>
+__global__ void __launch_bounds__(TPB) k_host_load_drift(HostDriftArgs a) {
+    const int o = a.o0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= a.o1) return;
+    const int s = a.slot_of_id[o];
+    const size_t o3 = 3 * (size_t)o;
+    double4 x;
+    x.x = a.pos[o3];
+    x.y = a.pos[o3 + 1];
+    x.z = a.pos[o3 + 2];
+    x.w = a.xt[s].w;  // the type does not change inside the trait call
+    const double vx = a.vel[o3], vy = a.vel[o3 + 1], vz = a.vel[o3 + 2];
+    const double fx = a.frc[o3], fy = a.frc[o3 + 1], fz = a.frc[o3 + 2];
+    double bx = 0.0, by = 0.0, bz = 0.0;
+    if (!a.always_rebuild) {
+        bx = a.xbx[s];
+        by = a.xby[s];
+        bz = a.xbz[s];
+    }
+    const double m = a.mass[type_of(x.w) - 1];
+    const double ax = __ddiv_rn(fx, m), ay = __ddiv_rn(fy, m), az = __ddiv_rn(fz, m);
+    x.x = __dadd_rn(x.x, __dadd_rn(__dmul_rn(vx, a.dt), __dmul_rn(__dmul_rn(ax, 0.5), a.dt2)));
+    x.y = __dadd_rn(x.y, __dadd_rn(__dmul_rn(vy, a.dt), __dmul_rn(__dmul_rn(ay, 0.5), a.dt2)));
+    x.z = __dadd_rn(x.z, __dadd_rn(__dmul_rn(vz, a.dt), __dmul_rn(__dmul_rn(az, 0.5), a.dt2)));
+    wrap_pos<ORTHO>(a.box, x.x, x.y, x.z);
+    a.xt[s] = x;
+    a.xf[s] = make_float4((float)x.x, (float)x.y, (float)x.z, __int_as_float(type_of(x.w)));
+    a.vx[s] = vx;
+    a.vy[s] = vy;
+    a.vz[s] = vz;
+    a.fx[s] = fx;
+    a.fy[s] = fy;
+    a.fz[s] = fz;
+    a.pos[o3] = x.x;
+    a.pos[o3 + 1] = x.y;
+    a.pos[o3 + 2] = x.z;
+    if (a.always_rebuild) {
+        if (o == 0) a.flags[FLAG_REBUILD] = 1;
+    } else {
+        double dx = x.x - bx, dy = x.y - by, dz = x.z - bz;
+        min_image<ORTHO>(a.box, dx, dy, dz);
+        if (!(norm2(dx, dy, dz) <= a.half_skin2)) a.flags[FLAG_REBUILD] = 1;
+    }
+}
+
+struct StoreRangeArgs {
+    int o0, o1;
+    const int *slot_of_id;
+    const double *vx, *vy, *vz, *fx, *fy, *fz;
+    double *vel, *frc;  // AoS staging (device)
+};
+
+__global__ void __launch_bounds__(TPB) k_store_range(StoreRangeArgs a) {
+    const int o = a.o0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= a.o1) return;
+    const int s = a.slot_of_id[o];
+    const size_t o3 = 3 * (size_t)o;
+    a.vel[o3] = a.vx[s];
+    a.vel[o3 + 1] = a.vy[s];
+    a.vel[o3 + 2] = a.vz[s];
+    a.frc[o3] = a.fx[s];
+    a.frc[o3 + 1] = a.fy[s];
+    a.frc[o3 + 2] = a.fz[s];
+}
+
 // Skin trigger on freshly uploaded positions: any |minimg(x - x_build)|^2 > (skin/2)^2 => rebuild.
 template <bool ORTHO>
 __global__ void __launch_bounds__(TPB) k_check_displacement(int n, const double4 *__restrict__ xt,
@@ -221,6 +311,8 @@ struct VVArgs {
     unsigned int *ticket;
     pisb_thermo *thermo;  // record of the step the KICK completes
     const double *vscale;  // NVT: thermostat scale exp(-dt/2 xi_1) read from device memory (null for NVE)
+    double4 *xt_out;       // DRIFT: where x(t+dt) goes -- xt itself, or the other position buffer when the batch
+    float4 *xf_out;        //        continues with k_force_vv launches (which alternate the two buffers)
 };
 
 template <bool KICK, bool DRIFT, bool ORTHO>
@@ -278,8 +370,8 @@ __global__ void __launch_bounds__(TPB, 4) k_vv(VVArgs a) {
             x.y = __dadd_rn(x.y, __dadd_rn(__dmul_rn(vy, a.dt), __dmul_rn(__dmul_rn(ay, 0.5), a.dt2)));
             x.z = __dadd_rn(x.z, __dadd_rn(__dmul_rn(vz, a.dt), __dmul_rn(__dmul_rn(az, 0.5), a.dt2)));
             wrap_pos<ORTHO>(a.box, x.x, x.y, x.z);
-            a.xt[i] = x;
-            a.xf[i] = make_float4((float)x.x, (float)x.y, (float)x.z, __int_as_float(type_of(x.w)));
+            a.xt_out[i] = x;
+            a.xf_out[i] = make_float4((float)x.x, (float)x.y, (float)x.z, __int_as_float(type_of(x.w)));
             if (a.always_rebuild) {
                 if (i == 0) a.flags[FLAG_REBUILD] = 1;
             } else {
@@ -1035,6 +1127,98 @@ __global__ void __launch_bounds__(TPB_FORCE, 8) k_force_v3(Force2Args a) {
     block_reduce_finalize<2, TPB_FORCE>(red, a.partials, a.ticket, [&](int qq, double s) {
         if (qq == 0) th->pe = s / 2.0;
         else th->virial_pair = s / 2.0;
+    });
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_force_vv<MULTI, DRIFT>: the force pass with the integrator in its epilogue -- ONE kernel per NVE step.
+//   force  : k_force_v3's loop, unchanged (same pair terms, same summation order)
+//   kick   : second half of step k      v += ((a_t + a_tdt) * 0.5) * dt      potential.rs:28-30, + KE, tr(X F^T)
+//   drift  : first half of step k+1     x += (v*dt) + ((a*0.5) * dt^2), wrap, skin trigger   potential.rs:16-22
+// The force pass is bound by the FP64 pipe and the L1TEX gather path and leaves ~80 % of the HBM bandwidth idle; the
+// 200 B/atom the separate k_vv<kick,drift> launch streams (0.16 ms per step at 4M atoms) ride along for free here.
+// Other threads still gather x(t) while this one already knows x(t+dt), so the drifted position goes to the OTHER
+// position buffer (xt_out / xf_out); the host swaps the two after every drifting launch.
+// Arithmetic of the epilogue is k_vv<true, DRIFT, true>'s, operation for operation.
+// ------------------------------------------------------------------------------------------------
+struct ForceVVArgs {
+    Force2Args f;                // f.fx/fy/fz receive F(t+dt); f.ax must be null
+    double *vx, *vy, *vz;
+    const double *gx, *gy, *gz;  // F(t)
+    const double *xbx, *xby, *xbz;
+    const double *mass;
+    double4 *xt_out;
+    float4 *xf_out;
+    double dt, dt2, half_skin2;
+    int always_rebuild;
+    int *flags;
+};
+
+template <bool MULTI, bool DRIFT>
+__global__ void __launch_bounds__(TPB_FORCE, 8) k_force_vv(ForceVVArgs b) {
+    const Force2Args &a = b.f;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double red[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};  // pe, pair virial, ke, x*fx, y*fy, z*fz
+    const bool active = i < a.n;
+    bool interior = true;
+    if (active) interior = is_interior(a.boxf, a.xf[i]);
+    const bool warp_interior = __all_sync(0xffffffffu, interior);
+    if (active) {
+        double fx = 0.0, fy = 0.0, fz = 0.0, pe = 0.0, vir = 0.0;
+        if (warp_interior) force3_body<MULTI, false>(a, i, fx, fy, fz, pe, vir);
+        else force3_body<MULTI, true>(a, i, fx, fy, fz, pe, vir);
+        a.fx[i] = fx;
+        a.fy[i] = fy;
+        a.fz[i] = fz;
+        red[0] = pe;
+        red[1] = vir;
+        // ---- integrator epilogue ----
+        double4 x = a.xt[i];  // L1/L2 hit: this thread read it at the top of the force loop
+        double vx = b.vx[i], vy = b.vy[i], vz = b.vz[i];
+        const double gx = b.gx[i], gy = b.gy[i], gz = b.gz[i];
+        double bx = 0.0, by = 0.0, bz = 0.0;
+        if (DRIFT && !b.always_rebuild) {
+            bx = b.xbx[i];
+            by = b.xby[i];
+            bz = b.xbz[i];
+        }
+        const double m = b.mass[type_of(x.w) - 1];
+        const double ax = __ddiv_rn(fx, m), ay = __ddiv_rn(fy, m), az = __ddiv_rn(fz, m);
+        const double ox = __ddiv_rn(gx, m), oy = __ddiv_rn(gy, m), oz = __ddiv_rn(gz, m);
+        vx = __dadd_rn(vx, __dmul_rn(__dmul_rn(__dadd_rn(ox, ax), 0.5), b.dt));
+        vy = __dadd_rn(vy, __dmul_rn(__dmul_rn(__dadd_rn(oy, ay), 0.5), b.dt));
+        vz = __dadd_rn(vz, __dmul_rn(__dmul_rn(__dadd_rn(oz, az), 0.5), b.dt));
+        b.vx[i] = vx;
+        b.vy[i] = vy;
+        b.vz[i] = vz;
+        red[2] = __dmul_rn(__dmul_rn(0.5, m), norm2(vx, vy, vz));
+        red[3] = __dmul_rn(x.x, fx);
+        red[4] = __dmul_rn(x.y, fy);
+        red[5] = __dmul_rn(x.z, fz);
+        if (DRIFT) {
+            x.x = __dadd_rn(x.x, __dadd_rn(__dmul_rn(vx, b.dt), __dmul_rn(__dmul_rn(ax, 0.5), b.dt2)));
+            x.y = __dadd_rn(x.y, __dadd_rn(__dmul_rn(vy, b.dt), __dmul_rn(__dmul_rn(ay, 0.5), b.dt2)));
+            x.z = __dadd_rn(x.z, __dadd_rn(__dmul_rn(vz, b.dt), __dmul_rn(__dmul_rn(az, 0.5), b.dt2)));
+            wrap_pos<true>(a.box, x.x, x.y, x.z);
+            b.xt_out[i] = x;
+            b.xf_out[i] = make_float4((float)x.x, (float)x.y, (float)x.z, __int_as_float(type_of(x.w)));
+            if (b.always_rebuild) {
+                if (i == 0) b.flags[FLAG_REBUILD] = 1;
+            } else {
+                double dx = x.x - bx, dy = x.y - by, dz = x.z - bz;
+                min_image<true>(a.box, dx, dy, dz);
+                if (!(norm2(dx, dy, dz) <= b.half_skin2)) b.flags[FLAG_REBUILD] = 1;
+            }
+        }
+    }
+    pisb_thermo *th = a.thermo;
+    double t3[3];
+    block_reduce_finalize<6, TPB_FORCE>(red, a.partials, a.ticket, [&](int q, double s) {
+        if (q == 0) th->pe = s / 2.0;
+        else if (q == 1) th->virial_pair = s / 2.0;
+        else if (q == 2) th->ke = s;
+        else t3[q - 3] = s;
+        if (q == 5) th->virial_ref = (t3[0] + t3[1]) + t3[2];
     });
 }
 

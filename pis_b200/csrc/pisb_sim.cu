@@ -57,6 +57,10 @@ struct pisb_handle {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;  // overlaps the position read-back of the host-buffer step with the force kernel
     cudaEvent_t ev_pos = nullptr;
+    cudaStream_t up_stream = nullptr;    // chunked host-buffer step: host->device copies run ahead of the drift kernels
+    std::vector<cudaEvent_t> ev_chunk;   // ... one arrival / one departure event per chunk
+    int host_pipeline = 1;               // option "host_pipeline": 0 = whole-array copies (the unpipelined sequence)
+    int host_chunk_atoms = 0;            // option "host_chunk_atoms": atoms per chunk, 0 = auto (n/8, at least 65536)
     std::string err;
 
     // potential
@@ -72,6 +76,7 @@ struct pisb_handle {
     int force_variant = 0;  // 0 = auto (v3 when orthorhombic + fully periodic, else v1), 1 = v1, 2 = v2, 3 = v3
     int build_variant = 0;
     int cell_div = 0;  // cells per list cutoff per dimension: 0 = auto, 1 = reference-sized cells, 2 = half-size cells
+    int fuse_vv = 1;   // option "fuse_vv": NVE batches run k_force_vv (force + kick + drift in one launch) when the default force kernel applies
 
     // box / grid
     BoxDev box{};
@@ -88,7 +93,7 @@ struct pisb_handle {
 
     // device arrays
     DevBuf<double4> xt, s_xt;
-    DevBuf<float4> xf;
+    DevBuf<float4> xf, xf2;  // xf2: the other FP32 shadow buffer of the fused force+integrator step (xt alternates with s_xt)
     DevBuf<float> xp;  // pair-packed FP32 positions (k_build_list_v3), rewritten at every rebuild
     DevBuf<PairF> tablef_d;
     DevBuf<double> v[3], f[3], g[3], xb[3], s_v[3], s_f[3];
@@ -137,6 +142,7 @@ struct pisb_handle {
         int m = 0;
         int64_t nvt_total = 0;     // 0: NVE steps; > 0: NVT steps with this ramp length
         const void *f0 = nullptr;  // which of the two force buffers held F(t) when the batch was captured
+        const void *x0 = nullptr;  // ... and which of the two position buffers held x(t) (fused steps alternate them)
         cudaGraphExec_t exec = nullptr;
     };
     std::vector<StepGraph> graphs;
@@ -470,6 +476,7 @@ int reserve_atoms(pisb_t *h, int n) {
     const size_t cap = (size_t)n;
     TRY(dev_reserve(h, h->xt, cap));
     TRY(dev_reserve(h, h->xf, cap));
+    TRY(dev_reserve(h, h->xf2, cap));
     TRY(dev_reserve(h, h->xp, ((cap + 1) / 2 + 32) * 8));
     TRY(dev_reserve(h, h->s_xt, cap));
     for (int d = 0; d < 3; ++d) {
@@ -486,8 +493,8 @@ int reserve_atoms(pisb_t *h, int n) {
     TRY(dev_reserve(h, h->cell_of, cap));
     TRY(dev_reserve(h, h->order, cap));
     TRY(dev_reserve(h, h->nnbr, cap));
-    // per-block partial sums: up to 4 quantities x blocks; small systems run the force kernel with 8 lanes per atom
-    TRY(dev_reserve(h, h->partials, (size_t)4 * (nblk(n, TPB_FORCE) + 1) + (size_t)4 * (nblk(std::min(n, 75000) * 8, TPB_FORCE) + 1)));
+    // per-block partial sums: up to 6 quantities x blocks (k_force_vv); small systems run the force kernel with 8 lanes per atom
+    TRY(dev_reserve(h, h->partials, (size_t)6 * (nblk(n, TPB_FORCE) + 1) + (size_t)4 * (nblk(std::min(n, 75000) * 8, TPB_FORCE) + 1)));
     return PISB_OK;
 }
 
@@ -634,13 +641,20 @@ int launch_force(pisb_t *h, double *const out[3], const double *const acc[3], pi
     return check_launch(h, "k_force");
 }
 
-int launch_vv(pisb_t *h, bool kick, bool drift, double dt, pisb_thermo *rec, const double *vscale = nullptr) {
+void swap_position_buffers(pisb_t *h) {
+    std::swap(h->xt, h->s_xt);
+    std::swap(h->xf, h->xf2);
+}
+
+int launch_vv(pisb_t *h, bool kick, bool drift, double dt, pisb_thermo *rec, const double *vscale = nullptr,
+              bool out_of_place = false) {
     LaunchScope ls(h, PISB_K_INTEGRATE);
     const double hs = 0.5 * h->skin;
     VVArgs a{h->n, h->xt.p, h->xf.p, h->v[0].p, h->v[1].p, h->v[2].p, h->f[0].p, h->f[1].p, h->f[2].p,
              h->g[0].p, h->g[1].p, h->g[2].p, h->xb[0].p, h->xb[1].p, h->xb[2].p, h->mass_d.p, h->box,
              dt, dt * dt, h->skin_half2_override >= 0.0 ? h->skin_half2_override : hs * hs,
-             (h->skin > 0.0 && h->skin_half2_override != 0.0) ? 0 : 1, h->flags, h->partials.p, h->ticket, rec, vscale};
+             (h->skin > 0.0 && h->skin_half2_override != 0.0) ? 0 : 1, h->flags, h->partials.p, h->ticket, rec, vscale,
+             out_of_place ? h->s_xt.p : h->xt.p, out_of_place ? h->xf2.p : h->xf.p};
     const int nb = nblk(h->n, TPB);
     cudaStream_t st = h->stream;
     const bool o = h->box.ortho != 0;
@@ -653,7 +667,43 @@ int launch_vv(pisb_t *h, bool kick, bool drift, double dt, pisb_thermo *rec, con
     else if (kick) VV(true, false);
     else VV(false, true);
 #undef VV
+    if (out_of_place) swap_position_buffers(h);
     return check_launch(h, "k_vv");
+}
+
+// NVE batches of systems the default force kernel serves (orthorhombic, fully periodic, enough atoms for one thread per
+// atom) run one k_force_vv launch per step instead of k_force_v3 + k_vv.
+bool fused_step_possible(const pisb_t *h) {
+    return h->fuse_vv && !h->multi && v2_possible(h) && (h->force_variant == 0 || h->force_variant == 3) &&
+           (h->force_variant == 3 || h->n > 75000);
+}
+
+// F(t+dt) -> g, kick with F(t) = f, [drift into the other position buffer], then f <-> g (and the position buffers).
+int launch_force_vv(pisb_t *h, bool drift, double dt, pisb_thermo *rec) {
+    {
+        LaunchScope ls(h, PISB_K_FORCE);
+        const double hs = 0.5 * h->skin;
+        ForceVVArgs fv{Force2Args{h->n, h->npad, h->xt.p, h->xf.p, h->nbr.p, h->nnbr.p, h->box, h->boxf, h->pairs[0], h->pairsf[0],
+                                  h->table_d.p, h->tablef_d.p, h->n_types, nullptr, nullptr, nullptr, h->g[0].p, h->g[1].p, h->g[2].p,
+                                  h->partials.p, h->ticket, rec, nullptr},
+                       h->v[0].p, h->v[1].p, h->v[2].p, h->f[0].p, h->f[1].p, h->f[2].p, h->xb[0].p, h->xb[1].p, h->xb[2].p,
+                       h->mass_d.p, h->s_xt.p, h->xf2.p, dt, dt * dt,
+                       h->skin_half2_override >= 0.0 ? h->skin_half2_override : hs * hs,
+                       (h->skin > 0.0 && h->skin_half2_override != 0.0) ? 0 : 1, h->flags};
+        const bool multi = h->n_types > 1;
+        const int nb = nblk(h->n, TPB_FORCE);
+        cudaStream_t st = h->stream;
+        if (drift) {
+            if (multi) k_force_vv<true, true><<<nb, TPB_FORCE, 0, st>>>(fv);
+            else k_force_vv<false, true><<<nb, TPB_FORCE, 0, st>>>(fv);
+        } else {
+            if (multi) k_force_vv<true, false><<<nb, TPB_FORCE, 0, st>>>(fv);
+            else k_force_vv<false, false><<<nb, TPB_FORCE, 0, st>>>(fv);
+        }
+    }
+    for (int d = 0; d < 3; ++d) std::swap(h->f[d], h->g[d]);
+    if (drift) swap_position_buffers(h);
+    return check_launch(h, "k_force_vv");
 }
 
 int read_flags(pisb_t *h) {
@@ -814,6 +864,17 @@ int do_compute(pisb_t *h, int accumulate, double *pe) {
 int capture_conditional_rebuild(pisb_t *h);
 
 int enqueue_nve_steps(pisb_t *h, double dt, int64_t cnt, pisb_thermo *rec0) {
+    if (fused_step_possible(h)) {
+        // drift (into the other position buffer), [rebuild], (force+kick+drift, [rebuild]) x (cnt-1), force+kick:
+        // cnt position-buffer swaps and cnt force-buffer swaps, so an even batch ends on the buffers it started from
+        TRY(launch_vv(h, false, true, dt, nullptr, nullptr, true));
+        for (int64_t s = 0; s < cnt; ++s) {
+            if (h->capturing) TRY(capture_conditional_rebuild(h));
+            else TRY(launch_rebuild_chain(h));
+            TRY(launch_force_vv(h, s + 1 < cnt, dt, rec0 + s));
+        }
+        return PISB_OK;
+    }
     for (int64_t s = 0; s < cnt; ++s) {
         pisb_thermo *rec = rec0 + s;
         if (s == 0) TRY(launch_vv(h, false, true, dt, nullptr));
@@ -879,7 +940,9 @@ void graph_signature(pisb_t *h, double dt, std::vector<unsigned char> &sig) {
     };
     // f and g trade places every step: the pair is part of the signature, the current assignment is the graph's key
     const void *fa = std::min<const void *>(h->f[0].p, h->g[0].p), *fb = std::max<const void *>(h->f[0].p, h->g[0].p);
-    const void *ptrs[] = {h->xt.p, h->s_xt.p, h->xf.p, h->xp.p, h->tablef_d.p, h->v[0].p, h->v[1].p, h->v[2].p, fa, fb,
+    // so do the two position buffers (and FP32 shadows) of fused steps
+    const void *ptrs[] = {std::min<const void *>(h->xt.p, h->s_xt.p), std::max<const void *>(h->xt.p, h->s_xt.p),
+                          std::min<const void *>(h->xf.p, h->xf2.p), std::max<const void *>(h->xf.p, h->xf2.p), h->xp.p, h->tablef_d.p, h->v[0].p, h->v[1].p, h->v[2].p, fa, fb,
                           std::min<const void *>(h->f[1].p, h->g[1].p), std::max<const void *>(h->f[1].p, h->g[1].p),
                           std::min<const void *>(h->f[2].p, h->g[2].p), std::max<const void *>(h->f[2].p, h->g[2].p), h->xb[0].p, h->xb[1].p, h->xb[2].p, h->s_v[0].p,
                           h->s_v[1].p, h->s_v[2].p, h->s_f[0].p, h->s_f[1].p, h->s_f[2].p, h->id.p, h->s_id.p,
@@ -887,7 +950,7 @@ void graph_signature(pisb_t *h, double dt, std::vector<unsigned char> &sig) {
                           h->tile_sum.p, h->mass_d.p, h->partials.p, h->table_d.p, h->thermo_d.p, h->flags, h->ticket, h->nhc_d.p,
                           h->nhc_energy_d.p};
     put(ptrs, sizeof ptrs);
-    const int ints[] = {h->n, h->npad, h->kcap, h->n_types, h->force_variant, h->build_variant, h->cell_div};
+    const int ints[] = {h->n, h->npad, h->kcap, h->n_types, h->force_variant, h->build_variant, h->cell_div, h->fuse_vv};
     put(ints, sizeof ints);
     const double dbl[] = {dt, h->skin, h->skin_half2_override, h->max_rcut};
     put(dbl, sizeof dbl);
@@ -930,6 +993,7 @@ int capture_step_graph(pisb_t *h, double dt, int m, int64_t nvt_total) {
     sg.m = m;
     sg.nvt_total = nvt_total;
     sg.f0 = h->f[0].p;
+    sg.x0 = h->xt.p;
     sg.exec = exec;
     h->graphs.push_back(sg);
     return PISB_OK;
@@ -949,7 +1013,7 @@ int get_step_graph(pisb_t *h, double dt, int m, int64_t nvt_total, cudaGraphExec
     }
     for (int pass = 0; pass < 2; ++pass) {
         for (auto &g : h->graphs)
-            if (g.m == m && g.nvt_total == nvt_total && g.f0 == h->f[0].p) {
+            if (g.m == m && g.nvt_total == nvt_total && g.f0 == h->f[0].p && g.x0 == h->xt.p) {
                 *out = g.exec;
                 return PISB_OK;
             }
@@ -959,9 +1023,14 @@ int get_step_graph(pisb_t *h, double dt, int m, int64_t nvt_total, cudaGraphExec
             int rc = PISB_OK;
             for (int parity = 0; parity < 2 && rc == PISB_OK; ++parity) {
                 for (int mm = GRAPH_M; mm >= 2 && rc == PISB_OK; mm /= 2) rc = capture_step_graph(h, dt, mm, nvt_total);
+                // pointers only (nothing executes during a capture); fused steps flip the position buffers with the force buffers
+                const bool fused = nvt_total == 0 && fused_step_possible(h);
                 for (int d = 0; d < 3; ++d) std::swap(h->f[d], h->g[d]);
-                if (rc != PISB_OK && parity == 0)  // leave the buffers as they were
+                if (fused) swap_position_buffers(h);
+                if (rc != PISB_OK && parity == 0) {  // leave the buffers as they were
                     for (int d = 0; d < 3; ++d) std::swap(h->f[d], h->g[d]);
+                    if (fused) swap_position_buffers(h);
+                }
             }
             if (rc != PISB_OK) return rc;
         }
@@ -1003,8 +1072,9 @@ int do_step_nve(pisb_t *h, double dt, int64_t nsteps, pisb_thermo *out) {
                 CUDA_TRY(h, cudaGraphLaunch(exec, h->stream));
                 h->n_graph_launches++;
                 graph_steps += piece;
-                // fixed nodes: piece+1 integrator launches, piece condition setters, piece force launches
-                h->n_launches += 3 * piece + 1;
+                // fixed nodes: piece condition setters + either one drift and piece k_force_vv launches, or piece+1 integrator
+                // and piece force launches
+                h->n_launches += (fused_step_possible(h) ? 2 : 3) * piece + 1;
             } else {
                 TRY(enqueue_nve_steps(h, dt, piece, h->thermo_d.p));
             }
@@ -1902,6 +1972,7 @@ int pisb_destroy(pisb_t *h) {
     dev_free(h, h->xp);
     dev_free(h, h->tablef_d);
     dev_free(h, h->s_xt);
+    dev_free(h, h->xf2);
     for (int d = 0; d < 3; ++d) {
         dev_free(h, h->v[d]);
         dev_free(h, h->f[d]);
@@ -1959,6 +2030,8 @@ int pisb_destroy(pisb_t *h) {
     drop_graphs(h);
     if (h->graph_stream) cudaStreamDestroy(h->graph_stream);
     if (h->ev_pos) cudaEventDestroy(h->ev_pos);
+    for (cudaEvent_t e : h->ev_chunk) cudaEventDestroy(e);
+    if (h->up_stream) cudaStreamDestroy(h->up_stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -2082,6 +2155,103 @@ int pisb_thermo_now(pisb_t *h, pisb_thermo *out) {
     return PISB_OK;
 }
 
+// The host-buffer step for an atom set the handle already holds (same count, valid list => slot_of_id maps every id to
+// its cell-sorted slot): the three arrays travel in chunks of the original atom order and the step is pipelined over PCIe.
+//   up_stream   : H2D x, v, F of chunk c                                 (the link stays busy from the first byte)
+//   stream      : k_host_load_drift(c) as soon as chunk c is there       (hidden under the copies of chunk c+1)
+//   copy_stream : D2H x(t+dt) of chunk c                                 (full duplex: goes down while c+1 comes up)
+// then [rebuild], the force pass with the kick (k_force_vv when the default kernel applies), and v, F leave chunk by
+// chunk behind k_store_range.  Same kernels' arithmetic, same results as the whole-array sequence below.
+static int host_step_pipelined(pisb_t *h, double *pos, double *vel, double *force, double dt, double *pe) {
+    const int n = h->n;
+    const size_t n3 = (size_t)3 * n;
+    TRY(dev_reserve(h, h->st_pos, n3));
+    TRY(dev_reserve(h, h->st_vel, n3));
+    TRY(dev_reserve(h, h->st_frc, n3));
+    TRY(check_bad_type(h));
+    TRY(reserve_thermo(h, 2));
+    if (!h->up_stream) CUDA_TRY(h, cudaStreamCreateWithFlags(&h->up_stream, cudaStreamNonBlocking));
+    int chunk = h->host_chunk_atoms > 0 ? h->host_chunk_atoms : std::max(65536, (n + 7) / 8);
+    chunk = (chunk + TPB - 1) / TPB * TPB;
+    const int nchunk = (n + chunk - 1) / chunk;
+    while (h->ev_chunk.size() < (size_t)2 * nchunk + 1) {
+        cudaEvent_t e;
+        CUDA_TRY(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->ev_chunk.push_back(e);
+    }
+    // the staging arrays may still be read by work queued on the main stream (an asynchronous pisb_upload)
+    cudaEvent_t ev_start = h->ev_chunk[(size_t)2 * nchunk];
+    CUDA_TRY(h, cudaEventRecord(ev_start, h->stream));
+    CUDA_TRY(h, cudaStreamWaitEvent(h->up_stream, ev_start, 0));
+    CUDA_TRY(h, cudaStreamWaitEvent(h->copy_stream, ev_start, 0));
+    const double hs = 0.5 * h->skin;
+    const double half_skin2 = h->skin_half2_override >= 0.0 ? h->skin_half2_override : hs * hs;
+    const int always = (h->skin > 0.0 && h->skin_half2_override != 0.0) ? 0 : 1;
+    for (int c = 0; c < nchunk; ++c) {
+        const int o0 = c * chunk, o1 = std::min(n, o0 + chunk);
+        const size_t off = (size_t)3 * o0, cnt = (size_t)3 * (o1 - o0);
+        cudaEvent_t ev_up = h->ev_chunk[2 * c], ev_dr = h->ev_chunk[2 * c + 1];
+        CUDA_TRY(h, cudaMemcpyAsync(h->st_pos.p + off, pos + off, sizeof(double) * cnt, cudaMemcpyHostToDevice, h->up_stream));
+        CUDA_TRY(h, cudaMemcpyAsync(h->st_vel.p + off, vel + off, sizeof(double) * cnt, cudaMemcpyHostToDevice, h->up_stream));
+        CUDA_TRY(h, cudaMemcpyAsync(h->st_frc.p + off, force + off, sizeof(double) * cnt, cudaMemcpyHostToDevice, h->up_stream));
+        CUDA_TRY(h, cudaEventRecord(ev_up, h->up_stream));
+        CUDA_TRY(h, cudaStreamWaitEvent(h->stream, ev_up, 0));
+        {
+            LaunchScope ls(h, PISB_K_COPY);
+            HostDriftArgs a{o0, o1, h->st_pos.p, h->st_vel.p, h->st_frc.p, h->slot_of_id.p, h->xt.p, h->xf.p,
+                            h->v[0].p, h->v[1].p, h->v[2].p, h->f[0].p, h->f[1].p, h->f[2].p, h->xb[0].p, h->xb[1].p, h->xb[2].p,
+                            h->mass_d.p, h->box, dt, dt * dt, half_skin2, always, h->flags};
+            if (h->box.ortho) k_host_load_drift<true><<<nblk(o1 - o0, TPB), TPB, 0, h->stream>>>(a);
+            else k_host_load_drift<false><<<nblk(o1 - o0, TPB), TPB, 0, h->stream>>>(a);
+            TRY(check_launch(h, "k_host_load_drift"));
+        }
+        CUDA_TRY(h, cudaEventRecord(ev_dr, h->stream));
+        CUDA_TRY(h, cudaStreamWaitEvent(h->copy_stream, ev_dr, 0));
+        CUDA_TRY(h, cudaMemcpyAsync(pos + off, h->st_pos.p + off, sizeof(double) * cnt, cudaMemcpyDeviceToHost, h->copy_stream));
+    }
+    h->forces_current = false;
+    TRY(launch_rebuild_chain(h));  // runs only if the drift raised the skin trigger; refreshes slot_of_id
+    if (fused_step_possible(h)) {
+        TRY(launch_force_vv(h, false, dt, h->thermo_d.p));
+    } else {
+        double *outp[3] = {h->g[0].p, h->g[1].p, h->g[2].p};
+        TRY(launch_force(h, outp, nullptr, h->thermo_d.p));
+        for (int d = 0; d < 3; ++d) std::swap(h->f[d], h->g[d]);
+        TRY(launch_vv(h, true, false, dt, h->thermo_d.p));
+    }
+    for (int c = 0; c < nchunk; ++c) {
+        const int o0 = c * chunk, o1 = std::min(n, o0 + chunk);
+        const size_t off = (size_t)3 * o0, cnt = (size_t)3 * (o1 - o0);
+        cudaEvent_t ev_st = h->ev_chunk[2 * c];
+        {
+            LaunchScope ls(h, PISB_K_COPY);
+            StoreRangeArgs a{o0, o1, h->slot_of_id.p, h->v[0].p, h->v[1].p, h->v[2].p, h->f[0].p, h->f[1].p, h->f[2].p,
+                             h->st_vel.p, h->st_frc.p};
+            k_store_range<<<nblk(o1 - o0, TPB), TPB, 0, h->stream>>>(a);
+            TRY(check_launch(h, "k_store_range"));
+        }
+        CUDA_TRY(h, cudaEventRecord(ev_st, h->stream));
+        CUDA_TRY(h, cudaStreamWaitEvent(h->copy_stream, ev_st, 0));
+        CUDA_TRY(h, cudaMemcpyAsync(vel + off, h->st_vel.p + off, sizeof(double) * cnt, cudaMemcpyDeviceToHost, h->copy_stream));
+        CUDA_TRY(h, cudaMemcpyAsync(force + off, h->st_frc.p + off, sizeof(double) * cnt, cudaMemcpyDeviceToHost, h->copy_stream));
+    }
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_thermo, h->thermo_d.p, sizeof(pisb_thermo), cudaMemcpyDeviceToHost, h->stream));
+    TRY(read_flags(h));
+    CUDA_TRY(h, cudaStreamSynchronize(h->copy_stream));
+    if (h->h_flags[FLAG_NBUILDS] != h->n_builds_host) {
+        h->n_builds_host = h->h_flags[FLAG_NBUILDS];
+        h->max_nbr = h->h_flags[FLAG_MAXNBR];
+    }
+    if (h->h_flags[FLAG_MAXNBR] > h->kcap) {
+        h->list_valid = false;
+        return fail(h, PISB_ERR_CAPACITY, "a neighbour list overflowed during the step; repeat the call (capacity grows on the next build)");
+    }
+    h->n_steps += 1;
+    h->forces_current = true;
+    if (pe) *pe = h->h_thermo[0].pe;
+    return PISB_OK;
+}
+
 int pisb_verlet_step_nve_host(pisb_t *h, int64_t n, double *pos, double *vel, double *force,
                               const int32_t *types, double dt, double *pe) {
     if (!h) return PISB_ERR_INVALID;
@@ -2090,6 +2260,8 @@ int pisb_verlet_step_nve_host(pisb_t *h, int64_t n, double *pos, double *vel, do
     // types are only re-sent when the atom set is new (they cannot change inside the trait call)
     const bool fresh = !h->have_atoms || h->n != (int)n;
     if (fresh && !types) return fail(h, PISB_ERR_INVALID, "types is NULL on first call");
+    if (!fresh && h->host_pipeline && !h->multi && h->have_box && h->grid_ok && h->list_valid && h->slot_of_id.p)
+        return host_step_pipelined(h, pos, vel, force, dt, pe);
     TRY(do_upload(h, n, pos, vel, force, fresh ? types : nullptr));
     if (h->multi) return fail(h, PISB_ERR_STATE, "the host-buffer step is a single-GPU entry point");
     // One verlet_step_nve, written out so that x(t+dt) -- final right after the drift -- travels back over PCIe on a
@@ -2407,6 +2579,18 @@ int pisb_set_option(pisb_t *h, const char *name, double value) {
     }
     if (!std::strcmp(name, "halo_mode")) {
         h->halo_mode = (int)value;
+        return PISB_OK;
+    }
+    if (!std::strcmp(name, "host_pipeline")) {
+        h->host_pipeline = value != 0.0 ? 1 : 0;
+        return PISB_OK;
+    }
+    if (!std::strcmp(name, "host_chunk_atoms")) {
+        h->host_chunk_atoms = value > 0 ? (int)value : 0;
+        return PISB_OK;
+    }
+    if (!std::strcmp(name, "fuse_vv")) {
+        h->fuse_vv = value != 0.0 ? 1 : 0;
         return PISB_OK;
     }
     if (!std::strcmp(name, "force_variant")) {

@@ -639,3 +639,125 @@ def test_cuda_graph_small_system_matches_oracle():
     th = mgr.step_nve(0.25, 200)
     assert np.max(np.abs(th["pe"] - ref[1:, 0]) / np.abs(ref[1:, 0])) <= ENERGY_TOL
     assert np.max(np.abs(th["ke"] - ref[1:, 1]) / np.abs(ref[1:, 1])) <= ENERGY_TOL
+
+
+def _run_batches(atoms, fuse, graphs, batches, table=None, nvt_first=False):
+    mgr = make_manager(skin=SKIN, variant=6, table=table)      # force_variant 3: the fused step is selectable at any size
+    mgr.set_option("fuse_vv", fuse)
+    mgr.set_option("cuda_graphs", graphs)
+    mgr.attach(atoms)
+    mgr.compute()
+    if nvt_first:   # an NVT batch flips the force buffers but not the position buffers: the NVE graphs must cope
+        chain = mgr.nhc_new(60.0, 60.0, 50.0)
+        mgr.step_nvt_nhc(0.25, 5, chain, 0, 5)
+    th = np.concatenate([mgr.step_nve(0.25, k) for k in batches])
+    st = mgr.stats()
+    mgr.download(atoms)
+    mgr.close()
+    return th, st
+
+
+@pytest.mark.parametrize("graphs", [1, 0])
+def test_fused_force_integrator_step_equals_separate_kernels(graphs):
+    """k_force_vv (force + kick + drift in one launch, positions double-buffered) against k_force_v3 + k_vv: the same
+    arithmetic per atom, so positions / velocities / forces and the force kernel's reductions (PE, pair virial) are
+    bit-identical across rebuilds, odd batch sizes and single steps; KE and tr(X F^T) are reduced over 128- instead of
+    256-thread blocks and agree to rounding."""
+    batches = (64, 7, 1, 33, 46, 2, 3)
+    a1 = fcc_argon(12, temperature=60.0, seed=5)
+    a2 = fcc_argon(12, temperature=60.0, seed=5)
+    t1, s1 = _run_batches(a1, 1, graphs, batches)
+    t0, s0 = _run_batches(a2, 0, graphs, batches)
+    assert np.array_equal(a1.positions, a2.positions)
+    assert np.array_equal(a1.velocities, a2.velocities)
+    assert np.array_equal(a1.forces, a2.forces)
+    for key in ("pe", "virial_pair"):
+        assert np.array_equal(t1[key], t0[key]), key
+    for key in ("ke", "virial_ref"):
+        assert np.max(np.abs(t1[key] - t0[key]) / np.maximum(np.abs(t0[key]), 1e-3)) <= 1e-12, key
+    assert s1["n_builds"] == s0["n_builds"] and s1["n_builds"] >= 4
+    assert s1["n_launches"] < s0["n_launches"]     # one kernel per step instead of two
+
+
+def test_fused_step_after_an_nvt_batch_and_with_two_types():
+    """Buffer-parity corner: an NVT batch (unfused) flips f/g only, the fused NVE batches that follow flip f/g and the
+    position buffers together.  Two atom types exercise the table path of k_force_vv."""
+    table = {(1, 1): LennardJones(0.238, 3.405, 8.5), (1, 2): LennardJones(0.15, 3.0, 7.5), (2, 2): LennardJones(0.07, 2.8, 7.0)}
+    res = []
+    for fuse in (1, 0):
+        atoms = fcc_argon(10, temperature=60.0, seed=9)
+        atoms.type_ids[::3] = 2
+        atoms.masses = [39.948, 20.18]
+        th, st = _run_batches(atoms, fuse, 1, (8, 5, 16, 1, 10), table=table, nvt_first=True)
+        res.append((atoms, th, st))
+    (a1, t1, s1), (a0, t0, s0) = res
+    assert np.array_equal(a1.positions, a0.positions) and np.array_equal(a1.velocities, a0.velocities)
+    assert np.array_equal(a1.forces, a0.forces)
+    assert np.array_equal(t1["pe"], t0["pe"])
+    assert np.max(np.abs(t1["ke"] - t0["ke"]) / np.abs(t0["ke"])) <= 1e-12
+    assert s1["n_builds"] == s0["n_builds"]
+
+
+def test_fused_step_trace_matches_oracle():
+    """The fused step against the oracle directly (the 256k- and 4M-atom tests reach it through the defaults; this one
+    forces it at 4000 atoms for 300 steps with rebuilds)."""
+    atoms = fcc_argon(10, temperature=40.0, seed=21)
+    orc = make_oracle(atoms, {(1, 1): argon_pair(8.5)})
+    x, v = atoms.positions.copy(), atoms.velocities.copy()
+    ref = orc.run_nve(x, v, np.zeros_like(x), atoms.type_ids, 0.25, 300)
+    mgr = make_manager(skin=SKIN, rc=8.5, variant=6)
+    mgr.attach(atoms)
+    mgr.compute()
+    th = mgr.step_nve(0.25, 300)
+    assert mgr.stats()["n_builds"] >= 3
+    assert np.max(np.abs(th["pe"] - ref[1:, 0]) / np.abs(ref[1:, 0])) <= ENERGY_TOL
+    assert np.max(np.abs(th["ke"] - ref[1:, 1]) / np.abs(ref[1:, 1])) <= ENERGY_TOL
+    p_gpu = np.array([atoms.pressure(k, w) for k, w in zip(th["ke"], th["virial_ref"])])
+    assert np.max(np.abs(p_gpu - ref[1:, 4]) / np.maximum(np.abs(ref[1:, 4]), 1e-6)) <= 1e-6
+    mgr.download(atoms)
+    assert np.abs(atoms.positions - x).max() < 1e-8
+
+
+@pytest.mark.parametrize("variant", [0, 6])
+def test_pipelined_host_step_equals_whole_array_step(variant):
+    """pisb_verlet_step_nve_host cuts the trait call's 3 x N host arrays into chunks and pipelines upload, drift and
+    download (k_host_load_drift / k_store_range); option host_pipeline = 0 keeps the whole-array sequence.  Same
+    arithmetic per atom, so 40 hot steps (with rebuilds, ragged last chunk) are bit-identical -- with the separate
+    kernels (variant 0 at this size) and with the fused force + kick kernel (variant 6)."""
+    res = []
+    for pipe in (1, 0):
+        atoms = fcc_argon(9, temperature=80.0, seed=17)            # 2916 atoms
+        mgr = make_manager(skin=SKIN, variant=variant)
+        mgr.set_option("host_pipeline", pipe)
+        mgr.set_option("host_chunk_atoms", 700)                    # 5 chunks, the last one ragged
+        mgr.compute_potential(atoms)
+        pes = [mgr.verlet_step_nve(atoms, 0.25) for _ in range(40)]
+        res.append((atoms, np.array(pes), mgr.stats()))
+        mgr.close()
+    (a1, p1, s1), (a0, p0, s0) = res
+    assert np.array_equal(a1.positions, a0.positions)
+    assert np.array_equal(a1.velocities, a0.velocities)
+    assert np.array_equal(a1.forces, a0.forces)
+    assert np.array_equal(p1, p0)
+    assert s1["n_builds"] == s0["n_builds"] and s1["n_builds"] >= 2
+
+
+def test_pipelined_host_step_follows_host_side_edits():
+    """The host arrays are authoritative at every call: velocities rescaled and an atom moved by the caller between two
+    trait calls must be honoured (the list is rebuilt if the edit broke the skin criterion)."""
+    atoms = fcc_argon(8, temperature=30.0, seed=4)
+    table = {(1, 1): argon_pair()}
+    mgr = make_manager(skin=SKIN)
+    mgr.compute_potential(atoms)
+    for _ in range(3):
+        mgr.verlet_step_nve(atoms, 0.25)
+    atoms.velocities *= 0.5
+    atoms.positions[5] += np.array([1.2, -0.5, 0.4])               # beyond skin/2 = 0.51
+    orc = make_oracle(atoms, table)
+    x, v, f = atoms.positions.copy(), atoms.velocities.copy(), atoms.forces.copy()
+    pe_ref = orc.verlet_step_nve(x, v, f, atoms.type_ids, 0.25)
+    pe = mgr.verlet_step_nve(atoms, 0.25)
+    assert abs(pe - pe_ref) <= ENERGY_TOL * abs(pe_ref)
+    assert np.array_equal(atoms.positions, x)
+    assert force_rel_err(atoms.forces, f).max() <= FORCE_TOL
+    assert np.abs(atoms.velocities - v).max() <= 1e-12 * max(1.0, np.abs(v).max())
