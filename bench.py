@@ -287,17 +287,20 @@ def run_single(args):
     while res_steps < e2e_steps:                 # Simulation::run of pis_host.cpp: one batch per dump interval
         chunk = min(10, e2e_steps - res_steps)   # dump cadence of example/input.pis
         mgr.step_nve(DT, chunk)                  # thermo records (32 B per step) come back with the batch
+        mgr.download_end()                       # the previous dump frame travelled while this batch ran
         d2h_res += 32 * chunk
         res_steps += chunk
         if res_steps % 10 == 0:
-            mgr.download(atoms, positions=True, velocities=False, forces=False)
+            mgr.download_begin(atoms, positions=True, velocities=False, forces=False)
             d2h_res += 24 * n
+    mgr.download_end()
     mgr.synchronize()
     res_s = time.perf_counter() - t0
     e2e_resident = {"value": n * e2e_steps / res_s, "unit": UNIT, "ms_per_step": 1e3 * res_s / e2e_steps,
                     "d2h_bytes_per_step": d2h_res // e2e_steps, "h2d_bytes_per_step": 0,
                     "call": "Simulation::run loop of the C++ host: state uploaded once, pisb_step_nve(dt, steps to the next dump) "
-                            "returning one thermo record per step, positions downloaded every 10 steps"}
+                            "returning one thermo record per step, positions of every 10th step snapshotted on the device and "
+                            "copied back (pisb_download_begin/_end) while the next batch runs"}
 
     # ---- CPU baseline: oracle port on a bounded sample ----
     cpu = None

@@ -18,6 +18,7 @@
 #ifndef PISB200_H
 #define PISB200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -178,6 +179,20 @@ PISB_API int pisb_get_box(pisb_t *h, double *h9, double *hinv9);
  * atoms.positions / velocities / forces on the host (e.g. DumpTraj::write_atoms_info,
  * src/writers/dump_traj.rs:52-66). */
 PISB_API int pisb_download(pisb_t *h, double *pos, double *vel, double *force);
+
+/* The same copy, asynchronous: for the dump steps of Simulation::run (src/simulation.rs:31-37,84-86), so that the
+ * positions of a dump step travel over PCIe while the next batch of steps already runs.  pisb_download_begin takes a
+ * snapshot of the state on the device (in stream order, ORIGINAL atom order) and starts the device->host copies on a
+ * second stream; the arrays are valid after pisb_download_end.  One download may be in flight per handle; the
+ * destination should be page-locked (pisb_host_register) or the copy degrades to a synchronous one.  Single GPU. */
+PISB_API int pisb_download_begin(pisb_t *h, double *pos, double *vel, double *force);
+PISB_API int pisb_download_end(pisb_t *h);
+
+/* Page-lock / unlock host arrays the caller owns (nalgebra's Matrix3xX storage of Atoms.positions / velocities /
+ * forces, src/atoms/new.rs:9-17) so that the host-buffer step and the downloads run at PCIe line rate and
+ * asynchronously.  Thin wrappers over cudaHostRegister / cudaHostUnregister; no handle needed. */
+PISB_API int pisb_host_register(void *ptr, size_t bytes);
+PISB_API int pisb_host_unregister(void *ptr);
 
 /* Observables of the CURRENT device state (KE, virial_ref from current x, v, F; pe/virial_pair of
  * the last force evaluation).  Replaces Atoms::kinetic_energy / virial_tensor().trace(). */

@@ -69,6 +69,10 @@ SIGNATURES = {
     "pisb_compute": (C.c_int, [_vp, C.c_int, _dp]),
     "pisb_step_nve": (C.c_int, [_vp, C.c_double, C.c_int64, _vp]),
     "pisb_download": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "pisb_download_begin": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "pisb_download_end": (C.c_int, [_vp]),
+    "pisb_host_register": (C.c_int, [_vp, C.c_size_t]),
+    "pisb_host_unregister": (C.c_int, [_vp]),
     "pisb_thermo_now": (C.c_int, [_vp, C.POINTER(Thermo)]),
     "pisb_verlet_step_nve_host": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp, C.c_double, _dp]),
     "pisb_neighbours": (C.c_int, [_vp, _vp, _vp, C.c_int64]),

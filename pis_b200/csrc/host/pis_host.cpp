@@ -268,6 +268,13 @@ void LJCudaManager::download(Atoms &atoms, bool pos, bool vel, bool frc) {
                         frc ? atoms.forces.data() : nullptr));
 }
 
+void LJCudaManager::download_begin(Atoms &atoms, bool pos, bool vel, bool frc) {
+    check(pisb_download_begin(h_, pos ? atoms.positions.data() : nullptr, vel ? atoms.velocities.data() : nullptr,
+                              frc ? atoms.forces.data() : nullptr));
+}
+
+void LJCudaManager::download_end() { check(pisb_download_end(h_)); }
+
 pisb_stats_t LJCudaManager::stats() {
     pisb_stats_t s{};
     check(pisb_stats(h_, &s));
@@ -570,6 +577,18 @@ void Simulation::run(LJCudaManager &mgr, SimulationContext &ctx, FILE *out) {
     std::fprintf(out, "0 %s\n", rust_display_f64(first_potential).c_str());
     std::vector<pisb_thermo> th;
     std::vector<double> ext_e, h_trace;
+    // Dump steps (NVE / NVT, where the box does not change): the positions are snapshotted on the device and copied back on a
+    // second stream while the NEXT batch of steps runs; the frame is written when that batch returns.  The position array
+    // is page-locked for the run so the copy is a true asynchronous DMA.
+    const bool async_dump = !npt && dump_step > 0;
+    const bool pos_pinned = async_dump && pisb_host_register(atoms.positions.data(), atoms.positions.size() * sizeof(double)) == PISB_OK;
+    size_t pending_dump = 0;  // step whose positions are in flight (0 = none)
+    auto flush_dump = [&]() {
+        if (pending_dump == 0) return;
+        mgr.download_end();
+        dumper.write_step(atoms, pending_dump);
+        pending_dump = 0;
+    };
     size_t i = 0;
     while (i < steps) {
         // run up to the next dump step on the device; only thermo scalars come back per step
@@ -586,15 +605,21 @@ void Simulation::run(LJCudaManager &mgr, SimulationContext &ctx, FILE *out) {
         } else {
             mgr.step_nve(dt, (int64_t)chunk, th.data());
         }
+        flush_dump();  // the frame of the previous dump step travelled while this batch ran
         for (size_t k = 0; k < chunk; ++k) {
             const size_t step = i + k + 1;
             if (npt) {  // scale_box changed atoms.sim_box (transformations.rs:8-13): pressure and dump bounds use the step's box
                 bool pbc[3] = {atoms.sim_box.pbc[0], atoms.sim_box.pbc[1], atoms.sim_box.pbc[2]};
                 atoms.sim_box = SimulationBox::make(&h_trace[9 * k], pbc);
             }
-            if (dump_step > 0 && step % dump_step == 0) {
-                mgr.download(atoms, true, false, false);
-                dumper.write_step(atoms, step);
+            if (dump_step > 0 && step % dump_step == 0) {  // batches end on dump steps, so the device state IS this step's
+                if (async_dump) {
+                    pending_dump = step;
+                    mgr.download_begin(atoms, true, false, false);
+                } else {
+                    mgr.download(atoms, true, false, false);
+                    dumper.write_step(atoms, step);
+                }
             }
             const double ke = th[k].ke, pe = th[k].pe;
             // compute_hamiltonian (simulation.rs:90-115): NVT adds the thermostat's kinetic + potential energy, NPT also
@@ -604,6 +629,8 @@ void Simulation::run(LJCudaManager &mgr, SimulationContext &ctx, FILE *out) {
         }
         i += chunk;
     }
+    flush_dump();
+    if (pos_pinned) pisb_host_unregister(atoms.positions.data());
     mgr.download(atoms, true, true, true);
     std::fflush(out);
 }

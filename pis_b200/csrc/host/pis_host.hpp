@@ -88,6 +88,10 @@ class LJCudaManager {
     void step_npt_mtk(double dt, int64_t nsteps, pisb_mtk &baro, pisb_nhc &chain, int64_t first_step, int64_t total_steps,
                       pisb_thermo *out, double *ext_energy, double *h9_trace);  // verlet_step_npt_mtk x nsteps (potential.rs:112-135)
     void download(Atoms &atoms, bool pos, bool vel, bool frc);
+    // asynchronous position download of a dump step: begin takes a device-side snapshot and copies it on a second stream
+    // while the next batch runs; the array is valid after end
+    void download_begin(Atoms &atoms, bool pos, bool vel, bool frc);
+    void download_end();
     pisb_stats_t stats();
     std::map<std::pair<int, int>, LennardJones> table;
 

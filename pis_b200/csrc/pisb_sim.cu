@@ -100,6 +100,8 @@ struct pisb_handle {
     DevBuf<int> id, s_id, slot_of_id, cell_of, order, nnbr, nbr;
     DevBuf<int> cell_count, cell_start, tile_sum;
     DevBuf<double> mass_d, partials, st_pos, st_vel, st_frc;
+    DevBuf<double> dl_pos, dl_vel, dl_frc;  // snapshot of an asynchronous download (pisb_download_begin / _end)
+    bool dl_pending = false;
     DevBuf<int> st_types;
     DevBuf<PairDev> table_d;
     DevBuf<NhcDev> nhc_d;
@@ -828,6 +830,40 @@ int do_download(pisb_t *h, double *pos, double *vel, double *frc) {
     return PISB_OK;
 }
 
+// pisb_download_begin: snapshot into buffers of its own (the staging arrays belong to uploads and host-buffer steps),
+// copies on copy_stream behind an event, so the main stream is free for the next batch at once.
+int do_download_begin(pisb_t *h, double *pos, double *vel, double *frc) {
+    if (!h->have_atoms) return fail(h, PISB_ERR_STATE, "download before upload");
+    if (h->multi) return fail(h, PISB_ERR_STATE, "pisb_download_begin is a single-GPU entry point (use pisb_download_owned)");
+    if (h->dl_pending) return fail(h, PISB_ERR_STATE, "a download is already in flight: call pisb_download_end first");
+    const int n = h->n;
+    const size_t n3 = (size_t)3 * n;
+    if (pos) TRY(dev_reserve(h, h->dl_pos, n3));
+    if (vel) TRY(dev_reserve(h, h->dl_vel, n3));
+    if (frc) TRY(dev_reserve(h, h->dl_frc, n3));
+    {
+        LaunchScope ls(h, PISB_K_COPY);
+        StoreArgs sa{n, h->xt.p, h->v[0].p, h->v[1].p, h->v[2].p, h->f[0].p, h->f[1].p, h->f[2].p, h->id.p,
+                     pos ? h->dl_pos.p : nullptr, vel ? h->dl_vel.p : nullptr, frc ? h->dl_frc.p : nullptr};
+        k_store_aos<<<nblk(n, TPB), TPB, 0, h->stream>>>(sa);
+        TRY(check_launch(h, "k_store_aos"));
+    }
+    CUDA_TRY(h, cudaEventRecord(h->ev_pos, h->stream));
+    CUDA_TRY(h, cudaStreamWaitEvent(h->copy_stream, h->ev_pos, 0));
+    h->dl_pending = true;
+    if (pos) CUDA_TRY(h, cudaMemcpyAsync(pos, h->dl_pos.p, sizeof(double) * n3, cudaMemcpyDeviceToHost, h->copy_stream));
+    if (vel) CUDA_TRY(h, cudaMemcpyAsync(vel, h->dl_vel.p, sizeof(double) * n3, cudaMemcpyDeviceToHost, h->copy_stream));
+    if (frc) CUDA_TRY(h, cudaMemcpyAsync(frc, h->dl_frc.p, sizeof(double) * n3, cudaMemcpyDeviceToHost, h->copy_stream));
+    return PISB_OK;
+}
+
+int do_download_end(pisb_t *h) {
+    if (!h->dl_pending) return PISB_OK;
+    h->dl_pending = false;
+    CUDA_TRY(h, cudaStreamSynchronize(h->copy_stream));
+    return PISB_OK;
+}
+
 int check_bad_type(pisb_t *h) {
     if (h->h_flags[FLAG_BADTYPE] != 0) {
         int o = h->h_flags[FLAG_BADTYPE];
@@ -971,6 +1007,15 @@ int enqueue_nvt_steps(pisb_t *h, double dt, int64_t cnt, int64_t total_steps, pi
 int capture_step_graph(pisb_t *h, double dt, int m, int64_t nvt_total) {
     if (!h->graph_stream) CUDA_TRY(h, cudaStreamCreateWithFlags(&h->graph_stream, cudaStreamNonBlocking));
     const int64_t launches_before = h->n_launches;
+    // nothing executes during a capture, but the enqueue functions rotate the force / position buffers as they go: a capture
+    // that fails half way must leave the handle's buffer assignment exactly as it found it
+    const DevBuf<double> f_before[3] = {h->f[0], h->f[1], h->f[2]}, g_before[3] = {h->g[0], h->g[1], h->g[2]};
+    const DevBuf<double4> xt_before = h->xt, s_xt_before = h->s_xt;
+    const DevBuf<float4> xf_before = h->xf, xf2_before = h->xf2;
+    auto restore = [&]() {
+        for (int d = 0; d < 3; ++d) h->f[d] = f_before[d], h->g[d] = g_before[d];
+        h->xt = xt_before, h->s_xt = s_xt_before, h->xf = xf_before, h->xf2 = xf2_before;
+    };
     CUDA_TRY(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
     h->capturing = true;
     const int rc = nvt_total > 0 ? enqueue_nvt_steps(h, dt, m, nvt_total, h->thermo_d.p, h->nhc_energy_d.p)
@@ -982,6 +1027,7 @@ int capture_step_graph(pisb_t *h, double dt, int m, int64_t nvt_total) {
     if (rc != PISB_OK || e != cudaSuccess) {
         if (graph) cudaGraphDestroy(graph);
         cudaGetLastError();
+        restore();
         if (rc != PISB_OK) return rc;
         return fail(h, PISB_ERR_CUDA, fmt("cudaStreamEndCapture: %s", cudaGetErrorString(e)));
     }
@@ -1967,12 +2013,16 @@ int pisb_destroy(pisb_t *h) {
     if (!h) return PISB_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);  // a download still in flight
     dev_free(h, h->xt);
     dev_free(h, h->xf);
     dev_free(h, h->xp);
     dev_free(h, h->tablef_d);
     dev_free(h, h->s_xt);
     dev_free(h, h->xf2);
+    dev_free(h, h->dl_pos);
+    dev_free(h, h->dl_vel);
+    dev_free(h, h->dl_frc);
     for (int d = 0; d < 3; ++d) {
         dev_free(h, h->v[d]);
         dev_free(h, h->f[d]);
@@ -2134,6 +2184,40 @@ int pisb_download(pisb_t *h, double *pos, double *vel, double *force) {
     if (!h) return PISB_ERR_INVALID;
     CUDA_TRY(h, cudaSetDevice(h->device));
     return do_download(h, pos, vel, force);
+}
+
+int pisb_download_begin(pisb_t *h, double *pos, double *vel, double *force) {
+    if (!h) return PISB_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    return do_download_begin(h, pos, vel, force);
+}
+
+int pisb_download_end(pisb_t *h) {
+    if (!h) return PISB_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    return do_download_end(h);
+}
+
+int pisb_host_register(void *ptr, size_t bytes) {
+    if (!ptr || bytes == 0) return PISB_ERR_INVALID;
+    const cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        g_create_error = fmt("cudaHostRegister: %s", cudaGetErrorString(e));
+        return e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? PISB_ERR_NO_DEVICE : PISB_ERR_CUDA;
+    }
+    return PISB_OK;
+}
+
+int pisb_host_unregister(void *ptr) {
+    if (!ptr) return PISB_ERR_INVALID;
+    const cudaError_t e = cudaHostUnregister(ptr);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        g_create_error = fmt("cudaHostUnregister: %s", cudaGetErrorString(e));
+        return PISB_ERR_CUDA;
+    }
+    return PISB_OK;
 }
 
 int pisb_thermo_now(pisb_t *h, pisb_thermo *out) {

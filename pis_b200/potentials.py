@@ -221,6 +221,17 @@ class LJCudaManager:
                                        capi._ptr(atoms.forces) if forces else None)
         capi.check(self._h, rc)
 
+    def download_begin(self, atoms: Atoms, positions=True, velocities=False, forces=False):
+        """Asynchronous download for dump steps (Simulation::run, src/simulation.rs:31-37): the device takes a snapshot in
+        stream order and copies it on a second stream while the next batch runs; valid after download_end()."""
+        rc = capi.load().pisb_download_begin(self._h, capi._ptr(atoms.positions) if positions else None,
+                                             capi._ptr(atoms.velocities) if velocities else None,
+                                             capi._ptr(atoms.forces) if forces else None)
+        capi.check(self._h, rc)
+
+    def download_end(self):
+        capi.check(self._h, capi.load().pisb_download_end(self._h))
+
     def thermo_now(self) -> dict:
         t = capi.Thermo()
         capi.check(self._h, capi.load().pisb_thermo_now(self._h, C.byref(t)))

@@ -761,3 +761,36 @@ def test_pipelined_host_step_follows_host_side_edits():
     assert np.array_equal(atoms.positions, x)
     assert force_rel_err(atoms.forces, f).max() <= FORCE_TOL
     assert np.abs(atoms.velocities - v).max() <= 1e-12 * max(1.0, np.abs(v).max())
+
+
+def test_asynchronous_download_is_a_snapshot():
+    """pisb_download_begin snapshots the state in stream order; steps enqueued afterwards must not leak into it."""
+    from pis_b200 import capi
+
+    atoms = fcc_argon(8, temperature=50.0, seed=8, pinned=True)
+    mgr = make_manager(skin=SKIN)
+    mgr.attach(atoms)
+    mgr.compute()
+    mgr.step_nve(0.25, 20)
+    ref = fcc_argon(8, temperature=50.0, seed=8)
+    mgr.download(ref)
+    mgr.download_begin(atoms, positions=True, velocities=True, forces=True)
+    with pytest.raises(capi.PisbError):
+        mgr.download_begin(atoms)                     # one download in flight per handle
+    mgr.step_nve(0.25, 30)                            # the next batch runs while the copy is in flight
+    mgr.download_end()
+    assert np.array_equal(atoms.positions, ref.positions)
+    assert np.array_equal(atoms.velocities, ref.velocities)
+    assert np.array_equal(atoms.forces, ref.forces)
+    mgr.download_end()                                # idempotent
+    # page-locking caller-owned arrays (what the Rust shim does with nalgebra's storage)
+    buf = np.zeros((atoms.n_atoms, 3))
+    lib = capi.load()
+    assert lib.pisb_host_register(capi._ptr(buf), buf.nbytes) == capi.PISB_OK
+    plain = fcc_argon(8, temperature=50.0, seed=8)
+    plain.positions = buf
+    mgr.download_begin(plain, positions=True)
+    mgr.download_end()
+    assert lib.pisb_host_unregister(capi._ptr(buf)) == capi.PISB_OK
+    mgr.download(ref)
+    assert np.array_equal(buf, ref.positions)
