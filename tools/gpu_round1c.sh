@@ -3,7 +3,7 @@
 # bench with the defaults (fused step kernel, pipelined host step) and with both switched off, launch list, smoke.
 mkdir -p gpurun_out
 O=gpurun_out
-timeout 600 python -m pytest tests -m gpu -q -n 4 --durations=12 > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $O/pytest_gpu.log
+timeout 480 python -m pytest tests -m gpu -q -n 6 --durations=12 > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $O/pytest_gpu.log
 tail -n 30 $O/pytest_gpu.log
 timeout 200 ncu --set full --clock-control none --import-source on -k regex:"k_force_vv" -s 1 -c 1 -f -o $O/prof_force_vv python tools/prof_one.py 0 0 100 6 43 0 > $O/ncu_fvv.log 2>&1; tail -n 2 $O/ncu_fvv.log
 python tools/ncu_summary.py $O/prof_force_vv.ncu-rep > $O/prof_force_vv.summary.json 2>$O/ncu_summary.err
