@@ -1051,17 +1051,19 @@ __device__ __forceinline__ void force2_body(const Force2Args &a, int i, int (*q)
 // as one int4 per 4 neighbours and prefetched one tile ahead (the index stream comes from DRAM), four
 // gathers are in flight per thread, rint is the magic-constant form and interior warps skip the image
 // search.  Same results as v1/v2, bit for bit.
-template <bool MULTI, bool IMAGE>
+template <bool MULTI, bool IMAGE, bool TILE_EF = false>
 __device__ __forceinline__ void force3_body(const Force2Args &a, int i, double &fx, double &fy, double &fz, double &pe,
                                             double &vir) {
     const double4 xi = a.xt[i];
     const int ti = MULTI ? type_of(xi.w) : 1;
     const int nn = a.nnbr[i];
     const int4 *tiles = reinterpret_cast<const int4 *>(a.nbr) + i;
-    int4 cur = nn > 0 ? ldg_stream_i4(tiles) : make_int4(i, i, i, i);
+    const unsigned long long pol = TILE_EF ? l2_evict_first_policy() : 0ull;
+    auto load_tile = [&](const int4 *p) { return TILE_EF ? ldg_stream_i4_ef(p, pol) : ldg_stream_i4(p); };
+    int4 cur = nn > 0 ? load_tile(tiles) : make_int4(i, i, i, i);
     for (int k = 0; k < nn; k += 4) {
         int4 nxt = cur;
-        if (k + 4 < nn) nxt = ldg_stream_i4(tiles + (size_t)((k >> 2) + 1) * a.npad);
+        if (k + 4 < nn) nxt = load_tile(tiles + (size_t)((k >> 2) + 1) * a.npad);
         int j[4] = {cur.x, cur.y, cur.z, cur.w};
         bool in[4];
         double4 xj[4];
@@ -1154,33 +1156,47 @@ struct ForceVVArgs {
     int *flags;
 };
 
-template <bool MULTI, bool DRIFT>
+// HINT (experiment switches, option fuse_vv = 1 + HINT): bit 0 = the epilogue's streams use evict-first loads / stores
+// (__ldcs / __stcs), bit 1 = its operands are prefetched into L2 when the thread starts, bit 2 = the index tiles carry an
+// L2 evict-first policy.
+template <bool MULTI, bool DRIFT, int HINT>
 __global__ void __launch_bounds__(TPB_FORCE, 8) k_force_vv(ForceVVArgs b) {
     const Force2Args &a = b.f;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double red[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};  // pe, pair virial, ke, x*fx, y*fy, z*fz
     const bool active = i < a.n;
+    constexpr bool STREAM = (HINT & 1) != 0, PREFETCH = (HINT & 2) != 0, TILE_EF = (HINT & 4) != 0;
+    auto lds = [&](const double *p) { return STREAM ? __ldcs(p) : *p; };
+    auto sts = [&](double *p, double v) {
+        if (STREAM) __stcs(p, v);
+        else *p = v;
+    };
     bool interior = true;
     if (active) interior = is_interior(a.boxf, a.xf[i]);
     const bool warp_interior = __all_sync(0xffffffffu, interior);
     if (active) {
+        if (PREFETCH && (threadIdx.x & 15) == 0) {  // one request per 128-byte line of each stream
+            prefetch_l2(b.vx + i), prefetch_l2(b.vy + i), prefetch_l2(b.vz + i);
+            prefetch_l2(b.gx + i), prefetch_l2(b.gy + i), prefetch_l2(b.gz + i);
+            if (DRIFT && !b.always_rebuild) prefetch_l2(b.xbx + i), prefetch_l2(b.xby + i), prefetch_l2(b.xbz + i);
+        }
         double fx = 0.0, fy = 0.0, fz = 0.0, pe = 0.0, vir = 0.0;
-        if (warp_interior) force3_body<MULTI, false>(a, i, fx, fy, fz, pe, vir);
-        else force3_body<MULTI, true>(a, i, fx, fy, fz, pe, vir);
-        a.fx[i] = fx;
-        a.fy[i] = fy;
-        a.fz[i] = fz;
+        if (warp_interior) force3_body<MULTI, false, TILE_EF>(a, i, fx, fy, fz, pe, vir);
+        else force3_body<MULTI, true, TILE_EF>(a, i, fx, fy, fz, pe, vir);
+        sts(a.fx + i, fx);
+        sts(a.fy + i, fy);
+        sts(a.fz + i, fz);
         red[0] = pe;
         red[1] = vir;
         // ---- integrator epilogue ----
         double4 x = a.xt[i];  // L1/L2 hit: this thread read it at the top of the force loop
-        double vx = b.vx[i], vy = b.vy[i], vz = b.vz[i];
-        const double gx = b.gx[i], gy = b.gy[i], gz = b.gz[i];
+        double vx = lds(b.vx + i), vy = lds(b.vy + i), vz = lds(b.vz + i);
+        const double gx = lds(b.gx + i), gy = lds(b.gy + i), gz = lds(b.gz + i);
         double bx = 0.0, by = 0.0, bz = 0.0;
         if (DRIFT && !b.always_rebuild) {
-            bx = b.xbx[i];
-            by = b.xby[i];
-            bz = b.xbz[i];
+            bx = lds(b.xbx + i);
+            by = lds(b.xby + i);
+            bz = lds(b.xbz + i);
         }
         const double m = b.mass[type_of(x.w) - 1];
         const double ax = __ddiv_rn(fx, m), ay = __ddiv_rn(fy, m), az = __ddiv_rn(fz, m);
@@ -1188,9 +1204,9 @@ __global__ void __launch_bounds__(TPB_FORCE, 8) k_force_vv(ForceVVArgs b) {
         vx = __dadd_rn(vx, __dmul_rn(__dmul_rn(__dadd_rn(ox, ax), 0.5), b.dt));
         vy = __dadd_rn(vy, __dmul_rn(__dmul_rn(__dadd_rn(oy, ay), 0.5), b.dt));
         vz = __dadd_rn(vz, __dmul_rn(__dmul_rn(__dadd_rn(oz, az), 0.5), b.dt));
-        b.vx[i] = vx;
-        b.vy[i] = vy;
-        b.vz[i] = vz;
+        sts(b.vx + i, vx);
+        sts(b.vy + i, vy);
+        sts(b.vz + i, vz);
         red[2] = __dmul_rn(__dmul_rn(0.5, m), norm2(vx, vy, vz));
         red[3] = __dmul_rn(x.x, fx);
         red[4] = __dmul_rn(x.y, fy);
@@ -1200,7 +1216,7 @@ __global__ void __launch_bounds__(TPB_FORCE, 8) k_force_vv(ForceVVArgs b) {
             x.y = __dadd_rn(x.y, __dadd_rn(__dmul_rn(vy, b.dt), __dmul_rn(__dmul_rn(ay, 0.5), b.dt2)));
             x.z = __dadd_rn(x.z, __dadd_rn(__dmul_rn(vz, b.dt), __dmul_rn(__dmul_rn(az, 0.5), b.dt2)));
             wrap_pos<true>(a.box, x.x, x.y, x.z);
-            b.xt_out[i] = x;
+            b.xt_out[i] = x;  // gathered by the next launch: default policy
             b.xf_out[i] = make_float4((float)x.x, (float)x.y, (float)x.z, __int_as_float(type_of(x.w)));
             if (b.always_rebuild) {
                 if (i == 0) b.flags[FLAG_REBUILD] = 1;

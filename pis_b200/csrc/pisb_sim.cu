@@ -695,13 +695,24 @@ int launch_force_vv(pisb_t *h, bool drift, double dt, pisb_thermo *rec) {
         const bool multi = h->n_types > 1;
         const int nb = nblk(h->n, TPB_FORCE);
         cudaStream_t st = h->stream;
-        if (drift) {
-            if (multi) k_force_vv<true, true><<<nb, TPB_FORCE, 0, st>>>(fv);
-            else k_force_vv<false, true><<<nb, TPB_FORCE, 0, st>>>(fv);
-        } else {
-            if (multi) k_force_vv<true, false><<<nb, TPB_FORCE, 0, st>>>(fv);
-            else k_force_vv<false, false><<<nb, TPB_FORCE, 0, st>>>(fv);
+#define FVV(HINT)                                                                     \
+    do {                                                                              \
+        if (drift) {                                                                  \
+            if (multi) k_force_vv<true, true, HINT><<<nb, TPB_FORCE, 0, st>>>(fv);    \
+            else k_force_vv<false, true, HINT><<<nb, TPB_FORCE, 0, st>>>(fv);         \
+        } else {                                                                      \
+            if (multi) k_force_vv<true, false, HINT><<<nb, TPB_FORCE, 0, st>>>(fv);   \
+            else k_force_vv<false, false, HINT><<<nb, TPB_FORCE, 0, st>>>(fv);        \
+        }                                                                             \
+    } while (0)
+        switch (h->fuse_vv - 1) {
+            case 1: FVV(1); break;
+            case 3: FVV(3); break;
+            case 5: FVV(5); break;
+            case 7: FVV(7); break;
+            default: FVV(0); break;
         }
+#undef FVV
     }
     for (int d = 0; d < 3; ++d) std::swap(h->f[d], h->g[d]);
     if (drift) swap_position_buffers(h);
@@ -2674,7 +2685,7 @@ int pisb_set_option(pisb_t *h, const char *name, double value) {
         return PISB_OK;
     }
     if (!std::strcmp(name, "fuse_vv")) {
-        h->fuse_vv = value != 0.0 ? 1 : 0;
+        h->fuse_vv = value > 0.0 ? (int)value : 0;  // 1 + HINT bits of k_force_vv (experiment switches)
         return PISB_OK;
     }
     if (!std::strcmp(name, "force_variant")) {

@@ -14,6 +14,9 @@ m.insert((1, 1), LennardJones(0.238, 3.405, 2.5 * 3.405))
 m.set_option("force_variant", fv)
 m.set_option("build_variant", bv)
 m.set_option("cell_div", int(sys.argv[6]) if len(sys.argv) > 6 else 0)
+for kv in sys.argv[7:]:   # further library options name=value, e.g. cuda_graphs=0 (ncu cannot profile kernel nodes of graphs
+    name, _, val = kv.partition("=")   # that hold conditional nodes), fuse_vv=0
+    m.set_option(name, float(val))
 m.attach(atoms)
 m.compute()
 m.step_nve(0.25, steps)
