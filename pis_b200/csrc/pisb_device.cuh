@@ -135,15 +135,29 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// Deterministic block reduction of NQ doubles per thread into partials[q * nblocks + blockIdx.x];
-// the last block to finish (ticket) sums the partials in fixed order and calls fin(q, sum).
-// All threads of the block must call this.  smem: NQ * 32 doubles.
+// Deterministic grid reduction of NQ doubles per thread, in three fixed-order levels:
+//   block   : warp shuffles + shared memory                       -> partials[q * nblocks + block]
+//   group   : the LAST block of every RED_GROUP consecutive blocks (a ticket per group) sums the group's partials
+//                                                                  -> level1[q * ngroups + group]
+//   grid    : the last group to finish (ticket[0]) sums the group sums and calls fin(q, sum).
+// Every sum has a fixed association, so results do not depend on scheduling.  A single last block summing ALL block
+// partials (31 250 x NQ loads from one SM at 4M atoms) was a 60 us (NQ = 2) to 240 us (NQ = 6) serial tail of the force
+// kernels; with groups the last block reads 64 + nblocks/64 values per quantity.
+// All threads of the block must call this.  partials: NQ * (nblocks + ngroups) doubles; ticket: 1 + ngroups words, zeroed
+// once (they reset themselves).
+constexpr int RED_GROUP = 64;
+
+__host__ __device__ inline unsigned int red_groups(unsigned int nblocks) { return (nblocks + RED_GROUP - 1) / RED_GROUP; }
+
 template <int NQ, int NT, typename Fin>
 __device__ __forceinline__ void block_reduce_finalize(double (&v)[NQ], double *__restrict__ partials,
                                                       unsigned int *__restrict__ ticket, Fin fin) {
     __shared__ double s_red[NQ][NT / 32];
-    __shared__ bool s_last;
+    __shared__ bool s_group_last, s_grid_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned int nb = gridDim.x, ng = red_groups(nb), g = blockIdx.x / RED_GROUP;
+    const unsigned int b0 = g * RED_GROUP, gs = min((unsigned int)RED_GROUP, nb - b0);
+    double *__restrict__ level1 = partials + (size_t)NQ * nb;
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
         double w = warp_sum(v[q]);
@@ -155,23 +169,40 @@ __device__ __forceinline__ void block_reduce_finalize(double (&v)[NQ], double *_
         for (int q = 0; q < NQ; ++q) {
             double w = lane < NT / 32 ? s_red[q][lane] : 0.0;
             w = warp_sum(w);
-            if (lane == 0) partials[(size_t)q * gridDim.x + blockIdx.x] = w;
+            if (lane == 0) partials[(size_t)q * nb + blockIdx.x] = w;
         }
     }
     if (threadIdx.x == 0) {
         __threadfence();
-        unsigned int t = atomicAdd(ticket, 1u);
-        s_last = (t == gridDim.x - 1);
+        s_group_last = atomicAdd(&ticket[1 + g], 1u) == gs - 1;
+        s_grid_last = false;
     }
     __syncthreads();
-    if (!s_last) return;
+    if (!s_group_last) return;
+    // ---- last block of its group: lanes take the partials b0 + lane, b0 + lane + 32, then the shuffle tree ----
+    if (warp == 0) {
+        __threadfence();
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            double acc = 0.0;
+            for (unsigned int k = lane; k < gs; k += 32) acc += __ldcg(&partials[(size_t)q * nb + b0 + k]);
+            acc = warp_sum(acc);
+            if (lane == 0) level1[(size_t)q * ng + g] = acc;
+        }
+        if (lane == 0) {
+            ticket[1 + g] = 0u;
+            __threadfence();
+            s_grid_last = atomicAdd(&ticket[0], 1u) == ng - 1;
+        }
+    }
+    __syncthreads();
+    if (!s_grid_last) return;
     __threadfence();
-    // fixed-order sum over blocks: thread t takes blocks t, t+NT, ... then the block tree
+    // ---- last group: thread t takes the group sums t, t+NT, ... then the block tree ----
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
         double acc = 0.0;
-        for (unsigned int b = threadIdx.x; b < gridDim.x; b += NT)
-            acc += __ldcg(&partials[(size_t)q * gridDim.x + b]);
+        for (unsigned int b = threadIdx.x; b < ng; b += NT) acc += __ldcg(&level1[(size_t)q * ng + b]);
         double w = warp_sum(acc);
         __syncthreads();
         if (lane == 0) s_red[q][warp] = w;
@@ -182,7 +213,7 @@ __device__ __forceinline__ void block_reduce_finalize(double (&v)[NQ], double *_
             if (lane == 0) fin(q, z);
         }
     }
-    if (threadIdx.x == 0) *ticket = 0u;
+    if (threadIdx.x == 0) ticket[0] = 0u;
 }
 
 }  // namespace pisb

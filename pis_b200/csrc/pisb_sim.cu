@@ -112,6 +112,7 @@ struct pisb_handle {
     DevBuf<pisb_thermo> thermo_d;
     int *flags = nullptr;
     unsigned int *ticket = nullptr;
+    size_t ticket_cap = 0;  // words: 1 + one per group of 64 blocks (block_reduce_finalize)
     int *h_flags = nullptr;          // pinned
     pisb_thermo *h_thermo = nullptr; // pinned
     size_t h_thermo_cap = 0;
@@ -495,8 +496,22 @@ int reserve_atoms(pisb_t *h, int n) {
     TRY(dev_reserve(h, h->cell_of, cap));
     TRY(dev_reserve(h, h->order, cap));
     TRY(dev_reserve(h, h->nnbr, cap));
-    // per-block partial sums: up to 6 quantities x blocks (k_force_vv); small systems run the force kernel with 8 lanes per atom
-    TRY(dev_reserve(h, h->partials, (size_t)6 * (nblk(n, TPB_FORCE) + 1) + (size_t)4 * (nblk(std::min(n, 75000) * 8, TPB_FORCE) + 1)));
+    // block_reduce_finalize: NQ x (blocks + groups) partial sums and 1 + groups tickets for the largest user --
+    // k_force_vv (6 quantities, 128-thread blocks), k_npt_post (19 quantities, 256-thread blocks), k_force_split<8> (2
+    // quantities, 8 lanes per atom below 75k atoms)
+    auto need = [](size_t nq, size_t blocks) { return nq * (blocks + red_groups((unsigned int)blocks) + 2); };
+    const size_t b_force = (size_t)nblk(n, TPB_FORCE), b_stream = (size_t)nblk(n, TPB), b_split = (size_t)nblk(std::min(n, 75000) * 8, TPB_FORCE);
+    TRY(dev_reserve(h, h->partials, std::max(need(6, b_force), std::max(need(19, b_stream), need(2, b_split)))));
+    const size_t tickets = 2 + red_groups((unsigned int)std::max(b_force, b_split));
+    if (tickets > h->ticket_cap) {
+        // zero-initialised once; the words reset themselves at the end of every reduction
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        if (h->ticket) cudaFree(h->ticket);
+        h->ticket = nullptr;
+        CUDA_TRY(h, cudaMalloc((void **)&h->ticket, sizeof(unsigned int) * tickets * 2));
+        h->ticket_cap = tickets * 2;
+        CUDA_TRY(h, cudaMemsetAsync(h->ticket, 0, sizeof(unsigned int) * h->ticket_cap, h->stream));
+    }
     return PISB_OK;
 }
 
@@ -1332,7 +1347,7 @@ int do_step_npt(pisb_t *h, double dt, int64_t nsteps, pisb_mtk *baro, pisb_nhc *
     TRY(dev_reserve(h, h->nhc_d, 1));
     TRY(dev_reserve(h, h->nhc_energy_d, 1));
     TRY(dev_reserve(h, h->npt_tensors_d, 19));
-    TRY(dev_reserve(h, h->partials, (size_t)19 * (nblk(h->n, TPB) + 1)));
+    TRY(dev_reserve(h, h->partials, (size_t)19 * (nblk(h->n, TPB) + red_groups((unsigned int)nblk(h->n, TPB)) + 2)));
     TRY(reserve_thermo(h, 4));
     if (!h->h_npt) CUDA_TRY(h, cudaHostAlloc((void **)&h->h_npt, sizeof(double) * 32, cudaHostAllocDefault));
     NhcDev init{};
@@ -2009,11 +2024,12 @@ int pisb_create(int device, int n_types, const double *mass, const double *eps, 
         cudaEventCreateWithFlags(&h->ev_pos, cudaEventDisableTiming) != cudaSuccess)
         return bail(fail(h, PISB_ERR_CUDA, "cudaStreamCreate failed"));
     if (cudaMalloc((void **)&h->flags, sizeof(int) * FLAG_COUNT) != cudaSuccess ||
-        cudaMalloc((void **)&h->ticket, sizeof(unsigned int)) != cudaSuccess ||
+        cudaMalloc((void **)&h->ticket, sizeof(unsigned int) * 64) != cudaSuccess ||
         cudaHostAlloc((void **)&h->h_flags, sizeof(int) * FLAG_COUNT, cudaHostAllocDefault) != cudaSuccess)
         return bail(fail(h, PISB_ERR_CUDA, "allocating control words failed"));
     cudaMemsetAsync(h->flags, 0, sizeof(int) * FLAG_COUNT, h->stream);
-    cudaMemsetAsync(h->ticket, 0, sizeof(unsigned int), h->stream);
+    h->ticket_cap = 64;
+    cudaMemsetAsync(h->ticket, 0, sizeof(unsigned int) * 64, h->stream);
     int rc = build_pair_table(h);
     if (rc != PISB_OK) return bail(rc);
     *out = h;
