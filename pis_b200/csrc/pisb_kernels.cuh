@@ -1817,8 +1817,9 @@ __device__ __forceinline__ int build3_body(const Build2Args &a, const float *__r
     return cnt;
 }
 
-template <bool MULTI>
-__global__ void __launch_bounds__(TPB_FORCE) k_build_list_v3(Build2Args a, const float *__restrict__ xp, int fast_ok) {
+// MINB: resident blocks per SM the register allocation aims for (8 -> 64 registers, 10 -> 48, 12 -> 40)
+template <bool MULTI, int MINB = 8>
+__global__ void __launch_bounds__(TPB_FORCE, MINB) k_build_list_v3(Build2Args a, const float *__restrict__ xp, int fast_ok) {
     if (a.flags[FLAG_REBUILD] == 0) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < a.n && xf_is_ghost(a.xf[i])) a.nnbr[i] = 0;

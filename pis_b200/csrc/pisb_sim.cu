@@ -76,6 +76,7 @@ struct pisb_handle {
     int force_variant = 0;  // 0 = auto (v3 when orthorhombic + fully periodic, else v1), 1 = v1, 2 = v2, 3 = v3
     int build_variant = 0;
     int cell_div = 0;  // cells per list cutoff per dimension: 0 = auto, 1 = reference-sized cells, 2 = half-size cells
+    int build_minb = 8;  // option "build_minb" (experiment): resident blocks per SM k_build_list_v3 is compiled for
     int fuse_vv = 1;   // option "fuse_vv": NVE batches run k_force_vv (force + kick + drift in one launch) when the default force kernel applies
 
     // box / grid
@@ -588,6 +589,9 @@ int launch_rebuild_chain(pisb_t *h) {
                 else k_build_list_v2<false><<<nb, TPB_FORCE, 0, st>>>(b2);
             } else {  // default: v3, packed FP32 pair records + bit-mask append for interior warps
                 if (multi) k_build_list_v3<true><<<nb, TPB_FORCE, 0, st>>>(b2, h->xp.p, 1);
+                else if (h->build_minb == 10) k_build_list_v3<false, 10><<<nb, TPB_FORCE, 0, st>>>(b2, h->xp.p, 1);
+                else if (h->build_minb == 12) k_build_list_v3<false, 12><<<nb, TPB_FORCE, 0, st>>>(b2, h->xp.p, 1);
+                else if (h->build_minb == 6) k_build_list_v3<false, 6><<<nb, TPB_FORCE, 0, st>>>(b2, h->xp.p, 1);
                 else k_build_list_v3<false><<<nb, TPB_FORCE, 0, st>>>(b2, h->xp.p, 1);
             }
         } else if (h->box.ortho) {
@@ -1012,7 +1016,7 @@ void graph_signature(pisb_t *h, double dt, std::vector<unsigned char> &sig) {
                           h->tile_sum.p, h->mass_d.p, h->partials.p, h->table_d.p, h->thermo_d.p, h->flags, h->ticket, h->nhc_d.p,
                           h->nhc_energy_d.p};
     put(ptrs, sizeof ptrs);
-    const int ints[] = {h->n, h->npad, h->kcap, h->n_types, h->force_variant, h->build_variant, h->cell_div, h->fuse_vv};
+    const int ints[] = {h->n, h->npad, h->kcap, h->n_types, h->force_variant, h->build_variant, h->cell_div, h->fuse_vv, h->build_minb};
     put(ints, sizeof ints);
     const double dbl[] = {dt, h->skin, h->skin_half2_override, h->max_rcut};
     put(dbl, sizeof dbl);
@@ -2698,6 +2702,10 @@ int pisb_set_option(pisb_t *h, const char *name, double value) {
     }
     if (!std::strcmp(name, "host_chunk_atoms")) {
         h->host_chunk_atoms = value > 0 ? (int)value : 0;
+        return PISB_OK;
+    }
+    if (!std::strcmp(name, "build_minb")) {
+        h->build_minb = (int)value;
         return PISB_OK;
     }
     if (!std::strcmp(name, "fuse_vv")) {
