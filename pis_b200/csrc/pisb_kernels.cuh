@@ -1696,7 +1696,6 @@ __device__ __forceinline__ PairRec ldg_pair(const float *xp, int q) {
     return r;
 }
 
-constexpr int B3_PAIRS = 4;  // pair records in flight per thread (8 candidates)
 
 // The exact reference predicate for a guard-band candidate (rare).  Out of line, by-value arguments only (taking the
 // address of a kernel parameter would force a local copy of the whole argument struct).  v2_possible() => fully periodic.
@@ -1711,7 +1710,11 @@ __device__ __noinline__ bool build3_exact_out(double h0, double h1, double h2, d
     return norm2(__dmul_rn(h0, sx), __dmul_rn(h1, sy), __dmul_rn(h2, sz)) > t_list;
 }
 
-template <bool IMAGE>
+// B3_PAIRS: pair records in flight per thread (2 candidates each).  ROW_PF: the cell_start words of the NEXT stencil row
+// are loaded while the current row is scanned (a row is ~7 pair records: without it every row starts with two dependent
+// load latencies -- cell_start, then the first records -- that nothing overlaps; ncu: 44 % of the stall cycles were
+// long-scoreboard at 6.6 warps per scheduler).
+template <bool IMAGE, int B3_PAIRS = 4, bool ROW_PF = false>
 __device__ __forceinline__ int build3_body(const Build2Args &a, const float *__restrict__ xp, int i) {
     int cnt = 0;
     const double4 xi = a.xt[i];
@@ -1786,6 +1789,51 @@ __device__ __forceinline__ int build3_body(const Build2Args &a, const float *__r
         }
     };
     const int nx = a.g.n[0];
+    if (ROW_PF) {
+        const int xlo = c[0] + a.g.lo[0], xhi = c[0] + a.g.hi[0];
+        const int xa = max(xlo, 0), xb = min(xhi, nx - 1) + 1;
+        // row (dy, dz) of the stencil -> first cell of the grid row it maps to, or -1 if the row is skipped
+        auto row_base = [&](int dy, int dz) {
+            int cz = c[2] + dz, cy = c[1] + dy;
+            if (cz < 0 || cz >= a.g.n[2]) {
+                if (!IMAGE || a.g.local[2]) return -1;
+                cz += cz < 0 ? a.g.n[2] : -a.g.n[2];
+            }
+            if (cy < 0 || cy >= a.g.n[1]) {
+                if (!IMAGE || a.g.local[1]) return -1;
+                cy += cy < 0 ? a.g.n[1] : -a.g.n[1];
+            }
+            return (cz * a.g.n[1] + cy) * nx;
+        };
+        int dy_n = a.g.lo[1], dz_n = a.g.lo[2];
+        int rb_n = row_base(dy_n, dz_n), jb_n = 0, je_n = 0;
+        if (rb_n >= 0) {
+            jb_n = __ldg(&a.cell_start[rb_n + xa]);
+            je_n = __ldg(&a.cell_start[rb_n + xb]);
+        }
+        while (dz_n <= a.g.hi[2]) {
+            const int rb = rb_n, jb = jb_n, je = je_n;
+            if (++dy_n > a.g.hi[1]) dy_n = a.g.lo[1], ++dz_n;
+            if (dz_n <= a.g.hi[2]) {
+                rb_n = row_base(dy_n, dz_n);
+                if (rb_n >= 0) {
+                    jb_n = __ldg(&a.cell_start[rb_n + xa]);
+                    je_n = __ldg(&a.cell_start[rb_n + xb]);
+                }
+            }
+            if (rb < 0) continue;
+            if (IMAGE && xlo < 0 && !a.g.local[0]) scan(__ldg(&a.cell_start[rb + xlo + nx]), __ldg(&a.cell_start[rb + nx]));
+            if (i >= jb && i < je) {
+                scan(jb, i);
+                scan(i + 1, je);
+            } else {
+                scan(jb, je);
+            }
+            if (IMAGE && xhi >= nx && !a.g.local[0]) scan(__ldg(&a.cell_start[rb]), __ldg(&a.cell_start[rb + xhi - nx + 1]));
+        }
+        a.nnbr[i] = cnt < a.kcap ? cnt : a.kcap;
+        return cnt;
+    }
     for (int dz = a.g.lo[2]; dz <= a.g.hi[2]; ++dz) {
         int cz = c[2] + dz;
         if (cz < 0 || cz >= a.g.n[2]) {
@@ -1818,7 +1866,7 @@ __device__ __forceinline__ int build3_body(const Build2Args &a, const float *__r
 }
 
 // MINB: resident blocks per SM the register allocation aims for (8 -> 64 registers, 10 -> 48, 12 -> 40)
-template <bool MULTI, int MINB = 8>
+template <bool MULTI, int MINB = 8, int NP = 4, bool ROW_PF = false>
 __global__ void __launch_bounds__(TPB_FORCE, MINB) k_build_list_v3(Build2Args a, const float *__restrict__ xp, int fast_ok) {
     if (a.flags[FLAG_REBUILD] == 0) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1829,7 +1877,7 @@ __global__ void __launch_bounds__(TPB_FORCE, MINB) k_build_list_v3(Build2Args a,
     const bool warp_interior = __all_sync(0xffffffffu, interior);
     int cnt = 0;
     if (active) {
-        if (!MULTI && fast_ok) cnt = warp_interior ? build3_body<false>(a, xp, i) : build3_body<true>(a, xp, i);
+        if (!MULTI && fast_ok) cnt = warp_interior ? build3_body<false, NP, ROW_PF>(a, xp, i) : build3_body<true, NP, ROW_PF>(a, xp, i);
         else cnt = warp_interior ? build2_body<MULTI, false>(a, i) : build2_body<MULTI, true>(a, i);
     }
     int m = cnt;

@@ -589,9 +589,15 @@ int launch_rebuild_chain(pisb_t *h) {
                 else k_build_list_v2<false><<<nb, TPB_FORCE, 0, st>>>(b2);
             } else {  // default: v3, packed FP32 pair records + bit-mask append for interior warps
                 if (multi) k_build_list_v3<true><<<nb, TPB_FORCE, 0, st>>>(b2, h->xp.p, 1);
+                // experiment switch build_minb = MINB + 100 * (pair records in flight) + 1000 * (row prefetch)
                 else if (h->build_minb == 10) k_build_list_v3<false, 10><<<nb, TPB_FORCE, 0, st>>>(b2, h->xp.p, 1);
                 else if (h->build_minb == 12) k_build_list_v3<false, 12><<<nb, TPB_FORCE, 0, st>>>(b2, h->xp.p, 1);
-                else if (h->build_minb == 6) k_build_list_v3<false, 6><<<nb, TPB_FORCE, 0, st>>>(b2, h->xp.p, 1);
+                else if (h->build_minb == 1008) k_build_list_v3<false, 8, 4, true><<<nb, TPB_FORCE, 0, st>>>(b2, h->xp.p, 1);
+                else if (h->build_minb == 1010) k_build_list_v3<false, 10, 4, true><<<nb, TPB_FORCE, 0, st>>>(b2, h->xp.p, 1);
+                else if (h->build_minb == 210) k_build_list_v3<false, 10, 2, false><<<nb, TPB_FORCE, 0, st>>>(b2, h->xp.p, 1);
+                else if (h->build_minb == 1210) k_build_list_v3<false, 10, 2, true><<<nb, TPB_FORCE, 0, st>>>(b2, h->xp.p, 1);
+                else if (h->build_minb == 808) k_build_list_v3<false, 8, 8, false><<<nb, TPB_FORCE, 0, st>>>(b2, h->xp.p, 1);
+                else if (h->build_minb == 1808) k_build_list_v3<false, 8, 8, true><<<nb, TPB_FORCE, 0, st>>>(b2, h->xp.p, 1);
                 else k_build_list_v3<false><<<nb, TPB_FORCE, 0, st>>>(b2, h->xp.p, 1);
             }
         } else if (h->box.ortho) {
