@@ -90,6 +90,24 @@ class ClockSampler:
                 "samples": len(self.rows), "reasons": reasons}
 
 
+def measure_pcie(n_doubles: int, reps: int = 4) -> dict:
+    """Host<->device copy rates of one 3N-double array from / to pinned memory, each direction alone."""
+    import torch
+
+    host = torch.empty(n_doubles, dtype=torch.float64).pin_memory()
+    dev = torch.empty(n_doubles, dtype=torch.float64, device="cuda")
+    out = {}
+    for name, fn in (("h2d_GBps", lambda: dev.copy_(host, non_blocking=True)), ("d2h_GBps", lambda: host.copy_(dev, non_blocking=True))):
+        fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        out[name] = 8.0 * n_doubles * reps / (time.perf_counter() - t0) / 1e9
+    return out
+
+
 def argon_oracle(atoms):
     from oracle.pis_oracle import Oracle
 
@@ -261,6 +279,9 @@ def run_single(args):
                           "unit": "GB/s", "frac": vv_bytes * n / (vv_ms * 1e-3) / 1e9 / peak, "ms_per_launch": vv_ms,
                           "launches": tim["integrate"]["launches"], "algorithmic_bytes_per_atom": vv_bytes}
 
+    # ---- the link the end-to-end call lives on: pinned 3N-double copies each way (torch plumbing, no product code) ----
+    pcie = measure_pcie(3 * n)
+
     # ---- end-to-end: the reference-facing trait call with HOST buffers, every step ----
     e2e_steps = max(3, min(args.e2e_steps, args.steps))
     mgr.download(atoms)
@@ -273,13 +294,18 @@ def run_single(args):
     e2e_s = time.perf_counter() - t0
     e2e = {"value": n * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 72 * n, "d2h_bytes_per_step": 72 * n + 32,
            "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
-           "call": "LJCudaManager.verlet_step_nve(atoms, dt) == pisb_verlet_step_nve_host: pinned host x,v,F up, "
-                   "one step, x,v,F + PE down"}
+           "call": "LJCudaManager.verlet_step_nve(atoms, dt) == pisb_verlet_step_nve_host: pinned host x,v,F up in chunks, "
+                   "drift per chunk, x(t+dt) down under the upload, force + kick, v,F + PE down in chunks",
+           "pcie": pcie,
+           # x, v, F up, then (after the force pass) v, F down; x(t+dt) can hide under the upload
+           "pcie_floor_ms": 1e3 * (72.0 * n / (pcie["h2d_GBps"] * 1e9) + 48.0 * n / (pcie["d2h_GBps"] * 1e9))}
 
     # ---- the same loop the C++ host's Simulation::run drives (device-resident; reported beside the strict e2e) ----
     mgr.attach(atoms)
     mgr.compute()
     mgr.step_nve(DT, 10)
+    mgr.download_begin(atoms, positions=True, velocities=False, forces=False)   # untimed: allocates the snapshot buffer
+    mgr.download_end()
     mgr.synchronize()
     t0 = time.perf_counter()
     d2h_res = 0

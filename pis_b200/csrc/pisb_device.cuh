@@ -50,22 +50,6 @@ __device__ __forceinline__ int4 ldg_stream_i4(const int4 *p) {
     return v;
 }
 
-// The same tile load carrying an L2 evict-first policy (createpolicy.fractional.L2::evict_first): the index stream is
-// read once per step and should not push gathered position sectors out of the 126 MB L2.
-__device__ __forceinline__ unsigned long long l2_evict_first_policy() {
-    unsigned long long pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ int4 ldg_stream_i4_ef(const int4 *p, unsigned long long pol) {
-    int4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;"
-                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                 : "l"(p), "l"(pol));
-    return v;
-}
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
 __device__ __forceinline__ int type_of(double w) { return (int)__double_as_longlong(w); }
 __device__ __forceinline__ double type_as_double(int t) { return __longlong_as_double((long long)t); }
 

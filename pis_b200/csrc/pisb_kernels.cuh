@@ -1051,19 +1051,17 @@ __device__ __forceinline__ void force2_body(const Force2Args &a, int i, int (*q)
 // as one int4 per 4 neighbours and prefetched one tile ahead (the index stream comes from DRAM), four
 // gathers are in flight per thread, rint is the magic-constant form and interior warps skip the image
 // search.  Same results as v1/v2, bit for bit.
-template <bool MULTI, bool IMAGE, bool TILE_EF = false>
+template <bool MULTI, bool IMAGE>
 __device__ __forceinline__ void force3_body(const Force2Args &a, int i, double &fx, double &fy, double &fz, double &pe,
                                             double &vir) {
     const double4 xi = a.xt[i];
     const int ti = MULTI ? type_of(xi.w) : 1;
     const int nn = a.nnbr[i];
     const int4 *tiles = reinterpret_cast<const int4 *>(a.nbr) + i;
-    const unsigned long long pol = TILE_EF ? l2_evict_first_policy() : 0ull;
-    auto load_tile = [&](const int4 *p) { return TILE_EF ? ldg_stream_i4_ef(p, pol) : ldg_stream_i4(p); };
-    int4 cur = nn > 0 ? load_tile(tiles) : make_int4(i, i, i, i);
+    int4 cur = nn > 0 ? ldg_stream_i4(tiles) : make_int4(i, i, i, i);
     for (int k = 0; k < nn; k += 4) {
         int4 nxt = cur;
-        if (k + 4 < nn) nxt = load_tile(tiles + (size_t)((k >> 2) + 1) * a.npad);
+        if (k + 4 < nn) nxt = ldg_stream_i4(tiles + (size_t)((k >> 2) + 1) * a.npad);
         int j[4] = {cur.x, cur.y, cur.z, cur.w};
         bool in[4];
         double4 xj[4];
@@ -1156,47 +1154,35 @@ struct ForceVVArgs {
     int *flags;
 };
 
-// HINT (experiment switches, option fuse_vv = 1 + HINT): bit 0 = the epilogue's streams use evict-first loads / stores
-// (__ldcs / __stcs), bit 1 = its operands are prefetched into L2 when the thread starts, bit 2 = the index tiles carry an
-// L2 evict-first policy.
-template <bool MULTI, bool DRIFT, int HINT>
+// (Evict-first loads / stores for the epilogue's streams, L2 prefetch of its operands at thread start and an L2 evict-first
+// policy on the index tiles were tried: 1.355 - 1.378 ms against 1.358 ms, nothing to gain -- profiles/r01_fused_step.jsonl.)
+template <bool MULTI, bool DRIFT>
 __global__ void __launch_bounds__(TPB_FORCE, 8) k_force_vv(ForceVVArgs b) {
     const Force2Args &a = b.f;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double red[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};  // pe, pair virial, ke, x*fx, y*fy, z*fz
     const bool active = i < a.n;
-    constexpr bool STREAM = (HINT & 1) != 0, PREFETCH = (HINT & 2) != 0, TILE_EF = (HINT & 4) != 0;
-    auto lds = [&](const double *p) { return STREAM ? __ldcs(p) : *p; };
-    auto sts = [&](double *p, double v) {
-        if (STREAM) __stcs(p, v);
-        else *p = v;
-    };
     bool interior = true;
     if (active) interior = is_interior(a.boxf, a.xf[i]);
     const bool warp_interior = __all_sync(0xffffffffu, interior);
     if (active) {
-        if (PREFETCH && (threadIdx.x & 15) == 0) {  // one request per 128-byte line of each stream
-            prefetch_l2(b.vx + i), prefetch_l2(b.vy + i), prefetch_l2(b.vz + i);
-            prefetch_l2(b.gx + i), prefetch_l2(b.gy + i), prefetch_l2(b.gz + i);
-            if (DRIFT && !b.always_rebuild) prefetch_l2(b.xbx + i), prefetch_l2(b.xby + i), prefetch_l2(b.xbz + i);
-        }
         double fx = 0.0, fy = 0.0, fz = 0.0, pe = 0.0, vir = 0.0;
-        if (warp_interior) force3_body<MULTI, false, TILE_EF>(a, i, fx, fy, fz, pe, vir);
-        else force3_body<MULTI, true, TILE_EF>(a, i, fx, fy, fz, pe, vir);
-        sts(a.fx + i, fx);
-        sts(a.fy + i, fy);
-        sts(a.fz + i, fz);
+        if (warp_interior) force3_body<MULTI, false>(a, i, fx, fy, fz, pe, vir);
+        else force3_body<MULTI, true>(a, i, fx, fy, fz, pe, vir);
+        a.fx[i] = fx;
+        a.fy[i] = fy;
+        a.fz[i] = fz;
         red[0] = pe;
         red[1] = vir;
         // ---- integrator epilogue ----
         double4 x = a.xt[i];  // L1/L2 hit: this thread read it at the top of the force loop
-        double vx = lds(b.vx + i), vy = lds(b.vy + i), vz = lds(b.vz + i);
-        const double gx = lds(b.gx + i), gy = lds(b.gy + i), gz = lds(b.gz + i);
+        double vx = b.vx[i], vy = b.vy[i], vz = b.vz[i];
+        const double gx = b.gx[i], gy = b.gy[i], gz = b.gz[i];
         double bx = 0.0, by = 0.0, bz = 0.0;
         if (DRIFT && !b.always_rebuild) {
-            bx = lds(b.xbx + i);
-            by = lds(b.xby + i);
-            bz = lds(b.xbz + i);
+            bx = b.xbx[i];
+            by = b.xby[i];
+            bz = b.xbz[i];
         }
         const double m = b.mass[type_of(x.w) - 1];
         const double ax = __ddiv_rn(fx, m), ay = __ddiv_rn(fy, m), az = __ddiv_rn(fz, m);
@@ -1204,9 +1190,9 @@ __global__ void __launch_bounds__(TPB_FORCE, 8) k_force_vv(ForceVVArgs b) {
         vx = __dadd_rn(vx, __dmul_rn(__dmul_rn(__dadd_rn(ox, ax), 0.5), b.dt));
         vy = __dadd_rn(vy, __dmul_rn(__dmul_rn(__dadd_rn(oy, ay), 0.5), b.dt));
         vz = __dadd_rn(vz, __dmul_rn(__dmul_rn(__dadd_rn(oz, az), 0.5), b.dt));
-        sts(b.vx + i, vx);
-        sts(b.vy + i, vy);
-        sts(b.vz + i, vz);
+        b.vx[i] = vx;
+        b.vy[i] = vy;
+        b.vz[i] = vz;
         red[2] = __dmul_rn(__dmul_rn(0.5, m), norm2(vx, vy, vz));
         red[3] = __dmul_rn(x.x, fx);
         red[4] = __dmul_rn(x.y, fy);
@@ -1216,7 +1202,7 @@ __global__ void __launch_bounds__(TPB_FORCE, 8) k_force_vv(ForceVVArgs b) {
             x.y = __dadd_rn(x.y, __dadd_rn(__dmul_rn(vy, b.dt), __dmul_rn(__dmul_rn(ay, 0.5), b.dt2)));
             x.z = __dadd_rn(x.z, __dadd_rn(__dmul_rn(vz, b.dt), __dmul_rn(__dmul_rn(az, 0.5), b.dt2)));
             wrap_pos<true>(a.box, x.x, x.y, x.z);
-            b.xt_out[i] = x;  // gathered by the next launch: default policy
+            b.xt_out[i] = x;
             b.xf_out[i] = make_float4((float)x.x, (float)x.y, (float)x.z, __int_as_float(type_of(x.w)));
             if (b.always_rebuild) {
                 if (i == 0) b.flags[FLAG_REBUILD] = 1;
@@ -1710,11 +1696,11 @@ __device__ __noinline__ bool build3_exact_out(double h0, double h1, double h2, d
     return norm2(__dmul_rn(h0, sx), __dmul_rn(h1, sy), __dmul_rn(h2, sz)) > t_list;
 }
 
-// B3_PAIRS: pair records in flight per thread (2 candidates each).  ROW_PF: the cell_start words of the NEXT stencil row
-// are loaded while the current row is scanned (a row is ~7 pair records: without it every row starts with two dependent
-// load latencies -- cell_start, then the first records -- that nothing overlaps; ncu: 44 % of the stall cycles were
-// long-scoreboard at 6.6 warps per scheduler).
-template <bool IMAGE, int B3_PAIRS = 4, bool ROW_PF = false>
+// B3_PAIRS: pair records in flight per thread (2 candidates each).  Measured at 4M atoms in the melt, ms per build
+// (profiles/r01_build_occupancy.jsonl): 64 registers / 4 records 2.48, 48 registers / 4 records 2.31, 48 registers /
+// 2 records 2.30 (the default), 40 registers 2.34, 8 records 2.74; loading the next stencil row's cell_start words while
+// the current row is scanned changed nothing.
+template <bool IMAGE, int B3_PAIRS = 2>
 __device__ __forceinline__ int build3_body(const Build2Args &a, const float *__restrict__ xp, int i) {
     int cnt = 0;
     const double4 xi = a.xt[i];
@@ -1789,51 +1775,6 @@ __device__ __forceinline__ int build3_body(const Build2Args &a, const float *__r
         }
     };
     const int nx = a.g.n[0];
-    if (ROW_PF) {
-        const int xlo = c[0] + a.g.lo[0], xhi = c[0] + a.g.hi[0];
-        const int xa = max(xlo, 0), xb = min(xhi, nx - 1) + 1;
-        // row (dy, dz) of the stencil -> first cell of the grid row it maps to, or -1 if the row is skipped
-        auto row_base = [&](int dy, int dz) {
-            int cz = c[2] + dz, cy = c[1] + dy;
-            if (cz < 0 || cz >= a.g.n[2]) {
-                if (!IMAGE || a.g.local[2]) return -1;
-                cz += cz < 0 ? a.g.n[2] : -a.g.n[2];
-            }
-            if (cy < 0 || cy >= a.g.n[1]) {
-                if (!IMAGE || a.g.local[1]) return -1;
-                cy += cy < 0 ? a.g.n[1] : -a.g.n[1];
-            }
-            return (cz * a.g.n[1] + cy) * nx;
-        };
-        int dy_n = a.g.lo[1], dz_n = a.g.lo[2];
-        int rb_n = row_base(dy_n, dz_n), jb_n = 0, je_n = 0;
-        if (rb_n >= 0) {
-            jb_n = __ldg(&a.cell_start[rb_n + xa]);
-            je_n = __ldg(&a.cell_start[rb_n + xb]);
-        }
-        while (dz_n <= a.g.hi[2]) {
-            const int rb = rb_n, jb = jb_n, je = je_n;
-            if (++dy_n > a.g.hi[1]) dy_n = a.g.lo[1], ++dz_n;
-            if (dz_n <= a.g.hi[2]) {
-                rb_n = row_base(dy_n, dz_n);
-                if (rb_n >= 0) {
-                    jb_n = __ldg(&a.cell_start[rb_n + xa]);
-                    je_n = __ldg(&a.cell_start[rb_n + xb]);
-                }
-            }
-            if (rb < 0) continue;
-            if (IMAGE && xlo < 0 && !a.g.local[0]) scan(__ldg(&a.cell_start[rb + xlo + nx]), __ldg(&a.cell_start[rb + nx]));
-            if (i >= jb && i < je) {
-                scan(jb, i);
-                scan(i + 1, je);
-            } else {
-                scan(jb, je);
-            }
-            if (IMAGE && xhi >= nx && !a.g.local[0]) scan(__ldg(&a.cell_start[rb]), __ldg(&a.cell_start[rb + xhi - nx + 1]));
-        }
-        a.nnbr[i] = cnt < a.kcap ? cnt : a.kcap;
-        return cnt;
-    }
     for (int dz = a.g.lo[2]; dz <= a.g.hi[2]; ++dz) {
         int cz = c[2] + dz;
         if (cz < 0 || cz >= a.g.n[2]) {
@@ -1865,9 +1806,10 @@ __device__ __forceinline__ int build3_body(const Build2Args &a, const float *__r
     return cnt;
 }
 
-// MINB: resident blocks per SM the register allocation aims for (8 -> 64 registers, 10 -> 48, 12 -> 40)
-template <bool MULTI, int MINB = 8, int NP = 4, bool ROW_PF = false>
-__global__ void __launch_bounds__(TPB_FORCE, MINB) k_build_list_v3(Build2Args a, const float *__restrict__ xp, int fast_ok) {
+// 10 resident blocks per SM (48 registers, 40 warps): the kernel waits on its record loads (ncu: 44 % of the stall cycles
+// long-scoreboard at 6.6 warps per scheduler), so occupancy beats the handful of spills it costs.
+template <bool MULTI>
+__global__ void __launch_bounds__(TPB_FORCE, 10) k_build_list_v3(Build2Args a, const float *__restrict__ xp, int fast_ok) {
     if (a.flags[FLAG_REBUILD] == 0) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < a.n && xf_is_ghost(a.xf[i])) a.nnbr[i] = 0;
@@ -1877,7 +1819,7 @@ __global__ void __launch_bounds__(TPB_FORCE, MINB) k_build_list_v3(Build2Args a,
     const bool warp_interior = __all_sync(0xffffffffu, interior);
     int cnt = 0;
     if (active) {
-        if (!MULTI && fast_ok) cnt = warp_interior ? build3_body<false, NP, ROW_PF>(a, xp, i) : build3_body<true, NP, ROW_PF>(a, xp, i);
+        if (!MULTI && fast_ok) cnt = warp_interior ? build3_body<false>(a, xp, i) : build3_body<true>(a, xp, i);
         else cnt = warp_interior ? build2_body<MULTI, false>(a, i) : build2_body<MULTI, true>(a, i);
     }
     int m = cnt;

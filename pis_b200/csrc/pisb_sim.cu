@@ -76,7 +76,6 @@ struct pisb_handle {
     int force_variant = 0;  // 0 = auto (v3 when orthorhombic + fully periodic, else v1), 1 = v1, 2 = v2, 3 = v3
     int build_variant = 0;
     int cell_div = 0;  // cells per list cutoff per dimension: 0 = auto, 1 = reference-sized cells, 2 = half-size cells
-    int build_minb = 8;  // option "build_minb" (experiment): resident blocks per SM k_build_list_v3 is compiled for
     int fuse_vv = 1;   // option "fuse_vv": NVE batches run k_force_vv (force + kick + drift in one launch) when the default force kernel applies
 
     // box / grid
@@ -589,15 +588,6 @@ int launch_rebuild_chain(pisb_t *h) {
                 else k_build_list_v2<false><<<nb, TPB_FORCE, 0, st>>>(b2);
             } else {  // default: v3, packed FP32 pair records + bit-mask append for interior warps
                 if (multi) k_build_list_v3<true><<<nb, TPB_FORCE, 0, st>>>(b2, h->xp.p, 1);
-                // experiment switch build_minb = MINB + 100 * (pair records in flight) + 1000 * (row prefetch)
-                else if (h->build_minb == 10) k_build_list_v3<false, 10><<<nb, TPB_FORCE, 0, st>>>(b2, h->xp.p, 1);
-                else if (h->build_minb == 12) k_build_list_v3<false, 12><<<nb, TPB_FORCE, 0, st>>>(b2, h->xp.p, 1);
-                else if (h->build_minb == 1008) k_build_list_v3<false, 8, 4, true><<<nb, TPB_FORCE, 0, st>>>(b2, h->xp.p, 1);
-                else if (h->build_minb == 1010) k_build_list_v3<false, 10, 4, true><<<nb, TPB_FORCE, 0, st>>>(b2, h->xp.p, 1);
-                else if (h->build_minb == 210) k_build_list_v3<false, 10, 2, false><<<nb, TPB_FORCE, 0, st>>>(b2, h->xp.p, 1);
-                else if (h->build_minb == 1210) k_build_list_v3<false, 10, 2, true><<<nb, TPB_FORCE, 0, st>>>(b2, h->xp.p, 1);
-                else if (h->build_minb == 808) k_build_list_v3<false, 8, 8, false><<<nb, TPB_FORCE, 0, st>>>(b2, h->xp.p, 1);
-                else if (h->build_minb == 1808) k_build_list_v3<false, 8, 8, true><<<nb, TPB_FORCE, 0, st>>>(b2, h->xp.p, 1);
                 else k_build_list_v3<false><<<nb, TPB_FORCE, 0, st>>>(b2, h->xp.p, 1);
             }
         } else if (h->box.ortho) {
@@ -720,24 +710,13 @@ int launch_force_vv(pisb_t *h, bool drift, double dt, pisb_thermo *rec) {
         const bool multi = h->n_types > 1;
         const int nb = nblk(h->n, TPB_FORCE);
         cudaStream_t st = h->stream;
-#define FVV(HINT)                                                                     \
-    do {                                                                              \
-        if (drift) {                                                                  \
-            if (multi) k_force_vv<true, true, HINT><<<nb, TPB_FORCE, 0, st>>>(fv);    \
-            else k_force_vv<false, true, HINT><<<nb, TPB_FORCE, 0, st>>>(fv);         \
-        } else {                                                                      \
-            if (multi) k_force_vv<true, false, HINT><<<nb, TPB_FORCE, 0, st>>>(fv);   \
-            else k_force_vv<false, false, HINT><<<nb, TPB_FORCE, 0, st>>>(fv);        \
-        }                                                                             \
-    } while (0)
-        switch (h->fuse_vv - 1) {
-            case 1: FVV(1); break;
-            case 3: FVV(3); break;
-            case 5: FVV(5); break;
-            case 7: FVV(7); break;
-            default: FVV(0); break;
+if (drift) {
+            if (multi) k_force_vv<true, true><<<nb, TPB_FORCE, 0, st>>>(fv);
+            else k_force_vv<false, true><<<nb, TPB_FORCE, 0, st>>>(fv);
+        } else {
+            if (multi) k_force_vv<true, false><<<nb, TPB_FORCE, 0, st>>>(fv);
+            else k_force_vv<false, false><<<nb, TPB_FORCE, 0, st>>>(fv);
         }
-#undef FVV
     }
     for (int d = 0; d < 3; ++d) std::swap(h->f[d], h->g[d]);
     if (drift) swap_position_buffers(h);
@@ -1022,7 +1001,7 @@ void graph_signature(pisb_t *h, double dt, std::vector<unsigned char> &sig) {
                           h->tile_sum.p, h->mass_d.p, h->partials.p, h->table_d.p, h->thermo_d.p, h->flags, h->ticket, h->nhc_d.p,
                           h->nhc_energy_d.p};
     put(ptrs, sizeof ptrs);
-    const int ints[] = {h->n, h->npad, h->kcap, h->n_types, h->force_variant, h->build_variant, h->cell_div, h->fuse_vv, h->build_minb};
+    const int ints[] = {h->n, h->npad, h->kcap, h->n_types, h->force_variant, h->build_variant, h->cell_div, h->fuse_vv};
     put(ints, sizeof ints);
     const double dbl[] = {dt, h->skin, h->skin_half2_override, h->max_rcut};
     put(dbl, sizeof dbl);
@@ -2710,12 +2689,8 @@ int pisb_set_option(pisb_t *h, const char *name, double value) {
         h->host_chunk_atoms = value > 0 ? (int)value : 0;
         return PISB_OK;
     }
-    if (!std::strcmp(name, "build_minb")) {
-        h->build_minb = (int)value;
-        return PISB_OK;
-    }
     if (!std::strcmp(name, "fuse_vv")) {
-        h->fuse_vv = value > 0.0 ? (int)value : 0;  // 1 + HINT bits of k_force_vv (experiment switches)
+        h->fuse_vv = value != 0.0 ? 1 : 0;
         return PISB_OK;
     }
     if (!std::strcmp(name, "force_variant")) {

@@ -1,5 +1,6 @@
-"""A/B of the fused step kernel's cache-hint variants (option fuse_vv = 0: k_force_v3 + k_vv, 1 + HINT: k_force_vv<HINT>),
-4M atoms, graph replay; one JSON line per variant."""
+"""A/B of the fused step kernel (option fuse_vv = 0: k_force_v3 + k_vv, 1: k_force_vv), graph replay + per-kernel pass; one
+JSON line per variant.  (profiles/r01_fused_step.jsonl also holds the cache-hint variants 2/4/6/8 that were tried and
+removed.)"""
 import json, sys, time
 sys.path.insert(0, ".")
 from pis_b200 import LennardJones, LJCudaManager
@@ -7,7 +8,7 @@ from pis_b200.lattice import fcc_argon
 
 ncell = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 T0 = float(sys.argv[2]) if len(sys.argv) > 2 else 43.0
-variants = [int(v) for v in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0, 1, 2, 4, 6, 8]
+variants = [int(v) for v in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0, 1]
 steps = 100
 for fv in variants:
     atoms = fcc_argon(ncell, temperature=T0, seed=12345)
