@@ -90,11 +90,13 @@ class ClockSampler:
                 "samples": len(self.rows), "reasons": reasons}
 
 
-def measure_pcie(n_doubles: int, reps: int = 4) -> dict:
-    """Host<->device copy rates of one 3N-double array from / to pinned memory, each direction alone."""
+def measure_pcie(host_array, reps: int = 4) -> dict:
+    """Host<->device copy rates of one of the run's own pinned 3N-double arrays, each direction alone (the array is
+    overwritten: the caller downloads the state into it afterwards)."""
     import torch
 
-    host = torch.empty(n_doubles, dtype=torch.float64).pin_memory()
+    host = torch.from_numpy(host_array.reshape(-1))
+    n_doubles = host.numel()
     dev = torch.empty(n_doubles, dtype=torch.float64, device="cuda")
     out = {}
     for name, fn in (("h2d_GBps", lambda: dev.copy_(host, non_blocking=True)), ("d2h_GBps", lambda: host.copy_(dev, non_blocking=True))):
@@ -280,7 +282,7 @@ def run_single(args):
                           "launches": tim["integrate"]["launches"], "algorithmic_bytes_per_atom": vv_bytes}
 
     # ---- the link the end-to-end call lives on: pinned 3N-double copies each way (torch plumbing, no product code) ----
-    pcie = measure_pcie(3 * n)
+    pcie = measure_pcie(atoms.forces)
 
     # ---- end-to-end: the reference-facing trait call with HOST buffers, every step ----
     e2e_steps = max(3, min(args.e2e_steps, args.steps))

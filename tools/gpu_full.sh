@@ -7,7 +7,7 @@ mkdir -p gpurun_out
 O=gpurun_out
 timeout 400 python -m pytest tests -m gpu -q -n 6 > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $O/pytest_gpu.log
 tail -n 6 $O/pytest_gpu.log
-for K in "k_force_vv 2 prof_force_vv" "k_build_list_v3 1 prof_build_v3"; do
+for K in "k_force_vv 2 prof_force_vv" "k_build_list_v3 0 prof_build_v3"; do
   set -- $K
   timeout 150 ncu --set full --clock-control none --import-source on -k regex:"$1" -s $2 -c 1 -f -o $O/$3 python tools/prof_one.py 0 0 100 8 43 0 cuda_graphs=0 > $O/ncu_$3.log 2>&1; tail -n 1 $O/ncu_$3.log
   python tools/ncu_summary.py $O/$3.ncu-rep > $O/$3.summary.json 2>>$O/ncu_summary.err
