@@ -28,7 +28,10 @@ constexpr int TPB = 256;        // streaming kernels
 constexpr int TPB_FORCE = 128;  // force / build kernels
 
 // flags[] (device ints)
-enum { FLAG_REBUILD = 0, FLAG_MAXNBR = 1, FLAG_NBUILDS = 2, FLAG_BADTYPE = 3, FLAG_COMM_TIMEOUT = 4, FLAG_COUNT = 8 };
+// FLAG_DECISION: multi-GPU fused steps -- a stream-ordered copy of FLAG_REBUILD taken after the halo exchange.  The
+// speculative k_force_vv launch and the host both read THIS word: the kernel's own drift raises FLAG_REBUILD for the next
+// step while the launch is still running.
+enum { FLAG_REBUILD = 0, FLAG_MAXNBR = 1, FLAG_NBUILDS = 2, FLAG_BADTYPE = 3, FLAG_COMM_TIMEOUT = 4, FLAG_DECISION = 5, FLAG_COUNT = 8 };
 
 // Neighbour list layout: K-tiles of 4.  Entry (k, i) lives at ((k/4)*npad + i)*4 + k%4, so the four
 // neighbours k..k+3 of atom i are one aligned int4 and a warp reads 512 contiguous bytes per tile.
@@ -1159,9 +1162,10 @@ struct ForceVVArgs {
 template <bool MULTI, bool DRIFT>
 __global__ void __launch_bounds__(TPB_FORCE, 8) k_force_vv(ForceVVArgs b) {
     const Force2Args &a = b.f;
+    if (a.skip_flag && *a.skip_flag != 0) return;  // multi-GPU: speculative launch, a rebuild comes first
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double red[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};  // pe, pair virial, ke, x*fx, y*fy, z*fz
-    const bool active = i < a.n;
+    const bool active = i < a.n && !xf_is_ghost(a.xf[i]);  // ghost slots (multi-GPU) are filled by the halo exchange
     bool interior = true;
     if (active) interior = is_interior(a.boxf, a.xf[i]);
     const bool warp_interior = __all_sync(0xffffffffu, interior);

@@ -690,19 +690,20 @@ int launch_vv(pisb_t *h, bool kick, bool drift, double dt, pisb_thermo *rec, con
 
 // NVE batches of systems the default force kernel serves (orthorhombic, fully periodic, enough atoms for one thread per
 // atom) run one k_force_vv launch per step instead of k_force_v3 + k_vv.
-bool fused_step_possible(const pisb_t *h) {
-    return h->fuse_vv && !h->multi && v2_possible(h) && (h->force_variant == 0 || h->force_variant == 3) &&
+bool fused_step_possible(const pisb_t *h, bool multi_path = false) {
+    return h->fuse_vv && h->multi == multi_path && v2_possible(h) && (h->force_variant == 0 || h->force_variant == 3) &&
            (h->force_variant == 3 || h->n > 75000);
 }
 
 // F(t+dt) -> g, kick with F(t) = f, [drift into the other position buffer], then f <-> g (and the position buffers).
-int launch_force_vv(pisb_t *h, bool drift, double dt, pisb_thermo *rec) {
+// With a skip_flag the launch is speculative (multi-GPU) and the caller rotates the buffers once it knows the launch ran.
+int launch_force_vv(pisb_t *h, bool drift, double dt, pisb_thermo *rec, const int *skip_flag = nullptr) {
     {
         LaunchScope ls(h, PISB_K_FORCE);
         const double hs = 0.5 * h->skin;
         ForceVVArgs fv{Force2Args{h->n, h->npad, h->xt.p, h->xf.p, h->nbr.p, h->nnbr.p, h->box, h->boxf, h->pairs[0], h->pairsf[0],
                                   h->table_d.p, h->tablef_d.p, h->n_types, nullptr, nullptr, nullptr, h->g[0].p, h->g[1].p, h->g[2].p,
-                                  h->partials.p, h->ticket, rec, nullptr},
+                                  h->partials.p, h->ticket, rec, skip_flag},
                        h->v[0].p, h->v[1].p, h->v[2].p, h->f[0].p, h->f[1].p, h->f[2].p, h->xb[0].p, h->xb[1].p, h->xb[2].p,
                        h->mass_d.p, h->s_xt.p, h->xf2.p, dt, dt * dt,
                        h->skin_half2_override >= 0.0 ? h->skin_half2_override : hs * hs,
@@ -718,8 +719,10 @@ if (drift) {
             else k_force_vv<false, false><<<nb, TPB_FORCE, 0, st>>>(fv);
         }
     }
-    for (int d = 0; d < 3; ++d) std::swap(h->f[d], h->g[d]);
-    if (drift) swap_position_buffers(h);
+    if (!skip_flag) {
+        for (int d = 0; d < 3; ++d) std::swap(h->f[d], h->g[d]);
+        if (drift) swap_position_buffers(h);
+    }
     return check_launch(h, "k_force_vv");
 }
 
@@ -1897,11 +1900,19 @@ int do_step_nve_multi(pisb_t *h, double dt, int64_t nsteps, pisb_thermo *out) {
         const int64_t m = std::min(chunk_max, nsteps - done);
         TRY(reserve_thermo(h, (size_t)m + 1));
         CUDA_TRY(h, cudaMemsetAsync(h->thermo_d.p, 0, sizeof(pisb_thermo) * (m + 1), h->stream));
+        // Bricks the default force kernel serves step with k_force_vv like a single GPU: drift, then per step halo exchange,
+        // [rebuild], force + kick + drift of the next step in one launch (owned slots; ghost slots of the other position
+        // buffer are filled by the next exchange).
+        const bool fused = fused_step_possible(h, true);
         for (int64_t s = 0; s < m; ++s) {
             pisb_thermo *rec = h->thermo_d.p + s;
             double t0 = wall_now();
-            if (s == 0) TRY(launch_vv(h, false, true, dt, nullptr));
-            else TRY(launch_vv(h, true, true, dt, rec - 1));
+            if (fused) {
+                if (s == 0) TRY(launch_vv(h, false, true, dt, nullptr, nullptr, true));
+            } else {
+                if (s == 0) TRY(launch_vv(h, false, true, dt, nullptr));
+                else TRY(launch_vv(h, true, true, dt, rec - 1));
+            }
             double t1 = wall_now();
             // every rank must take the same branch: the skin-trigger flags ride along with the ghost exchange and
             // are max-reduced by k_halo_unpack; the host then reads the decision.  On a rebuild step the ghost
@@ -1913,25 +1924,37 @@ int do_step_nve_multi(pisb_t *h, double dt, int64_t nsteps, pisb_thermo *out) {
             const bool speculate = v2_possible(h) && (h->force_variant == 0 || h->force_variant == 3 || h->force_variant == 6);
             double *outp[3] = {h->g[0].p, h->g[1].p, h->g[2].p};
             if (speculate) {
+                if (fused)  // the decision word the speculative launch and the host read (see FLAG_DECISION)
+                    CUDA_TRY(h, cudaMemcpyAsync(h->flags + FLAG_DECISION, h->flags + FLAG_REBUILD, sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
                 CUDA_TRY(h, cudaEventRecord(h->ev_pos, h->stream));
                 CUDA_TRY(h, cudaStreamWaitEvent(h->copy_stream, h->ev_pos, 0));
                 CUDA_TRY(h, cudaMemcpyAsync(h->h_flags, h->flags, sizeof(int) * FLAG_COUNT, cudaMemcpyDeviceToHost, h->copy_stream));
-                TRY(launch_force(h, outp, nullptr, rec, h->flags + FLAG_REBUILD));
+                if (fused) TRY(launch_force_vv(h, s + 1 < m, dt, rec, h->flags + FLAG_DECISION));
+                else TRY(launch_force(h, outp, nullptr, rec, h->flags + FLAG_REBUILD));
                 const size_t spec_ev = h->ev_used;  // profiling: event pair of the speculative launch is ev_pool[spec_ev - 1]
                 CUDA_TRY(h, cudaStreamSynchronize(h->copy_stream));
                 // a launch that turned out to be a no-op is not a force evaluation: book it under the (tiny) reduce class
-                if (h->profiling && spec_ev > 0 && h->h_flags[FLAG_REBUILD] != 0) h->ev_pool[spec_ev - 1].cls = PISB_K_REDUCE;
+                if (h->profiling && spec_ev > 0 && h->h_flags[fused ? FLAG_DECISION : FLAG_REBUILD] != 0) h->ev_pool[spec_ev - 1].cls = PISB_K_REDUCE;
             } else {
                 CUDA_TRY(h, cudaMemcpyAsync(h->h_flags, h->flags, sizeof(int) * FLAG_COUNT, cudaMemcpyDeviceToHost, h->stream));
                 CUDA_TRY(h, cudaStreamSynchronize(h->stream));
             }
             double t2 = wall_now();
             if (h->h_flags[FLAG_COMM_TIMEOUT]) return fail(h, PISB_ERR_COMM, "timed out waiting for a peer's ghost data (peer-memory halo)");
-            const bool reb = h->h_flags[FLAG_REBUILD] != 0;
+            const bool reb = h->h_flags[(fused && speculate) ? FLAG_DECISION : FLAG_REBUILD] != 0;
             if (reb) TRY(multi_rebuild(h));
             double t3 = wall_now();
-            if (reb || !speculate) TRY(launch_force(h, outp, nullptr, rec));
-            for (int d = 0; d < 3; ++d) std::swap(h->f[d], h->g[d]);
+            if (fused) {
+                if (reb || !speculate) {
+                    TRY(launch_force_vv(h, s + 1 < m, dt, rec));  // rotates the buffers itself
+                } else {  // the speculative launch ran: rotate now
+                    for (int d = 0; d < 3; ++d) std::swap(h->f[d], h->g[d]);
+                    if (s + 1 < m) swap_position_buffers(h);
+                }
+            } else {
+                if (reb || !speculate) TRY(launch_force(h, outp, nullptr, rec));
+                for (int d = 0; d < 3; ++d) std::swap(h->f[d], h->g[d]);
+            }
             double t4 = wall_now();
             t_vv += t1 - t0;
             t_flag += t2 - t1;
@@ -1940,7 +1963,7 @@ int do_step_nve_multi(pisb_t *h, double dt, int64_t nsteps, pisb_thermo *out) {
             t_force += t4 - t3;
         }
         double t5 = wall_now();
-        TRY(launch_vv(h, true, false, dt, h->thermo_d.p + (m - 1)));
+        if (!fused) TRY(launch_vv(h, true, false, dt, h->thermo_d.p + (m - 1)));
         TRY(allreduce_thermo(h, (size_t)m));
         CUDA_TRY(h, cudaMemcpyAsync(h->h_thermo, h->thermo_d.p, sizeof(pisb_thermo) * m, cudaMemcpyDeviceToHost, h->stream));
         CUDA_TRY(h, cudaStreamSynchronize(h->stream));

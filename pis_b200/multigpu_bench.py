@@ -110,7 +110,10 @@ def run(args):
         capi.check(mgr._h, capi.load().pisb_neighbours(mgr._h, capi._ptr(nn), None, 0))
         nn_mean = float(nn[: int(mgr.stats()['n_atoms'])].mean())
         f_ms = tim["force"]["ms"] / max(tim["force"]["launches"], 1)
-        achieved = (48.0 + 4.0 * nn_mean) * n_own / (f_ms * 1e-3) / 1e9
+        # bricks of this size step with the fused kernel (force + kick + drift): 192 + 4K algorithmic bytes per owned atom,
+        # 48 + 4K for the plain force kernel (bench.py)
+        fused = tim.get("integrate", {"launches": 0})["launches"] < max(args.steps // 2, 1)   # unfused: one k_vv per step
+        achieved = ((192.0 if fused else 48.0) + 4.0 * nn_mean) * n_own / (f_ms * 1e-3) / 1e9
         peak = float(peaks.get("hbm_gbs", 6650.0))
         line = {
             "metric": B.METRIC, "value": value, "unit": B.UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -130,7 +133,7 @@ def run(args):
                             "pisb_download_owned (positions + global ids) every 10 steps (the example's dump cadence); "
                             "state is uploaded once"},
             "gpu_launches": int(st1["n_launches"] - st0["n_launches"]),
-            "roofline": {"kernel": "k_force_v3", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"kernel": "k_force_vv" if fused else "k_force_v3", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_kind, "mean_neighbours": nn_mean,
                          "ms_per_launch": f_ms, "share_of_step": tim["force"]["ms"] / ms_total,
                          "note": "rank 0's force kernel; FP64/L1 bound, see DESIGN.md"},

@@ -368,10 +368,11 @@ def test_gpu_matches_committed_ensemble_golden_vectors():
         assert np.max(np.abs(th["pe"] + th["ke"] + en - ref[1:, 2]) / np.abs(ref[1:, 2])) <= ENERGY_TOL
 
 
-@pytest.mark.parametrize("halo_mode", [2, 1])
-def test_multi_gpu_equals_single_gpu(halo_mode):
+@pytest.mark.parametrize("halo_mode,force_variant", [(2, 0), (1, 0), (2, 3), (1, 3)])
+def test_multi_gpu_equals_single_gpu(halo_mode, force_variant):
     """2-rank spatially decomposed run == 1-GPU run (neighbour sets exact per global id, forces 1e-10,
-    traces 1e-9), with the peer-memory halo (2) and with the NCCL fallback (1).  Needs 2 visible GPUs; the
+    traces 1e-9), with the peer-memory halo (2) and with the NCCL fallback (1); force_variant 3 makes the bricks step with
+    the fused k_force_vv kernel (speculative launch behind the decision word) as 4M-atom bricks do by default.  Needs 2 visible GPUs; the
     torchrun launch mirrors the driver's."""
     import json
     import os
@@ -385,7 +386,7 @@ def test_multi_gpu_equals_single_gpu(halo_mode):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", "29577", os.path.join(root, "tools", "multi_check.py"), "12", "40", "60"]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root, env=dict(os.environ, PISB_HALO_MODE=str(halo_mode)))
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root, env=dict(os.environ, PISB_HALO_MODE=str(halo_mode), PISB_FORCE_VARIANT=str(force_variant)))
     lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
     assert r.returncode == 0 and lines, r.stdout[-2000:] + r.stderr[-2000:]
     out = json.loads(lines[-1])

@@ -43,6 +43,11 @@ def main():
     mgr.insert((1, 1), LennardJones(ARGON["epsilon"], ARGON["sigma"], rc, True))
     halo_mode = int(os.environ.get("PISB_HALO_MODE", "0"))  # 0 auto (peer memory), 1 NCCL send/recv, 2 peer memory or fail
     mgr.set_option("halo_mode", halo_mode)
+    force_variant = int(os.environ.get("PISB_FORCE_VARIANT", "0"))  # 3: k_force_v3 / the fused k_force_vv step at any brick size
+    if force_variant:
+        mgr.set_option("force_variant", force_variant)
+    if "PISB_FUSE_VV" in os.environ:
+        mgr.set_option("fuse_vv", int(os.environ["PISB_FUSE_VV"]))
     mgr.attach_owned(atoms, gid)
     pe0 = mgr.compute()
     g0, _, _, f0 = (a_.copy() for a_ in mgr.download_owned())
@@ -77,7 +82,7 @@ def main():
         mag = np.linalg.norm(ref.forces, axis=1)
         den = np.maximum(mag, 1e-3 * np.sqrt((mag ** 2).mean()))
         out = {
-            "world": world, "grid": grid, "n_global": n_global, "steps": steps, "halo_mode": halo_mode,
+            "world": world, "grid": grid, "n_global": n_global, "steps": steps, "halo_mode": halo_mode, "force_variant": force_variant,
             "neighbour_rows_mismatching": mism,
             "force0_max_abs": float(np.abs(F0 - f0_ref).max()),
             "force_rel": float((np.linalg.norm(F1 - ref.forces, axis=1) / den).max()),
