@@ -46,6 +46,9 @@ def run(args):
     del pos, vel
     mgr = DistributedLJ(skin=B.SKIN, local_device=local, rank=rank, world=world, grid=grid)
     mgr.insert((1, 1), LennardJones(ARGON["epsilon"], ARGON["sigma"], B.RC, True))
+    for kv in getattr(args, "option", []):      # library options for A/B runs, e.g. --option fuse_vv=0
+        name, _, val = kv.partition("=")
+        mgr.set_option(name, float(val))
     mgr.attach_owned(atoms, gid)
     h2d_total = atoms.n_atoms * (72 + 8)
     mgr.compute()
@@ -82,6 +85,7 @@ def run(args):
     e2e_steps = max(10, min(args.e2e_steps, args.steps))
     mgr.download_owned(velocities=False, forces=False)  # untimed: allocates the pinned destination buffers that every later call reuses
     mgr.step_nve(B.DT, 10)
+    st_e2e0 = mgr.stats()
     dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -140,6 +144,7 @@ def run(args):
             "cpu_baseline": None,
             "kernel_ms_per_step_rank0": {k: round(v["ms"] / args.steps, 5) for k, v in tim.items() if v["launches"]},
             "list_builds_in_timed_region": int(st1["n_builds"] - st0["n_builds"]),
+            "list_builds_in_e2e_region": int(mgr.stats()["n_builds"] - st_e2e0["n_builds"]),
             "per_rank": [{"rank": g["rank"], "owned": g["stats"]["n_atoms"], "ghost": g["stats"]["n_ghost"],
                           "halo_ms_per_step": round(g["kernel_ms"].get("halo", 0.0) / args.steps, 5)} for g in gathered],
             "energy_drift_rel": float(np.abs((th["pe"] + th["ke"]) - (th["pe"][0] + th["ke"][0])).max() / abs(th["pe"][0] + th["ke"][0])),
