@@ -299,8 +299,10 @@ def run_single(args):
            "call": "LJCudaManager.verlet_step_nve(atoms, dt) == pisb_verlet_step_nve_host: pinned host x,v,F up in chunks, "
                    "drift per chunk, x(t+dt) down under the upload, force + kick, v,F + PE down in chunks",
            "pcie": pcie,
-           # x, v, F up, then (after the force pass) v, F down; x(t+dt) can hide under the upload
-           "pcie_floor_ms": 1e3 * (72.0 * n / (pcie["h2d_GBps"] * 1e9) + 48.0 * n / (pcie["d2h_GBps"] * 1e9))}
+           # x, v, F up, then (after the force pass) v, F down; x(t+dt) can hide under the upload.  The force pass (and a
+           # rebuild, when one is due) sits between the two transfers and overlaps neither: floor = link time + step time
+           "pcie_floor_ms": 1e3 * (72.0 * n / (pcie["h2d_GBps"] * 1e9) + 48.0 * n / (pcie["d2h_GBps"] * 1e9)),
+           "pcie_plus_step_floor_ms": 1e3 * (72.0 * n / (pcie["h2d_GBps"] * 1e9) + 48.0 * n / (pcie["d2h_GBps"] * 1e9)) + ms_per_step}
 
     # ---- the same loop the C++ host's Simulation::run drives (device-resident; reported beside the strict e2e) ----
     mgr.attach(atoms)
