@@ -244,8 +244,20 @@ PISB_API int pisb_download_owned(pisb_t *h, int64_t cap, double *pos, double *ve
  * multi-GPU mode (where list entries are global ids). */
 PISB_API int pisb_owned_ids(pisb_t *h, int64_t cap, int32_t *global_ids, int64_t *n_out);
 
-/* Tuning knobs (0 = keep default): list_capacity = neighbour slots per atom (auto-grown on
- * overflow), force_variant = kernel variant selector for A/B measurements. */
+/* Options (all have working defaults; the kernel selectors exist for A/B measurements and the parity tests):
+ *   list_capacity     neighbour slots per atom, 0 = automatic (estimated from the density, grown on overflow)
+ *   cuda_graphs       1 (default) = NVE / NVT batches replay CUDA graphs of 8 / 4 / 2 steps, 0 = classic launches
+ *   fuse_vv           1 (default) = NVE steps of systems above 75k atoms (or with force_variant 3) run k_force_vv, the
+ *                     force pass with the velocity-Verlet kick + drift in its epilogue; 0 = k_force_v3 + k_vv
+ *   host_pipeline     1 (default) = pisb_verlet_step_nve_host moves x, v, F in chunks and pipelines upload, drift and
+ *                     download; 0 = whole-array copies.  host_chunk_atoms = atoms per chunk, 0 = n/8 (>= 65536)
+ *   force_variant     0 = automatic (v3; 8 or 4 lanes per atom below 32k / 75k atoms; v1 for a triclinic or
+ *                     non-periodic box), 1 = v1 general all-FP64, 2 = FP32 pre-filter + queue, 3 = v3, 4 = TMA-staged
+ *                     shared-memory tile (prototype), 6 = 8 lanes per atom
+ *   build_variant     0 = automatic (v3), 1 = v1 general, 2 = scalar FP32 pre-filter, 3 = packed-FP32 pair records
+ *   cell_div          cells per list cutoff and dimension: 0 = automatic (2 with build_variant 2/3), 1, 2
+ *   halo_mode         multi-GPU per-step ghost exchange: 0 = peer memory when it can be mapped, 1 = NCCL send/recv,
+ *                     2 = peer memory or fail */
 PISB_API int pisb_set_option(pisb_t *h, const char *name, double value);
 
 #ifdef __cplusplus

@@ -92,3 +92,30 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
                 txt = open(os.path.join(base, f), errors="replace").read()
                 assert "pis_oracle" not in txt and "from oracle" not in txt and "import oracle" not in txt, f
+
+
+def test_roofline_traffic_file_matches_the_kernel_the_bench_reports():
+    """bench.py takes roofline.traffic (ncu dram bytes per launch) from profiles/force_traffic.json only when that capture is
+    of the kernel it times: the default 4M-atom run steps with k_force_vv."""
+    import json
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with open(os.path.join(root, "profiles", "force_traffic.json")) as f:
+        t = json.load(f)
+    assert t["kernel"].startswith("k_force_vv")
+    assert 1.5e9 < t["dram_bytes_per_launch"] < 4e9 and 0 < t["fp64_pipe_active_pct"] <= 100
+    # algorithmic bytes of the same launch (DESIGN.md section 4): (192 + 4K) per atom at K ~ 85, 4M atoms
+    assert 0.9 < t["dram_bytes_per_launch"] / ((192 + 4 * 85.3) * 4.0e6) < 1.3
+
+
+def test_every_library_option_is_documented_in_the_header():
+    import os
+    import re
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "pis_b200", "csrc", "pisb_sim.cu")).read()
+    body = src[src.index("int pisb_set_option("):]
+    names = set(re.findall(r'std::strcmp\(name, "(\w+)"\)', body))
+    header = open(os.path.join(root, "include", "pisb200.h")).read()
+    assert names and all(n in header for n in names), sorted(n for n in names if n not in header)
