@@ -1159,15 +1159,22 @@ struct ForceVVArgs {
 
 // (Evict-first loads / stores for the epilogue's streams, L2 prefetch of its operands at thread start and an L2 evict-first
 // policy on the index tiles were tried: 1.355 - 1.378 ms against 1.358 ms, nothing to gain -- profiles/r01_fused_step.jsonl.)
-template <bool MULTI, bool DRIFT>
+// BRICK: the multi-GPU form -- ghost slots are skipped (the halo exchange fills them) and the launch may be speculative
+// (skip_flag).  A template parameter, not a run-time test: with the two extra live values the single-GPU kernel's force loop
+// picked up a spill store + load per K-tile (ptxas: 8 -> 24 bytes, inside the loop), on the L1TEX path that bounds it.
+template <bool MULTI, bool DRIFT, bool BRICK>
 __global__ void __launch_bounds__(TPB_FORCE, 8) k_force_vv(ForceVVArgs b) {
     const Force2Args &a = b.f;
-    if (a.skip_flag && *a.skip_flag != 0) return;  // multi-GPU: speculative launch, a rebuild comes first
+    if (BRICK && a.skip_flag && *a.skip_flag != 0) return;  // speculative launch, a rebuild comes first
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double red[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};  // pe, pair virial, ke, x*fx, y*fy, z*fz
-    const bool active = i < a.n && !xf_is_ghost(a.xf[i]);  // ghost slots (multi-GPU) are filled by the halo exchange
+    bool active = i < a.n;
     bool interior = true;
-    if (active) interior = is_interior(a.boxf, a.xf[i]);
+    if (active) {
+        const float4 xfi = a.xf[i];  // one load serves both tests (written this way the force loop stays free of spills)
+        if (BRICK && xf_is_ghost(xfi)) active = false;
+        else interior = is_interior(a.boxf, xfi);
+    }
     const bool warp_interior = __all_sync(0xffffffffu, interior);
     if (active) {
         double fx = 0.0, fy = 0.0, fz = 0.0, pe = 0.0, vir = 0.0;

@@ -711,13 +711,19 @@ int launch_force_vv(pisb_t *h, bool drift, double dt, pisb_thermo *rec, const in
         const bool multi = h->n_types > 1;
         const int nb = nblk(h->n, TPB_FORCE);
         cudaStream_t st = h->stream;
-if (drift) {
-            if (multi) k_force_vv<true, true><<<nb, TPB_FORCE, 0, st>>>(fv);
-            else k_force_vv<false, true><<<nb, TPB_FORCE, 0, st>>>(fv);
+#define FVV(T, D)                                                              \
+    do {                                                                       \
+        if (h->multi) k_force_vv<T, D, true><<<nb, TPB_FORCE, 0, st>>>(fv);    \
+        else k_force_vv<T, D, false><<<nb, TPB_FORCE, 0, st>>>(fv);            \
+    } while (0)
+        if (drift) {
+            if (multi) FVV(true, true);
+            else FVV(false, true);
         } else {
-            if (multi) k_force_vv<true, false><<<nb, TPB_FORCE, 0, st>>>(fv);
-            else k_force_vv<false, false><<<nb, TPB_FORCE, 0, st>>>(fv);
+            if (multi) FVV(true, false);
+            else FVV(false, false);
         }
+#undef FVV
     }
     if (!skip_flag) {
         for (int d = 0; d < 3; ++d) std::swap(h->f[d], h->g[d]);
