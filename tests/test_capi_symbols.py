@@ -39,3 +39,32 @@ def test_argument_validation_without_device():
     assert b"bad potential table" in lib.pisb_last_error(None)
     assert lib.pisb_destroy(None) == capi.PISB_OK
     assert lib.pisb_set_box(None, None, None, None) == capi.PISB_ERR_INVALID
+
+
+def test_force_loops_have_no_local_memory_traffic():
+    """The force loop is bound by the L1TEX path; a register spill inside it (one STL + LDL per K-tile) costs ~8 % and is
+    easy to pick up with an innocent-looking extra live value (it happened when the multi-GPU ghost test went into
+    k_force_vv).  SASS check on the built library: no local-memory instruction between the first and the last 256-bit
+    neighbour gather of the step kernels."""
+    import shutil
+    import subprocess
+
+    import pytest
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    kernels = {
+        "k_force_v3<false>": "_ZN4pisb10k_force_v3ILb0EEEvNS_10Force2ArgsE",
+        "k_force_vv<false,drift,single GPU>": "_ZN4pisb10k_force_vvILb0ELb1ELb0EEEvNS_11ForceVVArgsE",
+        "k_force_vv<false,no drift,single GPU>": "_ZN4pisb10k_force_vvILb0ELb0ELb0EEEvNS_11ForceVVArgsE",
+        "k_force_vv<false,drift,brick>": "_ZN4pisb10k_force_vvILb0ELb1ELb1EEEvNS_11ForceVVArgsE",
+        "k_force_vv<false,no drift,brick>": "_ZN4pisb10k_force_vvILb0ELb0ELb1EEEvNS_11ForceVVArgsE",
+    }
+    for name, sym in kernels.items():
+        out = subprocess.run([cuobjdump, "-sass", "-fun", sym, capi.LIB_PATH], capture_output=True, text=True, timeout=120).stdout
+        ins = [ln for ln in out.splitlines() if re.match(r"\s+/\*[0-9a-f]{4}\*/", ln)]
+        gathers = [k for k, ln in enumerate(ins) if "LDG.E.ENL2.256" in ln]
+        assert len(gathers) >= 8, f"{name}: the 256-bit gathers were not found ({len(gathers)})"
+        inside = [ln.strip() for ln in ins[gathers[0]:gathers[-1] + 1] if re.search(r"\b(STL|LDL)\b", ln)]
+        assert not inside, f"{name}: local-memory traffic inside the force loop: {inside[:4]}"
