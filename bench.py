@@ -110,6 +110,23 @@ def measure_pcie(host_array, reps: int = 4) -> dict:
     return out
 
 
+# FP64 pipe yardstick (the north_star's alternative to the HBM fraction).  Issue slots of the force loop per listed pair,
+# counted in the SASS of k_force_v3 / k_force_vv: 14 distance + 5 reciprocal + 11 LJ + 5 accumulate;
+# the fused kernel's epilogue adds ~110 per atom (6 IEEE divisions, kick, drift, wrap, skin trigger).  Peak: the measured
+# DFMA rate of tools/microbench.cu, 57.2 per clock and SM (profiles/r01_microbench_pipes.txt), 148 SMs at 1965 MHz.
+FP64_SLOTS_PER_PAIR = 35.0
+FP64_SLOTS_EPILOGUE = 110.0
+FP64_PEAK_SLOTS_PER_S = 57.16 * 148 * 1.965e9
+
+
+def fp64_roofline(k_mean: float, n_atoms: int, ms_per_launch: float, fused: bool) -> dict:
+    slots = FP64_SLOTS_PER_PAIR * k_mean + (FP64_SLOTS_EPILOGUE if fused else 0.0)
+    achieved = slots * n_atoms / (ms_per_launch * 1e-3)
+    return {"bound": "fp64 pipe", "slots_per_atom": slots, "achieved": achieved / 1e12, "peak": FP64_PEAK_SLOTS_PER_S / 1e12,
+            "unit": "T FP64 instr/s", "frac": achieved / FP64_PEAK_SLOTS_PER_S,
+            "peak_source": "measured DFMA rate (tools/microbench.cu), 57.2 per clock and SM"}
+
+
 def argon_oracle(atoms):
     from oracle.pis_oracle import Oracle
 
@@ -349,7 +366,8 @@ def run_single(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": workload_config(args, 1), "clocks": clk.summary(), "e2e": e2e,
         "e2e_resident": e2e_resident,
-        "gpu_launches": int(launches), "roofline": roofline, "roofline_integrate": roofline_integrate, "cpu_baseline": cpu,
+        "gpu_launches": int(launches), "roofline": roofline, "roofline_fp64": fp64_roofline(k_mean, n, f_ms, fused),
+        "roofline_integrate": roofline_integrate, "cpu_baseline": cpu,
         "kernel_ms_per_step": kernel_ms, "ms_per_step_profiled": ms_profiled / args.steps,
         "list_builds_in_timed_region": int(builds), "list_builds_in_profiled_pass": int(st2["n_builds"] - st1["n_builds"]),
         "launch_path": "CUDA graphs (8/4/2 steps per replay, conditional rebuild node); gpu_launches counts executed kernel nodes",

@@ -47,3 +47,14 @@ def test_cuda_arm_json_line():
     assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-12
     assert d["e2e"]["h2d_bytes_per_step"] == 72 * d["config"]["n_atoms"] and d["e2e"]["value"] < d["value"]
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+
+
+def test_fp64_yardstick_arithmetic():
+    """roofline_fp64 of the CUDA arm: issue slots per atom x atoms / launch time against the measured DFMA rate."""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    r = bench.fp64_roofline(85.34, 4_000_000, 1.16, True)
+    assert abs(r["slots_per_atom"] - (35 * 85.34 + 110)) < 1e-9
+    assert 0.60 < r["frac"] < 0.70 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12     # ncu: 66 % for this launch
+    assert bench.fp64_roofline(85.34, 4_000_000, 1.09, False)["frac"] > r["frac"]
