@@ -488,6 +488,88 @@ ORC_API int64_t orc_build_neighbour_list(const orc_box *b, const orc_table *t, i
     return total;
 }
 
+/* All-core variant of orc_build_neighbour_list: the traversal of the reference's rayon closure
+ * (ref: lennard_jones.rs:362-412, `(0..n_cells).into_par_iter()`), cells distributed over threads.
+ * A row i is only ever written by the thread that owns i's cell, in the same (dx, dy, dz, jj)
+ * order as the serial traversal, so the CSR rows are identical to the serial function's, entry
+ * for entry.  ONE traversal: rows go into a padded scratch of cap/n entries per atom first and are
+ * compacted to CSR afterwards (returns -1 if a row or the total does not fit; the caller retries).
+ * Used by the parity tests at sizes where the serial two-pass build takes minutes (4M atoms). */
+ORC_API int64_t orc_build_neighbour_list_omp(const orc_box *b, const orc_table *t, int64_t n,
+                                             const double *pos, const int32_t *types, double extra,
+                                             int64_t *nbr_start, int32_t *nbr, int64_t cap, int n_threads) {
+    double max_rcut = orc_max_rcut(t) + extra;
+    uint64_t nc[3];
+    orc_divide_into_cells(b, max_rcut, nc);
+    int64_t nx = (int64_t)nc[0], ny = (int64_t)nc[1], nz = (int64_t)nc[2];
+    int64_t ncell_total = nx * ny * nz;
+    int64_t width = n > 0 ? cap / n : 0;
+    if (width < 1) return -1;
+    int64_t *cell_of = (int64_t *)malloc(sizeof(int64_t) * (size_t)(n > 0 ? n : 1));
+    int64_t *cell_start = (int64_t *)malloc(sizeof(int64_t) * (size_t)(ncell_total + 1));
+    int64_t *cell_atoms = (int64_t *)malloc(sizeof(int64_t) * (size_t)(n > 0 ? n : 1));
+    orc_rcut_cells(b, pos, n, nc[0], nc[1], nc[2], cell_of, cell_start, cell_atoms);
+#ifdef _OPENMP
+    if (n_threads <= 0) n_threads = omp_get_max_threads();
+#else
+    n_threads = 1;
+#endif
+    int64_t *count = (int64_t *)calloc((size_t)(n + 1), sizeof(int64_t));
+    int32_t *rows = (int32_t *)malloc(sizeof(int32_t) * (size_t)width * (size_t)(n > 0 ? n : 1));
+    int overflow = 0;
+#pragma omp parallel for schedule(dynamic, 8) num_threads(n_threads) reduction(| : overflow)
+    for (int64_t current_cell = 0; current_cell < ncell_total; ++current_cell) {
+        int64_t cx_i = current_cell % nx, cy_i = (current_cell / nx) % ny, cz_i = current_cell / (nx * ny);
+        int64_t seen[9];
+        int n_seen;
+        for (int dx = -1; dx <= 1; ++dx) {
+            n_seen = 0; /* tnc[tid].clear() sits inside the dx loop (:410) */
+            for (int dy = -1; dy <= 1; ++dy)
+                for (int dz = -1; dz <= 1; ++dz) {
+                    int64_t cx_j = rem_euclid(cx_i + dx, nx);
+                    int64_t cy_j = rem_euclid(cy_i + dy, ny);
+                    int64_t cz_j = rem_euclid(cz_i + dz, nz);
+                    int64_t a_neighbour_cell = (cz_j * ny + cy_j) * nx + cx_j;
+                    int dup = 0;
+                    for (int s = 0; s < n_seen; ++s)
+                        if (seen[s] == a_neighbour_cell) dup = 1;
+                    if (dup) continue;
+                    seen[n_seen++] = a_neighbour_cell;
+                    for (int64_t ii = cell_start[current_cell]; ii < cell_start[current_cell + 1]; ++ii) {
+                        int64_t i = cell_atoms[ii];
+                        for (int64_t jj = cell_start[a_neighbour_cell]; jj < cell_start[a_neighbour_cell + 1]; ++jj) {
+                            int64_t j = cell_atoms[jj];
+                            if (current_cell == a_neighbour_cell && i == j) continue;
+                            double rij[3] = {pos[3 * j] - pos[3 * i], pos[3 * j + 1] - pos[3 * i + 1],
+                                             pos[3 * j + 2] - pos[3 * i + 2]};
+                            orc_min_image(b, rij);
+                            int k = table_lookup(t, types[i], types[j]);
+                            if (k < 0) continue;
+                            if (sqrt(norm_squared3(rij)) > t->rcut[k] + extra) continue;
+                            if (count[i] < width) rows[i * width + count[i]] = (int32_t)j;
+                            else overflow = 1;
+                            count[i]++;
+                        }
+                    }
+                }
+        }
+    }
+    int64_t total = -1;
+    if (!overflow) {
+        nbr_start[0] = 0;
+        for (int64_t i = 0; i < n; ++i) nbr_start[i + 1] = nbr_start[i] + count[i];
+        total = nbr_start[n];
+#pragma omp parallel for schedule(static) num_threads(n_threads)
+        for (int64_t i = 0; i < n; ++i) memcpy(nbr + nbr_start[i], rows + i * width, sizeof(int32_t) * (size_t)count[i]);
+    }
+    free(rows);
+    free(count);
+    free(cell_of);
+    free(cell_start);
+    free(cell_atoms);
+    return total;
+}
+
 /* LJVPBuildListManager::compute_potential's list consumer: F_i += -f_ij over the full list,
  * PE = sum(u)/2.  ref: src/potentials/lennard_jones.rs:419-455.  Here the list may have been
  * built with extra = skin, so the reference cutoff test is re-applied per listed pair. */

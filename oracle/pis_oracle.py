@@ -69,6 +69,7 @@ def load():
             "orc_compute_potential_omp": (d, [bp, tp, i64, vp, vp, vp, C.c_int]),
             "orc_compute_potential_n2": (d, [bp, tp, i64, vp, vp, vp]),
             "orc_build_neighbour_list": (i64, [bp, tp, i64, vp, vp, d, vp, vp, i64]),
+            "orc_build_neighbour_list_omp": (i64, [bp, tp, i64, vp, vp, d, vp, vp, i64, C.c_int]),
             "orc_compute_potential_list": (d, [bp, tp, i64, vp, vp, vp, vp, vp]),
             "orc_kinetic_energy": (d, [i64, vp, vp, vp]),
             "orc_temperature": (d, [i64, d]),
@@ -191,16 +192,21 @@ class Oracle:
             raise ValueError(mode)
         return pe, f
 
-    def build_neighbour_list(self, pos, types, extra=0.0):
+    def build_neighbour_list(self, pos, types, extra=0.0, mode="serial", threads=0, cap_per_atom=64):
+        """CSR (start, nbr) of the full list; mode="omp" distributes the cells over threads (identical rows)."""
         pos = np.ascontiguousarray(pos, dtype=np.float64)
         types = np.ascontiguousarray(types, dtype=np.int32)
         n = pos.shape[0]
         start = np.zeros(n + 1, dtype=np.int64)
-        cap = max(64 * n, 1024)
+        cap = max(int(cap_per_atom) * n, 1024)
         while True:
-            nbr = np.zeros(cap, dtype=np.int32)
-            tot = self.lib.orc_build_neighbour_list(C.byref(self.box), C.byref(self.table), n, _p(pos), _p(types),
-                                                    float(extra), _p(start), _p(nbr), cap)
+            nbr = np.empty(cap, dtype=np.int32)
+            if mode == "omp":
+                tot = self.lib.orc_build_neighbour_list_omp(C.byref(self.box), C.byref(self.table), n, _p(pos), _p(types),
+                                                            float(extra), _p(start), _p(nbr), cap, int(threads))
+            else:
+                tot = self.lib.orc_build_neighbour_list(C.byref(self.box), C.byref(self.table), n, _p(pos), _p(types),
+                                                        float(extra), _p(start), _p(nbr), cap)
             if tot >= 0:
                 return start, nbr[:tot]
             cap *= 4

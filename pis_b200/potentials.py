@@ -247,6 +247,17 @@ class LJCudaManager:
         capi.check(self._h, lib.pisb_neighbours(self._h, capi._ptr(nn), capi._ptr(nb), max(cap, 1)))
         return [np.sort(nb[i, : nn[i]]) for i in range(n_atoms)]
 
+    def neighbours_padded(self, n_atoms: int):
+        """Current Verlet list in original ids as (counts, rows): rows[i, :counts[i]] are the neighbours of atom i in list
+        order, the rest of the row is undefined (test hook for sizes where a Python list of 4M arrays is too slow)."""
+        lib = capi.load()
+        nn = np.zeros(n_atoms, dtype=np.int32)
+        capi.check(self._h, lib.pisb_neighbours(self._h, capi._ptr(nn), None, 0))
+        cap = max(int(nn.max()) if n_atoms else 0, 1)
+        nb = np.empty((n_atoms, cap), dtype=np.int32)
+        capi.check(self._h, lib.pisb_neighbours(self._h, capi._ptr(nn), capi._ptr(nb), cap))
+        return nn, nb
+
     def invalidate_list(self):
         capi.check(self._h, capi.load().pisb_invalidate_list(self._h))
 

@@ -119,3 +119,28 @@ def test_every_library_option_is_documented_in_the_header():
     names = set(re.findall(r'std::strcmp\(name, "(\w+)"\)', body))
     header = open(os.path.join(root, "include", "pisb200.h")).read()
     assert names and all(n in header for n in names), sorted(n for n in names if n not in header)
+
+
+def test_example_inputs_are_the_reference_bytes():
+    """BASELINE configs[0] travels to the GPU box as tests/golden/example_input.pis (byte copy of the reference's
+    example/input.pis) and a regenerated example/argon4000.txt; both must hash to the reference's files (sha256 recorded by
+    tests/golden/make_example_inputs.py), and to the files themselves where /root/reference exists."""
+    import hashlib
+    import json
+
+    from tests.example_inputs import GOLDEN, argon4000_text, example_script
+
+    with open(os.path.join(GOLDEN, "example_sha256.json")) as f:
+        sha = json.load(f)
+    with open(os.path.join(GOLDEN, "example_input.pis"), "rb") as f:
+        script = f.read()
+    data = argon4000_text().encode()
+    assert hashlib.sha256(script).hexdigest() == sha["example/input.pis"]
+    assert hashlib.sha256(data).hexdigest() == sha["example/argon4000.txt"]
+    ref = "/root/reference/example"
+    if os.path.isdir(ref):
+        assert open(os.path.join(ref, "input.pis"), "rb").read() == script
+        assert open(os.path.join(ref, "argon4000.txt"), "rb").read() == data
+    nve = example_script(nve=True, steps=7)
+    assert "npt" not in [t for ln in nve.split("\n") for t in ln.split("#")[0].split()] and "run 7" in nve
+    assert "fix mynpt all npt temp 5.0 50.0 100 iso 0.01 0.01 1000" in example_script()

@@ -221,6 +221,45 @@ def test_golden_vectors():
     assert np.array_equal(x, np.array(g["positions_end"]))
 
 
+def test_oracle_matches_exact_arithmetic():
+    """tests/golden/exact_small.json holds a 60-digit mpmath evaluation of the reference's FORMULAS (lennard_jones.rs:33-55,
+    simulation_box.rs:17-42, potential.rs:15-33, properties.rs:17-65) on the committed 108-atom fixture, produced by
+    tests/golden/make_exact.py without touching the oracle.  The oracle's f64 restatement must agree to 1e-13: this pins
+    the oracle against the formulas themselves, not against its own output."""
+    with open(os.path.join(GOLDEN, "oracle_small.json")) as f:
+        g = json.load(f)
+    with open(os.path.join(GOLDEN, "exact_small.json")) as f:
+        e = json.load(f)
+    # no in/out decision sits within rounding distance of a threshold: the exact sets are the f64 sets
+    assert min(e["margin_rc0"], e["margin_list0"], e["margin_rc1"]) > 1e-9
+    pos, vel, types = np.array(g["positions"]), np.array(g["velocities"]), np.array(g["types"], dtype=np.int32)
+    o = make(g["L"], g["rc"])
+    tol = 1e-13
+    f0x = np.array(e["forces0"])
+    fscale = np.sqrt((f0x ** 2).sum(axis=1).mean())
+    for mode in ("serial", "omp", "n2"):
+        pe, f = o.compute_potential(pos, types, mode=mode)
+        assert abs(pe - e["pe0"]) <= tol * abs(e["pe0"]), mode
+        assert np.abs(f - f0x).max() <= tol * fscale, mode
+    start, nbr = o.build_neighbour_list(pos, types, extra=g["skin"])
+    assert [sorted(nbr[start[i]:start[i + 1]].tolist()) for i in range(len(pos))] == e["neighbours_skin"]
+    pe_l, f_l = o.compute_potential_list(pos, types, start, nbr)       # the list consumer (lennard_jones.rs:419-455)
+    assert abs(pe_l - e["pe0"]) <= tol * abs(e["pe0"])
+    assert np.abs(f_l - f0x).max() <= tol * fscale
+    # one verlet_step_nve and the observables of the new state
+    x, v, f = pos.copy(), vel.copy(), np.zeros_like(pos)
+    th = o.run_nve(x, v, f, types, g["dt"], 1)
+    assert abs(th[0, 0] - e["pe0"]) <= tol * abs(e["pe0"])
+    assert np.abs(x - np.array(e["positions1"])).max() <= tol * g["L"]
+    assert np.abs(v - np.array(e["velocities1"])).max() <= tol * np.abs(vel).max()
+    assert np.abs(f - np.array(e["forces1"])).max() <= tol * fscale
+    assert abs(th[1, 0] - e["pe1"]) <= tol * abs(e["pe1"])
+    assert abs(th[1, 1] - e["ke1"]) <= tol * abs(e["ke1"])
+    assert abs(th[1, 3] - e["temperature1"]) <= tol * abs(e["temperature1"])
+    assert abs(o.virial_trace(x, f) - e["virial_trace1"]) <= 1e-12 * np.abs(x * f).sum()     # sum r.F cancels: bound by sum |r.F|
+    assert abs(th[1, 4] - e["pressure1"]) <= 1e-12 * (2 * e["ke1"] + np.abs(x * f).sum()) / (3 * g["L"] ** 3)
+
+
 def test_golden_ensemble_vectors():
     """tests/golden/oracle_small_ensembles.json pins the NVT / NPT restatements (nvt.rs, npt.rs, potential.rs:35-135)."""
     with open(os.path.join(GOLDEN, "oracle_small.json")) as f:
