@@ -14,8 +14,8 @@
 // Kernel variants (pisb_set_option "force_variant" / "build_variant"; all give bit-identical results):
 //   k_force (v1)      plain all-FP64 loop, round(); also the only path for triclinic / non-periodic boxes
 //   k_force_v2        FP32 pre-filter + shared-memory compaction queue + exact FP64 pair terms
-//   k_force_v3        DEFAULT: all-FP64, int4 index tiles prefetched, 4 x 256-bit gathers in flight, magic rint,
-//                     interior-warp shortcut, 64-register launch bound
+//   k_force_v3        DEFAULT: all-FP64 LEAN loop (short-way distance + FP64 guard band, Newton reciprocal, factored constants),
+//                     int4 index tiles prefetched, 4 x 256-bit gathers in flight, interior-warp shortcut, 64-register bound
 //   k_force_v4        v3 with the block's cell tile staged in shared memory by TMA bulk copies (prototype)
 //   k_force_split<S>  S lanes per atom (auto below ~75k atoms): same pair terms, different summation order
 //   k_build_list (v1) all-FP64 27-cell scan;  k_build_list_v2  DEFAULT: FP32 pre-filter over contiguous x-rows
@@ -31,7 +31,12 @@ constexpr int TPB_FORCE = 128;  // force / build kernels
 // FLAG_DECISION: multi-GPU fused steps -- a stream-ordered copy of FLAG_REBUILD taken after the halo exchange.  The
 // speculative k_force_vv launch and the host both read THIS word: the kernel's own drift raises FLAG_REBUILD for the next
 // step while the launch is still running.
-enum { FLAG_REBUILD = 0, FLAG_MAXNBR = 1, FLAG_NBUILDS = 2, FLAG_BADTYPE = 3, FLAG_COMM_TIMEOUT = 4, FLAG_DECISION = 5, FLAG_COUNT = 8 };
+// FLAG_UNWRAPPED_A / _B: one word per position buffer (xt / s_xt trade places in fused steps): set by an upload that found a
+// coordinate outside [0, L) in that buffer, cleared by the drift that writes wrapped positions into it.  While it is set the
+// force kernels take the minimum-image path for EVERY warp: the interior shortcut uses raw differences and is only valid
+// when every position (the atom's and its neighbours') is the wrapped one.
+enum { FLAG_REBUILD = 0, FLAG_MAXNBR = 1, FLAG_NBUILDS = 2, FLAG_BADTYPE = 3, FLAG_COMM_TIMEOUT = 4, FLAG_DECISION = 5,
+       FLAG_UNWRAPPED_A = 6, FLAG_UNWRAPPED_B = 7, FLAG_COUNT = 8 };
 
 // Neighbour list layout: K-tiles of 4.  Entry (k, i) lives at ((k/4)*npad + i)*4 + k%4, so the four
 // neighbours k..k+3 of atom i are one aligned int4 and a warp reads 512 contiguous bytes per tile.
@@ -125,6 +130,8 @@ struct LoadArgs {
     float4 *xf;   // written when the current order/list is kept (null otherwise: the rebuild writes it)
     BoxDev box;
     const int *gids;  // multi-GPU: global ids of the uploaded (owned) atoms; null => id = upload index
+    int have_box;     // box is valid: positions can be tested against / wrapped into it
+    int unwrapped_flag;  // flags[] word of the position buffer being written
 };
 
 __global__ void __launch_bounds__(TPB) k_load_aos(LoadArgs a) {
@@ -141,6 +148,20 @@ __global__ void __launch_bounds__(TPB) k_load_aos(LoadArgs a) {
         t = 1;
     }
     x.w = type_as_double(t);
+    if (!a.have_box) {
+        if (o == 0) a.flags[a.unwrapped_flag] = 1;  // no box yet: nothing is known about these coordinates
+    } else if (a.box.ortho) {
+        if (a.gids) {
+            // multi-GPU: positions are GLOBAL WRAPPED coordinates everywhere (ownership, ghost selection, interior test)
+            wrap_pos<true>(a.box, x.x, x.y, x.z);
+        } else {
+            // single GPU: pisb_compute must not move the caller's positions (compute_potential leaves them alone and
+            // Sum r.F uses them as given); record that this buffer holds unwrapped coordinates instead
+            const bool out = (a.box.pbc[0] && !(x.x >= 0.0 && x.x < a.box.h[0])) || (a.box.pbc[1] && !(x.y >= 0.0 && x.y < a.box.h[4])) ||
+                             (a.box.pbc[2] && !(x.z >= 0.0 && x.z < a.box.h[8]));
+            if (out) a.flags[a.unwrapped_flag] = 1;
+        }
+    }
     a.xt[s] = x;
     if (a.xf) a.xf[s] = make_xf(a.box, x);
     a.vx[s] = a.vel ? a.vel[3 * (size_t)o] : 0.0;
@@ -205,6 +226,7 @@ struct HostDriftArgs {
     double dt, dt2, half_skin2;
     int always_rebuild;
     int *flags;
+    int unwrapped_flag;  // word of the position buffer written (cleared: the drift wraps)
 };
 
 template <bool ORTHO>
@@ -243,6 +265,7 @@ __global__ void __launch_bounds__(TPB) k_host_load_drift(HostDriftArgs a) {
     a.pos[o3] = x.x;
     a.pos[o3 + 1] = x.y;
     a.pos[o3 + 2] = x.z;
+    if (o == a.o0) a.flags[a.unwrapped_flag] = 0;
     if (a.always_rebuild) {
         if (o == 0) a.flags[FLAG_REBUILD] = 1;
     } else {
@@ -316,12 +339,14 @@ struct VVArgs {
     const double *vscale;  // NVT: thermostat scale exp(-dt/2 xi_1) read from device memory (null for NVE)
     double4 *xt_out;       // DRIFT: where x(t+dt) goes -- xt itself, or the other position buffer when the batch
     float4 *xf_out;        //        continues with k_force_vv launches (which alternate the two buffers)
+    int unwrapped_out;     // DRIFT: flags[] word of the buffer behind xt_out (cleared: it now holds wrapped positions)
 };
 
 template <bool KICK, bool DRIFT, bool ORTHO>
 __global__ void __launch_bounds__(TPB, 4) k_vv(VVArgs a) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double red[4] = {0.0, 0.0, 0.0, 0.0};  // ke, x*fx, y*fy, z*fz
+    if (DRIFT && i == 0) a.flags[a.unwrapped_out] = 0;  // nobody reads this word while a drift is running
     if (i < a.n && !is_ghost(a.xt[i].w)) {
         // every independent load first (the kernel is latency-bound otherwise: the mass lookup depends on x.w)
         double4 x = a.xt[i];
@@ -959,6 +984,7 @@ struct Force2Args {
     unsigned int *ticket;
     pisb_thermo *thermo;
     const int *skip_flag;  // multi-GPU: the launch is speculative and returns at once if *skip_flag != 0 (a rebuild comes first)
+    const int *unwrapped;  // FLAG_UNWRAPPED word of the position buffer xt: non-zero => no interior shortcut
 };
 
 // One in-range pair, reference operation order (bit-identical per-pair terms).
@@ -1050,10 +1076,114 @@ __device__ __forceinline__ void force2_body(const Force2Args &a, int i, int (*q)
     }
 }
 
-// v3: all-FP64 (no pre-filter, no queue, L1 stays a cache) with the latency fixed: the list is read
-// as one int4 per 4 neighbours and prefetched one tile ahead (the index stream comes from DRAM), four
-// gathers are in flight per thread, rint is the magic-constant form and interior warps skip the image
-// search.  Same results as v1/v2, bit for bit.
+// ------------------------------------------------------------------------------------------------
+// Lean force loop (the default kernels: k_force_v3, k_force_vv, k_force_split).  Arithmetic: pisb_device.cuh "Lean pair
+// arithmetic".  The in/out decision stays the reference's: the squared distance computed the short way is within
+// band = (4 L/rc + 32) 2^-51 (relative) of the reference's r2 = |h (h_inv d - round(h_inv d))|^2 -- the round trip
+// through the fractional coordinate costs a relative error of a few ulp of L/|d| -- so outside [t_lo, t_hi] both
+// agree, and inside it (one pair in ~10^11) the reference-order predicate is evaluated, out of line.
+// ------------------------------------------------------------------------------------------------
+__device__ __noinline__ bool exact_r2_gt(double h0, double h1, double h2, double i0, double i1, double i2, double xix, double xiy,
+                                         double xiz, double xjx, double xjy, double xjz, double t) {
+    double sx = __dmul_rn(i0, __dsub_rn(xjx, xix)), sy = __dmul_rn(i1, __dsub_rn(xjy, xiy)), sz = __dmul_rn(i2, __dsub_rn(xjz, xiz));
+    sx = __dsub_rn(sx, round(sx));
+    sy = __dsub_rn(sy, round(sy));
+    sz = __dsub_rn(sz, round(sz));
+    return norm2(__dmul_rn(h0, sx), __dmul_rn(h1, sy), __dmul_rn(h2, sz)) > t;
+}
+
+// per-atom sums of the lean loop; finish() applies the constant factors once
+template <bool MULTI>
+struct LeanAcc {
+    double fx = 0.0, fy = 0.0, fz = 0.0;  // sum w d           (MULTI: sum c24 w d)
+    double a = 0.0, b = 0.0;              // sum s12, sum s6   (MULTI: sum u, sum fs r2)
+    int cnt = 0;                          // pairs in range (for the energy shift)
+    __device__ __forceinline__ void pair(const PairDev &p, double dx, double dy, double dz, double r2) {
+        const double y = rcp_newton(r2);
+        const double s2 = p.sig2 * y;
+        const double s6 = (s2 * s2) * s2;
+        const double s12 = s6 * s6;
+        const double t = fma(2.0, s12, -s6);
+        if (MULTI) {
+            const double w = (p.c24 * t) * y;
+            fx = fma(w, dx, fx);
+            fy = fma(w, dy, fy);
+            fz = fma(w, dz, fz);
+            a += fma(p.c4, s12 - s6, -p.ucut);
+            b = fma(p.c24, t, b);
+        } else {
+            const double w = t * y;
+            fx = fma(w, dx, fx);
+            fy = fma(w, dy, fy);
+            fz = fma(w, dz, fz);
+            a += s12;
+            b += s6;
+            ++cnt;
+        }
+    }
+    // F_i = -sum fs rij, PE contribution sum u, pair virial sum fs r2 (lennard_jones.rs:33-55, :230-232)
+    __device__ __forceinline__ void finish(const PairDev &p0, double &ofx, double &ofy, double &ofz, double &pe, double &vir) const {
+        if (MULTI) {
+            ofx = -fx, ofy = -fy, ofz = -fz;
+            pe = a;
+            vir = b;
+        } else {
+            ofx = -p0.c24 * fx, ofy = -p0.c24 * fy, ofz = -p0.c24 * fz;
+            pe = fma(p0.c4, a - b, -(double)cnt * p0.ucut);
+            vir = p0.c24 * fma(2.0, a, -b);
+        }
+    }
+};
+
+// displacement xj - xi (minimum image when IMAGE) and its square, the short way
+template <bool IMAGE>
+__device__ __forceinline__ double lean_disp(const BoxDev &b, const double4 &xi, const double4 &xj, double &dx, double &dy, double &dz) {
+    dx = xj.x - xi.x;
+    dy = xj.y - xi.y;
+    dz = xj.z - xi.z;
+    if (IMAGE) {
+        dx = fma(-rint_magic_d(dx * b.hinv[0]), b.h[0], dx);
+        dy = fma(-rint_magic_d(dy * b.hinv[4]), b.h[4], dy);
+        dz = fma(-rint_magic_d(dz * b.hinv[8]), b.h[8], dz);
+    }
+    return fma(dz, dz, fma(dy, dy, dx * dx));
+}
+
+// the reference's `rij.norm() > rcut -> skip` from the lean r2, reference-order predicate inside the guard band
+__device__ __forceinline__ bool lean_in_range(const BoxDev &b, const PairDev &p, const double4 &xi, const double4 &xj, double r2) {
+    if (le_bits(r2, p.t_lo)) return true;
+    if (!le_bits(r2, p.t_hi)) return false;
+    return !exact_r2_gt(b.h[0], b.h[4], b.h[8], b.hinv[0], b.hinv[4], b.hinv[8], xi.x, xi.y, xi.z, xj.x, xj.y, xj.z, p.t_rc);
+}
+
+// An atom that met a guard-band pair in the fast loop (one pair in ~10^11 lands there) is redone here, start to finish,
+// with the reference-order predicate available.  Out of line and called AFTER the loop: a call inside the hot loop would
+// make every value live across it a spill (ptxas: 300 bytes of loop spills at the 64-register bound).
+template <bool MULTI, bool IMAGE>
+__device__ __noinline__ void force_atom_exact(const double4 *__restrict__ xt, const int *__restrict__ nbr, int npad, int i, int nn, int l, int stride,
+                                              BoxDev box, PairDev pair0, const PairDev *__restrict__ table, int n_types, double *out5) {
+    const double4 xi = xt[i];
+    const int ti = MULTI ? type_of(xi.w) : 1;
+    LeanAcc<MULTI> acc;
+    for (int k0 = 4 * l; k0 < nn; k0 += 4 * stride)
+        for (int k = k0; k < min(k0 + 4, nn); ++k) {
+            const int j = nbr[nbr_at(k, i, npad)];
+            const double4 xj = ldg_d4(&xt[j]);
+            double dx, dy, dz;
+            const double r2 = lean_disp<IMAGE>(box, xi, xj, dx, dy, dz);
+            PairDev p = pair0;
+            if (MULTI) {
+                const int tj = type_of(xj.w);
+                p = table[(min(ti, tj) - 1) * n_types + (max(ti, tj) - 1)];
+                if (!p.present) continue;
+            }
+            if (lean_in_range(box, p, xi, xj, r2)) acc.pair(p, dx, dy, dz, r2);
+        }
+    acc.finish(pair0, out5[0], out5[1], out5[2], out5[3], out5[4]);
+}
+
+// One thread per atom: the list is read as one int4 per 4 neighbours and prefetched one tile ahead (the index stream
+// comes from DRAM), four 256-bit gathers are in flight per thread, interior warps skip the image search.
 template <bool MULTI, bool IMAGE>
 __device__ __forceinline__ void force3_body(const Force2Args &a, int i, double &fx, double &fy, double &fz, double &pe,
                                             double &vir) {
@@ -1061,7 +1191,9 @@ __device__ __forceinline__ void force3_body(const Force2Args &a, int i, double &
     const int ti = MULTI ? type_of(xi.w) : 1;
     const int nn = a.nnbr[i];
     const int4 *tiles = reinterpret_cast<const int4 *>(a.nbr) + i;
-    int4 cur = nn > 0 ? ldg_stream_i4(tiles) : make_int4(i, i, i, i);
+    int4 cur = nn > 0 ? ldg_stream_i4(tiles) : make_int4(0, 0, 0, 0);
+    LeanAcc<MULTI> acc;
+    bool ambiguous = false;
     for (int k = 0; k < nn; k += 4) {
         int4 nxt = cur;
         if (k + 4 < nn) nxt = ldg_stream_i4(tiles + (size_t)((k >> 2) + 1) * a.npad);
@@ -1071,33 +1203,32 @@ __device__ __forceinline__ void force3_body(const Force2Args &a, int i, double &
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             in[u] = k + u < nn;
-            if (!in[u]) j[u] = i;
+            if (!in[u]) j[u] = 0;  // the tail of the last tile is not written by the build: any valid slot (a constant keeps `i` out of the loop's registers)
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) xj[u] = ldg_d4(&a.xt[j[u]]);
-        double dx[4], dy[4], dz[4], r2[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            disp_inrange_ortho<IMAGE>(a.box, xi, xj[u], dx[u], dy[u], dz[u]);
-            r2[u] = norm2(dx[u], dy[u], dz[u]);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
+            double dx, dy, dz;
+            const double r2 = lean_disp<IMAGE>(a.box, xi, xj[u], dx, dy, dz);
             PairDev p = a.pair0;
             if (MULTI) {
                 const int tj = type_of(xj[u].w);
                 p = a.table[(min(ti, tj) - 1) * a.n_types + (max(ti, tj) - 1)];
                 in[u] = in[u] && p.present;
             }
-            // `rij.norm() > rcut -> skip` as r2 > T; r2 and T are non-negative doubles, whose order is the order of their
-            // bit patterns: an integer compare keeps this test off the saturated FP64 pipe
-            if (in[u] && __double_as_longlong(r2[u]) <= __double_as_longlong(p.t_rc)) {
-                double uu, fs;
-                lj_pair(p, r2[u], uu, fs);
-                PISB_ACCUM(dx[u], dy[u], dz[u], r2[u], uu, fs);
+            if (in[u]) {
+                if (le_bits(r2, p.t_lo)) acc.pair(p, dx, dy, dz, r2);
+                else ambiguous |= le_bits(r2, p.t_hi);
             }
         }
         cur = nxt;
+    }
+    acc.finish(a.pair0, fx, fy, fz, pe, vir);
+    if (ambiguous) {
+        double o[5];
+        force_atom_exact<MULTI, IMAGE>(a.xt, a.nbr, a.npad, i, nn, 0, 1, a.box, a.pair0, a.table, a.n_types, o);
+        fx = o[0], fy = o[1], fz = o[2], pe = o[3], vir = o[4];
     }
 }
 
@@ -1108,8 +1239,8 @@ __global__ void __launch_bounds__(TPB_FORCE, 8) k_force_v3(Force2Args a) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double red[2] = {0.0, 0.0};
     const bool active = i < a.n && !xf_is_ghost(a.xf[i]);
-    bool interior = true;
-    if (active) interior = is_interior(a.boxf, a.xf[i]);
+    bool interior = *a.unwrapped == 0;
+    if (active) interior = interior && is_interior(a.boxf, a.xf[i]);
     const bool warp_interior = __all_sync(0xffffffffu, interior);
     if (active) {
         double fx = 0.0, fy = 0.0, fz = 0.0, pe = 0.0, vir = 0.0;
@@ -1155,6 +1286,7 @@ struct ForceVVArgs {
     double dt, dt2, half_skin2;
     int always_rebuild;
     int *flags;
+    int unwrapped_out;  // flags[] word of the buffer behind xt_out (cleared by a drifting launch; never the word this launch reads)
 };
 
 // (Evict-first loads / stores for the epilogue's streams, L2 prefetch of its operands at thread start and an L2 evict-first
@@ -1168,12 +1300,13 @@ __global__ void __launch_bounds__(TPB_FORCE, 8) k_force_vv(ForceVVArgs b) {
     if (BRICK && a.skip_flag && *a.skip_flag != 0) return;  // speculative launch, a rebuild comes first
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double red[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};  // pe, pair virial, ke, x*fx, y*fy, z*fz
+    if (DRIFT && i == 0) b.flags[b.unwrapped_out] = 0;
     bool active = i < a.n;
-    bool interior = true;
+    bool interior = *a.unwrapped == 0;
     if (active) {
         const float4 xfi = a.xf[i];  // one load serves both tests (written this way the force loop stays free of spills)
         if (BRICK && xf_is_ghost(xfi)) active = false;
-        else interior = is_interior(a.boxf, xfi);
+        else interior = interior && is_interior(a.boxf, xfi);
     }
     const bool warp_interior = __all_sync(0xffffffffu, interior);
     if (active) {
@@ -1249,6 +1382,8 @@ __device__ __forceinline__ void force_split_body(const Force2Args &a, int i, int
     const int ti = MULTI ? type_of(xi.w) : 1;
     const int nn = a.nnbr[i];
     const int4 *tiles = reinterpret_cast<const int4 *>(a.nbr) + i;
+    LeanAcc<MULTI> acc;
+    bool ambiguous = false;
     for (int k = 4 * l; k < nn; k += 4 * S) {
         const int4 cur = __ldg(tiles + (size_t)(k >> 2) * a.npad);
         int j[4] = {cur.x, cur.y, cur.z, cur.w};
@@ -1264,20 +1399,24 @@ __device__ __forceinline__ void force_split_body(const Force2Args &a, int i, int
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             double dx, dy, dz;
-            disp_inrange_ortho<IMAGE>(a.box, xi, xj[u], dx, dy, dz);
-            const double r2 = norm2(dx, dy, dz);
+            const double r2 = lean_disp<IMAGE>(a.box, xi, xj[u], dx, dy, dz);
             PairDev p = a.pair0;
             if (MULTI) {
                 const int tj = type_of(xj[u].w);
                 p = a.table[(min(ti, tj) - 1) * a.n_types + (max(ti, tj) - 1)];
                 in[u] = in[u] && p.present;
             }
-            if (in[u] && !(r2 > p.t_rc)) {
-                double uu, fs;
-                lj_pair(p, r2, uu, fs);
-                PISB_ACCUM(dx, dy, dz, r2, uu, fs);
+            if (in[u]) {
+                if (le_bits(r2, p.t_lo)) acc.pair(p, dx, dy, dz, r2);
+                else ambiguous |= le_bits(r2, p.t_hi);
             }
         }
+    }
+    acc.finish(a.pair0, fx, fy, fz, pe, vir);
+    if (ambiguous) {  // this lane's share of the row again, with the reference-order predicate in the guard band
+        double o[5];
+        force_atom_exact<MULTI, IMAGE>(a.xt, a.nbr, a.npad, i, nn, l, S, a.box, a.pair0, a.table, a.n_types, o);
+        fx = o[0], fy = o[1], fz = o[2], pe = o[3], vir = o[4];
     }
 }
 
@@ -1288,8 +1427,8 @@ __global__ void __launch_bounds__(TPB_FORCE) k_force_split(Force2Args a) {
     const int i = gt / S, l = gt % S;
     double red[2] = {0.0, 0.0};
     const bool active = i < a.n && !xf_is_ghost(a.xf[i]);
-    bool interior = true;
-    if (active) interior = is_interior(a.boxf, a.xf[i]);
+    bool interior = *a.unwrapped == 0;
+    if (active) interior = interior && is_interior(a.boxf, a.xf[i]);
     const bool warp_interior = __all_sync(0xffffffffu, interior);
     double fx = 0.0, fy = 0.0, fz = 0.0, pe = 0.0, vir = 0.0;
     if (active) {
@@ -1329,8 +1468,8 @@ __global__ void __launch_bounds__(TPB_FORCE) k_force_v2(Force2Args a) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double red[2] = {0.0, 0.0};
     const bool active = i < a.n && !xf_is_ghost(a.xf[i]);
-    bool interior = true;
-    if (active) interior = is_interior(a.boxf, a.xf[i]);
+    bool interior = *a.unwrapped == 0;
+    if (active) interior = interior && is_interior(a.boxf, a.xf[i]);
     const bool warp_interior = __all_sync(0xffffffffu, interior);
     if (active) {
         double fx = 0.0, fy = 0.0, fz = 0.0, pe = 0.0, vir = 0.0;
@@ -1391,6 +1530,8 @@ __device__ __forceinline__ void force4_body(const Force2Args &a, int i, const V4
     const int4 *tiles = reinterpret_cast<const int4 *>(a.nbr) + i;
     int4 cur = nn > 0 ? __ldg(tiles) : make_int4(0, 0, 0, 0);
     int r = 0, cur_end = sm.gend[0], cur_off = sm.prefix[0] - sm.gstart[0];
+    LeanAcc<MULTI> acc;
+    bool ambiguous = false;
     for (int k = 0; k < nn; k += 4) {
         int4 nxt = cur;
         if (k + 4 < nn) nxt = __ldg(tiles + (size_t)((k >> 2) + 1) * a.npad);
@@ -1411,27 +1552,28 @@ __device__ __forceinline__ void force4_body(const Force2Args &a, int i, const V4
             }
             xj[u] = sm.tile[loc];
         }
-        double dx[4], dy[4], dz[4], r2[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            disp_inrange_ortho<IMAGE>(a.box, xi, xj[u], dx[u], dy[u], dz[u]);
-            r2[u] = norm2(dx[u], dy[u], dz[u]);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
+            double dx, dy, dz;
+            const double r2 = lean_disp<IMAGE>(a.box, xi, xj[u], dx, dy, dz);
             PairDev p = a.pair0;
             if (MULTI) {
                 const int tj = type_of(xj[u].w);
                 p = a.table[(min(ti, tj) - 1) * a.n_types + (max(ti, tj) - 1)];
                 in[u] = in[u] && p.present;
             }
-            if (in[u] && !(r2[u] > p.t_rc)) {
-                double uu, fs;
-                lj_pair(p, r2[u], uu, fs);
-                PISB_ACCUM(dx[u], dy[u], dz[u], r2[u], uu, fs);
+            if (in[u]) {
+                if (le_bits(r2, p.t_lo)) acc.pair(p, dx, dy, dz, r2);
+                else ambiguous |= le_bits(r2, p.t_hi);
             }
         }
         cur = nxt;
+    }
+    acc.finish(a.pair0, fx, fy, fz, pe, vir);
+    if (ambiguous) {
+        double o[5];
+        force_atom_exact<MULTI, IMAGE>(a.xt, a.nbr, a.npad, i, nn, 0, 1, a.box, a.pair0, a.table, a.n_types, o);
+        fx = o[0], fy = o[1], fz = o[2], pe = o[3], vir = o[4];
     }
 }
 
@@ -1484,8 +1626,8 @@ __global__ void __launch_bounds__(TPB_FORCE, 4) k_force_v4(Force2Args a, const i
     const bool staged = sm.staged != 0;
     double red[2] = {0.0, 0.0};
     const bool active = i < a.n && !xf_is_ghost(a.xf[i]);
-    bool interior = true;
-    if (active) interior = is_interior(a.boxf, a.xf[i]);
+    bool interior = *a.unwrapped == 0;
+    if (active) interior = interior && is_interior(a.boxf, a.xf[i]);
     const bool warp_interior = __all_sync(0xffffffffu, interior);
     if (staged) {
         const unsigned bar = smem_u32(&sm.bar);

@@ -94,6 +94,7 @@ struct pisb_handle {
     // device arrays
     DevBuf<double4> xt, s_xt;
     DevBuf<float4> xf, xf2;  // xf2: the other FP32 shadow buffer of the fused force+integrator step (xt alternates with s_xt)
+    int xt_flag = FLAG_UNWRAPPED_A, s_xt_flag = FLAG_UNWRAPPED_B;  // flags[] word of each position buffer ("holds unwrapped coordinates")
     DevBuf<float> xp;  // pair-packed FP32 positions (k_build_list_v3), rewritten at every rebuild
     DevBuf<PairF> tablef_d;
     DevBuf<double> v[3], f[3], g[3], xb[3], s_v[3], s_f[3];
@@ -288,6 +289,7 @@ int build_pair_table(pisb_t *h) {
         p.sig2 = s * s;
         p.t_rc = sqrt_threshold(rc);
         p.t_list = sqrt_threshold(rc + h->skin);
+        p.t_lo = p.t_hi = p.t_rc;  // widened to the FP64 guard band once the box is known (setup_filter)
         if (h->shift) {
             // lennard_jones.rs:44-52, same expression order
             const double q = s / rc;
@@ -350,8 +352,22 @@ int setup_filter(pisb_t *h) {
         f.lo_list = f32_below(h->pairs[k].t_list * (1.0 - band_l));
         f.hi_list = f32_above(h->pairs[k].t_list * (1.0 + band_l));
     }
+    // FP64 guard band of the lean force loop (pisb_kernels.cuh "Lean force loop"): the short-way r2 and the reference's
+    // r2 = |h (h_inv d - round(h_inv d))|^2 differ by the rounding of the fractional round trip, a few ulp x L/|d|
+    // relative; band = 2 x (4 L/rc + 32) ulp covers it with an order of magnitude to spare.  Rounded outwards.
+    for (int k = 0; k < nt * nt; ++k) {
+        PairDev &p = h->pairs[k];
+        if (!p.present) continue;
+        const double band = 2.0 * (4.0 * lmax / h->rcut[k] + 32.0) * std::ldexp(1.0, -52);
+        p.t_lo = std::nextafter(p.t_rc * (1.0 - band), 0.0);
+        p.t_hi = std::nextafter(p.t_rc * (1.0 + band), INFINITY);
+    }
+    CUDA_TRY(h, cudaMemcpyAsync(h->table_d.p, h->pairs.data(), sizeof(PairDev) * nt * nt, cudaMemcpyHostToDevice, h->stream));
     TRY(dev_reserve(h, h->tablef_d, (size_t)nt * nt));
-    if (!v2_possible(h)) return PISB_OK;  // the FP32 pre-filter kernels are not selectable for this box
+    if (!v2_possible(h)) {  // the FP32 pre-filter kernels are not selectable for this box
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        return PISB_OK;
+    }
     CUDA_TRY(h, cudaMemcpyAsync(h->tablef_d.p, h->pairsf.data(), sizeof(PairF) * nt * nt, cudaMemcpyHostToDevice,
                                 h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -617,7 +633,7 @@ int launch_force(pisb_t *h, double *const out[3], const double *const acc[3], pi
         if (!v2_possible(h)) return fail(h, PISB_ERR_INVALID, "force_variant 2/3 needs an orthorhombic, fully periodic box");
         Force2Args f2{h->n, h->npad, h->xt.p, h->xf.p, h->nbr.p, h->nnbr.p, h->box, h->boxf, h->pairs[0], h->pairsf[0],
                       h->table_d.p, h->tablef_d.p, h->n_types, fa.ax, fa.ay, fa.az, out[0], out[1], out[2],
-                      h->partials.p, h->ticket, rec, skip_flag};
+                      h->partials.p, h->ticket, rec, skip_flag, h->flags + h->xt_flag};
         // only the default kernels honour skip_flag
         if (skip_flag && h->force_variant != 0 && h->force_variant != 3 && h->force_variant != 6)
             return fail(h, PISB_ERR_STATE, "speculative force launch needs force_variant 0, 3 or 6");
@@ -661,6 +677,7 @@ int launch_force(pisb_t *h, double *const out[3], const double *const acc[3], pi
 void swap_position_buffers(pisb_t *h) {
     std::swap(h->xt, h->s_xt);
     std::swap(h->xf, h->xf2);
+    std::swap(h->xt_flag, h->s_xt_flag);
 }
 
 int launch_vv(pisb_t *h, bool kick, bool drift, double dt, pisb_thermo *rec, const double *vscale = nullptr,
@@ -671,7 +688,7 @@ int launch_vv(pisb_t *h, bool kick, bool drift, double dt, pisb_thermo *rec, con
              h->g[0].p, h->g[1].p, h->g[2].p, h->xb[0].p, h->xb[1].p, h->xb[2].p, h->mass_d.p, h->box,
              dt, dt * dt, h->skin_half2_override >= 0.0 ? h->skin_half2_override : hs * hs,
              (h->skin > 0.0 && h->skin_half2_override != 0.0) ? 0 : 1, h->flags, h->partials.p, h->ticket, rec, vscale,
-             out_of_place ? h->s_xt.p : h->xt.p, out_of_place ? h->xf2.p : h->xf.p};
+             out_of_place ? h->s_xt.p : h->xt.p, out_of_place ? h->xf2.p : h->xf.p, out_of_place ? h->s_xt_flag : h->xt_flag};
     const int nb = nblk(h->n, TPB);
     cudaStream_t st = h->stream;
     const bool o = h->box.ortho != 0;
@@ -703,11 +720,11 @@ int launch_force_vv(pisb_t *h, bool drift, double dt, pisb_thermo *rec, const in
         const double hs = 0.5 * h->skin;
         ForceVVArgs fv{Force2Args{h->n, h->npad, h->xt.p, h->xf.p, h->nbr.p, h->nnbr.p, h->box, h->boxf, h->pairs[0], h->pairsf[0],
                                   h->table_d.p, h->tablef_d.p, h->n_types, nullptr, nullptr, nullptr, h->g[0].p, h->g[1].p, h->g[2].p,
-                                  h->partials.p, h->ticket, rec, skip_flag},
+                                  h->partials.p, h->ticket, rec, skip_flag, h->flags + h->xt_flag},
                        h->v[0].p, h->v[1].p, h->v[2].p, h->f[0].p, h->f[1].p, h->f[2].p, h->xb[0].p, h->xb[1].p, h->xb[2].p,
                        h->mass_d.p, h->s_xt.p, h->xf2.p, dt, dt * dt,
                        h->skin_half2_override >= 0.0 ? h->skin_half2_override : hs * hs,
-                       (h->skin > 0.0 && h->skin_half2_override != 0.0) ? 0 : 1, h->flags};
+                       (h->skin > 0.0 && h->skin_half2_override != 0.0) ? 0 : 1, h->flags, h->s_xt_flag};
         const bool multi = h->n_types > 1;
         const int nb = nblk(h->n, TPB_FORCE);
         cudaStream_t st = h->stream;
@@ -812,7 +829,8 @@ int do_upload(pisb_t *h, int64_t n64, const double *pos, const double *vel, cons
         LoadArgs la{n, h->st_pos.p, vel ? h->st_vel.p : nullptr, frc ? h->st_frc.p : nullptr,
                     h->st_types.p, same_set ? h->slot_of_id.p : nullptr, h->xt.p,
                     h->v[0].p, h->v[1].p, h->v[2].p, h->f[0].p, h->f[1].p, h->f[2].p, h->id.p, h->n_types, h->flags,
-                    (same_set && h->have_box) ? h->xf.p : nullptr, h->box, nullptr};
+                    (same_set && h->have_box) ? h->xf.p : nullptr, h->box, nullptr, h->have_box ? 1 : 0, h->xt_flag};
+        TRY(set_flag(h, h->xt_flag, 0));
         k_load_aos<<<nblk(n, TPB), TPB, 0, h->stream>>>(la);
         TRY(check_launch(h, "k_load_aos"));
         if (same_set && h->have_box) {
@@ -1020,7 +1038,7 @@ void graph_signature(pisb_t *h, double dt, std::vector<unsigned char> &sig) {
     put(h->grid.n, sizeof h->grid.n), put(h->grid.lo, sizeof h->grid.lo), put(h->grid.hi, sizeof h->grid.hi);
     put(&h->boxf.margin, sizeof(float));
     for (const PairDev &pd : h->pairs) {
-        const double v[] = {pd.c4, pd.c24, pd.sig2, pd.t_rc, pd.t_list, pd.ucut, (double)pd.present};
+        const double v[] = {pd.c4, pd.c24, pd.sig2, pd.t_rc, pd.t_list, pd.ucut, (double)pd.present, pd.t_lo, pd.t_hi};
         put(v, sizeof v);
     }
 }
@@ -2153,7 +2171,10 @@ int pisb_set_box(pisb_t *h, const double *h9, const double *hinv9, const int *pb
     if (changed) {
         h->grid_ok = false;
         h->list_valid = false;
-        if (h->have_atoms) TRY(setup_grid(h));
+        if (h->have_atoms) {
+            TRY(set_flag(h, h->xt_flag, 1));  // resident positions were not checked against THIS box: no interior shortcut until a drift wraps them
+            TRY(setup_grid(h));
+        }
     }
     return PISB_OK;
 }
@@ -2329,7 +2350,7 @@ static int host_step_pipelined(pisb_t *h, double *pos, double *vel, double *forc
             LaunchScope ls(h, PISB_K_COPY);
             HostDriftArgs a{o0, o1, h->st_pos.p, h->st_vel.p, h->st_frc.p, h->slot_of_id.p, h->xt.p, h->xf.p,
                             h->v[0].p, h->v[1].p, h->v[2].p, h->f[0].p, h->f[1].p, h->f[2].p, h->xb[0].p, h->xb[1].p, h->xb[2].p,
-                            h->mass_d.p, h->box, dt, dt * dt, half_skin2, always, h->flags};
+                            h->mass_d.p, h->box, dt, dt * dt, half_skin2, always, h->flags, h->xt_flag};
             if (h->box.ortho) k_host_load_drift<true><<<nblk(o1 - o0, TPB), TPB, 0, h->stream>>>(a);
             else k_host_load_drift<false><<<nblk(o1 - o0, TPB), TPB, 0, h->stream>>>(a);
             TRY(check_launch(h, "k_host_load_drift"));
@@ -2621,7 +2642,8 @@ int pisb_upload_owned(pisb_t *h, int64_t n_own, const double *pos, const double 
         LaunchScope ls(h, PISB_K_COPY);
         LoadArgs la{n, h->st_pos.p, vel ? h->st_vel.p : nullptr, force ? h->st_frc.p : nullptr, h->st_types.p, nullptr,
                     h->xt.p, h->v[0].p, h->v[1].p, h->v[2].p, h->f[0].p, h->f[1].p, h->f[2].p, h->id.p, h->n_types,
-                    h->flags, nullptr, h->box, h->m_dest.p};
+                    h->flags, nullptr, h->box, h->m_dest.p, 1, h->xt_flag};
+        TRY(set_flag(h, h->xt_flag, 0));
         k_load_aos<<<nblk(n, TPB), TPB, 0, h->stream>>>(la);
         TRY(check_launch(h, "k_load_aos"));
     }

@@ -228,6 +228,42 @@ def test_edge_positions_on_boundary_and_beyond():
     assert force_rel_err(atoms.forces, f_ref).max() <= FORCE_TOL
 
 
+@pytest.mark.parametrize("variant", [0, 6, 8])
+def test_unwrapped_inputs_far_outside_the_box_and_a_box_centred_on_the_origin(variant):
+    """Step-0 inputs need not lie in [0, L) (simulation.rs:28 calls compute_potential on them as read): atoms several
+    box lengths out, and a whole system given in [-L/2, L/2).  The interior-warp shortcut of the force kernels uses raw
+    coordinate differences, so it must stay off until a drift has wrapped the positions (the flag words FLAG_UNWRAPPED_*):
+    forces, energy and lists must equal those of the SAME system wrapped into the box, then both runs must stay together."""
+    base = _jittered(16, jitter=0.2, temperature=40.0, seed=17)      # 16384 atoms, box edge 86.6: interior warps exist
+    L = base.sim_box.h[0, 0]
+    rng = np.random.default_rng(3)
+    cases = {"centred": base.positions - 0.5 * L,
+             "far": base.positions + L * rng.integers(-3, 4, size=base.positions.shape).astype(np.float64)}
+    ref_mgr = make_manager(skin=SKIN, variant=variant)
+    ref_mgr.attach(base)
+    pe_ref = ref_mgr.compute()
+    rows_ref = ref_mgr.neighbours(base.n_atoms)
+    a_ref = Atoms(base.type_ids, base.masses, base.positions.copy(), base.sim_box, velocities=base.velocities.copy())
+    ref_mgr.download(a_ref, positions=False, velocities=False)
+    th_ref = ref_mgr.step_nve(0.25, 6)
+    for name, pos in cases.items():
+        a = Atoms(base.type_ids, base.masses, np.ascontiguousarray(pos), base.sim_box, velocities=base.velocities.copy())
+        m = make_manager(skin=SKIN, variant=variant)
+        m.attach(a)
+        pe = m.compute()
+        m.download(a, velocities=False)
+        assert np.array_equal(a.positions, pos), name                     # compute_potential leaves the positions alone
+        assert abs(pe - pe_ref) <= 1e-12 * abs(pe_ref), name
+        assert force_rel_err(a.forces, a_ref.forces).max() <= 1e-11, name  # image shifts by k L round differently: not bitwise
+        for r1, r0 in zip(m.neighbours(a.n_atoms), rows_ref):
+            assert np.array_equal(r1, r0), name
+        th = m.step_nve(0.25, 6)
+        for key in ("pe", "ke"):
+            assert np.max(np.abs(th[key] - th_ref[key]) / np.abs(th_ref[key])) <= 1e-10, (name, key)
+        m.download(a)
+        assert a.positions.min() >= 0.0 and a.positions.max() <= L        # the drift wrapped them
+
+
 def test_two_atoms_analytic():
     """u(2^(1/6) sigma) = -eps - u_cut and f = 0 there."""
     eps, sig, rc = 0.238, 3.405, 8.5
@@ -256,26 +292,37 @@ def test_errors():
         make_manager(skin=0.0, rc=8.5).compute_potential(atoms2)
 
 
-def test_v2_prefilter_is_bitwise_equal_to_v1():
-    """The FP32 pre-filter only decides in/out (exact fallback in the guard band) and phase 2 keeps
-    the reference operation order: v2 forces / energies are BIT-identical to the all-FP64 v1 kernels."""
+def test_kernel_families_agree():
+    """Two arithmetic families.  REFERENCE-ORDER kernels (v1 all-FP64, v2 FP32 pre-filter + queue) keep
+    the reference's operation order per pair: their forces / energies / trajectories are BIT-identical to one another.
+    The LEAN kernels (v3 and everything built on its loop: the defaults, the fused step kernel, the TMA-staged v4) shorten the per-pair arithmetic (pisb_device.cuh)
+    but take the same in/out decisions: bit-identical among themselves, and within rounding of the reference-order family."""
     atoms = _jittered(12, jitter=0.25, temperature=50.0)
-    out = []
-    for variant in (1, 2, 3, 5, 6):
+    out = {}
+    for variant in (1, 2, 5, 3, 6):
         a = Atoms(atoms.type_ids, atoms.masses, atoms.positions.copy(), atoms.sim_box, velocities=atoms.velocities.copy())
         m = make_manager(skin=SKIN, variant=variant)
         m.set_option("fuse_vv", 0)   # the force kernels proper; k_force_vv reduces KE over other block sizes (own test below)
         m.attach(a)
         pe0 = m.compute()
+        m.download(a, positions=False, velocities=False)
+        f0 = a.forces.copy()
         th = m.step_nve(0.25, 25)
         m.download(a)
-        out.append((pe0, th, a.positions.copy(), a.velocities.copy(), a.forces.copy()))
-    for other in (1, 2, 3, 4):
-        assert out[0][0] == out[other][0]
-        for name in ("pe", "ke", "virial_ref", "virial_pair"):
-            assert np.array_equal(out[0][1][name], out[other][1][name]), name
-        for k in (2, 3, 4):
-            assert np.array_equal(out[0][k], out[other][k])
+        out[variant] = (pe0, th, a.positions.copy(), a.velocities.copy(), a.forces.copy(), f0)
+    for base, others in ((1, (2,)), (3, (5, 6))):
+        for other in others:
+            assert out[base][0] == out[other][0]
+            for name in ("pe", "ke", "virial_ref", "virial_pair"):
+                assert np.array_equal(out[base][1][name], out[other][1][name]), name
+            for k in (2, 3, 4, 5):
+                assert np.array_equal(out[base][k], out[other][k])
+    ref, lean = out[1], out[3]
+    assert abs(lean[0] - ref[0]) <= 1e-13 * abs(ref[0])
+    assert force_rel_err(lean[5], ref[5]).max() <= 1e-12          # same state, two arithmetics: rounding only
+    for name in ("pe", "ke", "virial_pair"):
+        assert np.max(np.abs(lean[1][name] - ref[1][name]) / np.abs(ref[1][name])) <= 1e-11, name
+    assert np.abs(lean[2] - ref[2]).max() <= 1e-11                # 25 steps apart by accumulated rounding only
 
 
 def test_guard_band_pairs_sit_on_the_cutoff():
