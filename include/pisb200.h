@@ -226,8 +226,9 @@ PISB_API int pisb_synchronize(pisb_t *h);
 
 /* ---- multi-GPU: spatial decomposition, ONE PROCESS PER GPU (new; the reference is single-process) ----
  * The periodic box is cut into grid3[0] x grid3[1] x grid3[2] bricks (each 1 or 2), one per rank;
- * ranks exchange ghost-atom positions every step with ncclSend/ncclRecv over NVLink and migrate atoms
- * on list-rebuild steps.  Bootstrap: rank 0 calls pisb_comm_unique_id and broadcasts the 128 bytes
+ * ranks exchange ghost-atom positions every step -- by default with NVLink stores into each peer's CUDA-IPC
+ * mapped receive buffer from the packing kernel itself (ncclSend/ncclRecv is the fallback, option halo_mode) --
+ * and migrate atoms over NCCL on list-rebuild steps.  Bootstrap: rank 0 calls pisb_comm_unique_id and broadcasts the 128 bytes
  * (torch.distributed / MPI / a file -- plumbing), then every rank calls pisb_comm_init.
  * After pisb_comm_init: pisb_set_box (the GLOBAL box), pisb_upload_owned (this rank's atoms with
  * their global ids; atoms outside the rank's brick are migrated at the first rebuild), then
@@ -251,9 +252,12 @@ PISB_API int pisb_owned_ids(pisb_t *h, int64_t cap, int32_t *global_ids, int64_t
  *                     force pass with the velocity-Verlet kick + drift in its epilogue; 0 = k_force_v3 + k_vv
  *   host_pipeline     1 (default) = pisb_verlet_step_nve_host moves x, v, F in chunks and pipelines upload, drift and
  *                     download; 0 = whole-array copies.  host_chunk_atoms = atoms per chunk, 0 = n/8 (>= 65536)
- *   force_variant     0 = automatic (v3; 8 or 4 lanes per atom below 32k / 75k atoms; v1 for a triclinic or
- *                     non-periodic box), 1 = v1 general all-FP64, 2 = FP32 pre-filter + queue, 3 = v3, 4 = TMA-staged
- *                     shared-memory tile (prototype), 6 = 8 lanes per atom
+ *   force_variant     0 = automatic (two atoms per thread with a three-section pair list above 75k atoms of one type;
+ *                     thread per atom (v3) otherwise; 8 or 4 lanes per atom below 32k / 75k atoms; v1 for a triclinic or
+ *                     non-periodic box), 1 = v1 general all-FP64 in the reference's operation order, 2 = FP32 pre-filter +
+ *                     queue, 3 = v3 thread per atom, 4 = TMA-staged shared-memory tile (prototype), 5 = pair lists at any
+ *                     size, 6 = 8 lanes per atom
+ *   pair_lists        1 (default) = allow the two-atoms-per-thread path (csrc/pisb_pairlist.cuh), 0 = per-atom lists only
  *   build_variant     0 = automatic (v3), 1 = v1 general, 2 = scalar FP32 pre-filter, 3 = packed-FP32 pair records
  *   cell_div          cells per list cutoff and dimension: 0 = automatic (2 with build_variant 2/3), 1, 2
  *   halo_mode         multi-GPU per-step ghost exchange: 0 = peer memory when it can be mapped, 1 = NCCL send/recv,

@@ -14,6 +14,7 @@
 
 #include "pisb200.h"
 #include "pisb_kernels.cuh"
+#include "pisb_pairlist.cuh"
 #include "pisb_multi.cuh"
 #include "pisb_npt.cuh"
 
@@ -77,6 +78,8 @@ struct pisb_handle {
     int build_variant = 0;
     int cell_div = 0;  // cells per list cutoff per dimension: 0 = auto, 1 = reference-sized cells, 2 = half-size cells
     int fuse_vv = 1;   // option "fuse_vv": NVE batches run k_force_vv (force + kick + drift in one launch) when the default force kernel applies
+    int pair_lists = 1;  // option "pair_lists": two atoms per thread with a three-section list (pisb_pairlist.cuh) for large single-type systems
+    DevBuf<int4> pl_counts;
 
     // box / grid
     BoxDev box{};
@@ -329,6 +332,28 @@ bool v2_possible(const pisb_t *h) {
     return h->have_box && h->box.ortho && h->box.pbc[0] && h->box.pbc[1] && h->box.pbc[2];
 }
 
+// Large single-type systems in an orthorhombic periodic box step with two atoms per thread (pisb_pairlist.cuh);
+// force_variant 5 forces that path at any size (tests).
+bool pair_mode(const pisb_t *h) {
+    if (!v2_possible(h) || h->n_types != 1 || !h->pair_lists) return false;
+    if (!(h->build_variant == 0 || h->build_variant == 3)) return false;
+    return h->force_variant == 5 || (h->force_variant == 0 && h->n > 75000);
+}
+
+int pair_threads_padded(const pisb_t *h) { return ((h->npad + 1) / 2 + 31) / 32 * 32; }
+
+PairListArgs pair_list_args(const pisb_t *h) {
+    PairListArgs pl{};
+    pl.npp = pair_threads_padded(h);
+    pl.kcap = h->kcap;
+    const size_t sec = (size_t)h->kcap * (size_t)pl.npp;
+    pl.both = h->nbr.p;
+    pl.only_a = h->nbr.p + sec;
+    pl.only_b = h->nbr.p + 2 * sec;
+    pl.counts = h->pl_counts.p;
+    return pl;
+}
+
 int setup_filter(pisb_t *h) {
     if (!h->have_box) return PISB_OK;
     const int nt = h->n_types;
@@ -534,7 +559,10 @@ int reserve_atoms(pisb_t *h, int n) {
 int reserve_list(pisb_t *h) {
     h->npad = (std::max(h->n, h->ncap_atoms) + 31) / 32 * 32;
     h->kcap = (h->kcap + 3) / 4 * 4;  // whole K-tiles of 4
-    TRY(dev_reserve(h, h->nbr, (size_t)h->kcap * (size_t)h->npad));
+    // room for either list form: per-atom rows [kcap][npad], or the three sections of the pair lists [3][kcap][npp]
+    const size_t npp = (size_t)pair_threads_padded(h);
+    TRY(dev_reserve(h, h->nbr, std::max((size_t)h->kcap * (size_t)h->npad, 3 * (size_t)h->kcap * npp)));
+    TRY(dev_reserve(h, h->pl_counts, npp));
     return PISB_OK;
 }
 
@@ -599,7 +627,9 @@ int launch_rebuild_chain(pisb_t *h) {
             if (!v2_possible(h)) return fail(h, PISB_ERR_INVALID, "build_variant 2/3 needs an orthorhombic, fully periodic box");
             Build2Args b2{n, h->npad, h->kcap, h->xt.p, h->xf.p, h->cell_start.p, h->box, h->boxf, g, h->pairs[0],
                           h->pairsf[0], h->table_d.p, h->tablef_d.p, h->n_types, h->nbr.p, h->nnbr.p, h->flags};
-            if (h->build_variant == 2) {  // v2: scalar FP32 pre-filter (kept for A/B)
+            if (pair_mode(h)) {  // two atoms per thread, three-section list
+                k_build_pairs<<<nblk((n + 1) / 2, TPB_FORCE), TPB_FORCE, 0, st>>>(b2, pair_list_args(h), h->xp.p);
+            } else if (h->build_variant == 2) {  // v2: scalar FP32 pre-filter (kept for A/B)
                 if (multi) k_build_list_v2<true><<<nb, TPB_FORCE, 0, st>>>(b2);
                 else k_build_list_v2<false><<<nb, TPB_FORCE, 0, st>>>(b2);
             } else {  // default: v3, packed FP32 pair records + bit-mask append for interior warps
@@ -634,9 +664,18 @@ int launch_force(pisb_t *h, double *const out[3], const double *const acc[3], pi
         Force2Args f2{h->n, h->npad, h->xt.p, h->xf.p, h->nbr.p, h->nnbr.p, h->box, h->boxf, h->pairs[0], h->pairsf[0],
                       h->table_d.p, h->tablef_d.p, h->n_types, fa.ax, fa.ay, fa.az, out[0], out[1], out[2],
                       h->partials.p, h->ticket, rec, skip_flag, h->flags + h->xt_flag};
+        if (pair_mode(h)) {  // two atoms per thread (pisb_pairlist.cuh)
+            ForceVVArgs fv{};
+            fv.f = f2;
+            fv.flags = h->flags;
+            const int nbp = nblk((h->n + 1) / 2, TPB_FORCE);
+            if (h->multi) k_pforce<false, false, true><<<nbp, TPB_FORCE, 0, st>>>(fv, pair_list_args(h));
+            else k_pforce<false, false, false><<<nbp, TPB_FORCE, 0, st>>>(fv, pair_list_args(h));
+            return check_launch(h, "k_pforce");
+        }
         // only the default kernels honour skip_flag
         if (skip_flag && h->force_variant != 0 && h->force_variant != 3 && h->force_variant != 6)
-            return fail(h, PISB_ERR_STATE, "speculative force launch needs force_variant 0, 3 or 6");
+            return fail(h, PISB_ERR_STATE, "speculative force launch needs force_variant 0, 3, 5 or 6");
         // systems that cannot fill the GPU with one thread per atom: S lanes per atom (force_variant 6 forces S = 8)
         const int split = h->force_variant == 6 ? 8 : (h->force_variant == 0 ? (h->n <= 32768 ? 8 : (h->n <= 75000 ? 4 : 0)) : 0);
         if (split) {
@@ -708,8 +747,9 @@ int launch_vv(pisb_t *h, bool kick, bool drift, double dt, pisb_thermo *rec, con
 // NVE batches of systems the default force kernel serves (orthorhombic, fully periodic, enough atoms for one thread per
 // atom) run one k_force_vv launch per step instead of k_force_v3 + k_vv.
 bool fused_step_possible(const pisb_t *h, bool multi_path = false) {
-    return h->fuse_vv && h->multi == multi_path && v2_possible(h) && (h->force_variant == 0 || h->force_variant == 3) &&
-           (h->force_variant == 3 || h->n > 75000);
+    if (!h->fuse_vv || h->multi != multi_path || !v2_possible(h)) return false;
+    if (pair_mode(h)) return true;
+    return (h->force_variant == 0 || h->force_variant == 3) && (h->force_variant == 3 || h->n > 75000);
 }
 
 // F(t+dt) -> g, kick with F(t) = f, [drift into the other position buffer], then f <-> g (and the position buffers).
@@ -728,6 +768,17 @@ int launch_force_vv(pisb_t *h, bool drift, double dt, pisb_thermo *rec, const in
         const bool multi = h->n_types > 1;
         const int nb = nblk(h->n, TPB_FORCE);
         cudaStream_t st = h->stream;
+        if (pair_mode(h)) {
+            const int nbp = nblk((h->n + 1) / 2, TPB_FORCE);
+            const PairListArgs pl = pair_list_args(h);
+            if (drift) {
+                if (h->multi) k_pforce<true, true, true><<<nbp, TPB_FORCE, 0, st>>>(fv, pl);
+                else k_pforce<true, true, false><<<nbp, TPB_FORCE, 0, st>>>(fv, pl);
+            } else {
+                if (h->multi) k_pforce<true, false, true><<<nbp, TPB_FORCE, 0, st>>>(fv, pl);
+                else k_pforce<true, false, false><<<nbp, TPB_FORCE, 0, st>>>(fv, pl);
+            }
+        } else {
 #define FVV(T, D)                                                              \
     do {                                                                       \
         if (h->multi) k_force_vv<T, D, true><<<nb, TPB_FORCE, 0, st>>>(fv);    \
@@ -741,6 +792,7 @@ int launch_force_vv(pisb_t *h, bool drift, double dt, pisb_thermo *rec, const in
             else FVV(false, false);
         }
 #undef FVV
+        }
     }
     if (!skip_flag) {
         for (int d = 0; d < 3; ++d) std::swap(h->f[d], h->g[d]);
@@ -1028,7 +1080,9 @@ void graph_signature(pisb_t *h, double dt, std::vector<unsigned char> &sig) {
                           h->tile_sum.p, h->mass_d.p, h->partials.p, h->table_d.p, h->thermo_d.p, h->flags, h->ticket, h->nhc_d.p,
                           h->nhc_energy_d.p};
     put(ptrs, sizeof ptrs);
-    const int ints[] = {h->n, h->npad, h->kcap, h->n_types, h->force_variant, h->build_variant, h->cell_div, h->fuse_vv};
+    const int ints[] = {h->n, h->npad, h->kcap, h->n_types, h->force_variant, h->build_variant, h->cell_div, h->fuse_vv, h->pair_lists,
+                        pair_mode(h) ? 1 : 0};
+    put(&h->pl_counts.p, sizeof(void *));
     put(ints, sizeof ints);
     const double dbl[] = {dt, h->skin, h->skin_half2_override, h->max_rcut};
     put(dbl, sizeof dbl);
@@ -1945,7 +1999,7 @@ int do_step_nve_multi(pisb_t *h, double dt, int64_t nsteps, pisb_thermo *out) {
             // The force kernel is launched BEFORE the host knows the decision: it returns at once if the (now global) rebuild
             // flag is set, and the flag travels to the host on a second stream meanwhile -- on the ~80 % of steps without a
             // rebuild the GPU never waits for the host round trip.
-            const bool speculate = v2_possible(h) && (h->force_variant == 0 || h->force_variant == 3 || h->force_variant == 6);
+            const bool speculate = v2_possible(h) && (h->force_variant == 0 || h->force_variant == 3 || h->force_variant == 5 || h->force_variant == 6);
             double *outp[3] = {h->g[0].p, h->g[1].p, h->g[2].p};
             if (speculate) {
                 if (fused)  // the decision word the speculative launch and the host read (see FLAG_DECISION)
@@ -2101,6 +2155,7 @@ int pisb_destroy(pisb_t *h) {
     dev_free(h, h->order);
     dev_free(h, h->nnbr);
     dev_free(h, h->nbr);
+    dev_free(h, h->pl_counts);
     dev_free(h, h->cell_count);
     dev_free(h, h->cell_start);
     dev_free(h, h->tile_sum);
@@ -2471,11 +2526,25 @@ int pisb_neighbours(pisb_t *h, int32_t *nnbr, int32_t *nbr, int64_t cap_per_atom
         TRY(ensure_list(h));
     }
     const int n = h->n;
-    std::vector<int> hn(n), hid(n), hl(nbr ? (size_t)h->kcap * h->npad : 0);  // the list itself only when rows are wanted
+    // per-atom rows [kcap][npad], or the three sections of the pair lists [3][kcap][npp] (+ counts): entry(s, k) reads either
+    const bool pairs = pair_mode(h);
+    const PairListArgs pl = pairs ? pair_list_args(h) : PairListArgs{};
+    const size_t list_words = pairs ? 3 * (size_t)h->kcap * (size_t)pl.npp : (size_t)h->kcap * h->npad;
+    std::vector<int> hn(n), hid(n), hl(nbr ? list_words : 0);  // the list itself only when rows are wanted
+    std::vector<int4> hc(nbr && pairs ? (size_t)pl.npp : 0);
     CUDA_TRY(h, cudaMemcpyAsync(hn.data(), h->nnbr.p, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(hid.data(), h->id.p, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
     if (nbr) CUDA_TRY(h, cudaMemcpyAsync(hl.data(), h->nbr.p, sizeof(int) * hl.size(), cudaMemcpyDeviceToHost, h->stream));
+    if (nbr && pairs) CUDA_TRY(h, cudaMemcpyAsync(hc.data(), h->pl_counts.p, sizeof(int4) * hc.size(), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    const size_t sec = (size_t)h->kcap * (size_t)pl.npp;
+    auto entry = [&](int s, int k) -> int {
+        if (!pairs) return hl[nbr_at(k, s, h->npad)];
+        const int p = s >> 1;
+        const int nb = hc[p].x;  // BOTH first, then the atom's own section
+        if (k < nb) return hl[plist_at(k, p, pl.npp)];
+        return hl[(s & 1 ? 2 : 1) * sec + plist_at(k - nb, p, pl.npp)];
+    };
     int64_t total = 0;
     if (h->multi) {
         // rows in owned-slot order (the order pisb_download_owned uses); entries are GLOBAL ids
@@ -2490,7 +2559,7 @@ int pisb_neighbours(pisb_t *h, int32_t *nnbr, int32_t *nbr, int64_t cap_per_atom
             total += hn[s];
             if (nbr) {
                 if (hn[s] > cap_per_atom) return fail(h, PISB_ERR_CAPACITY, "cap_per_atom too small");
-                for (int k = 0; k < hn[s]; ++k) nbr[(size_t)o * cap_per_atom + k] = hid[hl[nbr_at(k, s, h->npad)]];
+                for (int k = 0; k < hn[s]; ++k) nbr[(size_t)o * cap_per_atom + k] = hid[entry(s, k)];
             }
             ++o;
         }
@@ -2503,7 +2572,7 @@ int pisb_neighbours(pisb_t *h, int32_t *nnbr, int32_t *nbr, int64_t cap_per_atom
         total += hn[s];
         if (nbr) {
             if (hn[s] > cap_per_atom) return fail(h, PISB_ERR_CAPACITY, fmt("cap_per_atom %lld < list length %d", (long long)cap_per_atom, hn[s]));
-            for (int k = 0; k < hn[s]; ++k) nbr[(size_t)o * cap_per_atom + k] = hid[hl[nbr_at(k, s, h->npad)]];
+            for (int k = 0; k < hn[s]; ++k) nbr[(size_t)o * cap_per_atom + k] = hid[entry(s, k)];
         }
     }
     h->total_nbr = total;
@@ -2744,8 +2813,10 @@ int pisb_set_option(pisb_t *h, const char *name, double value) {
         h->fuse_vv = value != 0.0 ? 1 : 0;
         return PISB_OK;
     }
-    if (!std::strcmp(name, "force_variant")) {
-        h->force_variant = (int)value;
+    if (!std::strcmp(name, "force_variant") || !std::strcmp(name, "pair_lists")) {
+        if (name[0] == 'f') h->force_variant = (int)value;
+        else h->pair_lists = value != 0.0 ? 1 : 0;
+        h->list_valid = false;  // the list form (per-atom rows / pair sections) follows the force kernel
         return PISB_OK;
     }
     if (!std::strcmp(name, "build_variant") || !std::strcmp(name, "cell_div")) {

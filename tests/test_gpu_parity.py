@@ -18,7 +18,7 @@ def _jittered(ncell, jitter=0.15, temperature=30.0, seed=7):
     return fcc_argon(ncell, temperature=temperature, seed=seed, jitter=jitter)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10])
 @pytest.mark.parametrize("ncell,skin", [(10, 0.0), (10, SKIN), (16, SKIN)])
 def test_compute_potential_parity(ncell, skin, variant):
     atoms = _jittered(ncell)
@@ -54,7 +54,7 @@ def test_argon4000_lattice_known_answer():
     assert all(len(r) == 54 for r in rows)
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 6, 7])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 6, 7, 9, 10])
 @pytest.mark.parametrize("ncell,skin", [(8, 0.0), (8, SKIN), (12, SKIN)])
 def test_neighbour_list_exact(ncell, skin, variant):
     atoms = _jittered(ncell, jitter=0.3)
@@ -228,7 +228,7 @@ def test_edge_positions_on_boundary_and_beyond():
     assert force_rel_err(atoms.forces, f_ref).max() <= FORCE_TOL
 
 
-@pytest.mark.parametrize("variant", [0, 6, 8])
+@pytest.mark.parametrize("variant", [0, 6, 8, 9])
 def test_unwrapped_inputs_far_outside_the_box_and_a_box_centred_on_the_origin(variant):
     """Step-0 inputs need not lie in [0, L) (simulation.rs:28 calls compute_potential on them as read): atoms several
     box lengths out, and a whole system given in [-L/2, L/2).  The interior-warp shortcut of the force kernels uses raw
@@ -345,7 +345,7 @@ def test_guard_band_pairs_sit_on_the_cutoff():
     orc = make_oracle(atoms, table)
     start, nbr = orc.build_neighbour_list(atoms.positions, atoms.type_ids, extra=SKIN)
     pe_ref, f_ref = orc.compute_potential(atoms.positions, atoms.type_ids)
-    for variant in (6, 7, 4):
+    for variant in (6, 7, 4, 9):
         mgr = make_manager(skin=SKIN, variant=variant)
         mgr.attach(atoms)
         for a_, b_ in zip(mgr.neighbours(atoms.n_atoms), csr_rows_sorted(start, nbr)):
@@ -690,8 +690,8 @@ def test_cuda_graph_small_system_matches_oracle():
     assert np.max(np.abs(th["ke"] - ref[1:, 1]) / np.abs(ref[1:, 1])) <= ENERGY_TOL
 
 
-def _run_batches(atoms, fuse, graphs, batches, table=None, nvt_first=False):
-    mgr = make_manager(skin=SKIN, variant=6, table=table)      # force_variant 3: the fused step is selectable at any size
+def _run_batches(atoms, fuse, graphs, batches, table=None, nvt_first=False, variant=6):
+    mgr = make_manager(skin=SKIN, variant=variant, table=table)      # force_variant 3 / 5: the fused step is selectable at any size
     mgr.set_option("fuse_vv", fuse)
     mgr.set_option("cuda_graphs", graphs)
     mgr.attach(atoms)
@@ -706,8 +706,9 @@ def _run_batches(atoms, fuse, graphs, batches, table=None, nvt_first=False):
     return th, st
 
 
+@pytest.mark.parametrize("variant", [6, 9])
 @pytest.mark.parametrize("graphs", [1, 0])
-def test_fused_force_integrator_step_equals_separate_kernels(graphs):
+def test_fused_force_integrator_step_equals_separate_kernels(graphs, variant):
     """k_force_vv (force + kick + drift in one launch, positions double-buffered) against k_force_v3 + k_vv: the same
     arithmetic per atom, so positions / velocities / forces and the force kernel's reductions (PE, pair virial) are
     bit-identical across rebuilds, odd batch sizes and single steps; KE and tr(X F^T) are reduced over 128- instead of
@@ -715,8 +716,8 @@ def test_fused_force_integrator_step_equals_separate_kernels(graphs):
     batches = (64, 7, 1, 33, 46, 2, 3)
     a1 = fcc_argon(12, temperature=60.0, seed=5)
     a2 = fcc_argon(12, temperature=60.0, seed=5)
-    t1, s1 = _run_batches(a1, 1, graphs, batches)
-    t0, s0 = _run_batches(a2, 0, graphs, batches)
+    t1, s1 = _run_batches(a1, 1, graphs, batches, variant=variant)
+    t0, s0 = _run_batches(a2, 0, graphs, batches, variant=variant)
     assert np.array_equal(a1.positions, a2.positions)
     assert np.array_equal(a1.velocities, a2.velocities)
     assert np.array_equal(a1.forces, a2.forces)
@@ -767,7 +768,7 @@ def test_fused_step_trace_matches_oracle():
     assert np.abs(atoms.positions - x).max() < 1e-8
 
 
-@pytest.mark.parametrize("variant", [0, 6])
+@pytest.mark.parametrize("variant", [0, 6, 9])
 def test_pipelined_host_step_equals_whole_array_step(variant):
     """pisb_verlet_step_nve_host cuts the trait call's 3 x N host arrays into chunks and pipelines upload, drift and
     download (k_host_load_drift / k_store_range); option host_pipeline = 0 keeps the whole-array sequence.  Same
