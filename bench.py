@@ -110,21 +110,36 @@ def measure_pcie(host_array, reps: int = 4) -> dict:
     return out
 
 
-# FP64 pipe yardstick (the north_star's alternative to the HBM fraction).  Issue slots of the force loop per listed pair,
-# counted in the SASS of k_force_v3 / k_force_vv: 14 distance + 5 reciprocal + 11 LJ + 5 accumulate;
-# the fused kernel's epilogue adds ~110 per atom (6 IEEE divisions, kick, drift, wrap, skin trigger).  Peak: the measured
-# DFMA rate of tools/microbench.cu, 57.2 per clock and SM (profiles/r01_microbench_pipes.txt), 148 SMs at 1965 MHz.
-FP64_SLOTS_PER_PAIR = 35.0
+# FP64 yardsticks of the force loop (the resource that binds it; the HBM view is reported beside it).
+#  * ALGORITHMIC flops per atom-step (full list, div and sqrt counted as 1):
+#        21 per LISTED pair (difference 3, minimum image 12, r2 5, compare 1) + 18 per IN-RANGE pair + ~20 (integrator)
+#    -> 21 K + 18 K_in + 20.  K and K_in are measured on the run's own list (pisb_pairs_in_range).
+#  * ISSUED slots per listed pair of the lean loop, counted in the SASS: 6 distance + 4 Newton
+#    reciprocal + 6 LJ + 5 accumulate + 2 loop overhead = 23 (round 1: 35); a warp pays the in-range part whenever ANY of
+#    its lanes is in range, so issue is charged per listed pair.  The fused kernel's epilogue adds ~110 per atom.
+#  * Peak: the measured DFMA issue rate of tools/microbench.cu, 57.16 per clock and SM (profiles/r01_microbench_pipes.txt),
+#    148 SMs at 1965 MHz = 16.6 T instr/s, i.e. 33.2 TFLOP/s when every slot is a fused multiply-add.  (There is no
+#    driver-written FP64 peak in MEASURED_PEAKS.json.)
+FP64_SLOTS_PER_PAIR = 23.0
 FP64_SLOTS_EPILOGUE = 110.0
 FP64_PEAK_SLOTS_PER_S = 57.16 * 148 * 1.965e9
 
 
-def fp64_roofline(k_mean: float, n_atoms: int, ms_per_launch: float, fused: bool) -> dict:
+def fp64_roofline(kernel: str, k_mean: float, k_in: float, n_atoms: int, ms_per_launch: float, fused: bool) -> dict:
+    flops = 21.0 * k_mean + 18.0 * k_in + (20.0 if fused else 0.0)
     slots = FP64_SLOTS_PER_PAIR * k_mean + (FP64_SLOTS_EPILOGUE if fused else 0.0)
-    achieved = slots * n_atoms / (ms_per_launch * 1e-3)
-    return {"bound": "fp64 pipe", "slots_per_atom": slots, "achieved": achieved / 1e12, "peak": FP64_PEAK_SLOTS_PER_S / 1e12,
-            "unit": "T FP64 instr/s", "frac": achieved / FP64_PEAK_SLOTS_PER_S,
-            "peak_source": "measured DFMA rate (tools/microbench.cu), 57.2 per clock and SM"}
+    t = ms_per_launch * 1e-3
+    achieved = flops * n_atoms / t
+    return {"kernel": kernel, "bound": "fp64", "achieved": achieved / 1e12, "peak": 2.0 * FP64_PEAK_SLOTS_PER_S / 1e12, "unit": "TFLOP/s",
+            "frac": achieved / (2.0 * FP64_PEAK_SLOTS_PER_S),
+            "algorithmic_flops_per_atom": flops, "mean_neighbours_listed": k_mean, "mean_neighbours_in_range": k_in,
+            "frac_of_dfma_issue_rate": achieved / FP64_PEAK_SLOTS_PER_S,
+            "issued_fp64_slots_per_atom": slots, "issue_frac": slots * n_atoms / t / FP64_PEAK_SLOTS_PER_S,
+            "peak_source": "measured DFMA issue rate x 2 flop (tools/microbench.cu: 57.16 per clock and SM, 148 SMs, 1965 MHz)",
+            "ms_per_launch": ms_per_launch,
+            "note": "algorithmic flops = 21 K + 18 K_in + 20 (SURVEY 8d); frac = algorithmic flops / (2 x measured DFMA rate); "
+                    "frac_of_dfma_issue_rate = the same flops / the DFMA rate (one flop per slot); issue_frac = FP64 instructions "
+                    "the kernel issues (SASS count x listed pairs) / the DFMA rate = the pipe's utilisation"}
 
 
 def argon_oracle(atoms):
@@ -135,20 +150,34 @@ def argon_oracle(atoms):
     return orc
 
 
-def time_cpu_path(ncell: int, temperature: float, steps: int, warmup: int, threads: int, seed: int = 12345):
+def host_cores() -> int:
+    """Threads the CPU arm may use: the cores this process is allowed on.  NOT omp_get_max_threads(): torchrun exports
+    OMP_NUM_THREADS=1 to its workers, which silently made round 1's N > 1 reference arm a single-thread run."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def time_cpu_path(ncell: int, temperature: float, steps: int, warmup: int, threads: int, seed: int = 12345, budget_s: float = 0.0):
     """The reference's CPU path (oracle port, OpenMP all-core variant of the LJVOffsetManager loop) on an
-    FCC-argon system of ncell^3*4 atoms: returns (atom-steps/s, cores, seconds per step list)."""
+    FCC-argon system of ncell^3*4 atoms: returns (atom-steps/s, cores, seconds per step list).  budget_s > 0: the first
+    warm-up step is timed and, if (warmup + steps) of them would not fit the budget, None is returned instead (the caller
+    picks a smaller sample)."""
     from pis_b200.lattice import fcc_argon
 
     atoms = fcc_argon(ncell, temperature=temperature, seed=seed)
     orc = argon_oracle(atoms)
-    cores = threads if threads > 0 else orc.max_threads()
+    cores = threads if threads > 0 else host_cores()
     mode = "omp" if cores > 1 else "serial"
     x, v = atoms.positions.copy(), atoms.velocities.copy()
     f = np.zeros_like(x)
     orc.compute_potential(x, atoms.type_ids, forces=f, mode=mode, threads=cores)
-    for _ in range(warmup):
+    for w in range(warmup):
+        t0 = time.perf_counter()
         orc.verlet_step_nve(x, v, f, atoms.type_ids, DT, mode=mode, threads=cores)
+        if w == 0 and budget_s > 0.0 and (time.perf_counter() - t0) * (warmup + steps) > budget_s:
+            return None
     per = []
     for _ in range(steps):
         t0 = time.perf_counter()
@@ -159,25 +188,35 @@ def time_cpu_path(ncell: int, temperature: float, steps: int, warmup: int, threa
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation of the path.  The Rust reference cannot be
-    built here (no rustc), so this is the oracle port, with all host threads, each step a bounded sample
-    (a 256k-atom FCC-argon block: same lattice, density, cutoff and dt as the 4M workload)."""
+    """--impl reference: the reference's own CPU implementation of the path, on the box's host cores.  The Rust reference
+    cannot be built here (no rustc), so this is the oracle port (kind "port"), all host threads.  At N = 1 it runs the REAL
+    configuration it prints (4M atoms, K timed steps after W warm-up steps); the per-GPU block of the same lattice is the
+    bounded sample at N > 1 (atom-steps/s is intensive), and a 256k-atom block replaces either if K + W steps of it would
+    not end within a few minutes on this host -- the line says which was timed (`sample_atoms`, `cpu_baseline.sample`)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    ncell = args.ref_ncell
     t0 = time.perf_counter()
-    value, cores, per = time_cpu_path(ncell, args.temperature, args.steps, args.warmup, args.cpu_threads)
+    cfg = workload_config(args, args.gpus)
+    res, ncell = None, args.ncell
+    if args.ref_ncell <= 0:                      # automatic: the real per-GPU block unless it blows the time budget
+        res = time_cpu_path(ncell, args.temperature, args.steps, args.warmup, args.cpu_threads, budget_s=args.ref_budget_s)
+    if res is None:
+        ncell = args.ref_ncell if args.ref_ncell > 0 else 40
+        res = time_cpu_path(ncell, args.temperature, args.steps, args.warmup, args.cpu_threads)
+    value, cores, per = res
     n = 4 * ncell ** 3
     ms = 1e3 * sum(per) / len(per)
-    sample = (f"{n}-atom FCC argon block per step (same a=5.41, rc=2.5sigma, dt=0.25, T0={args.temperature}K as the "
-              f"{4 * args.ncell ** 3}-atom workload), OpenMP all-core variant of the LJVOffsetManager loop, "
-              f"{args.steps} timed steps")
+    whole = n == cfg["n_atoms"]
+    sample = ((f"the whole {n}-atom workload" if whole else
+               f"a {n}-atom FCC argon block of the {cfg['n_atoms']}-atom workload per step (same a=5.41, rc=2.5sigma, dt=0.25, "
+               f"T0={args.temperature}K)") +
+              f", OpenMP all-core variant of the LJVOffsetManager loop on {cores} threads, {args.steps} timed steps after {args.warmup}")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if args.strong else "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, args.gpus),
+        "config": cfg, "sample_atoms": n, "sample_is_whole_workload": whole,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
@@ -192,6 +231,48 @@ def workload_config(args, n_gpus: int) -> dict:
             "n_atoms": n_atoms, "rc": RC, "skin": SKIN, "dt": DT, "T0": args.temperature,
             "l2_policy": "working set (state + neighbour list, GBs) >> 126 MB L2; no explicit flush",
             "parallelism": "1 GPU" if n_gpus == 1 else f"spatial decomposition over {n_gpus} GPUs"}
+
+
+STRONG_FILE = os.path.join(ROOT, "gpurun_out", "strong_32M_n1.json")
+
+
+def strong_leg_single(args) -> dict:
+    """BASELINE configs[3] at N = 1: the 32M-atom system (200^3 FCC cells) on ONE GPU, device-resident NVE steps timed with
+    CUDA events on the library stream -- the denominator of the strong-scaling curve the N > 1 runs report."""
+    import torch
+
+    from pis_b200 import LennardJones, LJCudaManager
+    from pis_b200.lattice import fcc_argon
+
+    atoms = fcc_argon(args.ncell_multi, temperature=args.temperature, seed=12345)
+    n = atoms.n_atoms
+    mgr = LJCudaManager(skin=SKIN, device=0)
+    mgr.insert((1, 1), LennardJones(0.238, SIGMA, RC, True))
+    mgr.attach(atoms)
+    del atoms
+    mgr.compute()
+    stream = torch.cuda.ExternalStream(mgr.stream_ptr)
+    mgr.step_nve(DT, max(args.strong_warmup, 3))
+    mgr.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record(stream)
+    mgr.step_nve(DT, args.strong_steps)
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / args.strong_steps
+    st = mgr.stats()
+    mgr.close()
+    out = {"value": n / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": args.strong_steps, "warmup": max(args.strong_warmup, 3),
+           "n_atoms": n, "n_gpus": 1, "device_bytes": st["device_bytes"],
+           "workload": f"synthetic FCC argon {n} atoms ({args.ncell_multi}^3 cells), same potential / dt / T0: BASELINE configs[3] on 1 GPU"}
+    try:
+        os.makedirs(os.path.dirname(STRONG_FILE), exist_ok=True)
+        with open(STRONG_FILE, "w") as f:
+            json.dump(out, f)
+    except OSError:
+        pass
+    return out
 
 
 def run_single(args):
@@ -214,8 +295,10 @@ def run_single(args):
         name, _, val = kv.partition("=")
         options[name] = float(val)
         mgr.set_option(name, float(val))
-    fv = options.get("force_variant", 0.0)   # mirrors fused_step_possible() of pisb_sim.cu
-    fused = options.get("fuse_vv", 1.0) != 0.0 and (fv == 3.0 or (fv == 0.0 and n > 75000))
+    fv = options.get("force_variant", 0.0)   # mirrors pair_mode() / quad_mode() / fused_step_possible() of pisb_sim.cu
+    pair = options.get("pair_lists", 1.0) != 0.0 and fv == 5.0
+    quad = not pair and (fv == 7.0 or (fv == 0.0 and n > 75000))
+    fused = options.get("fuse_vv", 1.0) != 0.0 and (pair or quad or fv == 3.0)
     mgr.attach(atoms)
     mgr.compute()
     stream = torch.cuda.ExternalStream(mgr.stream_ptr)
@@ -253,41 +336,50 @@ def run_single(args):
     mgr.set_profiling(False)
     st2 = mgr.stats()
 
-    # ---- roofline of the dominant kernel.  Algorithmic bytes per atom: LJ force 48 + 4K; the fused step
-    #      kernel k_force_vv adds the integrator's streams: kick 72 (v read + write, F(t) read) and, on every launch but
-    #      the last of a batch, drift 72 (x_build read, x + FP32 shadow write) -> 192 + 4K ----
+    # ---- roofline of the dominant kernel (one launch per step: LJ force pass + velocity-Verlet kick + drift).
+    #      It is bound by the FP64 pipe (ncu: profiles/), so the primary `roofline` is the FP64 one; the HBM view
+    #      (algorithmic bytes / measured copy peak) is reported beside it as `roofline_hbm`.
+    #      Algorithmic bytes per atom: LJ force 48 + 4K for a full list of K 4-byte indices; the fused step
+    #      kernel adds the integrator's streams: kick 72 (v read + write, F(t) read) and, on every launch but the last of a
+    #      batch, drift 72 (x_build read, x + FP32 shadow write) -> 192 + 4K.  The pair-list kernel reads FEWER index
+    #      words than 4K (two atoms share the entries of their common neighbours): `index_words_per_atom` says how many. ----
     peaks, peak_kind = measured_peaks()
-    nn = np.zeros(n, dtype=np.int32)
-    capi.check(mgr._h, capi.load().pisb_neighbours(mgr._h, capi._ptr(nn), None, 0))
-    k_mean = float(nn.mean())
+    ls = mgr.list_stats()
+    k_mean, k_in, words = ls["listed"] / n, ls["in_range"] / n, ls["index_words"] / n
     f_ms = tim["force"]["ms"] / max(tim["force"]["launches"], 1)
     force_launches = max(tim["force"]["launches"], 1)
     drift_frac = max(force_launches - 1, 0) / force_launches      # the profiled pass is one batch: its last launch does not drift
     per_atom = 48.0 + 4.0 * k_mean + ((72.0 + 72.0 * drift_frac) if fused else 0.0)
+    per_atom_stored = per_atom - 4.0 * k_mean + 4.0 * words
     bytes_per_launch = per_atom * n
-    kernel_name = "k_force_vv" if fused else "k_force_v3"
+    kernel_name = (("k_pforce" if pair else "k_force_q" if quad else "k_force_vv") + "<fused>") if fused else ("k_pforce" if pair else "k_force_q" if quad else "k_force_v3")
     achieved = bytes_per_launch / (f_ms * 1e-3) / 1e9
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    traffic, fp64_pct = None, None
+    traffic, fp64_pct, traffic_src = None, None, None
     tp = os.path.join(ROOT, "profiles", "force_traffic.json")
     if os.path.exists(tp):
         try:
             with open(tp) as f:
                 tj = json.load(f)
-            if str(tj.get("kernel", "")).startswith(kernel_name):    # a capture of another kernel says nothing about this one
+            if str(tj.get("kernel", "")).startswith(kernel_name.split("<")[0]):    # a capture of another kernel says nothing about this one
                 traffic, fp64_pct = tj.get("dram_bytes_per_launch"), tj.get("fp64_pipe_active_pct")
+                traffic_src = f"static ncu --set full capture {tj.get('source', 'profiles/force_traffic.json')} ({tj.get('commit', 'commit n/a')}); not re-measured in this run"
         except Exception:
             traffic = None
-    roofline = {"kernel": kernel_name, "bound": "hbm", "timing": "per-launch CUDA events over the K steps that follow the timed "
-                "region (same state, same kernels; ms_per_step_profiled beside ms_per_step)",
-                "algorithmic_bytes_per_launch": bytes_per_launch,
-                "fp64_pipe_active_pct_ncu": fp64_pct, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_kind,
-                "algorithmic_bytes_per_atom": per_atom, "mean_neighbours": k_mean,
-                "ms_per_launch": f_ms, "share_of_step": tim["force"]["ms"] / ms_profiled,
-                "note": ("one launch per step: LJ force pass with the velocity-Verlet kick + drift in its epilogue; " if fused else "") +
-                        "the force pass is bound by the FP64 pipe and L1TEX gather throughput, not by HBM (ncu: profiles/); "
-                        "frac is algorithmic HBM bytes / measured copy peak; traffic = ncu dram bytes per launch"}
+    timing_note = ("per-launch CUDA events over the K steps that follow the timed region (same state, same kernels; "
+                   "ms_per_step_profiled beside ms_per_step)")
+    roofline = fp64_roofline(kernel_name, k_mean, k_in, n, f_ms, fused)
+    roofline.update({"timing": timing_note, "share_of_step": tim["force"]["ms"] / ms_profiled, "traffic": traffic,
+                     "traffic_source": traffic_src, "fp64_pipe_active_pct_ncu": fp64_pct})
+    roofline_hbm = {"kernel": kernel_name, "bound": "hbm", "timing": timing_note,
+                    "algorithmic_bytes_per_launch": bytes_per_launch, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_kind,
+                    "algorithmic_bytes_per_atom": per_atom, "index_words_per_atom": words,
+                    "bytes_per_atom_with_the_stored_list": per_atom_stored,
+                    "frac_with_the_stored_list": per_atom_stored * n / (f_ms * 1e-3) / 1e9 / peak,
+                    "mean_neighbours": k_mean, "ms_per_launch": f_ms,
+                    "note": "not the binding resource: the force pass is bound by the FP64 pipe and the L1TEX gather path (ncu: "
+                            "profiles/); frac = algorithmic HBM bytes (SURVEY 8d, full list) / measured copy peak"}
     kernel_ms = {k: round(v["ms"] / args.steps, 5) for k, v in tim.items() if v["launches"]}
     # the streaming kernel next to it: k_vv<kick,drift> moves 200 B/atom per step; with the fused
     # step kernel only the drift that opens a batch is left (x 32 + v 24 + F 24 + x_build 24 read, x 32 + shadow 16 written)
@@ -352,11 +444,11 @@ def run_single(args):
     # ---- CPU baseline: oracle port on a bounded sample ----
     cpu = None
     if not args.no_cpu_baseline:
-        cvalue, cores, per = time_cpu_path(args.ref_ncell, args.temperature, args.cpu_steps, 1, args.cpu_threads)
+        cvalue, cores, per = time_cpu_path(args.cpu_ncell, args.temperature, args.cpu_steps, 1, args.cpu_threads)
         svalue, _, sper = time_cpu_path(args.ref_ncell_serial, args.temperature, 10, 1, 1)
         cpu = {"value": cvalue, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{4 * args.ref_ncell ** 3}-atom FCC argon block, {args.cpu_steps} steps, OpenMP all-core variant "
-                         f"({sum(per):.1f} s)",
+               "sample": f"{4 * args.cpu_ncell ** 3}-atom FCC argon block of the workload (same lattice, cutoff, dt, T0), {args.cpu_steps} steps, "
+                         f"OpenMP all-core variant on {cores} threads ({sum(per):.1f} s)",
                "serial_value": svalue, "serial_sample": f"{4 * args.ref_ncell_serial ** 3} atoms, 10 steps, 1 thread ({sum(sper):.1f} s) "
                                                         f"(what the reference actually executes)"}
 
@@ -366,7 +458,7 @@ def run_single(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": workload_config(args, 1), "clocks": clk.summary(), "e2e": e2e,
         "e2e_resident": e2e_resident,
-        "gpu_launches": int(launches), "roofline": roofline, "roofline_fp64": fp64_roofline(k_mean, n, f_ms, fused),
+        "gpu_launches": int(launches), "roofline": roofline, "roofline_hbm": roofline_hbm,
         "roofline_integrate": roofline_integrate, "cpu_baseline": cpu,
         "kernel_ms_per_step": kernel_ms, "ms_per_step_profiled": ms_profiled / args.steps,
         "list_builds_in_timed_region": int(builds), "list_builds_in_profiled_pass": int(st2["n_builds"] - st1["n_builds"]),
@@ -375,8 +467,15 @@ def run_single(args):
         "energy_drift_rel": float(np.abs(h - h[0]).max() / abs(h[0])),
         "stats": st1, "wall_s": time.perf_counter() - t_wall0,
     }
-    print(json.dumps(line), flush=True)
     mgr.close()
+    del atoms
+    if not args.no_strong:
+        try:
+            line["strong_32M"] = strong_leg_single(args)
+        except Exception as e:  # the headline line must not be lost to the extra leg
+            line["strong_32M"] = {"error": repr(e)[:300]}
+        line["wall_s"] = time.perf_counter() - t_wall0
+    print(json.dumps(line), flush=True)
 
 
 def main():
@@ -388,14 +487,20 @@ def main():
     ap.add_argument("--ncell", type=int, default=100, help="FCC cells per edge at N=1 (100 -> 4M atoms)")
     ap.add_argument("--ncell-multi", type=int, default=200, help="FCC cells per edge at N>1 (200 -> 32M atoms)")
     ap.add_argument("--temperature", type=float, default=43.0, help="initial temperature (K); 43 K exercises rebuilds")
-    ap.add_argument("--ref-ncell", type=int, default=40, help="CPU sample size (40 -> 256k atoms)")
+    ap.add_argument("--ref-ncell", type=int, default=0, help="--impl reference: FCC cells per edge of the CPU sample; 0 = the real per-GPU block (--ncell)")
+    ap.add_argument("--ref-budget-s", type=float, default=300.0, help="--impl reference: fall back to a 256k-atom block if K + W real-size steps would take longer")
+    ap.add_argument("--cpu-ncell", type=int, default=40, help="cpu_baseline leg of the GPU arm: CPU sample size (40 -> 256k atoms)")
     ap.add_argument("--ref-ncell-serial", type=int, default=20)
     ap.add_argument("--cpu-steps", type=int, default=40, help="CPU-baseline sample: steps of the ref-ncell block (~10 s on 16 cores)")
     ap.add_argument("--cpu-threads", type=int, default=0)
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--option", action="append", default=[], help="library option name=value (pisb_set_option), repeatable")
-    ap.add_argument("--strong", action="store_true", help="N>1: run the 32M-atom system instead of 4M atoms per GPU")
+    ap.add_argument("--strong", action="store_true", help="N>1: make the 32M-atom system the PRIMARY leg instead of 4M atoms per GPU")
+    ap.add_argument("--no-strong", action="store_true", help="skip the second, separately timed 32M-atom leg (`strong_32M`)")
+    ap.add_argument("--strong-steps", type=int, default=10)
+    ap.add_argument("--strong-warmup", type=int, default=3)
+    ap.add_argument("--no-multi-parity", action="store_true", help="N>1: skip the multi-GPU == single-GPU check that precedes the timed region")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

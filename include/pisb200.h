@@ -245,6 +245,12 @@ PISB_API int pisb_download_owned(pisb_t *h, int64_t cap, double *pos, double *ve
  * multi-GPU mode (where list entries are global ids). */
 PISB_API int pisb_owned_ids(pisb_t *h, int64_t cap, int32_t *global_ids, int64_t *n_out);
 
+/* What the current Verlet list holds (built first if need be), counted on the device: out3[0] = listed pairs (sum of the
+ * per-atom row lengths, each pair twice: a full list), out3[1] = of those, pairs inside the cutoff at the current
+ * positions (`rij.norm() > rcut -> skip`, lennard_jones.rs:224), out3[2] = index words stored (the pair lists of large
+ * systems store the common neighbours of two atoms once).  Multi-GPU: this rank's owned atoms. */
+PISB_API int pisb_list_stats(pisb_t *h, int64_t *out3);
+
 /* Options (all have working defaults; the kernel selectors exist for A/B measurements and the parity tests):
  *   list_capacity     neighbour slots per atom, 0 = automatic (estimated from the density, grown on overflow)
  *   cuda_graphs       1 (default) = NVE / NVT batches replay CUDA graphs of 8 / 4 / 2 steps, 0 = classic launches

@@ -77,6 +77,7 @@ SIGNATURES = {
     "pisb_verlet_step_nve_host": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp, C.c_double, _dp]),
     "pisb_neighbours": (C.c_int, [_vp, _vp, _vp, C.c_int64]),
     "pisb_invalidate_list": (C.c_int, [_vp]),
+    "pisb_list_stats": (C.c_int, [_vp, _vp]),
     "pisb_stats": (C.c_int, [_vp, C.POINTER(Stats)]),
     "pisb_set_profiling": (C.c_int, [_vp, C.c_int]),
     "pisb_timings": (C.c_int, [_vp, _vp, _vp]),

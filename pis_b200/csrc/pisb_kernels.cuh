@@ -1462,6 +1462,201 @@ __global__ void __launch_bounds__(TPB_FORCE) k_force_split(Force2Args a) {
     });
 }
 
+// ------------------------------------------------------------------------------------------------
+// k_force_q<MULTI, FUSED, DRIFT, BRICK>: FOUR LANES PER ATOM, lane l takes entry l of every K-tile.
+//
+// What binds the thread-per-atom loop after the FP64 diet is the L1TEX data pipe: one wavefront per distinct 128-byte
+// line a gather instruction touches, and the k-th neighbours of 32 DIFFERENT atoms share few lines (ncu r01: ~25 lines per
+// instruction, LSU data pipe 90 %).  The four entries of one K-tile of ONE atom, though, are consecutive acceptances of the
+// build's slot-order scan, i.e. mostly adjacent slots of one cell run: 4 records = 1-2 lines.  With four lanes per atom a
+// gather instruction covers the tiles of 8 atoms and touches ~17 lines instead of ~25 for the same 32 pairs (counted on
+// real lists, tools/sim_lanes.py: 31 wavefronts per atom against 58; 8 lanes per atom: 30, 2 lanes: 39, two atoms per
+// thread with shared entries: 48) -- the same pair evaluations, the same lists, the same arithmetic, ~half the L1 traffic.
+// The tile layout [K/4][npad][4] is unchanged: the group's index load is one 16-byte tile.
+// Four tiles per iteration keep four independent gathers in flight per lane; the next iteration's indices are loaded
+// before the current gathers are consumed.  The 4 partial sums of an atom meet in an xor butterfly (fixed order, identical
+// on all four lanes); then lane c < 3 owns COMPONENT c for the store and for the integrator epilogue
+// (potential.rs:16-30: kick, KE, tr(X F^T), drift, wrap, skin trigger -- same operations as k_vv, spread over the lanes).
+// ------------------------------------------------------------------------------------------------
+constexpr int TPB_Q = 256;  // 64 atoms per block
+
+__device__ __forceinline__ int ldg_stream_i32(const int *p) {
+    int v;
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
+template <bool MULTI, bool IMAGE>
+__device__ __forceinline__ void force_q_body(const Force2Args &a, int i, int l, int nn, LeanAcc<MULTI> &acc, bool &ambiguous) {
+    const double4 xi = a.xt[i];  // one address for the four lanes of the group
+    const int ti = MULTI ? type_of(xi.w) : 1;
+    const int *row = a.nbr + (size_t)i * 4 + l;  // entry 4t + l sits in tile t
+    const size_t tstride = (size_t)a.npad * 4;
+    int jn[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) jn[u] = 4 * u + l < nn ? ldg_stream_i32(row + (size_t)u * tstride) : -1;
+    for (int t = 0; 4 * t < nn; t += 4) {
+        int j[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) j[u] = jn[u];
+        if (4 * (t + 4) < nn) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) jn[u] = 4 * (t + 4 + u) + l < nn ? ldg_stream_i32(row + (size_t)(t + 4 + u) * tstride) : -1;
+        }
+        double4 xj[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) xj[u] = ldg_d4(&a.xt[max(j[u], 0)]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            double dx, dy, dz;
+            const double r2 = lean_disp<IMAGE>(a.box, xi, xj[u], dx, dy, dz);
+            PairDev p = a.pair0;
+            bool in = j[u] >= 0;
+            if (MULTI) {
+                const int tj = type_of(xj[u].w);
+                p = a.table[(min(ti, tj) - 1) * a.n_types + (max(ti, tj) - 1)];
+                in = in && p.present;
+            }
+            if (in) {
+                if (le_bits(r2, p.t_lo)) acc.pair(p, dx, dy, dz, r2);
+                else ambiguous |= le_bits(r2, p.t_hi);
+            }
+        }
+    }
+}
+
+template <bool MULTI, bool FUSED, bool DRIFT, bool BRICK>
+__global__ void __launch_bounds__(TPB_Q, 4) k_force_q(ForceVVArgs b) {
+    const Force2Args &a = b.f;
+    if (BRICK && a.skip_flag && *a.skip_flag != 0) return;  // speculative launch, a rebuild comes first
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = gt >> 2, l = gt & 3;
+    double red[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};  // pe, pair virial, ke, x*fx, y*fy, z*fz
+    if (FUSED && DRIFT && gt == 0) b.flags[b.unwrapped_out] = 0;
+    bool active = i < a.n;
+    bool interior = *a.unwrapped == 0;
+    if (active) {
+        const float4 xfi = a.xf[i];
+        if (BRICK && xf_is_ghost(xfi)) active = false;
+        else interior = interior && is_interior(a.boxf, xfi);
+    }
+    const bool warp_interior = __all_sync(0xffffffffu, interior);
+    LeanAcc<MULTI> acc;
+    bool ambiguous = false;
+    const int nn = active ? a.nnbr[i] : 0;
+    if (active) {
+        if (warp_interior) force_q_body<MULTI, false>(a, i, l, nn, acc, ambiguous);
+        else force_q_body<MULTI, true>(a, i, l, nn, acc, ambiguous);
+    }
+    double fx, fy, fz, pe, vir;
+    acc.finish(a.pair0, fx, fy, fz, pe, vir);
+    // a guard-band pair anywhere in the row (one in ~10^11): the four lanes redo their shares (whole tiles l, l+4, ...)
+    // with the reference-order predicate; out of line, after the loop
+    ambiguous = __shfl_xor_sync(0xffffffffu, (int)ambiguous, 1) | (int)ambiguous;
+    ambiguous = __shfl_xor_sync(0xffffffffu, (int)ambiguous, 2) | (int)ambiguous;
+    if (ambiguous && active) {
+        double o[5];
+        if (warp_interior) force_atom_exact<MULTI, false>(a.xt, a.nbr, a.npad, i, nn, l, 4, a.box, a.pair0, a.table, a.n_types, o);
+        else force_atom_exact<MULTI, true>(a.xt, a.nbr, a.npad, i, nn, l, 4, a.box, a.pair0, a.table, a.n_types, o);
+        fx = o[0], fy = o[1], fz = o[2], pe = o[3], vir = o[4];
+    }
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1) {
+        fx += __shfl_xor_sync(0xffffffffu, fx, o);
+        fy += __shfl_xor_sync(0xffffffffu, fy, o);
+        fz += __shfl_xor_sync(0xffffffffu, fz, o);
+        pe += __shfl_xor_sync(0xffffffffu, pe, o);
+        vir += __shfl_xor_sync(0xffffffffu, vir, o);
+    }
+    // lane c < 3 owns component c from here on
+    const int c = l;
+    double fc = c == 0 ? fx : (c == 1 ? fy : fz);
+    if (active) {
+        if (l == 0) {
+            red[0] = pe;
+            red[1] = vir;
+        }
+        if (c < 3) {
+            double *const fout = c == 0 ? a.fx : (c == 1 ? a.fy : a.fz);
+            if (!FUSED && a.ax) fc += (c == 0 ? a.ax : (c == 1 ? a.ay : a.az))[i];
+            fout[i] = fc;
+        }
+    }
+    if (FUSED) {
+        // ---- integrator epilogue, one component per lane (lane 3 carries the type word of the position record) ----
+        double xc = 0.0, vc = 0.0, v2 = 0.0, d2 = 0.0;
+        const double4 x4 = active ? a.xt[i] : make_double4(0.0, 0.0, 0.0, 0.0);
+        if (active && c < 3) {
+            xc = c == 0 ? x4.x : (c == 1 ? x4.y : x4.z);
+            double *const vp = c == 0 ? b.vx : (c == 1 ? b.vy : b.vz);
+            const double gc = (c == 0 ? b.gx : (c == 1 ? b.gy : b.gz))[i];
+            vc = vp[i];
+            const double m = b.mass[type_of(x4.w) - 1];
+            const double ac = __ddiv_rn(fc, m), oc = __ddiv_rn(gc, m);
+            vc = __dadd_rn(vc, __dmul_rn(__dmul_rn(__dadd_rn(oc, ac), 0.5), b.dt));
+            vp[i] = vc;
+            v2 = __dmul_rn(vc, vc);
+            red[3 + c] = __dmul_rn(xc, fc);
+            if (DRIFT) {
+                double bc = 0.0;
+                if (!b.always_rebuild) bc = (c == 0 ? b.xbx : (c == 1 ? b.xby : b.xbz))[i];
+                xc = __dadd_rn(xc, __dadd_rn(__dmul_rn(vc, b.dt), __dmul_rn(__dmul_rn(ac, 0.5), b.dt2)));
+                // wrap (simulation_box.rs:29-42, orthorhombic): s = h_inv x; s -= floor(s); x = h s
+                const double hc = a.box.h[4 * c], ic = a.box.hinv[4 * c];
+                double sc = __dmul_rn(ic, xc);
+                sc = __dsub_rn(sc, floor(sc));
+                xc = __dmul_rn(hc, sc);
+                // skin trigger: minimum image of x - x_build (simulation_box.rs:17-27), squared
+                double dc = xc - bc;
+                double sd = __dmul_rn(ic, dc);
+                sd = __dsub_rn(sd, round(sd));
+                dc = __dmul_rn(hc, sd);
+                d2 = __dmul_rn(dc, dc);
+            }
+        }
+        // KE = 0.5 m ((vx^2 + vy^2) + vz^2) and |d|^2 = (dx^2 + dy^2) + dz^2 in the reference's association, on lane 0
+        const unsigned full = 0xffffffffu;
+        const int base = threadIdx.x & 28;  // lane 0 of this group within the warp
+        const double v2y = __shfl_sync(full, v2, base + 1), v2z = __shfl_sync(full, v2, base + 2);
+        const double d2y = __shfl_sync(full, d2, base + 1), d2z = __shfl_sync(full, d2, base + 2);
+        if (active && l == 0) {
+            const double m = b.mass[type_of(x4.w) - 1];
+            red[2] = __dmul_rn(__dmul_rn(0.5, m), __dadd_rn(__dadd_rn(v2, v2y), v2z));
+            if (DRIFT) {
+                if (b.always_rebuild) {
+                    if (i == 0) b.flags[FLAG_REBUILD] = 1;
+                } else if (!(__dadd_rn(__dadd_rn(d2, d2y), d2z) <= b.half_skin2)) {
+                    b.flags[FLAG_REBUILD] = 1;
+                }
+            }
+        }
+        if (DRIFT && active) {
+            // position record {x, y, z, type bits} and its FP32 shadow: one 8-byte / 4-byte word per lane, 32 / 16 contiguous bytes per atom
+            double *const xo = reinterpret_cast<double *>(b.xt_out + i);
+            float *const fo = reinterpret_cast<float *>(b.xf_out + i);
+            xo[c] = c < 3 ? xc : x4.w;
+            fo[c] = c < 3 ? (float)xc : __int_as_float(type_of(x4.w));
+        }
+    }
+    pisb_thermo *th = a.thermo;
+    if (FUSED) {
+        double t3[3];
+        block_reduce_finalize<6, TPB_Q>(red, a.partials, a.ticket, [&](int q, double s) {
+            if (q == 0) th->pe = s / 2.0;
+            else if (q == 1) th->virial_pair = s / 2.0;
+            else if (q == 2) th->ke = s;
+            else t3[q - 3] = s;
+            if (q == 5) th->virial_ref = (t3[0] + t3[1]) + t3[2];
+        });
+    } else {
+        double r2[2] = {red[0], red[1]};
+        block_reduce_finalize<2, TPB_Q>(r2, a.partials, a.ticket, [&](int q, double s) {
+            if (q == 0) th->pe = s / 2.0;
+            else th->virial_pair = s / 2.0;
+        });
+    }
+}
+
 template <bool MULTI>
 __global__ void __launch_bounds__(TPB_FORCE) k_force_v2(Force2Args a) {
     __shared__ int s_q[QCAP][TPB_FORCE];

@@ -449,4 +449,62 @@ __global__ void __launch_bounds__(TPB_FORCE, 5) k_pforce(ForceVVArgs b, PairList
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// pisb_list_stats: what the CURRENT list holds, counted on the device from whichever list form is in use --
+// listed pairs (sum of the per-atom row lengths), pairs inside the cutoff right now (the reference predicate), index
+// words stored (pair lists store the common neighbours of two atoms once).  bench.py's roofline needs K and K_in.
+// ------------------------------------------------------------------------------------------------
+struct ListStatsArgs {
+    int n, npad, pairs;
+    const double4 *xt;
+    const int *nbr, *nnbr;
+    PairListArgs pl;
+    BoxDev box;
+    PairDev pair0;
+    const PairDev *table;
+    int n_types;
+    unsigned long long *out;  // [0] listed, [1] in range, [2] index words
+};
+
+template <bool ORTHO>
+__global__ void __launch_bounds__(TPB) k_list_stats(ListStatsArgs a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long listed = 0, inr = 0, words = 0;
+    if (i < a.n && !is_ghost(a.xt[i].w)) {
+        const double4 xi = a.xt[i];
+        const int ti = type_of(xi.w);
+        const int nn = a.nnbr[i];
+        const int p = i >> 1;
+        const int4 c = a.pairs ? a.pl.counts[p] : make_int4(0, 0, 0, 0);
+        listed = (unsigned long long)nn;
+        // an atom's share of the stored words: its own section + BOTH once per pair thread (charged to the even slot, or to
+        // the odd one when the even slot is a ghost and lists nothing)
+        if (a.pairs) words = (unsigned long long)((i & 1) ? c.z : c.y) + (((i & 1) == 0 || is_ghost(a.xt[i - 1].w)) ? (unsigned long long)c.x : 0ull);
+        else words = (unsigned long long)nn;
+        for (int k = 0; k < nn; ++k) {
+            int j;
+            if (!a.pairs) j = a.nbr[nbr_at(k, i, a.npad)];
+            else if (k < c.x) j = a.pl.both[plist_at(k, p, a.pl.npp)];
+            else j = ((i & 1) ? a.pl.only_b : a.pl.only_a)[plist_at(k - c.x, p, a.pl.npp)];
+            const double4 xj = ldg_d4(&a.xt[j]);
+            double dx = __dsub_rn(xj.x, xi.x), dy = __dsub_rn(xj.y, xi.y), dz = __dsub_rn(xj.z, xi.z);
+            min_image<ORTHO>(a.box, dx, dy, dz);
+            const int tj = type_of(xj.w);
+            const PairDev pd = a.n_types > 1 ? a.table[(min(ti, tj) - 1) * a.n_types + (max(ti, tj) - 1)] : a.pair0;
+            if (pd.present && !(norm2(dx, dy, dz) > pd.t_rc)) ++inr;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        listed += __shfl_down_sync(0xffffffffu, listed, o);
+        inr += __shfl_down_sync(0xffffffffu, inr, o);
+        words += __shfl_down_sync(0xffffffffu, words, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&a.out[0], listed);
+        atomicAdd(&a.out[1], inr);
+        atomicAdd(&a.out[2], words);
+    }
+}
+
 }  // namespace pisb

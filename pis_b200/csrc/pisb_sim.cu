@@ -332,12 +332,17 @@ bool v2_possible(const pisb_t *h) {
     return h->have_box && h->box.ortho && h->box.pbc[0] && h->box.pbc[1] && h->box.pbc[2];
 }
 
-// Large single-type systems in an orthorhombic periodic box step with two atoms per thread (pisb_pairlist.cuh);
-// force_variant 5 forces that path at any size (tests).
+// force_variant 5: two atoms per thread with a three-section pair list (pisb_pairlist.cuh).  Measured SLOWER than the
+// per-atom list at 4M atoms (1.55 ms per step kernel launch): kept selectable for the A/B record and its tests, never automatic.
 bool pair_mode(const pisb_t *h) {
     if (!v2_possible(h) || h->n_types != 1 || !h->pair_lists) return false;
     if (!(h->build_variant == 0 || h->build_variant == 3)) return false;
-    return h->force_variant == 5 || (h->force_variant == 0 && h->n > 75000);
+    return h->force_variant == 5;
+}
+
+// Systems large enough to fill the GPU (and force_variant 7 at any size) run k_force_q: four lanes per atom on the per-atom list.
+bool quad_mode(const pisb_t *h) {
+    return v2_possible(h) && !pair_mode(h) && (h->force_variant == 7 || (h->force_variant == 0 && h->n > 75000));
 }
 
 int pair_threads_padded(const pisb_t *h) { return ((h->npad + 1) / 2 + 31) / 32 * 32; }
@@ -542,8 +547,9 @@ int reserve_atoms(pisb_t *h, int n) {
     // quantities, 8 lanes per atom below 75k atoms)
     auto need = [](size_t nq, size_t blocks) { return nq * (blocks + red_groups((unsigned int)blocks) + 2); };
     const size_t b_force = (size_t)nblk(n, TPB_FORCE), b_stream = (size_t)nblk(n, TPB), b_split = (size_t)nblk(std::min(n, 75000) * 8, TPB_FORCE);
-    TRY(dev_reserve(h, h->partials, std::max(need(6, b_force), std::max(need(19, b_stream), need(2, b_split)))));
-    const size_t tickets = 2 + red_groups((unsigned int)std::max(b_force, b_split));
+    const size_t b_quad = ((size_t)n * 4 + TPB_Q - 1) / TPB_Q;  // k_force_q: four lanes per atom, 6 quantities
+    TRY(dev_reserve(h, h->partials, std::max(std::max(need(6, b_force), need(6, b_quad)), std::max(need(19, b_stream), need(2, b_split)))));
+    const size_t tickets = 2 + red_groups((unsigned int)std::max(std::max(b_force, b_quad), b_split));
     if (tickets > h->ticket_cap) {
         // zero-initialised once; the words reset themselves at the end of every reduction
         CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -673,6 +679,20 @@ int launch_force(pisb_t *h, double *const out[3], const double *const acc[3], pi
             else k_pforce<false, false, false><<<nbp, TPB_FORCE, 0, st>>>(fv, pair_list_args(h));
             return check_launch(h, "k_pforce");
         }
+        if (quad_mode(h)) {  // four lanes per atom
+            ForceVVArgs fv{};
+            fv.f = f2;
+            fv.flags = h->flags;
+            const unsigned nbq = (unsigned)(((size_t)h->n * 4 + TPB_Q - 1) / TPB_Q);
+            if (multi) {
+                if (h->multi) k_force_q<true, false, false, true><<<nbq, TPB_Q, 0, st>>>(fv);
+                else k_force_q<true, false, false, false><<<nbq, TPB_Q, 0, st>>>(fv);
+            } else {
+                if (h->multi) k_force_q<false, false, false, true><<<nbq, TPB_Q, 0, st>>>(fv);
+                else k_force_q<false, false, false, false><<<nbq, TPB_Q, 0, st>>>(fv);
+            }
+            return check_launch(h, "k_force_q");
+        }
         // only the default kernels honour skip_flag
         if (skip_flag && h->force_variant != 0 && h->force_variant != 3 && h->force_variant != 6)
             return fail(h, PISB_ERR_STATE, "speculative force launch needs force_variant 0, 3, 5 or 6");
@@ -748,8 +768,8 @@ int launch_vv(pisb_t *h, bool kick, bool drift, double dt, pisb_thermo *rec, con
 // atom) run one k_force_vv launch per step instead of k_force_v3 + k_vv.
 bool fused_step_possible(const pisb_t *h, bool multi_path = false) {
     if (!h->fuse_vv || h->multi != multi_path || !v2_possible(h)) return false;
-    if (pair_mode(h)) return true;
-    return (h->force_variant == 0 || h->force_variant == 3) && (h->force_variant == 3 || h->n > 75000);
+    if (pair_mode(h) || quad_mode(h)) return true;
+    return h->force_variant == 3;
 }
 
 // F(t+dt) -> g, kick with F(t) = f, [drift into the other position buffer], then f <-> g (and the position buffers).
@@ -778,6 +798,21 @@ int launch_force_vv(pisb_t *h, bool drift, double dt, pisb_thermo *rec, const in
                 if (h->multi) k_pforce<true, false, true><<<nbp, TPB_FORCE, 0, st>>>(fv, pl);
                 else k_pforce<true, false, false><<<nbp, TPB_FORCE, 0, st>>>(fv, pl);
             }
+        } else if (quad_mode(h)) {
+            const unsigned nbq = (unsigned)(((size_t)h->n * 4 + TPB_Q - 1) / TPB_Q);
+#define FQ(T, D)                                                                  \
+    do {                                                                          \
+        if (h->multi) k_force_q<T, true, D, true><<<nbq, TPB_Q, 0, st>>>(fv);     \
+        else k_force_q<T, true, D, false><<<nbq, TPB_Q, 0, st>>>(fv);             \
+    } while (0)
+            if (drift) {
+                if (multi) FQ(true, true);
+                else FQ(false, true);
+            } else {
+                if (multi) FQ(true, false);
+                else FQ(false, false);
+            }
+#undef FQ
         } else {
 #define FVV(T, D)                                                              \
     do {                                                                       \
@@ -1081,7 +1116,7 @@ void graph_signature(pisb_t *h, double dt, std::vector<unsigned char> &sig) {
                           h->nhc_energy_d.p};
     put(ptrs, sizeof ptrs);
     const int ints[] = {h->n, h->npad, h->kcap, h->n_types, h->force_variant, h->build_variant, h->cell_div, h->fuse_vv, h->pair_lists,
-                        pair_mode(h) ? 1 : 0};
+                        pair_mode(h) ? 1 : 0, quad_mode(h) ? 1 : 0};
     put(&h->pl_counts.p, sizeof(void *));
     put(ints, sizeof ints);
     const double dbl[] = {dt, h->skin, h->skin_half2_override, h->max_rcut};
@@ -1999,7 +2034,8 @@ int do_step_nve_multi(pisb_t *h, double dt, int64_t nsteps, pisb_thermo *out) {
             // The force kernel is launched BEFORE the host knows the decision: it returns at once if the (now global) rebuild
             // flag is set, and the flag travels to the host on a second stream meanwhile -- on the ~80 % of steps without a
             // rebuild the GPU never waits for the host round trip.
-            const bool speculate = v2_possible(h) && (h->force_variant == 0 || h->force_variant == 3 || h->force_variant == 5 || h->force_variant == 6);
+            const bool speculate = v2_possible(h) && (h->force_variant == 0 || h->force_variant == 3 || h->force_variant == 5 || h->force_variant == 6 ||
+                                                      h->force_variant == 7);
             double *outp[3] = {h->g[0].p, h->g[1].p, h->g[2].p};
             if (speculate) {
                 if (fused)  // the decision word the speculative launch and the host read (see FLAG_DECISION)
@@ -2576,6 +2612,33 @@ int pisb_neighbours(pisb_t *h, int32_t *nnbr, int32_t *nbr, int64_t cap_per_atom
         }
     }
     h->total_nbr = total;
+    return PISB_OK;
+}
+
+int pisb_list_stats(pisb_t *h, int64_t *out3) {
+    if (!h || !out3) return PISB_ERR_INVALID;
+    if (!h->have_atoms || !h->have_box) return fail(h, PISB_ERR_STATE, "list_stats before upload/set_box");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (h->multi) {
+        if (!h->list_valid) TRY(multi_rebuild(h));
+    } else {
+        TRY(ensure_list(h));
+    }
+    DevBuf<unsigned long long> d;
+    TRY(dev_reserve(h, d, 4));
+    CUDA_TRY(h, cudaMemsetAsync(d.p, 0, sizeof(unsigned long long) * 4, h->stream));
+    const bool pairs = pair_mode(h);
+    ListStatsArgs a{h->n, h->npad, pairs ? 1 : 0, h->xt.p, h->nbr.p, h->nnbr.p, pairs ? pair_list_args(h) : PairListArgs{}, h->box, h->pairs[0],
+                    h->table_d.p, h->n_types, d.p};
+    if (h->box.ortho) k_list_stats<true><<<nblk(h->n, TPB), TPB, 0, h->stream>>>(a);
+    else k_list_stats<false><<<nblk(h->n, TPB), TPB, 0, h->stream>>>(a);
+    TRY(check_launch(h, "k_list_stats"));
+    unsigned long long host[4] = {0, 0, 0, 0};
+    CUDA_TRY(h, cudaMemcpyAsync(host, d.p, sizeof host, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    dev_free(h, d);
+    for (int k = 0; k < 3; ++k) out3[k] = (int64_t)host[k];
+    h->total_nbr = (int64_t)host[0];
     return PISB_OK;
 }
 

@@ -258,6 +258,12 @@ class LJCudaManager:
         capi.check(self._h, lib.pisb_neighbours(self._h, capi._ptr(nn), capi._ptr(nb), cap))
         return nn, nb
 
+    def list_stats(self) -> dict:
+        """Listed pairs, pairs inside the cutoff now, index words stored (pisb_list_stats; device-side count)."""
+        out = np.zeros(3, dtype=np.int64)
+        capi.check(self._h, capi.load().pisb_list_stats(self._h, capi._ptr(out)))
+        return {"listed": int(out[0]), "in_range": int(out[1]), "index_words": int(out[2])}
+
     def invalidate_list(self):
         capi.check(self._h, capi.load().pisb_invalidate_list(self._h))
 

@@ -38,23 +38,47 @@ def test_reference_arm_other_ranks_exit_quietly():
 
 @pytest.mark.gpu
 def test_cuda_arm_json_line():
-    d = _run(["--steps", "12", "--warmup", "3", "--ncell", "24", "--ref-ncell", "8", "--ref-ncell-serial", "6", "--cpu-steps", "2",
-              "--e2e-steps", "3"])
-    assert BASE_KEYS | {"clocks", "gpu_launches", "roofline"} <= set(d)
+    d = _run(["--steps", "12", "--warmup", "3", "--ncell", "24", "--cpu-ncell", "8", "--ref-ncell-serial", "6", "--cpu-steps", "2",
+              "--e2e-steps", "3", "--no-strong"])
+    assert BASE_KEYS | {"clocks", "gpu_launches", "roofline", "roofline_hbm"} <= set(d)
     assert d["n_gpus"] == 1 and d["steps"] == 12 and d["warmup"] == 3 and d["higher_is_better"] is True
     assert d["gpu_launches"] > 30 and d["value"] > 1e7
-    rf = d["roofline"]
-    assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-12
+    rf, rh = d["roofline"], d["roofline_hbm"]
+    # the binding resource first: FP64, against the measured DFMA rate; the HBM view beside it
+    assert rf["bound"] == "fp64" and rf["unit"] == "TFLOP/s" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-12
+    assert 60 < rf["mean_neighbours_listed"] < 110 and 40 < rf["mean_neighbours_in_range"] < rf["mean_neighbours_listed"]
+    assert abs(rf["algorithmic_flops_per_atom"] - (21 * rf["mean_neighbours_listed"] + 18 * rf["mean_neighbours_in_range"])) < 1e-6 + 20
+    assert rh["bound"] == "hbm" and rh["unit"] == "GB/s" and abs(rh["frac"] - rh["achieved"] / rh["peak"]) < 1e-12
     assert d["e2e"]["h2d_bytes_per_step"] == 72 * d["config"]["n_atoms"] and d["e2e"]["value"] < d["value"]
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
 
 
+def test_reference_arm_ignores_torchrun_thread_cap():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers: the reference arm must still use the host's cores (round 1's
+    N > 1 reference numbers were single-thread runs because of it)."""
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1", "--ref-ncell", "8"],
+                       capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
+    assert r.returncode == 0, r.stderr[-1000:]
+    d = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+    assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
+    assert d["sample_atoms"] == 2048 and d["sample_is_whole_workload"] is False and "2048-atom" in d["cpu_baseline"]["sample"]
+
+
+def test_reference_arm_times_the_real_workload_when_it_fits():
+    d = _run(["--impl", "reference", "--steps", "2", "--warmup", "1", "--ncell", "8"])
+    assert d["sample_atoms"] == d["config"]["n_atoms"] == 2048 and d["sample_is_whole_workload"] is True
+
+
 def test_fp64_yardstick_arithmetic():
-    """roofline_fp64 of the CUDA arm: issue slots per atom x atoms / launch time against the measured DFMA rate."""
+    """`roofline` of the CUDA arm: algorithmic flops (21 K + 18 K_in + 20) against 2 x the measured DFMA rate,
+    and the issued-slot fraction (SASS count x listed pairs) against the DFMA rate."""
     sys.path.insert(0, ROOT)
     import bench
 
-    r = bench.fp64_roofline(85.34, 4_000_000, 1.16, True)
-    assert abs(r["slots_per_atom"] - (35 * 85.34 + 110)) < 1e-9
-    assert 0.60 < r["frac"] < 0.70 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12     # ncu: 66 % for this launch
-    assert bench.fp64_roofline(85.34, 4_000_000, 1.09, False)["frac"] > r["frac"]
+    r = bench.fp64_roofline("k", 85.34, 54.0, 4_000_000, 1.0, True)
+    assert abs(r["algorithmic_flops_per_atom"] - (21 * 85.34 + 18 * 54.0 + 20)) < 1e-9
+    assert abs(r["issued_fp64_slots_per_atom"] - (bench.FP64_SLOTS_PER_PAIR * 85.34 + bench.FP64_SLOTS_EPILOGUE)) < 1e-9
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12 and abs(r["frac_of_dfma_issue_rate"] - 2 * r["frac"]) < 1e-12
+    assert r["bound"] == "fp64" and 0 < r["issue_frac"] < 1
+    assert bench.fp64_roofline("k", 85.34, 54.0, 4_000_000, 0.8, True)["frac"] > r["frac"]

@@ -63,6 +63,10 @@ def test_force_loops_have_no_local_memory_traffic():
         "k_force_vv<false,no drift,single GPU>": "_ZN4pisb10k_force_vvILb0ELb0ELb0EEEvNS_11ForceVVArgsE",
         "k_force_vv<false,drift,brick>": "_ZN4pisb10k_force_vvILb0ELb1ELb1EEEvNS_11ForceVVArgsE",
         "k_force_vv<false,no drift,brick>": "_ZN4pisb10k_force_vvILb0ELb0ELb1EEEvNS_11ForceVVArgsE",
+        # four lanes per atom (the default above 75k atoms): one 32-bit reload per iteration of four tiles is tolerated
+        "k_force_q<false,fused,drift,single GPU>": "_ZN4pisb9k_force_qILb0ELb1ELb1ELb0EEEvNS_11ForceVVArgsE",
+        "k_force_q<false,fused,drift,brick>": "_ZN4pisb9k_force_qILb0ELb1ELb1ELb1EEEvNS_11ForceVVArgsE",
+        "k_force_q<false,plain,single GPU>": "_ZN4pisb9k_force_qILb0ELb0ELb0ELb0EEEvNS_11ForceVVArgsE",
     }
     for name, sym in kernels.items():
         out = subprocess.run([cuobjdump, "-sass", "-fun", sym, capi.LIB_PATH], capture_output=True, text=True, timeout=120).stdout
@@ -81,4 +85,5 @@ def test_force_loops_have_no_local_memory_traffic():
         assert len(loops) >= 2, f"{name}: expected the interior and the minimum-image gather loops, found {len(loops)}"
         for k, body in enumerate(loops):
             local = [t for t in body if re.search(r"\b(STL|LDL)\b", t)]
-            assert len(local) <= (0 if k == 0 else 2), f"{name}: local-memory traffic inside gather loop {k}: {local[:4]}"
+            allowed = (1 if k == 0 else 2) if name.startswith("k_force_q") else (0 if k == 0 else 2)
+            assert len(local) <= allowed, f"{name}: local-memory traffic inside gather loop {k}: {local[:4]}"

@@ -109,6 +109,13 @@ def test_config2_256k_atoms_1000_nve_steps_vs_oracle():
     assert np.max(np.abs(t_gpu - t_ref) / np.abs(t_ref)) <= ENERGY_TOL
     mgr.download(atoms)
     assert np.abs(atoms.positions - x).max() <= 1e-9
+    # forces of the two runs differ by the trajectories' accumulated rounding (|dx| ~ 1e-10 A x the LJ stiffness): compare them
+    # on ONE state instead -- the oracle's final positions, evaluated by both
+    assert force_rel_err(atoms.forces, f).max() <= 1e-8
+    atoms.positions[...] = x
+    mgr.attach(atoms)
+    mgr.compute()
+    mgr.download(atoms, positions=False, velocities=False)
     assert force_rel_err(atoms.forces, f).max() <= FORCE_TOL
 
 

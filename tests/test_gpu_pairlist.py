@@ -45,10 +45,11 @@ def _check_against_oracle(atoms, variant=9, rc=None, steps=30):
 
 
 @pytest.mark.parametrize("variant", [9, 10])
-@pytest.mark.parametrize("ncell", [5, 6, 11])
+@pytest.mark.parametrize("ncell", [6, 7, 11])
 def test_pair_lists_match_the_oracle(ncell, variant):
-    """ncell = 5: 27 A box, a grid of 5 half-size cells per edge -- the joint sweep would lap the periodic row and every pair
-    thread takes the two-sweep path; 6: laps only for atoms two cells apart; 11: joint sweeps, interior warps."""
+    """ncell = 6: 32.5 A box, the smallest the reference handles without double counting (3 cells of rc + skin), a grid of 6
+    half-size cells per edge -- the joint sweep of atoms two cells apart would lap the periodic row and falls back to two
+    sweeps; 11: joint sweeps, interior warps."""
     _check_against_oracle(fcc_argon(ncell, temperature=40.0, seed=ncell, jitter=0.2), variant=variant)
 
 

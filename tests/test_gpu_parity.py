@@ -18,7 +18,7 @@ def _jittered(ncell, jitter=0.15, temperature=30.0, seed=7):
     return fcc_argon(ncell, temperature=temperature, seed=seed, jitter=jitter)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12])
 @pytest.mark.parametrize("ncell,skin", [(10, 0.0), (10, SKIN), (16, SKIN)])
 def test_compute_potential_parity(ncell, skin, variant):
     atoms = _jittered(ncell)
@@ -228,7 +228,7 @@ def test_edge_positions_on_boundary_and_beyond():
     assert force_rel_err(atoms.forces, f_ref).max() <= FORCE_TOL
 
 
-@pytest.mark.parametrize("variant", [0, 6, 8, 9])
+@pytest.mark.parametrize("variant", [0, 6, 8, 9, 11])
 def test_unwrapped_inputs_far_outside_the_box_and_a_box_centred_on_the_origin(variant):
     """Step-0 inputs need not lie in [0, L) (simulation.rs:28 calls compute_potential on them as read): atoms several
     box lengths out, and a whole system given in [-L/2, L/2).  The interior-warp shortcut of the force kernels uses raw
@@ -299,7 +299,7 @@ def test_kernel_families_agree():
     but take the same in/out decisions: bit-identical among themselves, and within rounding of the reference-order family."""
     atoms = _jittered(12, jitter=0.25, temperature=50.0)
     out = {}
-    for variant in (1, 2, 5, 3, 6):
+    for variant in (1, 2, 5, 3, 6, 11):
         a = Atoms(atoms.type_ids, atoms.masses, atoms.positions.copy(), atoms.sim_box, velocities=atoms.velocities.copy())
         m = make_manager(skin=SKIN, variant=variant)
         m.set_option("fuse_vv", 0)   # the force kernels proper; k_force_vv reduces KE over other block sizes (own test below)
@@ -317,12 +317,13 @@ def test_kernel_families_agree():
                 assert np.array_equal(out[base][1][name], out[other][1][name]), name
             for k in (2, 3, 4, 5):
                 assert np.array_equal(out[base][k], out[other][k])
-    ref, lean = out[1], out[3]
-    assert abs(lean[0] - ref[0]) <= 1e-13 * abs(ref[0])
-    assert force_rel_err(lean[5], ref[5]).max() <= 1e-12          # same state, two arithmetics: rounding only
-    for name in ("pe", "ke", "virial_pair"):
-        assert np.max(np.abs(lean[1][name] - ref[1][name]) / np.abs(ref[1][name])) <= 1e-11, name
-    assert np.abs(lean[2] - ref[2]).max() <= 1e-11                # 25 steps apart by accumulated rounding only
+    for v in (3, 11):      # 11: four lanes per atom -- the lean arithmetic again, partial sums met in a butterfly
+        ref, lean = out[1], out[v]
+        assert abs(lean[0] - ref[0]) <= 1e-13 * abs(ref[0])
+        assert force_rel_err(lean[5], ref[5]).max() <= 1e-12          # same state, two arithmetics: rounding only
+        for name in ("pe", "ke", "virial_pair"):
+            assert np.max(np.abs(lean[1][name] - ref[1][name]) / np.abs(ref[1][name])) <= 1e-11, name
+        assert np.abs(lean[2] - ref[2]).max() <= 1e-11                # 25 steps apart by accumulated rounding only
 
 
 def test_guard_band_pairs_sit_on_the_cutoff():
@@ -706,7 +707,7 @@ def _run_batches(atoms, fuse, graphs, batches, table=None, nvt_first=False, vari
     return th, st
 
 
-@pytest.mark.parametrize("variant", [6, 9])
+@pytest.mark.parametrize("variant", [6, 9, 11])
 @pytest.mark.parametrize("graphs", [1, 0])
 def test_fused_force_integrator_step_equals_separate_kernels(graphs, variant):
     """k_force_vv (force + kick + drift in one launch, positions double-buffered) against k_force_v3 + k_vv: the same
@@ -768,7 +769,7 @@ def test_fused_step_trace_matches_oracle():
     assert np.abs(atoms.positions - x).max() < 1e-8
 
 
-@pytest.mark.parametrize("variant", [0, 6, 9])
+@pytest.mark.parametrize("variant", [0, 6, 9, 11])
 def test_pipelined_host_step_equals_whole_array_step(variant):
     """pisb_verlet_step_nve_host cuts the trait call's 3 x N host arrays into chunks and pipelines upload, drift and
     download (k_host_load_drift / k_store_range); option host_pipeline = 0 keeps the whole-array sequence.  Same
