@@ -298,232 +298,319 @@ double LJCudaManager::verlet_step_nve(Atoms &atoms, double dt) {
     return pe;
 }
 
-// ---- commands (src/readers/input_file/commands.rs) ---------------------------------------------------
-static void run_timestep(const std::vector<std::string> &a, size_t line, SimulationContext &ctx) { ctx.timestep = parse_float_at(a, 0, line); }
+// =====================================================================================================
+// Input script and LAMMPS-data readers.
+//
+// Written from the FILE FORMATS the reference accepts (its example/ inputs, the cases of src/tests/command_tests.rs and
+// the quirks listed in SURVEY appendix A), not from its parser: a typed token cursor, a statement table for the script
+// and a line classifier + per-section row readers for the data file.  What must match the reference is behaviour --
+// which inputs are accepted, what they mean, which error (kind and text) a bad input raises -- and tests/test_cli.py
+// pins that through `--check`.
+// =====================================================================================================
 
-static void run_runsteps(const std::vector<std::string> &a, size_t line, SimulationContext &ctx) {
-    ctx.steps = convert_to_usize(parse_int_at(a, 0, line), line);
-}
-
-static void run_velocity(const std::vector<std::string> &a, size_t line, SimulationContext &ctx) {  // :78-144
-    size_t read_args = 0;
-    StartVelocity sv;
-    sv.group = get_required(a, read_args, line);
-    ++read_args;
-    const std::string style = get_required(a, read_args, line);
-    ++read_args;
-    if (style == "create") {
-        sv.start_temperature = parse_float_at(a, read_args, line);
-        ++read_args;
-        int32_t seed = 0;
-        bool ok = true;
+// One line's words, consumed left to right with typed accessors.  Every accessor that needs a word raises
+// MissingArgument for the line when none is left; the maybe_* forms consume a word only if it has the wanted type.
+class Words {
+   public:
+    Words(std::vector<std::string> words, size_t line) : w_(std::move(words)), line_(line) {}
+    bool done() const { return at_ >= w_.size(); }
+    size_t left() const { return w_.size() - at_; }
+    size_t line() const { return line_; }
+    const std::string &word() { return get_required(w_, at_++, line_); }
+    double real() { return parse_f64(word()); }
+    size_t count() { return convert_to_usize(parse_i32(word()), line_); }
+    // the word `ahead` positions further on, or nullptr
+    const std::string *peek(size_t ahead = 0) const { return at_ + ahead < w_.size() ? &w_[at_ + ahead] : nullptr; }
+    std::optional<double> maybe_real() {
+        if (done()) return std::nullopt;
         try {
-            seed = parse_int_at(a, read_args, line);
+            const double v = parse_f64(w_[at_]);
+            ++at_;
+            return v;
         } catch (const PisError &) {
-            ok = false;
-        }
-        if (ok) {
-            ++read_args;
-            sv.seed = convert_to_usize(seed, line);
-        } else {
-            sv.seed = 0;
-        }
-    } else {
-        throw PisError("InvalidArgument", "Invalid argument: " + style + " at line: " + std::to_string(line));
-    }
-    while (read_args < a.size()) {
-        const std::string keyword = a[read_args++];
-        if (keyword == "dist") {
-            const std::string arg = get_required(a, read_args, line);
-            ++read_args;
-            if (arg == "uniform" || arg == "gaussian") sv.dist = arg;
-            else throw PisError("InvalidArgument", "Invalid argument: " + arg + " at line: " + std::to_string(line));
-        } else {
-            throw PisError("InvalidArgument", "Invalid argument: " + keyword + " at line: " + std::to_string(line));
+            return std::nullopt;
         }
     }
-    ctx.starting_velocity = sv;
-}
+    std::optional<size_t> maybe_count() {
+        if (done()) return std::nullopt;
+        int32_t v;
+        try {
+            v = parse_i32(w_[at_]);
+        } catch (const PisError &) {
+            return std::nullopt;
+        }
+        ++at_;
+        return convert_to_usize(v, line_);  // an integer that is there but negative is an error, not "absent"
+    }
+    std::vector<std::string> rest() {
+        std::vector<std::string> out(w_.begin() + (std::ptrdiff_t)std::min(at_, w_.size()), w_.end());
+        at_ = w_.size();
+        return out;
+    }
+    [[noreturn]] void reject(const std::string &what) const {
+        throw PisError("InvalidArgument", "Invalid argument: " + what + " at line: " + std::to_string(line_));
+    }
 
-static void run_read_data(const std::vector<std::string> &a, size_t line, SimulationContext &ctx) {  // :147-384
-    const std::string path = get_required(a, 0, line);
-    std::ifstream file(path);
-    if (!file) throw PisError("InputFileError", "Failed to open input file '" + path + "': No such file or directory (os error 2))");
-    std::string section;
-    size_t n_atoms = 0;
-    double xlo = 0.0, xhi = 1.0, ylo = 0.0, yhi = 1.0, zlo = 0.0, zhi = 1.0;
-    std::vector<double> masses, positions, velocities;
-    std::vector<int32_t> type_ids;
-    bool start_velocities = true;
-    auto mgr = std::make_unique<LJCudaManager>(ctx.skin, ctx.device);
-    std::string raw;
-    size_t line_num = 0;
-    for (; std::getline(file, raw); ++line_num) {
-        const std::string l = trim(raw);
-        if (l.empty() || l[0] == '#') continue;
-        const std::vector<std::string> ls = split_whitespace(l);
-        const std::string &first = get_required(ls, 0, line_num);
-        if (first == "Masses" || first == "Atoms" || first == "PairCoeffs") {
-            section = first;
-            continue;
-        }
-        if (first == "Velocities") {
-            start_velocities = false;
-            section = first;
-            continue;
-        }
-        if (ls.size() > 1) {
-            if (ls[1] == "atoms") {
-                n_atoms = convert_to_usize(parse_int_at(ls, 0, line_num), line_num);
-                type_ids.assign(n_atoms, 0);
-                positions.assign(3 * n_atoms, 0.0);
-                velocities.assign(3 * n_atoms, 0.0);
-                continue;
-            }
-            if (ls[1] == "atom") {
-                masses.resize(convert_to_usize(parse_int_at(ls, 0, line_num), line_num), 0.0);
-                continue;
-            }
-        }
-        if (ls.size() > 2) {
-            if (ls[2] == "xlo") { xlo = parse_float_at(ls, 0, line_num); xhi = parse_float_at(ls, 1, line_num); continue; }
-            if (ls[2] == "ylo") { ylo = parse_float_at(ls, 0, line_num); yhi = parse_float_at(ls, 1, line_num); continue; }
-            if (ls[2] == "zlo") { zlo = parse_float_at(ls, 0, line_num); zhi = parse_float_at(ls, 1, line_num); continue; }
-        }
-        if (section == "Masses") {
-            const size_t type_id = convert_to_usize(parse_int_at(ls, 0, line_num), line_num);
-            const double mass = parse_float_at(ls, 1, line_num);
-            if (type_id < 1) throw PisError("InvalidAtomType", "Atom type " + std::to_string(type_id) + " out of range");
-            if (type_id > masses.size()) throw PisError("InvalidAtomType", "Atom type " + std::to_string(type_id) + " out of range");  // reference: panic (OOB)
-            masses[type_id - 1] = mass;
-        } else if (section == "PairCoeffs") {
-            // "1 0.238 3.405 8.5" -> (1,1); the "i j eps sigma rc" form is unreachable for integer j because
-            // token 1 parses as a float first (reference quirk, commands.rs:271-291) -- reproduced.
-            const int i = (int)convert_to_usize(parse_int_at(ls, 0, line_num), line_num);
-            bool eps_ok = true;
-            double epsilon = 0.0;
-            try {
-                epsilon = parse_float_at(ls, 1, line_num);
-            } catch (const PisError &) {
-                eps_ok = false;
-            }
-            if (eps_ok) {
-                const double sigma = parse_float_at(ls, 2, line_num);
-                double rcut;
-                try { rcut = parse_float_at(ls, 3, line_num); } catch (const PisError &) { rcut = 2.5 * sigma; }
-                mgr->insert({i, i}, LennardJones{epsilon, sigma, rcut, true});
-            } else {
-                const int j = (int)convert_to_usize(parse_int_at(ls, 1, line_num), line_num);
-                epsilon = parse_float_at(ls, 2, line_num);
-                const double sigma = parse_float_at(ls, 3, line_num);
-                double rcut;
-                try { rcut = parse_float_at(ls, 4, line_num); } catch (const PisError &) { rcut = 2.5 * sigma; }
-                mgr->insert({i, j}, LennardJones{epsilon, sigma, rcut, true});
-            }
-            continue;
-        } else if (section == "Atoms") {
-            size_t id = convert_to_usize(parse_int_at(ls, 0, line_num), line_num);
-            if (id == 0 || id > n_atoms)
-                throw PisError("AtomCountMismatch", "Atom count mismatch: expected " + std::to_string(n_atoms) + ", found " + std::to_string(id));
-            --id;
-            type_ids[id] = (int32_t)convert_to_usize(parse_int_at(ls, 1, line_num), line_num);
-            positions[3 * id] = parse_float_at(ls, 2, line_num);
-            positions[3 * id + 1] = parse_float_at(ls, 3, line_num);
-            positions[3 * id + 2] = parse_float_at(ls, 4, line_num);
-        } else if (section == "Velocities") {
-            size_t id = convert_to_usize(parse_int_at(ls, 0, line_num), line_num);
-            if (id == 0 || id > n_atoms)
-                throw PisError("AtomCountMismatch", "Atom count mismatch: expected " + std::to_string(n_atoms) + ", found " + std::to_string(id));
-            --id;
-            velocities[3 * id] = parse_float_at(ls, 1, line_num);
-            velocities[3 * id + 1] = parse_float_at(ls, 2, line_num);
-            velocities[3 * id + 2] = parse_float_at(ls, 3, line_num);
-        }
-    }
-    Atoms atoms;
-    atoms.n_atoms = n_atoms;
-    atoms.type_ids = std::move(type_ids);
-    atoms.masses = std::move(masses);
-    atoms.positions = std::move(positions);
-    atoms.velocities = std::move(velocities);
-    atoms.forces.assign(3 * n_atoms, 0.0);
-    atoms.sim_box = SimulationBox::from_lammps_data(xlo, xhi, ylo, yhi, zlo, zhi, 0.0, 0.0, 0.0);
-    ctx.atoms = std::move(atoms);
-    if (!mgr->is_empty()) ctx.mgr = std::move(mgr);
-    if (ctx.starting_velocity) {
-        ctx.starting_velocity->start_velocity = start_velocities;
-    } else {
-        StartVelocity sv;
-        sv.start_velocity = start_velocities;
-        ctx.starting_velocity = sv;
+   private:
+    std::vector<std::string> w_;
+    size_t at_ = 0, line_;
+};
+
+// A trailing `keyword value value ...` clause of a statement: the keyword and how many reals follow it.
+struct Clause {
+    const char *keyword;
+    int reals;
+};
+
+// Reads `keyword v1 .. vn` clauses until the line ends; unknown keywords are rejected.  store(k, values) receives the
+// index of the clause in the table.
+template <typename Store>
+static void read_clauses(Words &w, const Clause *table, size_t n_table, Store store) {
+    while (!w.done()) {
+        const std::string key = w.word();
+        size_t k = 0;
+        while (k < n_table && key != table[k].keyword) ++k;
+        if (k == n_table) w.reject(key);
+        double v[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int r = 0; r < table[k].reals; ++r) v[r] = w.real();
+        store(k, v);
     }
 }
 
-static void run_fix(const std::vector<std::string> &a, size_t line, SimulationContext &ctx) {  // :387-459
-    size_t read_args = 0;
-    const std::string name = get_required(a, read_args++, line);
-    const std::string group = get_required(a, read_args++, line);
-    const std::string style = get_required(a, read_args++, line);
-    while (read_args < a.size()) {
-        const std::string keyword = a[read_args++];
-        if (keyword == "temp") {
-            const double t0 = parse_float_at(a, read_args++, line);
-            const double t1 = parse_float_at(a, read_args++, line);
-            const double tau = parse_float_at(a, read_args++, line);
-            if (style == "npt" || style == "nvt") ctx.nh_chain_args = NHThermostatChainArgs{name, group, t0, t1, tau};
-        } else if (keyword == "iso") {
-            const double p0 = parse_float_at(a, read_args++, line);
-            (void)parse_float_at(a, read_args++, line);
-            const double tau = parse_float_at(a, read_args++, line);
-            if (style == "npt") ctx.mtk_barostat_args = MTKBarostatArgs{name, group, p0, tau};
-        } else {
-            throw PisError("InvalidArgument", "Invalid argument: " + keyword + " at line: " + std::to_string(line));
-        }
+// ---- script statements ------------------------------------------------------------------------------
+// timestep <dt>
+static void stmt_timestep(Words &w, SimulationContext &ctx) { ctx.timestep = w.real(); }
+
+// run <steps>
+static void stmt_run(Words &w, SimulationContext &ctx) { ctx.steps = w.count(); }
+
+// velocity <group> create <T> [<seed>] [dist uniform|gaussian]
+//   the seed is optional: a fourth word that is not an integer leaves the seed at 0 and is read as a keyword
+static void stmt_velocity(Words &w, SimulationContext &ctx) {
+    StartVelocity sv;
+    sv.group = w.word();
+    const std::string style = w.word();
+    if (style != "create") w.reject(style);
+    sv.start_temperature = w.real();
+    sv.seed = w.maybe_count().value_or(0);
+    while (!w.done()) {
+        const std::string key = w.word();
+        if (key != "dist") w.reject(key);
+        const std::string kind = w.word();
+        if (kind != "uniform" && kind != "gaussian") w.reject(kind);
+        sv.dist = kind;
     }
+    ctx.starting_velocity = sv;  // replaces whatever a data file recorded before (start_velocity back to true)
 }
 
-static void run_pair_style(const std::vector<std::string> &a, size_t line, SimulationContext &ctx) {
+// fix <name> <group> <style> [temp <T0> <T1> <tau>] [iso <P0> <P1> <tau>]
+//   temp counts for the nvt and npt styles, iso for npt; any other style parses and changes nothing
+static void stmt_fix(Words &w, SimulationContext &ctx) {
+    const std::string name = w.word(), group = w.word(), style = w.word();
+    static const Clause clauses[] = {{"temp", 3}, {"iso", 3}};
+    const bool thermostat = style == "nvt" || style == "npt", barostat = style == "npt";
+    read_clauses(w, clauses, 2, [&](size_t k, const double *v) {
+        if (k == 0 && thermostat) ctx.nh_chain_args = NHThermostatChainArgs{name, group, v[0], v[1], v[2]};
+        if (k == 1 && barostat) ctx.mtk_barostat_args = MTKBarostatArgs{name, group, v[0], v[2]};
+    });
+}
+
+// pair_style <style> <args...>      kept verbatim; interpreted once the whole script has been read
+static void stmt_pair_style(Words &w, SimulationContext &ctx) {
     PotentialArgs p;
-    p.pair_style_line = line;
-    p.pair_style_args = a;
+    p.pair_style_line = w.line();
+    p.pair_style_args = w.rest();
     ctx.potential_args = p;
 }
 
-static void run_pair_coeff(const std::vector<std::string> &a, size_t line, SimulationContext &ctx) {
+// pair_coeff <i> <j> <eps> <sigma> [<rc>]      needs a pair_style before it
+static void stmt_pair_coeff(Words &w, SimulationContext &ctx) {
     if (!ctx.potential_args)
         throw PisError("PotentialNotInitialized", "Potential manager not initialized - missing pair_style or pair_coeff commands");
-    ctx.potential_args->pair_coeff_args.push_back(a);
-    ctx.potential_args->pair_coeff_lines.push_back(line);
+    ctx.potential_args->pair_coeff_lines.push_back(w.line());
+    ctx.potential_args->pair_coeff_args.push_back(w.rest());
 }
 
-static void run_dump(const std::vector<std::string> &a, size_t line, SimulationContext &ctx) {  // :484-496
-    size_t r = 0;
-    ctx.dump_args.name = get_required(a, r++, line);
-    ctx.dump_args.group = get_required(a, r++, line);
-    ctx.dump_args.style = get_required(a, r++, line);
-    ctx.dump_args.dump_step = convert_to_usize(parse_int_at(a, r++, line), line);
-    ctx.dump_args.file_name = get_required(a, r, line);
+// dump <name> <group> <style> <every> <file>
+static void stmt_dump(Words &w, SimulationContext &ctx) {
+    DumpArgs &d = ctx.dump_args;
+    d.name = w.word();
+    d.group = w.word();
+    d.style = w.word();
+    d.dump_step = w.count();
+    d.file_name = w.word();
 }
+
+static void stmt_read_data(Words &w, SimulationContext &ctx);
+
+struct Statement {
+    const char *keyword;
+    void (*read)(Words &, SimulationContext &);
+};
+static const Statement STATEMENTS[] = {
+    {"timestep", stmt_timestep}, {"run", stmt_run},           {"velocity", stmt_velocity},     {"read_data", stmt_read_data},
+    {"fix", stmt_fix},           {"pair_style", stmt_pair_style}, {"pair_coeff", stmt_pair_coeff}, {"dump", stmt_dump},
+};
 
 bool run_command(const std::string &command, const std::vector<std::string> &args, size_t line, SimulationContext &ctx) {
-    if (command == "timestep") run_timestep(args, line, ctx);
-    else if (command == "run") run_runsteps(args, line, ctx);
-    else if (command == "velocity") run_velocity(args, line, ctx);
-    else if (command == "read_data") run_read_data(args, line, ctx);
-    else if (command == "fix") run_fix(args, line, ctx);
-    else if (command == "pair_style") run_pair_style(args, line, ctx);
-    else if (command == "pair_coeff") run_pair_coeff(args, line, ctx);
-    else if (command == "dump") run_dump(args, line, ctx);
-    else return false;
-    return true;
+    for (const Statement &s : STATEMENTS)
+        if (command == s.keyword) {
+            Words w(args, line);
+            s.read(w, ctx);
+            return true;
+        }
+    return false;  // keywords are case-sensitive: "TimeStep" is unknown
+}
+
+// ---- LAMMPS data file -------------------------------------------------------------------------------
+// Layout accepted (example/argon4000.txt, example/data_run.txt):
+//     <N> atoms / <T> atom types / <lo> <hi> xlo xhi (ylo yhi, zlo zhi)          header fields, recognised by the word
+//                                                                                 that FOLLOWS the numbers
+//     Masses | PairCoeffs | Atoms | Velocities                                    section titles (first word of a line)
+//     rows of the open section: Masses `type m`, PairCoeffs `type eps sigma [rc]`, Atoms `id type x y z`,
+//     Velocities `id vx vy vz`; whatever follows the fields a row needs is ignored (trailing comments).
+// Blank lines and lines starting with '#' are skipped.  Atom ids are 1-based and address the arrays directly.
+class DataFile {
+   public:
+    explicit DataFile(double skin, int device) : mgr_(std::make_unique<LJCudaManager>(skin, device)) {}
+
+    void read(std::istream &in) {
+        std::string raw;
+        for (size_t line = 0; std::getline(in, raw); ++line) {
+            const std::string text = trim(raw);
+            if (text.empty() || text[0] == '#') continue;
+            Words w(split_whitespace(text), line);
+            if (open_section(*w.peek())) continue;
+            if (header_field(w)) continue;
+            if (row_) (this->*row_)(w);
+        }
+    }
+
+    // hand the result to the context: atoms + box, the potential if the file had a PairCoeffs section, and whether
+    // velocities still have to be created (no Velocities section)
+    void install(SimulationContext &ctx) {
+        Atoms atoms;
+        atoms.n_atoms = n_atoms_;
+        atoms.type_ids = std::move(types_);
+        atoms.masses = std::move(masses_);
+        atoms.positions = std::move(x_);
+        atoms.velocities = std::move(v_);
+        atoms.forces.assign(3 * n_atoms_, 0.0);
+        atoms.sim_box = SimulationBox::from_lammps_data(lo_[0], hi_[0], lo_[1], hi_[1], lo_[2], hi_[2], 0.0, 0.0, 0.0);
+        ctx.atoms = std::move(atoms);
+        if (!mgr_->is_empty()) ctx.mgr = std::move(mgr_);
+        if (!ctx.starting_velocity) ctx.starting_velocity = StartVelocity{};
+        ctx.starting_velocity->start_velocity = !has_velocities_;
+    }
+
+   private:
+    using Row = void (DataFile::*)(Words &);
+
+    bool open_section(const std::string &title) {
+        static const struct {
+            const char *title;
+            Row row;
+        } sections[] = {{"Masses", &DataFile::row_mass}, {"PairCoeffs", &DataFile::row_pair_coeff}, {"Atoms", &DataFile::row_atom},
+                        {"Velocities", &DataFile::row_velocity}};
+        for (const auto &s : sections)
+            if (title == s.title) {
+                row_ = s.row;
+                if (s.row == &DataFile::row_velocity) has_velocities_ = true;
+                return true;
+            }
+        return false;
+    }
+
+    // `<N> atoms`, `<T> atom types`, `<lo> <hi> xlo xhi`: the tag word sits right behind the numbers
+    bool header_field(Words &w) {
+        const std::string *tag1 = w.peek(1), *tag2 = w.peek(2);
+        if (tag1 && *tag1 == "atoms") {
+            n_atoms_ = w.count();
+            types_.assign(n_atoms_, 0);
+            x_.assign(3 * n_atoms_, 0.0);
+            v_.assign(3 * n_atoms_, 0.0);
+            return true;
+        }
+        if (tag1 && *tag1 == "atom") {
+            masses_.assign(w.count(), 0.0);
+            return true;
+        }
+        if (tag2) {
+            static const char *const axis_tag[3] = {"xlo", "ylo", "zlo"};
+            for (int d = 0; d < 3; ++d)
+                if (*tag2 == axis_tag[d]) {
+                    lo_[d] = w.real();
+                    hi_[d] = w.real();
+                    return true;
+                }
+        }
+        return false;
+    }
+
+    void row_mass(Words &w) {
+        const size_t type = w.count();
+        const double m = w.real();
+        if (type < 1 || type > masses_.size()) throw PisError("InvalidAtomType", "Atom type " + std::to_string(type) + " out of range");
+        masses_[type - 1] = m;
+    }
+
+    // `type eps sigma [rc]` (rc defaults to 2.5 sigma).  A second word that does not read as a real selects the
+    // two-type form `i j eps sigma [rc]` -- which an INTEGER j never does, because "2" reads as the real 2.0: the
+    // reference mis-reads such a line as a like-pair entry with eps = j, and so does this reader.
+    void row_pair_coeff(Words &w) {
+        const int i = (int)w.count();
+        int j = i;
+        std::optional<double> eps = w.maybe_real();
+        if (!eps) {
+            j = (int)w.count();
+            eps = w.real();
+        }
+        const double sigma = w.real();
+        const double rc = w.maybe_real().value_or(2.5 * sigma);
+        mgr_->insert({i, j}, LennardJones{*eps, sigma, rc, true});
+    }
+
+    size_t atom_index(Words &w) {
+        const size_t id = w.count();
+        if (id < 1 || id > n_atoms_)
+            throw PisError("AtomCountMismatch", "Atom count mismatch: expected " + std::to_string(n_atoms_) + ", found " + std::to_string(id));
+        return id - 1;
+    }
+
+    void row_atom(Words &w) {
+        const size_t i = atom_index(w);
+        types_[i] = (int32_t)w.count();
+        for (int c = 0; c < 3; ++c) x_[3 * i + c] = w.real();
+    }
+
+    void row_velocity(Words &w) {
+        const size_t i = atom_index(w);
+        for (int c = 0; c < 3; ++c) v_[3 * i + c] = w.real();
+    }
+
+    Row row_ = nullptr;
+    size_t n_atoms_ = 0;
+    double lo_[3] = {0.0, 0.0, 0.0}, hi_[3] = {1.0, 1.0, 1.0};
+    std::vector<double> masses_, x_, v_;
+    std::vector<int32_t> types_;
+    bool has_velocities_ = false;
+    std::unique_ptr<LJCudaManager> mgr_;
+};
+
+// read_data <file>
+static void stmt_read_data(Words &w, SimulationContext &ctx) {
+    const std::string path = w.word();
+    std::ifstream file(path);
+    if (!file) throw PisError("InputFileError", "Failed to open input file '" + path + "': No such file or directory (os error 2))");
+    DataFile data(ctx.skin, ctx.device);
+    data.read(file);
+    data.install(ctx);
 }
 
 // ---- DumpTraj (src/writers/dump_traj.rs) ---------------------------------------------------------------
 DumpTraj::DumpTraj(const DumpArgs &args) : path_(args.file_name) {
     out_ = std::fopen(path_.c_str(), "w");
     if (!out_) throw PisError("DumpCreateError", "Failed to create trajectory file '" + path_ + "': " + std::strerror(errno));
-    static char *buf = nullptr;
-    (void)buf;
     std::setvbuf(out_, nullptr, _IOFBF, 1 << 20);
 }
 
@@ -635,58 +722,48 @@ void Simulation::run(LJCudaManager &mgr, SimulationContext &ctx, FILE *out) {
     std::fflush(out);
 }
 
-// ---- System (src/system.rs) ----------------------------------------------------------------------------
+// ---- System: script -> context -> run -----------------------------------------------------------------
+// Script syntax: one statement per line, `keyword arg arg ...`; `#` starts a comment anywhere on a line; lines with fewer
+// than two words are skipped; an unknown keyword is an error that names the line (1-based).
 System &System::read() {
     std::ifstream file(infile_);
     if (!file) throw PisError("InputFileError", "Failed to open input file '" + infile_ + "': No such file or directory (os error 2))");
     std::string raw;
-    size_t line_num = 0;
-    while (std::getline(file, raw)) {
-        ++line_num;
-        const std::string l = trim(raw);
-        if (l.empty() || l[0] == '#') continue;
-        const size_t hash = l.find('#');
-        const std::string uncommented = trim(hash == std::string::npos ? l : l.substr(0, hash));
-        const std::vector<std::string> ls = split_whitespace(uncommented);
-        if (ls.size() < 2) continue;
-        const std::vector<std::string> args(ls.begin() + 1, ls.end());
-        if (!run_command(ls[0], args, line_num, ctx))
-            throw PisError("UnknownCommand", "Invalid command " + ls[0] + " found line: " + std::to_string(line_num));
+    for (size_t line = 1; std::getline(file, raw); ++line) {
+        std::vector<std::string> words = split_whitespace(raw.substr(0, raw.find('#')));
+        if (words.size() < 2) continue;
+        const std::string keyword = words.front();
+        words.erase(words.begin());
+        if (!run_command(keyword, words, line, ctx))
+            throw PisError("UnknownCommand", "Invalid command " + keyword + " found line: " + std::to_string(line));
     }
     return *this;
 }
 
+// `pair_style lj/cut <rc>` + `pair_coeff i j eps sigma [rc]` lines -> a manager that REPLACES one a data file installed.
+// The table key is stored as written (i, j), while lookups use (min, max): `pair_coeff 2 1 ...` is never found
+//  -- the device table reproduces that.
+static std::unique_ptr<LJCudaManager> potential_from_script(const PotentialArgs &pa, double skin, int device) {
+    Words style_line(pa.pair_style_args, pa.pair_style_line);
+    const std::string style = style_line.word();
+    if (style != "lj/cut") throw PisError("UnknownPairStyle", "Unknown pair style: '" + style + "'");
+    const double global_cutoff = style_line.real();
+    auto mgr = std::make_unique<LJCudaManager>(skin, device);
+    for (size_t k = 0; k < pa.pair_coeff_args.size(); ++k) {
+        Words w(pa.pair_coeff_args[k], pa.pair_coeff_lines[k]);
+        const int i = (int)w.count(), j = (int)w.count();
+        const double epsilon = w.real(), sigma = w.real();
+        mgr->insert({i, j}, LennardJones{epsilon, sigma, w.maybe_real().value_or(global_cutoff), true});
+    }
+    return mgr;
+}
+
 System &System::contextualize() {
-    if (ctx.atoms) {
-        if (ctx.atoms->n_atoms == 0) throw PisError("NoAtomsDefined", "No atoms defined in input file");
-        if (ctx.starting_velocity && ctx.starting_velocity->start_velocity) {
-            const double t = ctx.starting_velocity->start_temperature.value_or(300.0);
-            const size_t seed = ctx.starting_velocity->seed.value_or(0);
-            ctx.atoms->start_velocities(t, seed);
-        }
-    }
-    if (ctx.potential_args) {
-        const PotentialArgs &pa = *ctx.potential_args;
-        const std::string &style = get_required(pa.pair_style_args, 0, pa.pair_style_line);
-        if (style == "lj/cut") {
-            const double global_cutoff = parse_float_at(pa.pair_style_args, 1, pa.pair_style_line);
-            auto mgr = std::make_unique<LJCudaManager>(ctx.skin, ctx.device);
-            for (size_t k = 0; k < pa.pair_coeff_args.size(); ++k) {
-                const auto &pc = pa.pair_coeff_args[k];
-                const size_t cl = pa.pair_coeff_lines[k];
-                const int i = (int)convert_to_usize(parse_int_at(pc, 0, cl), cl);
-                const int j = (int)convert_to_usize(parse_int_at(pc, 1, cl), cl);
-                const double epsilon = parse_float_at(pc, 2, cl);
-                const double sigma = parse_float_at(pc, 3, cl);
-                double local_rcut;
-                try { local_rcut = parse_float_at(pc, 4, cl); } catch (const PisError &) { local_rcut = global_cutoff; }
-                mgr->insert({i, j}, LennardJones{epsilon, sigma, local_rcut, true});  // key stored as given (:162)
-            }
-            ctx.mgr = std::move(mgr);
-        } else {
-            throw PisError("UnknownPairStyle", "Unknown pair style: '" + style + "'");
-        }
-    }
+    if (ctx.atoms && ctx.atoms->n_atoms == 0) throw PisError("NoAtomsDefined", "No atoms defined in input file");
+    // velocities: created unless a Velocities section supplied them (default 300 K, seed 0 without a velocity statement)
+    if (ctx.atoms && ctx.starting_velocity && ctx.starting_velocity->start_velocity)
+        ctx.atoms->start_velocities(ctx.starting_velocity->start_temperature.value_or(300.0), ctx.starting_velocity->seed.value_or(0));
+    if (ctx.potential_args) ctx.mgr = potential_from_script(*ctx.potential_args, ctx.skin, ctx.device);
     return *this;
 }
 
@@ -695,50 +772,102 @@ void System::run(FILE *thermo_out) {
     Simulation::run(*ctx.mgr, ctx, thermo_out);
 }
 
+// `--check`: the parsed context as one JSON object (no GPU needed), what tests/test_cli.py reads.
+namespace {
+struct Json {
+    std::string s;
+    bool first = true;
+    void sep() {
+        if (!first) s += ", ";
+        first = false;
+    }
+    Json &key(const char *k) {
+        sep();
+        s += std::string("\"") + k + "\": ";
+        first = true;
+        return *this;
+    }
+    Json &raw(const std::string &v) {
+        s += v;
+        first = false;
+        return *this;
+    }
+    Json &str(const std::string &v) { return raw("\"" + v + "\""); }
+    Json &num(double v) { return raw(rust_display_f64(v)); }
+    Json &open(char c) {
+        s += c;
+        first = true;
+        return *this;
+    }
+    Json &close(char c) {
+        s += c;
+        first = false;
+        return *this;
+    }
+    template <typename It, typename F>
+    Json &list(It b, It e, F each) {
+        open('[');
+        for (; b != e; ++b) {
+            sep();
+            first = true;
+            each(*b);
+            first = false;
+        }
+        return close(']');
+    }
+};
+}  // namespace
+
 std::string System::describe() const {
-    std::ostringstream o;
-    o << "{\"timestep\": " << rust_display_f64(ctx.timestep) << ", \"steps\": " << ctx.steps;
-    o << ", \"dump\": {\"name\": \"" << ctx.dump_args.name << "\", \"group\": \"" << ctx.dump_args.group << "\", \"style\": \""
-      << ctx.dump_args.style << "\", \"dump_step\": " << ctx.dump_args.dump_step << ", \"file_name\": \"" << ctx.dump_args.file_name << "\"}";
-    o << ", \"ensemble\": \"" << (ctx.nh_chain_args ? (ctx.mtk_barostat_args ? "NPT" : "NVT") : "NVE") << "\"";
+    Json j;
+    j.open('{');
+    j.key("timestep").num(ctx.timestep);
+    j.key("steps").raw(std::to_string(ctx.steps));
+    j.key("dump").open('{');
+    j.key("name").str(ctx.dump_args.name).key("group").str(ctx.dump_args.group).key("style").str(ctx.dump_args.style);
+    j.key("dump_step").raw(std::to_string(ctx.dump_args.dump_step)).key("file_name").str(ctx.dump_args.file_name);
+    j.close('}');
+    j.key("ensemble").str(ctx.nh_chain_args ? (ctx.mtk_barostat_args ? "NPT" : "NVT") : "NVE");
     if (ctx.starting_velocity) {
-        const auto &sv = *ctx.starting_velocity;
-        o << ", \"velocity\": {\"group\": \"" << sv.group << "\", \"start_velocity\": " << (sv.start_velocity ? "true" : "false");
-        if (sv.start_temperature) o << ", \"temperature\": " << rust_display_f64(*sv.start_temperature);
-        if (sv.seed) o << ", \"seed\": " << *sv.seed;
-        if (sv.dist) o << ", \"dist\": \"" << *sv.dist << "\"";
-        o << "}";
+        const StartVelocity &sv = *ctx.starting_velocity;
+        j.key("velocity").open('{');
+        j.key("group").str(sv.group).key("start_velocity").raw(sv.start_velocity ? "true" : "false");
+        if (sv.start_temperature) j.key("temperature").num(*sv.start_temperature);
+        if (sv.seed) j.key("seed").raw(std::to_string(*sv.seed));
+        if (sv.dist) j.key("dist").str(*sv.dist);
+        j.close('}');
     }
     if (ctx.atoms) {
         const Atoms &a = *ctx.atoms;
-        o << ", \"atoms\": {\"n_atoms\": " << a.n_atoms << ", \"n_types\": " << a.masses.size() << ", \"box\": ["
-          << rust_display_f64(a.sim_box.h[0]) << ", " << rust_display_f64(a.sim_box.h[4]) << ", " << rust_display_f64(a.sim_box.h[8]) << "]";
-        o << ", \"first_positions\": [";
-        for (size_t i = 0; i < std::min<size_t>(a.n_atoms, 4) * 3; ++i) o << (i ? ", " : "") << rust_display_f64(a.positions[i]);
-        o << "], \"first_velocities\": [";
-        for (size_t i = 0; i < std::min<size_t>(a.n_atoms, 4) * 3; ++i) o << (i ? ", " : "") << rust_display_f64(a.velocities[i]);
-        o << "], \"masses\": [";
-        for (size_t i = 0; i < a.masses.size(); ++i) o << (i ? ", " : "") << rust_display_f64(a.masses[i]);
-        o << "], \"types_head\": [";
-        for (size_t i = 0; i < std::min<size_t>(a.n_atoms, 8); ++i) o << (i ? ", " : "") << a.type_ids[i];
-        o << "]}";
+        const size_t head = std::min<size_t>(a.n_atoms, 4) * 3;
+        auto num = [&](double v) { j.num(v); };
+        j.key("atoms").open('{');
+        j.key("n_atoms").raw(std::to_string(a.n_atoms)).key("n_types").raw(std::to_string(a.masses.size()));
+        const double edges[3] = {a.sim_box.h[0], a.sim_box.h[4], a.sim_box.h[8]};
+        j.key("box").list(edges, edges + 3, num);
+        j.key("first_positions").list(a.positions.begin(), a.positions.begin() + (std::ptrdiff_t)head, num);
+        j.key("first_velocities").list(a.velocities.begin(), a.velocities.begin() + (std::ptrdiff_t)head, num);
+        j.key("masses").list(a.masses.begin(), a.masses.end(), num);
+        j.key("types_head").list(a.type_ids.begin(), a.type_ids.begin() + (std::ptrdiff_t)std::min<size_t>(a.n_atoms, 8),
+                                 [&](int32_t t) { j.raw(std::to_string(t)); });
+        j.close('}');
     }
-    o << ", \"potential\": ";
+    j.key("potential");
     if (ctx.mgr) {
-        o << "{\"max_rcut\": " << rust_display_f64(ctx.mgr->max_rcut()) << ", \"pairs\": [";
-        bool firstp = true;
-        for (auto &kv : ctx.mgr->table) {
-            o << (firstp ? "" : ", ") << "{\"i\": " << kv.first.first << ", \"j\": " << kv.first.second << ", \"epsilon\": "
-              << rust_display_f64(kv.second.epsilon) << ", \"sigma\": " << rust_display_f64(kv.second.sigma) << ", \"rcut\": "
-              << rust_display_f64(kv.second.rcut) << "}";
-            firstp = false;
-        }
-        o << "]}";
+        j.open('{');
+        j.key("max_rcut").num(ctx.mgr->max_rcut());
+        j.key("pairs").list(ctx.mgr->table.begin(), ctx.mgr->table.end(), [&](const std::pair<const std::pair<int, int>, LennardJones> &kv) {
+            j.open('{');
+            j.key("i").raw(std::to_string(kv.first.first)).key("j").raw(std::to_string(kv.first.second));
+            j.key("epsilon").num(kv.second.epsilon).key("sigma").num(kv.second.sigma).key("rcut").num(kv.second.rcut);
+            j.close('}');
+        });
+        j.close('}');
     } else {
-        o << "null";
+        j.raw("null");
     }
-    o << "}";
-    return o.str();
+    j.close('}');
+    return j.s;
 }
 
 }  // namespace pis

@@ -5,9 +5,10 @@
 //   SimulationBox      src/simulation_box.rs
 //   Atoms              src/atoms/new.rs, src/atoms/properties.rs (scalar formulas)
 //   LennardJones, LJCudaManager  src/potentials/{lennard_jones,potential,kind}.rs  (device-backed)
-//   Command / run_*    src/readers/input_file/commands.rs
-//   SimulationContext  src/readers/simulation_context.rs
-//   System             src/system.rs
+//   script / data readers   the FORMATS of the reference's input script and LAMMPS data file (behaviour pinned by the cases
+//                           of src/tests/command_tests.rs, re-expressed in tests/test_cli.py); own grammar table + tokenizer
+//   SimulationContext  src/readers/simulation_context.rs (what a parsed script amounts to)
+//   System             src/system.rs (read -> contextualize -> run)
 //   Simulation         src/simulation.rs   (NVE, NVT and NPT arms)
 //   DumpTraj           src/writers/dump_traj.rs
 #pragma once
@@ -140,7 +141,8 @@ struct SimulationContext {         // simulation_context.rs:105-131
     int device = 0;
 };
 
-// Command dispatch (commands.rs:25-63). Returns false for an unknown command.
+// One script statement: looks the keyword up in the statement table and lets its reader consume the words.
+// Returns false for an unknown keyword.
 bool run_command(const std::string &command, const std::vector<std::string> &args, size_t line, SimulationContext &ctx);
 
 class DumpTraj {                   // dump_traj.rs:12-75

@@ -81,6 +81,67 @@ def test_parser_errors(tmp_path, script, needle):
     assert needle in check(tmp_path, script, expect_fail=True)
 
 
+@pytest.mark.parametrize("script,needle", [
+    # src/tests/command_tests.rs, re-expressed as script lines (its `line: 0` becomes the script's line number)
+    ("TIMESTEP 0.1\n", "Invalid command TIMESTEP found line: 1"),            # from_str_unknown_command_returns_none: keywords are case-sensitive
+    ("TimeStep 0.1\n", "Invalid command TimeStep found line: 1"),
+    ("timestep notanumber\n", "Error parsing floating number from string notanumber"),   # timestep_invalid_float_returns_float_parse_error
+    ("timestep one\n", "Error parsing floating number from string one"),
+    ("timestep 0.1.2\n", "Error parsing floating number from string 0.1.2"),
+    ("run -1\n", "Negative value -1 not allowed on line: 1"),                 # runsteps_negative_value_returns_negative_value_error
+    ("run ten\n", "Error parsing integer number from string ten"),            # runsteps_non_integer_returns_int_parse_error
+    ("run 1e3\n", "Error parsing integer number from string 1e3"),
+    ("velocity all scale 300.0 42\n", "Invalid argument: scale at line: 1"),  # velocity_unknown_style_returns_invalid_argument
+    ("velocity all create 300.0 42 badkeyword value\n", "Invalid argument: badkeyword"),  # velocity_invalid_keyword_or_dist_...
+    ("velocity all create 300.0 42 dist lorentzian\n", "Invalid argument: lorentzian"),
+    ("dump my_dump all atom 100\n", "Missing argument on line 1"),            # dump_missing_args_returns_missing_argument
+    ("dump my_dump all atom\n", "Missing argument on line 1"),
+    ("dump my_dump all\n", "Missing argument on line 1"),
+    ("dump my_dump all atom every output.lammpstrj\n", "Error parsing integer number from string every"),   # dump_non_integer_step_...
+    ("dump my_dump all atom 1.5 output.lammpstrj\n", "Error parsing integer number from string 1.5"),
+    ("fix myfix all\n", "Missing argument on line 1"),                        # fix_missing_required_args_returns_missing_argument
+    ("fix myfix all nvt badkeyword 300.0 300.0 0.1\n", "Invalid argument: badkeyword"),   # fix_unknown_keyword_returns_invalid_argument
+    ("fix myfix all npt unknown 1.0 1.0 1.0\n", "Invalid argument: unknown"),
+    ("\n\n# c\nrun 5\nfix myfix all npt unknown 1 1 1\n", "at line: 5"),    # errors name the script line
+])
+def test_parser_errors_from_the_reference_test_module(tmp_path, script, needle):
+    assert needle in check(tmp_path, script, expect_fail=True)
+
+
+def test_statements_from_the_reference_test_module(tmp_path):
+    """The success cases of src/tests/command_tests.rs through the script reader."""
+    assert check(tmp_path, "timestep 0.001\n")["timestep"] == 0.001                                  # timestep_sets_value_on_ctx
+    assert check(tmp_path, "run 5000\n")["steps"] == 5000                                            # runsteps_sets_value_on_ctx
+    v = check(tmp_path, "velocity all create 300.0 42\n")["velocity"]                                # velocity_create_minimal_sets_ctx
+    assert v["group"] == "all" and v["temperature"] == 300 and v["seed"] == 42 and "dist" not in v
+    assert check(tmp_path, "velocity all create 300.0\n")["velocity"]["seed"] == 0                   # ..._without_seed_ctx
+    for dist in ("gaussian", "uniform"):                                                             # velocity_create_dist_keyword_sets_distribution
+        assert check(tmp_path, f"velocity all create 300.0 42 dist {dist}\n")["velocity"]["dist"] == dist
+    v = check(tmp_path, "velocity all create 300.0 dist gaussian\n")["velocity"]                     # ..._without_seed
+    assert v["seed"] == 0 and v["dist"] == "gaussian"
+    d = check(tmp_path, "dump my_dump all atom 100 output.lammpstrj\n")["dump"]                      # dump_sets_all_fields_on_ctx
+    assert d == {"name": "my_dump", "group": "all", "style": "atom", "dump_step": 100, "file_name": "output.lammpstrj"}
+    # pair_style stores its words verbatim and pair_coeff appends to it (pair_style_stores_args_in_ctx, pair_coeff_appends_...)
+    p = check(tmp_path, "pair_style lj/cut 10.0\npair_coeff 1 1 0.238 3.405\npair_coeff 1 2 0.1 3.0 9.0\n")["potential"]
+    assert p["max_rcut"] == 10 and [(q["i"], q["j"], q["rcut"]) for q in p["pairs"]] == [(1, 1, 10), (1, 2, 9)]
+    # fix_nvt_temp_keyword_sets_nh_chain_args / fix_npt_sets_both_barostat_and_thermostat
+    assert check(tmp_path, "fix myfix all nvt temp 300.0 300.0 0.1\n")["ensemble"] == "NVT"
+    assert check(tmp_path, "fix myfix all npt temp 300.0 300.0 0.1 iso 1.0 1.0 1.0\n")["ensemble"] == "NPT"
+
+
+def test_two_type_data_file(tmp_path):
+    """The shape of the reference's example/data_run.txt: two atom types, two Masses rows, one PairCoeffs row per type."""
+    data = ("4 atoms\n2 atom types\n\n0.0 12.0 xlo xhi\n0.0 12.0 ylo yhi\n0.0 12.0 zlo zhi\n\nMasses\n1 39.948\n2 20.18\n\n"
+            "PairCoeffs\n1 0.238 3.405 8.5\n2 0.07 2.8\n\nAtoms\n1 1 1.0 1.0 1.0\n2 2 4.0 4.0 4.0\n4 2 7.0 7.5 8.0\n3 1 9.0 9.0 9.0\n")
+    ctx = check(tmp_path, "read_data data.txt\n", data)
+    a = ctx["atoms"]
+    assert a["n_atoms"] == 4 and a["n_types"] == 2 and a["masses"] == [39.948, 20.18] and a["types_head"] == [1, 2, 1, 2]
+    assert a["first_positions"][6:12] == [9, 9, 9, 7, 7.5, 8]                 # rows land at their ids, in any order
+    assert ctx["potential"]["pairs"] == [{"i": 1, "j": 1, "epsilon": 0.238, "sigma": 3.405, "rcut": 8.5},
+                                         {"i": 2, "j": 2, "epsilon": 0.07, "sigma": 2.8, "rcut": 7}]
+    assert "Atom type 3 out of range" in check(tmp_path, "read_data data.txt\n", data.replace("2 20.18", "3 20.18"), expect_fail=True)
+
+
 def test_velocity_command(tmp_path):
     ctx = check(tmp_path, "velocity all create 300.0 12345 dist gaussian\n")
     assert ctx["velocity"] == {"group": "all", "start_velocity": True, "temperature": 300, "seed": 12345, "dist": "gaussian"}
