@@ -297,8 +297,8 @@ def run_single(args):
         mgr.set_option(name, float(val))
     fv = options.get("force_variant", 0.0)   # mirrors pair_mode() / quad_mode() / fused_step_possible() of pisb_sim.cu
     pair = options.get("pair_lists", 1.0) != 0.0 and fv == 5.0
-    quad = not pair and (fv == 7.0 or (fv == 0.0 and n > 75000))
-    fused = options.get("fuse_vv", 1.0) != 0.0 and (pair or quad or fv == 3.0)
+    quad = not pair and fv == 7.0
+    fused = options.get("fuse_vv", 1.0) != 0.0 and (pair or quad or fv == 3.0 or (fv == 0.0 and n > 75000))
     mgr.attach(atoms)
     mgr.compute()
     stream = torch.cuda.ExternalStream(mgr.stream_ptr)

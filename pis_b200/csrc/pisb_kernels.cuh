@@ -985,6 +985,7 @@ struct Force2Args {
     pisb_thermo *thermo;
     const int *skip_flag;  // multi-GPU: the launch is speculative and returns at once if *skip_flag != 0 (a rebuild comes first)
     const int *unwrapped;  // FLAG_UNWRAPPED word of the position buffer xt: non-zero => no interior shortcut
+    cudaTextureObject_t xt_tex;  // experiment (option tex_gather): xt as a linear int4 texture, two texels per record
 };
 
 // One in-range pair, reference operation order (bit-identical per-pair terms).
@@ -1184,7 +1185,14 @@ __device__ __noinline__ void force_atom_exact(const double4 *__restrict__ xt, co
 
 // One thread per atom: the list is read as one int4 per 4 neighbours and prefetched one tile ahead (the index stream
 // comes from DRAM), four 256-bit gathers are in flight per thread, interior warps skip the image search.
-template <bool MULTI, bool IMAGE>
+// TEXM (experiment, option tex_gather): 1 = every other neighbour gather goes through the TEXTURE data pipe of L1TEX
+// (two int4 texel fetches per record) instead of the LSU data pipe that binds the loop, 2 = all of them.
+__device__ __forceinline__ double4 tex_d4(cudaTextureObject_t t, int j) {
+    const int4 lo = tex1Dfetch<int4>(t, 2 * j), hi = tex1Dfetch<int4>(t, 2 * j + 1);
+    return make_double4(__hiloint2double(lo.y, lo.x), __hiloint2double(lo.w, lo.z), __hiloint2double(hi.y, hi.x), __hiloint2double(hi.w, hi.z));
+}
+
+template <bool MULTI, bool IMAGE, int TEXM = 0>
 __device__ __forceinline__ void force3_body(const Force2Args &a, int i, double &fx, double &fy, double &fz, double &pe,
                                             double &vir) {
     const double4 xi = a.xt[i];
@@ -1206,7 +1214,7 @@ __device__ __forceinline__ void force3_body(const Force2Args &a, int i, double &
             if (!in[u]) j[u] = 0;  // the tail of the last tile is not written by the build: any valid slot (a constant keeps `i` out of the loop's registers)
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) xj[u] = ldg_d4(&a.xt[j[u]]);
+        for (int u = 0; u < 4; ++u) xj[u] = (TEXM == 2 || (TEXM == 1 && (u & 1))) ? tex_d4(a.xt_tex, j[u]) : ldg_d4(&a.xt[j[u]]);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             double dx, dy, dz;
@@ -1294,7 +1302,7 @@ struct ForceVVArgs {
 // BRICK: the multi-GPU form -- ghost slots are skipped (the halo exchange fills them) and the launch may be speculative
 // (skip_flag).  A template parameter, not a run-time test: with the two extra live values the single-GPU kernel's force loop
 // picked up a spill store + load per K-tile (ptxas: 8 -> 24 bytes, inside the loop), on the L1TEX path that bounds it.
-template <bool MULTI, bool DRIFT, bool BRICK>
+template <bool MULTI, bool DRIFT, bool BRICK, int TEXM = 0>
 __global__ void __launch_bounds__(TPB_FORCE, 8) k_force_vv(ForceVVArgs b) {
     const Force2Args &a = b.f;
     if (BRICK && a.skip_flag && *a.skip_flag != 0) return;  // speculative launch, a rebuild comes first
@@ -1311,8 +1319,8 @@ __global__ void __launch_bounds__(TPB_FORCE, 8) k_force_vv(ForceVVArgs b) {
     const bool warp_interior = __all_sync(0xffffffffu, interior);
     if (active) {
         double fx = 0.0, fy = 0.0, fz = 0.0, pe = 0.0, vir = 0.0;
-        if (warp_interior) force3_body<MULTI, false>(a, i, fx, fy, fz, pe, vir);
-        else force3_body<MULTI, true>(a, i, fx, fy, fz, pe, vir);
+        if (warp_interior) force3_body<MULTI, false, TEXM>(a, i, fx, fy, fz, pe, vir);
+        else force3_body<MULTI, true, TEXM>(a, i, fx, fy, fz, pe, vir);
         a.fx[i] = fx;
         a.fy[i] = fy;
         a.fz[i] = fz;

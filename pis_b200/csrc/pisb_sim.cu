@@ -79,6 +79,10 @@ struct pisb_handle {
     int cell_div = 0;  // cells per list cutoff per dimension: 0 = auto, 1 = reference-sized cells, 2 = half-size cells
     int fuse_vv = 1;   // option "fuse_vv": NVE batches run k_force_vv (force + kick + drift in one launch) when the default force kernel applies
     int pair_lists = 1;  // option "pair_lists": two atoms per thread with a three-section list (pisb_pairlist.cuh) for large single-type systems
+    int tex_gather = 0;  // option "tex_gather" (experiment): 1 = every other neighbour gather through the texture pipe, 2 = all
+    cudaTextureObject_t tex_obj[2] = {0, 0};  // linear int4 textures over the two position buffers
+    const void *tex_ptr[2] = {nullptr, nullptr};
+    size_t tex_cap[2] = {0, 0};
     DevBuf<int4> pl_counts;
 
     // box / grid
@@ -340,9 +344,31 @@ bool pair_mode(const pisb_t *h) {
     return h->force_variant == 5;
 }
 
-// Systems large enough to fill the GPU (and force_variant 7 at any size) run k_force_q: four lanes per atom on the per-atom list.
-bool quad_mode(const pisb_t *h) {
-    return v2_possible(h) && !pair_mode(h) && (h->force_variant == 7 || (h->force_variant == 0 && h->n > 75000));
+// force_variant 7: k_force_q, four lanes per atom on the per-atom list.  Measured SLOWER than one thread per atom at 4M atoms
+// (1.67 against 1.18 ms: 40 % more instructions for the same L1 data-pipe wavefronts, profiles/r02_force_q.*); selectable only.
+bool quad_mode(const pisb_t *h) { return v2_possible(h) && !pair_mode(h) && h->force_variant == 7; }
+
+// linear int4 texture over the current position buffer (two texels per 32-byte record), created on first use
+cudaTextureObject_t position_texture(pisb_t *h) {
+    const int k = h->xt_flag == FLAG_UNWRAPPED_A ? 0 : 1;
+    if (h->tex_ptr[k] != h->xt.p || h->tex_cap[k] != h->xt.cap) {
+        if (h->tex_obj[k]) cudaDestroyTextureObject(h->tex_obj[k]);
+        h->tex_obj[k] = 0;
+        cudaResourceDesc rd{};
+        rd.resType = cudaResourceTypeLinear;
+        rd.res.linear.devPtr = h->xt.p;
+        rd.res.linear.desc = cudaCreateChannelDesc<int4>();
+        rd.res.linear.sizeInBytes = h->xt.cap * sizeof(double4);
+        cudaTextureDesc td{};
+        td.readMode = cudaReadModeElementType;
+        if (cudaCreateTextureObject(&h->tex_obj[k], &rd, &td, nullptr) != cudaSuccess) {
+            cudaGetLastError();
+            h->tex_obj[k] = 0;
+        }
+        h->tex_ptr[k] = h->xt.p;
+        h->tex_cap[k] = h->xt.cap;
+    }
+    return h->tex_obj[k];
 }
 
 int pair_threads_padded(const pisb_t *h) { return ((h->npad + 1) / 2 + 31) / 32 * 32; }
@@ -669,7 +695,7 @@ int launch_force(pisb_t *h, double *const out[3], const double *const acc[3], pi
         if (!v2_possible(h)) return fail(h, PISB_ERR_INVALID, "force_variant 2/3 needs an orthorhombic, fully periodic box");
         Force2Args f2{h->n, h->npad, h->xt.p, h->xf.p, h->nbr.p, h->nnbr.p, h->box, h->boxf, h->pairs[0], h->pairsf[0],
                       h->table_d.p, h->tablef_d.p, h->n_types, fa.ax, fa.ay, fa.az, out[0], out[1], out[2],
-                      h->partials.p, h->ticket, rec, skip_flag, h->flags + h->xt_flag};
+                      h->partials.p, h->ticket, rec, skip_flag, h->flags + h->xt_flag, 0};
         if (pair_mode(h)) {  // two atoms per thread (pisb_pairlist.cuh)
             ForceVVArgs fv{};
             fv.f = f2;
@@ -769,7 +795,7 @@ int launch_vv(pisb_t *h, bool kick, bool drift, double dt, pisb_thermo *rec, con
 bool fused_step_possible(const pisb_t *h, bool multi_path = false) {
     if (!h->fuse_vv || h->multi != multi_path || !v2_possible(h)) return false;
     if (pair_mode(h) || quad_mode(h)) return true;
-    return h->force_variant == 3;
+    return (h->force_variant == 0 || h->force_variant == 3) && (h->force_variant == 3 || h->n > 75000);
 }
 
 // F(t+dt) -> g, kick with F(t) = f, [drift into the other position buffer], then f <-> g (and the position buffers).
@@ -780,7 +806,7 @@ int launch_force_vv(pisb_t *h, bool drift, double dt, pisb_thermo *rec, const in
         const double hs = 0.5 * h->skin;
         ForceVVArgs fv{Force2Args{h->n, h->npad, h->xt.p, h->xf.p, h->nbr.p, h->nnbr.p, h->box, h->boxf, h->pairs[0], h->pairsf[0],
                                   h->table_d.p, h->tablef_d.p, h->n_types, nullptr, nullptr, nullptr, h->g[0].p, h->g[1].p, h->g[2].p,
-                                  h->partials.p, h->ticket, rec, skip_flag, h->flags + h->xt_flag},
+                                  h->partials.p, h->ticket, rec, skip_flag, h->flags + h->xt_flag, 0},
                        h->v[0].p, h->v[1].p, h->v[2].p, h->f[0].p, h->f[1].p, h->f[2].p, h->xb[0].p, h->xb[1].p, h->xb[2].p,
                        h->mass_d.p, h->s_xt.p, h->xf2.p, dt, dt * dt,
                        h->skin_half2_override >= 0.0 ? h->skin_half2_override : hs * hs,
@@ -813,6 +839,15 @@ int launch_force_vv(pisb_t *h, bool drift, double dt, pisb_thermo *rec, const in
                 else FQ(false, false);
             }
 #undef FQ
+        } else if (h->tex_gather && !multi && !h->multi && position_texture(h)) {  // experiment: gathers through the texture pipe
+            fv.f.xt_tex = position_texture(h);
+            if (h->tex_gather == 1) {
+                if (drift) k_force_vv<false, true, false, 1><<<nb, TPB_FORCE, 0, st>>>(fv);
+                else k_force_vv<false, false, false, 1><<<nb, TPB_FORCE, 0, st>>>(fv);
+            } else {
+                if (drift) k_force_vv<false, true, false, 2><<<nb, TPB_FORCE, 0, st>>>(fv);
+                else k_force_vv<false, false, false, 2><<<nb, TPB_FORCE, 0, st>>>(fv);
+            }
         } else {
 #define FVV(T, D)                                                              \
     do {                                                                       \
@@ -1116,7 +1151,7 @@ void graph_signature(pisb_t *h, double dt, std::vector<unsigned char> &sig) {
                           h->nhc_energy_d.p};
     put(ptrs, sizeof ptrs);
     const int ints[] = {h->n, h->npad, h->kcap, h->n_types, h->force_variant, h->build_variant, h->cell_div, h->fuse_vv, h->pair_lists,
-                        pair_mode(h) ? 1 : 0, quad_mode(h) ? 1 : 0};
+                        pair_mode(h) ? 1 : 0, quad_mode(h) ? 1 : 0, h->tex_gather};
     put(&h->pl_counts.p, sizeof(void *));
     put(ints, sizeof ints);
     const double dbl[] = {dt, h->skin, h->skin_half2_override, h->max_rcut};
@@ -2192,6 +2227,8 @@ int pisb_destroy(pisb_t *h) {
     dev_free(h, h->nnbr);
     dev_free(h, h->nbr);
     dev_free(h, h->pl_counts);
+    for (int k = 0; k < 2; ++k)
+        if (h->tex_obj[k]) cudaDestroyTextureObject(h->tex_obj[k]);
     dev_free(h, h->cell_count);
     dev_free(h, h->cell_start);
     dev_free(h, h->tile_sum);
@@ -2874,6 +2911,10 @@ int pisb_set_option(pisb_t *h, const char *name, double value) {
     }
     if (!std::strcmp(name, "fuse_vv")) {
         h->fuse_vv = value != 0.0 ? 1 : 0;
+        return PISB_OK;
+    }
+    if (!std::strcmp(name, "tex_gather")) {
+        h->tex_gather = (int)value;
         return PISB_OK;
     }
     if (!std::strcmp(name, "force_variant") || !std::strcmp(name, "pair_lists")) {

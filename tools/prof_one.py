@@ -20,6 +20,7 @@ for kv in sys.argv[7:]:   # further library options name=value, e.g. cuda_graphs
 m.attach(atoms)
 m.compute()
 m.step_nve(0.25, steps)
-m.invalidate_list()
-m.compute()
+for _ in range(3):   # three full rebuild chains on the disordered state: launches steps+1 .. steps+3 of the build kernel are real builds
+    m.invalidate_list()
+    m.compute()
 print(m.stats())
