@@ -247,8 +247,8 @@ PISB_API int pisb_owned_ids(pisb_t *h, int64_t cap, int32_t *global_ids, int64_t
 
 /* What the current Verlet list holds (built first if need be), counted on the device: out3[0] = listed pairs (sum of the
  * per-atom row lengths, each pair twice: a full list), out3[1] = of those, pairs inside the cutoff at the current
- * positions (`rij.norm() > rcut -> skip`, lennard_jones.rs:224), out3[2] = index words stored (the pair lists of large
- * systems store the common neighbours of two atoms once).  Multi-GPU: this rank's owned atoms. */
+ * positions (`rij.norm() > rcut -> skip`, lennard_jones.rs:224), out3[2] = index words stored (== out3[0] for per-atom
+ * rows).  Multi-GPU: this rank's owned atoms. */
 PISB_API int pisb_list_stats(pisb_t *h, int64_t *out3);
 
 /* Options (all have working defaults; the kernel selectors exist for A/B measurements and the parity tests):
@@ -258,14 +258,11 @@ PISB_API int pisb_list_stats(pisb_t *h, int64_t *out3);
  *                     force pass with the velocity-Verlet kick + drift in its epilogue; 0 = k_force_v3 + k_vv
  *   host_pipeline     1 (default) = pisb_verlet_step_nve_host moves x, v, F in chunks and pipelines upload, drift and
  *                     download; 0 = whole-array copies.  host_chunk_atoms = atoms per chunk, 0 = n/8 (>= 65536)
- *   force_variant     0 = automatic (thread per atom (v3) above 75k atoms; 8 or 4 lanes per atom below 32k / 75k atoms;
- *                     v1 for a triclinic or non-periodic box), 1 = v1 general all-FP64 in the reference's operation order,
- *                     2 = FP32 pre-filter + queue, 3 = v3 thread per atom, 4 = TMA-staged shared-memory tile (prototype),
- *                     5 = two atoms per thread with a three-section pair list, 6 = 8 lanes per atom, 7 = 4 lanes per atom
- *                     taking one entry of every K-tile each (5 and 7: measured slower at 4M atoms, kept for the A/B record)
- *   pair_lists        1 (default) = allow the two-atoms-per-thread path (csrc/pisb_pairlist.cuh), 0 = per-atom lists only
- *   tex_gather        experiment: 0 (default) = neighbour gathers through the LSU path, 1 = every other one through the
- *                     texture path, 2 = all of them
+ *   force_variant     0 = automatic (v1 for a triclinic or non-periodic box; otherwise by size),
+ *                     1 = v1 general all-FP64 in the reference's operation order, 2 = FP32 pre-filter + queue,
+ *                     3 = v3 thread per atom, 4 = TMA-staged shared-memory cell-row tile (round-1 prototype),
+ *                     6 = 8 lanes per atom (whole K-tiles per lane), 7 = 4 lanes per atom taking one entry of every K-tile
+ *                     each (k_force_q), 8 = one block per brick of cells with shared-memory gathers (k_force_tile)
  *   build_variant     0 = automatic (v3), 1 = v1 general, 2 = scalar FP32 pre-filter, 3 = packed-FP32 pair records
  *   cell_div          cells per list cutoff and dimension: 0 = automatic (2 with build_variant 2/3), 1, 2
  *   halo_mode         multi-GPU per-step ghost exchange: 0 = peer memory when it can be mapped, 1 = NCCL send/recv,

@@ -14,7 +14,6 @@
 
 #include "pisb200.h"
 #include "pisb_kernels.cuh"
-#include "pisb_pairlist.cuh"
 #include "pisb_multi.cuh"
 #include "pisb_npt.cuh"
 
@@ -78,12 +77,7 @@ struct pisb_handle {
     int build_variant = 0;
     int cell_div = 0;  // cells per list cutoff per dimension: 0 = auto, 1 = reference-sized cells, 2 = half-size cells
     int fuse_vv = 1;   // option "fuse_vv": NVE batches run k_force_vv (force + kick + drift in one launch) when the default force kernel applies
-    int pair_lists = 1;  // option "pair_lists": two atoms per thread with a three-section list (pisb_pairlist.cuh) for large single-type systems
-    int tex_gather = 0;  // option "tex_gather" (experiment): 1 = every other neighbour gather through the texture pipe, 2 = all
-    cudaTextureObject_t tex_obj[2] = {0, 0};  // linear int4 textures over the two position buffers
-    const void *tex_ptr[2] = {nullptr, nullptr};
-    size_t tex_cap[2] = {0, 0};
-    DevBuf<int4> pl_counts;
+    int tile_halo_ok = 0;  // setup_grid: the grid suits k_force_tile (symmetric stencil, brick rows fit the tile tables)
 
     // box / grid
     BoxDev box{};
@@ -336,53 +330,27 @@ bool v2_possible(const pisb_t *h) {
     return h->have_box && h->box.ortho && h->box.pbc[0] && h->box.pbc[1] && h->box.pbc[2];
 }
 
-// force_variant 5: two atoms per thread with a three-section pair list (pisb_pairlist.cuh).  Measured SLOWER than the
-// per-atom list at 4M atoms (1.55 ms per step kernel launch): kept selectable for the A/B record and its tests, never automatic.
-bool pair_mode(const pisb_t *h) {
-    if (!v2_possible(h) || h->n_types != 1 || !h->pair_lists) return false;
-    if (!(h->build_variant == 0 || h->build_variant == 3)) return false;
-    return h->force_variant == 5;
-}
-
 // force_variant 7: k_force_q, four lanes per atom on the per-atom list.  Measured SLOWER than one thread per atom at 4M atoms
 // (1.67 against 1.18 ms: 40 % more instructions for the same L1 data-pipe wavefronts, profiles/r02_force_q.*); selectable only.
-bool quad_mode(const pisb_t *h) { return v2_possible(h) && !pair_mode(h) && h->force_variant == 7; }
+bool quad_mode(const pisb_t *h) { return v2_possible(h) && h->force_variant == 7; }
 
-// linear int4 texture over the current position buffer (two texels per 32-byte record), created on first use
-cudaTextureObject_t position_texture(pisb_t *h) {
-    const int k = h->xt_flag == FLAG_UNWRAPPED_A ? 0 : 1;
-    if (h->tex_ptr[k] != h->xt.p || h->tex_cap[k] != h->xt.cap) {
-        if (h->tex_obj[k]) cudaDestroyTextureObject(h->tex_obj[k]);
-        h->tex_obj[k] = 0;
-        cudaResourceDesc rd{};
-        rd.resType = cudaResourceTypeLinear;
-        rd.res.linear.devPtr = h->xt.p;
-        rd.res.linear.desc = cudaCreateChannelDesc<int4>();
-        rd.res.linear.sizeInBytes = h->xt.cap * sizeof(double4);
-        cudaTextureDesc td{};
-        td.readMode = cudaReadModeElementType;
-        if (cudaCreateTextureObject(&h->tex_obj[k], &rd, &td, nullptr) != cudaSuccess) {
-            cudaGetLastError();
-            h->tex_obj[k] = 0;
-        }
-        h->tex_ptr[k] = h->xt.p;
-        h->tex_cap[k] = h->xt.cap;
-    }
-    return h->tex_obj[k];
+// k_force_tile: one block per brick of cells, neighbour positions gathered from shared memory (force_variant 8; single type).
+bool tile_mode(const pisb_t *h) {
+    return v2_possible(h) && h->n_types == 1 && h->tile_halo_ok && h->force_variant == 8;
 }
 
-int pair_threads_padded(const pisb_t *h) { return ((h->npad + 1) / 2 + 31) / 32 * 32; }
+TileArgs tile_args(const pisb_t *h) {
+    TileArgs t{};
+    t.cell_start = h->cell_start.p;
+    t.g = h->grid;
+    t.edge = 2 * h->grid.hi[0];
+    for (int d = 0; d < 3; ++d) t.nb[d] = (h->grid.n[d] + t.edge - 1) / t.edge;
+    return t;
+}
 
-PairListArgs pair_list_args(const pisb_t *h) {
-    PairListArgs pl{};
-    pl.npp = pair_threads_padded(h);
-    pl.kcap = h->kcap;
-    const size_t sec = (size_t)h->kcap * (size_t)pl.npp;
-    pl.both = h->nbr.p;
-    pl.only_a = h->nbr.p + sec;
-    pl.only_b = h->nbr.p + 2 * sec;
-    pl.counts = h->pl_counts.p;
-    return pl;
+int tile_blocks(const pisb_t *h) {
+    const TileArgs t = tile_args(h);
+    return t.nb[0] * t.nb[1] * t.nb[2];
 }
 
 int setup_filter(pisb_t *h) {
@@ -523,6 +491,13 @@ int setup_grid(pisb_t *h) {
         }
     }
     g.ncell = g.n[0] * g.n[1] * g.n[2];
+    // k_force_tile needs one symmetric stencil reach r in every dimension, bricks of (2r)^3 cells whose (4r)^2 rows fit its tables
+    h->tile_halo_ok = 1;
+    for (int d = 0; d < 3; ++d)
+        if (g.hi[d] != g.hi[0] || g.lo[d] != -g.hi[0] || g.hi[0] < 1 || g.hi[0] > 2) h->tile_halo_ok = 0;
+    if ((int64_t)((g.n[0] + 2 * g.hi[0] - 1) / (2 * std::max(g.hi[0], 1))) * ((g.n[1] + 2 * g.hi[0] - 1) / (2 * std::max(g.hi[0], 1))) *
+            ((g.n[2] + 2 * g.hi[0] - 1) / (2 * std::max(g.hi[0], 1))) > (int64_t)h->n / 8 + 4096)
+        h->tile_halo_ok = 0;  // more bricks than the reduction buffers were sized for (very dilute systems)
     h->grid = g;
     TRY(dev_reserve(h, h->cell_count, (size_t)g.ncell + 2));
     TRY(dev_reserve(h, h->cell_start, (size_t)g.ncell + 2));
@@ -574,8 +549,9 @@ int reserve_atoms(pisb_t *h, int n) {
     auto need = [](size_t nq, size_t blocks) { return nq * (blocks + red_groups((unsigned int)blocks) + 2); };
     const size_t b_force = (size_t)nblk(n, TPB_FORCE), b_stream = (size_t)nblk(n, TPB), b_split = (size_t)nblk(std::min(n, 75000) * 8, TPB_FORCE);
     const size_t b_quad = ((size_t)n * 4 + TPB_Q - 1) / TPB_Q;  // k_force_q: four lanes per atom, 6 quantities
-    TRY(dev_reserve(h, h->partials, std::max(std::max(need(6, b_force), need(6, b_quad)), std::max(need(19, b_stream), need(2, b_split)))));
-    const size_t tickets = 2 + red_groups((unsigned int)std::max(std::max(b_force, b_quad), b_split));
+    const size_t b_tile = (size_t)n / 8 + 4096;                  // k_force_tile: one block per brick of >= 8 cells, cells <= 4 n + 1024
+    TRY(dev_reserve(h, h->partials, std::max(std::max(need(6, std::max(b_force, b_tile)), need(6, b_quad)), std::max(need(19, b_stream), need(2, b_split)))));
+    const size_t tickets = 2 + red_groups((unsigned int)std::max(std::max(std::max(b_force, b_tile), b_quad), b_split));
     if (tickets > h->ticket_cap) {
         // zero-initialised once; the words reset themselves at the end of every reduction
         CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -591,10 +567,7 @@ int reserve_atoms(pisb_t *h, int n) {
 int reserve_list(pisb_t *h) {
     h->npad = (std::max(h->n, h->ncap_atoms) + 31) / 32 * 32;
     h->kcap = (h->kcap + 3) / 4 * 4;  // whole K-tiles of 4
-    // room for either list form: per-atom rows [kcap][npad], or the three sections of the pair lists [3][kcap][npp]
-    const size_t npp = (size_t)pair_threads_padded(h);
-    TRY(dev_reserve(h, h->nbr, std::max((size_t)h->kcap * (size_t)h->npad, 3 * (size_t)h->kcap * npp)));
-    TRY(dev_reserve(h, h->pl_counts, npp));
+    TRY(dev_reserve(h, h->nbr, (size_t)h->kcap * (size_t)h->npad));
     return PISB_OK;
 }
 
@@ -659,9 +632,7 @@ int launch_rebuild_chain(pisb_t *h) {
             if (!v2_possible(h)) return fail(h, PISB_ERR_INVALID, "build_variant 2/3 needs an orthorhombic, fully periodic box");
             Build2Args b2{n, h->npad, h->kcap, h->xt.p, h->xf.p, h->cell_start.p, h->box, h->boxf, g, h->pairs[0],
                           h->pairsf[0], h->table_d.p, h->tablef_d.p, h->n_types, h->nbr.p, h->nnbr.p, h->flags};
-            if (pair_mode(h)) {  // two atoms per thread, three-section list
-                k_build_pairs<<<nblk((n + 1) / 2, TPB_FORCE), TPB_FORCE, 0, st>>>(b2, pair_list_args(h), h->xp.p);
-            } else if (h->build_variant == 2) {  // v2: scalar FP32 pre-filter (kept for A/B)
+            if (h->build_variant == 2) {  // v2: scalar FP32 pre-filter (kept for A/B)
                 if (multi) k_build_list_v2<true><<<nb, TPB_FORCE, 0, st>>>(b2);
                 else k_build_list_v2<false><<<nb, TPB_FORCE, 0, st>>>(b2);
             } else {  // default: v3, packed FP32 pair records + bit-mask append for interior warps
@@ -681,6 +652,21 @@ int launch_rebuild_chain(pisb_t *h) {
     return check_launch(h, "rebuild chain");
 }
 
+// k_force_tile's shared-memory block exceeds the 48 KB default: opt in once per instantiation
+int tile_smem_opt_in(pisb_t *h) {
+    static bool done = false;
+    if (done) return PISB_OK;
+    const int bytes = (int)sizeof(TileSmem);
+    CUDA_TRY(h, cudaFuncSetAttribute(k_force_tile<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_force_tile<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_force_tile<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_force_tile<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_force_tile<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_force_tile<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    done = true;
+    return PISB_OK;
+}
+
 // f_out = (acc ? acc + LJ : LJ); thermo record gets pe and virial_pair.
 int launch_force(pisb_t *h, double *const out[3], const double *const acc[3], pisb_thermo *rec, const int *skip_flag = nullptr) {
     LaunchScope ls(h, PISB_K_FORCE);
@@ -695,15 +681,15 @@ int launch_force(pisb_t *h, double *const out[3], const double *const acc[3], pi
         if (!v2_possible(h)) return fail(h, PISB_ERR_INVALID, "force_variant 2/3 needs an orthorhombic, fully periodic box");
         Force2Args f2{h->n, h->npad, h->xt.p, h->xf.p, h->nbr.p, h->nnbr.p, h->box, h->boxf, h->pairs[0], h->pairsf[0],
                       h->table_d.p, h->tablef_d.p, h->n_types, fa.ax, fa.ay, fa.az, out[0], out[1], out[2],
-                      h->partials.p, h->ticket, rec, skip_flag, h->flags + h->xt_flag, 0};
-        if (pair_mode(h)) {  // two atoms per thread (pisb_pairlist.cuh)
+                      h->partials.p, h->ticket, rec, skip_flag, h->flags + h->xt_flag};
+        if (tile_mode(h)) {  // one block per brick, shared-memory gathers
             ForceVVArgs fv{};
             fv.f = f2;
             fv.flags = h->flags;
-            const int nbp = nblk((h->n + 1) / 2, TPB_FORCE);
-            if (h->multi) k_pforce<false, false, true><<<nbp, TPB_FORCE, 0, st>>>(fv, pair_list_args(h));
-            else k_pforce<false, false, false><<<nbp, TPB_FORCE, 0, st>>>(fv, pair_list_args(h));
-            return check_launch(h, "k_pforce");
+            TRY(tile_smem_opt_in(h));
+            if (h->multi) k_force_tile<false, false, true><<<tile_blocks(h), TILE_TPB, sizeof(TileSmem), st>>>(fv, tile_args(h));
+            else k_force_tile<false, false, false><<<tile_blocks(h), TILE_TPB, sizeof(TileSmem), st>>>(fv, tile_args(h));
+            return check_launch(h, "k_force_tile");
         }
         if (quad_mode(h)) {  // four lanes per atom
             ForceVVArgs fv{};
@@ -794,7 +780,7 @@ int launch_vv(pisb_t *h, bool kick, bool drift, double dt, pisb_thermo *rec, con
 // atom) run one k_force_vv launch per step instead of k_force_v3 + k_vv.
 bool fused_step_possible(const pisb_t *h, bool multi_path = false) {
     if (!h->fuse_vv || h->multi != multi_path || !v2_possible(h)) return false;
-    if (pair_mode(h) || quad_mode(h)) return true;
+    if (quad_mode(h) || tile_mode(h)) return true;
     return (h->force_variant == 0 || h->force_variant == 3) && (h->force_variant == 3 || h->n > 75000);
 }
 
@@ -806,7 +792,7 @@ int launch_force_vv(pisb_t *h, bool drift, double dt, pisb_thermo *rec, const in
         const double hs = 0.5 * h->skin;
         ForceVVArgs fv{Force2Args{h->n, h->npad, h->xt.p, h->xf.p, h->nbr.p, h->nnbr.p, h->box, h->boxf, h->pairs[0], h->pairsf[0],
                                   h->table_d.p, h->tablef_d.p, h->n_types, nullptr, nullptr, nullptr, h->g[0].p, h->g[1].p, h->g[2].p,
-                                  h->partials.p, h->ticket, rec, skip_flag, h->flags + h->xt_flag, 0},
+                                  h->partials.p, h->ticket, rec, skip_flag, h->flags + h->xt_flag},
                        h->v[0].p, h->v[1].p, h->v[2].p, h->f[0].p, h->f[1].p, h->f[2].p, h->xb[0].p, h->xb[1].p, h->xb[2].p,
                        h->mass_d.p, h->s_xt.p, h->xf2.p, dt, dt * dt,
                        h->skin_half2_override >= 0.0 ? h->skin_half2_override : hs * hs,
@@ -814,15 +800,16 @@ int launch_force_vv(pisb_t *h, bool drift, double dt, pisb_thermo *rec, const in
         const bool multi = h->n_types > 1;
         const int nb = nblk(h->n, TPB_FORCE);
         cudaStream_t st = h->stream;
-        if (pair_mode(h)) {
-            const int nbp = nblk((h->n + 1) / 2, TPB_FORCE);
-            const PairListArgs pl = pair_list_args(h);
+        if (tile_mode(h)) {
+            TRY(tile_smem_opt_in(h));
+            const int nbt = tile_blocks(h);
+            const TileArgs ta = tile_args(h);
             if (drift) {
-                if (h->multi) k_pforce<true, true, true><<<nbp, TPB_FORCE, 0, st>>>(fv, pl);
-                else k_pforce<true, true, false><<<nbp, TPB_FORCE, 0, st>>>(fv, pl);
+                if (h->multi) k_force_tile<true, true, true><<<nbt, TILE_TPB, sizeof(TileSmem), st>>>(fv, ta);
+                else k_force_tile<true, true, false><<<nbt, TILE_TPB, sizeof(TileSmem), st>>>(fv, ta);
             } else {
-                if (h->multi) k_pforce<true, false, true><<<nbp, TPB_FORCE, 0, st>>>(fv, pl);
-                else k_pforce<true, false, false><<<nbp, TPB_FORCE, 0, st>>>(fv, pl);
+                if (h->multi) k_force_tile<true, false, true><<<nbt, TILE_TPB, sizeof(TileSmem), st>>>(fv, ta);
+                else k_force_tile<true, false, false><<<nbt, TILE_TPB, sizeof(TileSmem), st>>>(fv, ta);
             }
         } else if (quad_mode(h)) {
             const unsigned nbq = (unsigned)(((size_t)h->n * 4 + TPB_Q - 1) / TPB_Q);
@@ -839,15 +826,6 @@ int launch_force_vv(pisb_t *h, bool drift, double dt, pisb_thermo *rec, const in
                 else FQ(false, false);
             }
 #undef FQ
-        } else if (h->tex_gather && !multi && !h->multi && position_texture(h)) {  // experiment: gathers through the texture pipe
-            fv.f.xt_tex = position_texture(h);
-            if (h->tex_gather == 1) {
-                if (drift) k_force_vv<false, true, false, 1><<<nb, TPB_FORCE, 0, st>>>(fv);
-                else k_force_vv<false, false, false, 1><<<nb, TPB_FORCE, 0, st>>>(fv);
-            } else {
-                if (drift) k_force_vv<false, true, false, 2><<<nb, TPB_FORCE, 0, st>>>(fv);
-                else k_force_vv<false, false, false, 2><<<nb, TPB_FORCE, 0, st>>>(fv);
-            }
         } else {
 #define FVV(T, D)                                                              \
     do {                                                                       \
@@ -1150,9 +1128,8 @@ void graph_signature(pisb_t *h, double dt, std::vector<unsigned char> &sig) {
                           h->tile_sum.p, h->mass_d.p, h->partials.p, h->table_d.p, h->thermo_d.p, h->flags, h->ticket, h->nhc_d.p,
                           h->nhc_energy_d.p};
     put(ptrs, sizeof ptrs);
-    const int ints[] = {h->n, h->npad, h->kcap, h->n_types, h->force_variant, h->build_variant, h->cell_div, h->fuse_vv, h->pair_lists,
-                        pair_mode(h) ? 1 : 0, quad_mode(h) ? 1 : 0, h->tex_gather};
-    put(&h->pl_counts.p, sizeof(void *));
+    const int ints[] = {h->n, h->npad, h->kcap, h->n_types, h->force_variant, h->build_variant, h->cell_div, h->fuse_vv,
+                        quad_mode(h) ? 1 : 0, tile_mode(h) ? 1 : 0};
     put(ints, sizeof ints);
     const double dbl[] = {dt, h->skin, h->skin_half2_override, h->max_rcut};
     put(dbl, sizeof dbl);
@@ -2069,8 +2046,7 @@ int do_step_nve_multi(pisb_t *h, double dt, int64_t nsteps, pisb_thermo *out) {
             // The force kernel is launched BEFORE the host knows the decision: it returns at once if the (now global) rebuild
             // flag is set, and the flag travels to the host on a second stream meanwhile -- on the ~80 % of steps without a
             // rebuild the GPU never waits for the host round trip.
-            const bool speculate = v2_possible(h) && (h->force_variant == 0 || h->force_variant == 3 || h->force_variant == 5 || h->force_variant == 6 ||
-                                                      h->force_variant == 7);
+            const bool speculate = v2_possible(h) && (h->force_variant == 0 || h->force_variant == 3 || (h->force_variant >= 5 && h->force_variant <= 8));
             double *outp[3] = {h->g[0].p, h->g[1].p, h->g[2].p};
             if (speculate) {
                 if (fused)  // the decision word the speculative launch and the host read (see FLAG_DECISION)
@@ -2226,9 +2202,6 @@ int pisb_destroy(pisb_t *h) {
     dev_free(h, h->order);
     dev_free(h, h->nnbr);
     dev_free(h, h->nbr);
-    dev_free(h, h->pl_counts);
-    for (int k = 0; k < 2; ++k)
-        if (h->tex_obj[k]) cudaDestroyTextureObject(h->tex_obj[k]);
     dev_free(h, h->cell_count);
     dev_free(h, h->cell_start);
     dev_free(h, h->tile_sum);
@@ -2599,25 +2572,12 @@ int pisb_neighbours(pisb_t *h, int32_t *nnbr, int32_t *nbr, int64_t cap_per_atom
         TRY(ensure_list(h));
     }
     const int n = h->n;
-    // per-atom rows [kcap][npad], or the three sections of the pair lists [3][kcap][npp] (+ counts): entry(s, k) reads either
-    const bool pairs = pair_mode(h);
-    const PairListArgs pl = pairs ? pair_list_args(h) : PairListArgs{};
-    const size_t list_words = pairs ? 3 * (size_t)h->kcap * (size_t)pl.npp : (size_t)h->kcap * h->npad;
-    std::vector<int> hn(n), hid(n), hl(nbr ? list_words : 0);  // the list itself only when rows are wanted
-    std::vector<int4> hc(nbr && pairs ? (size_t)pl.npp : 0);
+    std::vector<int> hn(n), hid(n), hl(nbr ? (size_t)h->kcap * h->npad : 0);  // the list itself only when rows are wanted
     CUDA_TRY(h, cudaMemcpyAsync(hn.data(), h->nnbr.p, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(hid.data(), h->id.p, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
     if (nbr) CUDA_TRY(h, cudaMemcpyAsync(hl.data(), h->nbr.p, sizeof(int) * hl.size(), cudaMemcpyDeviceToHost, h->stream));
-    if (nbr && pairs) CUDA_TRY(h, cudaMemcpyAsync(hc.data(), h->pl_counts.p, sizeof(int4) * hc.size(), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-    const size_t sec = (size_t)h->kcap * (size_t)pl.npp;
-    auto entry = [&](int s, int k) -> int {
-        if (!pairs) return hl[nbr_at(k, s, h->npad)];
-        const int p = s >> 1;
-        const int nb = hc[p].x;  // BOTH first, then the atom's own section
-        if (k < nb) return hl[plist_at(k, p, pl.npp)];
-        return hl[(s & 1 ? 2 : 1) * sec + plist_at(k - nb, p, pl.npp)];
-    };
+    auto entry = [&](int s, int k) -> int { return hl[nbr_at(k, s, h->npad)]; };
     int64_t total = 0;
     if (h->multi) {
         // rows in owned-slot order (the order pisb_download_owned uses); entries are GLOBAL ids
@@ -2664,9 +2624,7 @@ int pisb_list_stats(pisb_t *h, int64_t *out3) {
     DevBuf<unsigned long long> d;
     TRY(dev_reserve(h, d, 4));
     CUDA_TRY(h, cudaMemsetAsync(d.p, 0, sizeof(unsigned long long) * 4, h->stream));
-    const bool pairs = pair_mode(h);
-    ListStatsArgs a{h->n, h->npad, pairs ? 1 : 0, h->xt.p, h->nbr.p, h->nnbr.p, pairs ? pair_list_args(h) : PairListArgs{}, h->box, h->pairs[0],
-                    h->table_d.p, h->n_types, d.p};
+    ListStatsArgs a{h->n, h->npad, h->xt.p, h->nbr.p, h->nnbr.p, h->box, h->pairs[0], h->table_d.p, h->n_types, d.p};
     if (h->box.ortho) k_list_stats<true><<<nblk(h->n, TPB), TPB, 0, h->stream>>>(a);
     else k_list_stats<false><<<nblk(h->n, TPB), TPB, 0, h->stream>>>(a);
     TRY(check_launch(h, "k_list_stats"));
@@ -2674,7 +2632,9 @@ int pisb_list_stats(pisb_t *h, int64_t *out3) {
     CUDA_TRY(h, cudaMemcpyAsync(host, d.p, sizeof host, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     dev_free(h, d);
-    for (int k = 0; k < 3; ++k) out3[k] = (int64_t)host[k];
+    out3[0] = (int64_t)host[0];
+    out3[1] = (int64_t)host[1];
+    out3[2] = (int64_t)host[0];  // index words stored == listed pairs for per-atom rows
     h->total_nbr = (int64_t)host[0];
     return PISB_OK;
 }
@@ -2913,14 +2873,8 @@ int pisb_set_option(pisb_t *h, const char *name, double value) {
         h->fuse_vv = value != 0.0 ? 1 : 0;
         return PISB_OK;
     }
-    if (!std::strcmp(name, "tex_gather")) {
-        h->tex_gather = (int)value;
-        return PISB_OK;
-    }
-    if (!std::strcmp(name, "force_variant") || !std::strcmp(name, "pair_lists")) {
-        if (name[0] == 'f') h->force_variant = (int)value;
-        else h->pair_lists = value != 0.0 ? 1 : 0;
-        h->list_valid = false;  // the list form (per-atom rows / pair sections) follows the force kernel
+    if (!std::strcmp(name, "force_variant")) {
+        h->force_variant = (int)value;
         return PISB_OK;
     }
     if (!std::strcmp(name, "build_variant") || !std::strcmp(name, "cell_div")) {
