@@ -254,15 +254,14 @@ PISB_API int pisb_list_stats(pisb_t *h, int64_t *out3);
 /* Options (all have working defaults; the kernel selectors exist for A/B measurements and the parity tests):
  *   list_capacity     neighbour slots per atom, 0 = automatic (estimated from the density, grown on overflow)
  *   cuda_graphs       1 (default) = NVE / NVT batches replay CUDA graphs of 8 / 4 / 2 steps, 0 = classic launches
- *   fuse_vv           1 (default) = NVE steps of systems above 75k atoms (or with force_variant 3) run k_force_vv, the
- *                     force pass with the velocity-Verlet kick + drift in its epilogue; 0 = k_force_v3 + k_vv
+ *   fuse_vv           1 (default) = NVE steps run ONE kernel, the force pass with the velocity-Verlet kick + drift in its
+ *                     epilogue (k_force_vv / k_force_q); 0 = force kernel + k_vv
  *   host_pipeline     1 (default) = pisb_verlet_step_nve_host moves x, v, F in chunks and pipelines upload, drift and
  *                     download; 0 = whole-array copies.  host_chunk_atoms = atoms per chunk, 0 = n/8 (>= 65536)
- *   force_variant     0 = automatic (v1 for a triclinic or non-periodic box; otherwise by size),
- *                     1 = v1 general all-FP64 in the reference's operation order, 2 = FP32 pre-filter + queue,
- *                     3 = v3 thread per atom, 4 = TMA-staged shared-memory cell-row tile (round-1 prototype),
- *                     6 = 8 lanes per atom (whole K-tiles per lane), 7 = 4 lanes per atom taking one entry of every K-tile
- *                     each (k_force_q), 8 = one block per brick of cells with shared-memory gathers (k_force_tile)
+ *   force_variant     0 = automatic (v1 for a triclinic or non-periodic box; otherwise k_force_q up to 75k atoms, one
+ *                     thread per atom above), 1 = v1 general all-FP64 in the reference's operation order, 2 = FP32
+ *                     pre-filter + queue, 3 = v3 thread per atom, 6 = 8 lanes per atom (whole K-tiles per lane),
+ *                     7 = k_force_q: 4 lanes per atom taking one entry of every K-tile each
  *   build_variant     0 = automatic (v3), 1 = v1 general, 2 = scalar FP32 pre-filter, 3 = packed-FP32 pair records
  *   cell_div          cells per list cutoff and dimension: 0 = automatic (2 with build_variant 2/3), 1, 2
  *   halo_mode         multi-GPU per-step ghost exchange: 0 = peer memory when it can be mapped, 1 = NCCL send/recv,

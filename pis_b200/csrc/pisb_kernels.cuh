@@ -16,8 +16,8 @@
 //   k_force_v2        FP32 pre-filter + shared-memory compaction queue + exact FP64 pair terms
 //   k_force_v3        DEFAULT: all-FP64 LEAN loop (short-way distance + FP64 guard band, Newton reciprocal, factored constants),
 //                     int4 index tiles prefetched, 4 x 256-bit gathers in flight, interior-warp shortcut, 64-register bound
-//   k_force_v4        v3 with the block's cell tile staged in shared memory by TMA bulk copies (prototype)
-//   k_force_split<S>  S lanes per atom (auto below ~75k atoms): same pair terms, different summation order
+//   k_force_q         four lanes per atom, lane l takes entry l of every K-tile, integrator in the epilogue (auto below 75k atoms)
+//   k_force_split<S>  S lanes per atom taking whole K-tiles (round-1 small-system kernel, force_variant 6)
 //   k_build_list (v1) all-FP64 27-cell scan;  k_build_list_v2  DEFAULT: FP32 pre-filter over contiguous x-rows
 #pragma once
 #include "pisb_device.cuh"
@@ -1463,271 +1463,6 @@ __global__ void __launch_bounds__(TPB_FORCE) k_force_split(Force2Args a) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_force_tile<FUSED, DRIFT, BRICK>: one block per BRICK of cells, neighbour positions gathered from SHARED MEMORY.
-//
-// ncu on the thread-per-atom loop (profiles/r02_force_vv_lean_full.*): L1TEX LSU data pipe 91 % -- 0.78 wavefronts per
-// gathered 32-byte record, because the records a warp gathers share almost no 128-byte lines -- FP64 pipe 43 %, issue
-// slots 48 %.  Fewer FP64 instructions (the lean loop), other lane mappings (k_force_q: same wavefronts, 40 % more
-// instructions), shared list entries (pair lists: more lines per gather) and the texture path (no spare pipe) all left
-// that limit where it is.  Shared memory serves the same random 32-byte reads at the crossbar's bandwidth floor:
-// 32 lanes x 32 bytes = 8 wavefronts per request, 0.25 per record, a third of the L1 cost.
-//   A block owns the atoms of a brick of E x E x E cells (E = 2 x the stencil reach: 4 half-size cells, ~19 A, ~175
-//   atoms) and stages the positions of the (E + 2 reach)^3 cells around it: (E + 2 reach)^2 contiguous slot ranges (one per
-//   cell row, 8 cells long), ~1400 atoms = 45 KB, fetched by TMA bulk copies (cp.async.bulk + mbarrier, SASS UBLKCP) that
-//   never touch the LSU data pipe.  Each atom is staged by ~8 blocks instead of being gathered 86 times.
-//   List entries are global slots in ascending order (the build scans rows in slot order), and the staged rows are
-//   ascending too: a running row pointer turns a slot into a tile address without a search.
-// Bricks whose halo would wrap around a periodic box edge, or overflow the tile, run the global-memory loop instead (same
-// arithmetic).  Lists, pair terms and per-atom summation order are those of k_force_v3: results are bit-identical to it.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-
-constexpr int TILE_TPB = 192;
-constexpr int TILE_CAP = 1664;       // atoms staged per block: 52 KB -> 4 blocks per SM
-constexpr int TILE_ROWS_MAX = 64;    // (E + 2 reach)^2 cell rows: 8 x 8 with half-size cells
-constexpr int TILE_OWN_MAX = 16;     // E^2 own cell rows
-
-struct TileSmem {
-    double4 tile[TILE_CAP];
-    unsigned long long bar;
-    int gstart[TILE_ROWS_MAX], gend[TILE_ROWS_MAX], prefix[TILE_ROWS_MAX];
-    int own_start[TILE_OWN_MAX], own_prefix[TILE_OWN_MAX + 1];
-    int n_rows, n_own_rows, staged, image;
-};
-
-struct TileArgs {
-    const int *cell_start;
-    Grid g;
-    int nb[3];   // bricks per dimension
-    int edge;    // cells per brick edge
-};
-
-// kick of step k (+ KE, tr(X F^T)) and, when DRIFT, drift + wrap + skin trigger of step k+1 for ONE atom: the epilogue of
-// k_force_vv, operation for operation (potential.rs:16-22, :28-30).  red[2..5] accumulate.
-template <bool DRIFT>
-__device__ __forceinline__ void vv_epilogue_atom(const ForceVVArgs &b, int i, double fx, double fy, double fz, double *red) {
-    const Force2Args &a = b.f;
-    double4 x = a.xt[i];
-    double vx = b.vx[i], vy = b.vy[i], vz = b.vz[i];
-    const double gx = b.gx[i], gy = b.gy[i], gz = b.gz[i];
-    double bx = 0.0, by = 0.0, bz = 0.0;
-    if (DRIFT && !b.always_rebuild) {
-        bx = b.xbx[i];
-        by = b.xby[i];
-        bz = b.xbz[i];
-    }
-    const double m = b.mass[type_of(x.w) - 1];
-    const double ax = __ddiv_rn(fx, m), ay = __ddiv_rn(fy, m), az = __ddiv_rn(fz, m);
-    const double ox = __ddiv_rn(gx, m), oy = __ddiv_rn(gy, m), oz = __ddiv_rn(gz, m);
-    vx = __dadd_rn(vx, __dmul_rn(__dmul_rn(__dadd_rn(ox, ax), 0.5), b.dt));
-    vy = __dadd_rn(vy, __dmul_rn(__dmul_rn(__dadd_rn(oy, ay), 0.5), b.dt));
-    vz = __dadd_rn(vz, __dmul_rn(__dmul_rn(__dadd_rn(oz, az), 0.5), b.dt));
-    b.vx[i] = vx;
-    b.vy[i] = vy;
-    b.vz[i] = vz;
-    red[2] += __dmul_rn(__dmul_rn(0.5, m), norm2(vx, vy, vz));
-    red[3] += __dmul_rn(x.x, fx);
-    red[4] += __dmul_rn(x.y, fy);
-    red[5] += __dmul_rn(x.z, fz);
-    if (DRIFT) {
-        x.x = __dadd_rn(x.x, __dadd_rn(__dmul_rn(vx, b.dt), __dmul_rn(__dmul_rn(ax, 0.5), b.dt2)));
-        x.y = __dadd_rn(x.y, __dadd_rn(__dmul_rn(vy, b.dt), __dmul_rn(__dmul_rn(ay, 0.5), b.dt2)));
-        x.z = __dadd_rn(x.z, __dadd_rn(__dmul_rn(vz, b.dt), __dmul_rn(__dmul_rn(az, 0.5), b.dt2)));
-        wrap_pos<true>(a.box, x.x, x.y, x.z);
-        b.xt_out[i] = x;
-        b.xf_out[i] = make_float4((float)x.x, (float)x.y, (float)x.z, __int_as_float(type_of(x.w)));
-        if (b.always_rebuild) {
-            if (i == 0) b.flags[FLAG_REBUILD] = 1;
-        } else {
-            double dx = x.x - bx, dy = x.y - by, dz = x.z - bz;
-            min_image<true>(a.box, dx, dy, dz);
-            if (!(norm2(dx, dy, dz) <= b.half_skin2)) b.flags[FLAG_REBUILD] = 1;
-        }
-    }
-}
-
-
-// neighbour loop of one atom with the gathers served by the staged tile (rows ascending, entries ascending)
-template <bool IMAGE>
-__device__ __forceinline__ void force_tile_body(const Force2Args &a, const TileSmem &sm, int i, LeanAcc<false> &acc, bool &ambiguous) {
-    const double4 xi = a.xt[i];
-    const int nn = a.nnbr[i];
-    const int4 *tiles = reinterpret_cast<const int4 *>(a.nbr) + i;
-    int4 cur = nn > 0 ? ldg_stream_i4(tiles) : make_int4(0, 0, 0, 0);
-    int r = 0, cur_end = sm.gend[0], cur_off = sm.prefix[0] - sm.gstart[0];
-    for (int k = 0; k < nn; k += 4) {
-        int4 nxt = cur;
-        if (k + 4 < nn) nxt = ldg_stream_i4(tiles + (size_t)((k >> 2) + 1) * a.npad);
-        const int j[4] = {cur.x, cur.y, cur.z, cur.w};
-        bool in[4];
-        double4 xj[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            in[u] = k + u < nn;
-            int loc = 0;
-            if (in[u]) {
-                while (j[u] >= cur_end) {  // the row pointer only advances
-                    ++r;
-                    cur_end = sm.gend[r];
-                    cur_off = sm.prefix[r] - sm.gstart[r];
-                }
-                loc = j[u] + cur_off;
-            }
-            xj[u] = sm.tile[loc];
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            double dx, dy, dz;
-            const double r2 = lean_disp<IMAGE>(a.box, xi, xj[u], dx, dy, dz);
-            if (in[u]) {
-                if (le_bits(r2, a.pair0.t_lo)) acc.pair(a.pair0, dx, dy, dz, r2);
-                else ambiguous |= le_bits(r2, a.pair0.t_hi);
-            }
-        }
-        cur = nxt;
-    }
-}
-
-template <bool FUSED, bool DRIFT, bool BRICK>
-__global__ void __launch_bounds__(TILE_TPB, 4) k_force_tile(ForceVVArgs b, TileArgs t) {
-    extern __shared__ __align__(128) unsigned char tile_raw[];
-    TileSmem &sm = *reinterpret_cast<TileSmem *>(tile_raw);
-    const Force2Args &a = b.f;
-    if (BRICK && a.skip_flag && *a.skip_flag != 0) return;  // speculative launch, a rebuild comes first
-    if (FUSED && DRIFT && blockIdx.x == 0 && threadIdx.x == 0) b.flags[b.unwrapped_out] = 0;
-    const int nx = t.g.n[0], ny = t.g.n[1], nz = t.g.n[2];
-    if (threadIdx.x == 0) {
-        int bc[3];
-        bc[0] = blockIdx.x % t.nb[0];
-        bc[1] = (blockIdx.x / t.nb[0]) % t.nb[1];
-        bc[2] = blockIdx.x / (t.nb[0] * t.nb[1]);
-        int c0[3], c1[3], s0[3], s1[3];  // own cells [c0, c1), staged cells [s0, s1)
-        bool wraps = false, edge_cells = *a.unwrapped != 0;
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-            const int reach = t.g.hi[d];
-            c0[d] = bc[d] * t.edge;
-            c1[d] = min(c0[d] + t.edge, t.g.n[d]);
-            s0[d] = c0[d] - reach;
-            s1[d] = c1[d] + reach;
-            if (t.g.local[d]) {  // brick-local (multi-GPU) dimension: no periodic images, ghosts fill the shell
-                s0[d] = max(s0[d], 0);
-                s1[d] = min(s1[d], t.g.n[d]);
-            } else {
-                if (s0[d] < 0 || s1[d] > t.g.n[d]) wraps = true;
-                // an atom sitting exactly on the upper box face is binned into cell 0: pairs across the face need the image
-                if (s0[d] <= 0 || s1[d] >= t.g.n[d]) edge_cells = true;
-            }
-        }
-        int total = 0, rows = 0, own_rows = 0, own_total = 0;
-        if (!wraps) {
-            for (int cz = s0[2]; cz < s1[2]; ++cz)
-                for (int cy = s0[1]; cy < s1[1]; ++cy, ++rows) {
-                    const int rb = (cz * ny + cy) * nx;
-                    sm.gstart[rows] = __ldg(&t.cell_start[rb + s0[0]]);
-                    sm.gend[rows] = __ldg(&t.cell_start[rb + s1[0]]);
-                    sm.prefix[rows] = total;
-                    total += sm.gend[rows] - sm.gstart[rows];
-                }
-        }
-        for (int cz = c0[2]; cz < c1[2]; ++cz)
-            for (int cy = c0[1]; cy < c1[1]; ++cy, ++own_rows) {
-                const int rb = (cz * ny + cy) * nx;
-                const int g0 = __ldg(&t.cell_start[rb + c0[0]]), g1 = __ldg(&t.cell_start[rb + c1[0]]);
-                sm.own_start[own_rows] = g0;
-                sm.own_prefix[own_rows] = own_total;
-                own_total += g1 - g0;
-            }
-        sm.own_prefix[own_rows] = own_total;
-        sm.n_own_rows = own_rows;
-        sm.n_rows = rows;
-        sm.staged = (!wraps && total <= TILE_CAP) ? 1 : 0;
-        sm.image = (wraps || edge_cells) ? 1 : 0;
-        if (sm.staged) {
-            const unsigned bar = smem_u32(&sm.bar);
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(total * 32) : "memory");
-        }
-    }
-    __syncthreads();
-    const bool staged = sm.staged != 0;
-    if (staged) {
-        // one TMA bulk copy per cell row (8 cells, ~22 records, ~700 bytes), issued by the first n_rows threads
-        const unsigned bar = smem_u32(&sm.bar);
-        if (threadIdx.x < sm.n_rows) {
-            const int rr = threadIdx.x;
-            const int len = sm.gend[rr] - sm.gstart[rr];
-            if (len > 0)
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                                 smem_u32(&sm.tile[sm.prefix[rr]])),
-                             "l"(a.xt + sm.gstart[rr]), "r"(len * 32), "r"(bar)
-                             : "memory");
-        }
-        unsigned done = 0;
-        while (!done) {
-            asm volatile(
-                "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}\n"
-                : "=r"(done)
-                : "r"(bar)
-                : "memory");
-        }
-    }
-    const bool image = sm.image != 0;
-    const int n_own = sm.own_prefix[sm.n_own_rows];
-    double red[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};  // pe, pair virial, ke, x*fx, y*fy, z*fz
-    for (int o = threadIdx.x; o < n_own; o += TILE_TPB) {
-        int r = 0;
-        while (o >= sm.own_prefix[r + 1]) ++r;
-        const int i = sm.own_start[r] + (o - sm.own_prefix[r]);
-        if (BRICK && xf_is_ghost(a.xf[i])) continue;
-        LeanAcc<false> acc;
-        bool ambiguous = false;
-        double fx, fy, fz, pe, vir;
-        if (staged) {
-            if (image) force_tile_body<true>(a, sm, i, acc, ambiguous);
-            else force_tile_body<false>(a, sm, i, acc, ambiguous);
-            acc.finish(a.pair0, fx, fy, fz, pe, vir);
-            if (ambiguous) {
-                double ex[5];
-                force_atom_exact<false, true>(a.xt, a.nbr, a.npad, i, a.nnbr[i], 0, 1, a.box, a.pair0, a.table, a.n_types, ex);
-                fx = ex[0], fy = ex[1], fz = ex[2], pe = ex[3], vir = ex[4];
-            }
-        } else {
-            force3_body<false, true>(a, i, fx, fy, fz, pe, vir);
-        }
-        red[0] += pe;
-        red[1] += vir;
-        if (!FUSED && a.ax) {
-            fx += a.ax[i];
-            fy += a.ay[i];
-            fz += a.az[i];
-        }
-        a.fx[i] = fx;
-        a.fy[i] = fy;
-        a.fz[i] = fz;
-        if (FUSED) vv_epilogue_atom<DRIFT>(b, i, fx, fy, fz, red);
-    }
-    pisb_thermo *th = a.thermo;
-    if (FUSED) {
-        double t3[3];
-        block_reduce_finalize<6, TILE_TPB>(red, a.partials, a.ticket, [&](int q, double s) {
-            if (q == 0) th->pe = s / 2.0;
-            else if (q == 1) th->virial_pair = s / 2.0;
-            else if (q == 2) th->ke = s;
-            else t3[q - 3] = s;
-            if (q == 5) th->virial_ref = (t3[0] + t3[1]) + t3[2];
-        });
-    } else {
-        double r2[2] = {red[0], red[1]};
-        block_reduce_finalize<2, TILE_TPB>(r2, a.partials, a.ticket, [&](int q, double s) {
-            if (q == 0) th->pe = s / 2.0;
-            else th->virial_pair = s / 2.0;
-        });
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
 // k_force_q<MULTI, FUSED, DRIFT, BRICK>: FOUR LANES PER ATOM, lane l takes entry l of every K-tile.
 //
 // What binds the thread-per-atom loop after the FP64 diet is the L1TEX data pipe: one wavefront per distinct 128-byte
@@ -1935,179 +1670,6 @@ __global__ void __launch_bounds__(TPB_FORCE) k_force_v2(Force2Args a) {
         double fx = 0.0, fy = 0.0, fz = 0.0, pe = 0.0, vir = 0.0;
         if (warp_interior) force2_body<MULTI, false>(a, i, s_q, fx, fy, fz, pe, vir);
         else force2_body<MULTI, true>(a, i, s_q, fx, fy, fz, pe, vir);
-        if (a.ax) {
-            fx += a.ax[i];
-            fy += a.ay[i];
-            fz += a.az[i];
-        }
-        a.fx[i] = fx;
-        a.fy[i] = fy;
-        a.fz[i] = fz;
-        red[0] = pe;
-        red[1] = vir;
-    }
-    pisb_thermo *th = a.thermo;
-    block_reduce_finalize<2, TPB_FORCE>(red, a.partials, a.ticket, [&](int qq, double s) {
-        if (qq == 0) th->pe = s / 2.0;
-        else th->virial_pair = s / 2.0;
-    });
-}
-
-// ------------------------------------------------------------------------------------------------
-// v4 (prototype): like v3, but each block first stages the positions of its whole cell tile -- the
-// 3 x 3 rows of x-contiguous cells around the block's own cells, nine contiguous slot ranges -- into
-// shared memory with TMA bulk copies (cp.async.bulk + mbarrier, SASS UBLKCP), and the neighbour
-// gathers then read shared memory instead of L1TEX/L2.  Blocks whose tile touches a periodic face,
-// spans two cell rows or exceeds the staging capacity run the v3 path.  Same results, bit for bit.
-// ------------------------------------------------------------------------------------------------
-constexpr int V4_CAP = 1728;  // atoms staged per block: 54 KB -> 4 blocks/SM
-
-struct V4Smem {
-    double4 tile[V4_CAP];
-    unsigned long long bar;
-    int gstart[9], gend[9], prefix[9];
-    int staged;
-};
-
-
-__device__ __forceinline__ int cell_of_slot(const int *__restrict__ cell_start, int ncell, int slot) {
-    int lo = 0, hi = ncell;  // largest c with cell_start[c] <= slot
-    while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (__ldg(&cell_start[mid]) <= slot) lo = mid;
-        else hi = mid;
-    }
-    return lo;
-}
-
-template <bool MULTI, bool IMAGE>
-__device__ __forceinline__ void force4_body(const Force2Args &a, int i, const V4Smem &sm, double &fx, double &fy,
-                                            double &fz, double &pe, double &vir) {
-    const double4 xi = a.xt[i];
-    const int ti = MULTI ? type_of(xi.w) : 1;
-    const int nn = a.nnbr[i];
-    const int4 *tiles = reinterpret_cast<const int4 *>(a.nbr) + i;
-    int4 cur = nn > 0 ? __ldg(tiles) : make_int4(0, 0, 0, 0);
-    int r = 0, cur_end = sm.gend[0], cur_off = sm.prefix[0] - sm.gstart[0];
-    LeanAcc<MULTI> acc;
-    bool ambiguous = false;
-    for (int k = 0; k < nn; k += 4) {
-        int4 nxt = cur;
-        if (k + 4 < nn) nxt = __ldg(tiles + (size_t)((k >> 2) + 1) * a.npad);
-        const int j[4] = {cur.x, cur.y, cur.z, cur.w};
-        bool in[4];
-        double4 xj[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            in[u] = k + u < nn;
-            int loc = 0;
-            if (in[u]) {
-                while (j[u] >= cur_end) {  // lists are in ascending slot order: the row pointer only advances
-                    ++r;
-                    cur_end = sm.gend[r];
-                    cur_off = sm.prefix[r] - sm.gstart[r];
-                }
-                loc = j[u] + cur_off;
-            }
-            xj[u] = sm.tile[loc];
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            double dx, dy, dz;
-            const double r2 = lean_disp<IMAGE>(a.box, xi, xj[u], dx, dy, dz);
-            PairDev p = a.pair0;
-            if (MULTI) {
-                const int tj = type_of(xj[u].w);
-                p = a.table[(min(ti, tj) - 1) * a.n_types + (max(ti, tj) - 1)];
-                in[u] = in[u] && p.present;
-            }
-            if (in[u]) {
-                if (le_bits(r2, p.t_lo)) acc.pair(p, dx, dy, dz, r2);
-                else ambiguous |= le_bits(r2, p.t_hi);
-            }
-        }
-        cur = nxt;
-    }
-    acc.finish(a.pair0, fx, fy, fz, pe, vir);
-    if (ambiguous) {
-        double o[5];
-        force_atom_exact<MULTI, IMAGE>(a.xt, a.nbr, a.npad, i, nn, 0, 1, a.box, a.pair0, a.table, a.n_types, o);
-        fx = o[0], fy = o[1], fz = o[2], pe = o[3], vir = o[4];
-    }
-}
-
-template <bool MULTI>
-__global__ void __launch_bounds__(TPB_FORCE, 4) k_force_v4(Force2Args a, const int *__restrict__ cell_start, Grid g) {
-    extern __shared__ __align__(128) unsigned char v4_raw[];
-    V4Smem &sm = *reinterpret_cast<V4Smem *>(v4_raw);
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (threadIdx.x == 0) {
-        const int i0 = blockIdx.x * blockDim.x;
-        const int i1 = min(i0 + (int)blockDim.x, a.n) - 1;
-        const int nx = g.n[0], ny = g.n[1], nz = g.n[2];
-        const int c0 = cell_of_slot(cell_start, g.ncell, i0), c1 = cell_of_slot(cell_start, g.ncell, i1);
-        const int cx0 = c0 % nx, cy0 = (c0 / nx) % ny, cz0 = c0 / (nx * ny);
-        const int cx1 = c1 % nx, cy1 = (c1 / nx) % ny, cz1 = c1 / (nx * ny);
-        int staged = (cy0 == cy1 && cz0 == cz1 && cx0 >= 1 && cx1 <= nx - 2 && cy0 >= 1 && cy0 <= ny - 2 && cz0 >= 1 &&
-                      cz0 <= nz - 2 && !g.local[0] && !g.local[1] && !g.local[2] && g.lo[0] == -1 && g.hi[0] == 1 && g.lo[1] == -1 &&
-                      g.hi[1] == 1 && g.lo[2] == -1 && g.hi[2] == 1)
-                         ? 1 : 0;
-        int total = 0;
-        if (staged) {
-            int rr = 0;
-            for (int dz = -1; dz <= 1; ++dz)
-                for (int dy = -1; dy <= 1; ++dy, ++rr) {
-                    const int rb = ((cz0 + dz) * ny + (cy0 + dy)) * nx;
-                    sm.gstart[rr] = __ldg(&cell_start[rb + cx0 - 1]);
-                    sm.gend[rr] = __ldg(&cell_start[rb + cx1 + 2]);
-                    sm.prefix[rr] = total;
-                    total += sm.gend[rr] - sm.gstart[rr];
-                }
-            if (total > V4_CAP) staged = 0;
-        }
-        sm.staged = staged;
-        if (staged) {
-            const unsigned bar = smem_u32(&sm.bar);
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(total * 32) : "memory");
-            for (int rr = 0; rr < 9; ++rr) {
-                const int len = sm.gend[rr] - sm.gstart[rr];
-                if (len > 0)
-                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                                     smem_u32(&sm.tile[sm.prefix[rr]])),
-                                 "l"(a.xt + sm.gstart[rr]), "r"(len * 32), "r"(bar)
-                                 : "memory");
-            }
-        }
-    }
-    __syncthreads();
-    const bool staged = sm.staged != 0;
-    double red[2] = {0.0, 0.0};
-    const bool active = i < a.n && !xf_is_ghost(a.xf[i]);
-    bool interior = *a.unwrapped == 0;
-    if (active) interior = interior && is_interior(a.boxf, a.xf[i]);
-    const bool warp_interior = __all_sync(0xffffffffu, interior);
-    if (staged) {
-        const unsigned bar = smem_u32(&sm.bar);
-        unsigned done = 0;
-        while (!done) {
-            asm volatile(
-                "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}\n"
-                : "=r"(done)
-                : "r"(bar)
-                : "memory");
-        }
-    }
-    if (active) {
-        double fx = 0.0, fy = 0.0, fz = 0.0, pe = 0.0, vir = 0.0;
-        if (staged) {
-            if (warp_interior) force4_body<MULTI, false>(a, i, sm, fx, fy, fz, pe, vir);
-            else force4_body<MULTI, true>(a, i, sm, fx, fy, fz, pe, vir);
-        } else {
-            if (warp_interior) force3_body<MULTI, false>(a, i, fx, fy, fz, pe, vir);
-            else force3_body<MULTI, true>(a, i, fx, fy, fz, pe, vir);
-        }
         if (a.ax) {
             fx += a.ax[i];
             fy += a.ay[i];

@@ -77,7 +77,6 @@ struct pisb_handle {
     int build_variant = 0;
     int cell_div = 0;  // cells per list cutoff per dimension: 0 = auto, 1 = reference-sized cells, 2 = half-size cells
     int fuse_vv = 1;   // option "fuse_vv": NVE batches run k_force_vv (force + kick + drift in one launch) when the default force kernel applies
-    int tile_halo_ok = 0;  // setup_grid: the grid suits k_force_tile (symmetric stencil, brick rows fit the tile tables)
 
     // box / grid
     BoxDev box{};
@@ -330,27 +329,12 @@ bool v2_possible(const pisb_t *h) {
     return h->have_box && h->box.ortho && h->box.pbc[0] && h->box.pbc[1] && h->box.pbc[2];
 }
 
-// force_variant 7: k_force_q, four lanes per atom on the per-atom list.  Measured SLOWER than one thread per atom at 4M atoms
-// (1.67 against 1.18 ms: 40 % more instructions for the same L1 data-pipe wavefronts, profiles/r02_force_q.*); selectable only.
-bool quad_mode(const pisb_t *h) { return v2_possible(h) && h->force_variant == 7; }
-
-// k_force_tile: one block per brick of cells, neighbour positions gathered from shared memory (force_variant 8; single type).
-bool tile_mode(const pisb_t *h) {
-    return v2_possible(h) && h->n_types == 1 && h->tile_halo_ok && h->force_variant == 8;
-}
-
-TileArgs tile_args(const pisb_t *h) {
-    TileArgs t{};
-    t.cell_start = h->cell_start.p;
-    t.g = h->grid;
-    t.edge = 2 * h->grid.hi[0];
-    for (int d = 0; d < 3; ++d) t.nb[d] = (h->grid.n[d] + t.edge - 1) / t.edge;
-    return t;
-}
-
-int tile_blocks(const pisb_t *h) {
-    const TileArgs t = tile_args(h);
-    return t.nb[0] * t.nb[1] * t.nb[2];
+// k_force_q -- four lanes per atom, integrator in the epilogue -- is the step kernel of systems too small to fill the GPU with
+// one thread per atom (measured, profiles/r02_small_systems.jsonl: 32k atoms 44 against 55 us per step, 4000 atoms 30.0
+// against 30.8; from 108k atoms up one thread per atom wins, 65 against 77 us, and at 4M atoms 1.18 against 1.67 ms per launch:
+// 40 % more instructions for the same L1TEX wavefronts).  force_variant 7 forces it at any size.
+bool quad_mode(const pisb_t *h) {
+    return v2_possible(h) && (h->force_variant == 7 || (h->force_variant == 0 && h->n <= 75000));
 }
 
 int setup_filter(pisb_t *h) {
@@ -491,13 +475,6 @@ int setup_grid(pisb_t *h) {
         }
     }
     g.ncell = g.n[0] * g.n[1] * g.n[2];
-    // k_force_tile needs one symmetric stencil reach r in every dimension, bricks of (2r)^3 cells whose (4r)^2 rows fit its tables
-    h->tile_halo_ok = 1;
-    for (int d = 0; d < 3; ++d)
-        if (g.hi[d] != g.hi[0] || g.lo[d] != -g.hi[0] || g.hi[0] < 1 || g.hi[0] > 2) h->tile_halo_ok = 0;
-    if ((int64_t)((g.n[0] + 2 * g.hi[0] - 1) / (2 * std::max(g.hi[0], 1))) * ((g.n[1] + 2 * g.hi[0] - 1) / (2 * std::max(g.hi[0], 1))) *
-            ((g.n[2] + 2 * g.hi[0] - 1) / (2 * std::max(g.hi[0], 1))) > (int64_t)h->n / 8 + 4096)
-        h->tile_halo_ok = 0;  // more bricks than the reduction buffers were sized for (very dilute systems)
     h->grid = g;
     TRY(dev_reserve(h, h->cell_count, (size_t)g.ncell + 2));
     TRY(dev_reserve(h, h->cell_start, (size_t)g.ncell + 2));
@@ -549,9 +526,8 @@ int reserve_atoms(pisb_t *h, int n) {
     auto need = [](size_t nq, size_t blocks) { return nq * (blocks + red_groups((unsigned int)blocks) + 2); };
     const size_t b_force = (size_t)nblk(n, TPB_FORCE), b_stream = (size_t)nblk(n, TPB), b_split = (size_t)nblk(std::min(n, 75000) * 8, TPB_FORCE);
     const size_t b_quad = ((size_t)n * 4 + TPB_Q - 1) / TPB_Q;  // k_force_q: four lanes per atom, 6 quantities
-    const size_t b_tile = (size_t)n / 8 + 4096;                  // k_force_tile: one block per brick of >= 8 cells, cells <= 4 n + 1024
-    TRY(dev_reserve(h, h->partials, std::max(std::max(need(6, std::max(b_force, b_tile)), need(6, b_quad)), std::max(need(19, b_stream), need(2, b_split)))));
-    const size_t tickets = 2 + red_groups((unsigned int)std::max(std::max(std::max(b_force, b_tile), b_quad), b_split));
+    TRY(dev_reserve(h, h->partials, std::max(std::max(need(6, b_force), need(6, b_quad)), std::max(need(19, b_stream), need(2, b_split)))));
+    const size_t tickets = 2 + red_groups((unsigned int)std::max(std::max(b_force, b_quad), b_split));
     if (tickets > h->ticket_cap) {
         // zero-initialised once; the words reset themselves at the end of every reduction
         CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -652,21 +628,6 @@ int launch_rebuild_chain(pisb_t *h) {
     return check_launch(h, "rebuild chain");
 }
 
-// k_force_tile's shared-memory block exceeds the 48 KB default: opt in once per instantiation
-int tile_smem_opt_in(pisb_t *h) {
-    static bool done = false;
-    if (done) return PISB_OK;
-    const int bytes = (int)sizeof(TileSmem);
-    CUDA_TRY(h, cudaFuncSetAttribute(k_force_tile<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    CUDA_TRY(h, cudaFuncSetAttribute(k_force_tile<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    CUDA_TRY(h, cudaFuncSetAttribute(k_force_tile<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    CUDA_TRY(h, cudaFuncSetAttribute(k_force_tile<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    CUDA_TRY(h, cudaFuncSetAttribute(k_force_tile<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    CUDA_TRY(h, cudaFuncSetAttribute(k_force_tile<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    done = true;
-    return PISB_OK;
-}
-
 // f_out = (acc ? acc + LJ : LJ); thermo record gets pe and virial_pair.
 int launch_force(pisb_t *h, double *const out[3], const double *const acc[3], pisb_thermo *rec, const int *skip_flag = nullptr) {
     LaunchScope ls(h, PISB_K_FORCE);
@@ -682,15 +643,6 @@ int launch_force(pisb_t *h, double *const out[3], const double *const acc[3], pi
         Force2Args f2{h->n, h->npad, h->xt.p, h->xf.p, h->nbr.p, h->nnbr.p, h->box, h->boxf, h->pairs[0], h->pairsf[0],
                       h->table_d.p, h->tablef_d.p, h->n_types, fa.ax, fa.ay, fa.az, out[0], out[1], out[2],
                       h->partials.p, h->ticket, rec, skip_flag, h->flags + h->xt_flag};
-        if (tile_mode(h)) {  // one block per brick, shared-memory gathers
-            ForceVVArgs fv{};
-            fv.f = f2;
-            fv.flags = h->flags;
-            TRY(tile_smem_opt_in(h));
-            if (h->multi) k_force_tile<false, false, true><<<tile_blocks(h), TILE_TPB, sizeof(TileSmem), st>>>(fv, tile_args(h));
-            else k_force_tile<false, false, false><<<tile_blocks(h), TILE_TPB, sizeof(TileSmem), st>>>(fv, tile_args(h));
-            return check_launch(h, "k_force_tile");
-        }
         if (quad_mode(h)) {  // four lanes per atom
             ForceVVArgs fv{};
             fv.f = f2;
@@ -709,7 +661,7 @@ int launch_force(pisb_t *h, double *const out[3], const double *const acc[3], pi
         if (skip_flag && h->force_variant != 0 && h->force_variant != 3 && h->force_variant != 6)
             return fail(h, PISB_ERR_STATE, "speculative force launch needs force_variant 0, 3, 5 or 6");
         // systems that cannot fill the GPU with one thread per atom: S lanes per atom (force_variant 6 forces S = 8)
-        const int split = h->force_variant == 6 ? 8 : (h->force_variant == 0 ? (h->n <= 32768 ? 8 : (h->n <= 75000 ? 4 : 0)) : 0);
+        const int split = h->force_variant == 6 ? 8 : 0;  // round-1 small-system kernel (whole K-tiles per lane), kept for A/B
         if (split) {
             const int nbs = nblk(h->n * split, TPB_FORCE);
             if (split == 8) {
@@ -719,15 +671,6 @@ int launch_force(pisb_t *h, double *const out[3], const double *const acc[3], pi
                 if (multi) k_force_split<true, 4><<<nbs, TPB_FORCE, 0, st>>>(f2);
                 else k_force_split<false, 4><<<nbs, TPB_FORCE, 0, st>>>(f2);
             }
-        } else if (h->force_variant == 4) {
-            static bool attr_set = false;
-            if (!attr_set) {
-                cudaFuncSetAttribute(k_force_v4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(V4Smem));
-                cudaFuncSetAttribute(k_force_v4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(V4Smem));
-                attr_set = true;
-            }
-            if (multi) k_force_v4<true><<<nb, TPB_FORCE, sizeof(V4Smem), st>>>(f2, h->cell_start.p, h->grid);
-            else k_force_v4<false><<<nb, TPB_FORCE, sizeof(V4Smem), st>>>(f2, h->cell_start.p, h->grid);
         } else if (h->force_variant != 2) {  // auto = v3 (measured fastest: profiles/)
             if (multi) k_force_v3<true><<<nb, TPB_FORCE, 0, st>>>(f2);
             else k_force_v3<false><<<nb, TPB_FORCE, 0, st>>>(f2);
@@ -780,7 +723,7 @@ int launch_vv(pisb_t *h, bool kick, bool drift, double dt, pisb_thermo *rec, con
 // atom) run one k_force_vv launch per step instead of k_force_v3 + k_vv.
 bool fused_step_possible(const pisb_t *h, bool multi_path = false) {
     if (!h->fuse_vv || h->multi != multi_path || !v2_possible(h)) return false;
-    if (quad_mode(h) || tile_mode(h)) return true;
+    if (quad_mode(h)) return true;
     return (h->force_variant == 0 || h->force_variant == 3) && (h->force_variant == 3 || h->n > 75000);
 }
 
@@ -800,18 +743,7 @@ int launch_force_vv(pisb_t *h, bool drift, double dt, pisb_thermo *rec, const in
         const bool multi = h->n_types > 1;
         const int nb = nblk(h->n, TPB_FORCE);
         cudaStream_t st = h->stream;
-        if (tile_mode(h)) {
-            TRY(tile_smem_opt_in(h));
-            const int nbt = tile_blocks(h);
-            const TileArgs ta = tile_args(h);
-            if (drift) {
-                if (h->multi) k_force_tile<true, true, true><<<nbt, TILE_TPB, sizeof(TileSmem), st>>>(fv, ta);
-                else k_force_tile<true, true, false><<<nbt, TILE_TPB, sizeof(TileSmem), st>>>(fv, ta);
-            } else {
-                if (h->multi) k_force_tile<true, false, true><<<nbt, TILE_TPB, sizeof(TileSmem), st>>>(fv, ta);
-                else k_force_tile<true, false, false><<<nbt, TILE_TPB, sizeof(TileSmem), st>>>(fv, ta);
-            }
-        } else if (quad_mode(h)) {
+        if (quad_mode(h)) {
             const unsigned nbq = (unsigned)(((size_t)h->n * 4 + TPB_Q - 1) / TPB_Q);
 #define FQ(T, D)                                                                  \
     do {                                                                          \
@@ -1129,7 +1061,7 @@ void graph_signature(pisb_t *h, double dt, std::vector<unsigned char> &sig) {
                           h->nhc_energy_d.p};
     put(ptrs, sizeof ptrs);
     const int ints[] = {h->n, h->npad, h->kcap, h->n_types, h->force_variant, h->build_variant, h->cell_div, h->fuse_vv,
-                        quad_mode(h) ? 1 : 0, tile_mode(h) ? 1 : 0};
+                        quad_mode(h) ? 1 : 0};
     put(ints, sizeof ints);
     const double dbl[] = {dt, h->skin, h->skin_half2_override, h->max_rcut};
     put(dbl, sizeof dbl);
@@ -2046,7 +1978,7 @@ int do_step_nve_multi(pisb_t *h, double dt, int64_t nsteps, pisb_thermo *out) {
             // The force kernel is launched BEFORE the host knows the decision: it returns at once if the (now global) rebuild
             // flag is set, and the flag travels to the host on a second stream meanwhile -- on the ~80 % of steps without a
             // rebuild the GPU never waits for the host round trip.
-            const bool speculate = v2_possible(h) && (h->force_variant == 0 || h->force_variant == 3 || (h->force_variant >= 5 && h->force_variant <= 8));
+            const bool speculate = v2_possible(h) && (h->force_variant == 0 || h->force_variant == 3 || h->force_variant == 6 || h->force_variant == 7);
             double *outp[3] = {h->g[0].p, h->g[1].p, h->g[2].p};
             if (speculate) {
                 if (fused)  // the decision word the speculative launch and the host read (see FLAG_DECISION)

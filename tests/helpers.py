@@ -23,13 +23,10 @@ VARIANTS = {
     2: (2, 2, 1),         # v2: FP32 pre-filter + queue force kernel, pre-filter build
     3: (3, 2, 1),         # v3: 4-wide prefetching all-FP64 force kernel, pre-filter build
     4: (3, 2, 2),         # v3 + half-size cells (5^3 stencil)
-    5: (4, 2, 1),         # v4: TMA-staged shared-memory cell tile (prototype)
     6: (3, 3, 1),         # v3 force + v3 build (packed-FP32 pair records, bit-mask append) == the defaults, explicit
     7: (3, 3, 2),         # v3 build with half-size cells (5^3 stencil)
-    8: (6, 3, 2),         # k_force_split<8>: 8 lanes per atom (the automatic choice below 32k atoms)
-    9: (8, 3, 2),         # k_force_tile: one block per brick of cells, neighbour positions gathered from shared memory
-    10: (8, 3, 1),        # k_force_tile over reference-sized cells (2 x 2 x 2 cell bricks)
-    11: (7, 3, 2),        # k_force_q: four lanes per atom, lane l takes entry l of every K-tile (the automatic choice above 75k atoms)
+    8: (6, 3, 2),         # k_force_split<8>: 8 lanes per atom taking whole K-tiles (round-1 small-system kernel)
+    11: (7, 3, 2),        # k_force_q: four lanes per atom, lane l takes entry l of every K-tile (the automatic choice up to 75k atoms)
     12: (7, 3, 1),        # k_force_q over reference-sized cells
 }
 

@@ -1,8 +1,7 @@
-"""The step-kernel alternatives to one thread per atom, forced at small sizes where the oracle is quick:
-  force_variant 7  k_force_q     four lanes per atom, lane l takes entry l of every K-tile
-  force_variant 8  k_force_tile  one block per brick of cells, neighbour positions gathered from shared memory (TMA-staged)
-Same per-atom lists, same lean arithmetic, so the oracle bars apply unchanged; exercised on the shapes where bricks and lane
-groups are ragged (odd counts, vacuum, grids of a few cells, very long rows) and where bricks wrap around the box."""
+"""k_force_q -- four lanes per atom, lane l takes entry l of every K-tile, integrator in the epilogue (the automatic step
+kernel up to 75k atoms; force_variant 7 forces it) -- and, beside it, the fused thread-per-atom kernel forced at small sizes
+(force_variant 3).  Same per-atom lists, same lean arithmetic, so the oracle bars apply unchanged; exercised on the shapes
+where lane groups are ragged (odd counts, vacuum, grids of a few cells, very short and very long rows, two types)."""
 import numpy as np
 import pytest
 
@@ -46,15 +45,15 @@ def _check_against_oracle(atoms, variant=9, rc=None, steps=30):
 
 
 
-@pytest.mark.parametrize("variant", [9, 10, 11, 12])
+@pytest.mark.parametrize("variant", [6, 11, 12])
 @pytest.mark.parametrize("ncell", [6, 7, 11])
 def test_step_kernel_variants_match_the_oracle(ncell, variant):
-    """ncell = 6: 32.5 A box, the smallest the reference handles without double counting: 6 half-size cells per edge, every
-    brick's halo wraps (k_force_tile takes its global-memory loop); 11: 59.5 A, interior bricks exist and are staged."""
+    """ncell = 6: 32.5 A box, the smallest the reference handles without double counting (6 half-size cells per edge, every
+    warp needs the minimum image); 11: 59.5 A, interior warps exist."""
     _check_against_oracle(fcc_argon(ncell, temperature=40.0, seed=ncell, jitter=0.2), variant=variant)
 
 
-@pytest.mark.parametrize("variant", [9, 11])
+@pytest.mark.parametrize("variant", [6, 11])
 def test_step_kernel_variants_odd_atom_count_vacuum_slab_and_non_cubic_box(variant):
     """Half the box empty (empty cells, bricks with no atoms, uneven density), three different box edges, an odd atom count."""
     base = fcc_argon(10, temperature=25.0, seed=8, jitter=0.1)
@@ -67,15 +66,15 @@ def test_step_kernel_variants_odd_atom_count_vacuum_slab_and_non_cubic_box(varia
     _check_against_oracle(atoms, variant=variant)
 
 
-@pytest.mark.parametrize("variant", [9, 11])
+@pytest.mark.parametrize("variant", [6, 11])
 def test_step_kernel_variants_long_cutoff(variant):
-    """rc = 4 sigma: ~330 entries per row, capacity regrown; the tile of a brick no longer fits shared memory (fallback)."""
+    """rc = 4 sigma: ~330 entries per row (83 K-tiles), capacity regrown."""
     atoms = fcc_argon(10, temperature=40.0, seed=3, jitter=0.12)
     mgr = _check_against_oracle(atoms, variant=variant, rc=4.0 * 3.405, steps=10)
     assert mgr.stats()["max_neighbours"] > 250
 
 
-@pytest.mark.parametrize("variant", [9, 11])
+@pytest.mark.parametrize("variant", [6, 11])
 def test_step_kernel_variants_hot_run_with_rebuilds(variant):
     """300 steps at 60 K (a rebuild every few steps): PE / KE traces vs the oracle; 13 x 13 x 13 half-size cells."""
     atoms = fcc_argon(12, temperature=60.0, seed=21)
@@ -94,37 +93,12 @@ def test_step_kernel_variants_hot_run_with_rebuilds(variant):
     assert np.abs(atoms.positions - x).max() < 1e-8
 
 
-def test_tile_kernel_is_bit_identical_to_thread_per_atom():
-    """k_force_tile changes WHERE neighbour positions are read from, not what is computed: same lists, same lean arithmetic,
-    same per-atom summation order as k_force_v3 / k_force_vv -> forces, energies and whole trajectories bit for bit."""
-    res = {}
-    for variant in (6, 9):
-        a = fcc_argon(14, temperature=50.0, seed=7, jitter=0.25)      # 10 976 atoms, 15^3 half-size cells: 4^3 bricks, 2^3 interior
-        m = make_manager(skin=SKIN, variant=variant)
-        m.attach(a)
-        pe = m.compute()
-        m.download(a, positions=False, velocities=False)
-        f0 = a.forces.copy()
-        th = m.step_nve(0.25, 40)
-        m.download(a)
-        res[variant] = (pe, f0, th, a.positions.copy(), a.velocities.copy(), a.forces.copy())
-    assert res[9][0] == res[6][0]
-    assert np.array_equal(res[9][1], res[6][1])
-    for key in ("pe", "virial_pair"):
-        assert np.array_equal(res[9][2][key], res[6][2][key]), key
-    for k in (3, 4, 5):
-        assert np.array_equal(res[9][k], res[6][k])
-    for key in ("ke", "virial_ref"):      # reduced over other block shapes
-        assert np.max(np.abs(res[9][2][key] - res[6][2][key]) / np.maximum(np.abs(res[6][2][key]), 1e-3)) <= 1e-12, key
-
-
 def test_four_lanes_two_types_and_a_missing_pair():
-    """The type-table form of k_force_q (MULTI): per-pair cutoffs, a missing (2,2) entry skipped like lennard_jones.rs:216-222;
-    k_force_tile is single-type and must hand two-type systems to the thread-per-atom kernel silently."""
+    """The type-table form of the step kernels (MULTI): per-pair cutoffs, a missing (2,2) entry skipped like lennard_jones.rs:216-222."""
     from pis_b200 import LennardJones
 
     table = {(1, 1): LennardJones(0.238, 3.405, 8.5), (1, 2): LennardJones(0.15, 3.0, 7.5)}
-    for variant in (11, 9):
+    for variant in (11, 6):
         atoms = fcc_argon(8, temperature=30.0, seed=9, jitter=0.1)
         atoms.type_ids[::3] = 2
         atoms.masses = [39.948, 20.18]
