@@ -198,6 +198,14 @@ PISB_API int pisb_host_unregister(void *ptr);
  * the last force evaluation).  Replaces Atoms::kinetic_energy / virial_tensor().trace(). */
 PISB_API int pisb_thermo_now(pisb_t *h, pisb_thermo *out);
 
+/* `velocity all create <temperature> <seed>` on the device: replaces Atoms::start_velocities
+ * (src/atoms/velocities.rs:10-15) for the atoms the handle holds -- Gaussian velocities with sigma_i = sqrt(kB T / m_i)
+ * (:17-33), remove_drift (:35-50), rescale_to_temperature (:52-59; kB = 0.0083144621, src/constants.rs:3; 3N degrees of
+ * freedom, src/atoms/properties.rs:28-43).  The reference's random stream (rand SmallRng + rand_distr Normal) is third-party
+ * and unpinned: the numbers come from this library's generator, keyed by (seed, global atom id, component), so any number of
+ * GPUs produces the velocities one GPU would.  Multi-GPU: collective (two small all-reduces).  Forces and list are kept. */
+PISB_API int pisb_start_velocities(pisb_t *h, double temperature, uint64_t seed);
+
 /* Strict drop-in for ONE trait call with HOST buffers: upload pos/vel/force (pinned staging),
  * one verlet_step_nve, download pos/vel/force, return PE.  This is what an unmodified
  * Simulation::run (src/simulation.rs:31-37,52) drives through the Rust shim. */

@@ -74,6 +74,7 @@ SIGNATURES = {
     "pisb_host_register": (C.c_int, [_vp, C.c_size_t]),
     "pisb_host_unregister": (C.c_int, [_vp]),
     "pisb_thermo_now": (C.c_int, [_vp, C.POINTER(Thermo)]),
+    "pisb_start_velocities": (C.c_int, [_vp, C.c_double, C.c_uint64]),
     "pisb_verlet_step_nve_host": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp, C.c_double, _dp]),
     "pisb_neighbours": (C.c_int, [_vp, _vp, _vp, C.c_int64]),
     "pisb_invalidate_list": (C.c_int, [_vp]),

@@ -42,6 +42,7 @@ int main(int argc, char **argv) {
         pis::System sys(infile);
         sys.ctx.device = device;
         sys.ctx.skin = skin < 0.0 ? 1.0 : skin;
+        sys.ctx.device_velocities = !check;  // a run creates velocities on the device; --check needs no GPU
         sys.read().contextualize();
         if (skin < 0.0 && sys.ctx.mgr) {  // default skin: 0.3 x the largest sigma
             double smax = 0.0;

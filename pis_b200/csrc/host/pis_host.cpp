@@ -194,6 +194,13 @@ LJCudaManager::~LJCudaManager() {
     if (h_) pisb_destroy(h_);
 }
 
+void LJCudaManager::start_velocities(double temperature, size_t seed) {
+    const int rc = pisb_start_velocities(h_, temperature, (uint64_t)seed);
+    if (rc == PISB_ERR_INVALID && h_)  // the reference's error for a bad variance (velocities.rs:25-26, errors.rs)
+        throw PisError("InvalidDistribution", pisb_last_error(h_));
+    check(rc);
+}
+
 void LJCudaManager::check(int rc) {
     if (rc != PISB_OK) throw PisError("Device", std::string("pisb error ") + std::to_string(rc) + ": " + pisb_last_error(h_));
 }
@@ -661,6 +668,11 @@ void Simulation::run(LJCudaManager &mgr, SimulationContext &ctx, FILE *out) {
     DumpTraj dumper(ctx.dump_args);
     dumper.write_step(atoms, 0);
     const double first_potential = mgr.compute_potential(atoms);  // uploads; forces stay resident too
+    if (ctx.velocities_pending) {  // `velocity all create T seed`: generated where the state lives, host copy refreshed once
+        mgr.start_velocities(ctx.starting_velocity->start_temperature.value_or(300.0), ctx.starting_velocity->seed.value_or(0));
+        mgr.download(atoms, false, true, false);
+        ctx.velocities_pending = false;
+    }
     std::fprintf(out, "0 %s\n", rust_display_f64(first_potential).c_str());
     std::vector<pisb_thermo> th;
     std::vector<double> ext_e, h_trace;
@@ -761,8 +773,10 @@ static std::unique_ptr<LJCudaManager> potential_from_script(const PotentialArgs 
 System &System::contextualize() {
     if (ctx.atoms && ctx.atoms->n_atoms == 0) throw PisError("NoAtomsDefined", "No atoms defined in input file");
     // velocities: created unless a Velocities section supplied them (default 300 K, seed 0 without a velocity statement)
-    if (ctx.atoms && ctx.starting_velocity && ctx.starting_velocity->start_velocity)
-        ctx.atoms->start_velocities(ctx.starting_velocity->start_temperature.value_or(300.0), ctx.starting_velocity->seed.value_or(0));
+    if (ctx.atoms && ctx.starting_velocity && ctx.starting_velocity->start_velocity) {
+        if (ctx.device_velocities) ctx.velocities_pending = true;  // Simulation::run: on the device, after the upload
+        else ctx.atoms->start_velocities(ctx.starting_velocity->start_temperature.value_or(300.0), ctx.starting_velocity->seed.value_or(0));
+    }
     if (ctx.potential_args) ctx.mgr = potential_from_script(*ctx.potential_args, ctx.skin, ctx.device);
     return *this;
 }

@@ -93,6 +93,7 @@ class LJCudaManager {
     // while the next batch runs; the array is valid after end
     void download_begin(Atoms &atoms, bool pos, bool vel, bool frc);
     void download_end();
+    void start_velocities(double temperature, size_t seed);  // Atoms::start_velocities (velocities.rs:10-15) on the device
     pisb_stats_t stats();
     std::map<std::pair<int, int>, LennardJones> table;
 
@@ -139,6 +140,10 @@ struct SimulationContext {         // simulation_context.rs:105-131
     DumpArgs dump_args;
     double skin = 0.0;  // NEW knob (not a reference command): Verlet skin handed to the CUDA manager
     int device = 0;
+    // `velocity ... create` is executed on the DEVICE once the atoms are resident (pisb_start_velocities): contextualize
+    // records the request here instead of running the host generator (same numbers, see Atoms::start_velocities)
+    bool device_velocities = false;
+    bool velocities_pending = false;
 };
 
 // One script statement: looks the keyword up in the statement table and lets its reader consume the words.

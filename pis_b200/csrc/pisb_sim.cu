@@ -16,6 +16,7 @@
 #include "pisb_kernels.cuh"
 #include "pisb_multi.cuh"
 #include "pisb_npt.cuh"
+#include "pisb_velocity.cuh"
 
 #include <dlfcn.h>
 #include <nccl.h>
@@ -108,6 +109,7 @@ struct pisb_handle {
     DevBuf<NhcDev> nhc_d;
     DevBuf<double> nhc_energy_d;
     DevBuf<double> npt_tensors_d;
+    DevBuf<double> vel_sums_d;  // pisb_start_velocities: total mass, momentum, atom count, kinetic energy
     double *h_npt = nullptr;         // pinned: 19 reduced tensor sums + thermostat energy
     double skin_half2_override = -1.0;  // NPT: skin trigger threshold reduced by the accumulated box strain
     DevBuf<pisb_thermo> thermo_d;
@@ -2139,6 +2141,7 @@ int pisb_destroy(pisb_t *h) {
     dev_free(h, h->tile_sum);
     dev_free(h, h->mass_d);
     dev_free(h, h->partials);
+    dev_free(h, h->vel_sums_d);
     dev_free(h, h->st_pos);
     dev_free(h, h->st_vel);
     dev_free(h, h->st_frc);
@@ -2335,6 +2338,44 @@ int pisb_thermo_now(pisb_t *h, pisb_thermo *out) {
     CUDA_TRY(h, cudaMemcpyAsync(h->h_thermo, h->thermo_d.p, sizeof(pisb_thermo), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     *out = h->h_thermo[0];
+    return PISB_OK;
+}
+
+// velocities.rs:10-59 on the device (pisb_velocity.cuh)
+int pisb_start_velocities(pisb_t *h, double temperature, uint64_t seed) {
+    if (!h) return PISB_ERR_INVALID;
+    if (!h->have_atoms) return fail(h, PISB_ERR_STATE, "start_velocities before upload");
+    const double kb = 0.0083144621;  // KB_KJPERMOLEKELVIN, src/constants.rs:3
+    for (double m : h->mass) {
+        const double sigma = std::sqrt(kb * temperature / m);
+        if (!(sigma >= 0.0) || !std::isfinite(sigma))  // rand_distr::Normal::new -> PisError::InvalidDistribution (velocities.rs:25-26)
+            return fail(h, PISB_ERR_INVALID, "Invalid normal distribution parameters: standard deviation is invalid");
+    }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    TRY(dev_reserve(h, h->vel_sums_d, 8));
+    auto splitmix = [](uint64_t x) {
+        x += 0x9E3779B97F4A7C15ULL;
+        uint64_t z = x;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+        return z ^ (z >> 31);
+    };
+    VelInitArgs a{h->n, h->xt.p, h->id.p, h->v[0].p, h->v[1].p, h->v[2].p, h->mass_d.p, kb * temperature,
+                  (unsigned long long)splitmix(seed * 0xD1342543DE82EF95ULL + 12345ULL), temperature, h->vel_sums_d.p,
+                  h->partials.p, h->ticket};
+    const int nb = nblk(h->n, TPB);
+    {
+        LaunchScope ls(h, PISB_K_INTEGRATE);
+        k_vel_create<<<nb, TPB, 0, h->stream>>>(a);
+        TRY(check_launch(h, "k_vel_create"));
+        if (h->multi) NCCL_TRY(h, g_nccl.AllReduce(a.sums, a.sums, 5, ncclDouble, ncclSum, h->comm, h->stream));
+        k_vel_remove_drift<<<nb, TPB, 0, h->stream>>>(a);
+        TRY(check_launch(h, "k_vel_remove_drift"));
+        if (h->multi) NCCL_TRY(h, g_nccl.AllReduce(a.sums + 5, a.sums + 5, 1, ncclDouble, ncclSum, h->comm, h->stream));
+        k_vel_rescale<<<nb, TPB, 0, h->stream>>>(a, kb);
+        TRY(check_launch(h, "k_vel_rescale"));
+    }
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return PISB_OK;
 }
 

@@ -48,6 +48,11 @@ def run_check(rank: int, world: int, local: int, ncell: int = 16, steps: int = 6
     st = mgr.stats()
     (F0,) = gather_by_gid(g0, [f0], n_global)
     X1, V1, F1 = gather_by_gid(g1, [x1, v1, f1], n_global)
+    # `velocity all create` on the device (pisb_start_velocities, collective): the bricks must get, per global id, the velocities
+    # one GPU generates (id-keyed generator, all-reduced drift / kinetic-energy sums)
+    mgr.start_velocities(35.0, 4242)
+    g2, _, v2, _ = (a_.copy() for a_ in mgr.download_owned(positions=False, forces=False))
+    (V2,) = gather_by_gid(g2, [v2], n_global)
     pieces = [None] * world
     dist.all_gather_object(pieces, (gr0, rows0, st))
     out = None
@@ -68,6 +73,11 @@ def run_check(rank: int, world: int, local: int, ncell: int = 16, steps: int = 6
         rows_ref = single.neighbours(n_global)
         th_ref = single.step_nve(0.25, steps)
         single.download(ref)
+        x_end, v_end, f_end = ref.positions.copy(), ref.velocities.copy(), ref.forces.copy()
+        single.start_velocities(35.0, 4242)
+        single.download(ref, positions=False, forces=False)
+        v_init_err = float(np.abs(V2 - ref.velocities).max() / np.abs(ref.velocities).max())
+        ref.positions[...], ref.velocities[...], ref.forces[...] = x_end, v_end, f_end
         mism = 0
         for g, rows, _ in pieces:
             for k, gi in enumerate(g):
@@ -86,11 +96,12 @@ def run_check(rank: int, world: int, local: int, ncell: int = 16, steps: int = 6
             "virial_ref_trace_rel": float(np.max(np.abs(th["virial_ref"] - th_ref["virial_ref"]) / np.maximum(np.abs(th_ref["virial_ref"]), 1.0))),
             "pos_max_abs": float(np.abs(X1 - ref.positions).max()),
             "vel_max_abs": float(np.abs(V1 - ref.velocities).max()),
+            "start_velocities_rel": v_init_err,
             "builds_multi": [p[2]["n_builds"] for p in pieces], "builds_single": single.stats()["n_builds"],
             "owned": [p[2]["n_atoms"] for p in pieces], "ghost": [p[2]["n_ghost"] for p in pieces],
         }
         ok = (mism == 0 and out["force_rel"] < 1e-10 and out["force0_max_abs"] < 1e-12 and out["pe0_rel"] < 1e-9 and out["pe_trace_rel"] < 1e-9
-              and out["ke_trace_rel"] < 1e-9)
+              and out["ke_trace_rel"] < 1e-9 and v_init_err < 1e-12)
         out["ok"] = bool(ok)
         single.close()
     dist.barrier()

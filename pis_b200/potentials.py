@@ -237,6 +237,11 @@ class LJCudaManager:
         capi.check(self._h, capi.load().pisb_thermo_now(self._h, C.byref(t)))
         return {"pe": t.pe, "ke": t.ke, "virial_ref": t.virial_ref, "virial_pair": t.virial_pair}
 
+    def start_velocities(self, temperature: float, seed: int = 0):
+        """Atoms::start_velocities (velocities.rs:10-15) on the device, for the attached atoms: Gaussian velocities
+        (this repository's id-keyed generator), drift removal, rescale to `temperature`."""
+        capi.check(self._h, capi.load().pisb_start_velocities(self._h, float(temperature), int(seed)))
+
     def neighbours(self, n_atoms: int):
         """Current Verlet list in original ids: list of sorted numpy arrays (test hook)."""
         lib = capi.load()

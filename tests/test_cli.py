@@ -332,3 +332,41 @@ def test_cli_nve_run_matches_oracle(tmp_path):
         assert np.abs(rows[:, 2:] - snaps[s]).max() < 1e-9
         if s == 0:  # frame 0 is the input, printed with Rust `{}` float formatting
             assert blk[9 + 1] == "2 1 " + " ".join(rust_display(c) for c in atoms.positions[1])
+
+
+@pytest.mark.gpu
+def test_cli_velocity_create_runs_on_the_device(tmp_path):
+    """`velocity all create T seed` after read_data (no Velocities section): the CLI generates the velocities on the device
+    (pisb_start_velocities) once the atoms are resident.  The thermo trace must be the oracle's run from the HOST
+    generator's velocities for the same (T, seed) -- the two generators are the same function of (seed, atom id) -- and
+    step 1 must show T close to the requested 20 K (rescale_to_temperature, velocities.rs:52-59)."""
+    from oracle.pis_oracle import Oracle
+    from pis_b200.lattice import create_velocities, fcc_argon
+
+    atoms = fcc_argon(6, temperature=0.0, seed=5, jitter=0.05)
+    n, L = atoms.n_atoms, atoms.sim_box.h[0, 0]
+    lines = [f"{n} atoms", "1 atom types", "", f"0.0 {rust_display(L)} xlo xhi", f"0.0 {rust_display(L)} ylo yhi",
+             f"0.0 {rust_display(L)} zlo zhi", "", "Masses", "1 39.948", "", "PairCoeffs", "1 0.238 3.405 8.5", "", "Atoms"]
+    lines += [f"{i + 1} 1 {repr(float(p[0]))} {repr(float(p[1]))} {repr(float(p[2]))}" for i, p in enumerate(atoms.positions)]
+    (tmp_path / "argon.txt").write_text("\n".join(lines) + "\n")
+    steps = 30
+    (tmp_path / "input.pis").write_text(f"timestep 0.25\nread_data argon.txt\nvelocity all create 20.0 77\nrun {steps}\n")
+    r = subprocess.run([CLI, "-i", "input.pis", "--skin", "1.0215"], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    out = r.stdout.strip().splitlines()
+    assert len(out) == steps + 1
+
+    o = Oracle.cubic(L)
+    o.insert(1, 1, 0.238, 3.405, 8.5)
+    x = atoms.positions.copy()
+    v = create_velocities(n, np.full(n, 39.948), 20.0, 77)
+    f = np.zeros_like(x)
+    o.compute_potential(x, atoms.type_ids, forces=f)
+    for s in range(1, steps + 1):
+        pe = o.verlet_step_nve(x, v, f, atoms.type_ids, 0.25)
+        ke = o.kinetic_energy(v, atoms.type_ids)
+        ref = [pe, ke, pe + ke, o.temperature(n, ke), o.pressure(x, f, ke)]
+        got = out[s].split()
+        for g, e in zip(got[1:], ref):
+            assert abs(float(g) - e) <= 1.1e-3 + 1e-9 * abs(e)
+    assert abs(float(out[1].split()[4]) - 20.0) < 0.5

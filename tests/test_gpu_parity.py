@@ -4,8 +4,8 @@ forces within 1e-10 relative; energy / temperature traces within 1e-9 relative."
 import numpy as np
 import pytest
 
-from pis_b200 import Atoms, LennardJones, SimulationBox
-from pis_b200.lattice import fcc_argon
+from pis_b200 import Atoms, LennardJones, SimulationBox, capi
+from pis_b200.lattice import ARGON, fcc_argon
 from tests.helpers import RC25, SKIN, argon_pair, csr_rows_sorted, force_rel_err, make_manager, make_oracle
 
 pytestmark = pytest.mark.gpu
@@ -845,3 +845,45 @@ def test_asynchronous_download_is_a_snapshot():
     assert lib.pisb_host_unregister(capi._ptr(buf)) == capi.PISB_OK
     mgr.download(ref)
     assert np.array_equal(buf, ref.positions)
+
+
+@pytest.mark.parametrize("two_types", [False, True])
+def test_device_velocity_initialisation_matches_the_host_generator(two_types):
+    """pisb_start_velocities = Atoms::start_velocities (velocities.rs:10-59) on the device: Gaussian components with
+    sigma_i = sqrt(kB T / m_i) from the repository's id-keyed generator, remove_drift, rescale_to_temperature.  Against the
+    host implementation of the same three steps (pis_b200.lattice.create_velocities, what the oracle runs are fed with):
+    equal to rounding (device log / cos differ from libm by an ulp), momentum zero, temperature exact; the state the
+    handle holds otherwise (positions, list, forces) is untouched, and NVE steps from the device-made velocities follow
+    the oracle's from the host-made ones."""
+    from pis_b200.atoms import KB_KJPERMOLEKELVIN
+    from pis_b200.lattice import create_velocities
+
+    atoms = fcc_argon(9, temperature=0.0, seed=3, jitter=0.05)
+    n = atoms.n_atoms
+    table = {(1, 1): argon_pair()}
+    if two_types:
+        types = np.where(np.arange(n) % 3 == 0, 2, 1).astype(np.int32)
+        atoms = Atoms(types, [ARGON["mass"], 83.798], atoms.positions, atoms.sim_box, velocities=atoms.velocities)
+        table = {(1, 1): argon_pair(), (1, 2): LennardJones(0.3, 3.5, 8.0, True), (2, 2): LennardJones(0.4, 3.6, 8.2, True)}
+    m_per_atom = np.asarray(atoms.masses)[atoms.type_ids - 1]
+    mgr = make_manager(skin=SKIN, table=table)
+    mgr.attach(atoms)
+    pe0 = mgr.compute()
+    mgr.start_velocities(37.5, 2024)
+    mgr.download(atoms, positions=False, forces=False)
+    v_host = create_velocities(n, m_per_atom, 37.5, 2024)
+    assert np.abs(atoms.velocities - v_host).max() <= 1e-13 * np.abs(v_host).max()
+    p = (atoms.velocities * m_per_atom[:, None]).sum(axis=0)
+    assert np.abs(p).max() <= 1e-9 * np.abs(atoms.velocities * m_per_atom[:, None]).sum()
+    ke = mgr.thermo_now()["ke"]
+    assert abs(2.0 * ke / (3.0 * n * KB_KJPERMOLEKELVIN) - 37.5) <= 1e-12 * 37.5
+    # the run that follows: device-made velocities on the GPU, host-made ones in the oracle
+    orc = make_oracle(atoms, table)
+    x, v, f = atoms.positions.copy(), v_host.copy(), np.zeros_like(v_host)
+    ref = orc.run_nve(x, v, f, atoms.type_ids, 0.25, 40)
+    assert abs(pe0 - ref[0, 0]) <= ENERGY_TOL * abs(ref[0, 0])
+    th = mgr.step_nve(0.25, 40)
+    assert np.max(np.abs(th["pe"] - ref[1:, 0]) / np.abs(ref[1:, 0])) <= ENERGY_TOL
+    assert np.max(np.abs(th["ke"] - ref[1:, 1]) / np.abs(ref[1:, 1])) <= ENERGY_TOL
+    with pytest.raises(capi.PisbError):
+        mgr.start_velocities(-1.0, 1)     # sqrt of a negative variance: InvalidDistribution (velocities.rs:25-26)
