@@ -142,6 +142,40 @@ def fp64_roofline(kernel: str, k_mean: float, k_in: float, n_atoms: int, ms_per_
                     "the kernel issues (SASS count x listed pairs) / the DFMA rate = the pipe's utilisation"}
 
 
+# What actually binds the step kernel (ncu, profiles/r02_force_vv_lean_full.*): the L1TEX DATA PIPE.  Every listed pair is one
+# scattered 32-byte record, and the data stage delivers one 128-byte line ("wavefront") per clock and SM whatever part of the
+# line is wanted: l1tex__data_pipe_lsu_wavefronts 90.9 % of peak, 0.878 wavefronts per listed pair (neighbours that share a
+# line share a wavefront), while the FP64 pipe is 43 % busy and DRAM 23 %.  Live part: listed pairs per second from this run's
+# list and launch time; the wavefronts-per-pair factor is the static ncu calibration (profiles/force_traffic.json).
+def l1tex_roofline(kernel: str, k_mean: float, n_atoms: int, ms_per_launch: float, sm_mhz, cal: dict) -> dict:
+    clock = float(sm_mhz or 1965.0) * 1e6
+    pairs_per_s = k_mean * n_atoms / (ms_per_launch * 1e-3)
+    peak = 148.0 * clock                                    # one data-pipe wavefront per clock and SM
+    w = float(cal.get("l1tex_wavefronts_per_listed_pair") or 1.0)
+    return {"kernel": kernel, "bound": "l1tex", "achieved": pairs_per_s * w / 1e9, "peak": peak / 1e9, "unit": "G wavefronts/s",
+            "frac": pairs_per_s * w / peak, "listed_pairs_per_s": pairs_per_s, "wavefronts_per_listed_pair_ncu": w,
+            "data_pipe_pct_ncu": cal.get("l1tex_data_pipe_lsu_wavefronts_pct"), "lsu_writeback_pct_ncu": cal.get("l1tex_lsu_writeback_active_pct"),
+            "sm_clock_mhz": clock / 1e6, "ms_per_launch": ms_per_launch, "peak_source": "1 data-pipe wavefront per clock and SM x 148 SMs x the SM clock sampled under load",
+            "note": "THE BINDING RESOURCE of the force loop (ncu: l1tex__data_pipe_lsu_wavefronts 90.9 % of peak; FP64 pipe 43 %, DRAM "
+                    "23 %): every listed pair is a scattered 32-byte record and costs one 128-byte data-pipe wavefront.  achieved = "
+                    "live listed pairs/s x the static ncu wavefronts-per-pair factor; *_ncu fields are static (profiles/force_traffic.json)"}
+
+
+def force_calibration(kernel_name: str):
+    """The static ncu capture of the dominant kernel (profiles/force_traffic.json): (all fields, dram bytes per launch, FP64 pipe
+    %, provenance note) -- empty when the capture is of another kernel."""
+    tp = os.path.join(ROOT, "profiles", "force_traffic.json")
+    try:
+        with open(tp) as f:
+            tj = json.load(f)
+    except Exception:
+        return {}, None, None, None
+    if not str(tj.get("kernel", "")).startswith(kernel_name.split("<")[0]):    # a capture of another kernel says nothing about this one
+        return {}, None, None, None
+    src = f"static ncu --set full capture {tj.get('source', 'profiles/force_traffic.json')} ({tj.get('commit', 'commit n/a')}); not re-measured in this run"
+    return tj, tj.get("dram_bytes_per_launch"), tj.get("fp64_pipe_active_pct"), src
+
+
 def argon_oracle(atoms):
     from oracle.pis_oracle import Oracle
 
@@ -295,10 +329,9 @@ def run_single(args):
         name, _, val = kv.partition("=")
         options[name] = float(val)
         mgr.set_option(name, float(val))
-    fv = options.get("force_variant", 0.0)   # mirrors pair_mode() / quad_mode() / fused_step_possible() of pisb_sim.cu
-    pair = options.get("pair_lists", 1.0) != 0.0 and fv == 5.0
-    quad = not pair and fv == 7.0
-    fused = options.get("fuse_vv", 1.0) != 0.0 and (pair or quad or fv == 3.0 or (fv == 0.0 and n > 75000))
+    fv = options.get("force_variant", 0.0)   # mirrors quad_mode() / fused_step_possible() of pisb_sim.cu
+    quad = fv == 7.0 or (fv == 0.0 and n <= 75000)
+    fused = options.get("fuse_vv", 1.0) != 0.0 and (quad or fv == 3.0 or fv == 0.0)
     mgr.attach(atoms)
     mgr.compute()
     stream = torch.cuda.ExternalStream(mgr.stream_ptr)
@@ -337,12 +370,12 @@ def run_single(args):
     st2 = mgr.stats()
 
     # ---- roofline of the dominant kernel (one launch per step: LJ force pass + velocity-Verlet kick + drift).
-    #      It is bound by the FP64 pipe (ncu: profiles/), so the primary `roofline` is the FP64 one; the HBM view
-    #      (algorithmic bytes / measured copy peak) is reported beside it as `roofline_hbm`.
+    #      ncu (profiles/r02_force_vv_lean_full.*) shows what binds it: the L1TEX data pipe (90.9 % of peak) -- not HBM (23 %), not
+    #      the FP64 pipe (43 % after the lean loop).  The primary `roofline` is therefore the L1TEX one; the HBM view
+    #      (algorithmic bytes / measured copy peak) and the FP64 view are reported beside it as `roofline_hbm` / `roofline_fp64`.
     #      Algorithmic bytes per atom: LJ force 48 + 4K for a full list of K 4-byte indices; the fused step
     #      kernel adds the integrator's streams: kick 72 (v read + write, F(t) read) and, on every launch but the last of a
-    #      batch, drift 72 (x_build read, x + FP32 shadow write) -> 192 + 4K.  The pair-list kernel reads FEWER index
-    #      words than 4K (two atoms share the entries of their common neighbours): `index_words_per_atom` says how many. ----
+    #      batch, drift 72 (x_build read, x + FP32 shadow write) -> 192 + 4K. ----
     peaks, peak_kind = measured_peaks()
     ls = mgr.list_stats()
     k_mean, k_in, words = ls["listed"] / n, ls["in_range"] / n, ls["index_words"] / n
@@ -352,25 +385,14 @@ def run_single(args):
     per_atom = 48.0 + 4.0 * k_mean + ((72.0 + 72.0 * drift_frac) if fused else 0.0)
     per_atom_stored = per_atom - 4.0 * k_mean + 4.0 * words
     bytes_per_launch = per_atom * n
-    kernel_name = (("k_pforce" if pair else "k_force_q" if quad else "k_force_vv") + "<fused>") if fused else ("k_pforce" if pair else "k_force_q" if quad else "k_force_v3")
+    kernel_name = (("k_force_q" if quad else "k_force_vv") + "<fused>") if fused else ("k_force_q" if quad else "k_force_v3")
     achieved = bytes_per_launch / (f_ms * 1e-3) / 1e9
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    traffic, fp64_pct, traffic_src = None, None, None
-    tp = os.path.join(ROOT, "profiles", "force_traffic.json")
-    if os.path.exists(tp):
-        try:
-            with open(tp) as f:
-                tj = json.load(f)
-            if str(tj.get("kernel", "")).startswith(kernel_name.split("<")[0]):    # a capture of another kernel says nothing about this one
-                traffic, fp64_pct = tj.get("dram_bytes_per_launch"), tj.get("fp64_pipe_active_pct")
-                traffic_src = f"static ncu --set full capture {tj.get('source', 'profiles/force_traffic.json')} ({tj.get('commit', 'commit n/a')}); not re-measured in this run"
-        except Exception:
-            traffic = None
+    tj, traffic, fp64_pct, traffic_src = force_calibration(kernel_name)
     timing_note = ("per-launch CUDA events over the K steps that follow the timed region (same state, same kernels; "
                    "ms_per_step_profiled beside ms_per_step)")
-    roofline = fp64_roofline(kernel_name, k_mean, k_in, n, f_ms, fused)
-    roofline.update({"timing": timing_note, "share_of_step": tim["force"]["ms"] / ms_profiled, "traffic": traffic,
-                     "traffic_source": traffic_src, "fp64_pipe_active_pct_ncu": fp64_pct})
+    roofline_fp64 = fp64_roofline(kernel_name, k_mean, k_in, n, f_ms, fused)
+    roofline_fp64.update({"timing": timing_note, "fp64_pipe_active_pct_ncu": fp64_pct})
     roofline_hbm = {"kernel": kernel_name, "bound": "hbm", "timing": timing_note,
                     "algorithmic_bytes_per_launch": bytes_per_launch, "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_kind,
@@ -378,8 +400,13 @@ def run_single(args):
                     "bytes_per_atom_with_the_stored_list": per_atom_stored,
                     "frac_with_the_stored_list": per_atom_stored * n / (f_ms * 1e-3) / 1e9 / peak,
                     "mean_neighbours": k_mean, "ms_per_launch": f_ms,
-                    "note": "not the binding resource: the force pass is bound by the FP64 pipe and the L1TEX gather path (ncu: "
+                    "note": "not the binding resource: the force pass is bound by the L1TEX data pipe (roofline_l1tex; ncu: "
                             "profiles/); frac = algorithmic HBM bytes (SURVEY 8d, full list) / measured copy peak"}
+    # the primary `roofline` is the resource that binds the kernel: the L1TEX data pipe
+    roofline = l1tex_roofline(kernel_name, k_mean, n, f_ms, clk.summary().get("sm_mhz"), tj)
+    roofline.update({"timing": timing_note, "share_of_step": tim["force"]["ms"] / ms_profiled, "traffic": traffic,
+                     "traffic_source": traffic_src, "algorithmic_bytes_per_launch": bytes_per_launch,
+                     "hbm_frac": achieved / peak, "fp64_frac": roofline_fp64["frac"]})
     kernel_ms = {k: round(v["ms"] / args.steps, 5) for k, v in tim.items() if v["launches"]}
     # the streaming kernel next to it: k_vv<kick,drift> moves 200 B/atom per step; with the fused
     # step kernel only the drift that opens a batch is left (x 32 + v 24 + F 24 + x_build 24 read, x 32 + shadow 16 written)
@@ -458,7 +485,7 @@ def run_single(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": workload_config(args, 1), "clocks": clk.summary(), "e2e": e2e,
         "e2e_resident": e2e_resident,
-        "gpu_launches": int(launches), "roofline": roofline, "roofline_hbm": roofline_hbm,
+        "gpu_launches": int(launches), "roofline": roofline, "roofline_hbm": roofline_hbm, "roofline_fp64": roofline_fp64,
         "roofline_integrate": roofline_integrate, "cpu_baseline": cpu,
         "kernel_ms_per_step": kernel_ms, "ms_per_step_profiled": ms_profiled / args.steps,
         "list_builds_in_timed_region": int(builds), "list_builds_in_profiled_pass": int(st2["n_builds"] - st1["n_builds"]),

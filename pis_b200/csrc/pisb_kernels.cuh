@@ -1874,11 +1874,17 @@ __device__ __noinline__ bool build3_exact_out(double h0, double h1, double h2, d
 // (profiles/r01_build_occupancy.jsonl): 64 registers / 4 records 2.48, 48 registers / 4 records 2.31, 48 registers /
 // 2 records 2.30 (the default), 40 registers 2.34, 8 records 2.74; loading the next stencil row's cell_start words while
 // the current row is scanned changed nothing.
-template <bool IMAGE, int B3_PAIRS = 2>
-__device__ __forceinline__ int build3_body(const Build2Args &a, const float *__restrict__ xp, int i) {
+// MULTI: per-pair cutoffs.  The block keeps the FP32 band {lo, hi} of every type pair in shared memory as a symmetric
+// (n_types + 2)^2 table whose row / column 0 and n_types + 1 hold {-1, -1} (nothing is accepted: padding slots carry type 0,
+// stale padding anything), so a candidate costs two LDS.64 on top of the single-type loop; a missing pair is {-1, -1} too.
+constexpr int B3_MAX_TYPES = 6;
+template <bool IMAGE, bool MULTI, int B3_PAIRS = 2>
+__device__ __forceinline__ int build3_body(const Build2Args &a, const float *__restrict__ xp, int i, const float2 *s_band) {
     int cnt = 0;
     const double4 xi = a.xt[i];
     const float4 xif = a.xf[i];
+    const int tdim = a.n_types + 2;
+    const float2 *band_row = MULTI ? s_band + xf_type(xif) * tdim : nullptr;
     int c[3];
     cell_coords<true>(a.box, a.g, xi.x, xi.y, xi.z, c);
     int *wp = a.nbr + (size_t)i * 4;  // slot of list entry number cnt
@@ -1916,10 +1922,18 @@ __device__ __forceinline__ int build3_body(const Build2Args &a, const float *__r
                     const f32x2_t r2 = f2_fma(dz, dz, f2_fma(dy, dy, f2_mul(dx, dx)));
                     float ra, rb;
                     f2_unpack(r2, ra, rb);
-                    if (ra <= hi) b_hi |= 1u << (2 * u);
-                    if (rb <= hi) b_hi |= 2u << (2 * u);
-                    if (ra < lo) b_lo |= 1u << (2 * u);
-                    if (rb < lo) b_lo |= 2u << (2 * u);
+                    float lo_a = lo, hi_a = hi, lo_b = lo, hi_b = hi;
+                    if (MULTI) {
+                        float wa, wb;
+                        f2_unpack(r[u].w, wa, wb);
+                        const float2 ba = band_row[min((unsigned)xf_type(make_float4(0.f, 0.f, 0.f, wa)), (unsigned)(tdim - 1))];
+                        const float2 bb = band_row[min((unsigned)xf_type(make_float4(0.f, 0.f, 0.f, wb)), (unsigned)(tdim - 1))];
+                        lo_a = ba.x, hi_a = ba.y, lo_b = bb.x, hi_b = bb.y;
+                    }
+                    if (ra <= hi_a) b_hi |= 1u << (2 * u);
+                    if (rb <= hi_b) b_hi |= 2u << (2 * u);
+                    if (ra < lo_a) b_lo |= 1u << (2 * u);
+                    if (rb < lo_b) b_lo |= 2u << (2 * u);
                 }
                 m_hi |= b_hi << (2 * s);
                 m_lo |= b_lo << (2 * s);
@@ -1934,8 +1948,13 @@ __device__ __forceinline__ int build3_body(const Build2Args &a, const float *__r
             while (band) {
                 const int b = __ffs(band) - 1;
                 band &= band - 1u;
+                double t_list = a.pair0.t_list;
+                if (MULTI) {
+                    const int ti = xf_type(xif), tj = xf_type(a.xf[2 * q0 + b]);
+                    t_list = a.table[(min(ti, tj) - 1) * a.n_types + (max(ti, tj) - 1)].t_list;
+                }
                 if (build3_exact_out(a.box.h[0], a.box.h[4], a.box.h[8], a.box.hinv[0], a.box.hinv[4], a.box.hinv[8], a.xt, xi.x,
-                                     xi.y, xi.z, 2 * q0 + b, a.pair0.t_list))
+                                     xi.y, xi.z, 2 * q0 + b, t_list))
                     m_hi &= ~(1u << b);
             }
             const int j0 = 2 * q0;
@@ -1985,6 +2004,20 @@ __device__ __forceinline__ int build3_body(const Build2Args &a, const float *__r
 template <bool MULTI>
 __global__ void __launch_bounds__(TPB_FORCE, 10) k_build_list_v3(Build2Args a, const float *__restrict__ xp, int fast_ok) {
     if (a.flags[FLAG_REBUILD] == 0) return;
+    __shared__ float2 s_band[MULTI ? (B3_MAX_TYPES + 2) * (B3_MAX_TYPES + 2) : 1];
+    if (MULTI && fast_ok) {
+        const int tdim = a.n_types + 2;
+        for (int k = threadIdx.x; k < tdim * tdim; k += blockDim.x) {
+            const int ti = k / tdim, tj = k % tdim;
+            float2 v = make_float2(-1.f, -1.f);
+            if (ti >= 1 && ti <= a.n_types && tj >= 1 && tj <= a.n_types) {
+                const PairF pf = a.tablef[(min(ti, tj) - 1) * a.n_types + (max(ti, tj) - 1)];
+                v = make_float2(pf.lo_list, pf.hi_list);
+            }
+            s_band[k] = v;
+        }
+        __syncthreads();
+    }
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < a.n && xf_is_ghost(a.xf[i])) a.nnbr[i] = 0;
     const bool active = i < a.n && !xf_is_ghost(a.xf[i]);
@@ -1993,7 +2026,7 @@ __global__ void __launch_bounds__(TPB_FORCE, 10) k_build_list_v3(Build2Args a, c
     const bool warp_interior = __all_sync(0xffffffffu, interior);
     int cnt = 0;
     if (active) {
-        if (!MULTI && fast_ok) cnt = warp_interior ? build3_body<false>(a, xp, i) : build3_body<true>(a, xp, i);
+        if (fast_ok) cnt = warp_interior ? build3_body<false, MULTI>(a, xp, i, s_band) : build3_body<true, MULTI>(a, xp, i, s_band);
         else cnt = warp_interior ? build2_body<MULTI, false>(a, i) : build2_body<MULTI, true>(a, i);
     }
     int m = cnt;

@@ -614,7 +614,7 @@ int launch_rebuild_chain(pisb_t *h) {
                 if (multi) k_build_list_v2<true><<<nb, TPB_FORCE, 0, st>>>(b2);
                 else k_build_list_v2<false><<<nb, TPB_FORCE, 0, st>>>(b2);
             } else {  // default: v3, packed FP32 pair records + bit-mask append for interior warps
-                if (multi) k_build_list_v3<true><<<nb, TPB_FORCE, 0, st>>>(b2, h->xp.p, 1);
+                if (multi) k_build_list_v3<true><<<nb, TPB_FORCE, 0, st>>>(b2, h->xp.p, h->n_types <= B3_MAX_TYPES ? 1 : 0);
                 else k_build_list_v3<false><<<nb, TPB_FORCE, 0, st>>>(b2, h->xp.p, 1);
             }
         } else if (h->box.ortho) {
@@ -2847,7 +2847,9 @@ int pisb_set_option(pisb_t *h, const char *name, double value) {
         return PISB_OK;
     }
     if (!std::strcmp(name, "force_variant")) {
-        h->force_variant = (int)value;
+        const int v = (int)value;
+        if (v < 0 || v == 4 || v == 5 || v > 7) return fail(h, PISB_ERR_INVALID, fmt("force_variant %d does not exist (0-3, 6, 7)", v));
+        h->force_variant = v;
         return PISB_OK;
     }
     if (!std::strcmp(name, "build_variant") || !std::strcmp(name, "cell_div")) {

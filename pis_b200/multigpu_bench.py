@@ -82,9 +82,9 @@ def run(args):
     # ---- 0. multi-GPU == single-GPU, on the driver's record ----
     multi_parity = None
     if not args.no_multi_parity:
-        # 24^3 cells = 55 296 atoms at 60 K, 40 steps (rebuilds + migration); force_variant 5 = the pair-list step kernel the
-        # 4M-atom bricks use, forced at this brick size
-        multi_parity = run_check(rank, world, local, ncell=24, steps=40, T0=60.0, halo_mode=0, force_variant=5)
+        # 24^3 cells = 55 296 atoms at 60 K, 40 steps (rebuilds + migration); force_variant 3 = the thread-per-atom fused step
+        # kernel (k_force_vv<.., BRICK>) the 4M-atom bricks use, forced at this brick size
+        multi_parity = run_check(rank, world, local, ncell=24, steps=40, T0=60.0, halo_mode=0, force_variant=3)
         flag = torch.tensor([1 if (rank != 0 or multi_parity["ok"]) else 0], dtype=torch.int64)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if int(flag.item()) == 0:
@@ -199,9 +199,13 @@ def run(args):
         # bricks of this size step with the fused kernel (force + kick + drift): 192 + 4K algorithmic bytes per owned atom,
         # 48 + 4K for the plain force kernel (bench.py)
         fused = tim.get("integrate", {"launches": 0})["launches"] < max(args.steps // 2, 1)   # unfused: one k_vv per step
-        kernel = "k_pforce<fused,brick>" if fused else "k_force_v3"
-        roofline = B.fp64_roofline(kernel, k_mean, k_in, n_own, f_ms, fused)
-        roofline.update({"share_of_step": tim["force"]["ms"] / ms_prof, "traffic": None, "note_rank": "rank 0's brick"})
+        kernel = "k_force_vv<fused,brick>" if fused else "k_force_v3"
+        roofline_fp64 = B.fp64_roofline(kernel, k_mean, k_in, n_own, f_ms, fused)
+        cal = B.force_calibration(kernel)[0]
+        clocks = clk.summary()
+        roofline = B.l1tex_roofline(kernel, k_mean, n_own, f_ms, clocks.get("sm_mhz"), cal)   # the binding resource (bench.py)
+        roofline.update({"share_of_step": tim["force"]["ms"] / ms_prof, "traffic": None, "note_rank": "rank 0's brick",
+                         "fp64_frac": roofline_fp64["frac"]})
         achieved = ((192.0 if fused else 48.0) + 4.0 * k_mean) * n_own / (f_ms * 1e-3) / 1e9
         peak = float(peaks.get("hbm_gbs", 6650.0))
         cfg = B.workload_config(args, world)
@@ -210,7 +214,7 @@ def run(args):
         line = {
             "metric": B.METRIC, "value": value, "unit": B.UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": cfg, "clocks": clk.summary(),
+            "dtype": "f64", "data": "synthetic", "config": cfg, "clocks": clocks,
             "e2e": {"value": n_global * e2e_steps / e2e_s, "unit": B.UNIT, "h2d_bytes_per_step": h2d_total // max(args.steps + e2e_steps + args.warmup, 1),
                     "d2h_bytes_per_step": d2h // e2e_steps, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
                     "call": "per rank: pisb_step_nve(dt, steps to the next dump) returning one thermo record per step and "
@@ -218,10 +222,10 @@ def run(args):
                             "state is uploaded once"},
             "gpu_launches": int(st1["n_launches"] - st0["n_launches"]),
             "multi_parity": multi_parity, "strong_32M": strong,
-            "roofline": roofline,
+            "roofline": roofline, "roofline_fp64": roofline_fp64,
             "roofline_hbm": {"kernel": kernel, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": None, "peak_source": peak_kind, "mean_neighbours": k_mean, "index_words_per_atom": words,
-                             "ms_per_launch": f_ms, "note": "rank 0's force kernel; not the binding resource (FP64 pipe / L1TEX), see DESIGN.md"},
+                             "ms_per_launch": f_ms, "note": "rank 0's force kernel; not the binding resource (the L1TEX data pipe is), see DESIGN.md"},
             "cpu_baseline": None,
             "ms_per_step_profiled": ms_prof / args.steps,
             "kernel_ms_per_step_rank0": {k: round(v["ms"] / args.steps, 5) for k, v in tim.items() if v["launches"]},

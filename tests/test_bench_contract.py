@@ -40,11 +40,14 @@ def test_reference_arm_other_ranks_exit_quietly():
 def test_cuda_arm_json_line():
     d = _run(["--steps", "12", "--warmup", "3", "--ncell", "24", "--cpu-ncell", "8", "--ref-ncell-serial", "6", "--cpu-steps", "2",
               "--e2e-steps", "3", "--no-strong"])
-    assert BASE_KEYS | {"clocks", "gpu_launches", "roofline", "roofline_hbm"} <= set(d)
+    assert BASE_KEYS | {"clocks", "gpu_launches", "roofline", "roofline_hbm", "roofline_fp64"} <= set(d)
     assert d["n_gpus"] == 1 and d["steps"] == 12 and d["warmup"] == 3 and d["higher_is_better"] is True
     assert d["gpu_launches"] > 30 and d["value"] > 1e7
-    rf, rh = d["roofline"], d["roofline_hbm"]
-    # the binding resource first: FP64, against the measured DFMA rate; the HBM view beside it
+    rl, rf, rh = d["roofline"], d["roofline_fp64"], d["roofline_hbm"]
+    # the binding resource first: the L1TEX data pipe (gather wavefronts per second against one per clock and SM); the FP64 view
+    # against the measured DFMA rate and the HBM view beside it
+    assert rl["bound"] == "l1tex" and abs(rl["frac"] - rl["achieved"] / rl["peak"]) < 1e-12 and 0 < rl["frac"] < 1.2
+    assert {"traffic", "share_of_step", "hbm_frac", "fp64_frac"} <= set(rl)
     assert rf["bound"] == "fp64" and rf["unit"] == "TFLOP/s" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-12
     assert 60 < rf["mean_neighbours_listed"] < 110 and 40 < rf["mean_neighbours_in_range"] < rf["mean_neighbours_listed"]
     assert abs(rf["algorithmic_flops_per_atom"] - (21 * rf["mean_neighbours_listed"] + 18 * rf["mean_neighbours_in_range"])) < 1e-6 + 20
@@ -82,3 +85,19 @@ def test_fp64_yardstick_arithmetic():
     assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12 and abs(r["frac_of_dfma_issue_rate"] - 2 * r["frac"]) < 1e-12
     assert r["bound"] == "fp64" and 0 < r["issue_frac"] < 1
     assert bench.fp64_roofline("k", 85.34, 54.0, 4_000_000, 0.8, True)["frac"] > r["frac"]
+
+
+def test_l1tex_yardstick_arithmetic():
+    """The primary `roofline`: listed pairs per second x the ncu-calibrated wavefronts per pair, against one data-pipe wavefront
+    per clock and SM.  The committed calibration file names the capture it comes from."""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    cal, traffic, fp64_pct, src = bench.force_calibration("k_force_vv<fused>")
+    assert cal and traffic > 1e9 and 0 < fp64_pct < 100 and "profiles/" in src
+    assert 0.5 < cal["l1tex_wavefronts_per_listed_pair"] <= 1.0 and cal["l1tex_data_pipe_lsu_wavefronts_pct"] > 50
+    assert bench.force_calibration("k_some_other_kernel") == ({}, None, None, None)
+    r = bench.l1tex_roofline("k", 85.4, 4_000_000, 1.18, 1965.0, cal)
+    assert r["bound"] == "l1tex" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
+    assert abs(r["peak"] - 148 * 1.965) < 1e-9 and abs(r["listed_pairs_per_s"] - 85.4 * 4e6 / 1.18e-3) < 1.0
+    assert 0.8 < r["frac"] < 1.0          # the ncu capture this is calibrated on says 90.9 %

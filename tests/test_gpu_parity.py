@@ -887,3 +887,36 @@ def test_device_velocity_initialisation_matches_the_host_generator(two_types):
     assert np.max(np.abs(th["ke"] - ref[1:, 1]) / np.abs(ref[1:, 1])) <= ENERGY_TOL
     with pytest.raises(capi.PisbError):
         mgr.start_velocities(-1.0, 1)     # sqrt of a negative variance: InvalidDistribution (velocities.rs:25-26)
+
+
+@pytest.mark.parametrize("variant", [4, 6, 7, 0])
+def test_multi_type_lists_exact_with_every_build(variant):
+    """Per-pair cutoffs in the list build: three types, six different rc + skin radii, one pair missing
+    from the table (never listed, lennard_jones.rs:216-222 skips it), on a box large enough for interior warps (the packed
+    FP32 v3 build without the image search) and boundary warps alike.  Rows exact against the oracle for the scalar
+    pre-filter build (variant 4) and the packed-FP32 v3 build with its shared-memory band table (6, 7, and the default)."""
+    atoms = fcc_argon(12, temperature=30.0, seed=5, jitter=0.25)
+    n = atoms.n_atoms
+    types = (1 + (np.arange(n) * 7 + (np.arange(n) // 5)) % 3).astype(np.int32)
+    atoms = Atoms(types, [39.948, 20.18, 83.798], atoms.positions, atoms.sim_box, velocities=atoms.velocities)
+    table = {(1, 1): LennardJones(0.238, 3.405, 8.5), (1, 2): LennardJones(0.15, 3.0, 7.5), (2, 2): LennardJones(0.07, 2.8, 7.0),
+             (1, 3): LennardJones(0.3, 3.5, 9.0), (3, 3): LennardJones(0.4, 3.6, 6.2)}          # (2, 3) missing
+    orc = make_oracle(atoms, table)
+    start, nbr = orc.build_neighbour_list(atoms.positions, atoms.type_ids, extra=SKIN)
+    pe_ref, f_ref = orc.compute_potential(atoms.positions, atoms.type_ids)
+    mgr = make_manager(skin=SKIN, table=table, variant=variant)
+    mgr.attach(atoms)
+    pe = mgr.compute()
+    rows = mgr.neighbours(n)
+    ref_rows = csr_rows_sorted(start, nbr)
+    bad = [i for i in range(n) if not np.array_equal(rows[i], ref_rows[i])]
+    assert not bad, f"{len(bad)} rows differ, first atom {bad[0]}"
+    mgr.download(atoms, positions=False, velocities=False)
+    assert abs(pe - pe_ref) <= ENERGY_TOL * abs(pe_ref)
+    assert force_rel_err(atoms.forces, f_ref).max() <= FORCE_TOL
+    # and a short hot run with rebuilds on the same table
+    x, v, f = atoms.positions.copy(), atoms.velocities.copy(), np.zeros_like(atoms.positions)
+    ref = orc.run_nve(x, v, f, atoms.type_ids, 0.25, 40)
+    th = mgr.step_nve(0.25, 40)
+    assert np.max(np.abs(th["pe"] - ref[1:, 0]) / np.abs(ref[1:, 0])) <= ENERGY_TOL
+    assert np.max(np.abs(th["ke"] - ref[1:, 1]) / np.abs(ref[1:, 1])) <= ENERGY_TOL
