@@ -60,8 +60,8 @@ typedef struct {
     int64_t n_ghost;        /* ghost atoms (multi-GPU), 0 on a single GPU */
     int64_t n_cells[3];     /* cell grid */
     int64_t list_capacity;  /* neighbour slots per atom (K_max) */
-    int64_t max_neighbours; /* largest list length at the last build */
-    int64_t total_neighbours; /* sum of list lengths at the last build */
+    int64_t max_neighbours; /* longest list row any build has produced since the capacity was last set (a running maximum) */
+    int64_t capacity_growths; /* times the capacity was raised AHEAD of an overflow (longest row within 12 % of it) */
     int64_t n_builds;       /* neighbour-list builds so far */
     int64_t n_steps;        /* NVE steps so far */
     int64_t n_launches;     /* kernels launched by this handle so far */
@@ -142,7 +142,9 @@ PISB_API int pisb_nhc_init(pisb_nhc *out, double start_temperature, double end_t
  *   of this batch in the run; total_steps: the run length the temperature ramp refers to.
  *   out[s] as in pisb_step_nve (ke is the kinetic energy after the second thermostat scaling);
  *   nhc_energy[s] (may be NULL) = nhc.kinetic_energy() + nhc.potential_energy(n), the thermostat's share of the
- *   Hamiltonian (simulation.rs:101-104).  Single-GPU only. */
+ *   Hamiltonian (simulation.rs:101-104).  On bricks (after pisb_comm_init) the call is collective: every rank advances a
+ *   replica of the chain from the all-reduced kinetic energy (one 4-number all-reduce per step) and n is the global atom count;
+ *   out[] then holds global sums on every rank. */
 PISB_API int pisb_step_nvt_nhc(pisb_t *h, double dt, int64_t nsteps, pisb_nhc *chain, int64_t first_step,
                                int64_t total_steps, pisb_thermo *out, double *nhc_energy);
 

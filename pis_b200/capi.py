@@ -25,7 +25,7 @@ THERMO_DTYPE = np.dtype([("pe", "f8"), ("ke", "f8"), ("virial_ref", "f8"), ("vir
 
 class Stats(C.Structure):
     _fields_ = [("n_atoms", C.c_int64), ("n_ghost", C.c_int64), ("n_cells", C.c_int64 * 3),
-                ("list_capacity", C.c_int64), ("max_neighbours", C.c_int64), ("total_neighbours", C.c_int64),
+                ("list_capacity", C.c_int64), ("max_neighbours", C.c_int64), ("capacity_growths", C.c_int64),
                 ("n_builds", C.c_int64), ("n_steps", C.c_int64), ("n_launches", C.c_int64),
                 ("device_bytes", C.c_int64)]
 

@@ -91,6 +91,7 @@ struct pisb_handle {
     bool list_valid = false;   // a list exists for the current atom set / box
     bool forces_current = false;
     int kcap_user = 0;
+    int n_capacity_growths = 0;  // grow_list_if_close: times the capacity was raised ahead of an overflow
 
     // device arrays
     DevBuf<double4> xt, s_xt;
@@ -558,6 +559,22 @@ int reserve_thermo(pisb_t *h, size_t n) {
         h->h_thermo_cap = n;
     }
     return PISB_OK;
+}
+
+// Keep the list capacity AHEAD of the lists.  A build inside a batch cannot reallocate: if a row outgrows the capacity the
+// batch goes on with a truncated row and the damage is only seen when the host reads the flags again (PISB_ERR_CAPACITY).
+// So whenever the longest row seen since the last look (FLAG_MAXNBR, a running maximum) has come within 12 % of the
+// capacity -- nothing truncated yet -- the capacity is raised now and the next call starts with a fresh build.  Density
+// changes over many rebuilds, the host looks every batch (<= 4096 steps) or host-buffer step: an overflow needs the longest row to
+// jump by more than 12 % between two looks.  Not on bricks (a rebuild is collective there) and not against a user-set capacity.
+int grow_list_if_close(pisb_t *h) {
+    if (h->kcap_user > 0 || h->multi) return PISB_OK;
+    const int mx = h->h_flags[FLAG_MAXNBR];
+    if (mx > h->kcap || (double)mx <= 0.88 * (double)h->kcap) return PISB_OK;
+    h->kcap = (int)(mx * 1.3) + 8;
+    h->list_valid = false;
+    h->n_capacity_growths++;
+    return reserve_list(h);
 }
 
 // ---- launch sequences ------------------------------------------------------------------------
@@ -1225,6 +1242,8 @@ int do_step_nve(pisb_t *h, double dt, int64_t nsteps, pisb_thermo *out) {
         if (out) std::memcpy(out + done, h->h_thermo, sizeof(pisb_thermo) * m);
         done += m;
         h->n_steps += m;
+        TRY(grow_list_if_close(h));
+        if (!h->list_valid && done < nsteps) TRY(ensure_list(h));
     }
     h->forces_current = true;
     return PISB_OK;
@@ -1252,10 +1271,13 @@ int enqueue_nvt_steps(pisb_t *h, double dt, int64_t cnt, int64_t total_steps, pi
     return check_launch(h, "nvt step");
 }
 
+int do_step_nvt_multi(pisb_t *h, double dt, int64_t nsteps, pisb_nhc *chain, int64_t first_step, int64_t total_steps,
+                      pisb_thermo *out, double *nhc_energy);
+
 int do_step_nvt(pisb_t *h, double dt, int64_t nsteps, pisb_nhc *chain, int64_t first_step, int64_t total_steps,
                 pisb_thermo *out, double *nhc_energy) {
     if (!h->have_atoms || !h->have_box) return fail(h, PISB_ERR_STATE, "set_box and upload must precede step_nvt_nhc");
-    if (h->multi) return fail(h, PISB_ERR_STATE, "pisb_step_nvt_nhc is a single-GPU entry point");
+    if (h->multi) return do_step_nvt_multi(h, dt, nsteps, chain, first_step, total_steps, out, nhc_energy);
     if (!chain || chain->chain_size != 3) return fail(h, PISB_ERR_INVALID, "chain must be a 3-link pisb_nhc (pisb_nhc_init)");
     if (nsteps < 0 || total_steps <= 0) return fail(h, PISB_ERR_INVALID, "bad step counts");
     if (nsteps == 0) return PISB_OK;
@@ -1329,6 +1351,8 @@ int do_step_nvt(pisb_t *h, double dt, int64_t nsteps, pisb_nhc *chain, int64_t f
         if (nhc_energy) std::memcpy(nhc_energy + done, he.data(), sizeof(double) * m);
         done += m;
         h->n_steps += m;
+        TRY(grow_list_if_close(h));
+        if (!h->list_valid && done < nsteps) TRY(ensure_list(h));
     }
     NhcDev fin{};
     CUDA_TRY(h, cudaMemcpy(&fin, h->nhc_d.p, sizeof fin, cudaMemcpyDeviceToHost));
@@ -1494,6 +1518,7 @@ int do_step_npt(pisb_t *h, double dt, int64_t nsteps, pisb_mtk *baro, pisb_nhc *
                 h->list_valid = false;
                 return fail(h, PISB_ERR_CAPACITY, "a neighbour list overflowed during the batch; re-upload the state and repeat the call");
             }
+            TRY(grow_list_if_close(h));  // a compressing box makes the rows longer: raise the capacity before one overflows (the next step rebuilds)
             std::memcpy(tensors, h->h_npt, sizeof tensors);
             volume = std::fabs(m3::det(h->box.h));
             mtk_delta_momentum(*baro, tensors, volume, dt, dm);
@@ -2038,6 +2063,79 @@ int do_step_nve_multi(pisb_t *h, double dt, int64_t nsteps, pisb_thermo *out) {
     return PISB_OK;
 }
 
+// verlet_step_nvt_nhc (potential.rs:35-58) on bricks.  The thermostat needs the GLOBAL kinetic energy twice per step: the
+// chain of every rank is advanced from the same all-reduced numbers by the same one-thread kernel, so the replicas stay
+// bit-identical without ever being exchanged.  Per step: chain half step, scaled drift, halo exchange (ghost positions +
+// the global rebuild decision), [collective rebuild], force, scaled kick (local KE / virial / PE of the owned atoms), ONE
+// all-reduce of the step's 4-number thermo record, chain half step from the reduced KE.
+int do_step_nvt_multi(pisb_t *h, double dt, int64_t nsteps, pisb_nhc *chain, int64_t first_step, int64_t total_steps,
+                      pisb_thermo *out, double *nhc_energy) {
+    if (!chain || chain->chain_size != 3) return fail(h, PISB_ERR_INVALID, "chain must be a 3-link pisb_nhc (pisb_nhc_init)");
+    if (nsteps < 0 || total_steps <= 0) return fail(h, PISB_ERR_INVALID, "bad step counts");
+    if (nsteps == 0) return PISB_OK;
+    if (!h->list_valid) TRY(multi_rebuild(h));
+    TRY(check_bad_type(h));
+    const int64_t chunk_max = 1024;
+    TRY(dev_reserve(h, h->nhc_d, 1));
+    TRY(dev_reserve(h, h->nhc_energy_d, (size_t)chunk_max));
+    TRY(reserve_thermo(h, (size_t)chunk_max + 2));
+    // the state entering the batch: global KE (potential.rs:41) and the global atom count (3N degrees of freedom)
+    pisb_thermo *ke0 = h->thermo_d.p + chunk_max;
+    {
+        LaunchScope ls(h, PISB_K_REDUCE);
+        k_observe<<<nblk(h->n, TPB), TPB, 0, h->stream>>>(h->n, h->xt.p, h->v[0].p, h->v[1].p, h->v[2].p, h->f[0].p, h->f[1].p,
+                                                          h->f[2].p, h->mass_d.p, h->partials.p, h->ticket, ke0);
+        TRY(check_launch(h, "k_observe"));
+        const double own = (double)h->n_own;  // rides in the spare record's pe slot through the same all-reduce
+        CUDA_TRY(h, cudaMemcpyAsync(&ke0->pe, &own, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        NCCL_TRY(h, g_nccl.AllReduce(ke0, ke0, 4, ncclDouble, ncclSum, h->comm, h->stream));
+        CUDA_TRY(h, cudaMemcpyAsync(h->h_thermo, ke0, sizeof(pisb_thermo), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    }
+    const long long n_global = (long long)std::llround(h->h_thermo[0].pe);
+    NhcDev init{};
+    init.c = *chain;
+    init.scale = 1.0;
+    init.ke_last = h->h_thermo[0].ke;
+    init.step_index = first_step;
+    CUDA_TRY(h, cudaMemcpyAsync(h->nhc_d.p, &init, sizeof init, cudaMemcpyHostToDevice, h->stream));
+    int64_t done = 0;
+    while (done < nsteps) {
+        const int64_t m = std::min(chunk_max, nsteps - done);
+        for (int64_t s = 0; s < m; ++s) {
+            pisb_thermo *rec = h->thermo_d.p + s;
+            k_nhc_half<<<1, 32, 0, h->stream>>>(h->nhc_d.p, nullptr, n_global, dt, 0, -1, 1, nullptr);
+            TRY(launch_vv(h, false, true, dt, nullptr, &h->nhc_d.p->scale));
+            TRY(halo_exchange(h, true));
+            TRY(read_flags(h));
+            if (h->h_flags[FLAG_COMM_TIMEOUT]) return fail(h, PISB_ERR_COMM, "timed out waiting for a peer's ghost data (peer-memory halo)");
+            if (h->h_flags[FLAG_REBUILD] != 0) TRY(multi_rebuild(h));
+            double *outp[3] = {h->g[0].p, h->g[1].p, h->g[2].p};
+            TRY(launch_force(h, outp, nullptr, rec));
+            for (int d = 0; d < 3; ++d) std::swap(h->f[d], h->g[d]);
+            TRY(launch_vv(h, true, false, dt, rec, &h->nhc_d.p->scale));
+            {
+                LaunchScope ls(h, PISB_K_REDUCE);
+                NCCL_TRY(h, g_nccl.AllReduce(rec, rec, 4, ncclDouble, ncclSum, h->comm, h->stream));
+            }
+            k_nhc_half<<<1, 32, 0, h->stream>>>(h->nhc_d.p, &rec->ke, n_global, dt, 1, -1, (long long)total_steps, h->nhc_energy_d.p + s);
+            h->n_launches += 2;
+        }
+        TRY(check_launch(h, "nvt step (bricks)"));
+        CUDA_TRY(h, cudaMemcpyAsync(h->h_thermo, h->thermo_d.p, sizeof(pisb_thermo) * m, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        if (out) std::memcpy(out + done, h->h_thermo, sizeof(pisb_thermo) * m);
+        if (nhc_energy) CUDA_TRY(h, cudaMemcpy(nhc_energy + done, h->nhc_energy_d.p, sizeof(double) * m, cudaMemcpyDeviceToHost));
+        done += m;
+        h->n_steps += m;
+    }
+    NhcDev fin{};
+    CUDA_TRY(h, cudaMemcpy(&fin, h->nhc_d.p, sizeof fin, cudaMemcpyDeviceToHost));
+    *chain = fin.c;
+    h->forces_current = true;
+    return PISB_OK;
+}
+
 }  // namespace
 
 // ================================================================================================
@@ -2468,12 +2566,13 @@ static int host_step_pipelined(pisb_t *h, double *pos, double *vel, double *forc
     }
     if (h->h_flags[FLAG_MAXNBR] > h->kcap) {
         h->list_valid = false;
-        return fail(h, PISB_ERR_CAPACITY, "a neighbour list overflowed during the step; repeat the call (capacity grows on the next build)");
+        return fail(h, PISB_ERR_CAPACITY, "a neighbour list overflowed during the step: the arrays hold a step computed from a truncated list -- "
+                                          "restore x, v, F as they were before the call and repeat it (the capacity grows on the next build)");
     }
     h->n_steps += 1;
     h->forces_current = true;
     if (pe) *pe = h->h_thermo[0].pe;
-    return PISB_OK;
+    return grow_list_if_close(h);
 }
 
 int pisb_verlet_step_nve_host(pisb_t *h, int64_t n, double *pos, double *vel, double *force,
@@ -2527,12 +2626,13 @@ int pisb_verlet_step_nve_host(pisb_t *h, int64_t n, double *pos, double *vel, do
     }
     if (h->h_flags[FLAG_MAXNBR] > h->kcap) {
         h->list_valid = false;
-        return fail(h, PISB_ERR_CAPACITY, "a neighbour list overflowed during the step; repeat the call (capacity grows on the next build)");
+        return fail(h, PISB_ERR_CAPACITY, "a neighbour list overflowed during the step: the arrays hold a step computed from a truncated list -- "
+                                          "restore x, v, F as they were before the call and repeat it (the capacity grows on the next build)");
     }
     h->n_steps += 1;
     h->forces_current = true;
     if (pe) *pe = h->h_thermo[0].pe;
-    return PISB_OK;
+    return grow_list_if_close(h);
 }
 
 int pisb_neighbours(pisb_t *h, int32_t *nnbr, int32_t *nbr, int64_t cap_per_atom) {
@@ -2626,7 +2726,7 @@ int pisb_stats(pisb_t *h, pisb_stats_t *out) {
     for (int d = 0; d < 3; ++d) out->n_cells[d] = h->grid.n[d];
     out->list_capacity = h->kcap;
     out->max_neighbours = h->max_nbr;
-    out->total_neighbours = h->total_nbr;
+    out->capacity_growths = h->n_capacity_growths;
     out->n_builds = h->n_builds_host;
     out->n_steps = h->n_steps;
     out->n_launches = h->n_launches;

@@ -48,6 +48,12 @@ def run_check(rank: int, world: int, local: int, ncell: int = 16, steps: int = 6
     st = mgr.stats()
     (F0,) = gather_by_gid(g0, [f0], n_global)
     X1, V1, F1 = gather_by_gid(g1, [x1, v1, f1], n_global)
+    # verlet_step_nvt_nhc on bricks (pisb_step_nvt_nhc, collective): Nose-Hoover chain replicated per rank, fed with the
+    # all-reduced kinetic energy; 30 steps of a 60 K -> 90 K ramp continuing from the NVE state
+    chain = mgr.nhc_new(T0, 1.5 * T0, 25.0)
+    th_nvt, en_nvt = mgr.step_nvt_nhc(0.25, 30, chain, 0, 30)
+    g3, x3, v3, _ = (a_.copy() for a_ in mgr.download_owned(forces=False))
+    X3, V3 = gather_by_gid(g3, [x3, v3], n_global)
     # `velocity all create` on the device (pisb_start_velocities, collective): the bricks must get, per global id, the velocities
     # one GPU generates (id-keyed generator, all-reduced drift / kinetic-energy sums)
     mgr.start_velocities(35.0, 4242)
@@ -74,6 +80,18 @@ def run_check(rank: int, world: int, local: int, ncell: int = 16, steps: int = 6
         th_ref = single.step_nve(0.25, steps)
         single.download(ref)
         x_end, v_end, f_end = ref.positions.copy(), ref.velocities.copy(), ref.forces.copy()
+        chain_ref = single.nhc_new(T0, 1.5 * T0, 25.0)
+        th_nvt_ref, en_nvt_ref = single.step_nvt_nhc(0.25, 30, chain_ref, 0, 30)
+        single.download(ref)
+        nvt = {
+            "pe_trace_rel": float(np.max(np.abs(th_nvt["pe"] - th_nvt_ref["pe"]) / np.abs(th_nvt_ref["pe"]))),
+            "ke_trace_rel": float(np.max(np.abs(th_nvt["ke"] - th_nvt_ref["ke"]) / np.abs(th_nvt_ref["ke"]))),
+            "thermostat_energy_rel": float(np.max(np.abs(en_nvt - en_nvt_ref) / np.maximum(np.abs(en_nvt_ref), 1e-3))),
+            "xi_rel": float(max(abs(a_ - b_) / max(abs(b_), 1e-12) for a_, b_ in zip(chain.xi, chain_ref.xi))),
+            "pos_max_abs": float(np.abs(X3 - ref.positions).max()), "vel_max_abs": float(np.abs(V3 - ref.velocities).max()),
+        }
+        nvt["ok"] = bool(nvt["pe_trace_rel"] < 1e-9 and nvt["ke_trace_rel"] < 1e-9 and nvt["thermostat_energy_rel"] < 1e-9
+                         and nvt["xi_rel"] < 1e-9 and nvt["pos_max_abs"] < 1e-9)
         single.start_velocities(35.0, 4242)
         single.download(ref, positions=False, forces=False)
         v_init_err = float(np.abs(V2 - ref.velocities).max() / np.abs(ref.velocities).max())
@@ -96,12 +114,12 @@ def run_check(rank: int, world: int, local: int, ncell: int = 16, steps: int = 6
             "virial_ref_trace_rel": float(np.max(np.abs(th["virial_ref"] - th_ref["virial_ref"]) / np.maximum(np.abs(th_ref["virial_ref"]), 1.0))),
             "pos_max_abs": float(np.abs(X1 - ref.positions).max()),
             "vel_max_abs": float(np.abs(V1 - ref.velocities).max()),
-            "start_velocities_rel": v_init_err,
+            "start_velocities_rel": v_init_err, "nvt": nvt,
             "builds_multi": [p[2]["n_builds"] for p in pieces], "builds_single": single.stats()["n_builds"],
             "owned": [p[2]["n_atoms"] for p in pieces], "ghost": [p[2]["n_ghost"] for p in pieces],
         }
         ok = (mism == 0 and out["force_rel"] < 1e-10 and out["force0_max_abs"] < 1e-12 and out["pe0_rel"] < 1e-9 and out["pe_trace_rel"] < 1e-9
-              and out["ke_trace_rel"] < 1e-9 and v_init_err < 1e-12)
+              and out["ke_trace_rel"] < 1e-9 and v_init_err < 1e-12 and nvt["ok"])
         out["ok"] = bool(ok)
         single.close()
     dist.barrier()

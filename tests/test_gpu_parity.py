@@ -920,3 +920,34 @@ def test_multi_type_lists_exact_with_every_build(variant):
     th = mgr.step_nve(0.25, 40)
     assert np.max(np.abs(th["pe"] - ref[1:, 0]) / np.abs(ref[1:, 0])) <= ENERGY_TOL
     assert np.max(np.abs(th["ke"] - ref[1:, 1]) / np.abs(ref[1:, 1])) <= ENERGY_TOL
+
+
+def test_list_capacity_is_raised_ahead_of_an_overflow_in_a_compressing_box():
+    """A build inside a batch cannot reallocate, so the capacity must stay AHEAD of the rows (grow_list_if_close: raised as
+    soon as the longest row comes within 12 % of it, nothing truncated yet).  Scenario: an expanded lattice (a = 6.0) under
+    NPT collapses by 45 % in volume within 130 steps -- the rows grow from ~67 to ~120 entries, past the 112 slots the
+    initial density suggested.  The run must go through without PISB_ERR_CAPACITY, raise the capacity on the way, and
+    still follow the oracle's NPT trace."""
+    atoms = fcc_argon(7, temperature=5.0, seed=12345, a=6.0)
+    table = {(1, 1): argon_pair(8.5)}
+    orc = make_oracle(atoms, table)
+    chain_ref = orc.nhc_new(5.0, 50.0, 100.0)
+    baro_ref = orc.mtk_new(0.02, 100.0, atoms.n_atoms, 5.0)
+    x, v = atoms.positions.copy(), atoms.velocities.copy()
+    steps = 130
+    ref, htr = orc.run_npt(x, v, np.zeros_like(x), atoms.type_ids, 0.25, steps, baro_ref, chain_ref)
+    mgr = make_manager(skin=SKIN, rc=8.5)
+    mgr.attach(atoms)
+    mgr.compute()
+    cap0 = mgr.stats()["list_capacity"]
+    chain = mgr.nhc_new(5.0, 50.0, 100.0)
+    baro = mgr.mtk_new(0.02, 100.0, atoms.n_atoms, 5.0)
+    th, en, hh = mgr.step_npt_mtk(0.25, steps, baro, chain, 0, steps, atoms)
+    st = mgr.stats()
+    assert st["capacity_growths"] >= 1 and st["list_capacity"] > cap0 and st["max_neighbours"] > cap0
+    vol = np.abs(np.linalg.det(hh))
+    assert vol[-1] < 0.65 * vol[0]
+    assert np.max(np.abs(th["pe"] - ref[1:, 0]) / np.abs(ref[1:, 0])) <= 1e-8
+    assert np.max(np.abs(th["ke"] - ref[1:, 1]) / np.abs(ref[1:, 1])) <= 1e-8
+    h_ref = htr[1:].reshape(-1, 3, 3).transpose(0, 2, 1)
+    assert np.abs(hh - h_ref).max() <= 1e-8 * np.abs(h_ref).max()
