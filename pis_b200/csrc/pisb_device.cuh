@@ -139,8 +139,11 @@ __device__ __forceinline__ double rcp_newton(double x) {
     return fma(y, e, y);
 }
 
-// non-negative doubles order like their bit patterns: keeps the cutoff tests off the FP64 pipe
-__device__ __forceinline__ bool le_bits(double a, double b) { return __double_as_longlong(a) <= __double_as_longlong(b); }
+// non-negative doubles order like their bit patterns: keeps the cutoff tests off the FP64 pipe.  Unsigned, so that a NaN
+// of either sign (the squared distance to the NaN record behind a list pad) compares above every finite threshold.
+__device__ __forceinline__ bool le_bits(double a, double b) {
+    return (unsigned long long)__double_as_longlong(a) <= (unsigned long long)__double_as_longlong(b);
+}
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

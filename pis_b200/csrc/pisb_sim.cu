@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <ctime>
 #include <string>
 #include <vector>
@@ -77,6 +78,8 @@ struct pisb_handle {
     int force_variant = 0;  // 0 = auto (v3 when orthorhombic + fully periodic, else v1), 1 = v1, 2 = v2, 3 = v3
     int build_variant = 0;
     int cell_div = 0;  // cells per list cutoff per dimension: 0 = auto, 1 = reference-sized cells, 2 = half-size cells
+    int build_window = 1;  // v3 build: per-row x window for interior warps (0 = scan the whole stencil row, for A/B)
+    int list_align = 0;    // v3 build: pad the rows of a warp to a common length after every stencil plane (1) / stencil row (2)
     int fuse_vv = 1;   // option "fuse_vv": NVE batches run k_force_vv (force + kick + drift in one launch) when the default force kernel applies
 
     // box / grid
@@ -112,6 +115,8 @@ struct pisb_handle {
     DevBuf<double> npt_tensors_d;
     DevBuf<double> vel_sums_d;  // pisb_start_velocities: total mass, momentum, atom count, kinetic energy
     double *h_npt = nullptr;         // pinned: 19 reduced tensor sums + thermostat energy
+    double *h_energy = nullptr;      // pinned: thermostat energy per step of an NVT batch (a pageable target would make every
+    size_t h_energy_cap = 0;         //         piece's read-back a synchronous copy)
     double skin_half2_override = -1.0;  // NPT: skin trigger threshold reduced by the accumulated box strain
     DevBuf<pisb_thermo> thermo_d;
     int *flags = nullptr;
@@ -212,6 +217,38 @@ int dev_reserve(pisb_t *h, DevBuf<T> &b, size_t n) {
     b.cap = n;
     h->device_bytes += (int64_t)(n * sizeof(T));
     return PISB_OK;
+}
+
+// Position buffers (xt / s_xt) carry one extra record IN FRONT of slot 0: {NaN, NaN, NaN, type 1}.  A list pad gathers it
+// (index -1 after one IMNMX in the force loop); its squared distance is NaN and fails every range test.
+int reserve_positions(pisb_t *h, DevBuf<double4> &b, size_t n) {
+    if (n <= b.cap) return PISB_OK;
+    if (b.p) {
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        CUDA_TRY(h, cudaFree(b.p - 1));
+        h->device_bytes -= (int64_t)((b.cap + 1) * sizeof(double4));
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    double4 *raw = nullptr;
+    CUDA_TRY(h, cudaMalloc((void **)&raw, (n + 1) * sizeof(double4)));
+    const double qnan = std::numeric_limits<double>::quiet_NaN();
+    double4 rec;
+    rec.x = rec.y = rec.z = qnan;
+    const long long type_one = 1;
+    std::memcpy(&rec.w, &type_one, sizeof(double));
+    CUDA_TRY(h, cudaMemcpy(raw, &rec, sizeof rec, cudaMemcpyHostToDevice));
+    b.p = raw + 1;
+    b.cap = n;
+    h->device_bytes += (int64_t)((n + 1) * sizeof(double4));
+    return PISB_OK;
+}
+
+void free_positions(pisb_t *h, DevBuf<double4> &b) {
+    if (b.p) cudaFree(b.p - 1);
+    if (b.cap) h->device_bytes -= (int64_t)((b.cap + 1) * sizeof(double4));
+    b.p = nullptr;
+    b.cap = 0;
 }
 
 // For buffers whose size follows a fluctuating count (migration / halo): grow with 50 % head-room so
@@ -497,18 +534,20 @@ int estimate_kcap(pisb_t *h) {
     const double n_glob = h->multi ? (double)h->n_own * h->dc.nranks : (double)h->n;
     double k = vol > 0 ? n_glob / vol * 4.18879020478639 * rl * rl * rl : 64.0;
     k = 1.3 * k + 24.0;
-    if (k > n_glob) k = std::max(n_glob, 1.0);
+    if (h->list_align == 1) k *= 1.35;  // alignment pads (measured on the thermal argon lattice: +31 % per plane, +71 % per row)
+    if (h->list_align == 2) k *= 1.8;
+    if (k > n_glob && !h->list_align) k = std::max(n_glob, 1.0);
     if (k > 4096.0) k = 4096.0;
     return (int)std::ceil(k);
 }
 
 int reserve_atoms(pisb_t *h, int n) {
     const size_t cap = (size_t)n;
-    TRY(dev_reserve(h, h->xt, cap));
+    TRY(reserve_positions(h, h->xt, cap));
     TRY(dev_reserve(h, h->xf, cap));
     TRY(dev_reserve(h, h->xf2, cap));
     TRY(dev_reserve(h, h->xp, ((cap + 1) / 2 + 32) * 8));
-    TRY(dev_reserve(h, h->s_xt, cap));
+    TRY(reserve_positions(h, h->s_xt, cap));
     for (int d = 0; d < 3; ++d) {
         TRY(dev_reserve(h, h->v[d], cap));
         TRY(dev_reserve(h, h->f[d], cap));
@@ -626,7 +665,12 @@ int launch_rebuild_chain(pisb_t *h) {
         if (v2) {
             if (!v2_possible(h)) return fail(h, PISB_ERR_INVALID, "build_variant 2/3 needs an orthorhombic, fully periodic box");
             Build2Args b2{n, h->npad, h->kcap, h->xt.p, h->xf.p, h->cell_start.p, h->box, h->boxf, g, h->pairs[0],
-                          h->pairsf[0], h->table_d.p, h->tablef_d.p, h->n_types, h->nbr.p, h->nnbr.p, h->flags};
+                          h->pairsf[0], h->table_d.p, h->tablef_d.p, h->n_types, h->nbr.p, h->nnbr.p, h->flags, 0.f, h->list_align};
+            if (h->build_window) {
+                float r2max = 0.f;  // hi_list is already the FP32 acceptance bound rounded up
+                for (const PairF &pf : h->pairsf) r2max = std::max(r2max, pf.hi_list);
+                b2.clip_r2 = r2max > 0.f ? f32_above((double)r2max * (1.0 + 1e-5)) : 0.f;
+            }
             if (h->build_variant == 2) {  // v2: scalar FP32 pre-filter (kept for A/B)
                 if (multi) k_build_list_v2<true><<<nb, TPB_FORCE, 0, st>>>(b2);
                 else k_build_list_v2<false><<<nb, TPB_FORCE, 0, st>>>(b2);
@@ -1079,7 +1123,7 @@ void graph_signature(pisb_t *h, double dt, std::vector<unsigned char> &sig) {
                           h->tile_sum.p, h->mass_d.p, h->partials.p, h->table_d.p, h->thermo_d.p, h->flags, h->ticket, h->nhc_d.p,
                           h->nhc_energy_d.p};
     put(ptrs, sizeof ptrs);
-    const int ints[] = {h->n, h->npad, h->kcap, h->n_types, h->force_variant, h->build_variant, h->cell_div, h->fuse_vv,
+    const int ints[] = {h->n, h->npad, h->kcap, h->n_types, h->force_variant, h->build_variant, h->cell_div, h->build_window, h->list_align, h->fuse_vv,
                         quad_mode(h) ? 1 : 0};
     put(ints, sizeof ints);
     const double dbl[] = {dt, h->skin, h->skin_half2_override, h->max_rcut};
@@ -1305,10 +1349,15 @@ int do_step_nvt(pisb_t *h, double dt, int64_t nsteps, pisb_nhc *chain, int64_t f
     CUDA_TRY(h, cudaMemcpyAsync(h->nhc_d.p, &init, sizeof init, cudaMemcpyHostToDevice, h->stream));
     const bool graphs = h->use_graphs && !h->profiling;
     int64_t done = 0;
-    std::vector<double> he;
+    if (h->h_energy_cap < (size_t)chunk_max) {
+        if (h->h_energy) cudaFreeHost(h->h_energy);
+        h->h_energy = nullptr, h->h_energy_cap = 0;
+        CUDA_TRY(h, cudaHostAlloc((void **)&h->h_energy, sizeof(double) * chunk_max, cudaHostAllocDefault));
+        h->h_energy_cap = (size_t)chunk_max;
+    }
+    double *he = h->h_energy;
     while (done < nsteps) {
         const int64_t m = std::min(chunk_max, nsteps - done);
-        he.resize((size_t)m);
         const int builds_before = (int)h->n_builds_host;
         int64_t off = 0, graph_steps = 0;
         while (off < m) {
@@ -1334,7 +1383,7 @@ int do_step_nvt(pisb_t *h, double dt, int64_t nsteps, pisb_nhc *chain, int64_t f
                 TRY(enqueue_nvt_steps(h, dt, piece, total_steps, h->thermo_d.p, h->nhc_energy_d.p));
             }
             CUDA_TRY(h, cudaMemcpyAsync(h->h_thermo + off, h->thermo_d.p, sizeof(pisb_thermo) * piece, cudaMemcpyDeviceToHost, h->stream));
-            CUDA_TRY(h, cudaMemcpyAsync(he.data() + off, h->nhc_energy_d.p, sizeof(double) * piece, cudaMemcpyDeviceToHost, h->stream));
+            CUDA_TRY(h, cudaMemcpyAsync(he + off, h->nhc_energy_d.p, sizeof(double) * piece, cudaMemcpyDeviceToHost, h->stream));
             off += piece;
         }
         TRY(read_flags(h));
@@ -1348,7 +1397,7 @@ int do_step_nvt(pisb_t *h, double dt, int64_t nsteps, pisb_nhc *chain, int64_t f
             return fail(h, PISB_ERR_CAPACITY, "a neighbour list overflowed during the batch; re-upload the state and repeat the call");
         }
         if (out) std::memcpy(out + done, h->h_thermo, sizeof(pisb_thermo) * m);
-        if (nhc_energy) std::memcpy(nhc_energy + done, he.data(), sizeof(double) * m);
+        if (nhc_energy) std::memcpy(nhc_energy + done, he, sizeof(double) * m);
         done += m;
         h->n_steps += m;
         TRY(grow_list_if_close(h));
@@ -2210,11 +2259,11 @@ int pisb_destroy(pisb_t *h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);  // a download still in flight
-    dev_free(h, h->xt);
+    free_positions(h, h->xt);
     dev_free(h, h->xf);
     dev_free(h, h->xp);
     dev_free(h, h->tablef_d);
-    dev_free(h, h->s_xt);
+    free_positions(h, h->s_xt);
     dev_free(h, h->xf2);
     dev_free(h, h->dl_pos);
     dev_free(h, h->dl_vel);
@@ -2249,6 +2298,7 @@ int pisb_destroy(pisb_t *h) {
     dev_free(h, h->nhc_energy_d);
     dev_free(h, h->npt_tensors_d);
     if (h->h_npt) cudaFreeHost(h->h_npt);
+    if (h->h_energy) cudaFreeHost(h->h_energy);
     dev_free(h, h->thermo_d);
     dev_free(h, h->m_dest);
     dev_free(h, h->m_pig);
@@ -2645,10 +2695,10 @@ int pisb_neighbours(pisb_t *h, int32_t *nnbr, int32_t *nbr, int64_t cap_per_atom
         TRY(ensure_list(h));
     }
     const int n = h->n;
-    std::vector<int> hn(n), hid(n), hl(nbr ? (size_t)h->kcap * h->npad : 0);  // the list itself only when rows are wanted
+    std::vector<int> hn(n), hid(n), hl(nbr || h->list_align ? (size_t)h->kcap * h->npad : 0);  // the list itself only when rows are wanted (or pads must be told from entries)
     CUDA_TRY(h, cudaMemcpyAsync(hn.data(), h->nnbr.p, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(hid.data(), h->id.p, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
-    if (nbr) CUDA_TRY(h, cudaMemcpyAsync(hl.data(), h->nbr.p, sizeof(int) * hl.size(), cudaMemcpyDeviceToHost, h->stream));
+    if (!hl.empty()) CUDA_TRY(h, cudaMemcpyAsync(hl.data(), h->nbr.p, sizeof(int) * hl.size(), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     auto entry = [&](int s, int k) -> int { return hl[nbr_at(k, s, h->npad)]; };
     int64_t total = 0;
@@ -2661,12 +2711,21 @@ int pisb_neighbours(pisb_t *h, int32_t *nnbr, int32_t *nbr, int64_t cap_per_atom
             long long wb;
             std::memcpy(&wb, &hx[s].w, 8);
             if ((wb >> 32) & 1) continue;
-            nnbr[o] = hn[s];
-            total += hn[s];
-            if (nbr) {
-                if (hn[s] > cap_per_atom) return fail(h, PISB_ERR_CAPACITY, "cap_per_atom too small");
-                for (int k = 0; k < hn[s]; ++k) nbr[(size_t)o * cap_per_atom + k] = hid[entry(s, k)];
+            int real = hn[s];
+            if (!hl.empty()) {  // alignment pads are no neighbours
+                real = 0;
+                for (int k = 0; k < hn[s]; ++k) {
+                    const int j = entry(s, k);
+                    if (nbr_is_pad(j)) continue;
+                    if (nbr) {
+                        if (real >= cap_per_atom) return fail(h, PISB_ERR_CAPACITY, "cap_per_atom too small");
+                        nbr[(size_t)o * cap_per_atom + real] = hid[j];
+                    }
+                    ++real;
+                }
             }
+            nnbr[o] = real;
+            total += real;
             ++o;
         }
         h->total_nbr = total;
@@ -2674,12 +2733,21 @@ int pisb_neighbours(pisb_t *h, int32_t *nnbr, int32_t *nbr, int64_t cap_per_atom
     }
     for (int s = 0; s < n; ++s) {
         const int o = hid[s];
-        nnbr[o] = hn[s];
-        total += hn[s];
-        if (nbr) {
-            if (hn[s] > cap_per_atom) return fail(h, PISB_ERR_CAPACITY, fmt("cap_per_atom %lld < list length %d", (long long)cap_per_atom, hn[s]));
-            for (int k = 0; k < hn[s]; ++k) nbr[(size_t)o * cap_per_atom + k] = hid[entry(s, k)];
+        int real = hn[s];
+        if (!hl.empty()) {  // alignment pads are no neighbours
+            real = 0;
+            for (int k = 0; k < hn[s]; ++k) {
+                const int j = entry(s, k);
+                if (nbr_is_pad(j)) continue;
+                if (nbr) {
+                    if (real >= cap_per_atom) return fail(h, PISB_ERR_CAPACITY, fmt("cap_per_atom %lld < list length of atom %d", (long long)cap_per_atom, o));
+                    nbr[(size_t)o * cap_per_atom + real] = hid[j];
+                }
+                ++real;
+            }
         }
+        nnbr[o] = real;
+        total += real;
     }
     h->total_nbr = total;
     return PISB_OK;
@@ -2707,7 +2775,7 @@ int pisb_list_stats(pisb_t *h, int64_t *out3) {
     dev_free(h, d);
     out3[0] = (int64_t)host[0];
     out3[1] = (int64_t)host[1];
-    out3[2] = (int64_t)host[0];  // index words stored == listed pairs for per-atom rows
+    out3[2] = (int64_t)(host[0] + host[2]);  // index words stored: listed pairs + alignment pads
     h->total_nbr = (int64_t)host[0];
     return PISB_OK;
 }
@@ -2952,8 +3020,16 @@ int pisb_set_option(pisb_t *h, const char *name, double value) {
         h->force_variant = v;
         return PISB_OK;
     }
-    if (!std::strcmp(name, "build_variant") || !std::strcmp(name, "cell_div")) {
-        if (name[0] == 'b') h->build_variant = (int)value;
+    if (!std::strcmp(name, "build_variant") || !std::strcmp(name, "cell_div") || !std::strcmp(name, "build_window") ||
+        !std::strcmp(name, "list_align")) {
+        if (!std::strcmp(name, "build_window")) h->build_window = value != 0.0 ? 1 : 0;
+        else if (!std::strcmp(name, "list_align")) {
+            const int v = (int)value;
+            if (v < 0 || v > 2) return fail(h, PISB_ERR_INVALID, fmt("list_align %d does not exist (0, 1, 2)", v));
+            h->list_align = v;
+            h->kcap = 0;  // the capacity estimate depends on it
+        }
+        else if (name[0] == 'b') h->build_variant = (int)value;
         else h->cell_div = (int)value;
         h->list_valid = false;
         h->grid_ok = false;
