@@ -274,12 +274,6 @@ PISB_API int pisb_list_stats(pisb_t *h, int64_t *out3);
  *                     7 = k_force_q: 4 lanes per atom taking one entry of every K-tile each
  *   build_variant     0 = automatic (v3), 1 = v1 general, 2 = scalar FP32 pre-filter, 3 = packed-FP32 pair records
  *   cell_div          cells per list cutoff and dimension: 0 = automatic (2 with build_variant 2/3), 1, 2
- *   list_align        0 (default) = list rows as the stencil walk produces them; 1 / 2 = the v3 build pads the rows of a
- *                     warp to a common length after every stencil plane / stencil row (pads are entries with the sign bit
- *                     set), so that entry k of 32 neighbouring atoms points into one window of consecutive slots and a
- *                     warp's position gather touches fewer 128-byte lines.  Same neighbours, same entry order
- *   build_window      1 (default) = the v3 build clips every stencil row to the x window that can hold a neighbour
- *                     (125 -> 83 cells scanned per atom, same lists); 0 = whole rows
  *   halo_mode         multi-GPU per-step ghost exchange: 0 = peer memory when it can be mapped, 1 = NCCL send/recv,
  *                     2 = peer memory or fail */
 PISB_API int pisb_set_option(pisb_t *h, const char *name, double value);

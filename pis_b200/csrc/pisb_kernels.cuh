@@ -44,17 +44,13 @@ __host__ __device__ __forceinline__ size_t nbr_at(int k, int i, int npad) {
     return ((size_t)(k >> 2) * (size_t)npad + (size_t)i) * 4 + (size_t)(k & 3);
 }
 
-// Every build closes the last K-tile of a row with pads (entries with the sign bit set, see NBR_PAD_BIT), so a consumer
-// that reads whole int4 tiles needs no `k + u < nn` test: a negative entry is no neighbour.
-__device__ __forceinline__ void nbr_close_row(int *nbr, int i, int npad, int cnt, int kcap) {
-    for (int k = cnt; (k & 3) && k < kcap; ++k) nbr[nbr_at(k, i, npad)] = (int)0x80000000u;
-}
-
-// Pads: an entry with the sign bit set is no neighbour.  Every build closes the last K-tile of a row with them, and
-// k_build_list_v3 with list_align uses them to keep the rows of a warp in step.  The position buffers carry a NaN record at
-// index -1, so the hot loop turns a pad into a gather of that record with one IMNMX instead of a predicate.
+// Pads: an entry with the sign bit set is no neighbour.  Every build closes the last K-tile of a row with them, and the
+// position buffers carry a NaN record at index -1 (reserve_positions), so the hot loop reads whole int4 tiles without a
+// `k < nn` test: one IMNMX turns a pad into a gather of that record, whose r2 is NaN and fails every range test.
 constexpr int NBR_PAD_BIT = (int)0x80000000u;
-__host__ __device__ __forceinline__ bool nbr_is_pad(int j) { return j < 0; }
+__device__ __forceinline__ void nbr_close_row(int *nbr, int i, int npad, int cnt, int kcap) {
+    for (int k = cnt; (k & 3) && k < kcap; ++k) nbr[nbr_at(k, i, npad)] = NBR_PAD_BIT;
+}
 
 struct Grid {
     int n[3];      // cells per dimension
@@ -863,7 +859,6 @@ __global__ void __launch_bounds__(TPB_FORCE) k_force(ForceArgs a) {
         for (int k = 0; k < nn; ++k) {
             const int j = jn;
             if (k + 1 < nn) jn = __ldg(a.nbr + nbr_at(k + 1, i, a.npad));
-            if (nbr_is_pad(j)) continue;
             const double4 xj = ldg_d4(&a.xt[j]);
             double dx = __dsub_rn(xj.x, xi.x), dy = __dsub_rn(xj.y, xi.y), dz = __dsub_rn(xj.z, xi.z);
             min_image<ORTHO>(a.box, dx, dy, dz);
@@ -1037,15 +1032,9 @@ __device__ __forceinline__ void force2_body(const Force2Args &a, int i, int (*q)
             {
                 const int4 t = __ldg(reinterpret_cast<const int4 *>(a.nbr) + ((size_t)(k >> 2) * a.npad + i));
                 j[0] = t.x;
-                j[1] = (k + 1 < nn) ? t.y : -1;
-                j[2] = (k + 2 < nn) ? t.z : -1;
-                j[3] = (k + 3 < nn) ? t.w : -1;
-            }
-            bool ok[FU];  // a real entry: not the tail of the last tile, not an alignment pad
-#pragma unroll
-            for (int u = 0; u < FU; ++u) {
-                ok[u] = !nbr_is_pad(j[u]);
-                if (!ok[u]) j[u] = i;
+                j[1] = (k + 1 < nn) ? t.y : i;
+                j[2] = (k + 2 < nn) ? t.z : i;
+                j[3] = (k + 3 < nn) ? t.w : i;
             }
 #pragma unroll
             for (int u = 0; u < FU; ++u) xjf[u] = __ldg(&a.xf[j[u]]);
@@ -1067,7 +1056,7 @@ __device__ __forceinline__ void force2_body(const Force2Args &a, int i, int (*q)
                     const double t_rc = MULTI ? a.table[pidx].t_rc : a.pair0.t_rc;
                     in = !(r2_exact_ortho(a.box, xi, xj) > t_rc);
                 }
-                if (in && ok[u]) {
+                if (in && (k + u < nn)) {
                     q[cnt][tid] = j[u];
                     ++cnt;
                 }
@@ -1188,7 +1177,6 @@ __device__ __noinline__ void force_atom_exact(const double4 *__restrict__ xt, co
     for (int k0 = 4 * l; k0 < nn; k0 += 4 * stride)
         for (int k = k0; k < min(k0 + 4, nn); ++k) {
             const int j = nbr[nbr_at(k, i, npad)];
-            if (nbr_is_pad(j)) continue;
             const double4 xj = ldg_d4(&xt[j]);
             double dx, dy, dz;
             const double r2 = lean_disp<IMAGE>(box, xi, xj, dx, dy, dz);
@@ -1222,8 +1210,8 @@ __device__ __forceinline__ void force3_body(const Force2Args &a, int i, double &
         if (rem > 4) nxt = ldg_stream_i4(tiles);
         const int j[4] = {cur.x, cur.y, cur.z, cur.w};
         double4 xj[4];
-        // a pad (the closed tail of the last tile, or an alignment pad) gathers the NaN record in front of slot 0
-        // (reserve_positions): its r2 is NaN and fails both range tests below -- one IMNMX, no predicate to keep alive
+        // a pad (the closed tail of the last tile) gathers the NaN record in front of slot 0 (reserve_positions): its r2 is
+        // NaN and fails both range tests below -- one IMNMX, no predicate to keep alive
 #pragma unroll
         for (int u = 0; u < 4; ++u) xj[u] = ldg_d4(&a.xt[max(j[u], -1)]);
 #pragma unroll
@@ -1411,7 +1399,7 @@ __device__ __forceinline__ void force_split_body(const Force2Args &a, int i, int
         double4 xj[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            in[u] = k + u < nn && !nbr_is_pad(j[u]);
+            in[u] = k + u < nn;
             if (!in[u]) j[u] = i;
         }
 #pragma unroll
@@ -1724,8 +1712,6 @@ struct Build2Args {
     int *nbr;
     int *nnbr;
     int *flags;
-    float clip_r2;  // v3 build: (largest list cutoff)^2 rounded up, for the per-row x window; <= 0 switches the window off
-    int align;      // v3 build: 0 = rows as they come, 1 = the rows of a warp padded to a common length after every stencil plane, 2 = after every stencil row
 };
 
 template <bool MULTI, bool IMAGE>
@@ -1902,7 +1888,7 @@ __device__ __noinline__ bool build3_exact_out(double h0, double h1, double h2, d
 // stale padding anything), so a candidate costs two LDS.64 on top of the single-type loop; a missing pair is {-1, -1} too.
 constexpr int B3_MAX_TYPES = 6;
 template <bool IMAGE, bool MULTI, int B3_PAIRS = 2>
-__device__ __forceinline__ int build3_body(const Build2Args &a, const float *__restrict__ xp, int i, const float2 *s_band, unsigned wmask) {
+__device__ __forceinline__ int build3_body(const Build2Args &a, const float *__restrict__ xp, int i, const float2 *s_band) {
     int cnt = 0;
     const double4 xi = a.xt[i];
     const float4 xif = a.xf[i];
@@ -1991,97 +1977,32 @@ __device__ __forceinline__ int build3_body(const Build2Args &a, const float *__r
         }
     };
     const int nx = a.g.n[0];
-    // Per-row x window (interior warps): every atom of the cell row (cy, cz) is at least gy, gz away from atom i in y, z
-    // (the distance to the nearest face of that row, from i's place inside its own cell), so only cells within
-    // w = sqrt(rl^2 - gy^2 - gz^2) of x_i can hold a list neighbour and a row with w^2 < 0 holds none.  Cells scanned per
-    // atom 125 -> 83 (half-size cells).  Conservative by construction (slack on the gaps and on w), and a window only ever
-    // drops candidates the distance test rejects: lists unchanged, entry order unchanged.
-    float ucell[3] = {0.f, 0.f, 0.f}, edge[3] = {0.f, 0.f, 0.f};
-    const bool clip = !IMAGE && a.clip_r2 > 0.f;
-    if (clip) {
-        const double r[3] = {xi.x, xi.y, xi.z};
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-            double p;  // position in cell units, the way cell_coords bins it
-            if (a.g.local[d]) {
-                double dc = r[d] - a.g.center[d];
-                dc -= a.box.h[4 * d] * rint(dc * a.box.hinv[4 * d]);
-                p = (dc + a.g.half[d]) * a.g.inv_edge[d];
-                edge[d] = (float)(1.0 / a.g.inv_edge[d]);
-            } else {
-                double sd = r[d] * a.box.hinv[4 * d];
-                sd -= floor(sd);
-                p = sd * (double)a.g.n[d];
-                edge[d] = (float)(a.box.h[4 * d] / (double)a.g.n[d]);
-            }
-            ucell[d] = (float)(p - (double)c[d]);
-        }
-    }
-    auto gap = [&](int d, int off) {  // lower bound of |x_j - x_i| along d for atoms of the cell at offset `off`, in length units
-        float gcell = off > 0 ? (float)off - ucell[d] : (off < 0 ? ucell[d] - (float)(off + 1) : 0.f);
-        gcell = fmaxf(gcell - 2e-3f, 0.f);
-        return gcell * edge[d];
-    };
-    // Aligned rows (a.align): the lanes of a warp are consecutive atoms of a cell row and walk the same stencil rows, but
-    // their row segments differ in length, so after a few rows entry k of one lane and entry k of the next point into
-    // different stencil rows and a warp's gather touches ~25 distinct 128-byte lines (the L1TEX data pipe is what bounds the
-    // force loop).  Padding every lane to the warp's longest row at a synchronisation point -- the end of a stencil plane
-    // (1) or of every stencil row (2) -- keeps the 32 lanes inside one window of consecutive slots.  A pad is an entry with
-    // the sign bit set: the force kernels skip it.  Every lane of `wmask` reaches every synchronisation point (skipped rows
-    // included), none after the last row.
-    auto sync_rows = [&]() {
-        const int m = __reduce_max_sync(wmask, cnt);
-        while (cnt < m) {
-            if (cnt < a.kcap) *wp = NBR_PAD_BIT;
-            ++cnt;
-            wp += (cnt & 3) ? (ptrdiff_t)1 : tile_step;
-        }
-    };
     for (int dz = a.g.lo[2]; dz <= a.g.hi[2]; ++dz) {
         int cz = c[2] + dz;
-        bool plane = true;
         if (cz < 0 || cz >= a.g.n[2]) {
             // interior atom: a wrapped cell lies beyond the cutoff (margin > rc + skin); brick-local dims never wrap
-            if (!IMAGE || a.g.local[2]) plane = false;
-            else cz += cz < 0 ? a.g.n[2] : -a.g.n[2];
-        }
-        float w2z = 0.f;
-        if (clip) {
-            const float gz = gap(2, dz);
-            w2z = fmaf(-gz, gz, a.clip_r2);
+            if (!IMAGE || a.g.local[2]) continue;
+            cz += cz < 0 ? a.g.n[2] : -a.g.n[2];
         }
         for (int dy = a.g.lo[1]; dy <= a.g.hi[1]; ++dy) {
             int cy = c[1] + dy;
-            bool row = plane;
             if (cy < 0 || cy >= a.g.n[1]) {
-                if (!IMAGE || a.g.local[1]) row = false;
-                else cy += cy < 0 ? a.g.n[1] : -a.g.n[1];
+                if (!IMAGE || a.g.local[1]) continue;
+                cy += cy < 0 ? a.g.n[1] : -a.g.n[1];
             }
-            int xlo = c[0] + a.g.lo[0], xhi = c[0] + a.g.hi[0];
-            if (clip && row) {
-                const float gy = gap(1, dy);
-                const float w2 = fmaf(-gy, gy, w2z);
-                if (w2 < 0.f) row = false;
-                const float wx = __fdividef(sqrtf(fmaxf(w2, 0.f)) * 1.0001f, edge[0]) + 2e-3f;  // window half-width in cells
-                xlo = max(xlo, c[0] + (int)floorf(ucell[0] - wx));
-                xhi = min(xhi, c[0] + (int)floorf(ucell[0] + wx));
+            const int rb = (cz * a.g.n[1] + cy) * nx;
+            const int xlo = c[0] + a.g.lo[0], xhi = c[0] + a.g.hi[0];
+            if (IMAGE && xlo < 0 && !a.g.local[0]) scan(__ldg(&a.cell_start[rb + xlo + nx]), __ldg(&a.cell_start[rb + nx]));
+            const int jb = __ldg(&a.cell_start[rb + max(xlo, 0)]);
+            const int je = __ldg(&a.cell_start[rb + min(xhi, nx - 1) + 1]);
+            if (i >= jb && i < je) {  // the range that holds i itself: skip i == j by splitting it
+                scan(jb, i);
+                scan(i + 1, je);
+            } else {
+                scan(jb, je);
             }
-            if (row) {
-                const int rb = (cz * a.g.n[1] + cy) * nx;
-                if (IMAGE && xlo < 0 && !a.g.local[0]) scan(__ldg(&a.cell_start[rb + xlo + nx]), __ldg(&a.cell_start[rb + nx]));
-                const int jb = __ldg(&a.cell_start[rb + max(xlo, 0)]);
-                const int je = __ldg(&a.cell_start[rb + min(xhi, nx - 1) + 1]);
-                if (i >= jb && i < je) {  // the range that holds i itself: skip i == j by splitting it
-                    scan(jb, i);
-                    scan(i + 1, je);
-                } else {
-                    scan(jb, je);
-                }
-                if (IMAGE && xhi >= nx && !a.g.local[0]) scan(__ldg(&a.cell_start[rb]), __ldg(&a.cell_start[rb + xhi - nx + 1]));
-            }
-            if (a.align == 2 && !(dz == a.g.hi[2] && dy == a.g.hi[1])) sync_rows();
+            if (IMAGE && xhi >= nx && !a.g.local[0]) scan(__ldg(&a.cell_start[rb]), __ldg(&a.cell_start[rb + xhi - nx + 1]));
         }
-        if (a.align == 1 && dz != a.g.hi[2]) sync_rows();
     }
     nbr_close_row(a.nbr, i, a.npad, cnt, a.kcap);
     a.nnbr[i] = cnt < a.kcap ? cnt : a.kcap;
@@ -2114,9 +2035,8 @@ __global__ void __launch_bounds__(TPB_FORCE, 10) k_build_list_v3(Build2Args a, c
     if (active) interior = is_interior(a.boxf, a.xf[i]);
     const bool warp_interior = __all_sync(0xffffffffu, interior);
     int cnt = 0;
-    const unsigned wmask = __ballot_sync(0xffffffffu, active);
     if (active) {
-        if (fast_ok) cnt = warp_interior ? build3_body<false, MULTI>(a, xp, i, s_band, wmask) : build3_body<true, MULTI>(a, xp, i, s_band, wmask);
+        if (fast_ok) cnt = warp_interior ? build3_body<false, MULTI>(a, xp, i, s_band) : build3_body<true, MULTI>(a, xp, i, s_band);
         else cnt = warp_interior ? build2_body<MULTI, false>(a, i) : build2_body<MULTI, true>(a, i);
     }
     int m = cnt;
@@ -2137,25 +2057,20 @@ struct ListStatsArgs {
     PairDev pair0;
     const PairDev *table;
     int n_types;
-    unsigned long long *out;  // [0] listed (real entries), [1] in range, [2] alignment pads
+    unsigned long long *out;  // [0] listed, [1] in range
 };
 
 template <bool ORTHO>
 __global__ void __launch_bounds__(TPB) k_list_stats(ListStatsArgs a) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long listed = 0, inr = 0, pads = 0;
+    unsigned long long listed = 0, inr = 0;
     if (i < a.n && !is_ghost(a.xt[i].w)) {
         const double4 xi = a.xt[i];
         const int ti = type_of(xi.w);
         const int nn = a.nnbr[i];
         listed = (unsigned long long)nn;
         for (int k = 0; k < nn; ++k) {
-            const int j = a.nbr[nbr_at(k, i, a.npad)];
-            if (nbr_is_pad(j)) {
-                ++pads;
-                continue;
-            }
-            const double4 xj = ldg_d4(&a.xt[j]);
+            const double4 xj = ldg_d4(&a.xt[a.nbr[nbr_at(k, i, a.npad)]]);
             double dx = __dsub_rn(xj.x, xi.x), dy = __dsub_rn(xj.y, xi.y), dz = __dsub_rn(xj.z, xi.z);
             min_image<ORTHO>(a.box, dx, dy, dz);
             const int tj = type_of(xj.w);
@@ -2167,12 +2082,10 @@ __global__ void __launch_bounds__(TPB) k_list_stats(ListStatsArgs a) {
     for (int o = 16; o > 0; o >>= 1) {
         listed += __shfl_down_sync(0xffffffffu, listed, o);
         inr += __shfl_down_sync(0xffffffffu, inr, o);
-        pads += __shfl_down_sync(0xffffffffu, pads, o);
     }
     if ((threadIdx.x & 31) == 0) {
-        atomicAdd(&a.out[0], listed - pads);
+        atomicAdd(&a.out[0], listed);
         atomicAdd(&a.out[1], inr);
-        atomicAdd(&a.out[2], pads);
     }
 }
 

@@ -78,8 +78,6 @@ struct pisb_handle {
     int force_variant = 0;  // 0 = auto (v3 when orthorhombic + fully periodic, else v1), 1 = v1, 2 = v2, 3 = v3
     int build_variant = 0;
     int cell_div = 0;  // cells per list cutoff per dimension: 0 = auto, 1 = reference-sized cells, 2 = half-size cells
-    int build_window = 1;  // v3 build: per-row x window for interior warps (0 = scan the whole stencil row, for A/B)
-    int list_align = 0;    // v3 build: pad the rows of a warp to a common length after every stencil plane (1) / stencil row (2)
     int fuse_vv = 1;   // option "fuse_vv": NVE batches run k_force_vv (force + kick + drift in one launch) when the default force kernel applies
 
     // box / grid
@@ -534,9 +532,7 @@ int estimate_kcap(pisb_t *h) {
     const double n_glob = h->multi ? (double)h->n_own * h->dc.nranks : (double)h->n;
     double k = vol > 0 ? n_glob / vol * 4.18879020478639 * rl * rl * rl : 64.0;
     k = 1.3 * k + 24.0;
-    if (h->list_align == 1) k *= 1.35;  // alignment pads (measured on the thermal argon lattice: +31 % per plane, +71 % per row)
-    if (h->list_align == 2) k *= 1.8;
-    if (k > n_glob && !h->list_align) k = std::max(n_glob, 1.0);
+    if (k > n_glob) k = std::max(n_glob, 1.0);
     if (k > 4096.0) k = 4096.0;
     return (int)std::ceil(k);
 }
@@ -665,12 +661,7 @@ int launch_rebuild_chain(pisb_t *h) {
         if (v2) {
             if (!v2_possible(h)) return fail(h, PISB_ERR_INVALID, "build_variant 2/3 needs an orthorhombic, fully periodic box");
             Build2Args b2{n, h->npad, h->kcap, h->xt.p, h->xf.p, h->cell_start.p, h->box, h->boxf, g, h->pairs[0],
-                          h->pairsf[0], h->table_d.p, h->tablef_d.p, h->n_types, h->nbr.p, h->nnbr.p, h->flags, 0.f, h->list_align};
-            if (h->build_window) {
-                float r2max = 0.f;  // hi_list is already the FP32 acceptance bound rounded up
-                for (const PairF &pf : h->pairsf) r2max = std::max(r2max, pf.hi_list);
-                b2.clip_r2 = r2max > 0.f ? f32_above((double)r2max * (1.0 + 1e-5)) : 0.f;
-            }
+                          h->pairsf[0], h->table_d.p, h->tablef_d.p, h->n_types, h->nbr.p, h->nnbr.p, h->flags};
             if (h->build_variant == 2) {  // v2: scalar FP32 pre-filter (kept for A/B)
                 if (multi) k_build_list_v2<true><<<nb, TPB_FORCE, 0, st>>>(b2);
                 else k_build_list_v2<false><<<nb, TPB_FORCE, 0, st>>>(b2);
@@ -1123,7 +1114,7 @@ void graph_signature(pisb_t *h, double dt, std::vector<unsigned char> &sig) {
                           h->tile_sum.p, h->mass_d.p, h->partials.p, h->table_d.p, h->thermo_d.p, h->flags, h->ticket, h->nhc_d.p,
                           h->nhc_energy_d.p};
     put(ptrs, sizeof ptrs);
-    const int ints[] = {h->n, h->npad, h->kcap, h->n_types, h->force_variant, h->build_variant, h->cell_div, h->build_window, h->list_align, h->fuse_vv,
+    const int ints[] = {h->n, h->npad, h->kcap, h->n_types, h->force_variant, h->build_variant, h->cell_div, h->fuse_vv,
                         quad_mode(h) ? 1 : 0};
     put(ints, sizeof ints);
     const double dbl[] = {dt, h->skin, h->skin_half2_override, h->max_rcut};
@@ -2695,10 +2686,10 @@ int pisb_neighbours(pisb_t *h, int32_t *nnbr, int32_t *nbr, int64_t cap_per_atom
         TRY(ensure_list(h));
     }
     const int n = h->n;
-    std::vector<int> hn(n), hid(n), hl(nbr || h->list_align ? (size_t)h->kcap * h->npad : 0);  // the list itself only when rows are wanted (or pads must be told from entries)
+    std::vector<int> hn(n), hid(n), hl(nbr ? (size_t)h->kcap * h->npad : 0);  // the list itself only when rows are wanted
     CUDA_TRY(h, cudaMemcpyAsync(hn.data(), h->nnbr.p, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(hid.data(), h->id.p, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
-    if (!hl.empty()) CUDA_TRY(h, cudaMemcpyAsync(hl.data(), h->nbr.p, sizeof(int) * hl.size(), cudaMemcpyDeviceToHost, h->stream));
+    if (nbr) CUDA_TRY(h, cudaMemcpyAsync(hl.data(), h->nbr.p, sizeof(int) * hl.size(), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     auto entry = [&](int s, int k) -> int { return hl[nbr_at(k, s, h->npad)]; };
     int64_t total = 0;
@@ -2711,21 +2702,12 @@ int pisb_neighbours(pisb_t *h, int32_t *nnbr, int32_t *nbr, int64_t cap_per_atom
             long long wb;
             std::memcpy(&wb, &hx[s].w, 8);
             if ((wb >> 32) & 1) continue;
-            int real = hn[s];
-            if (!hl.empty()) {  // alignment pads are no neighbours
-                real = 0;
-                for (int k = 0; k < hn[s]; ++k) {
-                    const int j = entry(s, k);
-                    if (nbr_is_pad(j)) continue;
-                    if (nbr) {
-                        if (real >= cap_per_atom) return fail(h, PISB_ERR_CAPACITY, "cap_per_atom too small");
-                        nbr[(size_t)o * cap_per_atom + real] = hid[j];
-                    }
-                    ++real;
-                }
+            nnbr[o] = hn[s];
+            total += hn[s];
+            if (nbr) {
+                if (hn[s] > cap_per_atom) return fail(h, PISB_ERR_CAPACITY, "cap_per_atom too small");
+                for (int k = 0; k < hn[s]; ++k) nbr[(size_t)o * cap_per_atom + k] = hid[entry(s, k)];
             }
-            nnbr[o] = real;
-            total += real;
             ++o;
         }
         h->total_nbr = total;
@@ -2733,21 +2715,12 @@ int pisb_neighbours(pisb_t *h, int32_t *nnbr, int32_t *nbr, int64_t cap_per_atom
     }
     for (int s = 0; s < n; ++s) {
         const int o = hid[s];
-        int real = hn[s];
-        if (!hl.empty()) {  // alignment pads are no neighbours
-            real = 0;
-            for (int k = 0; k < hn[s]; ++k) {
-                const int j = entry(s, k);
-                if (nbr_is_pad(j)) continue;
-                if (nbr) {
-                    if (real >= cap_per_atom) return fail(h, PISB_ERR_CAPACITY, fmt("cap_per_atom %lld < list length of atom %d", (long long)cap_per_atom, o));
-                    nbr[(size_t)o * cap_per_atom + real] = hid[j];
-                }
-                ++real;
-            }
+        nnbr[o] = hn[s];
+        total += hn[s];
+        if (nbr) {
+            if (hn[s] > cap_per_atom) return fail(h, PISB_ERR_CAPACITY, fmt("cap_per_atom %lld < list length %d", (long long)cap_per_atom, hn[s]));
+            for (int k = 0; k < hn[s]; ++k) nbr[(size_t)o * cap_per_atom + k] = hid[entry(s, k)];
         }
-        nnbr[o] = real;
-        total += real;
     }
     h->total_nbr = total;
     return PISB_OK;
@@ -2775,7 +2748,7 @@ int pisb_list_stats(pisb_t *h, int64_t *out3) {
     dev_free(h, d);
     out3[0] = (int64_t)host[0];
     out3[1] = (int64_t)host[1];
-    out3[2] = (int64_t)(host[0] + host[2]);  // index words stored: listed pairs + alignment pads
+    out3[2] = (int64_t)host[0];  // index words stored == listed pairs for per-atom rows
     h->total_nbr = (int64_t)host[0];
     return PISB_OK;
 }
@@ -3020,16 +2993,8 @@ int pisb_set_option(pisb_t *h, const char *name, double value) {
         h->force_variant = v;
         return PISB_OK;
     }
-    if (!std::strcmp(name, "build_variant") || !std::strcmp(name, "cell_div") || !std::strcmp(name, "build_window") ||
-        !std::strcmp(name, "list_align")) {
-        if (!std::strcmp(name, "build_window")) h->build_window = value != 0.0 ? 1 : 0;
-        else if (!std::strcmp(name, "list_align")) {
-            const int v = (int)value;
-            if (v < 0 || v > 2) return fail(h, PISB_ERR_INVALID, fmt("list_align %d does not exist (0, 1, 2)", v));
-            h->list_align = v;
-            h->kcap = 0;  // the capacity estimate depends on it
-        }
-        else if (name[0] == 'b') h->build_variant = (int)value;
+    if (!std::strcmp(name, "build_variant") || !std::strcmp(name, "cell_div")) {
+        if (name[0] == 'b') h->build_variant = (int)value;
         else h->cell_div = (int)value;
         h->list_valid = false;
         h->grid_ok = false;
