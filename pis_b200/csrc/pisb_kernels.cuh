@@ -1295,18 +1295,47 @@ struct ForceVVArgs {
     int always_rebuild;
     int *flags;
     int unwrapped_out;  // flags[] word of the buffer behind xt_out (cleared by a drifting launch; never the word this launch reads)
+    unsigned int *sm_queue;  // EXPERIMENT (force_sched 1): per-SM work counters, see sm_fetch_block
+    int sm_regions;
 };
+
+// EXPERIMENT: SM-aware work assignment.  The hardware hands consecutive thread blocks to DIFFERENT SMs, so the blocks that
+// share an SM's L1 work on atoms ~57 cell rows apart and share no neighbour records (L1 hit rate of the gathers: 53 %).
+// Here the work (blocks of NT consecutive slots) is cut into one contiguous region per SM and a thread block takes the next
+// block of its OWN SM's region: the 8 resident blocks of an SM then cover ~3 adjacent cell rows, whose stencil rows overlap.
+// A block whose region is exhausted steals from the next regions.  Results do not depend on who computes what.
+__device__ __forceinline__ int sm_fetch_block(unsigned int *q, int regions, int nblocks) {
+    __shared__ int s_work;
+    if (threadIdx.x == 0) {
+        unsigned int smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        const int per = (nblocks + regions - 1) / regions;
+        int work = -1;
+        for (int k = 0; k < regions && work < 0; ++k) {
+            const int r = (int)((smid + k) % regions);
+            const int lo = r * per, hi = min(lo + per, nblocks);
+            if (lo >= hi) continue;
+            const int c = (int)atomicAdd(&q[r], 1u);
+            if (lo + c < hi) work = lo + c;
+        }
+        s_work = work;
+    }
+    __syncthreads();
+    return s_work;
+}
 
 // (Evict-first loads / stores for the epilogue's streams, L2 prefetch of its operands at thread start and an L2 evict-first
 // policy on the index tiles were tried: 1.355 - 1.378 ms against 1.358 ms, nothing to gain -- profiles/r01_fused_step.jsonl.)
 // BRICK: the multi-GPU form -- ghost slots are skipped (the halo exchange fills them) and the launch may be speculative
 // (skip_flag).  A template parameter, not a run-time test: with the two extra live values the single-GPU kernel's force loop
 // picked up a spill store + load per K-tile (ptxas: 8 -> 24 bytes, inside the loop), on the L1TEX path that bounds it.
-template <bool MULTI, bool DRIFT, bool BRICK>
-__global__ void __launch_bounds__(TPB_FORCE, 8) k_force_vv(ForceVVArgs b) {
+template <bool MULTI, bool DRIFT, bool BRICK, int NT = TPB_FORCE>
+__global__ void __launch_bounds__(NT, 1024 / NT) k_force_vv(ForceVVArgs b) {
     const Force2Args &a = b.f;
     if (BRICK && a.skip_flag && *a.skip_flag != 0) return;  // speculative launch, a rebuild comes first
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int vblock = -1;
+    if (!BRICK && b.sm_queue) vblock = sm_fetch_block(b.sm_queue, b.sm_regions, (int)gridDim.x);
+    const int i = (vblock >= 0 ? vblock : (int)blockIdx.x) * NT + threadIdx.x;
     double red[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};  // pe, pair virial, ke, x*fx, y*fy, z*fz
     if (DRIFT && i == 0) b.flags[b.unwrapped_out] = 0;
     bool active = i < a.n;
@@ -1367,13 +1396,15 @@ __global__ void __launch_bounds__(TPB_FORCE, 8) k_force_vv(ForceVVArgs b) {
     }
     pisb_thermo *th = a.thermo;
     double t3[3];
-    block_reduce_finalize<6, TPB_FORCE>(red, a.partials, a.ticket, [&](int q, double s) {
+    block_reduce_finalize<6, NT>(red, a.partials, a.ticket, [&](int q, double s) {
         if (q == 0) th->pe = s / 2.0;
         else if (q == 1) th->virial_pair = s / 2.0;
         else if (q == 2) th->ke = s;
         else t3[q - 3] = s;
         if (q == 5) th->virial_ref = (t3[0] + t3[1]) + t3[2];
-    });
+        if (q == 5 && !BRICK && b.sm_queue)  // the grid's last block: every fetch is done, the counters start the next launch at 0
+            for (int r = 0; r < b.sm_regions; ++r) b.sm_queue[r] = 0u;
+    }, vblock);
 }
 
 // ------------------------------------------------------------------------------------------------
