@@ -167,12 +167,11 @@ __host__ __device__ inline unsigned int red_groups(unsigned int nblocks) { retur
 
 template <int NQ, int NT, typename Fin>
 __device__ __forceinline__ void block_reduce_finalize(double (&v)[NQ], double *__restrict__ partials,
-                                                      unsigned int *__restrict__ ticket, Fin fin, int vblock = -1) {
+                                                      unsigned int *__restrict__ ticket, Fin fin) {
     __shared__ double s_red[NQ][NT / 32];
     __shared__ bool s_group_last, s_grid_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned int bid = vblock >= 0 ? (unsigned int)vblock : blockIdx.x;  // the block of WORK this thread block did
-    const unsigned int nb = gridDim.x, ng = red_groups(nb), g = bid / RED_GROUP;
+    const unsigned int nb = gridDim.x, ng = red_groups(nb), g = blockIdx.x / RED_GROUP;
     const unsigned int b0 = g * RED_GROUP, gs = min((unsigned int)RED_GROUP, nb - b0);
     double *__restrict__ level1 = partials + (size_t)NQ * nb;
 #pragma unroll
@@ -186,7 +185,7 @@ __device__ __forceinline__ void block_reduce_finalize(double (&v)[NQ], double *_
         for (int q = 0; q < NQ; ++q) {
             double w = lane < NT / 32 ? s_red[q][lane] : 0.0;
             w = warp_sum(w);
-            if (lane == 0) partials[(size_t)q * nb + bid] = w;
+            if (lane == 0) partials[(size_t)q * nb + blockIdx.x] = w;
         }
     }
     if (threadIdx.x == 0) {

@@ -26,6 +26,8 @@ namespace pisb {
 
 constexpr int TPB = 256;        // streaming kernels
 constexpr int TPB_FORCE = 128;  // force / build kernels
+constexpr int TPB_VV = 512;     // k_force_v3 / k_force_vv: 2 resident blocks per SM at the 64-register bound (1.130 against 1.149 ms
+                                // per launch with 128; 256: 1.145, 1024: 1.180 -- profiles/r02_ab_force_block_sched_4M_43K.jsonl)
 
 // flags[] (device ints)
 // FLAG_DECISION: multi-GPU fused steps -- a stream-ordered copy of FLAG_REBUILD taken after the halo exchange.  The
@@ -1240,9 +1242,9 @@ __device__ __forceinline__ void force3_body(const Force2Args &a, int i, double &
     }
 }
 
-// 8 resident blocks/SM (64 registers, 32 warps): measured best, profiles/r01_force_launch_config.txt
+// 64 registers, 32 warps per SM: measured best, profiles/r01_force_launch_config.txt
 template <bool MULTI>
-__global__ void __launch_bounds__(TPB_FORCE, 8) k_force_v3(Force2Args a) {
+__global__ void __launch_bounds__(TPB_VV, 1024 / TPB_VV) k_force_v3(Force2Args a) {
     if (a.skip_flag && *a.skip_flag != 0) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double red[2] = {0.0, 0.0};
@@ -1266,7 +1268,7 @@ __global__ void __launch_bounds__(TPB_FORCE, 8) k_force_v3(Force2Args a) {
         red[1] = vir;
     }
     pisb_thermo *th = a.thermo;
-    block_reduce_finalize<2, TPB_FORCE>(red, a.partials, a.ticket, [&](int qq, double s) {
+    block_reduce_finalize<2, TPB_VV>(red, a.partials, a.ticket, [&](int qq, double s) {
         if (qq == 0) th->pe = s / 2.0;
         else th->virial_pair = s / 2.0;
     });
@@ -1295,47 +1297,16 @@ struct ForceVVArgs {
     int always_rebuild;
     int *flags;
     int unwrapped_out;  // flags[] word of the buffer behind xt_out (cleared by a drifting launch; never the word this launch reads)
-    unsigned int *sm_queue;  // EXPERIMENT (force_sched 1): per-SM work counters, see sm_fetch_block
-    int sm_regions;
 };
 
-// EXPERIMENT: SM-aware work assignment.  The hardware hands consecutive thread blocks to DIFFERENT SMs, so the blocks that
-// share an SM's L1 work on atoms ~57 cell rows apart and share no neighbour records (L1 hit rate of the gathers: 53 %).
-// Here the work (blocks of NT consecutive slots) is cut into one contiguous region per SM and a thread block takes the next
-// block of its OWN SM's region: the 8 resident blocks of an SM then cover ~3 adjacent cell rows, whose stencil rows overlap.
-// A block whose region is exhausted steals from the next regions.  Results do not depend on who computes what.
-__device__ __forceinline__ int sm_fetch_block(unsigned int *q, int regions, int nblocks) {
-    __shared__ int s_work;
-    if (threadIdx.x == 0) {
-        unsigned int smid;
-        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        const int per = (nblocks + regions - 1) / regions;
-        int work = -1;
-        for (int k = 0; k < regions && work < 0; ++k) {
-            const int r = (int)((smid + k) % regions);
-            const int lo = r * per, hi = min(lo + per, nblocks);
-            if (lo >= hi) continue;
-            const int c = (int)atomicAdd(&q[r], 1u);
-            if (lo + c < hi) work = lo + c;
-        }
-        s_work = work;
-    }
-    __syncthreads();
-    return s_work;
-}
-
-// (Evict-first loads / stores for the epilogue's streams, L2 prefetch of its operands at thread start and an L2 evict-first
-// policy on the index tiles were tried: 1.355 - 1.378 ms against 1.358 ms, nothing to gain -- profiles/r01_fused_step.jsonl.)
-// BRICK: the multi-GPU form -- ghost slots are skipped (the halo exchange fills them) and the launch may be speculative
-// (skip_flag).  A template parameter, not a run-time test: with the two extra live values the single-GPU kernel's force loop
-// picked up a spill store + load per K-tile (ptxas: 8 -> 24 bytes, inside the loop), on the L1TEX path that bounds it.
-template <bool MULTI, bool DRIFT, bool BRICK, int NT = TPB_FORCE>
+// (Two scheduling experiments, profiles/r02_ab_force_block_sched_4M_43K.jsonl: blocks of 256 / 512 / 1024 threads -- 1.145 /
+// 1.130 / 1.180 ms per launch against 1.149 with 128, so 512 it is; and an SM-aware work assignment that gives the resident
+// blocks of one SM adjacent cell rows, so that they share neighbour records in L1 -- 3 % SLOWER at every block size.)
+template <bool MULTI, bool DRIFT, bool BRICK, int NT = TPB_VV>
 __global__ void __launch_bounds__(NT, 1024 / NT) k_force_vv(ForceVVArgs b) {
     const Force2Args &a = b.f;
     if (BRICK && a.skip_flag && *a.skip_flag != 0) return;  // speculative launch, a rebuild comes first
-    int vblock = -1;
-    if (!BRICK && b.sm_queue) vblock = sm_fetch_block(b.sm_queue, b.sm_regions, (int)gridDim.x);
-    const int i = (vblock >= 0 ? vblock : (int)blockIdx.x) * NT + threadIdx.x;
+    const int i = blockIdx.x * NT + threadIdx.x;
     double red[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};  // pe, pair virial, ke, x*fx, y*fy, z*fz
     if (DRIFT && i == 0) b.flags[b.unwrapped_out] = 0;
     bool active = i < a.n;
@@ -1402,9 +1373,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_force_vv(ForceVVArgs b) {
         else if (q == 2) th->ke = s;
         else t3[q - 3] = s;
         if (q == 5) th->virial_ref = (t3[0] + t3[1]) + t3[2];
-        if (q == 5 && !BRICK && b.sm_queue)  // the grid's last block: every fetch is done, the counters start the next launch at 0
-            for (int r = 0; r < b.sm_regions; ++r) b.sm_queue[r] = 0u;
-    }, vblock);
+    });
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -78,9 +78,6 @@ struct pisb_handle {
     int force_variant = 0;  // 0 = auto (v3 when orthorhombic + fully periodic, else v1), 1 = v1, 2 = v2, 3 = v3
     int build_variant = 0;
     int cell_div = 0;  // cells per list cutoff per dimension: 0 = auto, 1 = reference-sized cells, 2 = half-size cells
-    int force_block = 0;  // EXPERIMENT: threads per block of k_force_vv (256 / 512 / 1024; 0 = 128)
-    int force_sched = 0;  // EXPERIMENT: 1 = k_force_vv blocks take work from their own SM's region (sm_fetch_block)
-    int sm_count = 148;
     int fuse_vv = 1;   // option "fuse_vv": NVE batches run k_force_vv (force + kick + drift in one launch) when the default force kernel applies
 
     // box / grid
@@ -568,7 +565,7 @@ int reserve_atoms(pisb_t *h, int n) {
     const size_t b_force = (size_t)nblk(n, TPB_FORCE), b_stream = (size_t)nblk(n, TPB), b_split = (size_t)nblk(std::min(n, 75000) * 8, TPB_FORCE);
     const size_t b_quad = ((size_t)n * 4 + TPB_Q - 1) / TPB_Q;  // k_force_q: four lanes per atom, 6 quantities
     TRY(dev_reserve(h, h->partials, std::max(std::max(need(6, b_force), need(6, b_quad)), std::max(need(19, b_stream), need(2, b_split)))));
-    const size_t tickets = 2 + red_groups((unsigned int)std::max(std::max(b_force, b_quad), b_split)) + 256;  // + per-SM work counters (the last 256 words)
+    const size_t tickets = 2 + red_groups((unsigned int)std::max(std::max(b_force, b_quad), b_split));
     if (tickets > h->ticket_cap) {
         // zero-initialised once; the words reset themselves at the end of every reduction
         CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -729,8 +726,8 @@ int launch_force(pisb_t *h, double *const out[3], const double *const acc[3], pi
                 else k_force_split<false, 4><<<nbs, TPB_FORCE, 0, st>>>(f2);
             }
         } else if (h->force_variant != 2) {  // auto = v3 (measured fastest: profiles/)
-            if (multi) k_force_v3<true><<<nb, TPB_FORCE, 0, st>>>(f2);
-            else k_force_v3<false><<<nb, TPB_FORCE, 0, st>>>(f2);
+            if (multi) k_force_v3<true><<<nblk(h->n, TPB_VV), TPB_VV, 0, st>>>(f2);
+            else k_force_v3<false><<<nblk(h->n, TPB_VV), TPB_VV, 0, st>>>(f2);
         } else {
             if (multi) k_force_v2<true><<<nb, TPB_FORCE, 0, st>>>(f2);
             else k_force_v2<false><<<nb, TPB_FORCE, 0, st>>>(f2);
@@ -796,10 +793,9 @@ int launch_force_vv(pisb_t *h, bool drift, double dt, pisb_thermo *rec, const in
                        h->v[0].p, h->v[1].p, h->v[2].p, h->f[0].p, h->f[1].p, h->f[2].p, h->xb[0].p, h->xb[1].p, h->xb[2].p,
                        h->mass_d.p, h->s_xt.p, h->xf2.p, dt, dt * dt,
                        h->skin_half2_override >= 0.0 ? h->skin_half2_override : hs * hs,
-                       (h->skin > 0.0 && h->skin_half2_override != 0.0) ? 0 : 1, h->flags, h->s_xt_flag,
-                       h->force_sched ? h->ticket + h->ticket_cap - 256 : nullptr, h->sm_count};
+                       (h->skin > 0.0 && h->skin_half2_override != 0.0) ? 0 : 1, h->flags, h->s_xt_flag};
         const bool multi = h->n_types > 1;
-        const int nb = nblk(h->n, TPB_FORCE);
+        const int nbv = nblk(h->n, TPB_VV);
         cudaStream_t st = h->stream;
         if (quad_mode(h)) {
             const unsigned nbq = (unsigned)(((size_t)h->n * 4 + TPB_Q - 1) / TPB_Q);
@@ -819,16 +815,9 @@ int launch_force_vv(pisb_t *h, bool drift, double dt, pisb_thermo *rec, const in
         } else {
 #define FVV(T, D)                                                              \
     do {                                                                       \
-        if (h->multi) k_force_vv<T, D, true><<<nb, TPB_FORCE, 0, st>>>(fv);    \
-        else k_force_vv<T, D, false><<<nb, TPB_FORCE, 0, st>>>(fv);            \
+        if (h->multi) k_force_vv<T, D, true><<<nbv, TPB_VV, 0, st>>>(fv);      \
+        else k_force_vv<T, D, false><<<nbv, TPB_VV, 0, st>>>(fv);              \
     } while (0)
-        if (!multi && !h->multi && h->force_block > TPB_FORCE) {  // block-size experiment (single type, single GPU)
-            const int fb = h->force_block;
-            const int nbb = nblk(h->n, fb);
-            if (fb == 256) { if (drift) k_force_vv<false, true, false, 256><<<nbb, 256, 0, st>>>(fv); else k_force_vv<false, false, false, 256><<<nbb, 256, 0, st>>>(fv); }
-            else if (fb == 512) { if (drift) k_force_vv<false, true, false, 512><<<nbb, 512, 0, st>>>(fv); else k_force_vv<false, false, false, 512><<<nbb, 512, 0, st>>>(fv); }
-            else { if (drift) k_force_vv<false, true, false, 1024><<<nbb, 1024, 0, st>>>(fv); else k_force_vv<false, false, false, 1024><<<nbb, 1024, 0, st>>>(fv); }
-        } else
         if (drift) {
             if (multi) FVV(true, true);
             else FVV(false, true);
@@ -1125,7 +1114,7 @@ void graph_signature(pisb_t *h, double dt, std::vector<unsigned char> &sig) {
                           h->tile_sum.p, h->mass_d.p, h->partials.p, h->table_d.p, h->thermo_d.p, h->flags, h->ticket, h->nhc_d.p,
                           h->nhc_energy_d.p};
     put(ptrs, sizeof ptrs);
-    const int ints[] = {h->n, h->npad, h->kcap, h->n_types, h->force_variant, h->build_variant, h->cell_div, h->force_block, h->force_sched, h->fuse_vv,
+    const int ints[] = {h->n, h->npad, h->kcap, h->n_types, h->force_variant, h->build_variant, h->cell_div, h->fuse_vv,
                         quad_mode(h) ? 1 : 0};
     put(ints, sizeof ints);
     const double dbl[] = {dt, h->skin, h->skin_half2_override, h->max_rcut};
@@ -2239,10 +2228,6 @@ int pisb_create(int device, int n_types, const double *mass, const double *eps, 
         return rc;
     };
     if (cudaSetDevice(device) != cudaSuccess) return bail(fail(h, PISB_ERR_CUDA, "cudaSetDevice failed"));
-    {
-        int sms = 0;
-        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) h->sm_count = std::min(sms, 256);
-    }
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_pos, cudaEventDisableTiming) != cudaSuccess)
@@ -3000,14 +2985,6 @@ int pisb_set_option(pisb_t *h, const char *name, double value) {
     }
     if (!std::strcmp(name, "fuse_vv")) {
         h->fuse_vv = value != 0.0 ? 1 : 0;
-        return PISB_OK;
-    }
-    if (!std::strcmp(name, "force_block")) {
-        h->force_block = (int)value;
-        return PISB_OK;
-    }
-    if (!std::strcmp(name, "force_sched")) {
-        h->force_sched = (int)value;
         return PISB_OK;
     }
     if (!std::strcmp(name, "force_variant")) {

@@ -59,10 +59,10 @@ def test_force_loops_have_no_local_memory_traffic():
         pytest.skip("cuobjdump not available")
     kernels = {
         "k_force_v3<false>": "_ZN4pisb10k_force_v3ILb0EEEvNS_10Force2ArgsE",
-        "k_force_vv<false,drift,single GPU>": "_ZN4pisb10k_force_vvILb0ELb1ELb0ELi128EEEvNS_11ForceVVArgsE",
-        "k_force_vv<false,no drift,single GPU>": "_ZN4pisb10k_force_vvILb0ELb0ELb0ELi128EEEvNS_11ForceVVArgsE",
-        "k_force_vv<false,drift,brick>": "_ZN4pisb10k_force_vvILb0ELb1ELb1ELi128EEEvNS_11ForceVVArgsE",
-        "k_force_vv<false,no drift,brick>": "_ZN4pisb10k_force_vvILb0ELb0ELb1ELi128EEEvNS_11ForceVVArgsE",
+        "k_force_vv<false,drift,single GPU>": "_ZN4pisb10k_force_vvILb0ELb1ELb0ELi512EEEvNS_11ForceVVArgsE",
+        "k_force_vv<false,no drift,single GPU>": "_ZN4pisb10k_force_vvILb0ELb0ELb0ELi512EEEvNS_11ForceVVArgsE",
+        "k_force_vv<false,drift,brick>": "_ZN4pisb10k_force_vvILb0ELb1ELb1ELi512EEEvNS_11ForceVVArgsE",
+        "k_force_vv<false,no drift,brick>": "_ZN4pisb10k_force_vvILb0ELb0ELb1ELi512EEEvNS_11ForceVVArgsE",
         # four lanes per atom (the default above 75k atoms): one 32-bit reload per iteration of four tiles is tolerated
         "k_force_q<false,fused,drift,single GPU>": "_ZN4pisb9k_force_qILb0ELb1ELb1ELb0EEEvNS_11ForceVVArgsE",
         "k_force_q<false,fused,drift,brick>": "_ZN4pisb9k_force_qILb0ELb1ELb1ELb1EEEvNS_11ForceVVArgsE",

@@ -712,7 +712,7 @@ def _run_batches(atoms, fuse, graphs, batches, table=None, nvt_first=False, vari
 def test_fused_force_integrator_step_equals_separate_kernels(graphs, variant):
     """k_force_vv (force + kick + drift in one launch, positions double-buffered) against k_force_v3 + k_vv: the same
     arithmetic per atom, so positions / velocities / forces and the force kernel's reductions (PE, pair virial) are
-    bit-identical across rebuilds, odd batch sizes and single steps; KE and tr(X F^T) are reduced over 128- instead of
+    bit-identical across rebuilds, odd batch sizes and single steps; KE and tr(X F^T) are reduced over 512- instead of
     256-thread blocks and agree to rounding."""
     batches = (64, 7, 1, 33, 46, 2, 3)
     a1 = fcc_argon(12, temperature=60.0, seed=5)
