@@ -251,6 +251,12 @@ PISB_API int pisb_upload_owned(pisb_t *h, int64_t n_own, const double *pos, cons
  * arbitrary -- global_ids identifies each row.  Arrays hold up to cap atoms; *n_out = count. */
 PISB_API int pisb_download_owned(pisb_t *h, int64_t cap, double *pos, double *vel, double *force,
                                  int32_t *global_ids, int64_t *n_out);
+/* The same rows, asynchronously: the owned atoms are snapshotted on the device, the copies run on a stream of their own and
+ * the next pisb_step_nve batch may start at once; *n_out is valid on return, the arrays after pisb_download_end(h).
+ * (Multi-GPU form of pisb_download_begin: a dump frame of Simulation::run, src/simulation.rs:84-86, hidden under the steps
+ * that follow.)  Host arrays should be page-locked (pisb_host_register). */
+PISB_API int pisb_download_owned_begin(pisb_t *h, int64_t cap, double *pos, double *vel, double *force,
+                                       int32_t *global_ids, int64_t *n_out);
 /* Test hook: global ids of the owned atoms in device slot order == the row order of pisb_neighbours in
  * multi-GPU mode (where list entries are global ids). */
 PISB_API int pisb_owned_ids(pisb_t *h, int64_t cap, int32_t *global_ids, int64_t *n_out);

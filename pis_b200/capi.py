@@ -96,6 +96,7 @@ SIGNATURES = {
     "pisb_comm_init": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp]),
     "pisb_upload_owned": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp, _vp]),
     "pisb_download_owned": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp, C.POINTER(C.c_int64)]),
+    "pisb_download_owned_begin": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp, C.POINTER(C.c_int64)]),
     "pisb_owned_ids": (C.c_int, [_vp, C.c_int64, _vp, C.POINTER(C.c_int64)]),
 }
 

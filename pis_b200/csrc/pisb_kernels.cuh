@@ -522,9 +522,18 @@ __global__ void __launch_bounds__(TPB) k_bin(int n, const double4 *__restrict__ 
         int c[3];
         cell_coords<ORTHO>(box, g, x.x, x.y, x.z, c);
         int cell = (c[2] * g.n[1] + c[1]) * g.n[0] + c[0];
-        if (is_dead(x.w)) cell = g.ncell;  // sentinel bucket (multi-GPU rebuilds)
+        // sentinel bucket (multi-GPU rebuilds): every stale ghost and every leaver lands on ONE counter -- 0.4M same-address
+        // atomics per rebuild of a 4M-atom brick (bin 0.065 against 0.017 ms per step) unless a warp sends one
+        const bool dead = is_dead(x.w);
+        const unsigned act = __activemask();
+        const unsigned md = __ballot_sync(act, dead);
+        if (dead) {
+            cell = g.ncell;
+            if ((threadIdx.x & 31) == __ffs(md) - 1) atomicAdd(&cell_count[cell], __popc(md));
+        } else {
+            atomicAdd(&cell_count[cell], 1);
+        }
         cell_of[i] = cell;
-        atomicAdd(&cell_count[cell], 1);
     }
 }
 
@@ -612,13 +621,26 @@ __global__ void __launch_bounds__(SCAN_TPB) k_scan_apply(int ncell, int n_atoms,
 }
 
 // Scatter slot indices into their cell segment (arrival order, fixed up by k_sort_cells).
-__global__ void __launch_bounds__(TPB) k_fill(int n, const int *__restrict__ cell_of,
+__global__ void __launch_bounds__(TPB) k_fill(int n, int ncell, const int *__restrict__ cell_of,
                                               const int *__restrict__ cell_start, int *__restrict__ cell_fill,
                                               int *__restrict__ order, const int *flags) {
     if (flags[FLAG_REBUILD] == 0) return;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        int c = cell_of[i];
-        int p = cell_start[c] + atomicAdd(&cell_fill[c], 1);
+        const int c = cell_of[i];
+        // the sentinel bucket (cell index ncell, dead slots of a multi-GPU rebuild) again gets one atomic per warp
+        const bool dead = c == ncell;
+        const unsigned act = __activemask();
+        const unsigned md = __ballot_sync(act, dead);
+        int p;
+        if (dead) {
+            const int lane = threadIdx.x & 31, leader = __ffs(md) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(&cell_fill[c], __popc(md));
+            base = __shfl_sync(md, base, leader);
+            p = cell_start[c] + base + __popc(md & ((1u << lane) - 1u));
+        } else {
+            p = cell_start[c] + atomicAdd(&cell_fill[c], 1);
+        }
         order[p] = i;
     }
 }

@@ -60,6 +60,9 @@ struct pisb_handle {
     cudaStream_t copy_stream = nullptr;  // overlaps the position read-back of the host-buffer step with the force kernel
     cudaEvent_t ev_pos = nullptr;
     cudaStream_t up_stream = nullptr;    // chunked host-buffer step: host->device copies run ahead of the drift kernels
+    cudaStream_t dl_stream = nullptr;    // multi-GPU: the asynchronous owned-atom download (copy_stream carries the per-step flag there)
+    cudaEvent_t ev_dl = nullptr;
+    DevBuf<int> dl_ids;
     std::vector<cudaEvent_t> ev_chunk;   // ... one arrival / one departure event per chunk
     int host_pipeline = 1;               // option "host_pipeline": 0 = whole-array copies (the unpipelined sequence)
     int host_chunk_atoms = 0;            // option "host_chunk_atoms": atoms per chunk, 0 = auto (n/8, at least 65536)
@@ -638,7 +641,7 @@ int launch_rebuild_chain(pisb_t *h) {
         k_scan_tiles<<<ntiles, SCAN_TPB, 0, st>>>(nb, h->cell_count.p, h->tile_sum.p, h->flags);
         k_scan_sums<<<1, SCAN_TPB, 0, st>>>(ntiles, h->tile_sum.p, h->flags);
         k_scan_apply<<<ntiles, SCAN_TPB, 0, st>>>(nb, n, h->cell_count.p, h->tile_sum.p, h->cell_start.p, h->flags);
-        k_fill<<<nblk_capped(n, TPB, 8), TPB, 0, st>>>(n, h->cell_of.p, h->cell_start.p, h->cell_count.p, h->order.p, h->flags);
+        k_fill<<<nblk_capped(n, TPB, 8), TPB, 0, st>>>(n, g.ncell, h->cell_of.p, h->cell_start.p, h->cell_count.p, h->order.p, h->flags);
         k_sort_cells<<<nblk(g.ncell, TPB), TPB, 0, st>>>(g.ncell, h->cell_start.p, h->order.p, h->id.p, h->flags);
         PermArgs pa{n, h->order.p, h->xt.p, h->v[0].p, h->v[1].p, h->v[2].p, h->f[0].p, h->f[1].p, h->f[2].p,
                     h->id.p, h->s_xt.p, h->s_v[0].p, h->s_v[1].p, h->s_v[2].p, h->s_f[0].p, h->s_f[1].p,
@@ -988,7 +991,7 @@ int do_download_begin(pisb_t *h, double *pos, double *vel, double *frc) {
 int do_download_end(pisb_t *h) {
     if (!h->dl_pending) return PISB_OK;
     h->dl_pending = false;
-    CUDA_TRY(h, cudaStreamSynchronize(h->copy_stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->multi && h->dl_stream ? h->dl_stream : h->copy_stream));
     return PISB_OK;
 }
 
@@ -2250,6 +2253,7 @@ int pisb_destroy(pisb_t *h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);  // a download still in flight
+    if (h->dl_stream) cudaStreamSynchronize(h->dl_stream);
     free_positions(h, h->xt);
     dev_free(h, h->xf);
     dev_free(h, h->xp);
@@ -2259,6 +2263,7 @@ int pisb_destroy(pisb_t *h) {
     dev_free(h, h->dl_pos);
     dev_free(h, h->dl_vel);
     dev_free(h, h->dl_frc);
+    dev_free(h, h->dl_ids);
     for (int d = 0; d < 3; ++d) {
         dev_free(h, h->v[d]);
         dev_free(h, h->f[d]);
@@ -2320,6 +2325,8 @@ int pisb_destroy(pisb_t *h) {
     if (h->ev_pos) cudaEventDestroy(h->ev_pos);
     for (cudaEvent_t e : h->ev_chunk) cudaEventDestroy(e);
     if (h->up_stream) cudaStreamDestroy(h->up_stream);
+    if (h->dl_stream) cudaStreamDestroy(h->dl_stream);
+    if (h->ev_dl) cudaEventDestroy(h->ev_dl);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -2922,6 +2929,44 @@ int pisb_download_owned(pisb_t *h, int64_t cap, double *pos, double *vel, double
     if (force) CUDA_TRY(h, cudaMemcpyAsync(force, h->st_frc.p, sizeof(double) * 3 * no, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(gids, h->st_types.p, sizeof(int) * no, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    *n_out = no;
+    return PISB_OK;
+}
+
+// pisb_download_owned_begin: the same rows, asynchronously.  The owned atoms are compacted into snapshot buffers on the main
+// stream (a few hundred microseconds), the copies run on a stream of their own behind an event, and the next batch may start
+// at once; pisb_download_end waits for the frame.  n_out is known on the host (the owned count changes only in a rebuild).
+int pisb_download_owned_begin(pisb_t *h, int64_t cap, double *pos, double *vel, double *force, int32_t *gids, int64_t *n_out) {
+    if (!h || !n_out || !gids) return PISB_ERR_INVALID;
+    if (!h->multi || !h->have_atoms) return fail(h, PISB_ERR_STATE, "pisb_download_owned_begin needs multi-GPU mode and uploaded atoms");
+    if (h->dl_pending) return fail(h, PISB_ERR_STATE, "a download is already in flight: call pisb_download_end first");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const int n = h->n, no = h->n_own;
+    if (no > cap) return fail(h, PISB_ERR_CAPACITY, "pisb_download_owned_begin: cap too small");
+    if (!h->dl_stream) CUDA_TRY(h, cudaStreamCreateWithFlags(&h->dl_stream, cudaStreamNonBlocking));
+    if (!h->ev_dl) CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_dl, cudaEventDisableTiming));
+    const size_t n3 = (size_t)3 * std::max(no, 1);
+    if (pos) TRY(dev_reserve_grow(h, h->dl_pos, n3));
+    if (vel) TRY(dev_reserve_grow(h, h->dl_vel, n3));
+    if (force) TRY(dev_reserve_grow(h, h->dl_frc, n3));
+    TRY(dev_reserve_grow(h, h->dl_ids, (size_t)std::max(no, 1)));
+    TRY(dev_reserve(h, h->m_cnt, (size_t)std::max(h->dc.nranks, 1)));
+    CUDA_TRY(h, cudaMemsetAsync(h->m_cnt.p, 0, sizeof(int), h->stream));
+    {
+        LaunchScope ls(h, PISB_K_COPY);
+        k_store_owned<<<nblk(std::max(n, 1), TPB), TPB, 0, h->stream>>>(n, h->xt.p, h->v[0].p, h->v[1].p, h->v[2].p, h->f[0].p,
+                                                                       h->f[1].p, h->f[2].p, h->id.p, h->m_cnt.p,
+                                                                       pos ? h->dl_pos.p : nullptr, vel ? h->dl_vel.p : nullptr,
+                                                                       force ? h->dl_frc.p : nullptr, h->dl_ids.p);
+        TRY(check_launch(h, "k_store_owned"));
+    }
+    CUDA_TRY(h, cudaEventRecord(h->ev_dl, h->stream));
+    CUDA_TRY(h, cudaStreamWaitEvent(h->dl_stream, h->ev_dl, 0));
+    h->dl_pending = true;
+    if (pos) CUDA_TRY(h, cudaMemcpyAsync(pos, h->dl_pos.p, sizeof(double) * 3 * no, cudaMemcpyDeviceToHost, h->dl_stream));
+    if (vel) CUDA_TRY(h, cudaMemcpyAsync(vel, h->dl_vel.p, sizeof(double) * 3 * no, cudaMemcpyDeviceToHost, h->dl_stream));
+    if (force) CUDA_TRY(h, cudaMemcpyAsync(force, h->dl_frc.p, sizeof(double) * 3 * no, cudaMemcpyDeviceToHost, h->dl_stream));
+    CUDA_TRY(h, cudaMemcpyAsync(gids, h->dl_ids.p, sizeof(int) * no, cudaMemcpyDeviceToHost, h->dl_stream));
     *n_out = no;
     return PISB_OK;
 }

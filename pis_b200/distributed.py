@@ -89,6 +89,21 @@ class DistributedLJ(LJCudaManager):
         k = n.value
         return gid[:k], pos[:k], vel[:k], frc[:k]
 
+    def download_owned_begin(self, positions=True, velocities=True, forces=True):
+        """Asynchronous form: returns the same views at once; they hold the frame after download_end().  A second set of
+        pinned destination arrays, so a synchronous download_owned between begin and end does not disturb the frame."""
+        cap = int(self.stats()["n_atoms"]) + 16
+        if getattr(self, "_dla_cap", 0) < cap:
+            self._dla_cap = int(cap * 1.1) + 1024
+            self._dla = [capi.pinned_empty((self._dla_cap, 3)) for _ in range(3)] + [capi.pinned_empty((self._dla_cap,), np.int32)]
+        pos, vel, frc, gid = self._dla
+        n = C.c_int64()
+        capi.check(self._h, capi.load().pisb_download_owned_begin(self._h, self._dla_cap, capi._ptr(pos) if positions else None,
+                                                                  capi._ptr(vel) if velocities else None,
+                                                                  capi._ptr(frc) if forces else None, capi._ptr(gid), C.byref(n)))
+        k = n.value
+        return gid[:k], pos[:k], vel[:k], frc[:k]
+
     def neighbours_owned(self):
         """(gids, rows): sorted global-id neighbour rows of the owned atoms and the global id of each row (test hook)."""
         n = int(self.stats()["n_atoms"])

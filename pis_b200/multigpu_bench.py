@@ -126,7 +126,8 @@ def run(args):
     # ---- end to end: the Simulation::run loop of the host -- one batch per dump interval, thermo records back with the
     #      batch, the owned POSITIONS (+ global ids: what DumpTraj::write_step needs) back on dump steps ----
     e2e_steps = max(10, min(args.e2e_steps, args.steps))
-    mgr.download_owned(velocities=False, forces=False)  # untimed: allocates the pinned destination buffers that every later call reuses
+    mgr.download_owned_begin(velocities=False, forces=False)  # untimed: allocates the pinned destination and snapshot buffers
+    mgr.download_end()
     mgr.step_nve(B.DT, 10)
     st_e2e0 = mgr.stats()
     dist.barrier()
@@ -137,11 +138,13 @@ def run(args):
     while s < e2e_steps:
         chunk = min(10, e2e_steps - s)                       # dump cadence of example/input.pis
         mgr.step_nve(B.DT, chunk)
+        mgr.download_end()                                   # the previous dump frame travelled while this batch ran
         d2h += 32 * chunk
         s += chunk
         if s % 10 == 0:
-            g_, x_, v_, f_ = mgr.download_owned(velocities=False, forces=False)
+            g_, x_, v_, f_ = mgr.download_owned_begin(velocities=False, forces=False)
             d2h += x_.nbytes + g_.nbytes
+    mgr.download_end()
     mgr.synchronize()
     dist.barrier()
     e2e_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64)
@@ -218,7 +221,7 @@ def run(args):
             "e2e": {"value": n_global * e2e_steps / e2e_s, "unit": B.UNIT, "h2d_bytes_per_step": h2d_total // max(args.steps + e2e_steps + args.warmup, 1),
                     "d2h_bytes_per_step": d2h // e2e_steps, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
                     "call": "per rank: pisb_step_nve(dt, steps to the next dump) returning one thermo record per step and "
-                            "pisb_download_owned (positions + global ids) every 10 steps (the example's dump cadence); "
+                            "pisb_download_owned_begin / pisb_download_end (positions + global ids) every 10 steps (the example's dump cadence, the frame travels under the next batch); "
                             "state is uploaded once"},
             "gpu_launches": int(st1["n_launches"] - st0["n_launches"]),
             "multi_parity": multi_parity, "strong_32M": strong,

@@ -45,6 +45,9 @@ def run_check(rank: int, world: int, local: int, ncell: int = 16, steps: int = 6
     gr0, rows0 = mgr.neighbours_owned()
     th = mgr.step_nve(0.25, steps)
     g1, x1, v1, f1 = (a_.copy() for a_ in mgr.download_owned())
+    # the asynchronous form of the same download must deliver the same frame -- a snapshot: the batch that follows the begin
+    # (run below as the first steps of the NVT leg) must not leak into it
+    ga, xa, va, fa = mgr.download_owned_begin()
     st = mgr.stats()
     (F0,) = gather_by_gid(g0, [f0], n_global)
     X1, V1, F1 = gather_by_gid(g1, [x1, v1, f1], n_global)
@@ -54,6 +57,10 @@ def run_check(rank: int, world: int, local: int, ncell: int = 16, steps: int = 6
     # so far that the CPU restatement's own kinetic energy swings between 0.0 and 7e7 within 30 steps -- nothing to compare.
     chain = mgr.nhc_new(T0, 1.5 * T0, 100.0)
     th_nvt, en_nvt = mgr.step_nvt_nhc(0.25, 30, chain, 0, 30)
+    mgr.download_end()
+    oa, o1 = np.argsort(ga), np.argsort(g1)
+    async_ok = bool(np.array_equal(ga[oa], g1[o1]) and np.array_equal(xa[oa], x1[o1]) and np.array_equal(va[oa], v1[o1])
+                    and np.array_equal(fa[oa], f1[o1]))
     g3, x3, v3, _ = (a_.copy() for a_ in mgr.download_owned(forces=False))
     X3, V3 = gather_by_gid(g3, [x3, v3], n_global)
     # `velocity all create` on the device (pisb_start_velocities, collective): the bricks must get, per global id, the velocities
@@ -62,7 +69,7 @@ def run_check(rank: int, world: int, local: int, ncell: int = 16, steps: int = 6
     g2, _, v2, _ = (a_.copy() for a_ in mgr.download_owned(positions=False, forces=False))
     (V2,) = gather_by_gid(g2, [v2], n_global)
     pieces = [None] * world
-    dist.all_gather_object(pieces, (gr0, rows0, st))
+    dist.all_gather_object(pieces, (gr0, rows0, st, async_ok))
     out = None
     if rank == 0:
         # the same system on ONE GPU
@@ -99,7 +106,7 @@ def run_check(rank: int, world: int, local: int, ncell: int = 16, steps: int = 6
         v_init_err = float(np.abs(V2 - ref.velocities).max() / np.abs(ref.velocities).max())
         ref.positions[...], ref.velocities[...], ref.forces[...] = x_end, v_end, f_end
         mism = 0
-        for g, rows, _ in pieces:
+        for g, rows, _, _ in pieces:
             for k, gi in enumerate(g):
                 if not np.array_equal(rows[k], rows_ref[gi]):
                     mism += 1
@@ -116,12 +123,12 @@ def run_check(rank: int, world: int, local: int, ncell: int = 16, steps: int = 6
             "virial_ref_trace_rel": float(np.max(np.abs(th["virial_ref"] - th_ref["virial_ref"]) / np.maximum(np.abs(th_ref["virial_ref"]), 1.0))),
             "pos_max_abs": float(np.abs(X1 - ref.positions).max()),
             "vel_max_abs": float(np.abs(V1 - ref.velocities).max()),
-            "start_velocities_rel": v_init_err, "nvt": nvt,
+            "start_velocities_rel": v_init_err, "nvt": nvt, "async_download_is_a_snapshot": all(p[3] for p in pieces),
             "builds_multi": [p[2]["n_builds"] for p in pieces], "builds_single": single.stats()["n_builds"],
             "owned": [p[2]["n_atoms"] for p in pieces], "ghost": [p[2]["n_ghost"] for p in pieces],
         }
         ok = (mism == 0 and out["force_rel"] < 1e-10 and out["force0_max_abs"] < 1e-12 and out["pe0_rel"] < 1e-9 and out["pe_trace_rel"] < 1e-9
-              and out["ke_trace_rel"] < 1e-9 and v_init_err < 1e-12 and nvt["ok"])
+              and out["ke_trace_rel"] < 1e-9 and v_init_err < 1e-12 and nvt["ok"] and out["async_download_is_a_snapshot"])
         out["ok"] = bool(ok)
         single.close()
     dist.barrier()
