@@ -123,7 +123,8 @@ struct pisb_handle {
     int *flags = nullptr;
     unsigned int *ticket = nullptr;
     size_t ticket_cap = 0;  // words: 1 + one per group of 64 blocks (block_reduce_finalize)
-    int *h_flags = nullptr;          // pinned
+    int *h_flags = nullptr;          // pinned; [FLAG_COUNT] = sequence number of k_publish_flags
+    int pub_seq = 0;
     pisb_thermo *h_thermo = nullptr; // pinned
     size_t h_thermo_cap = 0;
     int64_t device_bytes = 0;
@@ -2015,6 +2016,21 @@ int do_compute_multi(pisb_t *h, int accumulate, double *pe) {
     return PISB_OK;
 }
 
+// Spin until k_publish_flags of sequence number `seq` has landed in h_flags (page-locked host memory the kernel writes
+// directly).  Every ~64k polls the stream is queried so that a failed launch or a device fault ends the wait.
+int wait_published(pisb_t *h, int seq) {
+    volatile int *pub = h->h_flags + FLAG_COUNT;
+    for (unsigned long long it = 1;; ++it) {
+        if (__atomic_load_n(pub, __ATOMIC_ACQUIRE) == seq) return PISB_OK;
+        if ((it & 0xffffull) == 0) {
+            const cudaError_t e = cudaStreamQuery(h->stream);
+            if (e != cudaSuccess && e != cudaErrorNotReady) return fail(h, PISB_ERR_CUDA, fmt("waiting for the step decision: %s", cudaGetErrorString(e)));
+            if (e == cudaSuccess && __atomic_load_n(pub, __ATOMIC_ACQUIRE) != seq)
+                return fail(h, PISB_ERR_CUDA, "the stream drained without publishing the step decision");
+        }
+    }
+}
+
 int do_step_nve_multi(pisb_t *h, double dt, int64_t nsteps, pisb_thermo *out) {
     if (!h->list_valid) TRY(multi_rebuild(h));
     TRY(check_bad_type(h));
@@ -2051,15 +2067,15 @@ int do_step_nve_multi(pisb_t *h, double dt, int64_t nsteps, pisb_thermo *out) {
             const bool speculate = v2_possible(h) && (h->force_variant == 0 || h->force_variant == 3 || h->force_variant == 6 || h->force_variant == 7);
             double *outp[3] = {h->g[0].p, h->g[1].p, h->g[2].p};
             if (speculate) {
-                if (fused)  // the decision word the speculative launch and the host read (see FLAG_DECISION)
-                    CUDA_TRY(h, cudaMemcpyAsync(h->flags + FLAG_DECISION, h->flags + FLAG_REBUILD, sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
-                CUDA_TRY(h, cudaEventRecord(h->ev_pos, h->stream));
-                CUDA_TRY(h, cudaStreamWaitEvent(h->copy_stream, h->ev_pos, 0));
-                CUDA_TRY(h, cudaMemcpyAsync(h->h_flags, h->flags, sizeof(int) * FLAG_COUNT, cudaMemcpyDeviceToHost, h->copy_stream));
+                // the decision word the speculative launch and the host read (see FLAG_DECISION) is set, and the flags reach
+                // the host, through k_publish_flags: no copy engine, no second stream
+                const int seq = ++h->pub_seq;
+                k_publish_flags<<<1, 32, 0, h->stream>>>(h->flags, h->h_flags, seq, fused ? 1 : 0);
+                h->n_launches += 1;
                 if (fused) TRY(launch_force_vv(h, s + 1 < m, dt, rec, h->flags + FLAG_DECISION));
                 else TRY(launch_force(h, outp, nullptr, rec, h->flags + FLAG_REBUILD));
                 const size_t spec_ev = h->ev_used;  // profiling: event pair of the speculative launch is ev_pool[spec_ev - 1]
-                CUDA_TRY(h, cudaStreamSynchronize(h->copy_stream));
+                TRY(wait_published(h, seq));
                 // a launch that turned out to be a no-op is not a force evaluation: book it under the (tiny) reduce class
                 if (h->profiling && spec_ev > 0 && h->h_flags[fused ? FLAG_DECISION : FLAG_REBUILD] != 0) h->ev_pool[spec_ev - 1].cls = PISB_K_REDUCE;
             } else {
@@ -2237,7 +2253,7 @@ int pisb_create(int device, int n_types, const double *mass, const double *eps, 
         return bail(fail(h, PISB_ERR_CUDA, "cudaStreamCreate failed"));
     if (cudaMalloc((void **)&h->flags, sizeof(int) * FLAG_COUNT) != cudaSuccess ||
         cudaMalloc((void **)&h->ticket, sizeof(unsigned int) * 64) != cudaSuccess ||
-        cudaHostAlloc((void **)&h->h_flags, sizeof(int) * FLAG_COUNT, cudaHostAllocDefault) != cudaSuccess)
+        cudaHostAlloc((void **)&h->h_flags, sizeof(int) * (FLAG_COUNT + 2), cudaHostAllocDefault) != cudaSuccess)
         return bail(fail(h, PISB_ERR_CUDA, "allocating control words failed"));
     cudaMemsetAsync(h->flags, 0, sizeof(int) * FLAG_COUNT, h->stream);
     h->ticket_cap = 64;
