@@ -21,6 +21,7 @@
 
 #include <dlfcn.h>
 #include <nccl.h>
+#include <nvtx3/nvToolsExt.h>  // header-only; a no-op unless a profiler is attached
 
 using namespace pisb;
 
@@ -270,11 +271,17 @@ void dev_free(pisb_t *h, DevBuf<T> &b) {
 }
 
 // ---- profiling -------------------------------------------------------------------------------
+// One scope per launch (or launch group) of a kernel class: the launch counter, an NVTX range named after the class (the
+// phases of a step show up as ranges in an Nsight timeline: the reference has no tracing), and with
+// pisb_set_profiling an event pair for pisb_timings.
+static const char *const kClassName[PISB_K_COUNT] = {"pisb:integrate", "pisb:bin", "pisb:sort", "pisb:build", "pisb:force",
+                                                     "pisb:reduce", "pisb:halo", "pisb:copy"};
 struct LaunchScope {
     pisb_t *h;
     int idx = -1;
     LaunchScope(pisb_t *h_, int cls) : h(h_) {
         h->n_launches++;
+        nvtxRangePushA(kClassName[cls]);
         if (!h->profiling) return;
         if (h->ev_used == h->ev_pool.size()) {
             pisb_handle::Ev e;
@@ -289,6 +296,7 @@ struct LaunchScope {
     }
     ~LaunchScope() {
         if (idx >= 0) cudaEventRecord(h->ev_pool[idx].b, h->stream);
+        nvtxRangePop();
     }
 };
 
