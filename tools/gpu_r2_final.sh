@@ -1,0 +1,18 @@
+#!/bin/bash
+# round 2, final visit (1 GPU): the whole -m gpu suite on the final tree, smoke(), bench.py as the driver runs it, the reference
+# arm, the ncu launch list of a short bench and the --set full capture of the step kernel, memcheck / racecheck of smoke()
+mkdir -p gpurun_out
+O=gpurun_out
+{ nproc; free -g | head -2; nvidia-smi --query-gpu=name,memory.total --format=csv,noheader; git rev-parse --short HEAD 2>/dev/null; } > $O/r02_box_final.txt 2>&1
+timeout 1800 python -m pytest tests -m gpu -q --durations=8 > $O/r02_pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $O/r02_pytest_gpu.log
+tail -n 16 $O/r02_pytest_gpu.log
+timeout 300 python __graft_entry__.py --smoke > $O/r02_smoke.log 2>&1; echo "smoke rc=$?" >> $O/r02_smoke.log; tail -n 4 $O/r02_smoke.log
+timeout 600 python bench.py > $O/r02_bench_1gpu_4M.log 2> $O/r02_bench_1gpu_4M.err; echo "bench rc=$?"
+tail -c 1500 $O/r02_bench_1gpu_4M.log; tail -n 3 $O/r02_bench_1gpu_4M.err
+timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > $O/r02_bench_reference_arm.log 2> $O/r02_bench_reference_arm.err; echo "reference rc=$?"
+tail -c 800 $O/r02_bench_reference_arm.log
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/r02_launches.csv python bench.py --steps 6 --warmup 3 --no-strong --no-cpu-baseline --e2e-steps 3 > $O/r02_launches_bench.log 2>&1; echo "launch list rc=$?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_force_vv" -s 30 -c 1 -f -o $O/r02_prof_force_vv_final python tools/prof_one.py 0 0 100 40 43 0 cuda_graphs=0 > $O/r02_ncu_force_vv_final.log 2>&1; tail -n 2 $O/r02_ncu_force_vv_final.log
+timeout 420 compute-sanitizer --tool memcheck --error-exitcode 3 python __graft_entry__.py --smoke > $O/r02_sanitizer_memcheck.log 2>&1; echo "memcheck rc=$?" | tee -a $O/r02_sanitizer_memcheck.log
+timeout 420 compute-sanitizer --tool racecheck --error-exitcode 3 python __graft_entry__.py --smoke > $O/r02_sanitizer_racecheck.log 2>&1; echo "racecheck rc=$?" | tee -a $O/r02_sanitizer_racecheck.log
+tail -n 3 $O/r02_sanitizer_memcheck.log $O/r02_sanitizer_racecheck.log
