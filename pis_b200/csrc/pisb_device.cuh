@@ -159,6 +159,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 // Every sum has a fixed association, so results do not depend on scheduling.  A single last block summing ALL block
 // partials (31 250 x NQ loads from one SM at 4M atoms) was a 60 us (NQ = 2) to 240 us (NQ = 6) serial tail of the force
 // kernels; with groups the last block reads 64 + nblocks/64 values per quantity.
+// Grids of at most RED_GROUP blocks (the 4000-atom example: 63 blocks) stop after the second level.
 // All threads of the block must call this.  partials: NQ * (nblocks + ngroups) doubles; ticket: 1 + ngroups words, zeroed
 // once (they reset themselves).
 constexpr int RED_GROUP = 64;
@@ -203,14 +204,20 @@ __device__ __forceinline__ void block_reduce_finalize(double (&v)[NQ], double *_
             double acc = 0.0;
             for (unsigned int k = lane; k < gs; k += 32) acc += __ldcg(&partials[(size_t)q * nb + b0 + k]);
             acc = warp_sum(acc);
-            if (lane == 0) level1[(size_t)q * ng + g] = acc;
+            if (lane == 0) {
+                if (ng == 1) fin(q, acc);  // a grid of <= 64 blocks: the group sum IS the grid sum (the value the third level
+                else level1[(size_t)q * ng + g] = acc;  // would return, without its ticket, fences and 2 NQ barriers)
+            }
         }
         if (lane == 0) {
             ticket[1 + g] = 0u;
-            __threadfence();
-            s_grid_last = atomicAdd(&ticket[0], 1u) == ng - 1;
+            if (ng > 1) {
+                __threadfence();
+                s_grid_last = atomicAdd(&ticket[0], 1u) == ng - 1;
+            }
         }
     }
+    if (ng == 1) return;
     __syncthreads();
     if (!s_grid_last) return;
     __threadfence();

@@ -126,6 +126,7 @@ struct pisb_handle {
     size_t ticket_cap = 0;  // words: 1 + one per group of 64 blocks (block_reduce_finalize)
     int *h_flags = nullptr;          // pinned; [FLAG_COUNT] = sequence number of k_publish_flags
     int pub_seq = 0;
+    bool table_on_device = false;  // table_d holds the pair table (setup_filter)
     pisb_thermo *h_thermo = nullptr; // pinned
     size_t h_thermo_cap = 0;
     int64_t device_bytes = 0;
@@ -390,6 +391,10 @@ bool quad_mode(const pisb_t *h) {
 int setup_filter(pisb_t *h) {
     if (!h->have_box) return PISB_OK;
     const int nt = h->n_types;
+    // A box the FP32 / lean kernels cannot serve (triclinic: every NPT step after the first) runs on the reference-order
+    // kernels, which read only the box-independent part of the table (c4, c24, sig2, t_rc, t_list, ucut): once it is on the
+    // device there is nothing to recompute, upload or wait for when the box changes (a sync per NPT step).
+    if (!v2_possible(h) && h->table_on_device) return PISB_OK;
     double lmax = 0.0;
     for (int d = 0; d < 3; ++d) {
         h->boxf.L[d] = (float)h->box.h[4 * d];
@@ -422,6 +427,7 @@ int setup_filter(pisb_t *h) {
     }
     CUDA_TRY(h, cudaMemcpyAsync(h->table_d.p, h->pairs.data(), sizeof(PairDev) * nt * nt, cudaMemcpyHostToDevice, h->stream));
     TRY(dev_reserve(h, h->tablef_d, (size_t)nt * nt));
+    h->table_on_device = true;
     if (!v2_possible(h)) {  // the FP32 pre-filter kernels are not selectable for this box
         CUDA_TRY(h, cudaStreamSynchronize(h->stream));
         return PISB_OK;
