@@ -327,6 +327,13 @@ __global__ void k_publish_flags(int *__restrict__ flags, volatile int *__restric
     __syncwarp();
     if (t == 0) host[FLAG_COUNT] = seq;
 }
+// the same for any short word array (the rebuild's count tables): host[0..n) = src[0..n), then host[n] = seq; one warp
+__global__ void k_publish_words(const int *__restrict__ src, volatile int *__restrict__ host, int n, int seq) {
+    for (int k = threadIdx.x; k < n; k += 32) host[k] = src[k];
+    __threadfence_system();
+    __syncwarp();
+    if (threadIdx.x == 0) host[n] = seq;
+}
 
 // ---- owned-atom download ----------------------------------------------------------------------
 __global__ void __launch_bounds__(TPB) k_store_owned(int n, const double4 *__restrict__ xt, const double *vx,

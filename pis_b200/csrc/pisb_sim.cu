@@ -1663,12 +1663,15 @@ int load_nccl(pisb_t *h) {
     } while (0)
 
 // all-gather `cnt` (nranks ints per rank) and bring the nranks^2 table to the host (synchronous)
+int wait_published(pisb_t *h, volatile int *pub, int seq);
+
 int gather_counts(pisb_t *h) {
     const int R = h->dc.nranks;
     NCCL_TRY(h, g_nccl.AllGather(h->m_cnt.p, h->m_allcnt.p, R, ncclInt, h->comm, h->stream));
-    CUDA_TRY(h, cudaMemcpyAsync(h->h_counts, h->m_allcnt.p, sizeof(int) * R * R, cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-    return PISB_OK;
+    // to the host without a copy engine (a D2H copy would queue behind an asynchronous dump frame: 8.6 ms at 8 GPUs)
+    const int seq = ++h->pub_seq;
+    k_publish_words<<<1, 32, 0, h->stream>>>(h->m_allcnt.p, h->h_counts, R * R, seq);
+    return wait_published(h, h->h_counts + R * R, seq);
 }
 
 // grouped pairwise exchange of `rec` doubles per item with every other rank
@@ -1840,7 +1843,11 @@ int multi_rebuild(pisb_t *h) {
         }
         h->n = n_own + gr;  // live slots (cell-sorted) after the sort compacted the dead ones away
         tw[5] = wall_now();
-        TRY(read_flags(h));
+        {
+            const int seq = ++h->pub_seq;
+            k_publish_flags<<<1, 32, 0, st>>>(h->flags, h->h_flags, seq, 0);
+            TRY(wait_published(h, h->h_flags + FLAG_COUNT, seq));
+        }
         tw[6] = wall_now();
         const int mx = h->h_flags[FLAG_MAXNBR];
         h->n_builds_host = h->h_flags[FLAG_NBUILDS];
@@ -2032,8 +2039,7 @@ int do_compute_multi(pisb_t *h, int accumulate, double *pe) {
 
 // Spin until k_publish_flags of sequence number `seq` has landed in h_flags (page-locked host memory the kernel writes
 // directly).  Every ~64k polls the stream is queried so that a failed launch or a device fault ends the wait.
-int wait_published(pisb_t *h, int seq) {
-    volatile int *pub = h->h_flags + FLAG_COUNT;
+int wait_published(pisb_t *h, volatile int *pub, int seq) {
     for (unsigned long long it = 1;; ++it) {
         if (__atomic_load_n(pub, __ATOMIC_ACQUIRE) == seq) return PISB_OK;
         if ((it & 0xffffull) == 0) {
@@ -2089,7 +2095,7 @@ int do_step_nve_multi(pisb_t *h, double dt, int64_t nsteps, pisb_thermo *out) {
                 if (fused) TRY(launch_force_vv(h, s + 1 < m, dt, rec, h->flags + FLAG_DECISION));
                 else TRY(launch_force(h, outp, nullptr, rec, h->flags + FLAG_REBUILD));
                 const size_t spec_ev = h->ev_used;  // profiling: event pair of the speculative launch is ev_pool[spec_ev - 1]
-                TRY(wait_published(h, seq));
+                TRY(wait_published(h, h->h_flags + FLAG_COUNT, seq));
                 // a launch that turned out to be a no-op is not a force evaluation: book it under the (tiny) reduce class
                 if (h->profiling && spec_ev > 0 && h->h_flags[fused ? FLAG_DECISION : FLAG_REBUILD] != 0) h->ev_pool[spec_ev - 1].cls = PISB_K_REDUCE;
             } else {
@@ -2868,7 +2874,7 @@ int pisb_comm_init(pisb_t *h, int rank, int nranks, const void *unique_id, const
     h->dc.b[0] = rank % grid3[0];
     h->dc.b[1] = (rank / grid3[0]) % grid3[1];
     h->dc.b[2] = rank / (grid3[0] * grid3[1]);
-    CUDA_TRY(h, cudaHostAlloc((void **)&h->h_counts, sizeof(int) * nranks * nranks, cudaHostAllocDefault));
+    CUDA_TRY(h, cudaHostAlloc((void **)&h->h_counts, sizeof(int) * (nranks * nranks + 2), cudaHostAllocDefault));  // + the sequence word of k_publish_words
     h->grid_ok = false;
     h->list_valid = false;
     return PISB_OK;
