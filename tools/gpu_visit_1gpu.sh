@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, final visit (1 GPU): the whole -m gpu suite on the final tree, smoke(), bench.py as the driver runs it, the reference
+# single-GPU visit: the whole -m gpu suite on the final tree, smoke(), bench.py as the driver runs it, the reference
 # arm, the ncu launch list of a short bench and the --set full capture of the step kernel, memcheck / racecheck of smoke()
 mkdir -p gpurun_out
 O=gpurun_out
@@ -16,3 +16,4 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_f
 timeout 420 compute-sanitizer --tool memcheck --error-exitcode 3 python __graft_entry__.py --smoke > $O/r02_sanitizer_memcheck.log 2>&1; echo "memcheck rc=$?" | tee -a $O/r02_sanitizer_memcheck.log
 timeout 420 compute-sanitizer --tool racecheck --error-exitcode 3 python __graft_entry__.py --smoke > $O/r02_sanitizer_racecheck.log 2>&1; echo "racecheck rc=$?" | tee -a $O/r02_sanitizer_racecheck.log
 tail -n 3 $O/r02_sanitizer_memcheck.log $O/r02_sanitizer_racecheck.log
+timeout 300 python tools/small_systems.py > $O/r02_small_systems.jsonl 2> $O/r02_small_systems.err; echo "small rc=$?"; tail -n 12 $O/r02_small_systems.jsonl | cut -c1-400
