@@ -125,7 +125,7 @@ def run(args):
 
     # ---- end to end: the Simulation::run loop of the host -- one batch per dump interval, thermo records back with the
     #      batch, the owned POSITIONS (+ global ids: what DumpTraj::write_step needs) back on dump steps ----
-    e2e_steps = max(10, min(args.e2e_steps, args.steps))
+    e2e_steps = max(60, args.e2e_steps)   # >= 6 dump intervals: the frame of the LAST dump is waited for in the open (one per run)
     mgr.download_owned_begin(velocities=False, forces=False)  # untimed: allocates the pinned destination and snapshot buffers
     mgr.download_end()
     mgr.step_nve(B.DT, 10)
