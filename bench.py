@@ -142,10 +142,10 @@ def fp64_roofline(kernel: str, k_mean: float, k_in: float, n_atoms: int, ms_per_
                     "the kernel issues (SASS count x listed pairs) / the DFMA rate = the pipe's utilisation"}
 
 
-# What actually binds the step kernel (ncu, profiles/r02_force_vv_lean_full.*): the L1TEX DATA PIPE.  Every listed pair is one
+# What actually binds the step kernel (ncu, profiles/r02_force_vv_final.*): the L1TEX DATA PIPE.  Every listed pair is one
 # scattered 32-byte record, and the data stage delivers one 128-byte line ("wavefront") per clock and SM whatever part of the
-# line is wanted: l1tex__data_pipe_lsu_wavefronts 90.9 % of peak, 0.878 wavefronts per listed pair (neighbours that share a
-# line share a wavefront), while the FP64 pipe is 43 % busy and DRAM 23 %.  Live part: listed pairs per second from this run's
+# line is wanted: l1tex__data_pipe_lsu_wavefronts 89 % of peak, 0.83 wavefronts per listed pair (neighbours that share a
+# line share a wavefront), while the FP64 pipe is 45 % busy and DRAM 24 %.  Live part: listed pairs per second from this run's
 # list and launch time; the wavefronts-per-pair factor is the static ncu calibration (profiles/force_traffic.json).
 def l1tex_roofline(kernel: str, k_mean: float, n_atoms: int, ms_per_launch: float, sm_mhz, cal: dict) -> dict:
     clock = float(sm_mhz or 1965.0) * 1e6
@@ -156,9 +156,10 @@ def l1tex_roofline(kernel: str, k_mean: float, n_atoms: int, ms_per_launch: floa
             "frac": pairs_per_s * w / peak, "listed_pairs_per_s": pairs_per_s, "wavefronts_per_listed_pair_ncu": w,
             "data_pipe_pct_ncu": cal.get("l1tex_data_pipe_lsu_wavefronts_pct"), "lsu_writeback_pct_ncu": cal.get("l1tex_lsu_writeback_active_pct"),
             "sm_clock_mhz": clock / 1e6, "ms_per_launch": ms_per_launch, "peak_source": "1 data-pipe wavefront per clock and SM x 148 SMs x the SM clock sampled under load",
-            "note": "THE BINDING RESOURCE of the force loop (ncu: l1tex__data_pipe_lsu_wavefronts 90.9 % of peak; FP64 pipe 43 %, DRAM "
-                    "23 %): every listed pair is a scattered 32-byte record and costs one 128-byte data-pipe wavefront.  achieved = "
-                    "live listed pairs/s x the static ncu wavefronts-per-pair factor; *_ncu fields are static (profiles/force_traffic.json)"}
+            "note": f"THE BINDING RESOURCE of the force loop (ncu: l1tex__data_pipe_lsu_wavefronts {cal.get('l1tex_data_pipe_lsu_wavefronts_pct', float('nan')):.1f} % "
+                    f"of peak; FP64 pipe {cal.get('fp64_pipe_active_pct', float('nan')):.0f} %, DRAM {cal.get('dram_throughput_pct', float('nan')):.0f} %): every listed pair "
+                    "is a scattered 32-byte record and costs one 128-byte data-pipe wavefront.  achieved = live listed pairs/s x the "
+                    "static ncu wavefronts-per-pair factor; *_ncu fields are static (profiles/force_traffic.json)"}
 
 
 def force_calibration(kernel_name: str):
