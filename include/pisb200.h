@@ -66,6 +66,9 @@ typedef struct {
     int64_t n_steps;        /* NVE steps so far */
     int64_t n_launches;     /* kernels launched by this handle so far */
     int64_t device_bytes;   /* device memory held */
+    int64_t missing_type_pairs; /* unordered type pairs (i <= j) that atoms of this handle populate but the table does not hold:
+                                 * their pairs are skipped.  (The reference prints a line per candidate pair and skips it,
+                                 * lennard_jones.rs:216-222; here it is a count, taken when the types are uploaded.) */
 } pisb_stats_t;
 
 /* kernel classes for pisb_timings */

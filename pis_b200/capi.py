@@ -27,7 +27,7 @@ class Stats(C.Structure):
     _fields_ = [("n_atoms", C.c_int64), ("n_ghost", C.c_int64), ("n_cells", C.c_int64 * 3),
                 ("list_capacity", C.c_int64), ("max_neighbours", C.c_int64), ("capacity_growths", C.c_int64),
                 ("n_builds", C.c_int64), ("n_steps", C.c_int64), ("n_launches", C.c_int64),
-                ("device_bytes", C.c_int64)]
+                ("device_bytes", C.c_int64), ("missing_type_pairs", C.c_int64)]
 
     def as_dict(self) -> dict:
         d = {k: getattr(self, k) for k, _ in self._fields_ if k != "n_cells"}

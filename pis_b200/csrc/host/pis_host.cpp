@@ -250,6 +250,12 @@ void LJCudaManager::attach(const Atoms &atoms) {
     check(pisb_set_box(h_, atoms.sim_box.h, atoms.sim_box.h_inv, pbc));
     check(pisb_upload(h_, (int64_t)atoms.n_atoms, atoms.positions.data(), atoms.velocities.data(), atoms.forces.data(),
                       atoms.type_ids.data()));
+    // The reference prints "During force calculation between i and j atoms, potential was missing" for every candidate pair of
+    // every step (lennard_jones.rs:216-222) and skips the pair; here the pairs are skipped the same way and the host says so once.
+    pisb_stats_t st{};
+    if (pisb_stats(h_, &st) == PISB_OK && st.missing_type_pairs > 0)
+        std::fprintf(stderr, "warning: %lld type pair(s) with atoms present have no pair potential: their interactions are skipped\n",
+                     (long long)st.missing_type_pairs);
 }
 
 double LJCudaManager::compute(bool accumulate) {

@@ -1973,6 +1973,8 @@ __device__ __forceinline__ int build3_body(const Build2Args &a, const float *__r
             const int first = jb - 2 * q0, last = je - 2 * q0;  // valid bits: [first, last)
             unsigned valid = last >= 32 ? 0xffffffffu : ((1u << last) - 1u);
             if (first > 0) valid &= ~((1u << first) - 1u);
+            const unsigned self = (unsigned)(i - 2 * q0);  // the atom itself, when this chunk holds it, is no neighbour
+            if (self < 32u) valid &= ~(1u << self);
             m_hi &= valid;
             // FP32 guard band: the exact FP64 reference predicate decides
             unsigned band = m_hi & ~m_lo;
@@ -2017,12 +2019,7 @@ __device__ __forceinline__ int build3_body(const Build2Args &a, const float *__r
             if (IMAGE && xlo < 0 && !a.g.local[0]) scan(__ldg(&a.cell_start[rb + xlo + nx]), __ldg(&a.cell_start[rb + nx]));
             const int jb = __ldg(&a.cell_start[rb + max(xlo, 0)]);
             const int je = __ldg(&a.cell_start[rb + min(xhi, nx - 1) + 1]);
-            if (i >= jb && i < je) {  // the range that holds i itself: skip i == j by splitting it
-                scan(jb, i);
-                scan(i + 1, je);
-            } else {
-                scan(jb, je);
-            }
+            scan(jb, je);  // (i itself is masked out inside: splitting the range at i cost the centre row a second chunk)
             if (IMAGE && xhi >= nx && !a.g.local[0]) scan(__ldg(&a.cell_start[rb]), __ldg(&a.cell_start[rb + xhi - nx + 1]));
         }
     }

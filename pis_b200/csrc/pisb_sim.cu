@@ -127,6 +127,7 @@ struct pisb_handle {
     int *h_flags = nullptr;          // pinned; [FLAG_COUNT] = sequence number of k_publish_flags
     int pub_seq = 0;
     bool table_on_device = false;  // table_d holds the pair table (setup_filter)
+    int64_t missing_type_pairs = 0;  // populated type pairs without a potential (count_missing_pairs)
     pisb_thermo *h_thermo = nullptr; // pinned
     size_t h_thermo_cap = 0;
     int64_t device_bytes = 0;
@@ -902,6 +903,23 @@ int stage_in(pisb_t *h, DevBuf<double> &dst, const double *src, size_t count) {
     return PISB_OK;
 }
 
+// Type pairs the atoms populate but the table does not hold (their pairs are skipped, like the reference's `None => continue`,
+// lennard_jones.rs:216-222).  Host-side, only when types arrive and the table has a hole at all.
+void count_missing_pairs(pisb_t *h, int64_t n, const int32_t *types) {
+    h->missing_type_pairs = 0;
+    const int nt = h->n_types;
+    bool hole = false;
+    for (int a = 0; a < nt; ++a)  // the table is read at (min, max): the upper triangle is what counts
+        for (int b = a; b < nt; ++b) hole = hole || !h->pairs[(size_t)a * nt + b].present;
+    if (!hole || !types) return;
+    std::vector<int64_t> pop((size_t)nt, 0);
+    for (int64_t i = 0; i < n; ++i)
+        if (types[i] >= 1 && types[i] <= nt) pop[(size_t)types[i] - 1]++;
+    for (int a = 0; a < nt; ++a)
+        for (int b = a; b < nt; ++b)
+            if (!h->pairs[(size_t)a * nt + b].present && pop[a] > 0 && pop[b] > (a == b ? 1 : 0)) h->missing_type_pairs++;
+}
+
 int do_upload(pisb_t *h, int64_t n64, const double *pos, const double *vel, const double *frc,
               const int32_t *types) {
     if (n64 <= 0 || n64 > 2000000000LL) return fail(h, PISB_ERR_INVALID, "atom count out of range");
@@ -927,6 +945,7 @@ int do_upload(pisb_t *h, int64_t n64, const double *pos, const double *vel, cons
     if (types) {
         TRY(dev_reserve(h, h->st_types, (size_t)n));
         CUDA_TRY(h, cudaMemcpyAsync(h->st_types.p, types, sizeof(int) * n, cudaMemcpyHostToDevice, h->stream));
+        count_missing_pairs(h, n, types);
     }
     {
         LaunchScope ls(h, PISB_K_COPY);
@@ -2815,6 +2834,7 @@ int pisb_stats(pisb_t *h, pisb_stats_t *out) {
     out->n_steps = h->n_steps;
     out->n_launches = h->n_launches;
     out->device_bytes = h->device_bytes;
+    out->missing_type_pairs = h->missing_type_pairs;
     return PISB_OK;
 }
 
@@ -2924,6 +2944,7 @@ int pisb_upload_owned(pisb_t *h, int64_t n_own, const double *pos, const double 
         if (vel) CUDA_TRY(h, cudaMemcpyAsync(h->st_vel.p, vel, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, h->stream));
         if (force) CUDA_TRY(h, cudaMemcpyAsync(h->st_frc.p, force, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, h->stream));
         CUDA_TRY(h, cudaMemcpyAsync(h->st_types.p, types, sizeof(int) * n, cudaMemcpyHostToDevice, h->stream));
+    count_missing_pairs(h, n_own, types);  // this rank's atoms
         CUDA_TRY(h, cudaMemcpyAsync(h->m_dest.p, gids, sizeof(int) * n, cudaMemcpyHostToDevice, h->stream));
         LaunchScope ls(h, PISB_K_COPY);
         LoadArgs la{n, h->st_pos.p, vel ? h->st_vel.p : nullptr, force ? h->st_frc.p : nullptr, h->st_types.p, nullptr,

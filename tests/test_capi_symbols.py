@@ -28,7 +28,7 @@ def test_version_and_struct_layouts():
     lib = capi.load()
     assert b"sm_100a" in lib.pisb_version()
     assert C.sizeof(capi.Thermo) == 32 and capi.THERMO_DTYPE.itemsize == 32
-    assert C.sizeof(capi.Stats) == 8 * 12
+    assert C.sizeof(capi.Stats) == 8 * 13
     assert lib.pisb_device_count() >= 0
 
 

@@ -177,9 +177,9 @@ def test_two_types_and_missing_pair():
     atoms = _jittered(6, jitter=0.2)
     atoms.type_ids[::3] = 2
     atoms.masses = [39.948, 20.18]
-    for table in (
-        {(1, 1): LennardJones(0.238, 3.405, 8.5), (1, 2): LennardJones(0.15, 3.0, 7.5), (2, 2): LennardJones(0.07, 2.8, 7.0)},
-        {(1, 1): LennardJones(0.238, 3.405, 8.5), (2, 1): LennardJones(0.15, 3.0, 7.5), (2, 2): LennardJones(0.07, 2.8, 7.0)},
+    for missing, table in (
+        (0, {(1, 1): LennardJones(0.238, 3.405, 8.5), (1, 2): LennardJones(0.15, 3.0, 7.5), (2, 2): LennardJones(0.07, 2.8, 7.0)}),
+        (1, {(1, 1): LennardJones(0.238, 3.405, 8.5), (2, 1): LennardJones(0.15, 3.0, 7.5), (2, 2): LennardJones(0.07, 2.8, 7.0)}),
     ):
         atoms.forces[...] = 0.0
         orc = make_oracle(atoms, table)
@@ -191,6 +191,8 @@ def test_two_types_and_missing_pair():
         start, nbr = orc.build_neighbour_list(atoms.positions, atoms.type_ids, extra=0.5)
         for a_, b_ in zip(mgr.neighbours(atoms.n_atoms), csr_rows_sorted(start, nbr)):
             assert np.array_equal(a_, b_)
+        # the reference's "potential was missing" line per candidate pair (lennard_jones.rs:216-222) is a count here
+        assert mgr.stats()["missing_type_pairs"] == missing
 
 
 def test_triclinic_box_general_path():
