@@ -46,7 +46,9 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock + throttle reasons during the timed region (B200_PROFILING.md recipe).  NVML through pynvml when it is there
+    (a query takes tens of microseconds: one sample every 5 ms, so even a 30 ms region holds several); the nvidia-smi command
+    line of the recipe otherwise (one sample per ~0.2 s)."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -54,18 +56,50 @@ class ClockSampler:
 
     def __init__(self, index: int = 0):
         self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+        self.source = "nvidia-smi"
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            handle = None
+            try:  # the CUDA device, not the NVML index (CUDA_VISIBLE_DEVICES may renumber)
+                import torch
+                handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(torch.cuda.get_device_properties(index).uuid)).encode())
+            except Exception:
+                handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self._nvml = (pynvml, handle)
+            self.source = "nvml"
+        except Exception:
+            self._nvml = None
+
+    def _sample_nvml(self):
+        nv, hd = self._nvml
+        sm = nv.nvmlDeviceGetClockInfo(hd, nv.NVML_CLOCK_SM)
+        mx = nv.nvmlDeviceGetMaxClockInfo(hd, nv.NVML_CLOCK_SM)
+        try:
+            pw = nv.nvmlDeviceGetPowerUsage(hd) / 1000.0
+        except Exception:
+            pw = "n/a"
+        r = nv.nvmlDeviceGetCurrentClocksEventReasons(hd) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else nv.nvmlDeviceGetCurrentClocksThrottleReasons(hd)
+        act = lambda bit: "Active" if (r & bit) else "Not Active"
+        return [str(sm), str(mx), str(pw), act(nv.nvmlClocksEventReasonHwSlowdown), act(nv.nvmlClocksEventReasonHwThermalSlowdown),
+                act(nv.nvmlClocksEventReasonSwThermalSlowdown), act(nv.nvmlClocksEventReasonSwPowerCap)]
 
     def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(",")]
-                if len(parts) >= 7:
-                    self.rows.append(parts)
+                if self._nvml:
+                    self.rows.append(self._sample_nvml())
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                    parts = [p.strip() for p in out.strip().split(",")]
+                    if len(parts) >= 7:
+                        self.rows.append(parts)
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.005 if self._nvml else 0.2)
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -87,7 +121,7 @@ class ClockSampler:
         except ValueError:
             pw = None
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "power_w_max": pw,
-                "samples": len(self.rows), "reasons": reasons}
+                "samples": len(self.rows), "source": self.source, "reasons": reasons}
 
 
 def measure_pcie(host_array, reps: int = 4) -> dict:
