@@ -2295,6 +2295,7 @@ int pisb_create(int device, int n_types, const double *mass, const double *eps, 
         cudaHostAlloc((void **)&h->h_flags, sizeof(int) * (FLAG_COUNT + 2), cudaHostAllocDefault) != cudaSuccess)
         return bail(fail(h, PISB_ERR_CUDA, "allocating control words failed"));
     cudaMemsetAsync(h->flags, 0, sizeof(int) * FLAG_COUNT, h->stream);
+    std::memset(h->h_flags, 0, sizeof(int) * (FLAG_COUNT + 2));  // incl. the sequence word the host spins on (wait_published)
     h->ticket_cap = 64;
     cudaMemsetAsync(h->ticket, 0, sizeof(unsigned int) * 64, h->stream);
     int rc = build_pair_table(h);
@@ -2895,6 +2896,7 @@ int pisb_comm_init(pisb_t *h, int rank, int nranks, const void *unique_id, const
     h->dc.b[1] = (rank / grid3[0]) % grid3[1];
     h->dc.b[2] = rank / (grid3[0] * grid3[1]);
     CUDA_TRY(h, cudaHostAlloc((void **)&h->h_counts, sizeof(int) * (nranks * nranks + 2), cudaHostAllocDefault));  // + the sequence word of k_publish_words
+    std::memset(h->h_counts, 0, sizeof(int) * (nranks * nranks + 2));
     h->grid_ok = false;
     h->list_valid = false;
     return PISB_OK;
