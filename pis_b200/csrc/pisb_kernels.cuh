@@ -1227,6 +1227,8 @@ __device__ __forceinline__ void force3_body(const Force2Args &a, int i, double &
     int4 cur = nn > 0 ? ldg_stream_i4(tiles) : make_int4(0, 0, 0, 0);
     LeanAcc<MULTI> acc;
     bool ambiguous = false;
+    // (prefetch.global.L1 of the next tile's four records while the current tile is computed: 1.128 -> 1.509 ms per launch --
+    // every extra L1TEX request is paid in full, profiles/r02_ab_prefetch_4M_43K.jsonl)
     // the loop carries one pointer and one count (k and nn as two live values cost the 64-register kernel a reload per tile)
     for (int rem = nn; rem > 0; rem -= 4) {
         int4 nxt = cur;
