@@ -254,8 +254,9 @@ PISB_API int pisb_upload_owned(pisb_t *h, int64_t n_own, const double *pos, cons
  * arbitrary -- global_ids identifies each row.  Arrays hold up to cap atoms; *n_out = count. */
 PISB_API int pisb_download_owned(pisb_t *h, int64_t cap, double *pos, double *vel, double *force,
                                  int32_t *global_ids, int64_t *n_out);
-/* The same rows, asynchronously: the owned atoms are snapshotted on the device, the copies run on a stream of their own and
- * the next pisb_step_nve batch may start at once; *n_out is valid on return, the arrays after pisb_download_end(h).
+/* The same rows, asynchronously: the owned atoms are snapshotted on the device, the copies run on a stream of their own -- in
+ * pieces, spread over the steps of the next pisb_step_nve batch (option dump_spread_steps) -- and that batch may start at once;
+ * *n_out is valid on return, the arrays after pisb_download_end(h).
  * (Multi-GPU form of pisb_download_begin: a dump frame of Simulation::run, src/simulation.rs:84-86, hidden under the steps
  * that follow.)  Host arrays should be page-locked (pisb_host_register). */
 PISB_API int pisb_download_owned_begin(pisb_t *h, int64_t cap, double *pos, double *vel, double *force,
@@ -283,6 +284,8 @@ PISB_API int pisb_list_stats(pisb_t *h, int64_t *out3);
  *                     7 = k_force_q: 4 lanes per atom taking one entry of every K-tile each
  *   build_variant     0 = automatic (v3), 1 = v1 general, 2 = scalar FP32 pre-filter, 3 = packed-FP32 pair records
  *   cell_div          cells per list cutoff and dimension: 0 = automatic (2 with build_variant 2/3), 1, 2
+ *   dump_spread_steps multi-GPU: steps over which the frame of pisb_download_owned_begin is sent (8; pieces leave after each
+ *                     step's decision has reached the host, pisb_download_end sends the rest; 1 = the whole frame at once)
  *   halo_mode         multi-GPU per-step ghost exchange: 0 = peer memory when it can be mapped, 1 = NCCL send/recv,
  *                     2 = peer memory or fail */
 PISB_API int pisb_set_option(pisb_t *h, const char *name, double value);
