@@ -2,23 +2,28 @@
 //
 // Device data layout (all arrays in CELL-SORTED slot order; `id[slot]` = original atom index):
 //   xt  : double4 {x, y, z, type-bits}   one 32-byte sector per atom: a neighbour gather costs
-//                                        exactly one sector and carries the type for the pair table
+//                                        exactly one sector and carries the type for the pair table;
+//                                        index -1 holds a NaN record (what a list pad gathers)
 //   v*, f*, g* : SoA doubles             streamed, never gathered (f = force at current x,
 //                                        g = force at previous x, swapped by the host every step)
 //   xb* : SoA doubles                    positions at the last list build (skin trigger)
 //   xf  : float4                          FP32 shadow of the wrapped position (+ type / ghost bits) for the pre-filter
 //   nbr : int32 [K_cap/4][n_pad][4]      FULL Verlet list, transposed in K-tiles of 4 (see nbr_at): the neighbours
-//                                        k..k+3 of atom i are one aligned int4, a warp reads 512 contiguous bytes
+//                                        k..k+3 of atom i are one aligned int4, a warp reads 512 contiguous bytes;
+//                                        the last tile of a row is closed with pads (sign bit set)
 //   cell_start : int32 [n_cells+2]       CSR of the cell-sorted order (x fastest, like cell_index)
 //
-// Kernel variants (pisb_set_option "force_variant" / "build_variant"; all give bit-identical results):
+// Kernel variants (pisb_set_option "force_variant" / "build_variant"): the same in/out decision for every pair in all of
+// them; v1 / v2 keep the reference's operation order per pair (bit-identical pair terms), the lean kernels shorten it.
 //   k_force (v1)      plain all-FP64 loop, round(); also the only path for triclinic / non-periodic boxes
 //   k_force_v2        FP32 pre-filter + shared-memory compaction queue + exact FP64 pair terms
-//   k_force_v3        DEFAULT: all-FP64 LEAN loop (short-way distance + FP64 guard band, Newton reciprocal, factored constants),
+//   k_force_v3        all-FP64 LEAN loop (short-way distance + FP64 guard band, Newton reciprocal, factored constants),
 //                     int4 index tiles prefetched, 4 x 256-bit gathers in flight, interior-warp shortcut, 64-register bound
-//   k_force_q         four lanes per atom, lane l takes entry l of every K-tile, integrator in the epilogue (auto below 75k atoms)
+//   k_force_vv        DEFAULT above 75k atoms: k_force_v3's loop + the velocity-Verlet kick and drift in the epilogue
+//   k_force_q         DEFAULT up to 75k atoms: four lanes per atom, lane l takes entry l of every K-tile, integrator in the epilogue
 //   k_force_split<S>  S lanes per atom taking whole K-tiles (round-1 small-system kernel, force_variant 6)
-//   k_build_list (v1) all-FP64 27-cell scan;  k_build_list_v2  DEFAULT: FP32 pre-filter over contiguous x-rows
+//   k_build_list (v1) all-FP64 27-cell scan;  k_build_list_v2  scalar FP32 pre-filter over contiguous x-rows;
+//   k_build_list_v3   DEFAULT: packed-FP32 pair records, bit-mask append, per-pair bands for multi-type tables
 #pragma once
 #include "pisb_device.cuh"
 
