@@ -204,11 +204,13 @@ def run(args):
         fused = tim.get("integrate", {"launches": 0})["launches"] < max(args.steps // 2, 1)   # unfused: one k_vv per step
         kernel = "k_force_vv<fused,brick>" if fused else "k_force_v3"
         roofline_fp64 = B.fp64_roofline(kernel, k_mean, k_in, n_own, f_ms, fused)
-        cal = B.force_calibration(kernel)[0]
+        cal, traffic, _, traffic_src = B.force_calibration(kernel)
         clocks = clk.summary()
         roofline = B.l1tex_roofline(kernel, k_mean, n_own, f_ms, clocks.get("sm_mhz"), cal)   # the binding resource (bench.py)
-        roofline.update({"share_of_step": tim["force"]["ms"] / ms_prof, "traffic": None, "note_rank": "rank 0's brick",
-                         "fp64_frac": roofline_fp64["frac"]})
+        # traffic: the static single-GPU ncu capture of the same kernel on a 4M-atom system (a brick adds ghost gathers, not streams)
+        roofline.update({"share_of_step": tim["force"]["ms"] / ms_prof, "traffic": traffic if n_own >= 3000000 else None,
+                         "traffic_source": (traffic_src + "; single-GPU form of the kernel, 4M atoms") if traffic_src and n_own >= 3000000 else None,
+                         "note_rank": "rank 0's brick", "fp64_frac": roofline_fp64["frac"]})
         achieved = ((192.0 if fused else 48.0) + 4.0 * k_mean) * n_own / (f_ms * 1e-3) / 1e9
         peak = float(peaks.get("hbm_gbs", 6650.0))
         cfg = B.workload_config(args, world)
