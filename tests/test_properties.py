@@ -71,7 +71,10 @@ def _brute_force(pos, L, types, table):
 
 
 box_edge = st.floats(min_value=27.0, max_value=40.0)
-common = dict(deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large])
+# derandomize: the same examples in every run (the driver's suite must not depend on a seed); widen locally with
+# HYPOTHESIS_PROFILE-style edits when hunting
+common = dict(deadline=None, derandomize=True, database=None,
+              suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large])
 
 
 @settings(max_examples=25, **common)
