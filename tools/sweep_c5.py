@@ -11,7 +11,8 @@ SIG, EPS = 3.405, 0.238
 ncell = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 T0 = float(sys.argv[3]) if len(sys.argv) > 3 else 43.0
-for rho in (1.0, 0.8, 0.6):
+RHOS = tuple(float(v) for v in sys.argv[4].split(",")) if len(sys.argv) > 4 else (1.0, 0.8, 0.6)
+for rho in RHOS:
     a = SIG * (4.0 / rho) ** (1.0 / 3.0)
     for rcs in (2.5, 3.0, 4.0, 5.0):
         rc, skin = rcs * SIG, 0.3 * SIG
