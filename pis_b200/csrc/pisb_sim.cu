@@ -136,6 +136,7 @@ struct pisb_handle {
     size_t ticket_cap = 0;  // words: 1 + one per group of 64 blocks (block_reduce_finalize)
     int *h_flags = nullptr;          // pinned; [FLAG_COUNT] = sequence number of k_publish_flags
     int pub_seq = 0;
+    int *h_pub = nullptr;            // pinned, 16 ints behind h_flags: one published record (k_publish_words) + its sequence word
     bool table_on_device = false;  // table_d holds the pair table (setup_filter)
     bool list_checked = false;     // ensure_list has confirmed the list for the CURRENT positions and the device's REBUILD flag is clear
                                    // (kept by the NVE / NVT batches, which end on a kick; cleared by uploads, host-buffer steps, NPT)
@@ -1377,6 +1378,7 @@ int enqueue_nvt_steps(pisb_t *h, double dt, int64_t cnt, int64_t total_steps, pi
 
 int do_step_nvt_multi(pisb_t *h, double dt, int64_t nsteps, pisb_nhc *chain, int64_t first_step, int64_t total_steps,
                       pisb_thermo *out, double *nhc_energy);
+int wait_published(pisb_t *h, volatile int *pub, int seq);
 
 int do_step_nvt(pisb_t *h, double dt, int64_t nsteps, pisb_nhc *chain, int64_t first_step, int64_t total_steps,
                 pisb_thermo *out, double *nhc_energy) {
@@ -1398,8 +1400,12 @@ int do_step_nvt(pisb_t *h, double dt, int64_t nsteps, pisb_nhc *chain, int64_t f
         k_observe<<<nblk(h->n, TPB), TPB, 0, h->stream>>>(h->n, h->xt.p, h->v[0].p, h->v[1].p, h->v[2].p, h->f[0].p, h->f[1].p,
                                                           h->f[2].p, h->mass_d.p, h->partials.p, h->ticket, ke0);
         TRY(check_launch(h, "k_observe"));
-        CUDA_TRY(h, cudaMemcpyAsync(h->h_thermo, ke0, sizeof(pisb_thermo), cudaMemcpyDeviceToHost, h->stream));
-        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        // the record reaches the host through a publish kernel, not a copy: a 32-byte device-to-host copy would queue behind
+        // an asynchronous dump frame on the copy engine and start every batch of a dumping NVT run late (see ensure_list)
+        const int seq = ++h->pub_seq, words = (int)(sizeof(pisb_thermo) / sizeof(int));
+        k_publish_words<<<1, 32, 0, h->stream>>>(reinterpret_cast<const int *>(ke0), h->h_pub, words, seq);
+        TRY(wait_published(h, h->h_pub + words, seq));
+        std::memcpy(&h->h_thermo[0], h->h_pub, sizeof(pisb_thermo));
     }
     NhcDev init{};
     init.c = *chain;
@@ -2327,10 +2333,11 @@ int pisb_create(int device, int n_types, const double *mass, const double *eps, 
         return bail(fail(h, PISB_ERR_CUDA, "cudaStreamCreate failed"));
     if (cudaMalloc((void **)&h->flags, sizeof(int) * FLAG_COUNT) != cudaSuccess ||
         cudaMalloc((void **)&h->ticket, sizeof(unsigned int) * 64) != cudaSuccess ||
-        cudaHostAlloc((void **)&h->h_flags, sizeof(int) * (FLAG_COUNT + 2), cudaHostAllocDefault) != cudaSuccess)
+        cudaHostAlloc((void **)&h->h_flags, sizeof(int) * (FLAG_COUNT + 2 + 16), cudaHostAllocDefault) != cudaSuccess)
         return bail(fail(h, PISB_ERR_CUDA, "allocating control words failed"));
     cudaMemsetAsync(h->flags, 0, sizeof(int) * FLAG_COUNT, h->stream);
-    std::memset(h->h_flags, 0, sizeof(int) * (FLAG_COUNT + 2));  // incl. the sequence word the host spins on (wait_published)
+    std::memset(h->h_flags, 0, sizeof(int) * (FLAG_COUNT + 2 + 16));  // incl. the sequence words the host spins on (wait_published)
+    h->h_pub = h->h_flags + FLAG_COUNT + 2;
     h->ticket_cap = 64;
     cudaMemsetAsync(h->ticket, 0, sizeof(unsigned int) * 64, h->stream);
     int rc = build_pair_table(h);
